@@ -1,0 +1,221 @@
+/*
+ * h264r.h -- C ABI of the B200 macroblock-reconstruction engine (libh264r.so).
+ *
+ * This is the drop-in boundary for the hot path of Terice/VideoDecoder.  The reference has no
+ * plugin/FFI interface: it interleaves entropy decoding and reconstruction per macroblock inside
+ * Slice::PraseSliceDataer (h264/slice.cpp:278-389).  The seam is cut where nothing downstream feeds
+ * back into entropy decoding (CABAC contexts read neighbour *syntax* only): the host keeps
+ * NAL/SPS/PPS/slice-header parsing, CABAC and MV / intra-mode / QP derivation, and hands this
+ * library flat per-picture syntax buffers.  Each entry point below names the reference call it
+ * replaces or is driven by.
+ *
+ * Conventions
+ *  - every function returns 0 (H264R_OK) or a negative H264R_E_* code; the library never calls
+ *    exit() (the reference does: h264/macroblock.cpp:656-661, h264/block.cpp:50-51);
+ *  - the caller owns every pointer it passes and may reuse it as soon as the call returns,
+ *    except buffers obtained from h264r_host_alloc(), which must stay valid until the next
+ *    h264r_flush()/h264r_sync() (they are read by an asynchronous copy);
+ *  - a context is bound to one CUDA device and must be used from one host thread at a time
+ *    (the reference is single-threaded); different contexts are independent;
+ *  - there is NO CPU fallback: if no CUDA device is usable h264r_create() fails.
+ *
+ * Plain C, no CUDA or torch types.
+ */
+#ifndef H264R_H_
+#define H264R_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define H264R_ABI_VERSION 1
+
+/* ---- status codes ---------------------------------------------------------------------- */
+#define H264R_OK            0
+#define H264R_E_INVAL      -1   /* bad argument                                              */
+#define H264R_E_CUDA       -2   /* CUDA runtime / driver error (see h264r_last_error)         */
+#define H264R_E_NOMEM      -3   /* device or pinned-host allocation failed                    */
+#define H264R_E_STATE      -4   /* call sequence violated (e.g. submit without frame_begin)   */
+#define H264R_E_NODEVICE   -5   /* no usable CUDA device: the engine has no CPU path          */
+#define H264R_E_CAPACITY   -6   /* more pending pictures / frames than the context was sized for */
+
+/* ---- context flags (h264r_create) ---------------------------------------------------------
+ * H264R_REF_COMPAT reproduces, bit for bit, the reference decoder's deviations from the
+ * standard on the path it implements:
+ *   D1 chroma DC "transform" = c[1][1]*[[1,-1],[-1,1]]          (h264/matrix.cpp:150-171 via h264/residual.cpp:214)
+ *   D3 no Clip1 after pred+residual; planes are the low 8 bits  (h264/macroblock.cpp:1467-1481, h264/picture.cpp:396-409)
+ *   D4 no chroma prediction of any kind: U/V = residual         (h264/macroblock.cpp:1477-1480)
+ *   D5 Intra16x16 DC, top-only: sums column 15 of the MB above  (h264/macroblock.cpp:1410-1411)
+ *   D6/D7 quarter-pel tap coordinates                           (h264/staticcharts.h:1505, h264/macroblock.cpp:843-846)
+ *   D8 source offset of 4x4 sub-partitions 2,3                  (h264/macroblock.cpp:786-789)
+ *   no deblocking filter, 4x4 transform only.
+ * (D2, QPc = max(QPY'-2,0), is host-side: the caller passes qp_cb/qp_cr per macroblock.)
+ * Without the flag the engine follows ITU-T H.264 (03/2014): Clip1, 2x2 Hadamard, chroma
+ * intra prediction and MC, standard interpolation, 8x8 transform, Intra8x8, deblocking.
+ */
+#define H264R_REF_COMPAT   0x1u
+
+/* ---- macroblock classes (h264r_mb_hdr.mb_class) --------------------------------------------
+ * Collapsed from the reference's MbTypeName (h264/enums.h:13-73): the Intra16x16 mode/cbp
+ * variants I_16x16_<mode>_<cbpC>_<cbpL> travel in i16_mode / cbp; P_Skip is P_16x16 with zero
+ * coefficients (macroblock::Init0, h264/macroblock.cpp:81-142). */
+#define H264R_MB_I4x4      0
+#define H264R_MB_I8x8      1
+#define H264R_MB_I16x16    2
+#define H264R_MB_P16x16    4
+#define H264R_MB_P16x8     5
+#define H264R_MB_P8x16     6
+#define H264R_MB_P8x8      7
+
+/* h264r_mb_hdr.flags */
+#define H264R_AVAIL_A      0x01u  /* left MB usable for intra prediction  (macroblock::is_avaiable, h264/macroblock.cpp:1446) */
+#define H264R_AVAIL_B      0x02u  /* MB above                                                    */
+#define H264R_AVAIL_C      0x04u  /* MB above-right                                              */
+#define H264R_AVAIL_D      0x08u  /* MB above-left                                               */
+#define H264R_T8x8         0x10u  /* transform_size_8x8_flag                                     */
+#define H264R_SKIP         0x20u  /* informational: P_Skip                                       */
+
+/* sub_mb_type codes (2 bits per 8x8 quadrant, quadrant q in bits 2q..2q+1), P_8x8 only;
+ * same numbering as the reference's SubMbTypeName P_L0_* (h264/enums.h:89-93). */
+#define H264R_SUB_8x8      0
+#define H264R_SUB_8x4      1
+#define H264R_SUB_4x8      2
+#define H264R_SUB_4x4      3
+
+/* One record per macroblock, raster order within the picture.  16 bytes. */
+typedef struct h264r_mb_hdr {
+    uint8_t mb_class;      /* H264R_MB_*                                                       */
+    uint8_t flags;         /* H264R_AVAIL_* | H264R_T8x8 | H264R_SKIP                          */
+    uint8_t qp_y;          /* QP'Y used for luma dequantisation and deblocking (macroblock::QPY_, h264/macroblock.cpp:485) */
+    uint8_t qp_cb;         /* QP'C for Cb (reference: macroblock::QPC_, h264/macroblock.cpp:487-488) */
+    uint8_t qp_cr;         /* QP'C for Cr                                                      */
+    uint8_t cbp;           /* bits 0-3 CodedBlockPatternLuma, bits 4-5 CodedBlockPatternChroma */
+    uint8_t intra_modes;   /* bits 0-1 Intra16x16PredMode, bits 2-3 intra_chroma_pred_mode     */
+    uint8_t sub_mb_type;   /* 4 x 2 bits, H264R_SUB_*                                          */
+    union {
+        uint8_t pred4x4[8];   /* I4x4: Intra4x4PredMode[luma4x4BlkIdx], 4 bits each, even idx in the low nibble;
+                                 I8x8: Intra8x8PredMode[0..3] in pred4x4[0..1] the same way     */
+        int8_t  ref_idx[8];   /* P: ref_idx_l0 per 8x8 quadrant in [0..3] (index into ref_list0) */
+    } u;
+} h264r_mb_hdr;
+
+/* Motion vectors: int16 (x, y) in quarter-sample units, one pair per 4x4 luma block in RASTER
+ * order inside the macroblock (block b = 4*(y/4) + x/4), 64 bytes per MB; the final vectors
+ * mv_l0 = mvp + mvd as computed by picture::get_MvNeighbour + macroblock::Parse
+ * (h264/picture.cpp:280-394, h264/macroblock.cpp:391-398).  P pictures only.
+ *
+ * Coefficients: 384 int16 levels per MB (768 bytes) = 24 blocks x 16:
+ *   blocks 0..15  luma, luma4x4BlkIdx order as parsed (h264/residual.cpp:39-47),
+ *   blocks 16..19 Cb, 20..23 Cr, chroma4x4BlkIdx (raster 2x2) order.
+ * Inside a block the 16 levels are in raster (row-major) position, i.e. the host has already
+ * applied the inverse zig-zag scan (Inverse4x4Scan, h264/residual.cpp:136-168).  Intra16x16 luma
+ * DC levels and chroma DC levels are stored, before any Hadamard transform, in slot 0 of the
+ * block they belong to (luma: DC matrix element (r,c) goes to the block at raster position (r,c);
+ * chroma: DC level i goes to chroma block i).  With H264R_T8x8 the four blocks of an 8x8
+ * quadrant hold the 64 levels of that 8x8 transform block in raster 8x8 order.
+ */
+#define H264R_COEFF_PER_MB 384
+#define H264R_MV_PER_MB    32    /* int16 values: 16 blocks x (x,y) */
+
+#define H264R_SLICE_P 0          /* numbering of the reference's Slicetype (h264/enums.h:4-10) */
+#define H264R_SLICE_I 2
+
+#define H264R_MAX_REFS 16
+
+/* Per-picture parameters: what NAL::decode_PIC (h264/NAL.cpp:185-316) knows after the slice
+ * header and reference-list construction. */
+typedef struct h264r_pic_params {
+    int32_t  slice_type;                      /* H264R_SLICE_I / H264R_SLICE_P                       */
+    int32_t  num_ref_idx_l0;                  /* entries used in ref_list0                          */
+    int32_t  ref_list0[H264R_MAX_REFS];       /* frame ids (Decoder::list_Ref0, h264/Decoder.h:39)   */
+    /* explicit weighted prediction (Weight_CoefficWeight, h264/macroblock.cpp:524-577)              */
+    int32_t  weighted_pred;                   /* pps weighted_pred_flag                             */
+    int32_t  luma_log2_weight_denom;
+    int32_t  chroma_log2_weight_denom;
+    int16_t  luma_weight[H264R_MAX_REFS], luma_offset[H264R_MAX_REFS];
+    int16_t  chroma_weight[H264R_MAX_REFS][2], chroma_offset[H264R_MAX_REFS][2];
+    /* in-loop deblocking (slice header fields parsed at h264/slice.cpp:247-256; the reference has
+     * no filter, so these are ignored under H264R_REF_COMPAT)                                      */
+    int32_t  disable_deblocking_filter_idc;   /* 1 = off                                            */
+    int32_t  slice_alpha_c0_offset_div2;
+    int32_t  slice_beta_offset_div2;
+} h264r_pic_params;
+
+typedef struct h264r_ctx h264r_ctx;
+
+/* Creates a context on CUDA device `device` for pictures of w_mbs x h_mbs macroblocks.
+ * max_frames  = size of the device frame pool (decoded + reference pictures alive at once);
+ * max_pending = pictures that may be begun/submitted between two flushes (their syntax buffers
+ *               stay resident in HBM until the flush executes).
+ * Replaces: the per-picture `new picture(...)` + per-MB `new macroblock` heap graph
+ * (h264/NAL.cpp:194, h264/slice.cpp:295) with a planar device frame pool. */
+int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs,
+                 int max_frames, int max_pending, uint32_t flags);
+void h264r_destroy(h264r_ctx* ctx);
+
+/* Pinned host memory for syntax buffers (so submit can DMA straight from the parser's output). */
+void* h264r_host_alloc(h264r_ctx* ctx, size_t bytes);
+void  h264r_host_free(h264r_ctx* ctx, void* p);
+
+/* Picture bracket.  frame_id names a slot of the frame pool (0 <= frame_id < max_frames) and is
+ * what ref_list0 entries of later pictures refer to.
+ * Driven by: NAL::decode_PIC after Slice::PraseSliceHeader and Decoder::init_RefPicList /
+ * opra_RefModfication (h264/NAL.cpp:204-224). */
+int h264r_frame_begin(h264r_ctx* ctx, int frame_id, const h264r_pic_params* pp);
+
+/* Syntax of macroblocks [first_mb, first_mb + n_mbs) of the picture begun last, raster order.
+ * mv may be NULL for I pictures.  May be called several times per picture (chunked / per slice).
+ * Driven by: the macroblock loop of Slice::PraseSliceDataer (h264/slice.cpp:292-386); carries what
+ * macroblock::Parse / Init0 and residual::Parse produced (h264/macroblock.cpp:143-475, 81-142,
+ * h264/residual.cpp:21-129). */
+int h264r_submit_mbs(h264r_ctx* ctx, int frame_id, int first_mb, int n_mbs,
+                     const h264r_mb_hdr* hdr, const int16_t* mv, const int16_t* coeff);
+
+/* Marks the picture complete and queues its reconstruction.  Asynchronous; work is issued to the
+ * GPU at the next h264r_flush().  Replaces: residual::Decode + macroblock::Calc for every MB of the
+ * picture (h264/residual.cpp:184-201, h264/macroblock.cpp:18-47). */
+int h264r_frame_end(h264r_ctx* ctx, int frame_id);
+
+/* Issues all queued pictures.  Pictures whose references are complete (or queued earlier) are
+ * grouped into dependency waves; every wave is reconstructed by batched kernel launches, so
+ * independent GOPs / streams submitted together fill the GPU. */
+int h264r_flush(h264r_ctx* ctx);
+/* flush + wait for the device. */
+int h264r_sync(h264r_ctx* ctx);
+
+/* Reads back the reconstructed planes of frame_id (flushes and waits as needed).  Strides in
+ * bytes.  Replaces: picture::get_SampleXY (h264/picture.cpp:396-409), the reference's only sample
+ * accessor (used by its ASCII printer, h264/picture.cpp:53-76, and by inter prediction). */
+int h264r_read_planes(h264r_ctx* ctx, int frame_id, uint8_t* y, int y_stride,
+                      uint8_t* u, uint8_t* v, int c_stride);
+
+/* 16-byte position-dependent checksum of the three planes, computed on the device (kernel K5);
+ * see DESIGN.md for the definition.  Used to compare GOP-sharded runs across GPUs without
+ * moving pictures. */
+int h264r_frame_digest(h264r_ctx* ctx, int frame_id, uint8_t out[16]);
+/* Digests of many frames with one device->host copy. */
+int h264r_frame_digests(h264r_ctx* ctx, const int* frame_ids, int n, uint8_t* out /* n*16 */);
+
+/* Counter of luma samples that left [0,255] before the store since the last call (reset on read).
+ * Under H264R_REF_COMPAT such samples mean the content relies on the reference's unclipped int
+ * storage (D3), which 8-bit planes cannot represent: parity tests assert it is zero. */
+int h264r_range_excursions(h264r_ctx* ctx, uint64_t* count);
+
+/* Frame slot may be reused.  Replaces: Decoder::ctrl_Memory / clear_DecodedPic
+ * (h264/Decoder.cpp:38-82).  Stream-ordered: safe to call while work that reads the slot is queued. */
+int h264r_release(h264r_ctx* ctx, int frame_id);
+
+/* Device-time of the kernels issued by the last h264r_flush(), in milliseconds (CUDA events on the
+ * context's stream), and the number of kernel launches it made. */
+int h264r_last_flush_stats(h264r_ctx* ctx, float* kernel_ms, int* launches);
+
+const char* h264r_last_error(h264r_ctx* ctx);
+int h264r_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* H264R_H_ */

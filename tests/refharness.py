@@ -1,0 +1,76 @@
+"""TEST INFRASTRUCTURE: runs the compiled reference decoder (oracle/_ref/h264ref_harness, built by
+oracle/Makefile from the sources under /root/reference/h264 plus three shims) on a synthesized
+stream and parses what it dumps.  Only tests/, smoke() and bench.py's reference legs use this."""
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "h264ref_harness")
+
+HDR_INTS = 25
+MB_REC_INTS = 34 + 32 + 256 + 64 + 64 + 256
+
+
+def have_harness():
+    return os.path.exists(HARNESS)
+
+
+def run_reference(stream, queue, level=2, keep=None):
+    """Returns (pictures, stats).  pictures[i] = dict(y,u,v uint8 planes, raw int32 luma,
+    mb = dict of per-MB arrays (level 2), ref_list = decode indices of list_Ref0)."""
+    d = keep or tempfile.mkdtemp(prefix="h264ref_")
+    sp, qp, dp = (os.path.join(d, n) for n in ("s.264", "q.bin", "dump.bin"))
+    with open(sp, "wb") as f:
+        f.write(stream)
+    np.asarray(queue, dtype=np.int32).tofile(qp)
+    r = subprocess.run([HARNESS, sp, qp, dp if level >= 0 else "-", str(max(level, 0))],
+                       stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("reference harness failed (%d): %s" % (r.returncode, r.stderr[-2000:]))
+    stats = json.loads(r.stderr.strip().splitlines()[-1])
+    pics = parse_dump(dp) if level >= 0 else []
+    if keep is None:
+        for p in (sp, qp, dp):
+            if os.path.exists(p):
+                os.remove(p)
+        os.rmdir(d)
+    return pics, stats
+
+
+def parse_dump(path):
+    data = np.fromfile(path, dtype=np.uint8)
+    off = 0
+    pics = []
+    while off < data.size:
+        hdr = data[off:off + 4 * HDR_INTS].view(np.int32)
+        off += 4 * HDR_INTS
+        assert hdr[0] == 0x44363248, "bad dump magic"
+        wm, hm, level = int(hdr[2]), int(hdr[3]), int(hdr[6])
+        W, H = wm * 16, hm * 16
+        p = {"index": int(hdr[1]), "w_mbs": wm, "h_mbs": hm, "nal_type": int(hdr[4]), "poc": int(hdr[5]),
+             "dec_num": int(hdr[7]), "ref_list": [int(x) for x in hdr[9:9 + int(hdr[8])]]}
+        p["y"] = data[off:off + W * H].reshape(H, W).copy(); off += W * H
+        p["u"] = data[off:off + W * H // 4].reshape(H // 2, W // 2).copy(); off += W * H // 4
+        p["v"] = data[off:off + W * H // 4].reshape(H // 2, W // 2).copy(); off += W * H // 4
+        if level >= 1:
+            p["raw"] = data[off:off + 4 * W * H].view(np.int32).reshape(H, W).copy(); off += 4 * W * H
+        if level >= 2:
+            n = wm * hm
+            rec = data[off:off + 4 * n * MB_REC_INTS].view(np.int32).reshape(n, MB_REC_INTS); off += 4 * n * MB_REC_INTS
+            p["mb"] = {
+                "type": rec[:, 0].copy(), "premode": rec[:, 1].copy(), "qpy": rec[:, 2].copy(), "qpc": rec[:, 3].copy(),
+                "cbp_luma": rec[:, 4].copy(), "cbp_chroma": rec[:, 5].copy(), "chroma_mode": rec[:, 6].copy(),
+                "t8x8": rec[:, 7].copy(), "num_part": rec[:, 8].copy(), "skip": rec[:, 9].copy(),
+                "i4_modes": rec[:, 10:26].copy(), "sub_type": rec[:, 26:30].copy(), "ref_idx": rec[:, 30:34].copy(),
+                "mv": rec[:, 34:66].reshape(n, 4, 4, 2).copy(),
+                "res_y": rec[:, 66:322].reshape(n, 16, 16).copy(),
+                "res_u": rec[:, 322:386].reshape(n, 8, 8).copy(),
+                "res_v": rec[:, 386:450].reshape(n, 8, 8).copy(),
+                "pred_y": rec[:, 450:706].reshape(n, 16, 16).copy(),
+            }
+        pics.append(p)
+    return pics

@@ -6,7 +6,7 @@
  *
  * Pinning status:
  *   - with H264R_REF_COMPAT every function here is pinned against the compiled reference
- *     (oracle/_ref/h264ref_harness) by tests/test_oracle_vs_reference.py and the fixtures under
+ *     (oracle/_ref/h264ref_harness) by tests/test_oracle_vs_reference.py and by the fixtures under
  *     tests/golden/ that were produced by running that binary;
  *   - the spec-mode pieces the reference does not implement (Clip1, 2x2 chroma Hadamard, chroma
  *     intra prediction and MC, standard qpel taps, 8x8 transform, Intra8x8, deblocking) restate
@@ -26,7 +26,7 @@ typedef struct h264o_pic {
     int32_t  w_mbs, h_mbs;
     uint32_t flags;                 /* H264R_REF_COMPAT or 0 */
     uint8_t* y; uint8_t* u; uint8_t* v;   /* current planes, pitch w_mbs*16 / w_mbs*8 */
-    int32_t* raw_y;                 /* REF_COMPAT only: unclipped int luma, as the reference stores it (may be NULL in spec mode) */
+    int32_t* raw_y;                 /* optional: unclipped int luma, as the reference stores it (REF_COMPAT; may be NULL) */
     const h264r_mb_hdr* hdr;        /* [n_mbs] */
     const int16_t* mv;              /* [n_mbs][32] or NULL */
     const int16_t* coeff;           /* [n_mbs][384] */
@@ -34,7 +34,9 @@ typedef struct h264o_pic {
     const uint8_t* ref_y[H264R_MAX_REFS];  /* planes of ref_list0[i] */
     const uint8_t* ref_u[H264R_MAX_REFS];
     const uint8_t* ref_v[H264R_MAX_REFS];
+    int32_t  ref_id[H264R_MAX_REFS];       /* identity of ref_list0[i] (deblocking compares pictures, not indices) */
     uint64_t excursions;            /* luma samples outside [0,255] before the store */
+    uint8_t* excursion_map;         /* optional [n_mbs]: 1 where the MB had an excursion */
 } h264o_pic;
 
 /* residual::Decode for one MB (h264/residual.cpp:184-201): out_y[256], out_u[64], out_v[64] (row-major). */

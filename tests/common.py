@@ -1,0 +1,75 @@
+"""TEST INFRASTRUCTURE shared by the test modules: turning (abstract syntax + what the compiled
+reference derived) into h264r buffers, sanitising content, running sequences through the oracle."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+from videodecoder_b200 import abi, pack, synth  # noqa: E402
+import oracle  # noqa: E402
+import refharness  # noqa: E402
+
+
+def buffers_from_dump(seq, pic, mbs, dpic):
+    """h264r buffers of one picture from its abstract syntax plus the values the reference's host
+    side derived (final MVs, Intra4x4PredMode, QPs: macroblock::Parse, h264/macroblock.cpp:143-475)."""
+    m = dpic["mb"]
+    n = mbs.shape[0]
+    hdr = pack.pack_headers(seq.w_mbs, seq.h_mbs, mbs, m["qpy"], m["qpc"], i4_modes=m["i4_modes"], part_ref=m["ref_idx"])
+    coeff = pack.pack_coeff(mbs)
+    is_p = pic.slice_type == synth.SLICE_P
+    mv = pack.pack_mvs(mbs, m["mv"]) if is_p else None
+    pp = abi.default_pic_params(abi.SLICE_P if is_p else abi.SLICE_I, ref_list=dpic["ref_list"] if is_p else ())
+    if is_p and seq.weighted_pred_flag:
+        pp.weighted_pred = 1
+        pp.luma_log2_weight_denom = pic.luma_log2_weight_denom
+        for i in range(pic.num_ref_idx_l0_active_minus1 + 1):
+            if pic.luma_weight_flag[i]:
+                pp.luma_weight[i], pp.luma_offset[i] = pic.luma_weight[i], pic.luma_offset[i]
+            else:
+                pp.luma_weight[i], pp.luma_offset[i] = 1 << pic.luma_log2_weight_denom, 0
+    return pp, hdr, mv, coeff
+
+
+def excursion_mbs(dpic):
+    """addresses of MBs whose reference int samples left [0,255]."""
+    wm, hm = dpic["w_mbs"], dpic["h_mbs"]
+    r = dpic["raw"].reshape(hm, 16, wm, 16)
+    bad = (r.min(axis=(1, 3)) < 0) | (r.max(axis=(1, 3)) > 255)
+    return np.flatnonzero(bad.reshape(-1))
+
+
+def sanitize_with_reference(seq, pics, max_iter=40):
+    """Zeroes the residual of macroblocks that make the reference's samples leave [0,255] until the
+    whole sequence is clean (content restriction that removes the no-Clip1 deviation D3).
+    Returns (stream, queue, dump)."""
+    for it in range(max_iter):
+        stream, queue = synth.serialize_stream(seq, pics)
+        dump, _ = refharness.run_reference(stream, queue, level=2)
+        dirty = False
+        for (pic, mbs), d in zip(pics, dump):
+            bad = excursion_mbs(d)
+            if bad.size:
+                synth.zero_residual(mbs, bad)
+                dirty = True
+                break       # later pictures depend on this one: fix in decode order
+        if not dirty:
+            return stream, queue, dump
+    raise RuntimeError("content did not converge to the [0,255] range")
+
+
+def oracle_sequence(seq, pics, dump, flags=abi.REF_COMPAT):
+    """Runs a whole sequence through the oracle using buffers derived from `dump`.
+    Returns list of oracle outputs (dict y,u,v,...)."""
+    out = []
+    for (pic, mbs), d in zip(pics, dump):
+        pp, hdr, mv, coeff = buffers_from_dump(seq, pic, mbs, d)
+        refs = [(out[i]["y"], out[i]["u"], out[i]["v"]) for i in d["ref_list"]] if pic.slice_type == synth.SLICE_P else []
+        o = oracle.recon_picture(seq.w_mbs, seq.h_mbs, flags, pp, hdr, mv, coeff, refs=refs, want_raw=True)
+        out.append(o)
+    return out

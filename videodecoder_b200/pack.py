@@ -1,0 +1,112 @@
+"""Host-side packing of macroblock syntax into the flat buffers of include/h264r.h.
+
+This is the Python twin of what the C++ host parser emits at the end of
+Slice::PraseSliceDataer (reference h264/slice.cpp:278-389): coefficient levels leave scan order
+(Inverse4x4Scan, reference h264/residual.cpp:136-168) and land block-major; motion vectors are
+expanded to one per 4x4 block; prediction modes and QPs go into the 16-byte header records.
+"""
+import numpy as np
+
+from . import abi
+from . import synth
+
+# scan index -> raster position inside a 4x4 block (reference h264/residual.cpp:136-141)
+ZZ = np.array([0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15])
+BLK_RASTER = synth.BLK_RASTER
+
+
+def pack_coeff(mbs):
+    """(n, 384) int16 from abstract syntax records (synth.MB_DTYPE)."""
+    n = mbs.shape[0]
+    out = np.zeros((n, 24, 16), dtype=np.int16)
+    i16 = mbs["kind"] == synth.I16x16
+    # 4x4 luma blocks: all 16 levels
+    tmp = np.zeros((n, 16, 16), dtype=np.int16)
+    tmp[:, :, ZZ] = mbs["luma"]
+    out[~i16, :16] = tmp[~i16]
+    # Intra16x16: 15 AC levels behind the DC slot, DC matrix element (r,c) -> block at raster (r,c)
+    tmp = np.zeros((n, 16, 16), dtype=np.int16)
+    tmp[:, :, ZZ[1:]] = mbs["luma"][:, :, :15]
+    tmp[:, BLK_RASTER[ZZ], 0] = mbs["luma_dc"]
+    out[i16, :16] = tmp[i16]
+    ch = np.zeros((n, 2, 4, 16), dtype=np.int16)
+    ch[:, :, :, ZZ[1:]] = mbs["chroma_ac"][:, :, :, :15]
+    ch[:, :, :, 0] = mbs["chroma_dc"]
+    out[:, 16:] = ch.reshape(n, 8, 16)
+    return out.reshape(n, 384)
+
+
+_CLASS = {synth.I4x4: abi.MB_I4x4, synth.I16x16: abi.MB_I16x16, synth.P16x16: abi.MB_P16x16,
+          synth.P16x8: abi.MB_P16x8, synth.P8x16: abi.MB_P8x16, synth.P8x8: abi.MB_P8x8,
+          synth.PSKIP: abi.MB_P16x16}
+
+
+def expand_mv(kind, sub_type, part_mv):
+    """part_mv[part][sub] = (x, y) -> 16 raster 4x4-block vectors (16, 2)."""
+    out = np.zeros((16, 2), dtype=np.int16)
+    for ras in range(16):
+        bx, by = ras % 4, ras // 4
+        q = (by >> 1) * 2 + (bx >> 1)
+        if kind in (synth.P16x16, synth.PSKIP):
+            part, sub = 0, 0
+        elif kind == synth.P16x8:
+            part, sub = by >> 1, 0
+        elif kind == synth.P8x16:
+            part, sub = bx >> 1, 0
+        else:
+            part = q
+            st = sub_type[q]
+            sub = {abi.SUB_8x8: 0, abi.SUB_8x4: by & 1, abi.SUB_4x8: bx & 1, abi.SUB_4x4: (by & 1) * 2 + (bx & 1)}[int(st)]
+        out[ras] = part_mv[part][sub]
+    return out
+
+
+def expand_ref(kind, part_ref):
+    """ref_idx per 8x8 quadrant."""
+    if kind in (synth.P16x16, synth.PSKIP):
+        return [part_ref[0]] * 4
+    if kind == synth.P16x8:
+        return [part_ref[0], part_ref[0], part_ref[1], part_ref[1]]
+    if kind == synth.P8x16:
+        return [part_ref[0], part_ref[1], part_ref[0], part_ref[1]]
+    return list(part_ref[:4])
+
+
+def pack_headers(w_mbs, h_mbs, mbs, qp_y, qp_c, i4_modes=None, part_ref=None):
+    """Header records.  qp_y / qp_c: per-MB QP'Y and QP'C (both chroma planes use qp_c);
+    i4_modes: (n,16) final Intra4x4PredMode per luma4x4BlkIdx; part_ref: (n,4) ref_idx_l0 per partition."""
+    n = mbs.shape[0]
+    hdr = np.zeros(n, dtype=abi.MB_HDR_DTYPE)
+    hdr["flags"] = abi.avail_flags(w_mbs, h_mbs)
+    hdr["qp_y"] = qp_y
+    hdr["qp_cb"] = qp_c
+    hdr["qp_cr"] = qp_c
+    for a in range(n):
+        k = int(mbs["kind"][a])
+        hdr["mb_class"][a] = _CLASS[k]
+        hdr["cbp"][a] = int(mbs["cbp_luma"][a]) | (int(mbs["cbp_chroma"][a]) << 4)
+        if k == synth.PSKIP:
+            hdr["flags"][a] |= abi.SKIP
+        if k in (synth.I4x4, synth.I16x16):
+            hdr["intra_modes"][a] = (int(mbs["i16_mode"][a]) & 3) | ((int(mbs["chroma_mode"][a]) & 3) << 2)
+            if k == synth.I4x4:
+                m = i4_modes[a]
+                for j in range(8):
+                    hdr["u"][a][j] = (int(m[2 * j]) & 15) | ((int(m[2 * j + 1]) & 15) << 4)
+        else:
+            st = mbs["sub_type"][a]
+            if k == synth.P8x8:
+                hdr["sub_mb_type"][a] = int(st[0]) | (int(st[1]) << 2) | (int(st[2]) << 4) | (int(st[3]) << 6)
+            hdr["u"][a][:4] = expand_ref(k, [int(x) for x in part_ref[a]])
+    return hdr
+
+
+def pack_mvs(mbs, part_mv):
+    """(n, 32) int16; part_mv: (n, 4, 4, 2) final vectors per partition / sub-partition."""
+    n = mbs.shape[0]
+    mv = np.zeros((n, 16, 2), dtype=np.int16)
+    for a in range(n):
+        k = int(mbs["kind"][a])
+        if k >= synth.P16x16:
+            mv[a] = expand_mv(k, mbs["sub_type"][a], part_mv[a])
+    return mv.reshape(n, 32)

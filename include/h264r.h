@@ -204,6 +204,16 @@ int h264r_frame_digests(h264r_ctx* ctx, const int* frame_ids, int n, uint8_t* ou
  * storage (D3), which 8-bit planes cannot represent: parity tests assert it is zero. */
 int h264r_range_excursions(h264r_ctx* ctx, uint64_t* count);
 
+/* Per-macroblock map of the same event for one frame: out[mb_addr] = 1 where a luma sample of that
+ * macroblock left [0,255].  Content generators use it to keep synthetic pictures in range. */
+int h264r_excursion_map(h264r_ctx* ctx, int frame_id, uint8_t* out /* w_mbs*h_mbs */);
+
+/* Kernel K1 on its own: dequantisation + inverse transforms of n_mbs macroblocks (any n_mbs, no
+ * picture structure needed).  out receives 384 int16 per macroblock: residual_Y 16x16 row-major,
+ * then residual_U 8x8, then residual_V 8x8, saturated to int16.  Host pointers; synchronous.
+ * Replaces: residual::Decode (h264/residual.cpp:184-201). */
+int h264r_residual_mbs(h264r_ctx* ctx, int n_mbs, const h264r_mb_hdr* hdr, const int16_t* coeff, int16_t* out);
+
 /* Frame slot may be reused.  Replaces: Decoder::ctrl_Memory / clear_DecodedPic
  * (h264/Decoder.cpp:38-82).  Stream-ordered: safe to call while work that reads the slot is queued. */
 int h264r_release(h264r_ctx* ctx, int frame_id);

@@ -73,3 +73,42 @@ def oracle_sequence(seq, pics, dump, flags=abi.REF_COMPAT):
         o = oracle.recon_picture(seq.w_mbs, seq.h_mbs, flags, pp, hdr, mv, coeff, refs=refs, want_raw=True)
         out.append(o)
     return out
+
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    """Fixture written by tests/golden/make_golden.py -> dict(w_mbs, h_mbs, pics=[dict(pp, hdr, mv, coeff, md5, y,u,v)])."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    out = {"w_mbs": int(z["w_mbs"]), "h_mbs": int(z["h_mbs"]), "pics": []}
+    for i in range(int(z["n_pics"])):
+        v = z["pp%d" % i]
+        st, nref, wp, ld = (int(x) for x in v[:4])
+        pp = abi.default_pic_params(st, ref_list=[int(x) for x in v[4:4 + nref]])
+        pp.weighted_pred, pp.luma_log2_weight_denom = wp, ld
+        for k in range(abi.MAX_REFS):
+            pp.luma_weight[k] = int(v[20 + k])
+            pp.luma_offset[k] = int(v[36 + k])
+        pic = {"pp": pp, "hdr": z["hdr%d" % i].copy().view(abi.MB_HDR_DTYPE).reshape(-1), "coeff": z["coeff%d" % i],
+               "mv": z["mv%d" % i] if ("mv%d" % i) in z.files else None, "md5": bytes(z["md5_%d" % i]).hex()}
+        if ("y%d" % i) in z.files:
+            pic["y"], pic["u"], pic["v"] = z["y%d" % i], z["u%d" % i], z["v%d" % i]
+        out["pics"].append(pic)
+    return out
+
+
+def planes_md5(y, u, v):
+    import hashlib
+    return hashlib.md5(np.ascontiguousarray(y).tobytes() + np.ascontiguousarray(u).tobytes() + np.ascontiguousarray(v).tobytes()).hexdigest()
+
+
+def run_sequence(recon, w_mbs, h_mbs, flags, pics):
+    """Runs pictures [(pp, hdr, mv, coeff)...] through `recon` (oracle.recon_picture or
+    emul.recon_picture), resolving ref_list0 frame ids as indices into the sequence."""
+    outs = []
+    for p in pics:
+        pp = p["pp"]
+        refs = [(outs[pp.ref_list0[i]]["y"], outs[pp.ref_list0[i]]["u"], outs[pp.ref_list0[i]]["v"]) for i in range(pp.num_ref_idx_l0)]
+        outs.append(recon(w_mbs, h_mbs, flags, pp, p["hdr"], p["mv"], p["coeff"], refs=refs))
+    return outs

@@ -1,0 +1,72 @@
+"""TEST INFRASTRUCTURE: builds and binds the host-side SIMT emulator of the kernel code
+(tests/emul/emul.cpp).  Lets the CPU suite check the kernels' arithmetic against the oracle."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from videodecoder_b200 import abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "emul", "emul.cpp")
+OUT = os.path.join(HERE, "emul", "_build", "libh264emul.so")
+DEPS = [SRC] + [os.path.join(ROOT, "videodecoder_b200", "csrc", "cuda", f) for f in ("h264r_core.cuh", "h264r_seq.cuh")] + [
+    os.path.join(ROOT, "include", "h264r.h")]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
+            os.makedirs(os.path.dirname(OUT), exist_ok=True)
+            subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                            "-fsanitize=undefined", "-fno-sanitize-recover=undefined", SRC, "-o", OUT], check=True)
+        _lib = ctypes.CDLL(OUT)
+        _lib.h264emul_recon_picture.restype = ctypes.c_ulonglong
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def residual(w_mbs, h_mbs, flags, hdr, coeff):
+    n = w_mbs * h_mbs
+    hdr = np.ascontiguousarray(hdr)
+    coeff = np.ascontiguousarray(coeff, dtype=np.int16)
+    out = np.zeros((n, 384), dtype=np.int16)
+    lib().h264emul_residual(w_mbs, h_mbs, ctypes.c_uint(flags), _ptr(hdr), _ptr(coeff), _ptr(out))
+    return (out[:, :256].reshape(n, 16, 16), out[:, 256:320].reshape(n, 8, 8), out[:, 320:].reshape(n, 8, 8))
+
+
+def recon_picture(w_mbs, h_mbs, flags, pp, hdr, mv, coeff, refs=()):
+    n = w_mbs * h_mbs
+    W, H = w_mbs * 16, h_mbs * 16
+    hdr = np.ascontiguousarray(hdr)
+    coeff = np.ascontiguousarray(coeff, dtype=np.int16)
+    mv = np.ascontiguousarray(mv, dtype=np.int16) if mv is not None else None
+    y = np.zeros((H, W), dtype=np.uint8)
+    u = np.zeros((H // 2, W // 2), dtype=np.uint8)
+    v = np.zeros((H // 2, W // 2), dtype=np.uint8)
+    emap = np.zeros(n, dtype=np.uint8)
+    arr = ctypes.c_void_p * abi.MAX_REFS
+    ry, ru, rv = arr(), arr(), arr()
+    keep = []
+    for i, planes in enumerate(refs):
+        planes = tuple(np.ascontiguousarray(x) for x in planes)
+        keep.append(planes)
+        ry[i], ru[i], rv[i] = (_ptr(x) for x in planes)
+    exc = lib().h264emul_recon_picture(w_mbs, h_mbs, ctypes.c_uint(flags), ctypes.byref(pp), _ptr(hdr), _ptr(mv), _ptr(coeff),
+                                       _ptr(y), _ptr(u), _ptr(v), ry, ru, rv, _ptr(emap))
+    return {"y": y, "u": u, "v": v, "excursions": int(exc), "excursion_map": emap}
+
+
+def digest(y, u, v):
+    out = (ctypes.c_uint32 * 4)()
+    y, u, v = (np.ascontiguousarray(x, dtype=np.uint8) for x in (y, u, v))
+    lib().h264emul_digest(_ptr(y), _ptr(u), _ptr(v), ctypes.c_int(y.shape[1]), ctypes.c_int(y.shape[0]), out)
+    return bytes(out)

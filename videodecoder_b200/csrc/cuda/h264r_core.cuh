@@ -1,0 +1,989 @@
+// h264r_core.cuh -- per-macroblock reconstruction "phases" shared by the CUDA kernels and by the
+// host-side SIMT emulator used in the CPU test-suite (tests/emul/emul.cpp).
+//
+// A macroblock is reconstructed by one warp.  The work is written as a sequence of phases; inside
+// a phase every lane works independently on the warp's shared working set (MbWork) and on global
+// memory, and phases are separated by __syncwarp().  Because a phase is an ordinary function of
+// (working set, lane) it also compiles for the host, where the emulator runs the 32 lanes one
+// after the other: the arithmetic of every kernel is therefore exercised by the CPU tests, the
+// GPU tests only add the parallel orchestration.
+//
+// Reference behaviour (Terice/VideoDecoder, paths relative to the reference root) is cited at each
+// function; REF_COMPAT (template parameter COMPAT) selects the reference's deviations from
+// ITU-T H.264 listed in include/h264r.h.
+#pragma once
+#include <stdint.h>
+#include "../../../include/h264r.h"
+
+#ifdef __CUDACC__
+#define HD __host__ __device__ __forceinline__
+#else
+#define HD inline
+struct int4 { int x, y, z, w; };
+struct uint4 { unsigned x, y, z, w; };
+struct uint2 { unsigned x, y; };
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define H264R_LDG(p) __ldg(p)          /* read-only for the lifetime of the kernel (syntax, reference frames) */
+#define H264R_LDCG(p) __ldcg(p)        /* written earlier in the same kernel by another warp: bypass L1 */
+#else
+#define H264R_LDG(p) (*(p))
+#define H264R_LDCG(p) (*(p))
+#endif
+
+namespace h264r {
+
+struct Geometry {
+    int w_mbs, h_mbs;
+    int pitch_y, pitch_c;      // bytes per row of the luma / chroma planes
+};
+
+// Everything a kernel needs to know about one picture of a wave (lives in device memory).
+struct PicDesc {
+    const h264r_mb_hdr* hdr;
+    const int16_t* mv;
+    const int16_t* coeff;
+    uint8_t* y; uint8_t* u; uint8_t* v;
+    const uint8_t* ref_y[H264R_MAX_REFS];
+    const uint8_t* ref_u[H264R_MAX_REFS];
+    const uint8_t* ref_v[H264R_MAX_REFS];
+    int32_t ref_id[H264R_MAX_REFS];
+    int32_t slice_type;
+    int32_t weighted_pred, luma_log2_wd, chroma_log2_wd;
+    int16_t luma_weight[H264R_MAX_REFS], luma_offset[H264R_MAX_REFS];
+    int16_t chroma_weight[H264R_MAX_REFS][2], chroma_offset[H264R_MAX_REFS][2];
+    int32_t deblock_on, alpha_off, beta_off;     // offsets already multiplied by 2
+    uint8_t* excursion_map;    // [n_mbs] or null
+    uint32_t* digest;          // 4 words
+    int32_t frame_id;
+    int32_t pad_;
+};
+
+// Shared working set of one warp (one macroblock in flight).
+constexpr int TILE_P = 28;                // pitch of the intra luma tile
+struct alignas(16) MbWork {
+    int16_t coef[24][16];                 // coefficient levels of the MB, block-major
+    int16_t res[384];                     // residual: Y 16x16, then U 8x8, then V 8x8
+    uint8_t tile[17 * TILE_P];            // luma samples x=-1..23, y=-1..15 at tile[(y+1)*TILE_P + x+1]
+    uint8_t ctile[2][9 * 12];             // chroma samples x=-1..7, y=-1..7 at [(y+1)*12 + x+1]
+    uint8_t e8[28];                       // Intra8x8 filtered edge
+    uint8_t dtile[24 * 24];               // deblocking luma tile x,y=-4..15 at [(y+4)*24 + x+4]
+    uint8_t dctile[2][12 * 12];           // deblocking chroma tiles x,y=-2..7 at [(y+2)*12 + x+2]
+    uint8_t bs[32];                       // boundary strengths [dir][edge][k]
+    uint32_t excursions;
+};
+
+HD int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+HD int clip1(int v) { return clip3(0, 255, v); }
+HD int iabs(int v) { return v < 0 ? -v : v; }
+HD int blk_raster(int i) { return (i & 1) | ((i & 4) >> 1) | ((i & 2) << 1) | (i & 8); }   // luma4x4BlkIdx <-> raster (involution)
+HD bool is_intra(int mb_class) { return mb_class <= H264R_MB_I16x16; }
+
+// ------------------------------------------------------------------------------------------------
+// K1: dequantisation + inverse transforms
+// ------------------------------------------------------------------------------------------------
+// 16*normAdjust4x4(m,i,j) (reference LevelScale4x4, h264/residual.cpp:170-183)
+HD int level_scale4(int m, int i, int j)
+{
+    // rows: positions (even,even) / (odd,odd) / other
+    const int v0[6] = {10, 11, 13, 14, 16, 18}, v1[6] = {16, 18, 20, 23, 25, 29}, v2[6] = {13, 14, 16, 18, 20, 23};
+    int oi = i & 1, oj = j & 1;
+    int v = (!oi && !oj) ? v0[m] : ((oi && oj) ? v1[m] : v2[m]);
+    return 16 * v;
+}
+
+// One 4x4 block: scaling + 2-D inverse integer transform + rounding
+// (reference residual::ScalingAndTransform_Residual4x4Blocks, h264/residual.cpp:367-434).
+HD void scale_idct4(const int c[16], int qp, bool dc_bypass, int r[16])
+{
+    int d[16];
+    int m = qp % 6, s = qp / 6;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        int ls = level_scale4(m, k >> 2, k & 3);
+        d[k] = (s >= 4) ? (c[k] * ls) * (1 << (s - 4)) : ((c[k] * ls + (1 << (3 - s))) >> (4 - s));
+    }
+    if (dc_bypass) d[0] = c[0];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int e0 = d[i * 4] + d[i * 4 + 2], e1 = d[i * 4] - d[i * 4 + 2];
+        int e2 = (d[i * 4 + 1] >> 1) - d[i * 4 + 3], e3 = d[i * 4 + 1] + (d[i * 4 + 3] >> 1);
+        d[i * 4] = e0 + e3; d[i * 4 + 1] = e1 + e2; d[i * 4 + 2] = e1 - e2; d[i * 4 + 3] = e0 - e3;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int g0 = d[j] + d[8 + j], g1 = d[j] - d[8 + j];
+        int g2 = (d[4 + j] >> 1) - d[12 + j], g3 = d[4 + j] + (d[12 + j] >> 1);
+        r[j] = (g0 + g3 + 32) >> 6; r[4 + j] = (g1 + g2 + 32) >> 6;
+        r[8 + j] = (g1 - g2 + 32) >> 6; r[12 + j] = (g0 - g3 + 32) >> 6;
+    }
+}
+
+// 8x8: ITU-T H.264 8.5.13 with flat scaling lists (no reference counterpart).
+HD int level_scale8(int m, int i, int j)
+{
+    const uint8_t v[6][6] = {{20, 18, 32, 19, 25, 24}, {22, 19, 35, 21, 28, 26}, {26, 23, 42, 24, 33, 31},
+                             {28, 25, 45, 26, 35, 33}, {32, 28, 51, 30, 40, 38}, {36, 32, 58, 34, 46, 43}};
+    int k;
+    if ((i & 3) == 0 && (j & 3) == 0) k = 0;
+    else if ((i & 1) && (j & 1)) k = 1;
+    else if ((i & 3) == 2 && (j & 3) == 2) k = 2;
+    else if (((i & 3) == 0 && (j & 1)) || ((i & 1) && (j & 3) == 0)) k = 3;
+    else if (((i & 3) == 0 && (j & 3) == 2) || ((i & 3) == 2 && (j & 3) == 0)) k = 4;
+    else k = 5;
+    return 16 * v[m][k];
+}
+HD void idct8_1d(int x[8])
+{
+    int a0 = x[0] + x[4], a4 = x[0] - x[4], a2 = (x[2] >> 1) - x[6], a6 = x[2] + (x[6] >> 1);
+    int a1 = -x[3] + x[5] - x[7] - (x[7] >> 1), a3 = x[1] + x[7] - x[3] - (x[3] >> 1);
+    int a5 = -x[1] + x[7] + x[5] + (x[5] >> 1), a7 = x[3] + x[5] + x[1] + (x[1] >> 1);
+    int b0 = a0 + a6, b2 = a4 + a2, b4 = a4 - a2, b6 = a0 - a6;
+    int b1 = a1 + (a7 >> 2), b7 = a7 - (a1 >> 2), b3 = a3 + (a5 >> 2), b5 = (a3 >> 2) - a5;
+    x[0] = b0 + b7; x[1] = b2 + b5; x[2] = b4 + b3; x[3] = b6 + b1;
+    x[4] = b6 - b1; x[5] = b4 - b3; x[6] = b2 - b5; x[7] = b0 - b7;
+}
+
+HD int sat16(int v) { return clip3(-32768, 32767, v); }
+
+// Phase R0: lanes 0..23 copy their 4x4 block of levels (32 bytes, two 128-bit loads) into the working set.
+HD void phase_load_coeff(MbWork& w, const PicDesc& pd, int a, int lane)
+{
+    if (lane == 0) w.excursions = 0;
+    if (lane < 24) {
+        const int4* src = reinterpret_cast<const int4*>(pd.coeff + (size_t)a * H264R_COEFF_PER_MB) + lane * 2;
+        int4 v0 = H264R_LDG(src), v1 = H264R_LDG(src + 1);
+        int4* dst = reinterpret_cast<int4*>(&w.coef[lane][0]);
+        dst[0] = v0; dst[1] = v1;
+    }
+}
+
+// Phase R1: lane b < 24 produces the residual of block b (luma blocks 0..15 in luma4x4BlkIdx order,
+// 16..19 Cb, 20..23 Cr).  With transform_size_8x8_flag lanes 0..3 produce one 8x8 block each.
+// Reference: residual::Decode and its callees (h264/residual.cpp:184-365).
+template <bool COMPAT>
+HD void phase_residual(MbWork& w, const h264r_mb_hdr& h, int lane)
+{
+    if (lane >= 24) return;
+    int c[16], r[16];
+    if (lane < 16) {
+        if (!COMPAT && (h.flags & H264R_T8x8) && h.mb_class != H264R_MB_I16x16) {
+            if (lane >= 4) return;
+            int qp = h.qp_y, m = qp % 6, s = qp / 6;
+            const int16_t* src = &w.coef[lane * 4][0];       // 64 levels, raster 8x8
+            int row[8];
+            int t[64];
+            for (int i = 0; i < 8; i++) {
+                for (int j = 0; j < 8; j++) {
+                    int ls = level_scale8(m, i, j), v = src[i * 8 + j];
+                    row[j] = (s >= 6) ? (v * ls) * (1 << (s - 6)) : ((v * ls + (1 << (5 - s))) >> (6 - s));
+                }
+                idct8_1d(row);
+                for (int j = 0; j < 8; j++) t[i * 8 + j] = row[j];
+            }
+            for (int j = 0; j < 8; j++) {
+                for (int i = 0; i < 8; i++) row[i] = t[i * 8 + j];
+                idct8_1d(row);
+                for (int i = 0; i < 8; i++)
+                    w.res[((lane >> 1) * 8 + i) * 16 + (lane & 1) * 8 + j] = (int16_t)sat16((row[i] + 32) >> 6);
+            }
+            return;
+        }
+        int qp = h.qp_y;
+        for (int k = 0; k < 16; k++) c[k] = w.coef[lane][k];
+        bool i16 = h.mb_class == H264R_MB_I16x16;
+        int ras = blk_raster(lane);
+        if (i16) {
+            // Intra16x16 DC: 4x4 Hadamard of the 16 DC levels, element (i,j) for the block at raster
+            // (i,j) (reference residual::Decode_Intra16x16, h264/residual.cpp:286-319)
+            int i = ras >> 2, j = ras & 3, f = 0;
+            for (int k = 0; k < 4; k++) {
+                // T[i][k]: rows {1,1,1,1},{1,1,-1,-1},{1,-1,-1,1},{1,-1,1,-1}; bit (4i+k) of 0xA6C0 = minus
+                int tik = (0xA6C0 >> (i * 4 + k)) & 1 ? -1 : 1;
+                int t = 0;
+                for (int l = 0; l < 4; l++) {
+                    int tlj = (0xA6C0 >> (l * 4 + j)) & 1 ? -1 : 1;      // T[l][j]
+                    t += w.coef[blk_raster(k * 4 + l)][0] * tlj;
+                }
+                f += tik * t;
+            }
+            int ls = level_scale4(qp % 6, 0, 0), s = qp / 6;
+            c[0] = (s >= 6) ? (f * ls) * (1 << (s - 6)) : ((f * ls + (1 << (5 - s))) >> (6 - s));
+        }
+        scale_idct4(c, qp, i16, r);
+        int bx = ras & 3, by = ras >> 2;
+        for (int k = 0; k < 16; k++) w.res[(by * 4 + (k >> 2)) * 16 + bx * 4 + (k & 3)] = (int16_t)sat16(r[k]);
+    } else {
+        int plane = (lane - 16) >> 2, b = (lane - 16) & 3;
+        int qp = plane ? h.qp_cr : h.qp_cb;
+        for (int k = 0; k < 16; k++) c[k] = w.coef[lane][k];
+        int c0 = w.coef[16 + plane * 4][0], c1 = w.coef[17 + plane * 4][0];
+        int c2 = w.coef[18 + plane * 4][0], c3 = w.coef[19 + plane * 4][0];
+        int f;
+        if (COMPAT) {
+            // reference's non-accumulating matrix product: c[1][1]*[[1,-1],[-1,1]] (h264/matrix.cpp:150-171)
+            f = (b == 0 || b == 3) ? c3 : -c3;
+        } else {
+            f = c0 + ((b & 1) ? -c1 : c1) + ((b & 2) ? -c2 : c2) + ((b == 1 || b == 2) ? -c3 : c3);
+        }
+        c[0] = ((f * level_scale4(qp % 6, 0, 0)) * (1 << (qp / 6))) >> 5;
+        scale_idct4(c, qp, true, r);
+        for (int k = 0; k < 16; k++)
+            w.res[256 + plane * 64 + ((b >> 1) * 4 + (k >> 2)) * 8 + (b & 1) * 4 + (k & 3)] = (int16_t)sat16(r[k]);
+    }
+}
+
+// luma sample = pred + residual; counts samples that leave [0,255].
+// COMPAT: no Clip1, the plane keeps the low 8 bits (reference macroblock::ConstructPicture,
+// h264/macroblock.cpp:1467-1481, and picture::get_SampleXY, h264/picture.cpp:396-409).
+template <bool COMPAT>
+HD uint8_t recon_luma(int v, uint32_t& exc)
+{
+    if (v < 0 || v > 255) exc++;
+    return COMPAT ? (uint8_t)v : (uint8_t)clip1(v);
+}
+template <bool COMPAT>
+HD uint8_t recon_chroma(int v) { return COMPAT ? (uint8_t)v : (uint8_t)clip1(v); }
+
+// ------------------------------------------------------------------------------------------------
+// K3: inter prediction
+// ------------------------------------------------------------------------------------------------
+HD int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
+
+struct RefPlane {
+    const uint8_t* p; int pitch, w, h;
+    HD int at(int x, int y) const
+    {
+        // coordinate clamp of the reference (h264/macroblock.cpp:828-830) = spec 8.4.2.2.1 eq. 8-239
+        return H264R_LDG(p + (size_t)clip3(0, h - 1, y) * pitch + clip3(0, w - 1, x));
+    }
+};
+
+// One luma prediction sample (reference macroblock::Prediction_Inter_LumaSampleInterpolation,
+// h264/macroblock.cpp:816-902; COMPAT keeps its tap coordinates, deviations D6/D7).
+template <bool COMPAT>
+HD int luma_interp(const RefPlane& R, int xi, int yi, int xf, int yf)
+{
+#define S(dx, dy) R.at(xi + (dx), yi + (dy))
+    int G = S(0, 0);
+    if ((xf | yf) == 0) return G;
+    int Hh = S(1, 0), M = S(0, 1);
+    int b1 = tap6(S(-2, 0), S(-1, 0), G, Hh, S(2, 0), S(3, 0));
+    int h1 = tap6(S(0, -2), S(0, -1), G, M, S(0, 2), S(0, 3));
+    int b = clip1((b1 + 16) >> 5), h = clip1((h1 + 16) >> 5);
+    int sel = xf * 4 + yf;
+    if (sel == 1) return (G + h + 1) >> 1;
+    if (sel == 2) return h;
+    if (sel == 3) return (M + h + 1) >> 1;
+    if (sel == 4) return (G + b + 1) >> 1;
+    if (sel == 5) return (b + h + 1) >> 1;
+    if (sel == 8) return b;
+    if (sel == 12) return (Hh + b + 1) >> 1;
+    int N = S(1, 1);
+    int s1 = tap6(COMPAT ? S(-2, -1) : S(-2, 1), S(-1, 1), M, N, S(2, 1), S(3, 1));
+    int s = clip1((s1 + 16) >> 5);
+    if (sel == 7) return (h + s + 1) >> 1;
+    int m1 = tap6(S(1, -2), S(1, -1), Hh, N, S(1, 2), S(1, 3));
+    int m = clip1((m1 + 16) >> 5);
+    if (sel == 13) return (b + m + 1) >> 1;
+    if (sel == 15) return (m + s + 1) >> 1;
+    int aa = tap6(S(-2, -2), S(-1, -2), S(0, -2), S(1, -2), S(2, -2), S(3, -2));
+    int bb, gg, hh;
+    if (COMPAT) {
+        bb = tap6(S(-2, -2), S(-1, -2), S(0, -1), S(1, -1), S(2, -2), S(3, -2));
+        gg = tap6(S(-2, 2), S(-1, 2), S(0, 2), S(1, 2), S(2, -2), S(3, -2));
+        hh = tap6(S(-2, 3), S(-1, 3), S(0, 3), S(1, 3), S(2, -3), S(3, -3));
+    } else {
+        bb = tap6(S(-2, -1), S(-1, -1), S(0, -1), S(1, -1), S(2, -1), S(3, -1));
+        gg = tap6(S(-2, 2), S(-1, 2), S(0, 2), S(1, 2), S(2, 2), S(3, 2));
+        hh = tap6(S(-2, 3), S(-1, 3), S(0, 3), S(1, 3), S(2, 3), S(3, 3));
+    }
+#undef S
+    int j = clip1((tap6(aa, bb, b1, s1, gg, hh) + 512) >> 10);
+    if (sel == 6) return (h + j + 1) >> 1;
+    if (sel == 9) return (b + j + 1) >> 1;
+    if (sel == 10) return j;
+    if (sel == 11) return (j + s + 1) >> 1;
+    return (j + m + 1) >> 1;    // 14
+}
+
+HD int weight_pred(int v, int logwd, int wgt, int off)
+{
+    // reference macroblock::Weight_CoefficWeight, single list (h264/macroblock.cpp:544-553)
+    if (logwd >= 1) return clip1(((v * wgt + (1 << (logwd - 1))) >> logwd) + off);
+    return clip1(v * wgt + off);
+}
+
+// Phase P1: luma of an inter MB.  Lane -> 4x4 block (lane >> 1), rows 2*(lane & 1) .. +1.
+// Every sample is interpolated from its block's vector, which equals the reference's
+// per-partition loops (macroblock::Decode / Prediction_Inter, h264/macroblock.cpp:591-813); the
+// reference's source-row offset for 4x4 sub-partitions 2 and 3 (1 instead of 4, D8,
+// h264/macroblock.cpp:786-789) is applied under COMPAT.  Result goes to the luma tile.
+template <bool COMPAT>
+HD void phase_inter_luma(MbWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane)
+{
+    int ras = lane >> 1, bx = ras & 3, by = ras >> 2, q = (by >> 1) * 2 + (bx >> 1);
+    int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    const int16_t* mvp = pd.mv + (size_t)a * H264R_MV_PER_MB + ras * 2;
+    int mvx = H264R_LDG(mvp), mvy = H264R_LDG(mvp + 1);
+    int ri = h.u.ref_idx[q] & 15;
+    RefPlane R{pd.ref_y[ri], g.pitch_y, g.w_mbs * 16, g.h_mbs * 16};
+    int x0 = mbx * 16 + bx * 4, y0 = mby * 16 + by * 4;
+    int ys = y0;
+    if (COMPAT && h.mb_class == H264R_MB_P8x8 && ((h.sub_mb_type >> (2 * q)) & 3) == H264R_SUB_4x4 && (by & 1)) ys = y0 - 3;
+    uint32_t exc = 0;
+    for (int yy = 0; yy < 2; yy++) {
+        int y = (lane & 1) * 2 + yy;
+        for (int x = 0; x < 4; x++) {
+            int v = luma_interp<COMPAT>(R, x0 + x + (mvx >> 2), ys + y + (mvy >> 2), mvx & 3, mvy & 3);
+            if (pd.weighted_pred) v = weight_pred(v, pd.luma_log2_wd, pd.luma_weight[ri], pd.luma_offset[ri]);
+            int px = bx * 4 + x, py = by * 4 + y;
+            w.tile[(py + 1) * TILE_P + px + 1] = recon_luma<COMPAT>(v + w.res[py * 16 + px], exc);
+        }
+    }
+    if (exc) {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(&w.excursions, exc);
+#else
+        w.excursions += exc;
+#endif
+    }
+}
+
+// Phase P2: chroma of an inter MB.  Lane -> plane (lane >> 4), 4 samples.
+// COMPAT: the reference has no chroma prediction, sample = residual (D4, h264/macroblock.cpp:1477-1480).
+// Otherwise ITU-T H.264 8.4.2.2.2 (1/8-sample bilinear) + weighted prediction.
+template <bool COMPAT>
+HD void phase_inter_chroma(MbWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane)
+{
+    int plane = lane >> 4, l = lane & 15;
+    // lane l covers chroma row-pair block: 2x2 samples of luma 4x4 block l (raster)
+    int bx = l & 3, by = l >> 2, q = (by >> 1) * 2 + (bx >> 1);
+    int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    int cw = g.w_mbs * 8, ch = g.h_mbs * 8;
+    if (COMPAT) {
+        for (int k = 0; k < 4; k++) {
+            int cx = bx * 2 + (k & 1), cy = by * 2 + (k >> 1);
+            w.ctile[plane][(cy + 1) * 12 + cx + 1] = (uint8_t)w.res[256 + plane * 64 + cy * 8 + cx];
+        }
+        return;
+    }
+    const int16_t* mvp = pd.mv + (size_t)a * H264R_MV_PER_MB + l * 2;
+    int mvx = H264R_LDG(mvp), mvy = H264R_LDG(mvp + 1);
+    int ri = h.u.ref_idx[q] & 15;
+    const uint8_t* ref = plane ? pd.ref_v[ri] : pd.ref_u[ri];
+    int xf = mvx & 7, yf = mvy & 7;
+    for (int k = 0; k < 4; k++) {
+        int cx = bx * 2 + (k & 1), cy = by * 2 + (k >> 1);
+        int xi = mbx * 8 + cx + (mvx >> 3), yi = mby * 8 + cy + (mvy >> 3);
+        int xa = clip3(0, cw - 1, xi), xb = clip3(0, cw - 1, xi + 1);
+        int ya = clip3(0, ch - 1, yi), yb = clip3(0, ch - 1, yi + 1);
+        int A = H264R_LDG(ref + (size_t)ya * g.pitch_c + xa), B = H264R_LDG(ref + (size_t)ya * g.pitch_c + xb);
+        int C = H264R_LDG(ref + (size_t)yb * g.pitch_c + xa), D = H264R_LDG(ref + (size_t)yb * g.pitch_c + xb);
+        int v = ((8 - xf) * (8 - yf) * A + xf * (8 - yf) * B + (8 - xf) * yf * C + xf * yf * D + 32) >> 6;
+        if (pd.weighted_pred) v = weight_pred(v, pd.chroma_log2_wd, pd.chroma_weight[ri][plane], pd.chroma_offset[ri][plane]);
+        w.ctile[plane][(cy + 1) * 12 + cx + 1] = recon_chroma<false>(v + w.res[256 + plane * 64 + cy * 8 + cx]);
+    }
+}
+
+// Phase S: write the reconstructed MB from the tiles to the frame.  Lanes 0..15 one luma row
+// (16 bytes), 16..23 one Cb row, 24..31 one Cr row (8 bytes).
+HD void phase_store(const MbWork& w, const PicDesc& pd, const Geometry& g, int a, int lane)
+{
+    int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    if (lane < 16) {
+        const uint8_t* s = &w.tile[(lane + 1) * TILE_P + 1];
+        uint32_t v[4];
+        for (int k = 0; k < 4; k++) v[k] = s[4 * k] | (s[4 * k + 1] << 8) | (s[4 * k + 2] << 16) | ((uint32_t)s[4 * k + 3] << 24);
+        uint4* d = reinterpret_cast<uint4*>(pd.y + (size_t)(mby * 16 + lane) * g.pitch_y + mbx * 16);
+        *d = uint4{v[0], v[1], v[2], v[3]};
+    } else {
+        int plane = (lane - 16) >> 3, row = (lane - 16) & 7;
+        const uint8_t* s = &w.ctile[plane][(row + 1) * 12 + 1];
+        uint32_t v0 = s[0] | (s[1] << 8) | (s[2] << 16) | ((uint32_t)s[3] << 24);
+        uint32_t v1 = s[4] | (s[5] << 8) | (s[6] << 16) | ((uint32_t)s[7] << 24);
+        uint2* d = reinterpret_cast<uint2*>((plane ? pd.v : pd.u) + (size_t)(mby * 8 + row) * g.pitch_c + mbx * 8);
+        *d = uint2{v0, v1};
+    }
+    if (lane == 0 && w.excursions && pd.excursion_map) pd.excursion_map[a] = 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: intra prediction
+// ------------------------------------------------------------------------------------------------
+// Phase I0: neighbouring samples of the MB into the tile borders: row y=-1 for x=-1..23 (lanes
+// 0..24), column x=-1 for y=0..15 (lanes 0..15), chroma borders.  Unavailable neighbours read as 0.
+// Neighbours were written by other warps of the same kernel, hence LDCG.
+HD void phase_intra_edges(MbWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane, bool chroma)
+{
+    int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    bool A = h.flags & H264R_AVAIL_A, B = h.flags & H264R_AVAIL_B, C = h.flags & H264R_AVAIL_C, D = h.flags & H264R_AVAIL_D;
+    const uint8_t* y = pd.y;
+    if (lane < 25) {
+        int x = lane - 1;     // -1..23
+        bool ok = x < 0 ? D : (x < 16 ? B : C);
+        w.tile[lane] = ok ? H264R_LDCG(y + (size_t)(mby * 16 - 1) * g.pitch_y + mbx * 16 + x) : 0;
+    }
+    if (lane < 16) w.tile[(lane + 1) * TILE_P] = A ? H264R_LDCG(y + (size_t)(mby * 16 + lane) * g.pitch_y + mbx * 16 - 1) : 0;
+    if (chroma) {
+        int plane = lane >> 4, l = lane & 15;
+        const uint8_t* c = plane ? pd.v : pd.u;
+        if (l < 9) {
+            int x = l - 1;
+            bool ok = x < 0 ? D : B;
+            w.ctile[plane][l] = ok ? H264R_LDCG(c + (size_t)(mby * 8 - 1) * g.pitch_c + mbx * 8 + x) : 0;
+        } else if (l < 16) {
+            // rows 0..6 here, row 7 below
+            int r = l - 9;
+            w.ctile[plane][(r + 1) * 12] = A ? H264R_LDCG(c + (size_t)(mby * 8 + r) * g.pitch_c + mbx * 8 - 1) : 0;
+            if (r == 6) w.ctile[plane][8 * 12] = A ? H264R_LDCG(c + (size_t)(mby * 8 + 7) * g.pitch_c + mbx * 8 - 1) : 0;
+        }
+    }
+}
+
+#define TL(x, y) w.tile[((y) + 1) * TILE_P + (x) + 1]
+
+// Phase I16: Intra16x16, 8 samples per lane (row lane >> 1, columns 8*(lane & 1) ..).
+// Reference: macroblock::Prediction_Intra16x16_{V,H,DC,Plane} (h264/macroblock.cpp:1373-1441).
+template <bool COMPAT>
+HD void phase_intra16(MbWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane)
+{
+    bool A = h.flags & H264R_AVAIL_A, B = h.flags & H264R_AVAIL_B, D = h.flags & H264R_AVAIL_D;
+    int mode = h.intra_modes & 3;
+    int row = lane >> 1, c0 = (lane & 1) * 8;
+    int dc = 0, pa = 0, pb = 0, pc = 0;
+    if (mode == 2) {
+        int sl = 0, st = 0;
+        for (int k = 0; k < 16; k++) { sl += TL(-1, k); st += TL(k, -1); }
+        if (A && B) dc = (sl + st + 16) >> 5;
+        else if (A) dc = (sl + 8) >> 4;
+        else if (B) {
+            if (COMPAT) {
+                // D5: top-only DC sums column 15 of the MB above (h264/macroblock.cpp:1410-1411)
+                int mbx = a % g.w_mbs, mby = a / g.w_mbs, sc = 0;
+                for (int k = 0; k < 16; k++) sc += H264R_LDCG(pd.y + (size_t)(mby * 16 - 16 + k) * g.pitch_y + mbx * 16 + 15);
+                dc = (sc + 8) >> 4;
+            } else dc = (st + 8) >> 4;
+        } else dc = 128;
+    } else if (mode == 3) {
+        // missing neighbours read as 0 (the tile borders already hold 0); corner only if D
+        int Hs = 0, Vs = 0;
+        for (int i = 1; i <= 8; i++) {
+            int hl = (7 - i) < 0 ? (D ? TL(-1, -1) : 0) : TL(7 - i, -1);
+            int vl = (7 - i) < 0 ? (D ? TL(-1, -1) : 0) : TL(-1, 7 - i);
+            Hs += i * (TL(7 + i, -1) - hl);
+            Vs += i * (TL(-1, 7 + i) - vl);
+        }
+        pa = 16 * (TL(15, -1) + TL(-1, 15)); pb = (5 * Hs + 32) >> 6; pc = (5 * Vs + 32) >> 6;
+    }
+    uint32_t exc = 0;
+    uint8_t out[8];
+    for (int k = 0; k < 8; k++) {
+        int x = c0 + k, v;
+        if (mode == 0) v = B ? TL(x, -1) : 0;
+        else if (mode == 1) v = A ? TL(-1, row) : 0;
+        else if (mode == 2) v = dc;
+        else v = clip1((pa + pb * (x - 7) + pc * (row - 7) + 16) >> 5);
+        out[k] = recon_luma<COMPAT>(v + w.res[row * 16 + x], exc);
+    }
+    // all lanes have read the borders they need before anybody overwrites TL(x>=0, y>=0): the
+    // interior is disjoint from the borders, so no extra barrier is required
+    for (int k = 0; k < 8; k++) TL(c0 + k, row) = out[k];
+    if (exc) {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(&w.excursions, exc);
+#else
+        w.excursions += exc;
+#endif
+    }
+}
+
+// Phase I4(ras): Intra4x4 prediction + reconstruction of the block at raster index ras; lanes 0..15
+// one sample each.  Reference: macroblock::Prediction_Intra4x4 and the nine mode functions
+// (h264/macroblock.cpp:973-990, 1037-1365); block order and the up-right substitution rule follow
+// macroblock::Calc / get_4x4Neighbour (h264/macroblock.cpp:28-33, 1092-1110).
+template <bool COMPAT>
+HD void phase_intra4(MbWork& w, const h264r_mb_hdr& h, int ras, int lane)
+{
+    if (lane >= 16) return;
+    int bx = ras & 3, by = ras >> 2, blk = blk_raster(ras);
+    int mode = (h.u.pred4x4[blk >> 1] >> ((blk & 1) * 4)) & 15;
+    bool left_ok = bx > 0 || (h.flags & H264R_AVAIL_A);
+    bool top_ok = by > 0 || (h.flags & H264R_AVAIL_B);
+    bool tr_ok;
+    if (blk == 3 || blk == 11) tr_ok = false;
+    else if (bx == 3) tr_ok = (by == 0) && (h.flags & H264R_AVAIL_C);
+    else if (by > 0) tr_ok = true;
+    else tr_ok = (h.flags & H264R_AVAIL_B) != 0;
+    int X = bx * 4, Y = by * 4;
+    // e[0..12] = L K J I M A B C D E F G H ; unavailable samples read as 0
+    int e[13];
+    for (int k = 0; k < 4; k++) e[3 - k] = left_ok ? TL(X - 1, Y + k) : 0;
+    bool tl_ok = (bx > 0 && by > 0) ? true : (bx > 0 ? (h.flags & H264R_AVAIL_B) != 0 : (by > 0 ? (h.flags & H264R_AVAIL_A) != 0 : (h.flags & H264R_AVAIL_D) != 0));
+    e[4] = tl_ok ? TL(X - 1, Y - 1) : 0;
+    for (int k = 0; k < 4; k++) e[5 + k] = top_ok ? TL(X + k, Y - 1) : 0;
+    for (int k = 0; k < 4; k++) e[9 + k] = top_ok ? (tr_ok ? TL(X + 4 + k, Y - 1) : e[8]) : 0;
+    int x = lane & 3, y = lane >> 2, v = 0;
+    const int* top = e + 5;
+    switch (mode) {
+    case 0: v = top[x]; break;
+    case 1: v = e[3 - y]; break;
+    case 2:
+        if (left_ok && top_ok) v = (top[0] + top[1] + top[2] + top[3] + e[0] + e[1] + e[2] + e[3] + 4) >> 3;
+        else if (left_ok) v = (e[0] + e[1] + e[2] + e[3] + 2) >> 2;
+        else if (top_ok) v = (top[0] + top[1] + top[2] + top[3] + 2) >> 2;
+        else v = 128;
+        break;
+    case 3:
+        v = (x == 3 && y == 3) ? (top[6] + 3 * top[7] + 2) >> 2 : (top[x + y] + 2 * top[x + y + 1] + top[x + y + 2] + 2) >> 2;
+        break;
+    case 4: v = (e[3 - y + x] + 2 * e[4 - y + x] + e[5 - y + x] + 2) >> 2; break;
+    case 5: {
+        int z = 2 * x - y, i = x - (y >> 1);
+        if (z >= 0 && !(z & 1)) v = (e[4 + i] + e[5 + i] + 1) >> 1;
+        else if (z >= 0) v = (e[3 + i] + 2 * e[4 + i] + e[5 + i] + 2) >> 2;
+        else if (z == -1) v = (e[3] + 2 * e[4] + e[5] + 2) >> 2;
+        else v = (e[4 - y] + 2 * e[5 - y] + e[6 - y] + 2) >> 2;
+        break;
+    }
+    case 6: {
+        int z = 2 * y - x, i = y - (x >> 1);
+        if (z >= 0 && !(z & 1)) v = (e[4 - i] + e[3 - i] + 1) >> 1;
+        else if (z >= 0) v = (e[5 - i] + 2 * e[4 - i] + e[3 - i] + 2) >> 2;
+        else if (z == -1) v = (e[3] + 2 * e[4] + e[5] + 2) >> 2;
+        else v = (e[4 + x] + 2 * e[3 + x] + e[2 + x] + 2) >> 2;
+        break;
+    }
+    case 7: {
+        int i = x + (y >> 1);
+        v = !(y & 1) ? (top[i] + top[i + 1] + 1) >> 1 : (top[i] + 2 * top[i + 1] + top[i + 2] + 2) >> 2;
+        break;
+    }
+    case 8: {
+        int z = x + 2 * y, i = y + (x >> 1);
+        if (z > 5) v = e[0];
+        else if (z == 5) v = (e[1] + 3 * e[0] + 2) >> 2;
+        else if (!(z & 1)) v = (e[3 - i] + e[2 - i] + 1) >> 1;
+        else v = (e[3 - i] + 2 * e[2 - i] + e[1 - i] + 2) >> 2;
+        break;
+    }
+    default: break;
+    }
+    uint32_t exc = 0;
+    uint8_t s = recon_luma<COMPAT>(v + w.res[(Y + y) * 16 + X + x], exc);
+    TL(X + x, Y + y) = s;
+    if (exc) {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(&w.excursions, exc);
+#else
+        w.excursions += exc;
+#endif
+    }
+}
+
+// Phase I8a(q): filtered neighbouring samples of 8x8 block q (ITU-T H.264 8.3.2.2.1) into w.e8:
+// e8[7-k] = left[k], e8[8] = corner, e8[9+k] = top[k] (k = 0..15).  Lane k < 25 produces e8[k].
+HD void intra8_avail(const h264r_mb_hdr& h, int q, bool& left_ok, bool& top_ok, bool& tl_ok, bool& tr_ok)
+{
+    int bx = q & 1, by = q >> 1;
+    left_ok = bx > 0 || (h.flags & H264R_AVAIL_A);
+    top_ok = by > 0 || (h.flags & H264R_AVAIL_B);
+    tl_ok = (bx > 0 && by > 0) ? true : (bx > 0 ? (h.flags & H264R_AVAIL_B) != 0 : (by > 0 ? (h.flags & H264R_AVAIL_A) != 0 : (h.flags & H264R_AVAIL_D) != 0));
+    tr_ok = q == 0 ? (h.flags & H264R_AVAIL_B) != 0 : (q == 1 ? (h.flags & H264R_AVAIL_C) != 0 : q == 2);
+}
+HD void phase_intra8_filter(MbWork& w, const h264r_mb_hdr& h, int q, int lane)
+{
+    if (lane >= 25) return;
+    bool left_ok, top_ok, tl_ok, tr_ok;
+    intra8_avail(h, q, left_ok, top_ok, tl_ok, tr_ok);
+    int X = (q & 1) * 8, Y = (q >> 1) * 8;
+    // unfiltered sample at edge index i (same indexing as e8)
+    auto raw = [&](int i) -> int {
+        if (i < 8) return TL(X - 1, Y + 7 - i);
+        if (i == 8) return TL(X - 1, Y - 1);
+        int k = i - 9;
+        if (k >= 8 && !tr_ok) k = 7;
+        return TL(X + k, Y - 1);
+    };
+    int v = 0;
+    if (lane < 8) {            // left[k], k = 7 - lane
+        if (left_ok) {
+            int k = 7 - lane;
+            if (k == 0) v = tl_ok ? (raw(8) + 2 * raw(7) + raw(6) + 2) >> 2 : (3 * raw(7) + raw(6) + 2) >> 2;
+            else if (k == 7) v = (raw(1) + 3 * raw(0) + 2) >> 2;
+            else v = (raw(lane + 1) + 2 * raw(lane) + raw(lane - 1) + 2) >> 2;
+        }
+    } else if (lane == 8) {
+        if (tl_ok) {
+            if (top_ok && left_ok) v = (raw(9) + 2 * raw(8) + raw(7) + 2) >> 2;
+            else if (top_ok) v = (3 * raw(8) + raw(9) + 2) >> 2;
+            else if (left_ok) v = (3 * raw(8) + raw(7) + 2) >> 2;
+            else v = raw(8);
+        }
+    } else if (top_ok) {
+        int k = lane - 9;
+        if (k == 0) v = tl_ok ? (raw(8) + 2 * raw(9) + raw(10) + 2) >> 2 : (3 * raw(9) + raw(10) + 2) >> 2;
+        else if (k == 15) v = (raw(23) + 3 * raw(24) + 2) >> 2;
+        else v = (raw(lane - 1) + 2 * raw(lane) + raw(lane + 1) + 2) >> 2;
+    }
+    w.e8[lane] = (uint8_t)v;
+}
+// Phase I8b(q): Intra8x8 prediction (8.3.2.2.2 - 8.3.2.2.10) + reconstruction, 2 samples per lane.
+HD void phase_intra8(MbWork& w, const h264r_mb_hdr& h, int q, int lane)
+{
+    bool left_ok, top_ok, tl_ok, tr_ok;
+    intra8_avail(h, q, left_ok, top_ok, tl_ok, tr_ok);
+    int mode = (h.u.pred4x4[q >> 1] >> ((q & 1) * 4)) & 15;
+    int X = (q & 1) * 8, Y = (q >> 1) * 8;
+    const uint8_t* e = w.e8;
+#define T8(k) ((int)e[9 + (k)])
+#define L8(k) ((int)e[7 - (k)])
+    uint32_t exc = 0;
+    for (int n = 0; n < 2; n++) {
+        int idx = lane * 2 + n, x = idx & 7, y = idx >> 3, v = 0;
+        switch (mode) {
+        case 0: v = T8(x); break;
+        case 1: v = L8(y); break;
+        case 2: {
+            int s = 0;
+            if (left_ok && top_ok) { for (int k = 0; k < 8; k++) s += T8(k) + L8(k); v = (s + 8) >> 4; }
+            else if (left_ok) { for (int k = 0; k < 8; k++) s += L8(k); v = (s + 4) >> 3; }
+            else if (top_ok) { for (int k = 0; k < 8; k++) s += T8(k); v = (s + 4) >> 3; }
+            else v = 128;
+            break;
+        }
+        case 3: v = (x == 7 && y == 7) ? (T8(14) + 3 * T8(15) + 2) >> 2 : (T8(x + y) + 2 * T8(x + y + 1) + T8(x + y + 2) + 2) >> 2; break;
+        case 4: v = (e[7 - y + x] + 2 * e[8 - y + x] + e[9 - y + x] + 2) >> 2; break;
+        case 5: {
+            int z = 2 * x - y, i = x - (y >> 1);
+            if (z >= 0 && !(z & 1)) v = (T8(i - 1) + T8(i) + 1) >> 1;
+            else if (z >= 0) v = (T8(i - 2) + 2 * T8(i - 1) + T8(i) + 2) >> 2;
+            else if (z == -1) v = (L8(0) + 2 * T8(-1) + T8(0) + 2) >> 2;
+            else v = (L8(y - 2 * x - 1) + 2 * L8(y - 2 * x - 2) + L8(y - 2 * x - 3) + 2) >> 2;
+            break;
+        }
+        case 6: {
+            int z = 2 * y - x, i = y - (x >> 1);
+            if (z >= 0 && !(z & 1)) v = (L8(i - 1) + L8(i) + 1) >> 1;
+            else if (z >= 0) v = (L8(i - 2) + 2 * L8(i - 1) + L8(i) + 2) >> 2;
+            else if (z == -1) v = (L8(0) + 2 * T8(-1) + T8(0) + 2) >> 2;
+            else v = (T8(x - 2 * y - 1) + 2 * T8(x - 2 * y - 2) + T8(x - 2 * y - 3) + 2) >> 2;
+            break;
+        }
+        case 7: {
+            int i = x + (y >> 1);
+            v = !(y & 1) ? (T8(i) + T8(i + 1) + 1) >> 1 : (T8(i) + 2 * T8(i + 1) + T8(i + 2) + 2) >> 2;
+            break;
+        }
+        case 8: {
+            int z = x + 2 * y, i = y + (x >> 1);
+            if (z > 13) v = L8(7);
+            else if (z == 13) v = (L8(6) + 3 * L8(7) + 2) >> 2;
+            else if (!(z & 1)) v = (L8(i) + L8(i + 1) + 1) >> 1;
+            else v = (L8(i) + 2 * L8(i + 1) + L8(i + 2) + 2) >> 2;
+            break;
+        }
+        default: break;
+        }
+        TL(X + x, Y + y) = recon_luma<false>(v + w.res[(Y + y) * 16 + X + x], exc);
+    }
+#undef T8
+#undef L8
+    if (exc) {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(&w.excursions, exc);
+#else
+        w.excursions += exc;
+#endif
+    }
+}
+
+// Phase IC: chroma of an intra MB.  COMPAT: sample = residual (D4).  Otherwise ITU-T H.264 8.3.4.
+// Lane -> plane (lane >> 4), 4 samples: row (l >> 1), columns 4*(l & 1)...
+template <bool COMPAT>
+HD void phase_intra_chroma(MbWork& w, const h264r_mb_hdr& h, int lane)
+{
+    int plane = lane >> 4, l = lane & 15;
+    int y = l >> 1, x0 = (l & 1) * 4;
+    uint8_t* t = w.ctile[plane];
+#define CT(x, y) t[((y) + 1) * 12 + (x) + 1]
+    int out[4];
+    if (COMPAT) {
+        for (int k = 0; k < 4; k++) out[k] = (uint8_t)w.res[256 + plane * 64 + y * 8 + x0 + k];
+    } else {
+        bool A = h.flags & H264R_AVAIL_A, B = h.flags & H264R_AVAIL_B;
+        int mode = (h.intra_modes >> 2) & 3;
+        int pa = 0, pb = 0, pc = 0, dc = 0;
+        if (mode == 0) {
+            int b = (y >> 2) * 2 + (x0 >> 2), xo = x0, yo = (y >> 2) * 4, st = 0, sl = 0;
+            for (int k = 0; k < 4; k++) { st += CT(xo + k, -1); sl += CT(-1, yo + k); }
+            if (b == 0 || b == 3) dc = (A && B) ? (st + sl + 4) >> 3 : (A ? (sl + 2) >> 2 : (B ? (st + 2) >> 2 : 128));
+            else if (b == 1) dc = B ? (st + 2) >> 2 : (A ? (sl + 2) >> 2 : 128);
+            else dc = A ? (sl + 2) >> 2 : (B ? (st + 2) >> 2 : 128);
+        } else if (mode == 3) {
+            int Hs = 0, Vs = 0;
+            for (int k = 0; k < 4; k++) {
+                Hs += (k + 1) * (CT(4 + k, -1) - CT(2 - k, -1));
+                Vs += (k + 1) * (CT(-1, 4 + k) - CT(-1, 2 - k));
+            }
+            pa = 16 * (CT(-1, 7) + CT(7, -1)); pb = (34 * Hs + 32) >> 6; pc = (34 * Vs + 32) >> 6;
+        }
+        for (int k = 0; k < 4; k++) {
+            int x = x0 + k, v;
+            if (mode == 0) v = dc;
+            else if (mode == 1) v = CT(-1, y);
+            else if (mode == 2) v = CT(x, -1);
+            else v = clip1((pa + pb * (x - 3) + pc * (y - 3) + 16) >> 5);
+            out[k] = clip1(v + w.res[256 + plane * 64 + y * 8 + x]);
+        }
+    }
+    for (int k = 0; k < 4; k++) CT(x0 + k, y) = (uint8_t)out[k];
+#undef CT
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: deblocking filter, ITU-T H.264 8.7 (no reference counterpart)
+// ------------------------------------------------------------------------------------------------
+struct DeblockTables {
+    uint8_t alpha[52], beta[52], tc0[52][3];
+};
+// Tables 8-16 / 8-17 of ITU-T H.264: alpha'(indexA), beta'(indexB), tC0'(indexA, bS)
+#define H264R_DEBLOCK_INIT                                                                                              \
+    {{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 4, 4, 5, 6, 7, 8, 9, 10, 12, 13,                                 \
+      15, 17, 20, 22, 25, 28, 32, 36, 40, 45, 50, 56, 63, 71, 80, 90, 101, 113, 127, 144,                               \
+      162, 182, 203, 226, 255, 255},                                                                                    \
+     {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4,                                    \
+      6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13, 14, 14, 15, 15, 16, 16,                                   \
+      17, 17, 18, 18},                                                                                                  \
+     {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0},     \
+      {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 1}, {0, 0, 1}, {0, 0, 1},     \
+      {0, 0, 1}, {0, 1, 1}, {0, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 2}, {1, 1, 2}, {1, 1, 2},     \
+      {1, 1, 2}, {1, 2, 3}, {1, 2, 3}, {2, 2, 3}, {2, 2, 4}, {2, 3, 4}, {2, 3, 4}, {3, 3, 5}, {3, 4, 6}, {3, 4, 6},     \
+      {4, 5, 7}, {4, 5, 8}, {4, 6, 9}, {5, 7, 10}, {6, 8, 11}, {6, 8, 13}, {7, 10, 14}, {8, 11, 16}, {9, 12, 18},       \
+      {10, 13, 20}, {11, 15, 23}, {13, 17, 25}}}
+#ifdef __CUDACC__
+static __constant__ DeblockTables c_deblock_tables = H264R_DEBLOCK_INIT;
+#endif
+static const DeblockTables h_deblock_tables = H264R_DEBLOCK_INIT;
+HD const DeblockTables& deblock_tables()
+{
+#if defined(__CUDA_ARCH__)
+    return c_deblock_tables;
+#else
+    return h_deblock_tables;
+#endif
+}
+
+#define DT(x, y) w.dtile[((y) + 4) * 24 + (x) + 4]
+#define DCT(p, x, y) w.dctile[p][((y) + 2) * 12 + (x) + 2]
+
+HD bool blk_coded(const MbWork& w, const h264r_mb_hdr& h, int ras)
+{
+    if (h.flags & H264R_T8x8) {
+        int q = (ras >> 3) * 2 + ((ras & 3) >> 1);
+        for (int k = 0; k < 64; k++) if (w.coef[q * 4 + (k >> 4)][k & 15]) return true;
+        return false;
+    }
+    int blk = blk_raster(ras);
+    for (int k = 0; k < 16; k++) if (w.coef[blk][k]) return true;
+    return false;
+}
+HD bool blk_coded_global(const PicDesc& pd, const h264r_mb_hdr& h, int a, int ras)
+{
+    const int16_t* c = pd.coeff + (size_t)a * H264R_COEFF_PER_MB;
+    int first, n;
+    if (h.flags & H264R_T8x8) { first = ((ras >> 3) * 2 + ((ras & 3) >> 1)) * 64; n = 64; }
+    else { first = blk_raster(ras) * 16; n = 16; }
+    const int4* p = reinterpret_cast<const int4*>(c + first);
+    for (int k = 0; k < n / 8; k++) { int4 v = H264R_LDG(p + k); if (v.x | v.y | v.z | v.w) return true; }
+    return false;
+}
+
+// Phase D0a: load the tiles (luma x,y = -4..15; chroma x,y = -2..7).  w.coef must hold the MB's levels.
+HD void phase_deblock_load(MbWork& w, const PicDesc& pd, const Geometry& g, int a, int lane)
+{
+    int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    for (int i = lane; i < 20 * 5; i += 32) {          // 20 rows x 5 words
+        int r = i / 5 - 4, cw = (i % 5) * 4 - 4;
+        int yy = mby * 16 + r, xx = mbx * 16 + cw;
+        uint32_t v = 0;
+        if (yy >= 0 && xx >= 0) v = H264R_LDCG(reinterpret_cast<const uint32_t*>(pd.y + (size_t)yy * g.pitch_y + xx));
+        uint8_t* d = &DT(cw, r);
+        d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8); d[2] = (uint8_t)(v >> 16); d[3] = (uint8_t)(v >> 24);
+    }
+    for (int i = lane; i < 2 * 10 * 5; i += 32) {      // 2 planes x 10 rows x 5 half-words
+        int p = i / 50, r = (i % 50) / 5 - 2, cw = (i % 5) * 2 - 2;
+        int yy = mby * 8 + r, xx = mbx * 8 + cw;
+        uint32_t v = 0;
+        if (yy >= 0 && xx >= 0) v = H264R_LDCG(reinterpret_cast<const uint16_t*>((p ? pd.v : pd.u) + (size_t)yy * g.pitch_c + xx));
+        DCT(p, cw, r) = (uint8_t)v; DCT(p, cw + 1, r) = (uint8_t)(v >> 8);
+    }
+}
+
+// Phase D0b: boundary strengths; lane = dir*16 + edge*4 + k.
+HD void phase_deblock_bs(MbWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane)
+{
+    int dir = lane >> 4, e = (lane >> 2) & 3, k = lane & 3;
+    int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    int bs = 0;
+    bool t8 = (h.flags & H264R_T8x8) != 0;
+    int an = a, rasq, rasp;
+    bool active = true, mb_edge = (e == 0);
+    if (mb_edge) {
+        active = dir == 0 ? mbx > 0 : mby > 0;
+        an = dir == 0 ? a - 1 : a - g.w_mbs;
+        rasq = dir == 0 ? k * 4 : k;
+        rasp = dir == 0 ? k * 4 + 3 : 12 + k;
+    } else {
+        active = !(t8 && (e & 1));
+        rasq = dir == 0 ? k * 4 + e : e * 4 + k;
+        rasp = dir == 0 ? rasq - 1 : rasq - 4;
+    }
+    if (active) {
+        h264r_mb_hdr hn = h;
+        if (mb_edge) {
+            const int4* hp = reinterpret_cast<const int4*>(pd.hdr + an);
+            int4 raw = H264R_LDG(hp);
+            hn = *reinterpret_cast<h264r_mb_hdr*>(&raw);
+        }
+        if (is_intra(h.mb_class) || is_intra(hn.mb_class)) bs = mb_edge ? 4 : 3;
+        else if (blk_coded(w, h, rasq) || (mb_edge ? blk_coded_global(pd, hn, an, rasp) : blk_coded(w, h, rasp))) bs = 2;
+        else {
+            int qq = (rasq >> 3) * 2 + ((rasq & 3) >> 1), qp_ = (rasp >> 3) * 2 + ((rasp & 3) >> 1);
+            int refq = pd.ref_id[h.u.ref_idx[qq] & 15], refp = pd.ref_id[hn.u.ref_idx[qp_] & 15];
+            const int16_t* mq = pd.mv + (size_t)a * H264R_MV_PER_MB + rasq * 2;
+            const int16_t* mp = pd.mv + (size_t)an * H264R_MV_PER_MB + rasp * 2;
+            if (refq != refp) bs = 1;
+            else if (iabs(H264R_LDG(mq) - H264R_LDG(mp)) >= 4 || iabs(H264R_LDG(mq + 1) - H264R_LDG(mp + 1)) >= 4) bs = 1;
+        }
+    }
+    w.bs[lane] = (uint8_t)bs;
+}
+
+// one line across one edge; p[i] / q[i] are passed by reference (modified in place)
+HD void deblock_luma_line(int& p3, int& p2, int& p1, int& p0, int& q0, int& q1, int& q2, int& q3, int bs, int alpha, int beta, int tc0)
+{
+    if (!(iabs(p0 - q0) < alpha && iabs(p1 - p0) < beta && iabs(q1 - q0) < beta)) return;
+    int ap = iabs(p2 - p0), aq = iabs(q2 - q0);
+    int P0 = p0, P1 = p1, P2 = p2, Q0 = q0, Q1 = q1, Q2 = q2;
+    if (bs < 4) {
+        int tc = tc0 + (ap < beta) + (aq < beta);
+        int delta = clip3(-tc, tc, (((Q0 - P0) * 4) + (P1 - Q1) + 4) >> 3);
+        p0 = clip1(P0 + delta); q0 = clip1(Q0 - delta);
+        if (ap < beta) p1 = P1 + clip3(-tc0, tc0, (P2 + ((P0 + Q0 + 1) >> 1) - (P1 * 2)) >> 1);
+        if (aq < beta) q1 = Q1 + clip3(-tc0, tc0, (Q2 + ((P0 + Q0 + 1) >> 1) - (Q1 * 2)) >> 1);
+    } else {
+        bool small = iabs(P0 - Q0) < ((alpha >> 2) + 2);
+        if (ap < beta && small) {
+            p0 = (P2 + 2 * P1 + 2 * P0 + 2 * Q0 + Q1 + 4) >> 3;
+            p1 = (P2 + P1 + P0 + Q0 + 2) >> 2;
+            p2 = (2 * p3 + 3 * P2 + P1 + P0 + Q0 + 4) >> 3;
+        } else p0 = (2 * P1 + P0 + Q1 + 2) >> 2;
+        if (aq < beta && small) {
+            q0 = (P1 + 2 * P0 + 2 * Q0 + 2 * Q1 + Q2 + 4) >> 3;
+            q1 = (P0 + Q0 + Q1 + Q2 + 2) >> 2;
+            q2 = (2 * q3 + 3 * Q2 + Q1 + Q0 + P0 + 4) >> 3;
+        } else q0 = (2 * Q1 + Q0 + P1 + 2) >> 2;
+    }
+}
+HD void deblock_chroma_line(int p1, int& p0, int& q0, int q1, int bs, int alpha, int beta, int tc0)
+{
+    if (!(iabs(p0 - q0) < alpha && iabs(p1 - p0) < beta && iabs(q1 - q0) < beta)) return;
+    int P0 = p0, Q0 = q0;
+    if (bs < 4) {
+        int tc = tc0 + 1;
+        int delta = clip3(-tc, tc, (((Q0 - P0) * 4) + (p1 - q1) + 4) >> 3);
+        p0 = clip1(P0 + delta); q0 = clip1(Q0 - delta);
+    } else {
+        p0 = (2 * p1 + P0 + q1 + 2) >> 2;
+        q0 = (2 * q1 + Q0 + p1 + 2) >> 2;
+    }
+}
+
+// Phase D1(dir): filter the edges of one direction inside the tiles.  Lanes 0..15: one luma line
+// each (a row for vertical edges, a column for horizontal ones); 16..23 Cb lines; 24..31 Cr lines.
+// qp_n = QP (per plane) of the left / upper neighbour MB.
+HD void phase_deblock_dir(MbWork& w, const PicDesc& pd, const h264r_mb_hdr& h, const h264r_mb_hdr& hn, int dir, int lane)
+{
+    const DeblockTables& T = deblock_tables();
+    if (lane < 16) {
+        for (int e = 0; e < 4; e++) {
+            int bs = w.bs[dir * 16 + e * 4 + (lane >> 2)];
+            if (!bs) continue;
+            int qpav = e == 0 ? (h.qp_y + hn.qp_y + 1) >> 1 : h.qp_y;
+            int ia = clip3(0, 51, qpav + pd.alpha_off), ib = clip3(0, 51, qpav + pd.beta_off);
+            int alpha = T.alpha[ia], beta = T.beta[ib], tc0 = bs < 4 ? T.tc0[ia][bs - 1] : 0;
+            int s[8];
+            for (int i = 0; i < 8; i++) s[i] = dir == 0 ? DT(e * 4 - 4 + i, lane) : DT(lane, e * 4 - 4 + i);
+            deblock_luma_line(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], bs, alpha, beta, tc0);
+            for (int i = 1; i < 7; i++) {
+                if (dir == 0) DT(e * 4 - 4 + i, lane) = (uint8_t)s[i];
+                else DT(lane, e * 4 - 4 + i) = (uint8_t)s[i];
+            }
+        }
+    } else {
+        int p = (lane - 16) >> 3, line = (lane - 16) & 7;
+        int qp_q = p ? h.qp_cr : h.qp_cb, qp_p = p ? hn.qp_cr : hn.qp_cb;
+        for (int e = 0; e < 4; e += 2) {
+            int bs = w.bs[dir * 16 + e * 4 + (line >> 1)];
+            if (!bs) continue;
+            int qpav = e == 0 ? (qp_q + qp_p + 1) >> 1 : qp_q;
+            int ia = clip3(0, 51, qpav + pd.alpha_off), ib = clip3(0, 51, qpav + pd.beta_off);
+            int alpha = T.alpha[ia], beta = T.beta[ib], tc0 = bs < 4 ? T.tc0[ia][bs - 1] : 0;
+            int pos = e * 2;
+            int p1, p0, q0, q1;
+            if (dir == 0) { p1 = DCT(p, pos - 2, line); p0 = DCT(p, pos - 1, line); q0 = DCT(p, pos, line); q1 = DCT(p, pos + 1, line); }
+            else { p1 = DCT(p, line, pos - 2); p0 = DCT(p, line, pos - 1); q0 = DCT(p, line, pos); q1 = DCT(p, line, pos + 1); }
+            deblock_chroma_line(p1, p0, q0, q1, bs, alpha, beta, tc0);
+            if (dir == 0) { DCT(p, pos - 1, line) = (uint8_t)p0; DCT(p, pos, line) = (uint8_t)q0; }
+            else { DCT(p, line, pos - 1) = (uint8_t)p0; DCT(p, line, pos) = (uint8_t)q0; }
+        }
+    }
+}
+
+// Phase D2: write back what this MB may have changed: luma rows 0..15 x columns -4..15 and rows
+// -3..-1 x columns 0..15; chroma rows 0..7 x columns -2..7 and row -1 x columns 0..7.
+HD void phase_deblock_store(const MbWork& w, const PicDesc& pd, const Geometry& g, int a, int lane)
+{
+    int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    auto word = [](const uint8_t* s) { return (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24); };
+    for (int i = lane; i < 19 * 5; i += 32) {
+        int r = i / 5 - 3, cw = (i % 5) * 4 - 4;
+        if (r < 0 && cw < 0) continue;
+        int yy = mby * 16 + r, xx = mbx * 16 + cw;
+        if (yy < 0 || xx < 0) continue;
+        *reinterpret_cast<uint32_t*>(pd.y + (size_t)yy * g.pitch_y + xx) = word(&w.dtile[(r + 4) * 24 + cw + 4]);
+    }
+    for (int i = lane; i < 2 * 9 * 5; i += 32) {
+        int p = i / 45, r = (i % 45) / 5 - 1, cw = (i % 5) * 2 - 2;
+        if (r < 0 && cw < 0) continue;
+        int yy = mby * 8 + r, xx = mbx * 8 + cw;
+        if (yy < 0 || xx < 0) continue;
+        const uint8_t* s = &w.dctile[p][(r + 2) * 12 + cw + 2];
+        *reinterpret_cast<uint16_t*>((p ? pd.v : pd.u) + (size_t)yy * g.pitch_c + xx) = (uint16_t)(s[0] | (s[1] << 8));
+    }
+}
+
+#undef DT
+#undef DCT
+#undef TL
+
+// ------------------------------------------------------------------------------------------------
+// K5: frame digest (same definition as oracle/restate/h264_restate.c:h264o_digest)
+// ------------------------------------------------------------------------------------------------
+HD uint32_t digest_mix(uint32_t i)
+{
+    uint32_t h = i * 0x9E3779B1u + 0x7F4A7C15u;
+    h ^= h >> 15; h *= 0x85EBCA6Bu; h ^= h >> 13;
+    return h;
+}
+HD void digest_accumulate(uint32_t d[4], uint32_t sample, uint32_t index)
+{
+    d[0] += sample;
+    d[1] += sample * (index + 1u);
+    d[2] += sample * digest_mix(index);
+    d[3] += (sample ^ 0xA5u) * digest_mix(index ^ 0x5BD1E995u);
+}
+
+}  // namespace h264r

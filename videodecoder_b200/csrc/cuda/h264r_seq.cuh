@@ -1,0 +1,92 @@
+// h264r_seq.cuh -- the order in which the phases of h264r_core.cuh are run for one macroblock.
+//
+// `Exec` abstracts "run this phase on all 32 lanes, then synchronise the warp":
+//   device: every lane calls f(lane) and the warp meets at __syncwarp();
+//   host emulator: a loop over lanes 0..31.
+// Keeping the sequences here means the CPU tests run exactly the phase order the kernels use.
+#pragma once
+#include "h264r_core.cuh"
+
+namespace h264r {
+
+HD h264r_mb_hdr load_hdr(const PicDesc& pd, int a)
+{
+    const int4* p = reinterpret_cast<const int4*>(pd.hdr + a);
+    int4 raw = H264R_LDG(p);
+    return *reinterpret_cast<h264r_mb_hdr*>(&raw);
+}
+
+// K1 alone: residual of one MB into out[384] (int16: Y 16x16, U 8x8, V 8x8)
+template <bool COMPAT, class Exec>
+HD void seq_residual(Exec& ex, MbWork& w, const PicDesc& pd, int a, int16_t* out)
+{
+    h264r_mb_hdr h = load_hdr(pd, a);
+    ex([&](int lane) { phase_load_coeff(w, pd, a, lane); });
+    ex([&](int lane) { phase_residual<COMPAT>(w, h, lane); });
+    ex([&](int lane) { for (int k = lane; k < 384; k += 32) out[k] = w.res[k]; });
+}
+
+// K1 + K3: one inter macroblock
+template <bool COMPAT, class Exec>
+HD void seq_inter_mb(Exec& ex, MbWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a)
+{
+    ex([&](int lane) { phase_load_coeff(w, pd, a, lane); });
+    ex([&](int lane) { phase_residual<COMPAT>(w, h, lane); });
+    ex([&](int lane) {
+        phase_inter_luma<COMPAT>(w, pd, g, h, a, lane);
+        phase_inter_chroma<COMPAT>(w, pd, g, h, a, lane);
+    });
+    ex([&](int lane) { phase_store(w, pd, g, a, lane); });
+}
+
+// K1 + K2: one intra macroblock (its neighbours A, B, C, D are complete)
+template <bool COMPAT, class Exec>
+HD void seq_intra_mb(Exec& ex, MbWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a)
+{
+    ex([&](int lane) {
+        phase_load_coeff(w, pd, a, lane);
+        phase_intra_edges(w, pd, g, h, a, lane, !COMPAT);
+    });
+    ex([&](int lane) { phase_residual<COMPAT>(w, h, lane); });
+    if (h.mb_class == H264R_MB_I16x16) {
+        ex([&](int lane) {
+            phase_intra16<COMPAT>(w, pd, g, h, a, lane);
+            phase_intra_chroma<COMPAT>(w, h, lane);
+        });
+    } else if (h.mb_class == H264R_MB_I4x4) {
+        ex([&](int lane) {
+            phase_intra4<COMPAT>(w, h, 0, lane);
+            phase_intra_chroma<COMPAT>(w, h, lane);
+        });
+        for (int ras = 1; ras < 16; ras++) ex([&](int lane) { phase_intra4<COMPAT>(w, h, ras, lane); });
+    } else {
+        for (int q = 0; q < 4; q++) {
+            ex([&](int lane) {
+                phase_intra8_filter(w, h, q, lane);
+                if (q == 0) phase_intra_chroma<COMPAT>(w, h, lane);
+            });
+            ex([&](int lane) { phase_intra8(w, h, q, lane); });
+        }
+    }
+    ex([&](int lane) { phase_store(w, pd, g, a, lane); });
+}
+
+// K4: deblock one macroblock in place (its neighbours A, B, C are completely filtered)
+template <class Exec>
+HD void seq_deblock_mb(Exec& ex, MbWork& w, const PicDesc& pd, const Geometry& g, int a)
+{
+    h264r_mb_hdr h = load_hdr(pd, a);
+    int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    h264r_mb_hdr hl = mbx > 0 ? load_hdr(pd, a - 1) : h;
+    h264r_mb_hdr ht = mby > 0 ? load_hdr(pd, a - g.w_mbs) : h;
+    ex([&](int lane) {
+        phase_load_coeff(w, pd, a, lane);
+        phase_deblock_load(w, pd, g, a, lane);
+    });
+    ex([&](int lane) { phase_deblock_bs(w, pd, g, h, a, lane); });
+    ex([&](int lane) { phase_deblock_dir(w, pd, h, hl, 0, lane); });
+    ex([&](int lane) { phase_deblock_dir(w, pd, h, ht, 1, lane); });
+    ex([&](int lane) { phase_deblock_store(w, pd, g, a, lane); });
+}
+
+}  // namespace h264r

@@ -1,0 +1,195 @@
+"""ctypes binding of libh264r.so (the C ABI of include/h264r.h).
+
+There is no CPU fallback anywhere in this package: if the CUDA library is missing or no sm_100
+device is visible, creating an Engine raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import abi, build
+
+_lib = None
+
+
+class H264RError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("h264r error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib_path():
+    return os.path.join(build.LIB, "libh264r.so")
+
+
+def load_library():
+    """Loads (building if needed and possible) libh264r.so and declares the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        path = build.build_cuda()
+    L = ctypes.CDLL(path)
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    L.h264r_abi_version.restype = ci
+    L.h264r_last_error.restype = ctypes.c_char_p
+    L.h264r_last_error.argtypes = [vp]
+    L.h264r_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci, ctypes.c_uint32]
+    L.h264r_destroy.argtypes = [vp]
+    L.h264r_destroy.restype = None
+    L.h264r_host_alloc.argtypes = [vp, ctypes.c_size_t]
+    L.h264r_host_alloc.restype = vp
+    L.h264r_host_free.argtypes = [vp, vp]
+    L.h264r_host_free.restype = None
+    L.h264r_frame_begin.argtypes = [vp, ci, ctypes.POINTER(abi.PicParams)]
+    L.h264r_submit_mbs.argtypes = [vp, ci, ci, ci, vp, vp, vp]
+    L.h264r_frame_end.argtypes = [vp, ci]
+    L.h264r_flush.argtypes = [vp]
+    L.h264r_sync.argtypes = [vp]
+    L.h264r_read_planes.argtypes = [vp, ci, vp, ci, vp, vp, ci]
+    L.h264r_frame_digest.argtypes = [vp, ci, vp]
+    L.h264r_frame_digests.argtypes = [vp, vp, ci, vp]
+    L.h264r_range_excursions.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
+    L.h264r_excursion_map.argtypes = [vp, ci, vp]
+    L.h264r_residual_mbs.argtypes = [vp, ci, vp, vp, vp]
+    L.h264r_release.argtypes = [vp, ci]
+    L.h264r_last_flush_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ci)]
+    if L.h264r_abi_version() != abi.ABI_VERSION:
+        raise RuntimeError("libh264r.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+EXPORTS = [
+    "h264r_abi_version", "h264r_last_error", "h264r_create", "h264r_destroy", "h264r_host_alloc", "h264r_host_free",
+    "h264r_frame_begin", "h264r_submit_mbs", "h264r_frame_end", "h264r_flush", "h264r_sync", "h264r_read_planes",
+    "h264r_frame_digest", "h264r_frame_digests", "h264r_range_excursions", "h264r_excursion_map",
+    "h264r_residual_mbs", "h264r_release", "h264r_last_flush_stats",
+]
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return ctypes.c_void_p(a)
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class PinnedBuffer:
+    """numpy view over memory from h264r_host_alloc (page-locked)."""
+
+    def __init__(self, engine, dtype, shape):
+        self.engine = engine
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape))
+        self.nbytes = n * dtype.itemsize
+        self.ptr = engine.L.h264r_host_alloc(engine.ctx, self.nbytes)
+        if not self.ptr:
+            raise H264RError(abi.E_NOMEM, "pinned allocation of %d bytes failed" % self.nbytes)
+        buf = (ctypes.c_uint8 * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.engine.L.h264r_host_free(self.engine.ctx, self.ptr)
+            self.ptr = None
+            self.array = None
+
+
+class Engine:
+    """One reconstruction context on one GPU (h264r_ctx)."""
+
+    def __init__(self, w_mbs, h_mbs, max_frames, max_pending=None, flags=abi.REF_COMPAT, device=0):
+        self.L = load_library()
+        self.w_mbs, self.h_mbs, self.n_mbs = w_mbs, h_mbs, w_mbs * h_mbs
+        self.flags = flags
+        self.max_frames = max_frames
+        self.ctx = ctypes.c_void_p()
+        rc = self.L.h264r_create(ctypes.byref(self.ctx), device, w_mbs, h_mbs, max_frames, max_pending or max_frames, flags)
+        if rc != 0:
+            raise H264RError(rc, self.L.h264r_last_error(None).decode())
+
+    def close(self):
+        if self.ctx:
+            self.L.h264r_destroy(self.ctx)
+            self.ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise H264RError(rc, self.L.h264r_last_error(self.ctx).decode())
+
+    def pinned(self, dtype, shape):
+        return PinnedBuffer(self, dtype, shape)
+
+    def frame_begin(self, frame_id, pp):
+        self._check(self.L.h264r_frame_begin(self.ctx, frame_id, ctypes.byref(pp)))
+
+    def submit_mbs(self, frame_id, hdr, mv, coeff, first_mb=0, n_mbs=None):
+        n = n_mbs if n_mbs is not None else (hdr.shape[0] if hasattr(hdr, "shape") else self.n_mbs)
+        self._check(self.L.h264r_submit_mbs(self.ctx, frame_id, first_mb, n, _ptr(hdr), _ptr(mv), _ptr(coeff)))
+
+    def frame_end(self, frame_id):
+        self._check(self.L.h264r_frame_end(self.ctx, frame_id))
+
+    def submit_picture(self, frame_id, pp, hdr, mv, coeff):
+        hdr = np.ascontiguousarray(hdr)
+        coeff = np.ascontiguousarray(coeff, dtype=np.int16)
+        mv = np.ascontiguousarray(mv, dtype=np.int16) if mv is not None else None
+        self.frame_begin(frame_id, pp)
+        self.submit_mbs(frame_id, hdr, mv, coeff)
+        self.frame_end(frame_id)
+
+    def flush(self):
+        self._check(self.L.h264r_flush(self.ctx))
+
+    def sync(self):
+        self._check(self.L.h264r_sync(self.ctx))
+
+    def read_planes(self, frame_id):
+        W, H = self.w_mbs * 16, self.h_mbs * 16
+        y = np.empty((H, W), dtype=np.uint8)
+        u = np.empty((H // 2, W // 2), dtype=np.uint8)
+        v = np.empty((H // 2, W // 2), dtype=np.uint8)
+        self._check(self.L.h264r_read_planes(self.ctx, frame_id, _ptr(y), W, _ptr(u), _ptr(v), W // 2))
+        return y, u, v
+
+    def digests(self, frame_ids):
+        ids = np.ascontiguousarray(frame_ids, dtype=np.int32)
+        out = np.empty((ids.size, 16), dtype=np.uint8)
+        self._check(self.L.h264r_frame_digests(self.ctx, _ptr(ids), int(ids.size), _ptr(out)))
+        return out
+
+    def range_excursions(self):
+        c = ctypes.c_uint64()
+        self._check(self.L.h264r_range_excursions(self.ctx, ctypes.byref(c)))
+        return int(c.value)
+
+    def excursion_map(self, frame_id):
+        out = np.empty(self.n_mbs, dtype=np.uint8)
+        self._check(self.L.h264r_excursion_map(self.ctx, frame_id, _ptr(out)))
+        return out
+
+    def residual_mbs(self, hdr, coeff):
+        hdr = np.ascontiguousarray(hdr)
+        coeff = np.ascontiguousarray(coeff, dtype=np.int16)
+        n = hdr.shape[0]
+        out = np.empty((n, 384), dtype=np.int16)
+        self._check(self.L.h264r_residual_mbs(self.ctx, n, _ptr(hdr), _ptr(coeff), _ptr(out)))
+        return out[:, :256].reshape(n, 16, 16), out[:, 256:320].reshape(n, 8, 8), out[:, 320:].reshape(n, 8, 8)
+
+    def release(self, frame_id):
+        self._check(self.L.h264r_release(self.ctx, frame_id))
+
+    def last_flush_stats(self):
+        ms, n = ctypes.c_float(), ctypes.c_int()
+        self._check(self.L.h264r_last_flush_stats(self.ctx, ctypes.byref(ms), ctypes.byref(n)))
+        return float(ms.value), int(n.value)

@@ -222,6 +222,16 @@ int h264r_release(h264r_ctx* ctx, int frame_id);
  * context's stream), and the number of kernel launches it made. */
 int h264r_last_flush_stats(h264r_ctx* ctx, float* kernel_ms, int* launches);
 
+/* Measurement support.  h264r_set_profiling(1) makes h264r_flush() bracket every kernel launch with
+ * CUDA events on the context's stream; h264r_last_flush_kernel_ms() then returns, per kernel family
+ * (0 = inter K1+K3, 1 = intra K1+K2, 2 = deblock K4), the summed device time and the number of
+ * launches of the last flush.  h264r_mark()/h264r_elapsed_ms() record and compare user events
+ * (slot 0..3) on the same stream, e.g. around a submit..flush..digest sequence. */
+int h264r_set_profiling(h264r_ctx* ctx, int on);
+int h264r_last_flush_kernel_ms(h264r_ctx* ctx, float ms[3], int launches[3]);
+int h264r_mark(h264r_ctx* ctx, int slot);
+int h264r_elapsed_ms(h264r_ctx* ctx, int slot_from, int slot_to, float* ms);
+
 const char* h264r_last_error(h264r_ctx* ctx);
 int h264r_abi_version(void);
 

@@ -35,6 +35,11 @@ struct h264r_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_ctrl = nullptr;
     bool ctrl_in_flight = false;
+    bool profiling = false;
+    std::vector<cudaEvent_t> kev;           // profiling events: pairs per launch
+    std::vector<int> kev_family;
+    int kev_used = 0;
+    cudaEvent_t marks[4] = {nullptr, nullptr, nullptr, nullptr};
     // frame pool: per slot Y, U, V
     uint8_t* d_frames = nullptr;
     size_t y_bytes = 0, c_bytes = 0, frame_bytes = 0;
@@ -224,6 +229,8 @@ void h264r_destroy(h264r_ctx* c)
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_ctrl) cudaEventDestroy(c->ev_ctrl);
+    for (auto e : c->kev) cudaEventDestroy(e);
+    for (auto e : c->marks) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -360,6 +367,23 @@ int h264r_flush(h264r_ctx* ctx)
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->device);
+    ctx->kev_used = 0;
+    ctx->kev_family.clear();
+    auto prof_begin = [&](int family) {
+        if (!ctx->profiling) return;
+        if ((int)ctx->kev.size() < ctx->kev_used + 2) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            ctx->kev.push_back(a); ctx->kev.push_back(b);
+        }
+        ctx->kev_family.push_back(family);
+        cudaEventRecord(ctx->kev[ctx->kev_used], ctx->stream);
+    };
+    auto prof_end = [&]() {
+        if (!ctx->profiling) return;
+        cudaEventRecord(ctx->kev[ctx->kev_used + 1], ctx->stream);
+        ctx->kev_used += 2;
+    };
     for (int wv = 0; wv < n_waves; wv++) {
         const WaveLists& L = wl[wv];
         if (L.n_inter) {
@@ -367,17 +391,23 @@ int h264r_flush(h264r_ctx* ctx)
             long want = (total + INTER_WARPS - 1) / INTER_WARPS;
             long cap = (long)sm_count * 16 * 4;                   // 16 resident CTAs per SM, four passes
             int blocks = (int)(want < cap ? want : cap);
+            prof_begin(0);
             if (compat) k_inter<true><<<blocks, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, d_lists + L.inter_off, L.n_inter, ctx->g, ctx->d_exc_counter);
             else k_inter<false><<<blocks, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, d_lists + L.inter_off, L.n_inter, ctx->g, ctx->d_exc_counter);
+            prof_end();
             ctx->last_launches++;
         }
         if (L.n_intra) {
+            prof_begin(1);
             if (compat) k_intra<true><<<L.n_intra, WAVE_WARPS * 32, ctx->smem_wave, ctx->stream>>>(d_desc, d_lists + L.intra_off, ctx->g, ctx->d_diag, ctx->n_diag, ctx->d_exc_counter);
             else k_intra<false><<<L.n_intra, WAVE_WARPS * 32, ctx->smem_wave, ctx->stream>>>(d_desc, d_lists + L.intra_off, ctx->g, ctx->d_diag, ctx->n_diag, ctx->d_exc_counter);
+            prof_end();
             ctx->last_launches++;
         }
         if (L.n_deb) {
+            prof_begin(2);
             k_deblock<<<L.n_deb, WAVE_WARPS * 32, ctx->smem_wave, ctx->stream>>>(d_desc, d_lists + L.deb_off, ctx->g, ctx->d_diag, ctx->n_diag);
+            prof_end();
             ctx->last_launches++;
         }
     }
@@ -543,6 +573,47 @@ int h264r_last_flush_stats(h264r_ctx* ctx, float* kernel_ms, int* launches)
             CU(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
         }
     }
+    return H264R_OK;
+}
+
+int h264r_set_profiling(h264r_ctx* ctx, int on)
+{
+    if (!ctx) return H264R_E_INVAL;
+    ctx->profiling = on != 0;
+    return H264R_OK;
+}
+
+int h264r_last_flush_kernel_ms(h264r_ctx* ctx, float ms[3], int launches[3])
+{
+    if (!ctx || !ms || !launches) return H264R_E_INVAL;
+    for (int k = 0; k < 3; k++) { ms[k] = 0.f; launches[k] = 0; }
+    CU(cudaSetDevice(ctx->device));
+    for (int i = 0; i < ctx->kev_used; i += 2) {
+        float t = 0.f;
+        CU(cudaEventSynchronize(ctx->kev[i + 1]));
+        CU(cudaEventElapsedTime(&t, ctx->kev[i], ctx->kev[i + 1]));
+        int f = ctx->kev_family[i / 2];
+        ms[f] += t; launches[f]++;
+    }
+    return H264R_OK;
+}
+
+int h264r_mark(h264r_ctx* ctx, int slot)
+{
+    if (!ctx || slot < 0 || slot > 3) return H264R_E_INVAL;
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->marks[slot]) CU(cudaEventCreate(&ctx->marks[slot]));
+    CU(cudaEventRecord(ctx->marks[slot], ctx->stream));
+    return H264R_OK;
+}
+
+int h264r_elapsed_ms(h264r_ctx* ctx, int slot_from, int slot_to, float* ms)
+{
+    if (!ctx || !ms || slot_from < 0 || slot_from > 3 || slot_to < 0 || slot_to > 3 || !ctx->marks[slot_from] || !ctx->marks[slot_to])
+        return fail(ctx, H264R_E_INVAL, "elapsed_ms: bad slot");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->marks[slot_to]));
+    CU(cudaEventElapsedTime(ms, ctx->marks[slot_from], ctx->marks[slot_to]));
     return H264R_OK;
 }
 

@@ -56,6 +56,10 @@ def load_library():
     L.h264r_residual_mbs.argtypes = [vp, ci, vp, vp, vp]
     L.h264r_release.argtypes = [vp, ci]
     L.h264r_last_flush_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ci)]
+    L.h264r_set_profiling.argtypes = [vp, ci]
+    L.h264r_last_flush_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 3), ctypes.POINTER(ci * 3)]
+    L.h264r_mark.argtypes = [vp, ci]
+    L.h264r_elapsed_ms.argtypes = [vp, ci, ci, ctypes.POINTER(ctypes.c_float)]
     if L.h264r_abi_version() != abi.ABI_VERSION:
         raise RuntimeError("libh264r.so ABI version mismatch")
     _lib = L
@@ -66,7 +70,8 @@ EXPORTS = [
     "h264r_abi_version", "h264r_last_error", "h264r_create", "h264r_destroy", "h264r_host_alloc", "h264r_host_free",
     "h264r_frame_begin", "h264r_submit_mbs", "h264r_frame_end", "h264r_flush", "h264r_sync", "h264r_read_planes",
     "h264r_frame_digest", "h264r_frame_digests", "h264r_range_excursions", "h264r_excursion_map",
-    "h264r_residual_mbs", "h264r_release", "h264r_last_flush_stats",
+    "h264r_residual_mbs", "h264r_release", "h264r_last_flush_stats", "h264r_set_profiling",
+    "h264r_last_flush_kernel_ms", "h264r_mark", "h264r_elapsed_ms",
 ]
 
 
@@ -193,3 +198,19 @@ class Engine:
         ms, n = ctypes.c_float(), ctypes.c_int()
         self._check(self.L.h264r_last_flush_stats(self.ctx, ctypes.byref(ms), ctypes.byref(n)))
         return float(ms.value), int(n.value)
+
+    def set_profiling(self, on):
+        self._check(self.L.h264r_set_profiling(self.ctx, 1 if on else 0))
+
+    def last_flush_kernel_ms(self):
+        ms, n = (ctypes.c_float * 3)(), (ctypes.c_int * 3)()
+        self._check(self.L.h264r_last_flush_kernel_ms(self.ctx, ctypes.byref(ms), ctypes.byref(n)))
+        return list(ms), list(n)
+
+    def mark(self, slot):
+        self._check(self.L.h264r_mark(self.ctx, slot))
+
+    def elapsed_ms(self, a, b):
+        ms = ctypes.c_float()
+        self._check(self.L.h264r_elapsed_ms(self.ctx, a, b, ctypes.byref(ms)))
+        return float(ms.value)

@@ -112,3 +112,22 @@ def run_sequence(recon, w_mbs, h_mbs, flags, pics):
         refs = [(outs[pp.ref_list0[i]]["y"], outs[pp.ref_list0[i]]["u"], outs[pp.ref_list0[i]]["v"]) for i in range(pp.num_ref_idx_l0)]
         outs.append(recon(w_mbs, h_mbs, flags, pp, p["hdr"], p["mv"], p["coeff"], refs=refs))
     return outs
+
+
+def sanitize_with_oracle(w_mbs, h_mbs, gop, max_iter=40):
+    """REF_COMPAT content restriction for directly generated syntax: zero the residual of macroblocks
+    whose luma leaves [0,255] (oracle's excursion map), picture by picture in decode order."""
+    from videodecoder_b200 import workload
+    outs = []
+    for p in gop:
+        pp = p["pp"]
+        refs = [(outs[pp.ref_list0[i]]["y"], outs[pp.ref_list0[i]]["u"], outs[pp.ref_list0[i]]["v"]) for i in range(pp.num_ref_idx_l0)]
+        for _ in range(max_iter):
+            o = oracle.recon_picture(w_mbs, h_mbs, abi.REF_COMPAT, pp, p["hdr"], p["mv"], p["coeff"], refs=refs)
+            if o["excursions"] == 0:
+                break
+            workload.zero_mbs(p, np.flatnonzero(o["excursion_map"]))
+        else:
+            raise RuntimeError("no convergence")
+        outs.append(o)
+    return gop

@@ -1,0 +1,68 @@
+"""CPU: the kernel code (h264r_core.cuh / h264r_seq.cuh, run by the host SIMT emulator) against the
+oracle on directly generated syntax, in both modes, including what the reference lacks
+(8x8 transform, Intra8x8, 8x4 sub-partitions, chroma prediction / MC, deblocking)."""
+import numpy as np
+import pytest
+
+from common import *  # noqa: F401,F403
+import emul
+from videodecoder_b200 import workload
+
+
+@pytest.mark.parametrize("compat", [True, False])
+@pytest.mark.parametrize("seed,w,h", [(7, 8, 6), (8, 5, 3), (9, 1, 1), (10, 2, 7)])
+def test_gop(built, compat, seed, w, h):
+    rng = np.random.default_rng(seed)
+    cfg = workload.WorkloadConfig(compat=compat, num_ref=2, p_intra_in_p=0.12, mv_range=90,
+                                  p_t8x8=0.0 if compat else 0.5, p_i8x8=0.0 if compat else 0.5,
+                                  p_sub=(0.4, 0, 0.3, 0.3) if compat else (0.25, 0.25, 0.25, 0.25), qp=int(rng.integers(14, 44)))
+    gop = workload.make_gop(rng, w, h, 4, cfg)
+    flags = abi.REF_COMPAT if compat else 0
+    if compat:
+        sanitize_with_oracle(w, h, gop)     # outside [0,255] the reference's int samples have no 8-bit equivalent (D3)
+    want = run_sequence(oracle.recon_picture, w, h, flags, gop)
+    got = run_sequence(emul.recon_picture, w, h, flags, gop)
+    for i, (a, b) in enumerate(zip(want, got)):
+        for k in "yuv":
+            assert np.array_equal(a[k], b[k]), "picture %d plane %s" % (i, k)
+        assert a["excursions"] == b["excursions"]
+        assert oracle.digest(a["y"], a["u"], a["v"]) == emul.digest(b["y"], b["u"], b["v"])
+
+
+def test_deblock_offsets_and_qp_extremes(built):
+    """alpha/beta offsets and QPs at both ends of the tables"""
+    for qp, offs in ((2, (0, 6, 6)), (50, (0, -6, -6)), (30, (0, 3, -3))):
+        rng = np.random.default_rng(qp)
+        cfg = workload.WorkloadConfig(compat=False, qp=qp, p_intra_in_p=0.2, max_amp=40.0)
+        gop = workload.make_gop(rng, 6, 4, 3, cfg)
+        for p in gop:
+            p["pp"].disable_deblocking_filter_idc, p["pp"].slice_alpha_c0_offset_div2, p["pp"].slice_beta_offset_div2 = offs
+        want = run_sequence(oracle.recon_picture, 6, 4, 0, gop)
+        got = run_sequence(emul.recon_picture, 6, 4, 0, gop)
+        for a, b in zip(want, got):
+            for k in "yuv":
+                assert np.array_equal(a[k], b[k])
+
+
+def test_deblocking_disabled_equals_plain_reconstruction(built):
+    rng = np.random.default_rng(5)
+    cfg = workload.WorkloadConfig(compat=False)
+    gop = workload.make_gop(rng, 4, 4, 2, cfg)
+    for p in gop:
+        p["pp"].disable_deblocking_filter_idc = 1
+    a = run_sequence(emul.recon_picture, 4, 4, 0, gop)
+    for p in gop:
+        p["pp"].disable_deblocking_filter_idc = 0
+    b = run_sequence(emul.recon_picture, 4, 4, 0, gop)
+    assert not np.array_equal(a[0]["y"], b[0]["y"])      # the filter does something on this content
+
+
+def test_residual_linearity_property(built):
+    """with QP >= 24 dequantisation is linear: residual(2c) - 2 residual(c) stays within rounding."""
+    rng = np.random.default_rng(3)
+    cfg = workload.WorkloadConfig(compat=True, qp=30)
+    pic = workload.make_picture(rng, 6, 4, False, cfg)
+    pic["hdr"]["mb_class"] = abi.MB_I4x4
+    r1 = emul.residual(6, 4, abi.REF_COMPAT, pic["hdr"], pic["coeff"])[0].astype(np.int32)
+    r2 = emul.residual(6, 4, abi.REF_COMPAT, pic["hdr"], pic["coeff"] * 2)[0].astype(np.int32)
+    assert np.abs(r2 - 2 * r1).max() <= 1

@@ -319,9 +319,9 @@ int h264r_flush(h264r_ctx* ctx)
     // pictures whose frame_end has been called, in submission order
     std::vector<Pending*> run;
     for (auto& p : ctx->pending) if (p.ended) run.push_back(&p);
+    if (run.empty()) return H264R_OK;       // keeps the statistics of the last real flush
     ctx->last_launches = 0;
     ctx->timing_valid = false;
-    if (run.empty()) return H264R_OK;
     const bool compat = (ctx->flags & H264R_REF_COMPAT) != 0;
     // dependency waves
     int n_waves = 0;

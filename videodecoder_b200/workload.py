@@ -203,23 +203,25 @@ def zero_mbs(pic, addrs):
     pic["hdr"]["cbp"][addrs] = 0
 
 
-def sanitize(engine_factory, w_mbs, h_mbs, gop, max_iter=16):
+def sanitize(engine_factory, w_mbs, h_mbs, gop, max_iter=24):
     """Zeroes the residual of macroblocks flagged by the engine's excursion map until a REF_COMPAT
-    run of the GOP keeps every luma sample in [0,255].  Returns the number of iterations."""
+    run of the GOP keeps every luma sample in [0,255].  Pictures are settled one at a time in decode
+    order (a picture only depends on earlier ones), each with a few submit / inspect / zero rounds.
+    Returns the total number of rounds."""
     eng = engine_factory(len(gop))
+    rounds = 0
     try:
-        for it in range(max_iter):
-            for i, p in enumerate(gop):
-                pp = p["pp"]
-                eng.submit_picture(i, pp, p["hdr"], p["mv"], p["coeff"])
-            eng.sync()
-            total = eng.range_excursions()
-            if total == 0:
-                return it
-            for i, p in enumerate(gop):
+        for i, p in enumerate(gop):
+            for it in range(max_iter):
+                eng.submit_picture(i, p["pp"], p["hdr"], p["mv"], p["coeff"])
+                eng.sync()
+                rounds += 1
+                if eng.range_excursions() == 0:
+                    break
                 bad = np.flatnonzero(eng.excursion_map(i))
-                if bad.size:
-                    zero_mbs(p, bad)
-        raise RuntimeError("workload did not converge to the [0,255] range")
+                zero_mbs(p, bad)
+            else:
+                raise RuntimeError("picture %d did not converge to the [0,255] range" % i)
+        return rounds
     finally:
         eng.close()

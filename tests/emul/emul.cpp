@@ -69,7 +69,8 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
     PicDesc pd;
     fill_desc(pd, pp, hdr, mv, coeff, y, u, v, ref_y, ref_u, ref_v, exc_map);
     HostExec ex;
-    MbWork w;
+    WarpWork ww;
+    MbWork& w = ww.mb;
     unsigned long long exc = 0;
     const bool compat = (flags & H264R_REF_COMPAT) != 0;
     int n = w_mbs * h_mbs;
@@ -77,8 +78,7 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
     for (int a = 0; a < n; a++) {
         h264r_mb_hdr h = load_hdr(pd, a);
         if (is_intra(h.mb_class)) continue;
-        if (compat) seq_inter_mb<true>(ex, w, pd, g, h, a); else seq_inter_mb<false>(ex, w, pd, g, h, a);
-        exc += w.excursions;
+        exc += compat ? seq_inter_any<true>(ex, ww, pd, g, h, a) : seq_inter_any<false>(ex, ww, pd, g, h, a);
     }
     for (int a = 0; a < n; a++) {
         h264r_mb_hdr h = load_hdr(pd, a);

@@ -40,10 +40,10 @@ template <bool COMPAT>
 __global__ void __launch_bounds__(INTER_WARPS * 32) k_inter(const PicDesc* __restrict__ descs, const int* __restrict__ list,
                                                             int n_pics, Geometry g, uint32_t* excursions)
 {
-    __shared__ MbWork work[INTER_WARPS];
+    __shared__ WarpWork work[INTER_WARPS];
     int warp = threadIdx.x >> 5;
     WarpExec ex{(int)(threadIdx.x & 31)};
-    MbWork& w = work[warp];
+    WarpWork& w = work[warp];
     const int n_mbs = g.w_mbs * g.h_mbs;
     const long total = (long)n_pics * n_mbs;
     for (long i = (long)blockIdx.x * INTER_WARPS + warp; i < total; i += (long)gridDim.x * INTER_WARPS) {
@@ -51,8 +51,8 @@ __global__ void __launch_bounds__(INTER_WARPS * 32) k_inter(const PicDesc* __res
         const PicDesc& pd = descs[list[p]];
         h264r_mb_hdr h = load_hdr(pd, a);
         if (is_intra(h.mb_class)) continue;       // warp-uniform
-        seq_inter_mb<COMPAT>(ex, w, pd, g, h, a);
-        if (ex.lane == 0 && w.excursions) atomicAdd(excursions, w.excursions);
+        uint32_t exc = seq_inter_any<COMPAT>(ex, w, pd, g, h, a);
+        if (ex.lane == 0 && exc) atomicAdd(excursions, exc);
         __syncwarp();
     }
 }

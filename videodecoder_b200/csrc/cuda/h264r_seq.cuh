@@ -6,6 +6,7 @@
 // Keeping the sequences here means the CPU tests run exactly the phase order the kernels use.
 #pragma once
 #include "h264r_core.cuh"
+#include "h264r_mc.cuh"
 
 namespace h264r {
 
@@ -37,6 +38,26 @@ HD void seq_inter_mb(Exec& ex, MbWork& w, const PicDesc& pd, const Geometry& g, 
         phase_inter_chroma<COMPAT>(w, pd, g, h, a, lane);
     });
     ex([&](int lane) { phase_store(w, pd, g, a, lane); });
+}
+
+// working set of a warp: the generic phases and the fast inter path never run at the same time
+union WarpWork {
+    MbWork mb;
+    InterWork in;
+    HD WarpWork() {}
+};
+
+// K1 + K3 for any inter macroblock: fast path for the 4x4 transform, generic phases for the 8x8 transform.
+// Returns the number of luma excursions.
+template <bool COMPAT, class Exec>
+HD uint32_t seq_inter_any(Exec& ex, WarpWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a)
+{
+    if (!COMPAT && (h.flags & H264R_T8x8)) {
+        seq_inter_mb<COMPAT>(ex, w.mb, pd, g, h, a);
+        return w.mb.excursions;
+    }
+    seq_inter_mb_fast<COMPAT>(ex, w.in, pd, g, h, a);
+    return w.in.excursions;
 }
 
 // K1 + K2: one intra macroblock (its neighbours A, B, C, D are complete)

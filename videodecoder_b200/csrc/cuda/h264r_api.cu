@@ -53,8 +53,10 @@ struct h264r_ctx {
     uint8_t* h_ctrl = nullptr;
     uint8_t* d_ctrl = nullptr;
     size_t ctrl_bytes = 0;
-    int* d_diag = nullptr;
-    int n_diag = 0;
+    // wavefront hand-over words, zeroed at the start of every flush:
+    // progress words indexed by (position in the flush's picture lists, macroblock row): 3*max_pending*H, then 2*max_pending tickets
+    int* d_sync = nullptr;
+    size_t sync_ints = 0;
     std::vector<uint8_t> frame_state;
     std::vector<int> frame_wave;            // wave of a queued frame inside the current flush
     std::vector<Pending> pending;
@@ -62,7 +64,6 @@ struct h264r_ctx {
     bool timing_valid = false;
     int last_launches = 0;
     std::string err;
-    size_t smem_wave = 0;
 
     uint8_t* frame_y(int f) const { return d_frames + (size_t)f * frame_bytes; }
     uint8_t* frame_u(int f) const { return frame_y(f) + y_bytes; }
@@ -188,27 +189,8 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     CUC(cudaMallocHost(&c->h_ctrl, c->ctrl_bytes));
     CUC(cudaMemsetAsync(c->d_exc_counter, 0, 256, c->stream));
     CUC(cudaMemsetAsync(c->d_exc_maps, 0, (size_t)max_frames * c->n_mbs, c->stream));
-    // anti-diagonal table of the wavefront kernels: first ticket of every diagonal d = x + 2y
-    {
-        int W = w_mbs, H = h_mbs;
-        c->n_diag = (W - 1) + 2 * (H - 1) + 1;
-        std::vector<int> start(c->n_diag + 1, 0);
-        for (int d = 0; d < c->n_diag; d++) {
-            int ymin = d - (W - 1) <= 0 ? 0 : (d - (W - 1) + 1) >> 1;
-            int ymax = d / 2 < H - 1 ? d / 2 : H - 1;
-            start[d + 1] = start[d] + (ymax >= ymin ? ymax - ymin + 1 : 0);
-        }
-        CUC(cudaMalloc(&c->d_diag, sizeof(int) * (c->n_diag + 1)));
-        CUC(cudaMemcpy(c->d_diag, start.data(), sizeof(int) * (c->n_diag + 1), cudaMemcpyHostToDevice));
-    }
-    c->smem_wave = sizeof(MbWork) * WAVE_WARPS + align_up((size_t)c->n_mbs, 16);
-    if (c->smem_wave > (size_t)prop.sharedMemPerBlockOptin) {
-        fail(nullptr, 0, "h264r_create: picture too large for the wavefront kernels' shared-memory flags");
-        return cleanup(H264R_E_CAPACITY);
-    }
-    CUC(cudaFuncSetAttribute(k_intra<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_wave));
-    CUC(cudaFuncSetAttribute(k_intra<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_wave));
-    CUC(cudaFuncSetAttribute(k_deblock, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_wave));
+    c->sync_ints = (size_t)3 * max_pending * h_mbs + (size_t)2 * max_pending;
+    CUC(cudaMalloc(&c->d_sync, c->sync_ints * sizeof(int)));
     CUC(cudaStreamSynchronize(c->stream));
     c->frame_state.assign(max_frames, FRAME_FREE);
     c->frame_wave.assign(max_frames, -1);
@@ -224,7 +206,7 @@ void h264r_destroy(h264r_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_frames); cudaFree(c->d_digests); cudaFree(c->d_exc_maps); cudaFree(c->d_exc_counter);
-    cudaFree(c->d_syntax); cudaFree(c->d_ctrl); cudaFree(c->d_diag);
+    cudaFree(c->d_syntax); cudaFree(c->d_ctrl); cudaFree(c->d_sync);
     if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -364,6 +346,8 @@ int h264r_flush(h264r_ctx* ctx)
     CU(cudaMemcpyAsync(ctx->d_ctrl, ctx->h_ctrl, list_off + (size_t)pos * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaEventRecord(ctx->ev_ctrl, ctx->stream));
     ctx->ctrl_in_flight = true;
+    CU(cudaMemsetAsync(ctx->d_sync, 0, ctx->sync_ints * sizeof(int), ctx->stream));
+    int* tickets = ctx->d_sync + (size_t)3 * ctx->max_pending * ctx->g.h_mbs;
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -398,15 +382,19 @@ int h264r_flush(h264r_ctx* ctx)
             ctx->last_launches++;
         }
         if (L.n_intra) {
+            int rows = L.n_intra * ctx->g.h_mbs, blocks = (rows + ROW_WARPS - 1) / ROW_WARPS;
+            int* prog = ctx->d_sync + (size_t)L.intra_off * ctx->g.h_mbs;
             prof_begin(1);
-            if (compat) k_intra<true><<<L.n_intra, WAVE_WARPS * 32, ctx->smem_wave, ctx->stream>>>(d_desc, d_lists + L.intra_off, ctx->g, ctx->d_diag, ctx->n_diag, ctx->d_exc_counter);
-            else k_intra<false><<<L.n_intra, WAVE_WARPS * 32, ctx->smem_wave, ctx->stream>>>(d_desc, d_lists + L.intra_off, ctx->g, ctx->d_diag, ctx->n_diag, ctx->d_exc_counter);
+            if (compat) k_intra_rows<true><<<blocks, ROW_WARPS * 32, 0, ctx->stream>>>(d_desc, d_lists + L.intra_off, L.n_intra, ctx->g, prog, tickets + 2 * wv, ctx->d_exc_counter);
+            else k_intra_rows<false><<<blocks, ROW_WARPS * 32, 0, ctx->stream>>>(d_desc, d_lists + L.intra_off, L.n_intra, ctx->g, prog, tickets + 2 * wv, ctx->d_exc_counter);
             prof_end();
             ctx->last_launches++;
         }
         if (L.n_deb) {
+            int rows = L.n_deb * ctx->g.h_mbs, blocks = (rows + ROW_WARPS - 1) / ROW_WARPS;
+            int* prog = ctx->d_sync + (size_t)L.deb_off * ctx->g.h_mbs;
             prof_begin(2);
-            k_deblock<<<L.n_deb, WAVE_WARPS * 32, ctx->smem_wave, ctx->stream>>>(d_desc, d_lists + L.deb_off, ctx->g, ctx->d_diag, ctx->n_diag);
+            k_deblock_rows<<<blocks, ROW_WARPS * 32, 0, ctx->stream>>>(d_desc, d_lists + L.deb_off, L.n_deb, ctx->g, prog, tickets + 2 * wv + 1);
             prof_end();
             ctx->last_launches++;
         }

@@ -15,7 +15,6 @@ struct WarpExec {
 };
 
 constexpr int INTER_WARPS = 4;       // warps per CTA of the inter / residual kernels
-constexpr int WAVE_WARPS = 32;       // warps per CTA of the wavefront kernels (one CTA per picture)
 
 // ------------------------------------------------------------------------------------------------
 // K1 alone: dequant + inverse transform of n_mbs macroblocks -> int16 residual (384 per MB).
@@ -58,101 +57,125 @@ __global__ void __launch_bounds__(INTER_WARPS * 32) k_inter(const PicDesc* __res
 }
 
 // ------------------------------------------------------------------------------------------------
-// Wavefront scheduling shared by K2 (intra) and K4 (deblock): one CTA per picture.  Macroblocks
-// are handed to warps in anti-diagonal order (d = x + 2y, then y), so a macroblock's neighbours
-// A (d-1), B (d-2), C (d-1), D (d-3) were handed out earlier; a warp waits for them on per-MB
-// flags in shared memory.  All warps of a CTA are resident, and every dependency points to an
-// earlier ticket, so the spin-wait cannot deadlock.
+// Wavefront scheduling shared by K2 (intra) and K4 (deblock): one WARP per macroblock row.
+//
+// Macroblock (x, y) needs A (x-1, y), B (x, y-1), C (x+1, y-1), D (x-1, y-1).  A is the previous
+// macroblock of the same warp; B, C, D belong to the warp of row y-1, which publishes in
+// progress[y-1] how many leading macroblocks of its row are final.  The warp of row y may start
+// (x, y) once progress[y-1] >= min(x + 2, W): rows run two macroblocks behind each other, the
+// classic anti-diagonal wavefront, with up to min(H, W/2) rows of every picture of the wave in
+// flight at once and all pictures of the wave side by side (n_pics * H warps spread over all SMs).
+//
+// Row warps are numbered (picture, row) -> picture * H + row and handed to CTAs through an atomic
+// ticket, so the warp a row waits for always belongs to the same CTA or to a CTA that took an
+// earlier ticket, i.e. one that is already running: the spin-wait cannot deadlock whatever order
+// the hardware starts CTAs in.  The hand-over is st.release.gpu / ld.acquire.gpu on the progress
+// word; neighbouring samples are then read with ld.global.cg (L2) by the phases.
+//
+// In P pictures only the intra macroblocks take part (k_inter reconstructed the rest before this
+// launch): the warp finds them with a ballot over the row's mb_class bytes and publishes, after each
+// one, the position of the NEXT intra macroblock of its row (everything before it is final).
 // ------------------------------------------------------------------------------------------------
-// ticket -> macroblock address in anti-diagonal order
-__device__ __forceinline__ int wave_mb(int ticket, int W, int H, const int* __restrict__ diag_start, int n_diag)
+__device__ __forceinline__ int ld_acquire_gpu(const int* p)
 {
-    // binary search for the diagonal that contains the ticket
-    int lo = 0, hi = n_diag - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (diag_start[mid] <= ticket) lo = mid; else hi = mid - 1;
-    }
-    int d = lo, k = ticket - diag_start[d];
-    int ymin = d - (W - 1) <= 0 ? 0 : (d - (W - 1) + 1) >> 1;
-    int y = ymin + k, x = d - 2 * y;
-    return y * W + x;
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_progress(const int* p, int need)
+{
+    while (ld_acquire_gpu(p) < need) __nanosleep(20);
 }
 
-__device__ __forceinline__ void wait_flag(volatile uint8_t* f)
+constexpr int ROW_WARPS = 4;          // row warps per CTA of the wavefront kernels
+constexpr int ROW_MASK_WORDS = 16;    // intra bitmap of a row: up to 512 macroblocks (8192 samples) wide
+
+// Takes the CTA's ticket and returns the flat row index of the calling warp.
+__device__ __forceinline__ int row_ticket(int* ticket)
 {
-    while (!*f) __nanosleep(32);
+    __shared__ int s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1);
+    __syncthreads();
+    return s_ticket * ROW_WARPS + (int)(threadIdx.x >> 5);
 }
 
 template <bool COMPAT>
-__global__ void __launch_bounds__(WAVE_WARPS * 32) k_intra(const PicDesc* __restrict__ descs, const int* __restrict__ list,
-                                                          Geometry g, const int* __restrict__ diag_start, int n_diag,
-                                                          uint32_t* excursions)
+__global__ void __launch_bounds__(ROW_WARPS * 32) k_intra_rows(const PicDesc* __restrict__ descs, const int* __restrict__ list,
+                                                              int n_pics, Geometry g, int* progress, int* ticket,
+                                                              uint32_t* excursions)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    MbWork* work = reinterpret_cast<MbWork*>(smem);
-    volatile uint8_t* done = smem + sizeof(MbWork) * WAVE_WARPS;
-    __shared__ int ticket_counter;
-    const PicDesc& pd = descs[list[blockIdx.x]];
-    const int W = g.w_mbs, H = g.h_mbs, n_mbs = W * H;
-    // inter macroblocks were reconstructed by k_inter before this launch
-    for (int a = threadIdx.x; a < n_mbs; a += blockDim.x) done[a] = !is_intra(H264R_LDG(&pd.hdr[a].mb_class));
-    if (threadIdx.x == 0) ticket_counter = 0;
-    __syncthreads();
-    int warp = threadIdx.x >> 5;
+    __shared__ MbWork work[ROW_WARPS];
+    __shared__ uint32_t s_mask[ROW_WARPS][ROW_MASK_WORDS];
+    const int W = g.w_mbs, H = g.h_mbs;
+    const int flat = row_ticket(ticket);
+    if (flat >= n_pics * H) return;
+    const int warp = threadIdx.x >> 5;
     WarpExec ex{(int)(threadIdx.x & 31)};
+    const int p = flat / H, row = flat - p * H;
+    const PicDesc& pd = descs[list[p]];
+    int* prog = progress + (size_t)p * H;
     MbWork& w = work[warp];
-    for (;;) {
-        int t = 0;
-        if (ex.lane == 0) t = atomicAdd(&ticket_counter, 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= n_mbs) break;
-        int a = wave_mb(t, W, H, diag_start, n_diag);
-        if (done[a]) continue;                    // not an intra MB
-        h264r_mb_hdr h = load_hdr(pd, a);
-        if (h.flags & H264R_AVAIL_A) wait_flag(&done[a - 1]);
-        if (h.flags & H264R_AVAIL_B) wait_flag(&done[a - W]);
-        if (h.flags & H264R_AVAIL_C) wait_flag(&done[a - W + 1]);
-        if (h.flags & H264R_AVAIL_D) wait_flag(&done[a - W - 1]);
-        __threadfence();
-        seq_intra_mb<COMPAT>(ex, w, pd, g, h, a);
-        if (ex.lane == 0 && w.excursions) atomicAdd(excursions, w.excursions);
-        __threadfence();                          // samples visible before the flag
-        __syncwarp();
-        if (ex.lane == 0) done[a] = 1;
+    uint32_t* mask = s_mask[warp];
+    // bitmap of the intra macroblocks of this row
+    const int n_words = (W + 31) >> 5;
+    for (int k = 0; k < n_words; k++) {
+        int x = k * 32 + ex.lane;
+        bool intra = x < W && is_intra(H264R_LDG(&pd.hdr[row * W + x].mb_class));
+        uint32_t m = __ballot_sync(0xffffffffu, intra);
+        if (ex.lane == 0) mask[k] = m;
     }
+    __syncwarp();
+    auto next_intra = [&](int from) -> int {      // first intra macroblock at x >= from, or W
+        for (int k = from >> 5; k < n_words; k++) {
+            uint32_t m = mask[k];
+            if (k == (from >> 5)) m &= 0xffffffffu << (from & 31);
+            if (m) return k * 32 + __ffs(m) - 1;
+        }
+        return W;
+    };
+    int x = next_intra(0);
+    if (ex.lane == 0 && x > 0) st_release_gpu(&prog[row], x);
+    uint32_t exc = 0;
+    while (x < W) {
+        const int a = row * W + x;
+        h264r_mb_hdr h = load_hdr(pd, a);
+        if (row > 0) {
+            int need = x + 2 < W ? x + 2 : W;
+            wait_progress(&prog[row - 1], need);
+        }
+        seq_intra_mb<COMPAT>(ex, w, pd, g, h, a);
+        exc += w.excursions;
+        x = next_intra(x + 1);
+        // ex() ended with __syncwarp(): every lane's stores precede lane 0's release
+        if (ex.lane == 0) st_release_gpu(&prog[row], x);
+    }
+    if (ex.lane == 0 && exc) atomicAdd(excursions, exc);
 }
 
-__global__ void __launch_bounds__(WAVE_WARPS * 32) k_deblock(const PicDesc* __restrict__ descs, const int* __restrict__ list,
-                                                            Geometry g, const int* __restrict__ diag_start, int n_diag)
+__global__ void __launch_bounds__(ROW_WARPS * 32) k_deblock_rows(const PicDesc* __restrict__ descs, const int* __restrict__ list,
+                                                                int n_pics, Geometry g, int* progress, int* ticket)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    MbWork* work = reinterpret_cast<MbWork*>(smem);
-    volatile uint8_t* done = smem + sizeof(MbWork) * WAVE_WARPS;
-    __shared__ int ticket_counter;
-    const PicDesc& pd = descs[list[blockIdx.x]];
-    const int W = g.w_mbs, H = g.h_mbs, n_mbs = W * H;
-    for (int a = threadIdx.x; a < n_mbs; a += blockDim.x) done[a] = 0;
-    if (threadIdx.x == 0) ticket_counter = 0;
-    __syncthreads();
-    int warp = threadIdx.x >> 5;
+    __shared__ MbWork work[ROW_WARPS];
+    const int W = g.w_mbs, H = g.h_mbs;
+    const int flat = row_ticket(ticket);
+    if (flat >= n_pics * H) return;
+    const int warp = threadIdx.x >> 5;
     WarpExec ex{(int)(threadIdx.x & 31)};
+    const int p = flat / H, row = flat - p * H;
+    const PicDesc& pd = descs[list[p]];
+    int* prog = progress + (size_t)p * H;
     MbWork& w = work[warp];
-    for (;;) {
-        int t = 0;
-        if (ex.lane == 0) t = atomicAdd(&ticket_counter, 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= n_mbs) break;
-        int a = wave_mb(t, W, H, diag_start, n_diag);
-        int mbx = a % W, mby = a / W;
-        if (mbx > 0) wait_flag(&done[a - 1]);
-        if (mby > 0) wait_flag(&done[a - W]);
-        if (mby > 0 && mbx < W - 1) wait_flag(&done[a - W + 1]);
-        __threadfence();
-        seq_deblock_mb(ex, w, pd, g, a);
-        __threadfence();
-        __syncwarp();
-        if (ex.lane == 0) done[a] = 1;
+    for (int x = 0; x < W; x++) {
+        if (row > 0) {
+            int need = x + 2 < W ? x + 2 : W;
+            wait_progress(&prog[row - 1], need);
+        }
+        seq_deblock_mb(ex, w, pd, g, row * W + x);
+        if (ex.lane == 0) st_release_gpu(&prog[row], x + 1);
     }
 }
 

@@ -293,8 +293,8 @@ def main():
     eng.set_profiling(True)
     barrier()
     kern_ms = 0.0
-    fam_ms = np.zeros(3)
-    fam_n = np.zeros(3, dtype=np.int64)
+    fam_ms = np.zeros(4)
+    fam_n = np.zeros(4, dtype=np.int64)
     for _ in range(args.steps):
         submit_all()
         eng.mark(2)
@@ -367,7 +367,7 @@ def main():
             "e2e": {"value": frames_per_step * args.steps / (e2e_ms / 1000.0), "unit": "frames/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": G * F * 16},
             "gpu_launches": int(args.steps * (2 * flush_launches + 1)),
-            "kernel_ms_per_step": {"inter": fam_ms[0] / args.steps, "intra": fam_ms[1] / args.steps, "deblock": fam_ms[2] / args.steps},
+            "kernel_ms_per_step": {"inter": fam_ms[0] / args.steps, "intra": fam_ms[1] / args.steps, "deblock": fam_ms[2] / args.steps, "pad": fam_ms[3] / args.steps},
             "roofline": {"bound": "hbm", "kernel": names[fam], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch,
                          "avg_launch_ms": sec_per_launch * 1000.0},

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define H264R_ABI_VERSION 1
+#define H264R_ABI_VERSION 2
 
 /* ---- status codes ---------------------------------------------------------------------- */
 #define H264R_OK            0
@@ -224,11 +224,12 @@ int h264r_last_flush_stats(h264r_ctx* ctx, float* kernel_ms, int* launches);
 
 /* Measurement support.  h264r_set_profiling(1) makes h264r_flush() bracket every kernel launch with
  * CUDA events on the context's stream; h264r_last_flush_kernel_ms() then returns, per kernel family
- * (0 = inter K1+K3, 1 = intra K1+K2, 2 = deblock K4), the summed device time and the number of
- * launches of the last flush.  h264r_mark()/h264r_elapsed_ms() record and compare user events
+ * (0 = inter K1+K3, 1 = intra K1+K2, 2 = deblock K4, 3 = border replication), the summed device time
+ * and the number of launches of the last flush.  h264r_mark()/h264r_elapsed_ms() record and compare user events
  * (slot 0..3) on the same stream, e.g. around a submit..flush..digest sequence. */
 int h264r_set_profiling(h264r_ctx* ctx, int on);
-int h264r_last_flush_kernel_ms(h264r_ctx* ctx, float ms[3], int launches[3]);
+#define H264R_KERNEL_FAMILIES 4
+int h264r_last_flush_kernel_ms(h264r_ctx* ctx, float ms[H264R_KERNEL_FAMILIES], int launches[H264R_KERNEL_FAMILIES]);
 int h264r_mark(h264r_ctx* ctx, int slot);
 int h264r_elapsed_ms(h264r_ctx* ctx, int slot_from, int slot_to, float* ms);
 

@@ -59,15 +59,59 @@ void h264emul_residual(int w_mbs, int h_mbs, unsigned flags, const h264r_mb_hdr*
     }
 }
 
-// whole picture; planes have pitch w_mbs*16 / w_mbs*8.  Returns the number of luma excursions.
+// A frame of the emulated frame pool: planes with the replicated border of the device frame pool.
+struct PaddedFrame {
+    int W, H, py, pc;
+    std::vector<uint8_t> buf_y, buf_u, buf_v;
+    PaddedFrame(int W_, int H_) : W(W_), H(H_), py(W_ + 2 * PAD_X), pc(W_ / 2 + 2 * PAD_XC),
+        buf_y((size_t)py * (H_ + 2 * PAD_Y)), buf_u((size_t)pc * (H_ / 2 + 2 * PAD_YC)), buf_v(buf_u.size()) {}
+    uint8_t* y() { return buf_y.data() + (size_t)PAD_Y * py + PAD_X; }
+    uint8_t* u() { return buf_u.data() + (size_t)PAD_YC * pc + PAD_XC; }
+    uint8_t* v() { return buf_v.data() + (size_t)PAD_YC * pc + PAD_XC; }
+    void load(const uint8_t* sy, const uint8_t* su, const uint8_t* sv)
+    {
+        for (int r = 0; r < H; r++) memcpy(y() + (size_t)r * py, sy + (size_t)r * W, W);
+        for (int r = 0; r < H / 2; r++) { memcpy(u() + (size_t)r * pc, su + (size_t)r * (W / 2), W / 2); memcpy(v() + (size_t)r * pc, sv + (size_t)r * (W / 2), W / 2); }
+    }
+    void store(uint8_t* dy, uint8_t* du, uint8_t* dv)
+    {
+        for (int r = 0; r < H; r++) memcpy(dy + (size_t)r * W, y() + (size_t)r * py, W);
+        for (int r = 0; r < H / 2; r++) { memcpy(du + (size_t)r * (W / 2), u() + (size_t)r * pc, W / 2); memcpy(dv + (size_t)r * (W / 2), v() + (size_t)r * pc, W / 2); }
+    }
+    void pad()      // what k_pad does on the device
+    {
+        for (int r = -PAD_Y; r < H + PAD_Y; r++) for (int lane = 0; lane < 32; lane++) pad_row_phase(y(), py, W, H, PAD_X, PAD_Y, r, lane);
+        for (int r = -PAD_YC; r < H / 2 + PAD_YC; r++)
+            for (int lane = 0; lane < 32; lane++) {
+                pad_row_phase(u(), pc, W / 2, H / 2, PAD_XC, PAD_YC, r, lane);
+                pad_row_phase(v(), pc, W / 2, H / 2, PAD_XC, PAD_YC, r, lane);
+            }
+    }
+};
+
+// whole picture; caller's planes have pitch w_mbs*16 / w_mbs*8 (copied into / out of padded frames).
+// Returns the number of luma excursions.
 unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, const h264r_pic_params* pp,
                                           const h264r_mb_hdr* hdr, const int16_t* mv, const int16_t* coeff,
                                           uint8_t* y, uint8_t* u, uint8_t* v, const uint8_t* const* ref_y,
                                           const uint8_t* const* ref_u, const uint8_t* const* ref_v, uint8_t* exc_map)
 {
-    Geometry g{w_mbs, h_mbs, w_mbs * 16, w_mbs * 8};
+    const int W = w_mbs * 16, H = h_mbs * 16;
+    PaddedFrame cur(W, H);
+    std::vector<PaddedFrame> refs;
+    const uint8_t* ry[H264R_MAX_REFS] = {nullptr}; const uint8_t* ru[H264R_MAX_REFS] = {nullptr}; const uint8_t* rv[H264R_MAX_REFS] = {nullptr};
+    refs.reserve(H264R_MAX_REFS);
+    for (int i = 0; i < H264R_MAX_REFS; i++) {
+        if (!ref_y || !ref_y[i]) continue;
+        refs.emplace_back(W, H);
+        refs.back().load(ref_y[i], ref_u[i], ref_v[i]);
+        refs.back().pad();
+        ry[i] = refs.back().y(); ru[i] = refs.back().u(); rv[i] = refs.back().v();
+    }
+    for (int i = 0; i < H264R_MAX_REFS; i++) if (!ry[i] && ry[0]) { ry[i] = ry[0]; ru[i] = ru[0]; rv[i] = rv[0]; }
+    Geometry g{w_mbs, h_mbs, cur.py, cur.pc};
     PicDesc pd;
-    fill_desc(pd, pp, hdr, mv, coeff, y, u, v, ref_y, ref_u, ref_v, exc_map);
+    fill_desc(pd, pp, hdr, mv, coeff, cur.y(), cur.u(), cur.v(), ry, ru, rv, exc_map);
     HostExec ex;
     WarpWork ww;
     MbWork& w = ww.mb;
@@ -88,6 +132,7 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
     }
     if (!compat && pd.deblock_on)
         for (int a = 0; a < n; a++) seq_deblock_mb(ex, w, pd, g, a);
+    cur.store(y, u, v);
     return exc;
 }
 

@@ -3,7 +3,7 @@ import ctypes
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 REF_COMPAT = 0x1
 
 MB_I4x4, MB_I8x8, MB_I16x16 = 0, 1, 2

@@ -54,7 +54,7 @@ struct h264r_ctx {
     uint8_t* d_ctrl = nullptr;
     size_t ctrl_bytes = 0;
     // wavefront hand-over words, zeroed at the start of every flush:
-    // progress words indexed by (position in the flush's picture lists, macroblock row): 3*max_pending*H, then 2*max_pending tickets
+    // progress words indexed by (position in the flush's picture lists, macroblock row): 4*max_pending*H, then 2*max_pending tickets
     int* d_sync = nullptr;
     size_t sync_ints = 0;
     std::vector<uint8_t> frame_state;
@@ -65,8 +65,9 @@ struct h264r_ctx {
     int last_launches = 0;
     std::string err;
 
-    uint8_t* frame_y(int f) const { return d_frames + (size_t)f * frame_bytes; }
-    uint8_t* frame_u(int f) const { return frame_y(f) + y_bytes; }
+    // sample (0,0) of each plane; every plane is surrounded by a replicated border (PAD_* of h264r_mc.cuh)
+    uint8_t* frame_y(int f) const { return d_frames + (size_t)f * frame_bytes + (size_t)PAD_Y * g.pitch_y + PAD_X; }
+    uint8_t* frame_u(int f) const { return d_frames + (size_t)f * frame_bytes + y_bytes + (size_t)PAD_YC * g.pitch_c + PAD_XC; }
     uint8_t* frame_v(int f) const { return frame_u(f) + c_bytes; }
     uint8_t* slot_ptr(int s) const { return d_syntax + (size_t)s * slot_bytes; }
 };
@@ -156,12 +157,12 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     c->device = device;
     c->flags = flags;
     c->g.w_mbs = w_mbs; c->g.h_mbs = h_mbs;
-    c->g.pitch_y = (int)align_up((size_t)w_mbs * 16, 128);
-    c->g.pitch_c = (int)align_up((size_t)w_mbs * 8, 128);
+    c->g.pitch_y = (int)align_up((size_t)w_mbs * 16 + 2 * PAD_X, 128);
+    c->g.pitch_c = (int)align_up((size_t)w_mbs * 8 + 2 * PAD_XC, 128);
     c->n_mbs = w_mbs * h_mbs;
     c->max_frames = max_frames; c->max_pending = max_pending;
-    c->y_bytes = (size_t)c->g.pitch_y * h_mbs * 16;
-    c->c_bytes = (size_t)c->g.pitch_c * h_mbs * 8;
+    c->y_bytes = (size_t)c->g.pitch_y * (h_mbs * 16 + 2 * PAD_Y);
+    c->c_bytes = (size_t)c->g.pitch_c * (h_mbs * 8 + 2 * PAD_YC);
     c->frame_bytes = align_up(c->y_bytes + 2 * c->c_bytes, 256);
     c->off_mv = align_up((size_t)c->n_mbs * sizeof(h264r_mb_hdr), 256);
     c->off_coeff = c->off_mv + align_up((size_t)c->n_mbs * H264R_MV_PER_MB * 2, 256);
@@ -189,7 +190,7 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     CUC(cudaMallocHost(&c->h_ctrl, c->ctrl_bytes));
     CUC(cudaMemsetAsync(c->d_exc_counter, 0, 256, c->stream));
     CUC(cudaMemsetAsync(c->d_exc_maps, 0, (size_t)max_frames * c->n_mbs, c->stream));
-    c->sync_ints = (size_t)3 * max_pending * h_mbs + (size_t)2 * max_pending;
+    c->sync_ints = (size_t)4 * max_pending * h_mbs + (size_t)2 * max_pending;
     CUC(cudaMalloc(&c->d_sync, c->sync_ints * sizeof(int)));
     CUC(cudaStreamSynchronize(c->stream));
     c->frame_state.assign(max_frames, FRAME_FREE);
@@ -329,7 +330,7 @@ int h264r_flush(h264r_ctx* ctx)
         ctx->ctrl_in_flight = false;
     }
     for (int i = 0; i < n; i++) fill_desc(ctx, *run[i], h_desc[i]);
-    struct WaveLists { int inter_off, n_inter, intra_off, n_intra, deb_off, n_deb; };
+    struct WaveLists { int inter_off, n_inter, intra_off, n_intra, deb_off, n_deb, all_off, n_all; };
     std::vector<WaveLists> wl(n_waves);
     int pos = 0;
     for (int wv = 0; wv < n_waves; wv++) {
@@ -342,12 +343,15 @@ int h264r_flush(h264r_ctx* ctx)
         wl[wv].deb_off = pos;
         for (int i = 0; i < n; i++) if (run[i]->wave == wv && h_desc[i].deblock_on) h_lists[pos++] = i;
         wl[wv].n_deb = pos - wl[wv].deb_off;
+        wl[wv].all_off = pos;
+        for (int i = 0; i < n; i++) if (run[i]->wave == wv) h_lists[pos++] = i;
+        wl[wv].n_all = pos - wl[wv].all_off;
     }
     CU(cudaMemcpyAsync(ctx->d_ctrl, ctx->h_ctrl, list_off + (size_t)pos * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaEventRecord(ctx->ev_ctrl, ctx->stream));
     ctx->ctrl_in_flight = true;
     CU(cudaMemsetAsync(ctx->d_sync, 0, ctx->sync_ints * sizeof(int), ctx->stream));
-    int* tickets = ctx->d_sync + (size_t)3 * ctx->max_pending * ctx->g.h_mbs;
+    int* tickets = ctx->d_sync + (size_t)4 * ctx->max_pending * ctx->g.h_mbs;
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -395,6 +399,17 @@ int h264r_flush(h264r_ctx* ctx)
             int* prog = ctx->d_sync + (size_t)L.deb_off * ctx->g.h_mbs;
             prof_begin(2);
             k_deblock_rows<<<blocks, ROW_WARPS * 32, 0, ctx->stream>>>(d_desc, d_lists + L.deb_off, L.n_deb, ctx->g, prog, tickets + 2 * wv + 1);
+            prof_end();
+            ctx->last_launches++;
+        }
+        {
+            // border replication of the finished pictures of this wave
+            int rows = ctx->g.h_mbs * 16 + 2 * PAD_Y + (compat ? 0 : 2 * (ctx->g.h_mbs * 8 + 2 * PAD_YC));
+            long warps = (long)L.n_all * rows;
+            long cap = (long)sm_count * 16;
+            int blocks = (int)((warps + 3) / 4 < cap ? (warps + 3) / 4 : cap);
+            prof_begin(3);
+            k_pad<<<blocks, 128, 0, ctx->stream>>>(d_desc, d_lists + L.all_off, L.n_all, ctx->g, compat ? 0 : 1);
             prof_end();
             ctx->last_launches++;
         }
@@ -571,10 +586,10 @@ int h264r_set_profiling(h264r_ctx* ctx, int on)
     return H264R_OK;
 }
 
-int h264r_last_flush_kernel_ms(h264r_ctx* ctx, float ms[3], int launches[3])
+int h264r_last_flush_kernel_ms(h264r_ctx* ctx, float ms[H264R_KERNEL_FAMILIES], int launches[H264R_KERNEL_FAMILIES])
 {
     if (!ctx || !ms || !launches) return H264R_E_INVAL;
-    for (int k = 0; k < 3; k++) { ms[k] = 0.f; launches[k] = 0; }
+    for (int k = 0; k < H264R_KERNEL_FAMILIES; k++) { ms[k] = 0.f; launches[k] = 0; }
     CU(cudaSetDevice(ctx->device));
     for (int i = 0; i < ctx->kev_used; i += 2) {
         float t = 0.f;

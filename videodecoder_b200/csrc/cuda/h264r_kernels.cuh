@@ -180,6 +180,26 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_deblock_rows(const PicDesc* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Border replication of finished pictures (so that later P pictures can stage reference windows without
+// coordinate clamps).  One warp per padded row; luma always, chroma when `chroma` (spec mode: the
+// reference has no chroma motion compensation, D4).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_pad(const PicDesc* __restrict__ descs, const int* __restrict__ list, int n_pics, Geometry g, int chroma)
+{
+    const int Wl = g.w_mbs * 16, Hl = g.h_mbs * 16, Wc = Wl >> 1, Hc = Hl >> 1;
+    const int rows_l = Hl + 2 * PAD_Y, rows_c = chroma ? Hc + 2 * PAD_YC : 0, rows = rows_l + 2 * rows_c;
+    const int lane = threadIdx.x & 31;
+    const long total = (long)n_pics * rows;
+    for (long i = (long)blockIdx.x * 4 + (threadIdx.x >> 5); i < total; i += (long)gridDim.x * 4) {
+        int p = (int)(i / rows), r = (int)(i - (long)p * rows);
+        const PicDesc& pd = descs[list[p]];
+        if (r < rows_l) pad_row_phase(pd.y, g.pitch_y, Wl, Hl, PAD_X, PAD_Y, r - PAD_Y, lane);
+        else if (r < rows_l + rows_c) pad_row_phase(pd.u, g.pitch_c, Wc, Hc, PAD_XC, PAD_YC, r - rows_l - PAD_YC, lane);
+        else pad_row_phase(pd.v, g.pitch_c, Wc, Hc, PAD_XC, PAD_YC, r - rows_l - rows_c - PAD_YC, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K5: frame digest.  One CTA per picture; every thread folds 4-sample words, block reduction, the
 // CTA writes the four sums (no zeroing pass, no atomics on global memory).
 // ------------------------------------------------------------------------------------------------

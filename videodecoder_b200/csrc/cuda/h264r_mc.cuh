@@ -1,25 +1,32 @@
-// h264r_mc.cuh -- fast path of K1+K3 (inter macroblocks).
+// h264r_mc.cuh -- K1+K3 for inter macroblocks (4x4 transform): residual in registers, reference
+// windows staged once in shared memory, quarter-sample interpolation with dp4a on packed bytes.
 //
-// Same results as phase_residual / phase_inter_luma / phase_inter_chroma of h264r_core.cuh (which
-// stay as the straightforward statement of the arithmetic and as the fallback for the 8x8
-// transform), restructured for instruction count:
-//   * residual: lanes 0..23 own one 4x4 block each and keep it in registers; blocks whose
-//     coded_block_pattern bit is clear are neither loaded nor transformed (the reference zero-fills
-//     them: h264/residual.cpp:44-46), a macroblock with cbp == 0 skips the phase altogether;
-//   * motion compensation: the reference window of every prediction block is staged ONCE in shared
-//     memory with the coordinate clamp applied while staging (reference h264/macroblock.cpp:828-830),
-//     then every lane produces 8 samples (a row segment) with dp4a: each 6-tap sum is two dp4a on
-//     byte groups obtained with funnel shifts, and every quantity of the 16 quarter-sample positions,
-//     including the reference's own tap pattern for j and s (D6/D7), is a per-row dp4a accumulation;
-//   * prediction block size is chosen per macroblock from the 16 per-4x4 vectors: 16x16 when they
-//     are all equal, 8x8 when every quadrant is uniform, 4x4 otherwise.
-// Every function is a per-lane phase (no shuffles), so the host emulator runs this code too.
+// Same results as phase_residual / phase_inter_luma / phase_inter_chroma of h264r_core.cuh (kept as
+// the plain statement of the arithmetic and as the path for the 8x8 transform); this file is the
+// throughput version:
+//   * reference pictures carry a replicated border (PAD_* below, written by k_pad), so the
+//     coordinate clamp of the reference (h264/macroblock.cpp:828-830, = ITU-T H.264 eq. 8-239..8-240)
+//     becomes a clamp of the BLOCK position and window staging is plain word loads;
+//   * the window of every prediction block is staged once (16x16: one 22x24-byte window; uniform 8x8
+//     quadrants: four 14x16; otherwise sixteen 10x12), already shifted so that consumers read
+//     aligned words;
+//   * every lane produces a 4x2 patch (block lane>>1, rows 2*(lane&1)..+1) from 8 window rows: per
+//     row three LDS + six PRMT give the eight byte groups A_k = x[k-2..k+1], and every quantity of
+//     the 16 quarter-sample positions is a dp4a accumulation over those groups -- including the
+//     reference's own tap pattern for j and s (D6/D7), see the derivation at mc_accum;
+//   * no per-lane branches: lanes that do not need a quantity compute it anyway and drop it through
+//     select masks; what NO lane of the warp needs is skipped by choosing one of three instantiations
+//     (full-sample only / no centre position j / everything) with a warp-uniform switch;
+//   * rounding, Clip1, the (P+Q+1)>>1 averages, the residual add and the range check run on packed
+//     bytes / 16-bit pairs.
+// Every function is a per-lane phase (cross-lane traffic goes through shared memory), so the host
+// emulator of the CPU test-suite runs this code too.
 #pragma once
 #include "h264r_core.cuh"
 
 namespace h264r {
 
-// ---- intrinsics with host emulation ----------------------------------------------------------------
+// ---- intrinsics with host emulation -------------------------------------------------------------------
 HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int shift_bits)
 {
 #if defined(__CUDA_ARCH__)
@@ -41,17 +48,95 @@ HD int dp4a_us(uint32_t a, uint32_t b, int c)
     return c;
 #endif
 }
+// byte permute: result byte i = byte (sel nibble i) of the 8-byte pool {a (0..3), b (4..7)}; selectors 0..7 only
+HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    uint64_t pool = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((pool >> (8 * ((sel >> (4 * i)) & 7))) & 255u) << (8 * i);
+    return r;
+#endif
+}
+// bytes {sat8(v0), sat8(v1), sat8(v2), sat8(v3)}, sat8 = clamp to [0,255]
+HD uint32_t pack_sat_u8(int v0, int v1, int v2, int v3)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t hi, r;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(v3), "r"(v2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v1), "r"(v0), "r"(hi));
+    return r;
+#else
+    return (uint32_t)clip1(v0) | ((uint32_t)clip1(v1) << 8) | ((uint32_t)clip1(v2) << 16) | ((uint32_t)clip1(v3) << 24);
+#endif
+}
+// per byte (a + b + 1) >> 1
+HD uint32_t avg_u8x4(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) & 0xfefefefeu) >> 1); }
+// per 16-bit half a + b (wrapping)
+HD uint32_t add_s16x2(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("add.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+#else
+    return ((a + b) & 0xffffu) | (((a >> 16) + (b >> 16)) << 16);
+#endif
+}
+// per 16-bit half clamp to [0,255]
+HD uint32_t clip255_s16x2(uint32_t a)
+{
+#if defined(__CUDA_ARCH__)
+    return __vimin_s16x2_relu(a, 0x00ff00ffu);
+#else
+    int lo = (int16_t)(a & 0xffff), hi = (int16_t)(a >> 16);
+    return (uint32_t)clip1(lo) | ((uint32_t)clip1(hi) << 16);
+#endif
+}
 HD constexpr uint32_t taps4(int a, int b, int c, int d)
 {
     return (uint32_t)(a & 255) | ((uint32_t)(b & 255) << 8) | ((uint32_t)(c & 255) << 16) | ((uint32_t)(d & 255) << 24);
 }
 
-// Working set of the fast inter path (one per warp)
+// Replicated border around every plane of the frame pool (samples).  Luma: a 16x16 block clamped to
+// [-(16+3), W+2] x [-(16+3), H+3] reads columns -21..W+20 (+ up to 7 bytes of word alignment) and rows
+// -22..H+21.  Chroma (spec mode): coordinates are clamped to [-8, Wc+7] x [-8, Hc+7].
+constexpr int PAD_X = 32, PAD_Y = 24, PAD_XC = 16, PAD_YC = 12;
+
+// Border replication of one row r (-pady <= r < H + pady) of a plane whose sample (0,0) is at org.
+// Rows inside the picture get their two side borders, rows above / below are copies of the (extended)
+// first / last row.  Lanes stride over 4-byte words.
+HD void pad_row_phase(uint8_t* org, int pitch, int W, int H, int padx, int pady, int r, int lane)
+{
+    (void)pady;
+    const int rs = clip3(0, H - 1, r);
+    const uint8_t* src = org + (ptrdiff_t)rs * pitch;
+    uint8_t* dst = org + (ptrdiff_t)r * pitch;
+    const uint32_t left = (uint32_t)H264R_LDCG(src) * 0x01010101u, right = (uint32_t)H264R_LDCG(src + W - 1) * 0x01010101u;
+    const int pw = padx >> 2;
+    if (r >= 0 && r < H) {
+        for (int i = lane; i < 2 * pw; i += 32) {
+            if (i < pw) *reinterpret_cast<uint32_t*>(dst - padx + 4 * i) = left;
+            else *reinterpret_cast<uint32_t*>(dst + W + 4 * (i - pw)) = right;
+        }
+    } else {
+        for (int i = lane; i < (W >> 2) + 2 * pw; i += 32) {
+            int x = 4 * i - padx;
+            uint32_t v = x < 0 ? left : (x >= W ? right : H264R_LDCG(reinterpret_cast<const uint32_t*>(src + x)));
+            *reinterpret_cast<uint32_t*>(dst + x) = v;
+        }
+    }
+}
+
+// Working set of the inter path (one per warp)
 struct alignas(16) InterWork {
-    uint8_t win[2560];          // staged reference windows (see window geometry below)
+    uint32_t win[480];          // staged windows, see phase_inter_stage
     int16_t res[384];           // residual
+    uint8_t need[32];           // per lane: NEED_* of its block
     uint32_t excursions;
-    int32_t bs;                 // prediction block size chosen for the macroblock (16 / 8 / 4)
+    int32_t shape;              // 0: one 16x16 window, 1: four 8x8 windows, 2: sixteen 4x4 windows
     uint32_t pad_[2];
 };
 
@@ -61,6 +146,7 @@ struct Dequant {                // per QP: d = (c * mul + add) >> shr for the th
 };
 HD Dequant make_dequant(int qp)
 {
+    // normAdjust4x4 (reference residual::LevelScale4x4, h264/residual.cpp:170-183): columns = (even,even) / (odd,odd) / other
     const int v[6][3] = {{10, 16, 13}, {11, 18, 14}, {13, 20, 16}, {14, 23, 18}, {16, 25, 20}, {18, 29, 23}};
     int s = (qp * 43) >> 8, m = qp - 6 * s;         // qp / 6, qp % 6 for 0 <= qp < 64
     Dequant q;
@@ -68,7 +154,8 @@ HD Dequant make_dequant(int qp)
     else { for (int k = 0; k < 3; k++) q.mul[k] = 16 * v[m][k]; q.add = 1 << (3 - s); q.shr = 4 - s; }
     return q;
 }
-// c: 16 levels (raster); returns residual in r.  Same arithmetic as scale_idct4.
+// c: 16 levels (raster); returns residual in r.  Same arithmetic as scale_idct4
+// (reference residual::ScalingAndTransform_Residual4x4Blocks, h264/residual.cpp:367-434).
 HD void idct4_fast(const int c[16], const Dequant& q, bool dc_bypass, int r[16])
 {
     int d[16];
@@ -94,7 +181,8 @@ HD void idct4_fast(const int c[16], const Dequant& q, bool dc_bypass, int r[16])
 }
 
 // Phase: residual of an inter macroblock (4x4 transform) straight from global memory into res[].
-// Lane b < 24 owns block b.  Uncoded blocks write zeros.
+// Lane b < 24 owns block b.  Uncoded blocks (coded_block_pattern bit clear: the reference zero-fills
+// them, h264/residual.cpp:44-46) are neither loaded nor transformed and write zeros.
 template <bool COMPAT>
 HD void phase_residual_inter_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane)
 {
@@ -153,161 +241,7 @@ HD void phase_residual_inter_fast(int16_t* res, const PicDesc& pd, const h264r_m
     }
 }
 
-// ---- K3: window staging --------------------------------------------------------------------------------
-// Window geometry (bytes): sample (px, py) of the prediction block sits at win[(py + 3) * pitch + px + 4];
-// rows -3..bh+2, columns -4..: 16x16 block: 22 rows x 24 bytes (pitch 32); 8x8: 14 x 16 (pitch 16);
-// 4x4: 10 x 12 (pitch 16).
-HD uint32_t ref_word(const uint8_t* ref, int gpitch, int W, int H, int x, int y)
-{
-    // 4 samples (x..x+3, y) with the coordinate clamp; word loads when the span is inside the picture
-    if (y >= 0 && y < H && x >= 0 && x + 7 < W) {
-        const uint8_t* p = ref + (size_t)y * gpitch + x;
-        uintptr_t ad = reinterpret_cast<uintptr_t>(p);
-        const uint32_t* q = reinterpret_cast<const uint32_t*>(ad & ~(uintptr_t)3);
-        int sh = (int)(ad & 3) * 8;
-        uint32_t lo = H264R_LDG(q);
-        if (sh == 0) return lo;
-        uint32_t hi = H264R_LDG(q + 1);
-        return funnel_r(lo, hi, sh);
-    }
-    int yy = clip3(0, H - 1, y);
-    const uint8_t* row = ref + (size_t)yy * gpitch;
-    uint32_t v = 0;
-    for (int i = 0; i < 4; i++) v |= (uint32_t)H264R_LDG(row + clip3(0, W - 1, x + i)) << (8 * i);
-    return v;
-}
-// items first, first + STRIDE, ... of a window of NROWS x NWORDS words
-template <int NROWS, int NWORDS, int PITCH, int STRIDE>
-HD void stage_window(uint8_t* dst, const uint8_t* ref, int gpitch, int W, int H, int sx, int sy, int first)
-{
-#pragma unroll 1
-    for (int it = first; it < NROWS * NWORDS; it += STRIDE) {
-        int row = it / NWORDS, j = it - row * NWORDS;
-        *reinterpret_cast<uint32_t*>(dst + row * PITCH + j * 4) = ref_word(ref, gpitch, W, H, sx + 4 * j, sy + row);
-    }
-}
-
-// ---- K3: one row segment of N samples ---------------------------------------------------------------------
-// Table-driven: for every source row dr = -3..3 a position needs, up to four raw quantities are
-// accumulated with dp4a on the byte groups A = x[-2..1], B = x[2..5] of each sample:
-//   QH  6-tap of row 0 (b1)                QS  the "s1" sum (row +1; the reference takes tap K from row -1, D6)
-//   QV  vertical 6-tap (column 0 or +1)    QJ  the part of j1 that is not 20*QH + 20*QS
-// so that in BOTH modes j1 = QJ + 20 QH + 20 QS.  Spec: QJ = H(-2) - 5 H(-1) - 5 H(2) + H(3).  Reference
-// (D7, h264/macroblock.cpp:843-846; with L = x[-2]-5x[-1], M = 20x[0]+20x[1], R = -5x[2]+x[3]):
-//   j1 = aa - 5bb + 20b1 + 20s1 - 5gg + hh,  aa = L(-2)+M(-2)+R(-2), bb = L(-2)+M(-1)+R(-2),
-//   gg = L(2)+M(2)+R(-2), hh = L(3)+M(3)+R(-3)
-//   => QJ = R(-3) + [-4L + M - 9R](-2) + [-5M](-1) + [-5L - 5M](2) + [L + M](3).
-struct McRowTaps { uint32_t sa, sb, ja, jb; int jm, vt; };
-template <bool COMPAT>
-HD McRowTaps mc_row_taps(int dr)
-{
-    constexpr uint32_t TA = taps4(1, -5, 20, 20), TB = taps4(-5, 1, 0, 0);
-    McRowTaps t{0, 0, 0, 0, 0, 0};
-    t.vt = dr == -2 || dr == 3 ? 1 : (dr == -1 || dr == 2 ? -5 : (dr == 0 || dr == 1 ? 20 : 0));
-    if (COMPAT) {
-        if (dr == -1) t.sa = taps4(1, 0, 0, 0);
-        if (dr == 1) { t.sa = taps4(0, -5, 20, 20); t.sb = TB; }
-        t.jm = 1;
-        if (dr == -3) t.jb = TB;
-        if (dr == -2) { t.ja = taps4(-4, 20, 20, 20); t.jb = taps4(45, -9, 0, 0); }
-        if (dr == -1) t.ja = taps4(0, 0, -100, -100);
-        if (dr == 2) t.ja = taps4(-5, 25, -100, -100);
-        if (dr == 3) t.ja = TA;
-    } else {
-        if (dr == 1) { t.sa = TA; t.sb = TB; }
-        if (dr == -2 || dr == -1 || dr == 2 || dr == 3) { t.ja = TA; t.jb = TB; t.jm = t.vt; }
-    }
-    return t;
-}
-// bit 0: QH, bit 1: QS, bit 2: QV (column 0), bit 3: QV (column +1), bit 4: QJ
-HD int mc_needs(int sel)
-{
-    // index = xFrac * 4 + yFrac:   G   d   h   n   a   e   i   p   b   f   j   q   c   g   k   r
-    const uint8_t need[16] = {0, 4, 4, 4, 1, 5, 0x17, 6, 1, 0x13, 0x13, 0x13, 1, 9, 0x1b, 10};
-    return need[sel];
-}
-
-template <bool COMPAT, int N>
-HD void mc_row(const uint8_t* win, int pitch, int r, int c0, int xf, int yf, int out[N])
-{
-    constexpr int NW = N == 8 ? 4 : 3;
-    constexpr uint32_t TA = taps4(1, -5, 20, 20), TB = taps4(-5, 1, 0, 0);
-    const int sel = xf * 4 + yf;
-    const int need = mc_needs(sel);
-    const bool nH = need & 1, nS = (need & 2) != 0, nV = (need & 12) != 0, nJ = (need & 16) != 0;
-    const int vshift = (need & 8) ? 24 : 16;
-    uint32_t w[NW];
-    int G[N], Hn[N], Mn[N], QH[N], QS[N], QV[N], QJ[N];
-#pragma unroll
-    for (int k = 0; k < N; k++) { G[k] = Hn[k] = Mn[k] = QH[k] = QS[k] = QV[k] = QJ[k] = 0; }
-    const int dr_lo = nJ ? (COMPAT ? -3 : -2) : (nV ? -2 : ((COMPAT && nS) ? -1 : 0));
-    const int dr_hi = (nJ || nV) ? 3 : ((nS || sel == 3) ? 1 : 0);
-#pragma unroll 1
-    for (int dr = dr_lo; dr <= dr_hi; dr++) {
-        const McRowTaps t = mc_row_taps<COMPAT>(dr);
-        const uint32_t* p = reinterpret_cast<const uint32_t*>(win + (r + dr) * pitch + c0);
-#pragma unroll
-        for (int i = 0; i < NW; i++) w[i] = p[i];
-        const bool doH = nH && dr == 0, doS = nS && (t.sa | t.sb) != 0, doJ = nJ && (t.ja | t.jb) != 0, doV = nV && t.vt != 0;
-        const uint32_t tv = (uint32_t)(t.vt & 255) << vshift;
-#pragma unroll
-        for (int k = 0; k < N; k++) {
-            const int sA = 2 + k, sB = 6 + k;
-            uint32_t A = (sA & 3) == 0 ? w[sA >> 2] : funnel_r(w[sA >> 2], w[(sA >> 2) + 1], (sA & 3) * 8);
-            uint32_t B = (sB & 3) == 0 ? w[sB >> 2] : funnel_r(w[sB >> 2], w[(sB >> 2) + 1 < NW ? (sB >> 2) + 1 : (sB >> 2)], (sB & 3) * 8);
-            if (dr == 0) { G[k] = (int)((A >> 16) & 255u); Hn[k] = (int)(A >> 24); }
-            if (dr == 1) Mn[k] = (int)((A >> 16) & 255u);
-            if (doH) QH[k] = dp4a_us(B, TB, dp4a_us(A, TA, 0));
-            if (doS) QS[k] = dp4a_us(B, t.sb, dp4a_us(A, t.sa, QS[k]));
-            if (doJ) QJ[k] += t.jm * dp4a_us(B, t.jb, dp4a_us(A, t.ja, 0));
-            if (doV) QV[k] = dp4a_us(A, tv, QV[k]);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < N; k++) {
-        int b = clip1((QH[k] + 16) >> 5), v = clip1((QV[k] + 16) >> 5), s = clip1((QS[k] + 16) >> 5);
-        int j = clip1((QJ[k] + 20 * QH[k] + 20 * QS[k] + 512) >> 10);
-        int o;
-        switch (sel) {
-        case 0: o = G[k]; break;
-        case 1: o = (G[k] + v + 1) >> 1; break;
-        case 2: o = v; break;
-        case 3: o = (Mn[k] + v + 1) >> 1; break;
-        case 4: o = (G[k] + b + 1) >> 1; break;
-        case 5: o = (b + v + 1) >> 1; break;
-        case 6: o = (v + j + 1) >> 1; break;
-        case 7: o = (v + s + 1) >> 1; break;
-        case 8: o = b; break;
-        case 9: o = (b + j + 1) >> 1; break;
-        case 10: o = j; break;
-        case 11: o = (j + s + 1) >> 1; break;
-        case 12: o = (Hn[k] + b + 1) >> 1; break;
-        case 13: o = (b + v + 1) >> 1; break;
-        case 14: o = (j + v + 1) >> 1; break;
-        default: o = (v + s + 1) >> 1; break;
-        }
-        out[k] = o;
-    }
-}
-
-// prediction block size of an inter macroblock: 16, 8 or 4 (see file header); mv[16] = packed (x | y << 16)
-template <bool COMPAT>
-HD int inter_block_size(const h264r_mb_hdr& h, const uint32_t mv[16])
-{
-    bool d8 = false;
-    if (COMPAT && h.mb_class == H264R_MB_P8x8) { uint32_t s = h.sub_mb_type; d8 = ((s & (s >> 1)) & 0x55u) != 0; }
-    if (d8) return 4;
-    bool q_uniform = true, all = true;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        int b0 = (q >> 1) * 8 + (q & 1) * 2;
-        q_uniform = q_uniform && mv[b0] == mv[b0 + 1] && mv[b0] == mv[b0 + 4] && mv[b0] == mv[b0 + 5];
-        all = all && mv[b0] == mv[0];
-    }
-    if (!q_uniform) return 4;
-    bool ref_same = h.u.ref_idx[0] == h.u.ref_idx[1] && h.u.ref_idx[0] == h.u.ref_idx[2] && h.u.ref_idx[0] == h.u.ref_idx[3];
-    return (all && ref_same) ? 16 : 8;
-}
+// ---- motion vectors, window shape --------------------------------------------------------------------
 HD void load_mvs(const PicDesc& pd, int a, uint32_t mv[16])
 {
     const uint4* p = reinterpret_cast<const uint4*>(pd.mv + (size_t)a * H264R_MV_PER_MB);
@@ -319,122 +253,299 @@ HD void load_mvs(const PicDesc& pd, int a, uint32_t mv[16])
 }
 HD int mv_x(uint32_t v) { return (int)(int16_t)(v & 0xffff); }
 HD int mv_y(uint32_t v) { return (int)v >> 16; }
-
 HD uint32_t load_mv1(const PicDesc& pd, int a, int blk)
 {
     return H264R_LDG(reinterpret_cast<const uint32_t*>(pd.mv + (size_t)a * H264R_MV_PER_MB) + blk);
 }
+// 0: all sixteen vectors (and reference indices) equal; 1: every 8x8 quadrant uniform; 2: anything else.
+// Under COMPAT a P_8x8 macroblock with a 4x4 sub-partition always takes shape 2: the reference's source-row
+// offset of sub-blocks 2 and 3 (D8, h264/macroblock.cpp:786-789) makes equal vectors read different rows.
+template <bool COMPAT>
+HD int inter_shape(const h264r_mb_hdr& h, const uint32_t mv[16])
+{
+    if (COMPAT && h.mb_class == H264R_MB_P8x8) { uint32_t s = h.sub_mb_type; if ((s & (s >> 1)) & 0x55u) return 2; }
+    bool q_uniform = true, all = true;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        int b0 = (q >> 1) * 8 + (q & 1) * 2;
+        q_uniform = q_uniform && mv[b0] == mv[b0 + 1] && mv[b0] == mv[b0 + 4] && mv[b0] == mv[b0 + 5];
+        all = all && mv[b0] == mv[0];
+    }
+    if (!q_uniform) return 2;
+    bool ref_same = h.u.ref_idx[0] == h.u.ref_idx[1] && h.u.ref_idx[0] == h.u.ref_idx[2] && h.u.ref_idx[0] == h.u.ref_idx[3];
+    return (all && ref_same) ? 0 : 1;
+}
 
-// Phase M0: stage the windows of the macroblock.
+// ---- what a quarter-sample position needs ---------------------------------------------------------------
+// Position sel = xFrac*4 + yFrac produces (P + Q + 1) >> 1 with P, Q out of
+//   F  a full sample: G (0,0), H (+1,0) or M (0,+1)          b  Clip1((b1+16)>>5), b1 = 6-tap of row 0
+//   v  Clip1((v1+16)>>5), v1 = 6-tap of column 0 (h) or +1 (m)  s  Clip1((s1+16)>>5), s1 = 6-tap of row +1
+//   j  Clip1((j1+512)>>10)
+// (reference predPart table, h264/macroblock.cpp:893-901).
+constexpr int NEED_H = 1, NEED_S = 2, NEED_V = 4, NEED_J = 8;
+struct McSel {
+    // select masks (0 / ~0): P <- G, H, M, b, v, j;  Q <- G, b, v, s, j
+    uint32_t pG, pH, pM, pb, pv, pj, qG, qb, qv, qs, qj;
+    uint32_t tv1, tv5, tv20;     // vertical taps 1, -5, 20 in the byte of column 0 (h) or +1 (m) of A_k
+    int need;
+};
+HD McSel mc_select(int xf, int yf)
+{
+    const int sel = xf * 4 + yf;
+    //                      sel:  0  1  2  3  4  5  6  7  8  9 10 11 12 13 14 15
+    // P: 0 G, 1 H, 2 M, 3 b, 4 v, 5 j   0  0  4  2  0  3  4  4  3  3  5  5  1  3  5  4
+    // Q: 0 G, 1 b, 2 v, 3 s, 4 j        0  2  2  2  1  2  4  3  1  4  4  3  1  2  2  3
+    const uint64_t PT = 0x4531553344302400ull, QT = 0x3221344134212220ull;
+    const int p = (int)((PT >> (4 * sel)) & 15), q = (int)((QT >> (4 * sel)) & 15);
+    McSel m;
+    m.pG = p == 0 ? ~0u : 0u; m.pH = p == 1 ? ~0u : 0u; m.pM = p == 2 ? ~0u : 0u;
+    m.pb = p == 3 ? ~0u : 0u; m.pv = p == 4 ? ~0u : 0u; m.pj = p == 5 ? ~0u : 0u;
+    m.qG = q == 0 ? ~0u : 0u; m.qb = q == 1 ? ~0u : 0u; m.qv = q == 2 ? ~0u : 0u;
+    m.qs = q == 3 ? ~0u : 0u; m.qj = q == 4 ? ~0u : 0u;
+    const bool nj = p == 5 || q == 4;
+    m.need = ((p == 3 || q == 1 || nj) ? NEED_H : 0) | ((q == 3 || nj) ? NEED_S : 0) | ((p == 4 || q == 2) ? NEED_V : 0) | (nj ? NEED_J : 0);
+    const int vshift = xf == 3 ? 24 : 16;
+    m.tv1 = 1u << vshift; m.tv5 = (uint32_t)(-5 & 255) << vshift; m.tv20 = 20u << vshift;
+    return m;
+}
+HD int mc_need(int xf, int yf) { return mc_select(xf, yf).need; }
+
+// ---- window staging ----------------------------------------------------------------------------------------
+// One staged word = bytes (x .. x+3, y) of the padded reference plane, x of any alignment.
+HD uint32_t ref_word(const uint8_t* ref, int gpitch, int x, int y)
+{
+    const uint8_t* p = ref + (ptrdiff_t)y * gpitch + x;
+    uintptr_t ad = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(ad & ~(uintptr_t)3);
+    return funnel_r(H264R_LDG(q), H264R_LDG(q + 1), (int)(ad & 3) * 8);
+}
+// items first, first + STRIDE, ... of a window of NROWS x NWORDS words whose top-left byte is (sx, sy)
+template <int NROWS, int NWORDS, int STRIDE>
+HD void stage_window(uint32_t* dst, const uint8_t* ref, int gpitch, int sx, int sy, int first)
+{
+#pragma unroll
+    for (int i = 0; i < (NROWS * NWORDS + STRIDE - 1) / STRIDE; i++) {
+        int it = first + i * STRIDE;
+        if (it < NROWS * NWORDS) {
+            int row = it / NWORDS, j = it - row * NWORDS;
+            dst[it] = ref_word(ref, gpitch, sx + 4 * j, sy + row);
+        }
+    }
+}
+
+// Phase M0: shape of the macroblock, this lane's NEED bits, and the windows.
+// Window of a bw x bh block at integer position (xb, yb): bytes xb-2 .. and rows yb-3 .. yb+bh+2
+// (the reference's j reaches row -3, D7).  Block positions are clamped to [-(bw+3), W+2] x [-(bh+3), H+3],
+// which gives every sample the value of the reference's per-sample coordinate clamp.
 template <bool COMPAT>
 HD void phase_inter_stage(InterWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane)
 {
-    int bs;
-    {
-        uint32_t mv[16];
-        load_mvs(pd, a, mv);
-        bs = inter_block_size<COMPAT>(h, mv);
-    }
-    if (lane == 0) w.bs = bs;
-    int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    uint32_t mv[16];
+    load_mvs(pd, a, mv);
+    const int shape = inter_shape<COMPAT>(h, mv);
+    if (lane == 0) { w.shape = shape; w.excursions = 0; }
+    const int mbx = a % g.w_mbs, mby = a / g.w_mbs;
     const int W = g.w_mbs * 16, H = g.h_mbs * 16;
-    if (bs == 16) {
-        uint32_t v = load_mv1(pd, a, 0);
+    {
+        uint32_t v = load_mv1(pd, a, lane >> 1);
+        w.need[lane] = (uint8_t)mc_need(mv_x(v) & 3, mv_y(v) & 3);
+    }
+    if (shape == 0) {
+        const uint32_t v = mv[0];
         const uint8_t* ref = pd.ref_y[h.u.ref_idx[0] & 15];
-        stage_window<22, 6, 32, 32>(w.win, ref, g.pitch_y, W, H, mbx * 16 + (mv_x(v) >> 2) - 4, mby * 16 + (mv_y(v) >> 2) - 3, lane);
-    } else if (bs == 8) {
-        int q = lane >> 3, b0 = (q >> 1) * 8 + (q & 1) * 2;
-        uint32_t v = load_mv1(pd, a, b0);
+        int xb = clip3(-19, W + 2, mbx * 16 + (mv_x(v) >> 2)), yb = clip3(-19, H + 3, mby * 16 + (mv_y(v) >> 2));
+        stage_window<22, 6, 32>(w.win, ref, g.pitch_y, xb - 2, yb - 3, lane);
+    } else if (shape == 1) {
+        const int q = lane >> 3, b0 = (q >> 1) * 8 + (q & 1) * 2;
+        const uint32_t v = load_mv1(pd, a, b0);
         const uint8_t* ref = pd.ref_y[h.u.ref_idx[q] & 15];
-        stage_window<14, 4, 16, 8>(w.win + q * (14 * 16), ref, g.pitch_y, W, H, mbx * 16 + (q & 1) * 8 + (mv_x(v) >> 2) - 4,
-                                   mby * 16 + (q >> 1) * 8 + (mv_y(v) >> 2) - 3, lane & 7);
+        int xb = clip3(-11, W + 2, mbx * 16 + (q & 1) * 8 + (mv_x(v) >> 2)), yb = clip3(-11, H + 3, mby * 16 + (q >> 1) * 8 + (mv_y(v) >> 2));
+        stage_window<14, 4, 8>(w.win + q * 56, ref, g.pitch_y, xb - 2, yb - 3, lane & 7);
     } else {
-        int b = lane >> 1, bx = b & 3, by = b >> 2, q = (by >> 1) * 2 + (bx >> 1);
-        uint32_t v = load_mv1(pd, a, b);
+        const int b = lane >> 1, bx = b & 3, by = b >> 2, q = (by >> 1) * 2 + (bx >> 1);
+        const uint32_t v = load_mv1(pd, a, b);
         const uint8_t* ref = pd.ref_y[h.u.ref_idx[q] & 15];
         int ys = mby * 16 + by * 4;
         // reference's source-row offset for 4x4 sub-partitions 2 and 3 (D8, h264/macroblock.cpp:786-789)
         if (COMPAT && h.mb_class == H264R_MB_P8x8 && ((h.sub_mb_type >> (2 * q)) & 3) == H264R_SUB_4x4 && (by & 1)) ys -= 3;
-        stage_window<10, 3, 16, 2>(w.win + b * 160, ref, g.pitch_y, W, H, mbx * 16 + bx * 4 + (mv_x(v) >> 2) - 4, ys + (mv_y(v) >> 2) - 3, lane & 1);
+        int xb = clip3(-7, W + 2, mbx * 16 + bx * 4 + (mv_x(v) >> 2)), yb = clip3(-7, H + 3, ys + (mv_y(v) >> 2));
+        stage_window<10, 3, 2>(w.win + b * 30, ref, g.pitch_y, xb - 2, yb - 3, lane & 1);
     }
 }
 
-// luma: prediction (+ weighting) + residual -> packed bytes; `bad` collects the sign of out-of-range values
-template <bool COMPAT, int N>
-HD void finish_luma(int pred[N], const int16_t* res_row, bool coded, const PicDesc& pd, int ri, int& bad, uint32_t packed[N / 4])
+// ---- interpolation ----------------------------------------------------------------------------------------------
+// One window row contributes to one output row at vertical offset DY = -3..3.  A[k] = x[k-2 .. k+1] for the
+// lane's samples k = 0..3 and A[k+4] = x[k+2 .. k+5].  With TA = (1,-5,20,20) on A[k] and TB = (-5,1,0,0) on
+// A[k+4] a dp4a pair is the 6-tap row filter; a vertical tap is a dp4a with one non-zero byte.
+//
+// j under COMPAT: the reference computes j1 = tap6(aa, bb, b1, s1, gg, hh) from row sums whose outer taps
+// come from the wrong rows (D7, h264/macroblock.cpp:843-846) and s1 with tap K from row -1 (D6,
+// h264/staticcharts.h:1505).  With L = x[-2]-5x[-1], M = 20x[0]+20x[1], R = -5x[2]+x[3] of a row:
+//   aa = L(-2)+M(-2)+R(-2)   bb = L(-2)+M(-1)+R(-2)   gg = L(2)+M(2)+R(-2)   hh = L(3)+M(3)+R(-3)
+//   j1 = aa - 5bb + 20 b1 + 20 s1 - 5gg + hh
+//      = R(-3) + [-4L + M - 9R](-2) + [-5M](-1) + [-5L - 5M](2) + [L + M](3)  +  20 b1 + 20 s1
+// so QJ accumulates the bracketed part with one or two dp4a per row.  Spec mode: j1 = sum over rows of
+// vertical tap * row filter = (F(-2) + F(3)) - 5 (F(-1) + F(2)) + 20 b1 + 20 s1, accumulated in QJ / QJ5.
+struct McAcc { int QH[4], QS[4], QV[4], QJ[4], QJ5[4]; uint32_t P, Q; };
+
+template <bool COMPAT, int CLS, int DY>
+HD void mc_accum(const uint32_t A[8], const McSel& m, McAcc& c)
 {
-    if (pd.weighted_pred) {
-#pragma unroll
-        for (int k = 0; k < N; k++) pred[k] = weight_pred(pred[k], pd.luma_log2_wd, pd.luma_weight[ri], pd.luma_offset[ri]);
+    constexpr uint32_t TA = taps4(1, -5, 20, 20), TB = taps4(-5, 1, 0, 0);
+    if (DY < -3 || DY > 3) return;
+    if (DY == 0) {       // full samples G (x[0] = byte 2 of A[k]: the four of them are A[2]) and H (A[3])
+        c.P = (A[2] & m.pG) | (A[3] & m.pH);
+        c.Q = A[2] & m.qG;
     }
-    if (coded) {
+    if (DY == 1) c.P |= A[2] & m.pM;
+    if (CLS == 0) return;
 #pragma unroll
-        for (int k = 0; k < N; k += 2) {
-            uint32_t rr = *reinterpret_cast<const uint32_t*>(res_row + k);
-            pred[k] += (int)(int16_t)(rr & 0xffff);
-            pred[k + 1] += (int)rr >> 16;
+    for (int k = 0; k < 4; k++) {
+        if (DY == 0) c.QH[k] = dp4a_us(A[k + 4], TB, dp4a_us(A[k], TA, 0));
+        if (COMPAT) {
+            if (DY == -1) c.QS[k] = dp4a_us(A[k], taps4(1, 0, 0, 0), 0);
+            if (DY == 1) c.QS[k] = dp4a_us(A[k + 4], TB, dp4a_us(A[k], taps4(0, -5, 20, 20), c.QS[k]));
+        } else {
+            if (DY == 1) c.QS[k] = dp4a_us(A[k + 4], TB, dp4a_us(A[k], TA, 0));
+        }
+        if (DY == -2) c.QV[k] = dp4a_us(A[k], m.tv1, 0);
+        if (DY == -1 || DY == 2) c.QV[k] = dp4a_us(A[k], m.tv5, c.QV[k]);
+        if (DY == 0 || DY == 1) c.QV[k] = dp4a_us(A[k], m.tv20, c.QV[k]);
+        if (DY == 3) c.QV[k] = dp4a_us(A[k], m.tv1, c.QV[k]);
+        if (CLS == 2) {
+            if (COMPAT) {
+                if (DY == -3) c.QJ[k] = dp4a_us(A[k + 4], TB, 0);
+                if (DY == -2) c.QJ[k] = dp4a_us(A[k + 4], taps4(45, -9, 0, 0), dp4a_us(A[k], taps4(-4, 20, 20, 20), c.QJ[k]));
+                if (DY == -1) c.QJ[k] = dp4a_us(A[k], taps4(0, 0, -100, -100), c.QJ[k]);
+                if (DY == 2) c.QJ[k] = dp4a_us(A[k], taps4(-5, 25, -100, -100), c.QJ[k]);
+                if (DY == 3) c.QJ[k] = dp4a_us(A[k], TA, c.QJ[k]);
+            } else {
+                if (DY == -2) c.QJ[k] = dp4a_us(A[k + 4], TB, dp4a_us(A[k], TA, 0));
+                if (DY == 3) c.QJ[k] = dp4a_us(A[k + 4], TB, dp4a_us(A[k], TA, c.QJ[k]));
+                if (DY == -1) c.QJ5[k] = dp4a_us(A[k + 4], TB, dp4a_us(A[k], TA, 0));
+                if (DY == 2) c.QJ5[k] = dp4a_us(A[k + 4], TB, dp4a_us(A[k], TA, c.QJ5[k]));
+            }
         }
     }
-#pragma unroll
-    for (int i = 0; i < N / 4; i++) packed[i] = 0;
-#pragma unroll
-    for (int k = 0; k < N; k++) {
-        int v = pred[k];
-        bad |= v | (255 - v);                       // sign bit set when v < 0 or v > 255
-        packed[k >> 2] |= (uint32_t)(COMPAT ? (v & 255) : clip1(v)) << ((k & 3) * 8);
-    }
 }
-template <int N>
-HD uint32_t count_excursions(const int pred[N])
+
+// the four prediction samples of one output row, packed
+template <bool COMPAT, int CLS>
+HD uint32_t mc_finish(const McSel& m, const McAcc& c)
 {
+    uint32_t P = c.P, Q = c.Q;
+    if (CLS >= 1) {
+        uint32_t b = pack_sat_u8((c.QH[0] + 16) >> 5, (c.QH[1] + 16) >> 5, (c.QH[2] + 16) >> 5, (c.QH[3] + 16) >> 5);
+        uint32_t s = pack_sat_u8((c.QS[0] + 16) >> 5, (c.QS[1] + 16) >> 5, (c.QS[2] + 16) >> 5, (c.QS[3] + 16) >> 5);
+        uint32_t v = pack_sat_u8((c.QV[0] + 16) >> 5, (c.QV[1] + 16) >> 5, (c.QV[2] + 16) >> 5, (c.QV[3] + 16) >> 5);
+        P |= (b & m.pb) | (v & m.pv);
+        Q |= (b & m.qb) | (v & m.qv) | (s & m.qs);
+    }
+    if (CLS == 2) {
+        int j1[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            j1[k] = c.QJ[k] + 20 * (c.QH[k] + c.QS[k]) + 512;
+            if (!COMPAT) j1[k] -= 5 * c.QJ5[k];
+        }
+        uint32_t j = pack_sat_u8(j1[0] >> 10, j1[1] >> 10, j1[2] >> 10, j1[3] >> 10);
+        P |= j & m.pj;
+        Q |= j & m.qj;
+    }
+    return avg_u8x4(P, Q);
+}
+
+// A[0..7] of one window row from its three words
+HD void mc_groups(const uint32_t* row, uint32_t A[8])
+{
+    uint32_t w0 = row[0], w1 = row[1], w2 = row[2];
+    A[0] = w0; A[1] = prmt(w0, w1, 0x4321); A[2] = prmt(w0, w1, 0x5432); A[3] = prmt(w0, w1, 0x6543);
+    A[4] = w1; A[5] = prmt(w1, w2, 0x4321); A[6] = prmt(w1, w2, 0x5432); A[7] = prmt(w1, w2, 0x6543);
+}
+
+// the lane's 4x2 patch: wp = first of its 8 window rows (row -3 of output row 0), pitch in words
+template <bool COMPAT, int CLS>
+HD void mc_patch(const uint32_t* wp, int pitch, const McSel& m, uint32_t out[2])
+{
+    McAcc c0, c1;
+    uint32_t A[8];
+#define MC_ROW(RR)                                       \
+    mc_groups(wp + (RR) * pitch, A);                     \
+    mc_accum<COMPAT, CLS, (RR) - 3>(A, m, c0);           \
+    mc_accum<COMPAT, CLS, (RR) - 4>(A, m, c1);
+    if (CLS == 0) {
+        // every lane of the warp sits on a full-sample position: row 0 of both output rows
+        MC_ROW(3) MC_ROW(4)
+    } else {
+        if (CLS == 2 && COMPAT) { MC_ROW(0) }          // row -3 is reached only by the reference's j (D7)
+        MC_ROW(1) MC_ROW(2) MC_ROW(3) MC_ROW(4) MC_ROW(5) MC_ROW(6) MC_ROW(7)
+    }
+#undef MC_ROW
+    out[0] = mc_finish<COMPAT, CLS>(m, c0);
+    out[1] = mc_finish<COMPAT, CLS>(m, c1);
+}
+
+// packed prediction + residual -> packed samples; returns the number of samples that left [0,255]
+template <bool COMPAT>
+HD uint32_t add_residual(uint32_t pred, const int16_t* res_row, uint32_t& packed)
+{
+    const uint2 r = *reinterpret_cast<const uint2*>(res_row);
+    uint32_t s0 = add_s16x2(prmt(pred, 0u, 0x4140), r.x), s1 = add_s16x2(prmt(pred, 0u, 0x4342), r.y);
     uint32_t n = 0;
-    for (int k = 0; k < N; k++) n += (pred[k] < 0 || pred[k] > 255);
+    if ((s0 | s1) & 0xff00ff00u)
+        n = ((s0 & 0xff00u) != 0) + ((s0 & 0xff000000u) != 0) + ((s1 & 0xff00u) != 0) + ((s1 & 0xff000000u) != 0);
+    if (!COMPAT) { s0 = clip255_s16x2(s0); s1 = clip255_s16x2(s1); }
+    packed = prmt(s0, s1, 0x6420);          // COMPAT: the plane keeps the low 8 bits (D3)
     return n;
+}
+HD uint32_t weight_packed(uint32_t pred, int logwd, int wgt, int off)
+{
+    return (uint32_t)weight_pred((int)(pred & 255u), logwd, wgt, off) | ((uint32_t)weight_pred((int)((pred >> 8) & 255u), logwd, wgt, off) << 8) |
+           ((uint32_t)weight_pred((int)((pred >> 16) & 255u), logwd, wgt, off) << 16) | ((uint32_t)weight_pred((int)(pred >> 24), logwd, wgt, off) << 24);
 }
 
 // Phase M1: compute and store the macroblock (luma from the staged windows; chroma: COMPAT = residual
-// only, D4; spec = bilinear from the reference planes).
+// only, D4; spec = bilinear from the padded reference planes, ITU-T H.264 8.4.2.2.2).
 template <bool COMPAT>
 HD void phase_inter_compute(InterWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane, bool coded)
 {
-    const int bs = w.bs;
-    int mbx = a % g.w_mbs, mby = a / g.w_mbs;
-    uint8_t* ybase = pd.y + (size_t)(mby * 16) * g.pitch_y + mbx * 16;
-    uint32_t exc = 0;
-    if (bs != 4) {
-        int row, col, ri, pitch, wr, c0, blk;
-        const uint8_t* win;
-        if (bs == 16) { row = lane >> 1; col = (lane & 1) * 8; win = w.win; pitch = 32; wr = row + 3; c0 = col; blk = 0; ri = h.u.ref_idx[0] & 15; }
-        else {
-            int q = lane >> 3, rr = lane & 7;
-            row = (q >> 1) * 8 + rr; col = (q & 1) * 8; win = w.win + q * (14 * 16); pitch = 16; wr = rr + 3; c0 = 0;
-            blk = (q >> 1) * 8 + (q & 1) * 2; ri = h.u.ref_idx[q] & 15;
-        }
-        uint32_t v = load_mv1(pd, a, blk);
-        int pred[8];
-        mc_row<COMPAT, 8>(win, pitch, wr, c0, mv_x(v) & 3, mv_y(v) & 3, pred);
-        uint32_t packed[2];
-        int bad = 0;
-        finish_luma<COMPAT, 8>(pred, &w.res[row * 16 + col], coded, pd, ri, bad, packed);
-        if (bad < 0) exc += count_excursions<8>(pred);
-        *reinterpret_cast<uint2*>(ybase + (size_t)row * g.pitch_y + col) = uint2{packed[0], packed[1]};
-    } else {
-        int b = lane >> 1, bx = b & 3, by = b >> 2, q = (by >> 1) * 2 + (bx >> 1);
-        int ri = h.u.ref_idx[q] & 15;
-        uint32_t v = load_mv1(pd, a, b);
-        const uint8_t* win = w.win + b * 160;
-#pragma unroll 1
-        for (int n = 0; n < 2; n++) {
-            int rr = (lane & 1) * 2 + n, row = by * 4 + rr, col = bx * 4;
-            int pred[4];
-            mc_row<COMPAT, 4>(win, 16, rr + 3, 0, mv_x(v) & 3, mv_y(v) & 3, pred);
-            uint32_t packed[1];
-            int bad = 0;
-            finish_luma<COMPAT, 4>(pred, &w.res[row * 16 + col], coded, pd, ri, bad, packed);
-            if (bad < 0) exc += count_excursions<4>(pred);
-            *reinterpret_cast<uint32_t*>(ybase + (size_t)row * g.pitch_y + col) = packed[0];
-        }
+    const int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    // warp-wide union of the NEED bits
+    int wn;
+    {
+        const uint4* np = reinterpret_cast<const uint4*>(w.need);
+        uint4 n0 = np[0], n1 = np[1];
+        uint32_t o = n0.x | n0.y | n0.z | n0.w | n1.x | n1.y | n1.z | n1.w;
+        o |= o >> 16; o |= o >> 8;
+        wn = (int)(o & 15u);
     }
+    const int b = lane >> 1, half = lane & 1, bx = b & 3, by = b >> 2, q = (by >> 1) * 2 + (bx >> 1);
+    const int shape = w.shape;
+    const uint32_t* wp;
+    int pitch;
+    if (shape == 0) { wp = w.win + (by * 4 + half * 2) * 6 + bx; pitch = 6; }
+    else if (shape == 1) { wp = w.win + q * 56 + ((by & 1) * 4 + half * 2) * 4 + (bx & 1); pitch = 4; }
+    else { wp = w.win + b * 30 + half * 2 * 3; pitch = 3; }
+    const uint32_t v = load_mv1(pd, a, b);
+    const McSel m = mc_select(mv_x(v) & 3, mv_y(v) & 3);
+    uint32_t pred[2];
+    if (wn == 0) mc_patch<COMPAT, 0>(wp, pitch, m, pred);
+    else if (!(wn & NEED_J)) mc_patch<COMPAT, 1>(wp, pitch, m, pred);
+    else mc_patch<COMPAT, 2>(wp, pitch, m, pred);
+    const int ri = h.u.ref_idx[q] & 15;
+    if (pd.weighted_pred) {
+        pred[0] = weight_packed(pred[0], pd.luma_log2_wd, pd.luma_weight[ri], pd.luma_offset[ri]);
+        pred[1] = weight_packed(pred[1], pd.luma_log2_wd, pd.luma_weight[ri], pd.luma_offset[ri]);
+    }
+    const int row = by * 4 + half * 2, col = bx * 4;
+    uint8_t* yp = pd.y + (size_t)(mby * 16 + row) * g.pitch_y + mbx * 16 + col;
+    uint32_t exc = 0;
+    if (coded) {
+        exc += add_residual<COMPAT>(pred[0], &w.res[row * 16 + col], pred[0]);
+        exc += add_residual<COMPAT>(pred[1], &w.res[(row + 1) * 16 + col], pred[1]);
+    }
+    *reinterpret_cast<uint32_t*>(yp) = pred[0];
+    *reinterpret_cast<uint32_t*>(yp + g.pitch_y) = pred[1];
     // chroma: lane -> plane (lane >> 4), row (l >> 1), 4 samples
     {
         int plane = lane >> 4, l = lane & 15, cy = l >> 1, cx0 = (l & 1) * 4;
@@ -442,27 +553,27 @@ HD void phase_inter_compute(InterWork& w, const PicDesc& pd, const Geometry& g, 
         uint32_t packed = 0;
         if (COMPAT) {
             if (coded) {
-                const uint32_t* rp = reinterpret_cast<const uint32_t*>(&w.res[256 + plane * 64 + cy * 8 + cx0]);
-                uint32_t r0 = rp[0], r1 = rp[1];
-                packed = (r0 & 255u) | ((r0 >> 8) & 0xff00u) | ((r1 & 255u) << 16) | ((r1 << 8) & 0xff000000u);
+                const uint2 r = *reinterpret_cast<const uint2*>(&w.res[256 + plane * 64 + cy * 8 + cx0]);
+                packed = prmt(r.x, r.y, 0x6420);
             }
         } else {
             const int cw = g.w_mbs * 8, ch = g.h_mbs * 8;
             for (int k = 0; k < 4; k++) {
-                int cx = cx0 + k, blk = (cy >> 1) * 4 + (cx >> 1), q = (cy >> 2) * 2 + (cx >> 2);
-                int ri = h.u.ref_idx[q] & 15;
-                const uint8_t* ref = plane ? pd.ref_v[ri] : pd.ref_u[ri];
+                int cx = cx0 + k, blk = (cy >> 1) * 4 + (cx >> 1), qq = (cy >> 2) * 2 + (cx >> 2);
+                int rc = h.u.ref_idx[qq] & 15;
+                const uint8_t* ref = plane ? pd.ref_v[rc] : pd.ref_u[rc];
                 uint32_t v2 = load_mv1(pd, a, blk);
                 int mvx = mv_x(v2), mvy = mv_y(v2);
                 int xf = mvx & 7, yf = mvy & 7;
                 int xi = mbx * 8 + cx + (mvx >> 3), yi = mby * 8 + cy + (mvy >> 3);
-                int xa = clip3(0, cw - 1, xi), xb = clip3(0, cw - 1, xi + 1), ya = clip3(0, ch - 1, yi), yb = clip3(0, ch - 1, yi + 1);
-                int A = H264R_LDG(ref + (size_t)ya * g.pitch_c + xa), B = H264R_LDG(ref + (size_t)ya * g.pitch_c + xb);
-                int C = H264R_LDG(ref + (size_t)yb * g.pitch_c + xa), D = H264R_LDG(ref + (size_t)yb * g.pitch_c + xb);
-                int v = ((8 - xf) * (8 - yf) * A + xf * (8 - yf) * B + (8 - xf) * yf * C + xf * yf * D + 32) >> 6;
-                if (pd.weighted_pred) v = weight_pred(v, pd.chroma_log2_wd, pd.chroma_weight[ri][plane], pd.chroma_offset[ri][plane]);
-                if (coded) v += w.res[256 + plane * 64 + cy * 8 + cx];
-                packed |= (uint32_t)clip1(v) << (8 * k);
+                // the replicated border makes a clamp to [-8, size+7] equal to the clamp to the picture
+                int xa = clip3(-8, cw + 7, xi), xb = clip3(-8, cw + 7, xi + 1), ya = clip3(-8, ch + 7, yi), yb = clip3(-8, ch + 7, yi + 1);
+                int A = H264R_LDG(ref + (ptrdiff_t)ya * g.pitch_c + xa), B = H264R_LDG(ref + (ptrdiff_t)ya * g.pitch_c + xb);
+                int C = H264R_LDG(ref + (ptrdiff_t)yb * g.pitch_c + xa), D = H264R_LDG(ref + (ptrdiff_t)yb * g.pitch_c + xb);
+                int pv = ((8 - xf) * (8 - yf) * A + xf * (8 - yf) * B + (8 - xf) * yf * C + xf * yf * D + 32) >> 6;
+                if (pd.weighted_pred) pv = weight_pred(pv, pd.chroma_log2_wd, pd.chroma_weight[rc][plane], pd.chroma_offset[rc][plane]);
+                if (coded) pv += w.res[256 + plane * 64 + cy * 8 + cx];
+                packed |= (uint32_t)clip1(pv) << (8 * k);
             }
         }
         *reinterpret_cast<uint32_t*>(cbase) = packed;
@@ -476,14 +587,13 @@ HD void phase_inter_compute(InterWork& w, const PicDesc& pd, const Geometry& g, 
     }
 }
 
-// K1+K3 fast sequence for one inter macroblock (4x4 transform).  8x8-transform macroblocks take
-// seq_inter_mb of h264r_seq.cuh.
+// K1+K3 sequence for one inter macroblock (4x4 transform).  8x8-transform macroblocks take seq_inter_mb
+// of h264r_seq.cuh.
 template <bool COMPAT, class Exec>
 HD void seq_inter_mb_fast(Exec& ex, InterWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a)
 {
     const bool coded = h.cbp != 0;
     ex([&](int lane) {
-        if (lane == 0) w.excursions = 0;
         if (coded) phase_residual_inter_fast<COMPAT>(w.res, pd, h, a, lane);
         phase_inter_stage<COMPAT>(w, pd, g, h, a, lane);
     });

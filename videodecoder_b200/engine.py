@@ -57,7 +57,7 @@ def load_library():
     L.h264r_release.argtypes = [vp, ci]
     L.h264r_last_flush_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ci)]
     L.h264r_set_profiling.argtypes = [vp, ci]
-    L.h264r_last_flush_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 3), ctypes.POINTER(ci * 3)]
+    L.h264r_last_flush_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 4), ctypes.POINTER(ci * 4)]
     L.h264r_mark.argtypes = [vp, ci]
     L.h264r_elapsed_ms.argtypes = [vp, ci, ci, ctypes.POINTER(ctypes.c_float)]
     if L.h264r_abi_version() != abi.ABI_VERSION:
@@ -203,7 +203,7 @@ class Engine:
         self._check(self.L.h264r_set_profiling(self.ctx, 1 if on else 0))
 
     def last_flush_kernel_ms(self):
-        ms, n = (ctypes.c_float * 3)(), (ctypes.c_int * 3)()
+        ms, n = (ctypes.c_float * 4)(), (ctypes.c_int * 4)()
         self._check(self.L.h264r_last_flush_kernel_ms(self.ctx, ctypes.byref(ms), ctypes.byref(n)))
         return list(ms), list(n)
 

@@ -303,6 +303,7 @@ def main():
         ms, _ = eng.last_flush_stats()
         kern_ms += ms
         fm, fn = eng.last_flush_kernel_ms()
+        launch_ms = eng.last_flush_launch_ms()
         fam_ms += np.array(fm)
         fam_n += np.array(fn)
     barrier()
@@ -373,6 +374,14 @@ def main():
                          "avg_launch_ms": sec_per_launch * 1000.0},
             "clocks": clk, "luma_range_excursions": excursions,
         }
+        # per-launch picture of the last timed flush: the first wave holds the I pictures, the others the P pictures
+        prof = {}
+        for fam_id, fam_name in ((0, "inter"), (1, "intra"), (2, "deblock"), (3, "pad")):
+            t = [m for m, f in launch_ms if f == fam_id]
+            if t:
+                prof[fam_name] = {"n": len(t), "first_ms": t[0], "rest_avg_ms": (sum(t[1:]) / (len(t) - 1)) if len(t) > 1 else None,
+                                  "max_ms": max(t)}
+        line["launch_profile"] = prof
         if world == 1 and not args.no_cpu_baseline and reference_available():
             try:
                 line["cpu_baseline"] = cpu_baseline(args.sample_frames)

@@ -230,6 +230,9 @@ int h264r_last_flush_stats(h264r_ctx* ctx, float* kernel_ms, int* launches);
 int h264r_set_profiling(h264r_ctx* ctx, int on);
 #define H264R_KERNEL_FAMILIES 4
 int h264r_last_flush_kernel_ms(h264r_ctx* ctx, float ms[H264R_KERNEL_FAMILIES], int launches[H264R_KERNEL_FAMILIES]);
+/* Per-launch device times of the last flush in issue order (needs h264r_set_profiling(1)): fills ms[] / family[]
+ * with up to cap entries and returns the number written (>= 0) or a negative error code. */
+int h264r_last_flush_launch_ms(h264r_ctx* ctx, float* ms, int* family, int cap);
 int h264r_mark(h264r_ctx* ctx, int slot);
 int h264r_elapsed_ms(h264r_ctx* ctx, int slot_from, int slot_to, float* ms);
 

@@ -117,6 +117,7 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
     MbWork& w = ww.mb;
     unsigned long long exc = 0;
     const bool compat = (flags & H264R_REF_COMPAT) != 0;
+    const bool use_fast_intra = !(flags & 0x80000000u);     // test switch: bit 31 selects the generic intra phases
     int n = w_mbs * h_mbs;
     // same order as the device: all inter MBs of the picture first, then the intra MBs
     for (int a = 0; a < n; a++) {
@@ -124,11 +125,18 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
         if (is_intra(h.mb_class)) continue;
         exc += compat ? seq_inter_any<true>(ex, ww, pd, g, h, a) : seq_inter_any<false>(ex, ww, pd, g, h, a);
     }
+    static uint16_t lut[INTRA4_LUT_SIZE];
+    intra4_lut_fill(lut, 0, 1);
+    int prev = -2;
     for (int a = 0; a < n; a++) {
         h264r_mb_hdr h = load_hdr(pd, a);
         if (!is_intra(h.mb_class)) continue;
-        if (compat) seq_intra_mb<true>(ex, w, pd, g, h, a); else seq_intra_mb<false>(ex, w, pd, g, h, a);
+        // as the row warps of k_intra_rows do: the left column comes from the warp's own tile when it has just done a - 1
+        bool carry = use_fast_intra && prev == a - 1 && (a % w_mbs) != 0;
+        if (!use_fast_intra) { if (compat) seq_intra_mb<true>(ex, w, pd, g, h, a); else seq_intra_mb<false>(ex, w, pd, g, h, a); }
+        else if (compat) seq_intra_any<true>(ex, w, lut, pd, g, h, a, carry); else seq_intra_any<false>(ex, w, lut, pd, g, h, a, carry);
         exc += w.excursions;
+        prev = a;
     }
     if (!compat && pd.deblock_on)
         for (int a = 0; a < n; a++) seq_deblock_mb(ex, w, pd, g, a);

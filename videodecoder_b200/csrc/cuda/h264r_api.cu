@@ -601,6 +601,19 @@ int h264r_last_flush_kernel_ms(h264r_ctx* ctx, float ms[H264R_KERNEL_FAMILIES], 
     return H264R_OK;
 }
 
+int h264r_last_flush_launch_ms(h264r_ctx* ctx, float* ms, int* family, int cap)
+{
+    if (!ctx || !ms || !family || cap < 0) return H264R_E_INVAL;
+    CU(cudaSetDevice(ctx->device));
+    int n = 0;
+    for (int i = 0; i < ctx->kev_used && n < cap; i += 2, n++) {
+        CU(cudaEventSynchronize(ctx->kev[i + 1]));
+        CU(cudaEventElapsedTime(&ms[n], ctx->kev[i], ctx->kev[i + 1]));
+        family[n] = ctx->kev_family[i / 2];
+    }
+    return n;
+}
+
 int h264r_mark(h264r_ctx* ctx, int slot)
 {
     if (!ctx || slot < 0 || slot > 3) return H264R_E_INVAL;

@@ -61,12 +61,16 @@ struct PicDesc {
 };
 
 // Shared working set of one warp (one macroblock in flight).
-constexpr int TILE_P = 28;                // pitch of the intra luma tile
+// Intra tiles: rows are 16-byte aligned so that whole rows move as 128-/64-bit words.
+constexpr int TILE_P = 48, TILE_X0 = 16;  // luma sample (x, y), x = -16..31, y = -1..15, at tile[(y+1)*TILE_P + x + TILE_X0]
+constexpr int CTILE_P = 16, CTILE_X0 = 8; // chroma sample (x, y), x = -8..7, y = -1..7, at ctile[p][(y+1)*CTILE_P + x + CTILE_X0]
+#define H264R_TI(x, y) (((y) + 1) * TILE_P + (x) + TILE_X0)
+#define H264R_CTI(x, y) (((y) + 1) * CTILE_P + (x) + CTILE_X0)
 struct alignas(16) MbWork {
     int16_t coef[24][16];                 // coefficient levels of the MB, block-major
     int16_t res[384];                     // residual: Y 16x16, then U 8x8, then V 8x8
-    uint8_t tile[17 * TILE_P];            // luma samples x=-1..23, y=-1..15 at tile[(y+1)*TILE_P + x+1]
-    uint8_t ctile[2][9 * 12];             // chroma samples x=-1..7, y=-1..7 at [(y+1)*12 + x+1]
+    uint8_t tile[17 * TILE_P];            // luma samples x=-1..23, y=-1..15 at tile[H264R_TI(x, y)]
+    uint8_t ctile[2][9 * CTILE_P];        // chroma samples x=-1..7, y=-1..7 at ctile[p][H264R_CTI(x, y)]
     uint8_t e8[28];                       // Intra8x8 filtered edge
     uint8_t dtile[24 * 24];               // deblocking luma tile x,y=-4..15 at [(y+4)*24 + x+4]
     uint8_t dctile[2][12 * 12];           // deblocking chroma tiles x,y=-2..7 at [(y+2)*12 + x+2]
@@ -339,7 +343,7 @@ HD void phase_inter_luma(MbWork& w, const PicDesc& pd, const Geometry& g, const 
             int v = luma_interp<COMPAT>(R, x0 + x + (mvx >> 2), ys + y + (mvy >> 2), mvx & 3, mvy & 3);
             if (pd.weighted_pred) v = weight_pred(v, pd.luma_log2_wd, pd.luma_weight[ri], pd.luma_offset[ri]);
             int px = bx * 4 + x, py = by * 4 + y;
-            w.tile[(py + 1) * TILE_P + px + 1] = recon_luma<COMPAT>(v + w.res[py * 16 + px], exc);
+            w.tile[H264R_TI(px, py)] = recon_luma<COMPAT>(v + w.res[py * 16 + px], exc);
         }
     }
     if (exc) {
@@ -365,7 +369,7 @@ HD void phase_inter_chroma(MbWork& w, const PicDesc& pd, const Geometry& g, cons
     if (COMPAT) {
         for (int k = 0; k < 4; k++) {
             int cx = bx * 2 + (k & 1), cy = by * 2 + (k >> 1);
-            w.ctile[plane][(cy + 1) * 12 + cx + 1] = (uint8_t)w.res[256 + plane * 64 + cy * 8 + cx];
+            w.ctile[plane][H264R_CTI(cx, cy)] = (uint8_t)w.res[256 + plane * 64 + cy * 8 + cx];
         }
         return;
     }
@@ -383,7 +387,7 @@ HD void phase_inter_chroma(MbWork& w, const PicDesc& pd, const Geometry& g, cons
         int C = H264R_LDG(ref + (size_t)yb * g.pitch_c + xa), D = H264R_LDG(ref + (size_t)yb * g.pitch_c + xb);
         int v = ((8 - xf) * (8 - yf) * A + xf * (8 - yf) * B + (8 - xf) * yf * C + xf * yf * D + 32) >> 6;
         if (pd.weighted_pred) v = weight_pred(v, pd.chroma_log2_wd, pd.chroma_weight[ri][plane], pd.chroma_offset[ri][plane]);
-        w.ctile[plane][(cy + 1) * 12 + cx + 1] = recon_chroma<false>(v + w.res[256 + plane * 64 + cy * 8 + cx]);
+        w.ctile[plane][H264R_CTI(cx, cy)] = recon_chroma<false>(v + w.res[256 + plane * 64 + cy * 8 + cx]);
     }
 }
 
@@ -393,14 +397,14 @@ HD void phase_store(const MbWork& w, const PicDesc& pd, const Geometry& g, int a
 {
     int mbx = a % g.w_mbs, mby = a / g.w_mbs;
     if (lane < 16) {
-        const uint8_t* s = &w.tile[(lane + 1) * TILE_P + 1];
+        const uint8_t* s = &w.tile[H264R_TI(0, lane)];
         uint32_t v[4];
         for (int k = 0; k < 4; k++) v[k] = s[4 * k] | (s[4 * k + 1] << 8) | (s[4 * k + 2] << 16) | ((uint32_t)s[4 * k + 3] << 24);
         uint4* d = reinterpret_cast<uint4*>(pd.y + (size_t)(mby * 16 + lane) * g.pitch_y + mbx * 16);
         *d = uint4{v[0], v[1], v[2], v[3]};
     } else {
         int plane = (lane - 16) >> 3, row = (lane - 16) & 7;
-        const uint8_t* s = &w.ctile[plane][(row + 1) * 12 + 1];
+        const uint8_t* s = &w.ctile[plane][H264R_CTI(0, row)];
         uint32_t v0 = s[0] | (s[1] << 8) | (s[2] << 16) | ((uint32_t)s[3] << 24);
         uint32_t v1 = s[4] | (s[5] << 8) | (s[6] << 16) | ((uint32_t)s[7] << 24);
         uint2* d = reinterpret_cast<uint2*>((plane ? pd.v : pd.u) + (size_t)(mby * 8 + row) * g.pitch_c + mbx * 8);
@@ -423,26 +427,26 @@ HD void phase_intra_edges(MbWork& w, const PicDesc& pd, const Geometry& g, const
     if (lane < 25) {
         int x = lane - 1;     // -1..23
         bool ok = x < 0 ? D : (x < 16 ? B : C);
-        w.tile[lane] = ok ? H264R_LDCG(y + (size_t)(mby * 16 - 1) * g.pitch_y + mbx * 16 + x) : 0;
+        w.tile[H264R_TI(x, -1)] = ok ? H264R_LDCG(y + (size_t)(mby * 16 - 1) * g.pitch_y + mbx * 16 + x) : 0;
     }
-    if (lane < 16) w.tile[(lane + 1) * TILE_P] = A ? H264R_LDCG(y + (size_t)(mby * 16 + lane) * g.pitch_y + mbx * 16 - 1) : 0;
+    if (lane < 16) w.tile[H264R_TI(-1, lane)] = A ? H264R_LDCG(y + (size_t)(mby * 16 + lane) * g.pitch_y + mbx * 16 - 1) : 0;
     if (chroma) {
         int plane = lane >> 4, l = lane & 15;
         const uint8_t* c = plane ? pd.v : pd.u;
         if (l < 9) {
             int x = l - 1;
             bool ok = x < 0 ? D : B;
-            w.ctile[plane][l] = ok ? H264R_LDCG(c + (size_t)(mby * 8 - 1) * g.pitch_c + mbx * 8 + x) : 0;
+            w.ctile[plane][H264R_CTI(x, -1)] = ok ? H264R_LDCG(c + (size_t)(mby * 8 - 1) * g.pitch_c + mbx * 8 + x) : 0;
         } else if (l < 16) {
             // rows 0..6 here, row 7 below
             int r = l - 9;
-            w.ctile[plane][(r + 1) * 12] = A ? H264R_LDCG(c + (size_t)(mby * 8 + r) * g.pitch_c + mbx * 8 - 1) : 0;
-            if (r == 6) w.ctile[plane][8 * 12] = A ? H264R_LDCG(c + (size_t)(mby * 8 + 7) * g.pitch_c + mbx * 8 - 1) : 0;
+            w.ctile[plane][H264R_CTI(-1, r)] = A ? H264R_LDCG(c + (size_t)(mby * 8 + r) * g.pitch_c + mbx * 8 - 1) : 0;
+            if (r == 6) w.ctile[plane][H264R_CTI(-1, 7)] = A ? H264R_LDCG(c + (size_t)(mby * 8 + 7) * g.pitch_c + mbx * 8 - 1) : 0;
         }
     }
 }
 
-#define TL(x, y) w.tile[((y) + 1) * TILE_P + (x) + 1]
+#define TL(x, y) w.tile[H264R_TI(x, y)]
 
 // Phase I16: Intra16x16, 8 samples per lane (row lane >> 1, columns 8*(lane & 1) ..).
 // Reference: macroblock::Prediction_Intra16x16_{V,H,DC,Plane} (h264/macroblock.cpp:1373-1441).
@@ -707,7 +711,7 @@ HD void phase_intra_chroma(MbWork& w, const h264r_mb_hdr& h, int lane)
     int plane = lane >> 4, l = lane & 15;
     int y = l >> 1, x0 = (l & 1) * 4;
     uint8_t* t = w.ctile[plane];
-#define CT(x, y) t[((y) + 1) * 12 + (x) + 1]
+#define CT(x, y) t[H264R_CTI(x, y)]
     int out[4];
     if (COMPAT) {
         for (int k = 0; k < 4; k++) out[k] = (uint8_t)w.res[256 + plane * 64 + y * 8 + x0 + k];

@@ -1,0 +1,350 @@
+// h264r_intra.cuh -- K1+K2 for Intra4x4 / Intra16x16 macroblocks, latency version.
+//
+// An I picture is a wavefront whose critical path is (W + 2H) macroblocks long (h264r_kernels.cuh), so what
+// matters here is the time ONE warp needs for ONE macroblock.  Same results as the generic phases of
+// h264r_core.cuh (phase_intra_edges / phase_residual / phase_intra16 / phase_intra4 / phase_store, which stay
+// as the plain statement of the arithmetic and as the path for Intra8x8), restructured:
+//   * residual with the register transform of h264r_mc.cuh (plus the Intra16x16 DC Hadamard);
+//   * neighbouring samples arrive as 32-bit words (top row) and, when the warp has just finished the
+//     macroblock to the left, from its own tile (no trip to L2 for the left column);
+//   * Intra4x4: every directional mode is (w0 e[i] + w1 e[i+1] + w2 e[i+2] + round) >> shift over the 13
+//     neighbouring samples e = L K J I M A..H; (i, w, shift) per (mode, sample) comes from a 144-entry
+//     table, and the sixteen blocks run as a 10-step anti-diagonal wavefront INSIDE the macroblock, two
+//     blocks per step on the two half-warps (block (bx,by) needs steps d-1, d-2, d-3 only, d = bx + 2by);
+//   * Intra16x16: sums and plane gradients with dp4a on the word-aligned top row, 8 packed samples per
+//     lane, stored straight to the frame.
+// Every function is a per-lane phase, so the host emulator of the CPU test-suite runs this code too.
+#pragma once
+#include "h264r_mc.cuh"
+
+namespace h264r {
+
+// ---- K1 for any 4x4-transform macroblock ---------------------------------------------------------------
+// Lane b < 24 owns block b (luma4x4BlkIdx order, then Cb, Cr) and writes its residual into res[384]
+// (Y 16x16, U 8x8, V 8x8).  Inter / Intra4x4: luma blocks whose coded_block_pattern bit is clear are zero
+// (the reference zero-fills them, h264/residual.cpp:44-46).  Intra16x16: DC levels go through the 4x4
+// Hadamard (reference residual::Decode_Intra16x16, h264/residual.cpp:286-319) and bypass the scaling.
+template <bool COMPAT>
+HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane)
+{
+    if (lane >= 24) return;
+    const int16_t* cbase = pd.coeff + (size_t)a * H264R_COEFF_PER_MB;
+    const int cbp_l = h.cbp & 15, cbp_c = (h.cbp >> 4) & 3;
+    const bool luma = lane < 16, i16 = h.mb_class == H264R_MB_I16x16;
+    bool active = luma ? (i16 || ((cbp_l >> (lane >> 2)) & 1) != 0) : cbp_c != 0;
+    int r[16];
+    bool zero = true;
+    if (active) {
+        const int4* src = reinterpret_cast<const int4*>(cbase) + lane * 2;
+        int4 v0 = H264R_LDG(src), v1 = (luma || cbp_c == 2) ? H264R_LDG(src + 1) : int4{0, 0, 0, 0};
+        if (!luma && cbp_c != 2) { v0.x &= 0xffff; v0.y = v0.z = v0.w = 0; }        // DC only: AC levels are not coded
+        int c[16];
+        const int w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int k = 0; k < 8; k++) { c[2 * k] = (int)(int16_t)(w[k] & 0xffff); c[2 * k + 1] = w[k] >> 16; }
+        int qp = h.qp_y;
+        bool bypass = false;
+        if (luma && i16) {
+            // element (i, j) of T * DC * T for the block at raster (i, j); DC(k, l) sits in slot 0 of the block at raster (k, l)
+            const int ras = blk_raster(lane), i = ras >> 2, j = ras & 3;
+            int f = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int t = 0;
+#pragma unroll
+                for (int l = 0; l < 4; l++) {
+                    int dc = H264R_LDG(cbase + blk_raster(k * 4 + l) * 16);
+                    t += ((0xA6C0 >> (l * 4 + j)) & 1) ? -dc : dc;       // T rows {++++},{++--},{+--+},{+-+-}: bit = minus
+                }
+                f += ((0xA6C0 >> (i * 4 + k)) & 1) ? -t : t;
+            }
+            const int v0t[6] = {10, 11, 13, 14, 16, 18};
+            int s = (qp * 43) >> 8, m = qp - 6 * s, ls = 16 * v0t[m];
+            c[0] = (s >= 6) ? (f * ls) * (1 << (s - 6)) : ((f * ls + (1 << (5 - s))) >> (6 - s));
+            bypass = true;
+        }
+        if (!luma) {
+            int plane = (lane - 16) >> 2, b = (lane - 16) & 3;
+            qp = plane ? h.qp_cr : h.qp_cb;
+            const int16_t* dcp = cbase + (16 + plane * 4) * 16;
+            int c0 = H264R_LDG(dcp), c1 = H264R_LDG(dcp + 16), c2 = H264R_LDG(dcp + 32), c3 = H264R_LDG(dcp + 48);
+            int f;
+            if (COMPAT) f = (b == 0 || b == 3) ? c3 : -c3;      // reference's chroma DC product (h264/matrix.cpp:150-171)
+            else f = c0 + ((b & 1) ? -c1 : c1) + ((b & 2) ? -c2 : c2) + ((b == 1 || b == 2) ? -c3 : c3);
+            const int v0t[6] = {10, 11, 13, 14, 16, 18};
+            int s = (qp * 43) >> 8, m = qp - 6 * s;
+            c[0] = ((f * 16 * v0t[m]) * (1 << s)) >> 5;
+            bypass = true;
+        }
+        int nz = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) nz |= c[k];
+        if (nz) {
+            Dequant q = make_dequant(qp);
+            idct4_fast(c, q, bypass, r);
+            zero = false;
+        }
+    }
+    // store the block: 4 rows of 4 int16 (8 bytes each)
+    int16_t* dst;
+    int pitch;
+    if (luma) { int ras = blk_raster(lane); dst = res + (ras >> 2) * 64 + (ras & 3) * 4; pitch = 16; }
+    else { int plane = (lane - 16) >> 2, b = (lane - 16) & 3; dst = res + 256 + plane * 64 + (b >> 1) * 32 + (b & 1) * 4; pitch = 8; }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t lo = 0, hi = 0;
+        if (!zero) {
+            lo = (uint32_t)(sat16(r[i * 4]) & 0xffff) | ((uint32_t)sat16(r[i * 4 + 1]) << 16);
+            hi = (uint32_t)(sat16(r[i * 4 + 2]) & 0xffff) | ((uint32_t)sat16(r[i * 4 + 3]) << 16);
+        }
+        *reinterpret_cast<uint2*>(dst + i * pitch) = uint2{lo, hi};
+    }
+}
+
+// ---- neighbouring samples ----------------------------------------------------------------------------------
+#define TL(x, y) w.tile[H264R_TI(x, y)]
+#define CTP(p, x, y) w.ctile[p][H264R_CTI(x, y)]
+
+// Tile borders of the macroblock: row y = -1 for x = -1..23 as seven words (lanes 0..6), column x = -1 for
+// y = 0..15 (lanes 8..23), chroma borders when `chroma` (top: lanes 24..29, left: lanes 8..23).  Unavailable
+// neighbours read as 0.  `carry`: the warp's tiles still hold the macroblock to the left, whose last column
+// is the left neighbour.  Other neighbours were written by other warps of the same kernel: ld.global.cg.
+HD void phase_intra_edges_fast(MbWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane, bool chroma, bool carry)
+{
+    const int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    const bool A = h.flags & H264R_AVAIL_A, B = h.flags & H264R_AVAIL_B, C = h.flags & H264R_AVAIL_C, D = h.flags & H264R_AVAIL_D;
+    if (lane < 7) {
+        const int x = lane * 4 - 4;
+        const bool ok = lane == 0 ? D : (lane <= 4 ? B : C);
+        uint32_t v = 0;
+        if (ok) v = H264R_LDCG(reinterpret_cast<const uint32_t*>(pd.y + (ptrdiff_t)(mby * 16 - 1) * g.pitch_y + mbx * 16 + x));
+        if (lane == 0) v &= 0xff000000u;
+        *reinterpret_cast<uint32_t*>(&TL(x, -1)) = v;
+    } else if (lane >= 8 && lane < 24) {
+        const int yy = lane - 8;
+        uint8_t v = 0;
+        if (A) v = carry ? TL(15, yy) : H264R_LDCG(pd.y + (ptrdiff_t)(mby * 16 + yy) * g.pitch_y + mbx * 16 - 1);
+        TL(-1, yy) = v;
+        if (chroma) {
+            const int p = yy >> 3, r = yy & 7;
+            const uint8_t* c = p ? pd.v : pd.u;
+            uint8_t cv = 0;
+            if (A) cv = carry ? CTP(p, 7, r) : H264R_LDCG(c + (ptrdiff_t)(mby * 8 + r) * g.pitch_c + mbx * 8 - 1);
+            CTP(p, -1, r) = cv;
+        }
+    } else if (chroma && lane >= 24 && lane < 30) {
+        const int p = (lane - 24) / 3, k = (lane - 24) - p * 3, x = k * 4 - 4;
+        const uint8_t* c = p ? pd.v : pd.u;
+        const bool ok = k == 0 ? D : B;
+        uint32_t v = 0;
+        if (ok) v = H264R_LDCG(reinterpret_cast<const uint32_t*>(c + (ptrdiff_t)(mby * 8 - 1) * g.pitch_c + mbx * 8 + x));
+        if (k == 0) v &= 0xff000000u;
+        *reinterpret_cast<uint32_t*>(&CTP(p, x, -1)) = v;
+    }
+}
+
+// ---- Intra16x16 --------------------------------------------------------------------------------------------
+// Lane -> row (lane >> 1), columns 8*(lane & 1)..+7.  Prediction (reference macroblock::Prediction_Intra16x16_
+// {V,H,DC,Plane}, h264/macroblock.cpp:1373-1441) + residual; writes the tile and the frame.
+template <bool COMPAT>
+HD void phase_intra16_fast(MbWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane)
+{
+    const bool A = h.flags & H264R_AVAIL_A, B = h.flags & H264R_AVAIL_B;
+    const int mode = h.intra_modes & 3;
+    const int row = lane >> 1, c0 = (lane & 1) * 8;
+    const int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    uint32_t p0, p1;
+    if (mode == 0) {
+        p0 = *reinterpret_cast<const uint32_t*>(&TL(c0, -1));
+        p1 = *reinterpret_cast<const uint32_t*>(&TL(c0 + 4, -1));
+    } else if (mode == 1) {
+        p0 = p1 = (uint32_t)TL(-1, row) * 0x01010101u;
+    } else if (mode == 2) {
+        int st = 0, sl = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) st = dp4a_us(*reinterpret_cast<const uint32_t*>(&TL(4 * k, -1)), 0x01010101u, st);
+#pragma unroll
+        for (int k = 0; k < 16; k++) sl += TL(-1, k);
+        int dc;
+        if (A && B) dc = (sl + st + 16) >> 5;
+        else if (A) dc = (sl + 8) >> 4;
+        else if (B) {
+            if (COMPAT) {
+                // D5: top-only DC sums column 15 of the MB above (h264/macroblock.cpp:1410-1411)
+                int sc = 0;
+                for (int k = 0; k < 16; k++) sc += H264R_LDCG(pd.y + (ptrdiff_t)(mby * 16 - 16 + k) * g.pitch_y + mbx * 16 + 15);
+                dc = (sc + 8) >> 4;
+            } else dc = (st + 8) >> 4;
+        } else dc = 128;
+        p0 = p1 = (uint32_t)dc * 0x01010101u;
+    } else {
+        // plane: H = sum i*(top[7+i] - top[7-i]), V likewise on the left column, i = 1..8 (index -1 = corner)
+        const uint32_t wm4 = *reinterpret_cast<const uint32_t*>(&TL(-4, -1)), w0 = *reinterpret_cast<const uint32_t*>(&TL(0, -1)),
+                       w4 = *reinterpret_cast<const uint32_t*>(&TL(4, -1)), w8 = *reinterpret_cast<const uint32_t*>(&TL(8, -1)),
+                       w12 = *reinterpret_cast<const uint32_t*>(&TL(12, -1));
+        int Hs = dp4a_us(wm4, taps4(0, 0, 0, -8), 0);
+        Hs = dp4a_us(w0, taps4(-7, -6, -5, -4), Hs);
+        Hs = dp4a_us(w4, taps4(-3, -2, -1, 0), Hs);
+        Hs = dp4a_us(w8, taps4(1, 2, 3, 4), Hs);
+        Hs = dp4a_us(w12, taps4(5, 6, 7, 8), Hs);
+        int Vs = 0;
+#pragma unroll
+        for (int i = 1; i <= 8; i++) Vs += i * ((int)TL(-1, 7 + i) - (int)TL(-1, 7 - i));
+        const int pa = 16 * ((int)TL(15, -1) + (int)TL(-1, 15)), pb = (5 * Hs + 32) >> 6, pc = (5 * Vs + 32) >> 6;
+        int v = pa + pb * (c0 - 7) + pc * (row - 7) + 16;
+        int s[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { s[k] = v >> 5; v += pb; }
+        p0 = pack_sat_u8(s[0], s[1], s[2], s[3]);
+        p1 = pack_sat_u8(s[4], s[5], s[6], s[7]);
+    }
+    uint32_t exc = add_residual<COMPAT>(p0, &w.res[row * 16 + c0], p0);
+    exc += add_residual<COMPAT>(p1, &w.res[row * 16 + c0 + 4], p1);
+    *reinterpret_cast<uint2*>(&TL(c0, row)) = uint2{p0, p1};
+    *reinterpret_cast<uint2*>(pd.y + (size_t)(mby * 16 + row) * g.pitch_y + mbx * 16 + c0) = uint2{p0, p1};
+    if (exc) {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(&w.excursions, exc);
+#else
+        w.excursions += exc;
+#endif
+    }
+}
+
+// ---- Intra4x4 ----------------------------------------------------------------------------------------------
+// Table entry for (mode, sample x, y): bits 0-3 i0, 4-5 w0, 6-7 w1, 8-9 w2, 10-11 shift;
+// pred = (w0 e[i0] + w1 e[i0+1] + w2 e[i0+2] + (1 << shift >> 1)) >> shift over e = L K J I M A B C D E F G H
+// (reference Prediction_Intra4x4_* , h264/macroblock.cpp:1037-1365 = ITU-T H.264 8.3.1.2.1-8.3.1.2.9).  Mode 2 (DC)
+// is not table driven.
+HD uint16_t intra4_entry(int mode, int x, int y)
+{
+    int i0 = 0, w0 = 1, w1 = 0, w2 = 0, sh = 0;
+    switch (mode) {
+    case 0: i0 = 5 + x; break;
+    case 1: i0 = 3 - y; break;
+    case 3:
+        if (x == 3 && y == 3) { i0 = 11; w1 = 3; sh = 2; }
+        else { i0 = 5 + x + y; w1 = 2; w2 = 1; sh = 2; }
+        break;
+    case 4: i0 = 3 - y + x; w1 = 2; w2 = 1; sh = 2; break;
+    case 5: {
+        int z = 2 * x - y, i = x - (y >> 1);
+        if (z >= 0 && !(z & 1)) { i0 = 4 + i; w1 = 1; sh = 1; }
+        else if (z >= 0) { i0 = 3 + i; w1 = 2; w2 = 1; sh = 2; }
+        else if (z == -1) { i0 = 3; w1 = 2; w2 = 1; sh = 2; }
+        else { i0 = 4 - y; w1 = 2; w2 = 1; sh = 2; }
+        break;
+    }
+    case 6: {
+        int z = 2 * y - x, i = y - (x >> 1);
+        if (z >= 0 && !(z & 1)) { i0 = 3 - i; w1 = 1; sh = 1; }
+        else if (z >= 0) { i0 = 3 - i; w1 = 2; w2 = 1; sh = 2; }
+        else if (z == -1) { i0 = 3; w1 = 2; w2 = 1; sh = 2; }
+        else { i0 = 2 + x; w1 = 2; w2 = 1; sh = 2; }
+        break;
+    }
+    case 7: {
+        int i = x + (y >> 1);
+        i0 = 5 + i;
+        if (!(y & 1)) { w1 = 1; sh = 1; } else { w1 = 2; w2 = 1; sh = 2; }
+        break;
+    }
+    case 8: {
+        int z = x + 2 * y, i = y + (x >> 1);
+        if (z > 5) { i0 = 0; }
+        else if (z == 5) { i0 = 0; w0 = 3; w1 = 1; sh = 2; }
+        else if (!(z & 1)) { i0 = 2 - i; w1 = 1; sh = 1; }
+        else { i0 = 1 - i; w1 = 2; w2 = 1; sh = 2; }
+        break;
+    }
+    default: break;
+    }
+    return (uint16_t)(i0 | (w0 << 4) | (w1 << 6) | (w2 << 8) | (sh << 10));
+}
+constexpr int INTRA4_LUT_SIZE = 9 * 16;
+HD void intra4_lut_fill(uint16_t* lut, int first, int stride)
+{
+    for (int k = first; k < INTRA4_LUT_SIZE; k += stride) lut[k] = intra4_entry(k >> 4, k & 3, (k >> 2) & 3);
+}
+
+// Step d = 0..9 of the macroblock's inner wavefront: blocks (bx, by) with bx + 2 by = d; half-warp `lane >> 4`
+// takes the block with by = by_min + (lane >> 4); lane & 15 = sample.  Availability and the up-right
+// substitution rule follow macroblock::Calc / get_4x4Neighbour (h264/macroblock.cpp:28-33, 1092-1110).
+template <bool COMPAT>
+HD void phase_intra4_pair(MbWork& w, const h264r_mb_hdr& h, const uint16_t* lut, int d, int lane)
+{
+    const int by_min = d > 3 ? (d - 2) >> 1 : 0, by_max = (d >> 1) < 3 ? (d >> 1) : 3;
+    const int by = by_min + (lane >> 4);
+    if (by > by_max) return;
+    const int bx = d - 2 * by, pos = lane & 15, x = pos & 3, y = pos >> 2;
+    const int ras = by * 4 + bx, blk = blk_raster(ras);
+    const int mode = (h.u.pred4x4[blk >> 1] >> ((blk & 1) * 4)) & 15;
+    const int X = bx * 4, Y = by * 4;
+    int v;
+    if (mode == 2) {
+        const bool left_ok = bx > 0 || (h.flags & H264R_AVAIL_A), top_ok = by > 0 || (h.flags & H264R_AVAIL_B);
+        const int st = dp4a_us(*reinterpret_cast<const uint32_t*>(&TL(X, Y - 1)), 0x01010101u, 0);
+        const int sl = (int)TL(X - 1, Y) + (int)TL(X - 1, Y + 1) + (int)TL(X - 1, Y + 2) + (int)TL(X - 1, Y + 3);
+        if (left_ok && top_ok) v = (st + sl + 4) >> 3;
+        else if (left_ok) v = (sl + 2) >> 2;
+        else if (top_ok) v = (st + 2) >> 2;
+        else v = 128;
+    } else {
+        bool tr_ok;
+        if (blk == 3 || blk == 11) tr_ok = false;
+        else if (bx == 3) tr_ok = (by == 0) && (h.flags & H264R_AVAIL_C) && (h.flags & H264R_AVAIL_B);
+        else if (by > 0) tr_ok = true;
+        else tr_ok = (h.flags & H264R_AVAIL_B) != 0;
+        const int trmax = tr_ok ? 7 : 3;
+        const uint32_t e = lut[mode * 16 + pos];
+        const int i0 = (int)(e & 15u);
+        const uint8_t* left = &TL(X - 1, Y + 3), * top = &TL(X, Y - 1);
+        int acc = (1 << ((e >> 10) & 3)) >> 1;
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            const int i = i0 + t, wt = (int)((e >> (4 + 2 * t)) & 3u);
+            const int k = i - 5 < trmax ? i - 5 : trmax;
+            const uint8_t* p = i <= 4 ? left - i * TILE_P : top + k;
+            acc += wt * (int)*p;
+        }
+        v = acc >> ((e >> 10) & 3);
+    }
+    uint32_t exc = 0;
+    TL(X + x, Y + y) = recon_luma<COMPAT>(v + w.res[(Y + y) * 16 + X + x], exc);
+    if (exc) {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(&w.excursions, exc);
+#else
+        w.excursions += exc;
+#endif
+    }
+}
+
+// ---- stores --------------------------------------------------------------------------------------------------
+// luma rows of the tile: lanes 0..15, one 128-bit row each
+HD void store_luma_tile(const MbWork& w, const PicDesc& pd, const Geometry& g, int a, int lane)
+{
+    if (lane >= 16) return;
+    const int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    *reinterpret_cast<uint4*>(pd.y + (size_t)(mby * 16 + lane) * g.pitch_y + mbx * 16) = *reinterpret_cast<const uint4*>(&TL(0, lane));
+}
+// chroma rows: lanes 16..31, one 64-bit row each.  COMPAT: the reference has no chroma prediction, sample =
+// residual (low 8 bits; D4, h264/macroblock.cpp:1477-1480); otherwise from the chroma tiles.
+template <bool COMPAT>
+HD void store_chroma(const MbWork& w, const PicDesc& pd, const Geometry& g, int a, int lane)
+{
+    if (lane < 16) return;
+    const int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    const int p = (lane - 16) >> 3, row = (lane - 16) & 7;
+    uint2 v;
+    if (COMPAT) {
+        const uint4 r = *reinterpret_cast<const uint4*>(&w.res[256 + p * 64 + row * 8]);
+        v = uint2{prmt(r.x, r.y, 0x6420), prmt(r.z, r.w, 0x6420)};
+    } else v = *reinterpret_cast<const uint2*>(&CTP(p, 0, row));
+    *reinterpret_cast<uint2*>((p ? pd.v : pd.u) + (size_t)(mby * 8 + row) * g.pitch_c + mbx * 8) = v;
+}
+
+#undef TL
+#undef CTP
+
+}  // namespace h264r

@@ -109,9 +109,11 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_intra_rows(const PicDesc* __
                                                               uint32_t* excursions)
 {
     __shared__ MbWork work[ROW_WARPS];
-    __shared__ uint32_t s_mask[ROW_WARPS][ROW_MASK_WORDS];
+    __shared__ uint32_t s_mask[ROW_WARPS][2][ROW_MASK_WORDS + 1];     // intra bitmaps of this row and of the row above
+    __shared__ uint16_t s_lut[INTRA4_LUT_SIZE];
+    intra4_lut_fill(s_lut, threadIdx.x, blockDim.x);
     const int W = g.w_mbs, H = g.h_mbs;
-    const int flat = row_ticket(ticket);
+    const int flat = row_ticket(ticket);          // __syncthreads() inside: the table is complete
     if (flat >= n_pics * H) return;
     const int warp = threadIdx.x >> 5;
     WarpExec ex{(int)(threadIdx.x & 31)};
@@ -119,15 +121,17 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_intra_rows(const PicDesc* __
     const PicDesc& pd = descs[list[p]];
     int* prog = progress + (size_t)p * H;
     MbWork& w = work[warp];
-    uint32_t* mask = s_mask[warp];
-    // bitmap of the intra macroblocks of this row
+    uint32_t* mask = s_mask[warp][0];
+    uint32_t* above = s_mask[warp][1];
     const int n_words = (W + 31) >> 5;
     for (int k = 0; k < n_words; k++) {
         int x = k * 32 + ex.lane;
         bool intra = x < W && is_intra(H264R_LDG(&pd.hdr[row * W + x].mb_class));
-        uint32_t m = __ballot_sync(0xffffffffu, intra);
-        if (ex.lane == 0) mask[k] = m;
+        bool intra_up = row > 0 && x < W && is_intra(H264R_LDG(&pd.hdr[(row - 1) * W + x].mb_class));
+        uint32_t m = __ballot_sync(0xffffffffu, intra), mu = __ballot_sync(0xffffffffu, intra_up);
+        if (ex.lane == 0) { mask[k] = m; above[k] = mu; }
     }
+    if (ex.lane == 0) above[n_words] = 0;
     __syncwarp();
     auto next_intra = [&](int from) -> int {      // first intra macroblock at x >= from, or W
         for (int k = from >> 5; k < n_words; k++) {
@@ -137,18 +141,23 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_intra_rows(const PicDesc* __
         }
         return W;
     };
-    int x = next_intra(0);
+    int x = next_intra(0), prev = -2;
     if (ex.lane == 0 && x > 0) st_release_gpu(&prog[row], x);
     uint32_t exc = 0;
     while (x < W) {
         const int a = row * W + x;
         h264r_mb_hdr h = load_hdr(pd, a);
         if (row > 0) {
-            int need = x + 2 < W ? x + 2 : W;
-            wait_progress(&prog[row - 1], need);
+            // B, C, D are final unless they are intra macroblocks the row above has not reached yet: wait for the
+            // last intra one among (x-1, x, x+1) of the row above
+            int last = -1;
+            for (int xx = x + 1; xx >= x - 1 && xx >= 0; xx--)
+                if (xx < W && ((above[xx >> 5] >> (xx & 31)) & 1)) { last = xx; break; }
+            if (last >= 0) wait_progress(&prog[row - 1], last + 1);
         }
-        seq_intra_mb<COMPAT>(ex, w, pd, g, h, a);
+        seq_intra_any<COMPAT>(ex, w, s_lut, pd, g, h, a, prev == x - 1);
         exc += w.excursions;
+        prev = x;
         x = next_intra(x + 1);
         // ex() ended with __syncwarp(): every lane's stores precede lane 0's release
         if (ex.lane == 0) st_release_gpu(&prog[row], x);

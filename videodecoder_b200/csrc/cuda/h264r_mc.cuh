@@ -95,6 +95,16 @@ HD uint32_t clip255_s16x2(uint32_t a)
     return (uint32_t)clip1(lo) | ((uint32_t)clip1(hi) << 16);
 #endif
 }
+// per 16-bit half clamp to [-32000, 32000]
+HD uint32_t clamp_s16x2(uint32_t a)
+{
+#if defined(__CUDA_ARCH__)
+    return __vmaxs2(__vmins2(a, 0x7d007d00u), 0x83008300u);
+#else
+    int lo = (int16_t)(a & 0xffff), hi = (int16_t)(a >> 16);
+    return (uint32_t)(clip3(-32000, 32000, lo) & 0xffff) | ((uint32_t)(clip3(-32000, 32000, hi) & 0xffff) << 16);
+#endif
+}
 HD constexpr uint32_t taps4(int a, int b, int c, int d)
 {
     return (uint32_t)(a & 255) | ((uint32_t)(b & 255) << 8) | ((uint32_t)(c & 255) << 16) | ((uint32_t)(d & 255) << 24);
@@ -180,66 +190,9 @@ HD void idct4_fast(const int c[16], const Dequant& q, bool dc_bypass, int r[16])
     }
 }
 
-// Phase: residual of an inter macroblock (4x4 transform) straight from global memory into res[].
-// Lane b < 24 owns block b.  Uncoded blocks (coded_block_pattern bit clear: the reference zero-fills
-// them, h264/residual.cpp:44-46) are neither loaded nor transformed and write zeros.
+// K1 for any 4x4-transform macroblock: h264r_intra.cuh
 template <bool COMPAT>
-HD void phase_residual_inter_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane)
-{
-    if (lane >= 24) return;
-    const int16_t* cbase = pd.coeff + (size_t)a * H264R_COEFF_PER_MB;
-    const int cbp_l = h.cbp & 15, cbp_c = (h.cbp >> 4) & 3;
-    bool luma = lane < 16;
-    bool active = luma ? ((cbp_l >> (lane >> 2)) & 1) != 0 : cbp_c != 0;
-    int r[16];
-    bool zero = true;
-    if (active) {
-        const int4* src = reinterpret_cast<const int4*>(cbase) + lane * 2;
-        int4 v0 = H264R_LDG(src), v1 = (luma || cbp_c == 2) ? H264R_LDG(src + 1) : int4{0, 0, 0, 0};
-        if (!luma && cbp_c != 2) { v0.x &= 0xffff; v0.y = v0.z = v0.w = 0; }        // DC only: AC levels are not coded
-        int c[16];
-        const int w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-        for (int k = 0; k < 8; k++) { c[2 * k] = (int)(int16_t)(w[k] & 0xffff); c[2 * k + 1] = w[k] >> 16; }
-        int qp = h.qp_y;
-        bool bypass = false;
-        if (!luma) {
-            int plane = (lane - 16) >> 2, b = (lane - 16) & 3;
-            qp = plane ? h.qp_cr : h.qp_cb;
-            const int16_t* dcp = cbase + (16 + plane * 4) * 16;
-            int c0 = H264R_LDG(dcp), c1 = H264R_LDG(dcp + 16), c2 = H264R_LDG(dcp + 32), c3 = H264R_LDG(dcp + 48);
-            int f;
-            if (COMPAT) f = (b == 0 || b == 3) ? c3 : -c3;      // reference's chroma DC product (h264/matrix.cpp:150-171)
-            else f = c0 + ((b & 1) ? -c1 : c1) + ((b & 2) ? -c2 : c2) + ((b == 1 || b == 2) ? -c3 : c3);
-            const int v0t[6] = {10, 11, 13, 14, 16, 18};
-            int s = (qp * 43) >> 8, m = qp - 6 * s;
-            c[0] = ((f * 16 * v0t[m]) * (1 << s)) >> 5;
-            bypass = true;
-        }
-        int nz = 0;
-#pragma unroll
-        for (int k = 0; k < 16; k++) nz |= c[k];
-        if (nz) {
-            Dequant q = make_dequant(qp);
-            idct4_fast(c, q, bypass, r);
-            zero = false;
-        }
-    }
-    // store the block: 4 rows of 4 int16 (8 bytes each)
-    int16_t* dst;
-    int pitch;
-    if (luma) { int ras = blk_raster(lane); dst = res + (ras >> 2) * 64 + (ras & 3) * 4; pitch = 16; }
-    else { int plane = (lane - 16) >> 2, b = (lane - 16) & 3; dst = res + 256 + plane * 64 + (b >> 1) * 32 + (b & 1) * 4; pitch = 8; }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        uint32_t lo = 0, hi = 0;
-        if (!zero) {
-            lo = (uint32_t)(sat16(r[i * 4]) & 0xffff) | ((uint32_t)sat16(r[i * 4 + 1]) << 16);
-            hi = (uint32_t)(sat16(r[i * 4 + 2]) & 0xffff) | ((uint32_t)sat16(r[i * 4 + 3]) << 16);
-        }
-        *reinterpret_cast<uint2*>(dst + i * pitch) = uint2{lo, hi};
-    }
-}
+HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane);
 
 // ---- motion vectors, window shape --------------------------------------------------------------------
 HD void load_mvs(const PicDesc& pd, int a, uint32_t mv[16])
@@ -489,7 +442,8 @@ HD void mc_patch(const uint32_t* wp, int pitch, const McSel& m, uint32_t out[2])
 template <bool COMPAT>
 HD uint32_t add_residual(uint32_t pred, const int16_t* res_row, uint32_t& packed)
 {
-    const uint2 r = *reinterpret_cast<const uint2*>(res_row);
+    uint2 r = *reinterpret_cast<const uint2*>(res_row);
+    if (!COMPAT) { r.x = clamp_s16x2(r.x); r.y = clamp_s16x2(r.y); }      // keeps pred + residual inside 16 bits; Clip1 gives the same sample
     uint32_t s0 = add_s16x2(prmt(pred, 0u, 0x4140), r.x), s1 = add_s16x2(prmt(pred, 0u, 0x4342), r.y);
     uint32_t n = 0;
     if ((s0 | s1) & 0xff00ff00u)
@@ -594,7 +548,7 @@ HD void seq_inter_mb_fast(Exec& ex, InterWork& w, const PicDesc& pd, const Geome
 {
     const bool coded = h.cbp != 0;
     ex([&](int lane) {
-        if (coded) phase_residual_inter_fast<COMPAT>(w.res, pd, h, a, lane);
+        if (coded) phase_residual_fast<COMPAT>(w.res, pd, h, a, lane);
         phase_inter_stage<COMPAT>(w, pd, g, h, a, lane);
     });
     ex([&](int lane) { phase_inter_compute<COMPAT>(w, pd, g, h, a, lane, coded); });

@@ -7,6 +7,7 @@
 #pragma once
 #include "h264r_core.cuh"
 #include "h264r_mc.cuh"
+#include "h264r_intra.cuh"
 
 namespace h264r {
 
@@ -90,6 +91,43 @@ HD void seq_intra_mb(Exec& ex, MbWork& w, const PicDesc& pd, const Geometry& g, 
         }
     }
     ex([&](int lane) { phase_store(w, pd, g, a, lane); });
+}
+
+// K1 + K2, latency version (h264r_intra.cuh) for Intra4x4 / Intra16x16; Intra8x8 takes the generic phases.
+// `carry`: the warp reconstructed the macroblock to the left immediately before (its tiles are still in w).
+template <bool COMPAT, class Exec>
+HD void seq_intra_any(Exec& ex, MbWork& w, const uint16_t* lut, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, bool carry)
+{
+    if (h.mb_class == H264R_MB_I8x8 || (h.flags & H264R_T8x8)) {
+        seq_intra_mb<COMPAT>(ex, w, pd, g, h, a);
+        return;
+    }
+    ex([&](int lane) {
+        if (lane == 0) w.excursions = 0;
+        phase_residual_fast<COMPAT>(w.res, pd, h, a, lane);
+        phase_intra_edges_fast(w, pd, g, h, a, lane, !COMPAT, carry);
+    });
+    if (h.mb_class == H264R_MB_I16x16) {
+        ex([&](int lane) {
+            phase_intra16_fast<COMPAT>(w, pd, g, h, a, lane);
+            if (COMPAT) store_chroma<true>(w, pd, g, a, lane);
+            else phase_intra_chroma<false>(w, h, lane);
+        });
+        if (!COMPAT) ex([&](int lane) { store_chroma<false>(w, pd, g, a, lane); });
+    } else {
+        for (int d = 0; d < 10; d++)
+            ex([&](int lane) {
+                phase_intra4_pair<COMPAT>(w, h, lut, d, lane);
+                if (d == 0 && !COMPAT) phase_intra_chroma<false>(w, h, lane);
+            });
+        ex([&](int lane) {
+            store_luma_tile(w, pd, g, a, lane);
+            store_chroma<COMPAT>(w, pd, g, a, lane);
+        });
+    }
+    ex([&](int lane) {
+        if (lane == 0 && w.excursions && pd.excursion_map) pd.excursion_map[a] = 1;
+    });
 }
 
 // K4: deblock one macroblock in place (its neighbours A, B, C are completely filtered)

@@ -58,6 +58,8 @@ def load_library():
     L.h264r_last_flush_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ci)]
     L.h264r_set_profiling.argtypes = [vp, ci]
     L.h264r_last_flush_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 4), ctypes.POINTER(ci * 4)]
+    L.h264r_last_flush_launch_ms.argtypes = [vp, vp, vp, ci]
+    L.h264r_last_flush_launch_ms.restype = ci
     L.h264r_mark.argtypes = [vp, ci]
     L.h264r_elapsed_ms.argtypes = [vp, ci, ci, ctypes.POINTER(ctypes.c_float)]
     if L.h264r_abi_version() != abi.ABI_VERSION:
@@ -71,7 +73,7 @@ EXPORTS = [
     "h264r_frame_begin", "h264r_submit_mbs", "h264r_frame_end", "h264r_flush", "h264r_sync", "h264r_read_planes",
     "h264r_frame_digest", "h264r_frame_digests", "h264r_range_excursions", "h264r_excursion_map",
     "h264r_residual_mbs", "h264r_release", "h264r_last_flush_stats", "h264r_set_profiling",
-    "h264r_last_flush_kernel_ms", "h264r_mark", "h264r_elapsed_ms",
+    "h264r_last_flush_kernel_ms", "h264r_last_flush_launch_ms", "h264r_mark", "h264r_elapsed_ms",
 ]
 
 
@@ -201,6 +203,14 @@ class Engine:
 
     def set_profiling(self, on):
         self._check(self.L.h264r_set_profiling(self.ctx, 1 if on else 0))
+
+    def last_flush_launch_ms(self, cap=4096):
+        """per-launch (ms, family) of the last flush, issue order"""
+        ms, fam = (ctypes.c_float * cap)(), (ctypes.c_int * cap)()
+        n = self.L.h264r_last_flush_launch_ms(self.ctx, ms, fam, cap)
+        if n < 0:
+            self._check(n)
+        return [(ms[i], fam[i]) for i in range(n)]
 
     def last_flush_kernel_ms(self):
         ms, n = (ctypes.c_float * 4)(), (ctypes.c_int * 4)()

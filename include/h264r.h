@@ -174,6 +174,17 @@ int h264r_frame_begin(h264r_ctx* ctx, int frame_id, const h264r_pic_params* pp);
 int h264r_submit_mbs(h264r_ctx* ctx, int frame_id, int first_mb, int n_mbs,
                      const h264r_mb_hdr* hdr, const int16_t* mv, const int16_t* coeff);
 
+/* The same, with the coefficients in packed form: blk_mask[i] (bits 0..23) says which of the 24 blocks of macroblock
+ * first_mb + i are present; `blocks` holds the present blocks only, 16 levels each (same order inside a block as
+ * above), macroblock after macroblock in ascending block index; n_blocks = total number of set bits.  A block that
+ * is not present is all zero -- this is what an entropy decoder has in hand after coded_block_flag
+ * (residual::residual_block_cabac, h264/residual.cpp:561-614) without first expanding into the reference's dense
+ * per-macroblock arrays, and it is what crosses PCIe.  With H264R_T8x8 the four bits of an 8x8 quadrant go together.
+ * Chunks of a picture must arrive in macroblock order; dense and packed submits cannot be mixed within a picture. */
+int h264r_submit_mbs_packed(h264r_ctx* ctx, int frame_id, int first_mb, int n_mbs,
+                            const h264r_mb_hdr* hdr, const int16_t* mv,
+                            const uint32_t* blk_mask, const int16_t* blocks, size_t n_blocks);
+
 /* Marks the picture complete and queues its reconstruction.  Asynchronous; work is issued to the
  * GPU at the next h264r_flush().  Replaces: residual::Decode + macroblock::Calc for every MB of the
  * picture (h264/residual.cpp:184-201, h264/macroblock.cpp:18-47). */
@@ -185,6 +196,10 @@ int h264r_frame_end(h264r_ctx* ctx, int frame_id);
 int h264r_flush(h264r_ctx* ctx);
 /* flush + wait for the device. */
 int h264r_sync(h264r_ctx* ctx);
+
+/* Waits until every syntax buffer submitted so far is resident in device memory (uploads run on their own
+ * stream and overlap the kernels of earlier waves and flushes). */
+int h264r_wait_uploads(h264r_ctx* ctx);
 
 /* Reads back the reconstructed planes of frame_id (flushes and waits as needed).  Strides in
  * bytes.  Replaces: picture::get_SampleXY (h264/picture.cpp:396-409), the reference's only sample

@@ -23,6 +23,7 @@ void fill_desc(PicDesc& pd, const h264r_pic_params* pp, const h264r_mb_hdr* hdr,
 {
     memset(&pd, 0, sizeof(pd));
     pd.hdr = hdr; pd.mv = mv; pd.coeff = coeff; pd.y = y; pd.u = u; pd.v = v;
+    pd.blk_mask = nullptr; pd.blk_off = nullptr;        // set by use_dense() / use_packed()
     for (int i = 0; i < H264R_MAX_REFS; i++) {
         pd.ref_y[i] = ref_y ? ref_y[i] : nullptr;
         pd.ref_u[i] = ref_u ? ref_u[i] : nullptr;
@@ -40,6 +41,33 @@ void fill_desc(PicDesc& pd, const h264r_pic_params* pp, const h264r_mb_hdr* hdr,
     pd.beta_off = pp->slice_beta_offset_div2 * 2;
     pd.excursion_map = exc_map;
 }
+// coefficient storage of a picture as the device sees it
+struct CoeffStore {
+    std::vector<uint32_t> mask, off;
+    std::vector<int16_t> blocks;
+    void use_dense(PicDesc& pd, int n_mbs)
+    {
+        mask.assign(n_mbs, 0xFFFFFFu); off.resize(n_mbs);
+        for (int a = 0; a < n_mbs; a++) off[a] = 24u * a;
+        pd.blk_mask = mask.data(); pd.blk_off = off.data();
+    }
+    // what a host parser would submit through h264r_submit_mbs_packed: only the blocks with a non-zero level
+    void use_packed(PicDesc& pd, int n_mbs, const int16_t* dense)
+    {
+        mask.assign(n_mbs, 0); off.resize(n_mbs); blocks.clear();
+        for (int a = 0; a < n_mbs; a++) {
+            off[a] = (uint32_t)(blocks.size() / 16);
+            for (int b = 0; b < 24; b++) {
+                const int16_t* p = dense + ((size_t)a * 24 + b) * 16;
+                bool nz = false;
+                for (int k = 0; k < 16; k++) nz = nz || p[k] != 0;
+                if (nz) { mask[a] |= 1u << b; blocks.insert(blocks.end(), p, p + 16); }
+            }
+        }
+        blocks.resize(blocks.size() + 16);       // keeps data() non-null for all-zero pictures
+        pd.coeff = blocks.data(); pd.blk_mask = mask.data(); pd.blk_off = off.data();
+    }
+};
 }  // namespace
 
 extern "C" {
@@ -51,6 +79,8 @@ void h264emul_residual(int w_mbs, int h_mbs, unsigned flags, const h264r_mb_hdr*
     memset(&pp, 0, sizeof(pp));
     PicDesc pd;
     fill_desc(pd, &pp, hdr, nullptr, coeff, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    CoeffStore cs;
+    if (flags & 0x40000000u) cs.use_packed(pd, w_mbs * h_mbs, coeff); else cs.use_dense(pd, w_mbs * h_mbs);
     HostExec ex;
     MbWork w;
     for (int a = 0; a < w_mbs * h_mbs; a++) {
@@ -112,6 +142,8 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
     Geometry g{w_mbs, h_mbs, cur.py, cur.pc};
     PicDesc pd;
     fill_desc(pd, pp, hdr, mv, coeff, cur.y(), cur.u(), cur.v(), ry, ru, rv, exc_map);
+    CoeffStore cs;
+    if (flags & 0x40000000u) cs.use_packed(pd, w_mbs * h_mbs, coeff); else cs.use_dense(pd, w_mbs * h_mbs);      // test switch: bit 30
     HostExec ex;
     WarpWork ww;
     MbWork& w = ww.mb;

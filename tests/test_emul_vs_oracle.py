@@ -29,6 +29,27 @@ def test_gop(built, compat, seed, w, h):
         assert oracle.digest(a["y"], a["u"], a["v"]) == emul.digest(b["y"], b["u"], b["v"])
 
 
+@pytest.mark.parametrize("compat", [True, False])
+@pytest.mark.parametrize("variant", [emul.PACKED, emul.GENERIC_INTRA])
+def test_gop_variants(built, compat, variant):
+    """packed coefficient storage (what h264r_submit_mbs_packed delivers) and the generic intra phases give the
+    same pictures as the default paths"""
+    rng = np.random.default_rng(21)
+    w, h = 7, 5
+    cfg = workload.WorkloadConfig(compat=compat, num_ref=2, p_intra_in_p=0.2, mv_range=70, p_t8x8=0.0 if compat else 0.4,
+                                  p_i8x8=0.0 if compat else 0.4, p_sub=(0.4, 0, 0.3, 0.3) if compat else (0.25, 0.25, 0.25, 0.25))
+    gop = workload.make_gop(rng, w, h, 3, cfg)
+    flags = abi.REF_COMPAT if compat else 0
+    if compat:
+        sanitize_with_oracle(w, h, gop)
+    want = run_sequence(oracle.recon_picture, w, h, flags, gop)
+    got = run_sequence(emul.recon_picture, w, h, flags | variant, gop)
+    for i, (a, b) in enumerate(zip(want, got)):
+        for k in "yuv":
+            assert np.array_equal(a[k], b[k]), "picture %d plane %s" % (i, k)
+        assert a["excursions"] == b["excursions"]
+
+
 def test_deblock_offsets_and_qp_extremes(built):
     """alpha/beta offsets and QPs at both ends of the tables"""
     for qp, offs in ((2, (0, 6, 6)), (50, (0, -6, -6)), (30, (0, 3, -3))):

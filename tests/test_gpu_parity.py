@@ -9,10 +9,14 @@ from videodecoder_b200 import engine
 pytestmark = pytest.mark.gpu
 
 
-def engine_sequence(w_mbs, h_mbs, flags, pics, batch=True):
+def engine_sequence(w_mbs, h_mbs, flags, pics, batch=True, packed=False):
     eng = engine.Engine(w_mbs, h_mbs, max_frames=len(pics), flags=flags)
     for i, p in enumerate(pics):
-        eng.submit_picture(i, p["pp"], p["hdr"], p["mv"], p["coeff"])
+        if packed:
+            mask, blocks = pack.pack_blocks(p["coeff"])
+            eng.submit_picture_packed(i, p["pp"], np.ascontiguousarray(p["hdr"]), p["mv"], mask, blocks)
+        else:
+            eng.submit_picture(i, p["pp"], p["hdr"], p["mv"], p["coeff"])
         if not batch:
             eng.sync()
     eng.sync()
@@ -24,11 +28,12 @@ def engine_sequence(w_mbs, h_mbs, flags, pics, batch=True):
 
 
 @pytest.mark.parametrize("name", ["qcif_i", "cif_ip", "qcif_wp", "hd1080_ip"])
-@pytest.mark.parametrize("batch", [True, False])
-def test_golden_reference_parity(built, name, batch):
-    """bit-exact Y/U/V against what the reference decoder reconstructed (MD5 + planes)."""
+@pytest.mark.parametrize("batch,packed", [(True, False), (False, False), (True, True), (False, True)])
+def test_golden_reference_parity(built, name, batch, packed):
+    """bit-exact Y/U/V against what the reference decoder reconstructed (MD5 + planes); dense and packed submits,
+    one flush for the whole sequence and one flush per picture."""
     g = load_golden(name)
-    outs, exc, dig = engine_sequence(g["w_mbs"], g["h_mbs"], abi.REF_COMPAT, g["pics"], batch)
+    outs, exc, dig = engine_sequence(g["w_mbs"], g["h_mbs"], abi.REF_COMPAT, g["pics"], batch, packed)
     assert exc == 0
     for i, (p, o) in enumerate(zip(g["pics"], outs)):
         if "y" in p:
@@ -38,8 +43,9 @@ def test_golden_reference_parity(built, name, batch):
         assert bytes(dig[i]) == oracle.digest(o["y"], o["u"], o["v"])
 
 
+@pytest.mark.parametrize("packed", [False, True])
 @pytest.mark.parametrize("name", ["qcif_i", "cif_ip", "qcif_wp"])
-def test_spec_mode_vs_oracle(built, name):
+def test_spec_mode_vs_oracle(built, name, packed):
     """same syntax in spec mode (Clip1, chroma prediction/MC, deblocking): engine == oracle."""
     g = load_golden(name)
     for p in g["pics"]:
@@ -47,7 +53,7 @@ def test_spec_mode_vs_oracle(built, name):
         p["hdr"]["qp_cb"] = abi.chroma_qp(p["hdr"]["qp_y"])
         p["hdr"]["qp_cr"] = abi.chroma_qp(p["hdr"]["qp_y"], 2)
     want = run_sequence(oracle.recon_picture, g["w_mbs"], g["h_mbs"], 0, g["pics"])
-    outs, _, _ = engine_sequence(g["w_mbs"], g["h_mbs"], 0, g["pics"])
+    outs, _, _ = engine_sequence(g["w_mbs"], g["h_mbs"], 0, g["pics"], packed=packed)
     for i, (w, o) in enumerate(zip(want, outs)):
         for k in "yuv":
             assert np.array_equal(w[k], o[k]), "picture %d plane %s" % (i, k)

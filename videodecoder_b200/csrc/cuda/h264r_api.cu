@@ -23,6 +23,9 @@ struct Pending {
     int n_intra;            // intra macroblocks seen by submit
     int n_submitted;
     int wave;
+    int layout;             // 0 = nothing submitted yet, 1 = dense (h264r_submit_mbs), 2 = packed (h264r_submit_mbs_packed)
+    size_t n_blocks;        // packed: coefficient blocks stored so far
+    uint64_t seq;           // order of frame_end calls (= order of the uploads on the copy stream)
 };
 
 }  // namespace
@@ -32,9 +35,15 @@ struct h264r_ctx {
     Geometry g{};
     int n_mbs = 0, max_frames = 0, max_pending = 0;
     uint32_t flags = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_ctrl = nullptr;
-    bool ctrl_in_flight = false;
+    cudaStream_t stream = nullptr;          // kernels, read-back
+    cudaStream_t copy_stream = nullptr;     // syntax uploads: overlap the kernels of earlier waves / flushes
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> ev_copied;     // per arena slot: its picture's syntax is resident
+    cudaEvent_t ev_flush[8] = {};           // ring: all kernels of flush number n are done
+    uint64_t flush_seq = 0, copy_waited_seq = 0, end_seq = 0;
+    std::vector<uint64_t> slot_flush_seq;   // flush that last read the slot
+    uint32_t* d_dense_mask = nullptr;       // blk_mask / blk_off of the dense layout (shared by all dense pictures)
+    uint32_t* d_dense_off = nullptr;
     bool profiling = false;
     std::vector<cudaEvent_t> kev;           // profiling events: pairs per launch
     std::vector<int> kev_family;
@@ -48,7 +57,7 @@ struct h264r_ctx {
     uint32_t* d_exc_counter = nullptr;
     // syntax arena: per slot hdr | mv | coeff
     uint8_t* d_syntax = nullptr;
-    size_t slot_bytes = 0, off_mv = 0, off_coeff = 0;
+    size_t slot_bytes = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_coeff = 0;
     // per-flush control block (descriptors + picture lists), pinned host mirror + device copy
     uint8_t* h_ctrl = nullptr;
     uint8_t* d_ctrl = nullptr;
@@ -60,7 +69,8 @@ struct h264r_ctx {
     std::vector<uint8_t> frame_state;
     std::vector<int> frame_wave;            // wave of a queued frame inside the current flush
     std::vector<Pending> pending;
-    std::vector<int> free_slots;
+    std::vector<int> free_slots;            // FIFO: the slot released longest ago is reused first
+    size_t free_head = 0;
     bool timing_valid = false;
     int last_launches = 0;
     std::string err;
@@ -104,6 +114,10 @@ void fill_desc(h264r_ctx* c, const Pending& p, PicDesc& pd)
     pd.hdr = reinterpret_cast<const h264r_mb_hdr*>(s);
     pd.mv = reinterpret_cast<const int16_t*>(s + c->off_mv);
     pd.coeff = reinterpret_cast<const int16_t*>(s + c->off_coeff);
+    if (p.layout == 2) {
+        pd.blk_mask = reinterpret_cast<const uint32_t*>(s + c->off_mask);
+        pd.blk_off = reinterpret_cast<const uint32_t*>(s + c->off_boff);
+    } else { pd.blk_mask = c->d_dense_mask; pd.blk_off = c->d_dense_off; }
     pd.y = c->frame_y(p.frame_id); pd.u = c->frame_u(p.frame_id); pd.v = c->frame_v(p.frame_id);
     for (int i = 0; i < H264R_MAX_REFS; i++) {
         int r = i < p.pp.num_ref_idx_l0 ? p.pp.ref_list0[i] : -1;
@@ -165,9 +179,11 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     c->c_bytes = (size_t)c->g.pitch_c * (h_mbs * 8 + 2 * PAD_YC);
     c->frame_bytes = align_up(c->y_bytes + 2 * c->c_bytes, 256);
     c->off_mv = align_up((size_t)c->n_mbs * sizeof(h264r_mb_hdr), 256);
-    c->off_coeff = c->off_mv + align_up((size_t)c->n_mbs * H264R_MV_PER_MB * 2, 256);
+    c->off_mask = c->off_mv + align_up((size_t)c->n_mbs * H264R_MV_PER_MB * 2, 256);
+    c->off_boff = c->off_mask + align_up((size_t)c->n_mbs * 4, 256);
+    c->off_coeff = c->off_boff + align_up((size_t)c->n_mbs * 4, 256);
     c->slot_bytes = c->off_coeff + align_up((size_t)c->n_mbs * H264R_COEFF_PER_MB * 2, 256);
-    c->ctrl_bytes = align_up((size_t)max_pending * sizeof(PicDesc), 256) + (size_t)max_pending * 4 * sizeof(int) + 256;
+    c->ctrl_bytes = align_up((size_t)max_pending * sizeof(PicDesc), 256);      // descriptor table, one entry per arena slot
     auto cleanup = [&](int code) { h264r_destroy(c); return code; };
 #define CUC(call)                                                                                             \
     do {                                                                                                      \
@@ -178,9 +194,21 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
         }                                                                                                     \
     } while (0)
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    c->ev_copied.assign(max_pending, nullptr);
+    for (int i = 0; i < max_pending; i++) CUC(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+    for (int i = 0; i < 8; i++) CUC(cudaEventCreateWithFlags(&c->ev_flush[i], cudaEventDisableTiming));
+    c->slot_flush_seq.assign(max_pending, 0);
+    {
+        std::vector<uint32_t> m(c->n_mbs, 0xFFFFFFu), o(c->n_mbs);
+        for (int a = 0; a < c->n_mbs; a++) o[a] = 24u * (uint32_t)a;
+        CUC(cudaMalloc(&c->d_dense_mask, (size_t)c->n_mbs * 4));
+        CUC(cudaMalloc(&c->d_dense_off, (size_t)c->n_mbs * 4));
+        CUC(cudaMemcpy(c->d_dense_mask, m.data(), (size_t)c->n_mbs * 4, cudaMemcpyHostToDevice));
+        CUC(cudaMemcpy(c->d_dense_off, o.data(), (size_t)c->n_mbs * 4, cudaMemcpyHostToDevice));
+    }
     CUC(cudaEventCreate(&c->ev0));
     CUC(cudaEventCreate(&c->ev1));
-    CUC(cudaEventCreateWithFlags(&c->ev_ctrl, cudaEventDisableTiming));
     CUC(cudaMalloc(&c->d_frames, c->frame_bytes * max_frames));
     CUC(cudaMalloc(&c->d_digests, (size_t)max_pending * 16));
     CUC(cudaMalloc(&c->d_exc_maps, (size_t)max_frames * c->n_mbs));
@@ -195,7 +223,7 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     CUC(cudaStreamSynchronize(c->stream));
     c->frame_state.assign(max_frames, FRAME_FREE);
     c->frame_wave.assign(max_frames, -1);
-    for (int s = max_pending - 1; s >= 0; s--) c->free_slots.push_back(s);
+    for (int s = 0; s < max_pending; s++) c->free_slots.push_back(s);
     *out = c;
     return H264R_OK;
 #undef CUC
@@ -205,13 +233,17 @@ void h264r_destroy(h264r_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_dense_mask); cudaFree(c->d_dense_off);
+    for (auto e : c->ev_copied) if (e) cudaEventDestroy(e);
+    for (auto e : c->ev_flush) if (e) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaFree(c->d_frames); cudaFree(c->d_digests); cudaFree(c->d_exc_maps); cudaFree(c->d_exc_counter);
     cudaFree(c->d_syntax); cudaFree(c->d_ctrl); cudaFree(c->d_sync);
     if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->ev_ctrl) cudaEventDestroy(c->ev_ctrl);
     for (auto e : c->kev) cudaEventDestroy(e);
     for (auto e : c->marks) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -245,25 +277,31 @@ int h264r_frame_begin(h264r_ctx* ctx, int frame_id, const h264r_pic_params* pp)
         uint8_t rs = ctx->frame_state[r];
         if (rs != FRAME_DONE && rs != FRAME_QUEUED) return fail(ctx, H264R_E_STATE, "frame_begin: reference frame is not reconstructed or queued");
     }
-    if (ctx->free_slots.empty()) return fail(ctx, H264R_E_CAPACITY, "frame_begin: max_pending pictures already queued; call h264r_flush");
+    if (ctx->free_head >= ctx->free_slots.size()) return fail(ctx, H264R_E_CAPACITY, "frame_begin: max_pending pictures already queued; call h264r_flush");
     Pending p{};
     p.frame_id = frame_id;
-    p.slot = ctx->free_slots.back();
-    ctx->free_slots.pop_back();
+    p.slot = ctx->free_slots[ctx->free_head++];
+    if (ctx->free_head > 4096 && ctx->free_head * 2 > ctx->free_slots.size()) {
+        ctx->free_slots.erase(ctx->free_slots.begin(), ctx->free_slots.begin() + ctx->free_head);
+        ctx->free_head = 0;
+    }
     p.pp = *pp;
     ctx->pending.push_back(p);
     ctx->frame_state[frame_id] = FRAME_OPEN;
     return H264R_OK;
 }
 
-int h264r_submit_mbs(h264r_ctx* ctx, int frame_id, int first_mb, int n_mbs, const h264r_mb_hdr* hdr, const int16_t* mv,
-                     const int16_t* coeff)
+// common part of the two submit calls: validation, header and motion-vector upload
+static int submit_common(h264r_ctx* ctx, int frame_id, int first_mb, int n_mbs, const h264r_mb_hdr* hdr, const int16_t* mv, int layout,
+                         Pending** out)
 {
-    if (!ctx || !hdr || !coeff || n_mbs <= 0 || first_mb < 0) return fail(ctx, H264R_E_INVAL, "submit_mbs: bad argument");
+    if (!ctx || !hdr || n_mbs <= 0 || first_mb < 0) return fail(ctx, H264R_E_INVAL, "submit_mbs: bad argument");
     Pending* p = find_pending(ctx, frame_id);
     if (!p || p->ended) return fail(ctx, H264R_E_STATE, "submit_mbs: no open picture with this frame id");
     if (first_mb + n_mbs > ctx->n_mbs) return fail(ctx, H264R_E_INVAL, "submit_mbs: macroblock range exceeds the picture");
     if (p->pp.slice_type == H264R_SLICE_P && !mv) return fail(ctx, H264R_E_INVAL, "submit_mbs: P picture needs motion vectors");
+    if (p->layout && p->layout != layout) return fail(ctx, H264R_E_STATE, "submit_mbs: dense and packed submits cannot be mixed within a picture");
+    if (layout == 2 && first_mb != p->n_submitted) return fail(ctx, H264R_E_STATE, "submit_mbs_packed: chunks must arrive in macroblock order");
     for (int i = 0; i < n_mbs; i++) {
         uint8_t cls = hdr[i].mb_class;
         if (cls == 3 || cls > H264R_MB_P8x8) return fail(ctx, H264R_E_INVAL, "submit_mbs: unknown mb_class");
@@ -273,13 +311,48 @@ int h264r_submit_mbs(h264r_ctx* ctx, int frame_id, int first_mb, int n_mbs, cons
             return fail(ctx, H264R_E_INVAL, "submit_mbs: 8x8 transform is not part of REF_COMPAT (the reference has none)");
     }
     CU(cudaSetDevice(ctx->device));
+    // the slot may still be read by the kernels of the flush that used it last
+    if (ctx->slot_flush_seq[p->slot] > ctx->copy_waited_seq) {
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_flush[ctx->slot_flush_seq[p->slot] & 7], 0));
+        ctx->copy_waited_seq = ctx->slot_flush_seq[p->slot];
+    }
+    p->layout = layout;
     uint8_t* s = ctx->slot_ptr(p->slot);
-    CU(cudaMemcpyAsync(s + (size_t)first_mb * sizeof(h264r_mb_hdr), hdr, (size_t)n_mbs * sizeof(h264r_mb_hdr), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(s + ctx->off_coeff + (size_t)first_mb * H264R_COEFF_PER_MB * 2, coeff, (size_t)n_mbs * H264R_COEFF_PER_MB * 2,
-                       cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(s + (size_t)first_mb * sizeof(h264r_mb_hdr), hdr, (size_t)n_mbs * sizeof(h264r_mb_hdr), cudaMemcpyHostToDevice, ctx->copy_stream));
     if (mv && p->pp.slice_type == H264R_SLICE_P)
         CU(cudaMemcpyAsync(s + ctx->off_mv + (size_t)first_mb * H264R_MV_PER_MB * 2, mv, (size_t)n_mbs * H264R_MV_PER_MB * 2,
-                           cudaMemcpyHostToDevice, ctx->stream));
+                           cudaMemcpyHostToDevice, ctx->copy_stream));
+    *out = p;
+    return H264R_OK;
+}
+
+int h264r_submit_mbs(h264r_ctx* ctx, int frame_id, int first_mb, int n_mbs, const h264r_mb_hdr* hdr, const int16_t* mv,
+                     const int16_t* coeff)
+{
+    if (!coeff) return fail(ctx, H264R_E_INVAL, "submit_mbs: bad argument");
+    Pending* p = nullptr;
+    int r = submit_common(ctx, frame_id, first_mb, n_mbs, hdr, mv, 1, &p);
+    if (r != H264R_OK) return r;
+    uint8_t* s = ctx->slot_ptr(p->slot);
+    CU(cudaMemcpyAsync(s + ctx->off_coeff + (size_t)first_mb * H264R_COEFF_PER_MB * 2, coeff, (size_t)n_mbs * H264R_COEFF_PER_MB * 2,
+                       cudaMemcpyHostToDevice, ctx->copy_stream));
+    p->n_submitted += n_mbs;
+    return H264R_OK;
+}
+
+int h264r_submit_mbs_packed(h264r_ctx* ctx, int frame_id, int first_mb, int n_mbs, const h264r_mb_hdr* hdr, const int16_t* mv,
+                            const uint32_t* blk_mask, const int16_t* blocks, size_t n_blocks)
+{
+    if (!blk_mask || (n_blocks && !blocks)) return fail(ctx, H264R_E_INVAL, "submit_mbs_packed: bad argument");
+    if (n_blocks > (size_t)24 * (n_mbs > 0 ? n_mbs : 0)) return fail(ctx, H264R_E_INVAL, "submit_mbs_packed: more blocks than 24 per macroblock");
+    Pending* p = nullptr;
+    int r = submit_common(ctx, frame_id, first_mb, n_mbs, hdr, mv, 2, &p);
+    if (r != H264R_OK) return r;
+    uint8_t* s = ctx->slot_ptr(p->slot);
+    CU(cudaMemcpyAsync(s + ctx->off_mask + (size_t)first_mb * 4, blk_mask, (size_t)n_mbs * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (n_blocks)
+        CU(cudaMemcpyAsync(s + ctx->off_coeff + p->n_blocks * 32, blocks, n_blocks * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+    p->n_blocks += n_blocks;
     p->n_submitted += n_mbs;
     return H264R_OK;
 }
@@ -290,6 +363,14 @@ int h264r_frame_end(h264r_ctx* ctx, int frame_id)
     Pending* p = find_pending(ctx, frame_id);
     if (!p || p->ended) return fail(ctx, H264R_E_STATE, "frame_end: no open picture with this frame id");
     if (p->n_submitted != ctx->n_mbs) return fail(ctx, H264R_E_STATE, "frame_end: picture is missing macroblocks");
+    CU(cudaSetDevice(ctx->device));
+    // the picture's descriptor travels with its syntax (see PicList in h264r_kernels.cuh)
+    PicDesc* h_desc = reinterpret_cast<PicDesc*>(ctx->h_ctrl);
+    PicDesc* d_desc = reinterpret_cast<PicDesc*>(ctx->d_ctrl);
+    fill_desc(ctx, *p, h_desc[p->slot]);
+    CU(cudaMemcpyAsync(&d_desc[p->slot], &h_desc[p->slot], sizeof(PicDesc), cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaEventRecord(ctx->ev_copied[p->slot], ctx->copy_stream));
+    p->seq = ++ctx->end_seq;
     p->ended = true;
     ctx->frame_state[frame_id] = FRAME_QUEUED;
     return H264R_OK;
@@ -318,40 +399,13 @@ int h264r_flush(h264r_ctx* ctx)
         ctx->frame_wave[p->frame_id] = wv;
         if (wv + 1 > n_waves) n_waves = wv + 1;
     }
-    // control block: descriptors, then per wave three lists (inter / intra / deblock)
     const int n = (int)run.size();
-    PicDesc* h_desc = reinterpret_cast<PicDesc*>(ctx->h_ctrl);
-    size_t list_off = align_up((size_t)ctx->max_pending * sizeof(PicDesc), 256);
-    int* h_lists = reinterpret_cast<int*>(ctx->h_ctrl + list_off);
     const PicDesc* d_desc = reinterpret_cast<const PicDesc*>(ctx->d_ctrl);
-    const int* d_lists = reinterpret_cast<const int*>(ctx->d_ctrl + list_off);
-    if (ctx->ctrl_in_flight) {               // the previous flush's upload of the pinned control block
-        CU(cudaEventSynchronize(ctx->ev_ctrl));
-        ctx->ctrl_in_flight = false;
-    }
-    for (int i = 0; i < n; i++) fill_desc(ctx, *run[i], h_desc[i]);
-    struct WaveLists { int inter_off, n_inter, intra_off, n_intra, deb_off, n_deb, all_off, n_all; };
-    std::vector<WaveLists> wl(n_waves);
-    int pos = 0;
-    for (int wv = 0; wv < n_waves; wv++) {
-        wl[wv].inter_off = pos;
-        for (int i = 0; i < n; i++) if (run[i]->wave == wv && run[i]->pp.slice_type == H264R_SLICE_P && run[i]->n_intra < ctx->n_mbs) h_lists[pos++] = i;
-        wl[wv].n_inter = pos - wl[wv].inter_off;
-        wl[wv].intra_off = pos;
-        for (int i = 0; i < n; i++) if (run[i]->wave == wv && run[i]->n_intra > 0) h_lists[pos++] = i;
-        wl[wv].n_intra = pos - wl[wv].intra_off;
-        wl[wv].deb_off = pos;
-        for (int i = 0; i < n; i++) if (run[i]->wave == wv && h_desc[i].deblock_on) h_lists[pos++] = i;
-        wl[wv].n_deb = pos - wl[wv].deb_off;
-        wl[wv].all_off = pos;
-        for (int i = 0; i < n; i++) if (run[i]->wave == wv) h_lists[pos++] = i;
-        wl[wv].n_all = pos - wl[wv].all_off;
-    }
-    CU(cudaMemcpyAsync(ctx->d_ctrl, ctx->h_ctrl, list_off + (size_t)pos * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaEventRecord(ctx->ev_ctrl, ctx->stream));
-    ctx->ctrl_in_flight = true;
+    const PicDesc* h_desc = reinterpret_cast<const PicDesc*>(ctx->h_ctrl);
     CU(cudaMemsetAsync(ctx->d_sync, 0, ctx->sync_ints * sizeof(int), ctx->stream));
-    int* tickets = ctx->d_sync + (size_t)4 * ctx->max_pending * ctx->g.h_mbs;
+    int* const progress0 = ctx->d_sync;
+    int* const tickets0 = ctx->d_sync + (size_t)4 * ctx->max_pending * ctx->g.h_mbs;
+    int prog_pos = 0, ticket_pos = 0;            // next free picture-sized progress region / ticket word
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -372,56 +426,83 @@ int h264r_flush(h264r_ctx* ctx)
         cudaEventRecord(ctx->kev[ctx->kev_used + 1], ctx->stream);
         ctx->kev_used += 2;
     };
+    // runs f(list) over the pictures of wave wv selected by pred, in chunks that fit the kernel parameters
+    PicList list;
+    auto for_chunks = [&](int wv, auto pred, auto f) {
+        list.n = 0;
+        for (int i = 0; i < n; i++) {
+            if (run[i]->wave != wv || !pred(*run[i])) continue;
+            list.slot[list.n++] = run[i]->slot;
+            if (list.n == PIC_LIST_MAX) { f(list); list.n = 0; }
+        }
+        if (list.n) f(list);
+    };
+    // uploads run on the copy stream in frame_end order: a wave may start when its last-ended picture is resident,
+    // so the upload of later waves overlaps the kernels of earlier ones
+    std::vector<Pending*> wave_last(n_waves, nullptr);
+    for (Pending* p : run) if (!wave_last[p->wave] || p->seq > wave_last[p->wave]->seq) wave_last[p->wave] = p;
     for (int wv = 0; wv < n_waves; wv++) {
-        const WaveLists& L = wl[wv];
-        if (L.n_inter) {
-            long total = (long)L.n_inter * ctx->n_mbs;
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[wave_last[wv]->slot], 0));
+        // block offsets of the pictures that arrived packed
+        for_chunks(wv, [&](const Pending& p) { return p.layout == 2; }, [&](const PicList& L) {
+            k_blk_scan<<<L.n, 1024, 0, ctx->stream>>>(d_desc, L, ctx->n_mbs);
+            ctx->last_launches++;
+        });
+        for_chunks(wv, [&](const Pending& p) { return p.pp.slice_type == H264R_SLICE_P && p.n_intra < ctx->n_mbs; }, [&](const PicList& L) {
+            long total = (long)L.n * ctx->n_mbs;
             long want = (total + INTER_WARPS - 1) / INTER_WARPS;
             long cap = (long)sm_count * 16 * 4;                   // 16 resident CTAs per SM, four passes
             int blocks = (int)(want < cap ? want : cap);
             prof_begin(0);
-            if (compat) k_inter<true><<<blocks, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, d_lists + L.inter_off, L.n_inter, ctx->g, ctx->d_exc_counter);
-            else k_inter<false><<<blocks, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, d_lists + L.inter_off, L.n_inter, ctx->g, ctx->d_exc_counter);
+            if (compat) k_inter<true><<<blocks, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g, ctx->d_exc_counter);
+            else k_inter<false><<<blocks, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g, ctx->d_exc_counter);
             prof_end();
             ctx->last_launches++;
-        }
-        if (L.n_intra) {
-            int rows = L.n_intra * ctx->g.h_mbs, blocks = (rows + ROW_WARPS - 1) / ROW_WARPS;
-            int* prog = ctx->d_sync + (size_t)L.intra_off * ctx->g.h_mbs;
+        });
+        for_chunks(wv, [&](const Pending& p) { return p.n_intra > 0; }, [&](const PicList& L) {
+            int rows = L.n * ctx->g.h_mbs, blocks = (rows + ROW_WARPS - 1) / ROW_WARPS;
+            int* prog = progress0 + (size_t)prog_pos * ctx->g.h_mbs;
+            prog_pos += L.n;
             prof_begin(1);
-            if (compat) k_intra_rows<true><<<blocks, ROW_WARPS * 32, 0, ctx->stream>>>(d_desc, d_lists + L.intra_off, L.n_intra, ctx->g, prog, tickets + 2 * wv, ctx->d_exc_counter);
-            else k_intra_rows<false><<<blocks, ROW_WARPS * 32, 0, ctx->stream>>>(d_desc, d_lists + L.intra_off, L.n_intra, ctx->g, prog, tickets + 2 * wv, ctx->d_exc_counter);
+            if (compat) k_intra_rows<true><<<blocks, ROW_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g, prog, tickets0 + ticket_pos, ctx->d_exc_counter);
+            else k_intra_rows<false><<<blocks, ROW_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g, prog, tickets0 + ticket_pos, ctx->d_exc_counter);
             prof_end();
+            ticket_pos++;
             ctx->last_launches++;
-        }
-        if (L.n_deb) {
-            int rows = L.n_deb * ctx->g.h_mbs, blocks = (rows + ROW_WARPS - 1) / ROW_WARPS;
-            int* prog = ctx->d_sync + (size_t)L.deb_off * ctx->g.h_mbs;
+        });
+        for_chunks(wv, [&](const Pending& p) { return h_desc[p.slot].deblock_on != 0; }, [&](const PicList& L) {
+            int rows = L.n * ctx->g.h_mbs, blocks = (rows + ROW_WARPS - 1) / ROW_WARPS;
+            int* prog = progress0 + (size_t)prog_pos * ctx->g.h_mbs;
+            prog_pos += L.n;
             prof_begin(2);
-            k_deblock_rows<<<blocks, ROW_WARPS * 32, 0, ctx->stream>>>(d_desc, d_lists + L.deb_off, L.n_deb, ctx->g, prog, tickets + 2 * wv + 1);
+            k_deblock_rows<<<blocks, ROW_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g, prog, tickets0 + ticket_pos);
             prof_end();
+            ticket_pos++;
             ctx->last_launches++;
-        }
-        {
-            // border replication of the finished pictures of this wave
+        });
+        // border replication of the finished pictures of this wave
+        for_chunks(wv, [&](const Pending&) { return true; }, [&](const PicList& L) {
             int rows = ctx->g.h_mbs * 16 + 2 * PAD_Y + (compat ? 0 : 2 * (ctx->g.h_mbs * 8 + 2 * PAD_YC));
-            long warps = (long)L.n_all * rows;
+            long warps = (long)L.n * rows;
             long cap = (long)sm_count * 16;
             int blocks = (int)((warps + 3) / 4 < cap ? (warps + 3) / 4 : cap);
             prof_begin(3);
-            k_pad<<<blocks, 128, 0, ctx->stream>>>(d_desc, d_lists + L.all_off, L.n_all, ctx->g, compat ? 0 : 1);
+            k_pad<<<blocks, 128, 0, ctx->stream>>>(d_desc, L, ctx->g, compat ? 0 : 1);
             prof_end();
             ctx->last_launches++;
-        }
+        });
     }
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaGetLastError());
     ctx->timing_valid = true;
+    ctx->flush_seq++;
+    CU(cudaEventRecord(ctx->ev_flush[ctx->flush_seq & 7], ctx->stream));
     std::vector<Pending> keep;
     for (auto& p : ctx->pending) {
         if (p.ended) {
             ctx->frame_state[p.frame_id] = FRAME_DONE;
             ctx->frame_wave[p.frame_id] = -1;
+            ctx->slot_flush_seq[p.slot] = ctx->flush_seq;
             ctx->free_slots.push_back(p.slot);
         } else keep.push_back(p);
     }
@@ -434,7 +515,16 @@ int h264r_sync(h264r_ctx* ctx)
     if (!ctx) return H264R_E_INVAL;
     int r = h264r_flush(ctx);
     if (r != H264R_OK) return r;
+    CU(cudaStreamSynchronize(ctx->copy_stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return H264R_OK;
+}
+
+int h264r_wait_uploads(h264r_ctx* ctx)
+{
+    if (!ctx) return H264R_E_INVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->copy_stream));
     return H264R_OK;
 }
 
@@ -470,26 +560,19 @@ int h264r_frame_digests(h264r_ctx* ctx, const int* frame_ids, int n, uint8_t* ou
         if (r != H264R_OK) return r;
     }
     CU(cudaSetDevice(ctx->device));
-    // K5 runs on demand: minimal descriptors (planes + digest slot) in chunks of max_pending
-    PicDesc* h_desc = reinterpret_cast<PicDesc*>(ctx->h_ctrl);
-    size_t list_off = align_up((size_t)ctx->max_pending * sizeof(PicDesc), 256);
-    int* h_lists = reinterpret_cast<int*>(ctx->h_ctrl + list_off);
-    for (int base = 0; base < n; base += ctx->max_pending) {
-        int m = n - base < ctx->max_pending ? n - base : ctx->max_pending;
-        CU(cudaStreamSynchronize(ctx->stream));      // the pinned control block may still be in flight
-        ctx->ctrl_in_flight = false;
-        for (int i = 0; i < m; i++) {
-            int f = frame_ids[base + i];
-            memset(&h_desc[i], 0, sizeof(PicDesc));
-            h_desc[i].y = ctx->frame_y(f); h_desc[i].u = ctx->frame_u(f); h_desc[i].v = ctx->frame_v(f);
-            h_desc[i].digest = ctx->d_digests + (size_t)i * 4;
-            h_lists[i] = i;
-        }
-        CU(cudaMemcpyAsync(ctx->d_ctrl, ctx->h_ctrl, list_off + (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        k_digest<<<m, 1024, 0, ctx->stream>>>(reinterpret_cast<const PicDesc*>(ctx->d_ctrl),
-                                              reinterpret_cast<const int*>(ctx->d_ctrl + list_off), ctx->g);
+    // K5 runs on demand, in chunks bounded by the parameter list and by the staging buffer (max_pending digests)
+    FramePool pool{ctx->d_frames, ctx->frame_bytes, (size_t)PAD_Y * ctx->g.pitch_y + PAD_X,
+                   ctx->y_bytes + (size_t)PAD_YC * ctx->g.pitch_c + PAD_XC, ctx->y_bytes + ctx->c_bytes + (size_t)PAD_YC * ctx->g.pitch_c + PAD_XC};
+    const int chunk = ctx->max_pending < PIC_LIST_MAX ? ctx->max_pending : PIC_LIST_MAX;
+    PicList list;
+    for (int base = 0; base < n; base += chunk) {
+        int m = n - base < chunk ? n - base : chunk;
+        list.n = m;
+        for (int i = 0; i < m; i++) list.slot[i] = frame_ids[base + i];
+        k_digest<<<m, 1024, 0, ctx->stream>>>(pool, list, ctx->g, ctx->d_digests);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(out + (size_t)base * 16, ctx->d_digests, (size_t)m * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        if (base + chunk < n) CU(cudaStreamSynchronize(ctx->stream));      // d_digests is reused by the next chunk
     }
     CU(cudaStreamSynchronize(ctx->stream));
     return H264R_OK;
@@ -534,6 +617,17 @@ int h264r_residual_mbs(h264r_ctx* ctx, int n_mbs, const h264r_mb_hdr* hdr, const
     memset(&pd, 0, sizeof(pd));
     pd.hdr = reinterpret_cast<const h264r_mb_hdr*>(d);
     pd.coeff = reinterpret_cast<const int16_t*>(d + hb);
+    // dense layout; the context's table covers n_mbs of a picture, larger calls get their own
+    uint32_t* d_ref = nullptr;
+    if (n_mbs <= ctx->n_mbs) { pd.blk_mask = ctx->d_dense_mask; pd.blk_off = ctx->d_dense_off; }
+    else {
+        std::vector<uint32_t> mo((size_t)2 * n_mbs);
+        for (int a = 0; a < n_mbs; a++) { mo[a] = 0xFFFFFFu; mo[(size_t)n_mbs + a] = 24u * (uint32_t)a; }
+        if (cudaMalloc(&d_ref, mo.size() * 4) != cudaSuccess) { cudaFree(d); return fail(ctx, H264R_E_NOMEM, "residual_mbs: out of device memory"); }
+        cudaMemcpyAsync(d_ref, mo.data(), mo.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        pd.blk_mask = d_ref; pd.blk_off = d_ref + n_mbs;
+    }
     int16_t* d_out = reinterpret_cast<int16_t*>(d + hb + cb);
     cudaError_t e = cudaMemcpyAsync(d, hdr, (size_t)n_mbs * sizeof(h264r_mb_hdr), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d + hb, coeff, (size_t)n_mbs * 768, cudaMemcpyHostToDevice, ctx->stream);
@@ -547,6 +641,7 @@ int h264r_residual_mbs(h264r_ctx* ctx, int n_mbs, const h264r_mb_hdr* hdr, const
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n_mbs * 768, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d);
+    cudaFree(d_ref);
     if (e != cudaSuccess) return fail(ctx, H264R_E_CUDA, std::string("residual_mbs: ") + cudaGetErrorString(e));
     return H264R_OK;
 }

@@ -43,7 +43,9 @@ struct Geometry {
 struct PicDesc {
     const h264r_mb_hdr* hdr;
     const int16_t* mv;
-    const int16_t* coeff;
+    const int16_t* coeff;      // coefficient blocks of the picture, 16 levels each, packed (see BlkRef)
+    const uint32_t* blk_mask;  // per macroblock: bit b set = block b is stored
+    const uint32_t* blk_off;   // per macroblock: index of its first stored block
     uint8_t* y; uint8_t* u; uint8_t* v;
     const uint8_t* ref_y[H264R_MAX_REFS];
     const uint8_t* ref_u[H264R_MAX_REFS];
@@ -77,6 +79,25 @@ struct alignas(16) MbWork {
     uint8_t bs[32];                       // boundary strengths [dir][edge][k]
     uint32_t excursions;
 };
+
+// Coefficient storage.  Macroblock a owns the blocks whose bit is set in blk_mask[a] (bit b = block b of the 24
+// of include/h264r.h), stored back to back from block index blk_off[a]; a block that is not stored is all zero.
+// The dense layout of h264r_submit_mbs is the special case mask = 0xFFFFFF, off = 24 a.
+struct BlkRef { uint32_t mask, off; };
+HD int popc32(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+HD BlkRef load_blkref(const PicDesc& pd, int a) { return BlkRef{H264R_LDG(pd.blk_mask + a), H264R_LDG(pd.blk_off + a)}; }
+HD const int16_t* blk_ptr(const PicDesc& pd, const BlkRef& r, int b)       // nullptr: block b is zero
+{
+    if (!((r.mask >> b) & 1u)) return nullptr;
+    return pd.coeff + ((size_t)r.off + popc32(r.mask & ((1u << b) - 1u))) * 16;
+}
 
 HD int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 HD int clip1(int v) { return clip3(0, 255, v); }
@@ -156,8 +177,10 @@ HD void phase_load_coeff(MbWork& w, const PicDesc& pd, int a, int lane)
 {
     if (lane == 0) w.excursions = 0;
     if (lane < 24) {
-        const int4* src = reinterpret_cast<const int4*>(pd.coeff + (size_t)a * H264R_COEFF_PER_MB) + lane * 2;
-        int4 v0 = H264R_LDG(src), v1 = H264R_LDG(src + 1);
+        const BlkRef br = load_blkref(pd, a);
+        const int4* src = reinterpret_cast<const int4*>(blk_ptr(pd, br, lane));
+        int4 v0 = int4{0, 0, 0, 0}, v1 = int4{0, 0, 0, 0};
+        if (src) { v0 = H264R_LDG(src); v1 = H264R_LDG(src + 1); }
         int4* dst = reinterpret_cast<int4*>(&w.coef[lane][0]);
         dst[0] = v0; dst[1] = v1;
     }
@@ -795,12 +818,16 @@ HD bool blk_coded(const MbWork& w, const h264r_mb_hdr& h, int ras)
 }
 HD bool blk_coded_global(const PicDesc& pd, const h264r_mb_hdr& h, int a, int ras)
 {
-    const int16_t* c = pd.coeff + (size_t)a * H264R_COEFF_PER_MB;
+    const BlkRef br = load_blkref(pd, a);
     int first, n;
-    if (h.flags & H264R_T8x8) { first = ((ras >> 3) * 2 + ((ras & 3) >> 1)) * 64; n = 64; }
-    else { first = blk_raster(ras) * 16; n = 16; }
-    const int4* p = reinterpret_cast<const int4*>(c + first);
-    for (int k = 0; k < n / 8; k++) { int4 v = H264R_LDG(p + k); if (v.x | v.y | v.z | v.w) return true; }
+    if (h.flags & H264R_T8x8) { first = ((ras >> 3) * 2 + ((ras & 3) >> 1)) * 4; n = 4; }
+    else { first = blk_raster(ras); n = 1; }
+    for (int k = 0; k < n; k++) {
+        const int4* p = reinterpret_cast<const int4*>(blk_ptr(pd, br, first + k));
+        if (!p) continue;
+        int4 v0 = H264R_LDG(p), v1 = H264R_LDG(p + 1);
+        if (v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) return true;
+    }
     return false;
 }
 

@@ -28,15 +28,16 @@ template <bool COMPAT>
 HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane)
 {
     if (lane >= 24) return;
-    const int16_t* cbase = pd.coeff + (size_t)a * H264R_COEFF_PER_MB;
+    const BlkRef br = load_blkref(pd, a);
     const int cbp_l = h.cbp & 15, cbp_c = (h.cbp >> 4) & 3;
     const bool luma = lane < 16, i16 = h.mb_class == H264R_MB_I16x16;
     bool active = luma ? (i16 || ((cbp_l >> (lane >> 2)) & 1) != 0) : cbp_c != 0;
     int r[16];
     bool zero = true;
     if (active) {
-        const int4* src = reinterpret_cast<const int4*>(cbase) + lane * 2;
-        int4 v0 = H264R_LDG(src), v1 = (luma || cbp_c == 2) ? H264R_LDG(src + 1) : int4{0, 0, 0, 0};
+        const int4* src = reinterpret_cast<const int4*>(blk_ptr(pd, br, lane));
+        int4 v0 = int4{0, 0, 0, 0}, v1 = int4{0, 0, 0, 0};
+        if (src) { v0 = H264R_LDG(src); if (luma || cbp_c == 2) v1 = H264R_LDG(src + 1); }
         if (!luma && cbp_c != 2) { v0.x &= 0xffff; v0.y = v0.z = v0.w = 0; }        // DC only: AC levels are not coded
         int c[16];
         const int w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -53,7 +54,8 @@ HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr&
                 int t = 0;
 #pragma unroll
                 for (int l = 0; l < 4; l++) {
-                    int dc = H264R_LDG(cbase + blk_raster(k * 4 + l) * 16);
+                    const int16_t* dp = blk_ptr(pd, br, blk_raster(k * 4 + l));
+                    int dc = dp ? H264R_LDG(dp) : 0;
                     t += ((0xA6C0 >> (l * 4 + j)) & 1) ? -dc : dc;       // T rows {++++},{++--},{+--+},{+-+-}: bit = minus
                 }
                 f += ((0xA6C0 >> (i * 4 + k)) & 1) ? -t : t;
@@ -66,8 +68,9 @@ HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr&
         if (!luma) {
             int plane = (lane - 16) >> 2, b = (lane - 16) & 3;
             qp = plane ? h.qp_cr : h.qp_cb;
-            const int16_t* dcp = cbase + (16 + plane * 4) * 16;
-            int c0 = H264R_LDG(dcp), c1 = H264R_LDG(dcp + 16), c2 = H264R_LDG(dcp + 32), c3 = H264R_LDG(dcp + 48);
+            const int16_t* d0 = blk_ptr(pd, br, 16 + plane * 4), * d1 = blk_ptr(pd, br, 17 + plane * 4);
+            const int16_t* d2 = blk_ptr(pd, br, 18 + plane * 4), * d3 = blk_ptr(pd, br, 19 + plane * 4);
+            int c0 = d0 ? H264R_LDG(d0) : 0, c1 = d1 ? H264R_LDG(d1) : 0, c2 = d2 ? H264R_LDG(d2) : 0, c3 = d3 ? H264R_LDG(d3) : 0;
             int f;
             if (COMPAT) f = (b == 0 || b == 3) ? c3 : -c3;      // reference's chroma DC product (h264/matrix.cpp:150-171)
             else f = c0 + ((b & 1) ? -c1 : c1) + ((b & 2) ? -c2 : c2) + ((b == 1 || b == 2) ? -c3 : c3);

@@ -14,6 +14,13 @@ struct WarpExec {
     }
 };
 
+// The pictures a launch works on: indices into the device descriptor table (one descriptor per syntax-arena slot),
+// passed BY VALUE in the kernel parameters.  Descriptors are uploaded with their picture's syntax (copy stream), so
+// a flush itself copies nothing: a host-to-device copy issued at flush time would queue behind every syntax upload
+// still in flight and serialise the kernels after them.
+constexpr int PIC_LIST_MAX = 944;
+struct PicList { int n; int slot[PIC_LIST_MAX]; };
+
 constexpr int INTER_WARPS = 4;       // warps per CTA of the inter / residual kernels
 
 // ------------------------------------------------------------------------------------------------
@@ -36,18 +43,18 @@ __global__ void __launch_bounds__(INTER_WARPS * 32) k_residual(PicDesc pd, int n
 // (picture, MB) pairs.
 // ------------------------------------------------------------------------------------------------
 template <bool COMPAT>
-__global__ void __launch_bounds__(INTER_WARPS * 32) k_inter(const PicDesc* __restrict__ descs, const int* __restrict__ list,
-                                                            int n_pics, Geometry g, uint32_t* excursions)
+__global__ void __launch_bounds__(INTER_WARPS * 32) k_inter(const PicDesc* __restrict__ descs, const __grid_constant__ PicList list,
+                                                            Geometry g, uint32_t* excursions)
 {
     __shared__ WarpWork work[INTER_WARPS];
     int warp = threadIdx.x >> 5;
     WarpExec ex{(int)(threadIdx.x & 31)};
     WarpWork& w = work[warp];
     const int n_mbs = g.w_mbs * g.h_mbs;
-    const long total = (long)n_pics * n_mbs;
+    const long total = (long)list.n * n_mbs;
     for (long i = (long)blockIdx.x * INTER_WARPS + warp; i < total; i += (long)gridDim.x * INTER_WARPS) {
         int p = (int)(i / n_mbs), a = (int)(i - (long)p * n_mbs);
-        const PicDesc& pd = descs[list[p]];
+        const PicDesc& pd = descs[list.slot[p]];
         h264r_mb_hdr h = load_hdr(pd, a);
         if (is_intra(h.mb_class)) continue;       // warp-uniform
         uint32_t exc = seq_inter_any<COMPAT>(ex, w, pd, g, h, a);
@@ -104,9 +111,8 @@ __device__ __forceinline__ int row_ticket(int* ticket)
 }
 
 template <bool COMPAT>
-__global__ void __launch_bounds__(ROW_WARPS * 32) k_intra_rows(const PicDesc* __restrict__ descs, const int* __restrict__ list,
-                                                              int n_pics, Geometry g, int* progress, int* ticket,
-                                                              uint32_t* excursions)
+__global__ void __launch_bounds__(ROW_WARPS * 32) k_intra_rows(const PicDesc* __restrict__ descs, const __grid_constant__ PicList list,
+                                                              Geometry g, int* progress, int* ticket, uint32_t* excursions)
 {
     __shared__ MbWork work[ROW_WARPS];
     __shared__ uint32_t s_mask[ROW_WARPS][2][ROW_MASK_WORDS + 1];     // intra bitmaps of this row and of the row above
@@ -114,11 +120,11 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_intra_rows(const PicDesc* __
     intra4_lut_fill(s_lut, threadIdx.x, blockDim.x);
     const int W = g.w_mbs, H = g.h_mbs;
     const int flat = row_ticket(ticket);          // __syncthreads() inside: the table is complete
-    if (flat >= n_pics * H) return;
+    if (flat >= list.n * H) return;
     const int warp = threadIdx.x >> 5;
     WarpExec ex{(int)(threadIdx.x & 31)};
     const int p = flat / H, row = flat - p * H;
-    const PicDesc& pd = descs[list[p]];
+    const PicDesc& pd = descs[list.slot[p]];
     int* prog = progress + (size_t)p * H;
     MbWork& w = work[warp];
     uint32_t* mask = s_mask[warp][0];
@@ -165,17 +171,17 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_intra_rows(const PicDesc* __
     if (ex.lane == 0 && exc) atomicAdd(excursions, exc);
 }
 
-__global__ void __launch_bounds__(ROW_WARPS * 32) k_deblock_rows(const PicDesc* __restrict__ descs, const int* __restrict__ list,
-                                                                int n_pics, Geometry g, int* progress, int* ticket)
+__global__ void __launch_bounds__(ROW_WARPS * 32) k_deblock_rows(const PicDesc* __restrict__ descs, const __grid_constant__ PicList list,
+                                                                Geometry g, int* progress, int* ticket)
 {
     __shared__ MbWork work[ROW_WARPS];
     const int W = g.w_mbs, H = g.h_mbs;
     const int flat = row_ticket(ticket);
-    if (flat >= n_pics * H) return;
+    if (flat >= list.n * H) return;
     const int warp = threadIdx.x >> 5;
     WarpExec ex{(int)(threadIdx.x & 31)};
     const int p = flat / H, row = flat - p * H;
-    const PicDesc& pd = descs[list[p]];
+    const PicDesc& pd = descs[list.slot[p]];
     int* prog = progress + (size_t)p * H;
     MbWork& w = work[warp];
     for (int x = 0; x < W; x++) {
@@ -189,19 +195,46 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_deblock_rows(const PicDesc* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Packed coefficient storage: blk_off[a] = number of stored blocks before macroblock a = exclusive scan of
+// popcount(blk_mask).  One CTA per picture submitted through h264r_submit_mbs_packed.
+// ------------------------------------------------------------------------------------------------
+struct ScanJob { const uint32_t* mask; uint32_t* off; };
+__global__ void __launch_bounds__(1024) k_blk_scan(const PicDesc* __restrict__ descs, const __grid_constant__ PicList list, int n_mbs)
+{
+    const PicDesc& pdj = descs[list.slot[blockIdx.x]];
+    const ScanJob job{pdj.blk_mask, const_cast<uint32_t*>(pdj.blk_off)};
+    const int per = (n_mbs + 1023) >> 10, first = threadIdx.x * per, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t sum = 0;
+    for (int k = 0; k < per; k++) if (first + k < n_mbs) sum += __popc(__ldg(job.mask + first + k) & 0xFFFFFFu);
+    uint32_t incl = sum;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    __shared__ uint32_t wsum[32];
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = wsum[lane], iv = v;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
+        wsum[lane] = iv - v;
+    }
+    __syncthreads();
+    uint32_t run = wsum[warp] + incl - sum;
+    for (int k = 0; k < per; k++) if (first + k < n_mbs) { job.off[first + k] = run; run += __popc(__ldg(job.mask + first + k) & 0xFFFFFFu); }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Border replication of finished pictures (so that later P pictures can stage reference windows without
 // coordinate clamps).  One warp per padded row; luma always, chroma when `chroma` (spec mode: the
 // reference has no chroma motion compensation, D4).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_pad(const PicDesc* __restrict__ descs, const int* __restrict__ list, int n_pics, Geometry g, int chroma)
+__global__ void __launch_bounds__(128) k_pad(const PicDesc* __restrict__ descs, const __grid_constant__ PicList list, Geometry g, int chroma)
 {
     const int Wl = g.w_mbs * 16, Hl = g.h_mbs * 16, Wc = Wl >> 1, Hc = Hl >> 1;
     const int rows_l = Hl + 2 * PAD_Y, rows_c = chroma ? Hc + 2 * PAD_YC : 0, rows = rows_l + 2 * rows_c;
     const int lane = threadIdx.x & 31;
-    const long total = (long)n_pics * rows;
+    const long total = (long)list.n * rows;
     for (long i = (long)blockIdx.x * 4 + (threadIdx.x >> 5); i < total; i += (long)gridDim.x * 4) {
         int p = (int)(i / rows), r = (int)(i - (long)p * rows);
-        const PicDesc& pd = descs[list[p]];
+        const PicDesc& pd = descs[list.slot[p]];
         if (r < rows_l) pad_row_phase(pd.y, g.pitch_y, Wl, Hl, PAD_X, PAD_Y, r - PAD_Y, lane);
         else if (r < rows_l + rows_c) pad_row_phase(pd.u, g.pitch_c, Wc, Hc, PAD_XC, PAD_YC, r - rows_l - PAD_YC, lane);
         else pad_row_phase(pd.v, g.pitch_c, Wc, Hc, PAD_XC, PAD_YC, r - rows_l - rows_c - PAD_YC, lane);
@@ -212,9 +245,14 @@ __global__ void __launch_bounds__(128) k_pad(const PicDesc* __restrict__ descs, 
 // K5: frame digest.  One CTA per picture; every thread folds 4-sample words, block reduction, the
 // CTA writes the four sums (no zeroing pass, no atomics on global memory).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_digest(const PicDesc* __restrict__ descs, const int* __restrict__ list, Geometry g)
+struct FramePool { uint8_t* base; size_t frame_bytes, off_y, off_u, off_v; };
+__global__ void __launch_bounds__(1024) k_digest(FramePool pool, const __grid_constant__ PicList frames, Geometry g, uint32_t* out)
 {
-    const PicDesc& pd = descs[list[blockIdx.x]];
+    struct { const uint8_t* y; const uint8_t* u; const uint8_t* v; uint32_t* digest; } pd;
+    {
+        const uint8_t* f = pool.base + (size_t)frames.slot[blockIdx.x] * pool.frame_bytes;
+        pd.y = f + pool.off_y; pd.u = f + pool.off_u; pd.v = f + pool.off_v; pd.digest = out + 4 * blockIdx.x;
+    }
     const int Wl = g.w_mbs * 16, Hl = g.h_mbs * 16, Wc = Wl / 2, Hc = Hl / 2;
     uint32_t d[4] = {0, 0, 0, 0};
     const int lw = Wl / 4, cw = Wc / 4;

@@ -45,6 +45,8 @@ def load_library():
     L.h264r_host_free.restype = None
     L.h264r_frame_begin.argtypes = [vp, ci, ctypes.POINTER(abi.PicParams)]
     L.h264r_submit_mbs.argtypes = [vp, ci, ci, ci, vp, vp, vp]
+    L.h264r_submit_mbs_packed.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, ctypes.c_size_t]
+    L.h264r_wait_uploads.argtypes = [vp]
     L.h264r_frame_end.argtypes = [vp, ci]
     L.h264r_flush.argtypes = [vp]
     L.h264r_sync.argtypes = [vp]
@@ -70,7 +72,7 @@ def load_library():
 
 EXPORTS = [
     "h264r_abi_version", "h264r_last_error", "h264r_create", "h264r_destroy", "h264r_host_alloc", "h264r_host_free",
-    "h264r_frame_begin", "h264r_submit_mbs", "h264r_frame_end", "h264r_flush", "h264r_sync", "h264r_read_planes",
+    "h264r_frame_begin", "h264r_submit_mbs", "h264r_submit_mbs_packed", "h264r_wait_uploads", "h264r_frame_end", "h264r_flush", "h264r_sync", "h264r_read_planes",
     "h264r_frame_digest", "h264r_frame_digests", "h264r_range_excursions", "h264r_excursion_map",
     "h264r_residual_mbs", "h264r_release", "h264r_last_flush_stats", "h264r_set_profiling",
     "h264r_last_flush_kernel_ms", "h264r_last_flush_launch_ms", "h264r_mark", "h264r_elapsed_ms",
@@ -144,6 +146,15 @@ class Engine:
         n = n_mbs if n_mbs is not None else (hdr.shape[0] if hasattr(hdr, "shape") else self.n_mbs)
         self._check(self.L.h264r_submit_mbs(self.ctx, frame_id, first_mb, n, _ptr(hdr), _ptr(mv), _ptr(coeff)))
 
+    def submit_mbs_packed(self, frame_id, hdr, mv, blk_mask, blocks, first_mb=0, n_mbs=None):
+        n = n_mbs if n_mbs is not None else hdr.shape[0]
+        n_blocks = 0 if blocks is None else int(blocks.size // 16)
+        self._check(self.L.h264r_submit_mbs_packed(self.ctx, frame_id, first_mb, n, _ptr(hdr), _ptr(mv), _ptr(blk_mask), _ptr(blocks),
+                                                   n_blocks))
+
+    def wait_uploads(self):
+        self._check(self.L.h264r_wait_uploads(self.ctx))
+
     def frame_end(self, frame_id):
         self._check(self.L.h264r_frame_end(self.ctx, frame_id))
 
@@ -153,6 +164,12 @@ class Engine:
         mv = np.ascontiguousarray(mv, dtype=np.int16) if mv is not None else None
         self.frame_begin(frame_id, pp)
         self.submit_mbs(frame_id, hdr, mv, coeff)
+        self.frame_end(frame_id)
+
+    def submit_picture_packed(self, frame_id, pp, hdr, mv, blk_mask, blocks):
+        """blk_mask, blocks as produced by pack.pack_blocks()"""
+        self.frame_begin(frame_id, pp)
+        self.submit_mbs_packed(frame_id, hdr, mv, blk_mask, blocks)
         self.frame_end(frame_id)
 
     def flush(self):

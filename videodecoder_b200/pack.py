@@ -110,3 +110,22 @@ def pack_mvs(mbs, part_mv):
         if k >= synth.P16x16:
             mv[a] = expand_mv(k, mbs["sub_type"][a], part_mv[a])
     return mv.reshape(n, 32)
+
+
+def pack_blocks(coeff):
+    """Dense coefficient buffer (n, 384) int16 -> what h264r_submit_mbs_packed takes:
+    (blk_mask uint32 (n,), blocks int16 (n_blocks, 16)); a block is kept iff it holds a non-zero level."""
+    c = np.ascontiguousarray(coeff, dtype=np.int16).reshape(-1, 24, 16)
+    present = (c != 0).any(axis=2)
+    mask = (present.astype(np.uint32) << np.arange(24, dtype=np.uint32)).sum(axis=1, dtype=np.uint32)
+    blocks = np.ascontiguousarray(c[present])
+    return mask, blocks
+
+
+def unpack_blocks(mask, blocks):
+    """inverse of pack_blocks (tests)"""
+    n = mask.shape[0]
+    present = ((mask[:, None] >> np.arange(24, dtype=np.uint32)) & 1).astype(bool)
+    c = np.zeros((n, 24, 16), dtype=np.int16)
+    c[present] = blocks.reshape(-1, 16)
+    return c.reshape(n, 384)

@@ -185,6 +185,25 @@ int h264r_submit_mbs_packed(h264r_ctx* ctx, int frame_id, int first_mb, int n_mb
                             const h264r_mb_hdr* hdr, const int16_t* mv,
                             const uint32_t* blk_mask, const int16_t* blocks, size_t n_blocks);
 
+/* Whole pictures with ONE transfer.  A picture buffer is pinned host memory laid out like the engine's device-side
+ * syntax slot; the host parser writes headers, vectors, block masks and the present blocks straight into it (same
+ * formats as h264r_submit_mbs_packed, whole picture, macroblock order) and h264r_submit_picture() ships it with a
+ * single DMA and queues the picture (no h264r_frame_end).  The buffer must stay untouched until the next
+ * h264r_sync() (or a read-back of the picture) returns, and may then be refilled.  max_blocks = 0 sizes for the worst case (24 per MB). */
+typedef struct h264r_picture_buf {
+    h264r_mb_hdr* hdr;        /* [n_mbs]                    */
+    int16_t*      mv;         /* [n_mbs * H264R_MV_PER_MB]  */
+    uint32_t*     blk_mask;   /* [n_mbs]                    */
+    int16_t*      blocks;     /* [max_blocks * 16]          */
+    size_t        max_blocks;
+    int32_t       n_intra;    /* number of intra macroblocks in hdr[], as counted by the parser; -1 = unknown: the
+                                 library then walks hdr[] itself (and validates mb_class while there)            */
+    void*         base;       /* owned by the library       */
+} h264r_picture_buf;
+int  h264r_picture_buf_alloc(h264r_ctx* ctx, size_t max_blocks, h264r_picture_buf* out);
+void h264r_picture_buf_free(h264r_ctx* ctx, h264r_picture_buf* buf);
+int  h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* buf, size_t n_blocks);
+
 /* Marks the picture complete and queues its reconstruction.  Asynchronous; work is issued to the
  * GPU at the next h264r_flush().  Replaces: residual::Decode + macroblock::Calc for every MB of the
  * picture (h264/residual.cpp:184-201, h264/macroblock.cpp:18-47). */

@@ -39,7 +39,7 @@ struct h264r_ctx {
     cudaStream_t copy_stream = nullptr;     // syntax uploads: overlap the kernels of earlier waves / flushes
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> ev_copied;     // per arena slot: its picture's syntax is resident
-    cudaEvent_t ev_flush[8] = {};           // ring: all kernels of flush number n are done
+    cudaEvent_t ev_flush[64] = {};           // ring: all kernels of flush number n are done
     uint64_t flush_seq = 0, copy_waited_seq = 0, end_seq = 0;
     std::vector<uint64_t> slot_flush_seq;   // flush that last read the slot
     uint32_t* d_dense_mask = nullptr;       // blk_mask / blk_off of the dense layout (shared by all dense pictures)
@@ -57,10 +57,11 @@ struct h264r_ctx {
     uint32_t* d_exc_counter = nullptr;
     // syntax arena: per slot hdr | mv | coeff
     uint8_t* d_syntax = nullptr;
-    size_t slot_bytes = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_coeff = 0;
+    // arena slot = what one upload carries, in this order: descriptor | hdr | mv | blk_mask | coefficient blocks;
+    // then blk_off (written by k_blk_scan, never uploaded)
+    size_t slot_bytes = 0, off_hdr = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_coeff = 0;
     // per-flush control block (descriptors + picture lists), pinned host mirror + device copy
     uint8_t* h_ctrl = nullptr;
-    uint8_t* d_ctrl = nullptr;
     size_t ctrl_bytes = 0;
     // wavefront hand-over words, zeroed at the start of every flush:
     // progress words indexed by (position in the flush's picture lists, macroblock row): 4*max_pending*H, then 2*max_pending tickets
@@ -111,7 +112,7 @@ void fill_desc(h264r_ctx* c, const Pending& p, PicDesc& pd)
 {
     memset(&pd, 0, sizeof(pd));
     uint8_t* s = c->slot_ptr(p.slot);
-    pd.hdr = reinterpret_cast<const h264r_mb_hdr*>(s);
+    pd.hdr = reinterpret_cast<const h264r_mb_hdr*>(s + c->off_hdr);
     pd.mv = reinterpret_cast<const int16_t*>(s + c->off_mv);
     pd.coeff = reinterpret_cast<const int16_t*>(s + c->off_coeff);
     if (p.layout == 2) {
@@ -178,11 +179,12 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     c->y_bytes = (size_t)c->g.pitch_y * (h_mbs * 16 + 2 * PAD_Y);
     c->c_bytes = (size_t)c->g.pitch_c * (h_mbs * 8 + 2 * PAD_YC);
     c->frame_bytes = align_up(c->y_bytes + 2 * c->c_bytes, 256);
-    c->off_mv = align_up((size_t)c->n_mbs * sizeof(h264r_mb_hdr), 256);
+    c->off_hdr = align_up(sizeof(PicDesc), 256);
+    c->off_mv = c->off_hdr + align_up((size_t)c->n_mbs * sizeof(h264r_mb_hdr), 256);
     c->off_mask = c->off_mv + align_up((size_t)c->n_mbs * H264R_MV_PER_MB * 2, 256);
-    c->off_boff = c->off_mask + align_up((size_t)c->n_mbs * 4, 256);
-    c->off_coeff = c->off_boff + align_up((size_t)c->n_mbs * 4, 256);
-    c->slot_bytes = c->off_coeff + align_up((size_t)c->n_mbs * H264R_COEFF_PER_MB * 2, 256);
+    c->off_coeff = c->off_mask + align_up((size_t)c->n_mbs * 4, 256);
+    c->off_boff = c->off_coeff + align_up((size_t)c->n_mbs * H264R_COEFF_PER_MB * 2, 256);
+    c->slot_bytes = c->off_boff + align_up((size_t)c->n_mbs * 4, 256);
     c->ctrl_bytes = align_up((size_t)max_pending * sizeof(PicDesc), 256);      // descriptor table, one entry per arena slot
     auto cleanup = [&](int code) { h264r_destroy(c); return code; };
 #define CUC(call)                                                                                             \
@@ -197,7 +199,7 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     c->ev_copied.assign(max_pending, nullptr);
     for (int i = 0; i < max_pending; i++) CUC(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
-    for (int i = 0; i < 8; i++) CUC(cudaEventCreateWithFlags(&c->ev_flush[i], cudaEventDisableTiming));
+    for (int i = 0; i < 64; i++) CUC(cudaEventCreateWithFlags(&c->ev_flush[i], cudaEventDisableTiming));
     c->slot_flush_seq.assign(max_pending, 0);
     {
         std::vector<uint32_t> m(c->n_mbs, 0xFFFFFFu), o(c->n_mbs);
@@ -214,7 +216,6 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     CUC(cudaMalloc(&c->d_exc_maps, (size_t)max_frames * c->n_mbs));
     CUC(cudaMalloc(&c->d_exc_counter, 256));
     CUC(cudaMalloc(&c->d_syntax, c->slot_bytes * max_pending));
-    CUC(cudaMalloc(&c->d_ctrl, c->ctrl_bytes));
     CUC(cudaMallocHost(&c->h_ctrl, c->ctrl_bytes));
     CUC(cudaMemsetAsync(c->d_exc_counter, 0, 256, c->stream));
     CUC(cudaMemsetAsync(c->d_exc_maps, 0, (size_t)max_frames * c->n_mbs, c->stream));
@@ -240,7 +241,7 @@ void h264r_destroy(h264r_ctx* c)
     for (auto e : c->ev_flush) if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaFree(c->d_frames); cudaFree(c->d_digests); cudaFree(c->d_exc_maps); cudaFree(c->d_exc_counter);
-    cudaFree(c->d_syntax); cudaFree(c->d_ctrl); cudaFree(c->d_sync);
+    cudaFree(c->d_syntax); cudaFree(c->d_sync);
     if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -313,12 +314,12 @@ static int submit_common(h264r_ctx* ctx, int frame_id, int first_mb, int n_mbs, 
     CU(cudaSetDevice(ctx->device));
     // the slot may still be read by the kernels of the flush that used it last
     if (ctx->slot_flush_seq[p->slot] > ctx->copy_waited_seq) {
-        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_flush[ctx->slot_flush_seq[p->slot] & 7], 0));
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_flush[ctx->slot_flush_seq[p->slot] & 63], 0));
         ctx->copy_waited_seq = ctx->slot_flush_seq[p->slot];
     }
     p->layout = layout;
     uint8_t* s = ctx->slot_ptr(p->slot);
-    CU(cudaMemcpyAsync(s + (size_t)first_mb * sizeof(h264r_mb_hdr), hdr, (size_t)n_mbs * sizeof(h264r_mb_hdr), cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaMemcpyAsync(s + ctx->off_hdr + (size_t)first_mb * sizeof(h264r_mb_hdr), hdr, (size_t)n_mbs * sizeof(h264r_mb_hdr), cudaMemcpyHostToDevice, ctx->copy_stream));
     if (mv && p->pp.slice_type == H264R_SLICE_P)
         CU(cudaMemcpyAsync(s + ctx->off_mv + (size_t)first_mb * H264R_MV_PER_MB * 2, mv, (size_t)n_mbs * H264R_MV_PER_MB * 2,
                            cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -357,6 +358,73 @@ int h264r_submit_mbs_packed(h264r_ctx* ctx, int frame_id, int first_mb, int n_mb
     return H264R_OK;
 }
 
+int h264r_picture_buf_alloc(h264r_ctx* ctx, size_t max_blocks, h264r_picture_buf* out)
+{
+    if (!ctx || !out) return fail(ctx, H264R_E_INVAL, "picture_buf_alloc: bad argument");
+    if (max_blocks == 0 || max_blocks > (size_t)24 * ctx->n_mbs) max_blocks = (size_t)24 * ctx->n_mbs;
+    CU(cudaSetDevice(ctx->device));
+    uint8_t* b = nullptr;
+    if (cudaMallocHost(&b, ctx->off_coeff + max_blocks * 32) != cudaSuccess) return fail(ctx, H264R_E_NOMEM, "picture_buf_alloc: pinned allocation failed");
+    memset(b, 0, ctx->off_coeff);
+    out->hdr = reinterpret_cast<h264r_mb_hdr*>(b + ctx->off_hdr);
+    out->mv = reinterpret_cast<int16_t*>(b + ctx->off_mv);
+    out->blk_mask = reinterpret_cast<uint32_t*>(b + ctx->off_mask);
+    out->blocks = reinterpret_cast<int16_t*>(b + ctx->off_coeff);
+    out->max_blocks = max_blocks;
+    out->n_intra = -1;
+    out->base = b;
+    return H264R_OK;
+}
+
+void h264r_picture_buf_free(h264r_ctx* ctx, h264r_picture_buf* buf)
+{
+    if (!ctx || !buf || !buf->base) return;
+    cudaSetDevice(ctx->device);
+    cudaFreeHost(buf->base);
+    memset(buf, 0, sizeof(*buf));
+}
+
+int h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* buf, size_t n_blocks)
+{
+    if (!ctx || !buf || !buf->base || n_blocks > buf->max_blocks) return fail(ctx, H264R_E_INVAL, "submit_picture: bad argument");
+    Pending* p = find_pending(ctx, frame_id);
+    if (!p || p->ended) return fail(ctx, H264R_E_STATE, "submit_picture: no open picture with this frame id");
+    if (p->layout || p->n_submitted) return fail(ctx, H264R_E_STATE, "submit_picture: the picture already has macroblocks");
+    if (buf->n_intra >= 0) {
+        // the parser counted while parsing: no second pass over the headers
+        if (buf->n_intra > ctx->n_mbs || (p->pp.slice_type != H264R_SLICE_P && buf->n_intra != ctx->n_mbs))
+            return fail(ctx, H264R_E_INVAL, "submit_picture: n_intra inconsistent with the picture");
+        p->n_intra = buf->n_intra;
+    } else {
+        const h264r_mb_hdr* hdr = buf->hdr;
+        for (int i = 0; i < ctx->n_mbs; i++) {
+            uint8_t cls = hdr[i].mb_class;
+            if (cls == 3 || cls > H264R_MB_P8x8) return fail(ctx, H264R_E_INVAL, "submit_picture: unknown mb_class");
+            if (cls <= H264R_MB_I16x16) p->n_intra++;
+            else if (p->pp.slice_type != H264R_SLICE_P) return fail(ctx, H264R_E_INVAL, "submit_picture: inter macroblock in an I picture");
+            if ((ctx->flags & H264R_REF_COMPAT) && (cls == H264R_MB_I8x8 || (hdr[i].flags & H264R_T8x8)))
+                return fail(ctx, H264R_E_INVAL, "submit_picture: 8x8 transform is not part of REF_COMPAT (the reference has none)");
+        }
+    }
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->slot_flush_seq[p->slot] > ctx->copy_waited_seq) {
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_flush[ctx->slot_flush_seq[p->slot] & 63], 0));
+        ctx->copy_waited_seq = ctx->slot_flush_seq[p->slot];
+    }
+    p->layout = 2;
+    p->n_blocks = n_blocks;
+    p->n_submitted = ctx->n_mbs;
+    // descriptor in front, then ONE transfer for descriptor + headers + vectors + masks + the blocks present
+    fill_desc(ctx, *p, *reinterpret_cast<PicDesc*>(buf->base));
+    CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot), buf->base, ctx->off_coeff + n_blocks * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaEventRecord(ctx->ev_copied[p->slot], ctx->copy_stream));
+    reinterpret_cast<PicDesc*>(ctx->h_ctrl)[p->slot].deblock_on = reinterpret_cast<const PicDesc*>(buf->base)->deblock_on;
+    p->seq = ++ctx->end_seq;
+    p->ended = true;
+    ctx->frame_state[frame_id] = FRAME_QUEUED;
+    return H264R_OK;
+}
+
 int h264r_frame_end(h264r_ctx* ctx, int frame_id)
 {
     if (!ctx) return H264R_E_INVAL;
@@ -366,9 +434,8 @@ int h264r_frame_end(h264r_ctx* ctx, int frame_id)
     CU(cudaSetDevice(ctx->device));
     // the picture's descriptor travels with its syntax (see PicList in h264r_kernels.cuh)
     PicDesc* h_desc = reinterpret_cast<PicDesc*>(ctx->h_ctrl);
-    PicDesc* d_desc = reinterpret_cast<PicDesc*>(ctx->d_ctrl);
     fill_desc(ctx, *p, h_desc[p->slot]);
-    CU(cudaMemcpyAsync(&d_desc[p->slot], &h_desc[p->slot], sizeof(PicDesc), cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot), &h_desc[p->slot], sizeof(PicDesc), cudaMemcpyHostToDevice, ctx->copy_stream));
     CU(cudaEventRecord(ctx->ev_copied[p->slot], ctx->copy_stream));
     p->seq = ++ctx->end_seq;
     p->ended = true;
@@ -400,7 +467,7 @@ int h264r_flush(h264r_ctx* ctx)
         if (wv + 1 > n_waves) n_waves = wv + 1;
     }
     const int n = (int)run.size();
-    const PicDesc* d_desc = reinterpret_cast<const PicDesc*>(ctx->d_ctrl);
+    const DescTable d_desc{ctx->d_syntax, ctx->slot_bytes};
     const PicDesc* h_desc = reinterpret_cast<const PicDesc*>(ctx->h_ctrl);
     CU(cudaMemsetAsync(ctx->d_sync, 0, ctx->sync_ints * sizeof(int), ctx->stream));
     int* const progress0 = ctx->d_sync;
@@ -496,7 +563,7 @@ int h264r_flush(h264r_ctx* ctx)
     CU(cudaGetLastError());
     ctx->timing_valid = true;
     ctx->flush_seq++;
-    CU(cudaEventRecord(ctx->ev_flush[ctx->flush_seq & 7], ctx->stream));
+    CU(cudaEventRecord(ctx->ev_flush[ctx->flush_seq & 63], ctx->stream));
     std::vector<Pending> keep;
     for (auto& p : ctx->pending) {
         if (p.ended) {

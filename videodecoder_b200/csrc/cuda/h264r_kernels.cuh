@@ -18,8 +18,13 @@ struct WarpExec {
 // passed BY VALUE in the kernel parameters.  Descriptors are uploaded with their picture's syntax (copy stream), so
 // a flush itself copies nothing: a host-to-device copy issued at flush time would queue behind every syntax upload
 // still in flight and serialise the kernels after them.
-constexpr int PIC_LIST_MAX = 944;
+constexpr int PIC_LIST_MAX = 940;
 struct PicList { int n; int slot[PIC_LIST_MAX]; };
+// descriptor of arena slot s: the first bytes of the slot itself (it is uploaded with, and in front of, the syntax)
+struct DescTable {
+    const uint8_t* base; size_t stride;
+    __device__ __forceinline__ const PicDesc& operator[](int slot) const { return *reinterpret_cast<const PicDesc*>(base + (size_t)slot * stride); }
+};
 
 constexpr int INTER_WARPS = 4;       // warps per CTA of the inter / residual kernels
 
@@ -43,7 +48,7 @@ __global__ void __launch_bounds__(INTER_WARPS * 32) k_residual(PicDesc pd, int n
 // (picture, MB) pairs.
 // ------------------------------------------------------------------------------------------------
 template <bool COMPAT>
-__global__ void __launch_bounds__(INTER_WARPS * 32) k_inter(const PicDesc* __restrict__ descs, const __grid_constant__ PicList list,
+__global__ void __launch_bounds__(INTER_WARPS * 32) k_inter(const DescTable descs, const __grid_constant__ PicList list,
                                                             Geometry g, uint32_t* excursions)
 {
     __shared__ WarpWork work[INTER_WARPS];
@@ -111,7 +116,7 @@ __device__ __forceinline__ int row_ticket(int* ticket)
 }
 
 template <bool COMPAT>
-__global__ void __launch_bounds__(ROW_WARPS * 32) k_intra_rows(const PicDesc* __restrict__ descs, const __grid_constant__ PicList list,
+__global__ void __launch_bounds__(ROW_WARPS * 32) k_intra_rows(const DescTable descs, const __grid_constant__ PicList list,
                                                               Geometry g, int* progress, int* ticket, uint32_t* excursions)
 {
     __shared__ MbWork work[ROW_WARPS];
@@ -171,7 +176,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_intra_rows(const PicDesc* __
     if (ex.lane == 0 && exc) atomicAdd(excursions, exc);
 }
 
-__global__ void __launch_bounds__(ROW_WARPS * 32) k_deblock_rows(const PicDesc* __restrict__ descs, const __grid_constant__ PicList list,
+__global__ void __launch_bounds__(ROW_WARPS * 32) k_deblock_rows(const DescTable descs, const __grid_constant__ PicList list,
                                                                 Geometry g, int* progress, int* ticket)
 {
     __shared__ MbWork work[ROW_WARPS];
@@ -199,7 +204,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_deblock_rows(const PicDesc* 
 // popcount(blk_mask).  One CTA per picture submitted through h264r_submit_mbs_packed.
 // ------------------------------------------------------------------------------------------------
 struct ScanJob { const uint32_t* mask; uint32_t* off; };
-__global__ void __launch_bounds__(1024) k_blk_scan(const PicDesc* __restrict__ descs, const __grid_constant__ PicList list, int n_mbs)
+__global__ void __launch_bounds__(1024) k_blk_scan(const DescTable descs, const __grid_constant__ PicList list, int n_mbs)
 {
     const PicDesc& pdj = descs[list.slot[blockIdx.x]];
     const ScanJob job{pdj.blk_mask, const_cast<uint32_t*>(pdj.blk_off)};
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(1024) k_blk_scan(const PicDesc* __restrict__ d
 // coordinate clamps).  One warp per padded row; luma always, chroma when `chroma` (spec mode: the
 // reference has no chroma motion compensation, D4).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_pad(const PicDesc* __restrict__ descs, const __grid_constant__ PicList list, Geometry g, int chroma)
+__global__ void __launch_bounds__(128) k_pad(const DescTable descs, const __grid_constant__ PicList list, Geometry g, int chroma)
 {
     const int Wl = g.w_mbs * 16, Hl = g.h_mbs * 16, Wc = Wl >> 1, Hc = Hl >> 1;
     const int rows_l = Hl + 2 * PAD_Y, rows_c = chroma ? Hc + 2 * PAD_YC : 0, rows = rows_l + 2 * rows_c;

@@ -10,6 +10,11 @@ import numpy as np
 
 from . import abi, build
 
+class PictureBufStruct(ctypes.Structure):
+    _fields_ = [("hdr", ctypes.c_void_p), ("mv", ctypes.c_void_p), ("blk_mask", ctypes.c_void_p), ("blocks", ctypes.c_void_p),
+                ("max_blocks", ctypes.c_size_t), ("n_intra", ctypes.c_int32), ("base", ctypes.c_void_p)]
+
+
 _lib = None
 
 
@@ -47,6 +52,10 @@ def load_library():
     L.h264r_submit_mbs.argtypes = [vp, ci, ci, ci, vp, vp, vp]
     L.h264r_submit_mbs_packed.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, ctypes.c_size_t]
     L.h264r_wait_uploads.argtypes = [vp]
+    L.h264r_picture_buf_alloc.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(PictureBufStruct)]
+    L.h264r_picture_buf_free.argtypes = [vp, ctypes.POINTER(PictureBufStruct)]
+    L.h264r_picture_buf_free.restype = None
+    L.h264r_submit_picture.argtypes = [vp, ci, ctypes.POINTER(PictureBufStruct), ctypes.c_size_t]
     L.h264r_frame_end.argtypes = [vp, ci]
     L.h264r_flush.argtypes = [vp]
     L.h264r_sync.argtypes = [vp]
@@ -72,7 +81,7 @@ def load_library():
 
 EXPORTS = [
     "h264r_abi_version", "h264r_last_error", "h264r_create", "h264r_destroy", "h264r_host_alloc", "h264r_host_free",
-    "h264r_frame_begin", "h264r_submit_mbs", "h264r_submit_mbs_packed", "h264r_wait_uploads", "h264r_frame_end", "h264r_flush", "h264r_sync", "h264r_read_planes",
+    "h264r_frame_begin", "h264r_submit_mbs", "h264r_submit_mbs_packed", "h264r_wait_uploads", "h264r_picture_buf_alloc", "h264r_picture_buf_free", "h264r_submit_picture", "h264r_frame_end", "h264r_flush", "h264r_sync", "h264r_read_planes",
     "h264r_frame_digest", "h264r_frame_digests", "h264r_range_excursions", "h264r_excursion_map",
     "h264r_residual_mbs", "h264r_release", "h264r_last_flush_stats", "h264r_set_profiling",
     "h264r_last_flush_kernel_ms", "h264r_last_flush_launch_ms", "h264r_mark", "h264r_elapsed_ms",
@@ -106,6 +115,40 @@ class PinnedBuffer:
             self.engine.L.h264r_host_free(self.engine.ctx, self.ptr)
             self.ptr = None
             self.array = None
+
+
+class PictureBuf:
+    """h264r_picture_buf: pinned staging of one picture in the engine's upload layout (numpy views)."""
+
+    def __init__(self, engine, max_blocks=0):
+        self.engine = engine
+        self.c = PictureBufStruct()
+        engine._check(engine.L.h264r_picture_buf_alloc(engine.ctx, max_blocks, ctypes.byref(self.c)))
+        n = engine.n_mbs
+
+        def view(ptr, dtype, count):
+            dt = np.dtype(dtype)
+            buf = (ctypes.c_uint8 * (count * dt.itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dt, count=count)
+        self.hdr = view(self.c.hdr, abi.MB_HDR_DTYPE, n)
+        self.mv = view(self.c.mv, np.int16, n * 32).reshape(n, 32)
+        self.blk_mask = view(self.c.blk_mask, np.uint32, n)
+        self.blocks = view(self.c.blocks, np.int16, int(self.c.max_blocks) * 16).reshape(-1, 16)
+        self.n_blocks = 0
+
+    def fill(self, hdr, mv, blk_mask, blocks):
+        self.hdr[:] = np.ascontiguousarray(hdr).view(abi.MB_HDR_DTYPE).reshape(-1)
+        if mv is not None:
+            self.mv[:] = mv
+        self.blk_mask[:] = blk_mask
+        self.n_blocks = int(blocks.shape[0])
+        self.blocks[:self.n_blocks] = blocks
+        self.c.n_intra = int((self.hdr["mb_class"] <= abi.MB_I16x16).sum())       # a parser counts this as it goes
+
+    def free(self):
+        if self.c.base:
+            self.hdr = self.mv = self.blk_mask = self.blocks = None
+            self.engine.L.h264r_picture_buf_free(self.engine.ctx, ctypes.byref(self.c))
 
 
 class Engine:
@@ -171,6 +214,14 @@ class Engine:
         self.frame_begin(frame_id, pp)
         self.submit_mbs_packed(frame_id, hdr, mv, blk_mask, blocks)
         self.frame_end(frame_id)
+
+    def picture_buf(self, max_blocks=0):
+        return PictureBuf(self, max_blocks)
+
+    def submit_picture_buf(self, frame_id, pp, buf):
+        """whole picture from a PictureBuf: one DMA, queued at once"""
+        self.frame_begin(frame_id, pp)
+        self._check(self.L.h264r_submit_picture(self.ctx, frame_id, ctypes.byref(buf.c), buf.n_blocks))
 
     def flush(self):
         self._check(self.L.h264r_flush(self.ctx))

@@ -7,6 +7,8 @@
 // test-suite compare the kernels' arithmetic with the oracle without a GPU.  It is NOT a CPU
 // fallback: nothing in the product loads it.
 #include "../../videodecoder_b200/csrc/cuda/h264r_seq.cuh"
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -139,7 +141,7 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
         ry[i] = refs.back().y(); ru[i] = refs.back().u(); rv[i] = refs.back().v();
     }
     for (int i = 0; i < H264R_MAX_REFS; i++) if (!ry[i] && ry[0]) { ry[i] = ry[0]; ru[i] = ru[0]; rv[i] = rv[0]; }
-    Geometry g{w_mbs, h_mbs, cur.py, cur.pc};
+    Geometry g = make_geometry(w_mbs, h_mbs, cur.py, cur.pc);
     PicDesc pd;
     fill_desc(pd, pp, hdr, mv, coeff, cur.y(), cur.u(), cur.v(), ry, ru, rv, exc_map);
     CoeffStore cs;
@@ -159,6 +161,9 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
     }
     static uint16_t lut[INTRA4_LUT_SIZE];
     intra4_lut_fill(lut, 0, 1);
+    for (int xf = 0; xf < 4; xf++)
+        for (int yf = 0; yf < 4; yf++)
+            if (mc_need(xf, yf) != mc_select(xf, yf).need) { fprintf(stderr, "mc_need table disagrees with mc_select at (%d,%d)\n", xf, yf); abort(); }
     int prev = -2;
     for (int a = 0; a < n; a++) {
         h264r_mb_hdr h = load_hdr(pd, a);

@@ -171,9 +171,7 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     ctx = c;
     c->device = device;
     c->flags = flags;
-    c->g.w_mbs = w_mbs; c->g.h_mbs = h_mbs;
-    c->g.pitch_y = (int)align_up((size_t)w_mbs * 16 + 2 * PAD_X, 128);
-    c->g.pitch_c = (int)align_up((size_t)w_mbs * 8 + 2 * PAD_XC, 128);
+    c->g = make_geometry(w_mbs, h_mbs, (int)align_up((size_t)w_mbs * 16 + 2 * PAD_X, 128), (int)align_up((size_t)w_mbs * 8 + 2 * PAD_XC, 128));
     c->n_mbs = w_mbs * h_mbs;
     c->max_frames = max_frames; c->max_pending = max_pending;
     c->y_bytes = (size_t)c->g.pitch_y * (h_mbs * 16 + 2 * PAD_Y);
@@ -516,13 +514,13 @@ int h264r_flush(h264r_ctx* ctx)
             ctx->last_launches++;
         });
         for_chunks(wv, [&](const Pending& p) { return p.pp.slice_type == H264R_SLICE_P && p.n_intra < ctx->n_mbs; }, [&](const PicList& L) {
-            long total = (long)L.n * ctx->n_mbs;
-            long want = (total + INTER_WARPS - 1) / INTER_WARPS;
-            long cap = (long)sm_count * 16 * 4;                   // 16 resident CTAs per SM, four passes
-            int blocks = (int)(want < cap ? want : cap);
+            // grid.y = picture, grid.x strides over its macroblocks; about eight CTA generations in total
+            int want = (ctx->n_mbs + INTER_WARPS - 1) / INTER_WARPS;
+            int cap = (sm_count * 16 * 8 + L.n - 1) / L.n;
+            dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)L.n);
             prof_begin(0);
-            if (compat) k_inter<true><<<blocks, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g, ctx->d_exc_counter);
-            else k_inter<false><<<blocks, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g, ctx->d_exc_counter);
+            if (compat) k_inter<true><<<grid, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g, ctx->d_exc_counter);
+            else k_inter<false><<<grid, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g, ctx->d_exc_counter);
             prof_end();
             ctx->last_launches++;
         });

@@ -37,7 +37,22 @@ namespace h264r {
 struct Geometry {
     int w_mbs, h_mbs;
     int pitch_y, pitch_c;      // bytes per row of the luma / chroma planes
+    uint32_t w_magic;          // ceil(2^32 / w_mbs): a / w_mbs = umulhi(a, w_magic) for every macroblock address a
 };
+HD Geometry make_geometry(int w_mbs, int h_mbs, int pitch_y, int pitch_c)
+{
+    return Geometry{w_mbs, h_mbs, pitch_y, pitch_c, (uint32_t)((0x100000000ull + (uint32_t)w_mbs - 1) / (uint32_t)w_mbs)};
+}
+// macroblock address -> (column, row)
+HD void mb_xy(const Geometry& g, int a, int& mbx, int& mby)
+{
+#if defined(__CUDA_ARCH__)
+    mby = (int)__umulhi((uint32_t)a, g.w_magic);
+#else
+    mby = (int)(((uint64_t)(uint32_t)a * g.w_magic) >> 32);
+#endif
+    mbx = a - mby * g.w_mbs;
+}
 
 // Everything a kernel needs to know about one picture of a wave (lives in device memory).
 struct PicDesc {
@@ -351,7 +366,8 @@ template <bool COMPAT>
 HD void phase_inter_luma(MbWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane)
 {
     int ras = lane >> 1, bx = ras & 3, by = ras >> 2, q = (by >> 1) * 2 + (bx >> 1);
-    int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    int mbx, mby;
+    mb_xy(g, a, mbx, mby);
     const int16_t* mvp = pd.mv + (size_t)a * H264R_MV_PER_MB + ras * 2;
     int mvx = H264R_LDG(mvp), mvy = H264R_LDG(mvp + 1);
     int ri = h.u.ref_idx[q] & 15;
@@ -387,7 +403,8 @@ HD void phase_inter_chroma(MbWork& w, const PicDesc& pd, const Geometry& g, cons
     int plane = lane >> 4, l = lane & 15;
     // lane l covers chroma row-pair block: 2x2 samples of luma 4x4 block l (raster)
     int bx = l & 3, by = l >> 2, q = (by >> 1) * 2 + (bx >> 1);
-    int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    int mbx, mby;
+    mb_xy(g, a, mbx, mby);
     int cw = g.w_mbs * 8, ch = g.h_mbs * 8;
     if (COMPAT) {
         for (int k = 0; k < 4; k++) {
@@ -418,7 +435,8 @@ HD void phase_inter_chroma(MbWork& w, const PicDesc& pd, const Geometry& g, cons
 // (16 bytes), 16..23 one Cb row, 24..31 one Cr row (8 bytes).
 HD void phase_store(const MbWork& w, const PicDesc& pd, const Geometry& g, int a, int lane)
 {
-    int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    int mbx, mby;
+    mb_xy(g, a, mbx, mby);
     if (lane < 16) {
         const uint8_t* s = &w.tile[H264R_TI(0, lane)];
         uint32_t v[4];
@@ -444,7 +462,8 @@ HD void phase_store(const MbWork& w, const PicDesc& pd, const Geometry& g, int a
 // Neighbours were written by other warps of the same kernel, hence LDCG.
 HD void phase_intra_edges(MbWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane, bool chroma)
 {
-    int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    int mbx, mby;
+    mb_xy(g, a, mbx, mby);
     bool A = h.flags & H264R_AVAIL_A, B = h.flags & H264R_AVAIL_B, C = h.flags & H264R_AVAIL_C, D = h.flags & H264R_AVAIL_D;
     const uint8_t* y = pd.y;
     if (lane < 25) {
@@ -488,7 +507,8 @@ HD void phase_intra16(MbWork& w, const PicDesc& pd, const Geometry& g, const h26
         else if (B) {
             if (COMPAT) {
                 // D5: top-only DC sums column 15 of the MB above (h264/macroblock.cpp:1410-1411)
-                int mbx = a % g.w_mbs, mby = a / g.w_mbs, sc = 0;
+                int mbx, mby, sc = 0;
+                mb_xy(g, a, mbx, mby);
                 for (int k = 0; k < 16; k++) sc += H264R_LDCG(pd.y + (size_t)(mby * 16 - 16 + k) * g.pitch_y + mbx * 16 + 15);
                 dc = (sc + 8) >> 4;
             } else dc = (st + 8) >> 4;
@@ -834,7 +854,8 @@ HD bool blk_coded_global(const PicDesc& pd, const h264r_mb_hdr& h, int a, int ra
 // Phase D0a: load the tiles (luma x,y = -4..15; chroma x,y = -2..7).  w.coef must hold the MB's levels.
 HD void phase_deblock_load(MbWork& w, const PicDesc& pd, const Geometry& g, int a, int lane)
 {
-    int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    int mbx, mby;
+    mb_xy(g, a, mbx, mby);
     for (int i = lane; i < 20 * 5; i += 32) {          // 20 rows x 5 words
         int r = i / 5 - 4, cw = (i % 5) * 4 - 4;
         int yy = mby * 16 + r, xx = mbx * 16 + cw;
@@ -856,7 +877,8 @@ HD void phase_deblock_load(MbWork& w, const PicDesc& pd, const Geometry& g, int 
 HD void phase_deblock_bs(MbWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane)
 {
     int dir = lane >> 4, e = (lane >> 2) & 3, k = lane & 3;
-    int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    int mbx, mby;
+    mb_xy(g, a, mbx, mby);
     int bs = 0;
     bool t8 = (h.flags & H264R_T8x8) != 0;
     int an = a, rasq, rasp;
@@ -977,7 +999,8 @@ HD void phase_deblock_dir(MbWork& w, const PicDesc& pd, const h264r_mb_hdr& h, c
 // -3..-1 x columns 0..15; chroma rows 0..7 x columns -2..7 and row -1 x columns 0..7.
 HD void phase_deblock_store(const MbWork& w, const PicDesc& pd, const Geometry& g, int a, int lane)
 {
-    int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    int mbx, mby;
+    mb_xy(g, a, mbx, mby);
     auto word = [](const uint8_t* s) { return (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24); };
     for (int i = lane; i < 19 * 5; i += 32) {
         int r = i / 5 - 3, cw = (i % 5) * 4 - 4;

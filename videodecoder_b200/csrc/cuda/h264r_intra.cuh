@@ -60,8 +60,7 @@ HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr&
                 }
                 f += ((0xA6C0 >> (i * 4 + k)) & 1) ? -t : t;
             }
-            const int v0t[6] = {10, 11, 13, 14, 16, 18};
-            int s = (qp * 43) >> 8, m = qp - 6 * s, ls = 16 * v0t[m];
+            int s = (qp * 43) >> 8, m = qp - 6 * s, ls = 16 * norm_adjust_dc(m);
             c[0] = (s >= 6) ? (f * ls) * (1 << (s - 6)) : ((f * ls + (1 << (5 - s))) >> (6 - s));
             bypass = true;
         }
@@ -74,9 +73,8 @@ HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr&
             int f;
             if (COMPAT) f = (b == 0 || b == 3) ? c3 : -c3;      // reference's chroma DC product (h264/matrix.cpp:150-171)
             else f = c0 + ((b & 1) ? -c1 : c1) + ((b & 2) ? -c2 : c2) + ((b == 1 || b == 2) ? -c3 : c3);
-            const int v0t[6] = {10, 11, 13, 14, 16, 18};
             int s = (qp * 43) >> 8, m = qp - 6 * s;
-            c[0] = ((f * 16 * v0t[m]) * (1 << s)) >> 5;
+            c[0] = ((f * 16 * norm_adjust_dc(m)) * (1 << s)) >> 5;
             bypass = true;
         }
         int nz = 0;
@@ -114,7 +112,8 @@ HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr&
 // is the left neighbour.  Other neighbours were written by other warps of the same kernel: ld.global.cg.
 HD void phase_intra_edges_fast(MbWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane, bool chroma, bool carry)
 {
-    const int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    int mbx, mby;
+    mb_xy(g, a, mbx, mby);
     const bool A = h.flags & H264R_AVAIL_A, B = h.flags & H264R_AVAIL_B, C = h.flags & H264R_AVAIL_C, D = h.flags & H264R_AVAIL_D;
     if (lane < 7) {
         const int x = lane * 4 - 4;
@@ -155,7 +154,8 @@ HD void phase_intra16_fast(MbWork& w, const PicDesc& pd, const Geometry& g, cons
     const bool A = h.flags & H264R_AVAIL_A, B = h.flags & H264R_AVAIL_B;
     const int mode = h.intra_modes & 3;
     const int row = lane >> 1, c0 = (lane & 1) * 8;
-    const int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    int mbx, mby;
+    mb_xy(g, a, mbx, mby);
     uint32_t p0, p1;
     if (mode == 0) {
         p0 = *reinterpret_cast<const uint32_t*>(&TL(c0, -1));
@@ -328,7 +328,8 @@ HD void phase_intra4_pair(MbWork& w, const h264r_mb_hdr& h, const uint16_t* lut,
 HD void store_luma_tile(const MbWork& w, const PicDesc& pd, const Geometry& g, int a, int lane)
 {
     if (lane >= 16) return;
-    const int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    int mbx, mby;
+    mb_xy(g, a, mbx, mby);
     *reinterpret_cast<uint4*>(pd.y + (size_t)(mby * 16 + lane) * g.pitch_y + mbx * 16) = *reinterpret_cast<const uint4*>(&TL(0, lane));
 }
 // chroma rows: lanes 16..31, one 64-bit row each.  COMPAT: the reference has no chroma prediction, sample =
@@ -337,7 +338,8 @@ template <bool COMPAT>
 HD void store_chroma(const MbWork& w, const PicDesc& pd, const Geometry& g, int a, int lane)
 {
     if (lane < 16) return;
-    const int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    int mbx, mby;
+    mb_xy(g, a, mbx, mby);
     const int p = (lane - 16) >> 3, row = (lane - 16) & 7;
     uint2 v;
     if (COMPAT) {

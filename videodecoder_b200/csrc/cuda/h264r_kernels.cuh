@@ -26,6 +26,9 @@ struct DescTable {
     __device__ __forceinline__ const PicDesc& operator[](int slot) const { return *reinterpret_cast<const PicDesc*>(base + (size_t)slot * stride); }
 };
 
+#ifndef H264R_INTER_MIN_CTAS
+#define H264R_INTER_MIN_CTAS 8       // resident CTAs per SM the inter kernel is compiled for (register cap 65536 / (128 * this))
+#endif
 constexpr int INTER_WARPS = 4;       // warps per CTA of the inter / residual kernels
 
 // ------------------------------------------------------------------------------------------------
@@ -44,11 +47,11 @@ __global__ void __launch_bounds__(INTER_WARPS * 32) k_residual(PicDesc pd, int n
 
 // ------------------------------------------------------------------------------------------------
 // K1+K3: all inter macroblocks of the P pictures of one wave.  No dependencies between MBs (their
-// references are complete pictures), so this is a flat grid: one warp per MB, grid-stride over
-// (picture, MB) pairs.
+// references are complete pictures), so this is a flat grid: one warp per MB, blockIdx.y = picture,
+// blockIdx.x strides over its macroblocks.
 // ------------------------------------------------------------------------------------------------
 template <bool COMPAT>
-__global__ void __launch_bounds__(INTER_WARPS * 32) k_inter(const DescTable descs, const __grid_constant__ PicList list,
+__global__ void __launch_bounds__(INTER_WARPS * 32, H264R_INTER_MIN_CTAS) k_inter(const DescTable descs, const __grid_constant__ PicList list,
                                                             Geometry g, uint32_t* excursions)
 {
     __shared__ WarpWork work[INTER_WARPS];
@@ -56,10 +59,8 @@ __global__ void __launch_bounds__(INTER_WARPS * 32) k_inter(const DescTable desc
     WarpExec ex{(int)(threadIdx.x & 31)};
     WarpWork& w = work[warp];
     const int n_mbs = g.w_mbs * g.h_mbs;
-    const long total = (long)list.n * n_mbs;
-    for (long i = (long)blockIdx.x * INTER_WARPS + warp; i < total; i += (long)gridDim.x * INTER_WARPS) {
-        int p = (int)(i / n_mbs), a = (int)(i - (long)p * n_mbs);
-        const PicDesc& pd = descs[list.slot[p]];
+    const PicDesc& pd = descs[list.slot[blockIdx.y]];
+    for (int a = blockIdx.x * INTER_WARPS + warp; a < n_mbs; a += gridDim.x * INTER_WARPS) {
         h264r_mb_hdr h = load_hdr(pd, a);
         if (is_intra(h.mb_class)) continue;       // warp-uniform
         uint32_t exc = seq_inter_any<COMPAT>(ex, w, pd, g, h, a);

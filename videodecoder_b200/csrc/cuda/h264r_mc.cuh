@@ -154,14 +154,22 @@ struct alignas(16) InterWork {
 struct Dequant {                // per QP: d = (c * mul + add) >> shr for the three position classes
     int mul[3], add, shr;
 };
+// normAdjust4x4 columns as byte tables indexed by qp % 6: (even,even) 10 11 13 14 16 18, (odd,odd) 16 18 20 23 25 29,
+// other 13 14 16 18 20 23
+HD constexpr uint64_t norm_adjust_ee() { return 0x12100E0D0B0Aull; }
+HD constexpr uint64_t norm_adjust_oo() { return 0x1D1917141210ull; }
+HD constexpr uint64_t norm_adjust_other() { return 0x171412100E0Dull; }
+HD int norm_adjust_dc(int m) { return (int)((norm_adjust_ee() >> (8 * m)) & 255); }
 HD Dequant make_dequant(int qp)
 {
     // normAdjust4x4 (reference residual::LevelScale4x4, h264/residual.cpp:170-183): columns = (even,even) / (odd,odd) / other
-    const int v[6][3] = {{10, 16, 13}, {11, 18, 14}, {13, 20, 16}, {14, 23, 18}, {16, 25, 20}, {18, 29, 23}};
+    // one byte per qp % 6 = 0..5, no local-memory table
     int s = (qp * 43) >> 8, m = qp - 6 * s;         // qp / 6, qp % 6 for 0 <= qp < 64
+    const int v[3] = {(int)((norm_adjust_ee() >> (8 * m)) & 255), (int)((norm_adjust_oo() >> (8 * m)) & 255),
+                      (int)((norm_adjust_other() >> (8 * m)) & 255)};
     Dequant q;
-    if (s >= 4) { for (int k = 0; k < 3; k++) q.mul[k] = (16 * v[m][k]) << (s - 4); q.add = 0; q.shr = 0; }
-    else { for (int k = 0; k < 3; k++) q.mul[k] = 16 * v[m][k]; q.add = 1 << (3 - s); q.shr = 4 - s; }
+    if (s >= 4) { for (int k = 0; k < 3; k++) q.mul[k] = (16 * v[k]) << (s - 4); q.add = 0; q.shr = 0; }
+    else { for (int k = 0; k < 3; k++) q.mul[k] = 16 * v[k]; q.add = 1 << (3 - s); q.shr = 4 - s; }
     return q;
 }
 // c: 16 levels (raster); returns residual in r.  Same arithmetic as scale_idct4
@@ -248,8 +256,9 @@ HD McSel mc_select(int xf, int yf)
     //                      sel:  0  1  2  3  4  5  6  7  8  9 10 11 12 13 14 15
     // P: 0 G, 1 H, 2 M, 3 b, 4 v, 5 j   0  0  4  2  0  3  4  4  3  3  5  5  1  3  5  4
     // Q: 0 G, 1 b, 2 v, 3 s, 4 j        0  2  2  2  1  2  4  3  1  4  4  3  1  2  2  3
-    const uint64_t PT = 0x4531553344302400ull, QT = 0x3221344134212220ull;
-    const int p = (int)((PT >> (4 * sel)) & 15), q = (int)((QT >> (4 * sel)) & 15);
+    const uint32_t PTl = 0x44302400u, PTh = 0x45315533u, QTl = 0x34212220u, QTh = 0x32213441u;
+    const int sh4 = 4 * (sel & 7);
+    const int p = (int)(((sel & 8 ? PTh : PTl) >> sh4) & 15u), q = (int)(((sel & 8 ? QTh : QTl) >> sh4) & 15u);
     McSel m;
     m.pG = p == 0 ? ~0u : 0u; m.pH = p == 1 ? ~0u : 0u; m.pM = p == 2 ? ~0u : 0u;
     m.pb = p == 3 ? ~0u : 0u; m.pv = p == 4 ? ~0u : 0u; m.pj = p == 5 ? ~0u : 0u;
@@ -261,27 +270,36 @@ HD McSel mc_select(int xf, int yf)
     m.tv1 = 1u << vshift; m.tv5 = (uint32_t)(-5 & 255) << vshift; m.tv20 = 20u << vshift;
     return m;
 }
-HD int mc_need(int xf, int yf) { return mc_select(xf, yf).need; }
+HD int mc_need(int xf, int yf)
+{
+    // mc_select(xf, yf).need as a table, 4 bits per position xf*4 + yf (checked against mc_select by the test emulator):
+    // 0:- 1:V 2:V 3:V 4:H 5:HV 6:HSVJ 7:SV 8:H 9:HSJ 10:HSJ 11:HSJ 12:H 13:HV 14:HSVJ 15:SV
+    const int sel = xf * 4 + yf;
+    const uint32_t lo = 0x6F514440u, hi = 0x6F51BBB1u;
+    return (int)(((sel & 8 ? hi : lo) >> (4 * (sel & 7))) & 15u);
+}
 
 // ---- window staging ----------------------------------------------------------------------------------------
-// One staged word = bytes (x .. x+3, y) of the padded reference plane, x of any alignment.
-HD uint32_t ref_word(const uint8_t* ref, int gpitch, int x, int y)
-{
-    const uint8_t* p = ref + (ptrdiff_t)y * gpitch + x;
-    uintptr_t ad = reinterpret_cast<uintptr_t>(p);
-    const uint32_t* q = reinterpret_cast<const uint32_t*>(ad & ~(uintptr_t)3);
-    return funnel_r(H264R_LDG(q), H264R_LDG(q + 1), (int)(ad & 3) * 8);
-}
-// items first, first + STRIDE, ... of a window of NROWS x NWORDS words whose top-left byte is (sx, sy)
+// Items first, first + STRIDE, ... of a window of NROWS x NWORDS words whose top-left byte is (sx, sy) of the padded
+// reference plane.  A staged word = 4 bytes at any alignment = funnel shift of two aligned words; the alignment is
+// the same for every word of a window (the pitch is a multiple of 4), and the source address advances incrementally.
 template <int NROWS, int NWORDS, int STRIDE>
 HD void stage_window(uint32_t* dst, const uint8_t* ref, int gpitch, int sx, int sy, int first)
 {
+    constexpr int DR = STRIDE / NWORDS, DJ = STRIDE % NWORDS;       // one step = DR rows + DJ words
+    int row = first / NWORDS, j = first - row * NWORDS;
+    const uint8_t* p0 = ref + (ptrdiff_t)(sy + row) * gpitch + sx + 4 * j;
+    const int sh = (int)(reinterpret_cast<uintptr_t>(p0) & 3) * 8;
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p0) & ~(uintptr_t)3);
+    const int wpitch = gpitch >> 2;
 #pragma unroll
     for (int i = 0; i < (NROWS * NWORDS + STRIDE - 1) / STRIDE; i++) {
-        int it = first + i * STRIDE;
-        if (it < NROWS * NWORDS) {
-            int row = it / NWORDS, j = it - row * NWORDS;
-            dst[it] = ref_word(ref, gpitch, sx + 4 * j, sy + row);
+        const int it = first + i * STRIDE;
+        if (it < NROWS * NWORDS) dst[it] = funnel_r(H264R_LDG(q), H264R_LDG(q + 1), sh);
+        q += DR * wpitch + DJ;
+        if (DJ) {
+            j += DJ;
+            if (j >= NWORDS) { j -= NWORDS; q += wpitch - NWORDS; }
         }
     }
 }
@@ -297,7 +315,8 @@ HD void phase_inter_stage(InterWork& w, const PicDesc& pd, const Geometry& g, co
     load_mvs(pd, a, mv);
     const int shape = inter_shape<COMPAT>(h, mv);
     if (lane == 0) { w.shape = shape; w.excursions = 0; }
-    const int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    int mbx, mby;
+    mb_xy(g, a, mbx, mby);
     const int W = g.w_mbs * 16, H = g.h_mbs * 16;
     {
         uint32_t v = load_mv1(pd, a, lane >> 1);
@@ -463,7 +482,8 @@ HD uint32_t weight_packed(uint32_t pred, int logwd, int wgt, int off)
 template <bool COMPAT>
 HD void phase_inter_compute(InterWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane, bool coded)
 {
-    const int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    int mbx, mby;
+    mb_xy(g, a, mbx, mby);
     // warp-wide union of the NEED bits
     int wn;
     {

@@ -135,7 +135,8 @@ template <class Exec>
 HD void seq_deblock_mb(Exec& ex, MbWork& w, const PicDesc& pd, const Geometry& g, int a)
 {
     h264r_mb_hdr h = load_hdr(pd, a);
-    int mbx = a % g.w_mbs, mby = a / g.w_mbs;
+    int mbx, mby;
+    mb_xy(g, a, mbx, mby);
     h264r_mb_hdr hl = mbx > 0 ? load_hdr(pd, a - 1) : h;
     h264r_mb_hdr ht = mby > 0 ? load_hdr(pd, a - g.w_mbs) : h;
     ex([&](int lane) {

@@ -25,7 +25,8 @@ class H264RError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(build.LIB, "libh264r.so")
+    # H264R_LIB: development switch to compare builds of the same library (tuning runs); the product is lib/libh264r.so
+    return os.environ.get("H264R_LIB") or os.path.join(build.LIB, "libh264r.so")
 
 
 def load_library():

@@ -245,7 +245,7 @@ def main():
             for i, p in enumerate(gops[g % U]):
                 mask, blocks = packed_src[g % U][i]
                 pb = eng.picture_buf(max(1, blocks.shape[0]))
-                pb.fill(p["hdr"], p["mv"], mask, blocks)
+                pb.fill(p["hdr"], p["mv"], mask, blocks, mv_partition=True)
                 if g < U:
                     coded_blocks += pb.n_blocks
                 frames.append((pb, None, None, None))
@@ -274,12 +274,12 @@ def main():
             pps.append(pp2)
     h2d = 0
     # bytes of one picture-buffer transfer: descriptor + headers + vectors + masks (fixed) + the blocks present
-    upload_fixed = (pinned[0][0][0].c.blocks - pinned[0][0][0].c.base) if packed else 0
+    upload_fixed = (pinned[0][0][0].c.mv - pinned[0][0][0].c.base) if packed else 0
     for g in range(G):
         for i in range(F):
             hb, mb, cb, kb = pinned[g if packed else g % U][i]
             if packed:
-                h2d += upload_fixed + hb.n_blocks * 32
+                h2d += upload_fixed + max(0, hb.n_mvs) * 4 + hb.n_blocks * 32
             else:
                 h2d += hb.nbytes + cb.nbytes + (mb.nbytes if mb else 0)
     all_ids = list(range(G * F))
@@ -297,7 +297,7 @@ def main():
                 hb, mb, cb, kb = pinned[g if packed else g % U][i]
                 rc = L.h264r_frame_begin(ctx, fid, pps[fid])
                 if packed:
-                    rc |= L.h264r_submit_picture(ctx, fid, hb.c, hb.n_blocks)
+                    rc |= L.h264r_submit_picture(ctx, fid, hb.c, hb.n_blocks, hb.n_mvs)
                 else:
                     rc |= L.h264r_submit_mbs(ctx, fid, 0, N_MBS, hb.ptr, mb.ptr if mb else None, cb.ptr)
                     rc |= L.h264r_frame_end(ctx, fid)

@@ -192,7 +192,7 @@ int h264r_submit_mbs_packed(h264r_ctx* ctx, int frame_id, int first_mb, int n_mb
  * h264r_sync() (or a read-back of the picture) returns, and may then be refilled.  max_blocks = 0 sizes for the worst case (24 per MB). */
 typedef struct h264r_picture_buf {
     h264r_mb_hdr* hdr;        /* [n_mbs]                    */
-    int16_t*      mv;         /* [n_mbs * H264R_MV_PER_MB]  */
+    int16_t*      mv;         /* [n_mbs * H264R_MV_PER_MB] (room for either vector layout) */
     uint32_t*     blk_mask;   /* [n_mbs]                    */
     int16_t*      blocks;     /* [max_blocks * 16]          */
     size_t        max_blocks;
@@ -202,7 +202,13 @@ typedef struct h264r_picture_buf {
 } h264r_picture_buf;
 int  h264r_picture_buf_alloc(h264r_ctx* ctx, size_t max_blocks, h264r_picture_buf* out);
 void h264r_picture_buf_free(h264r_ctx* ctx, h264r_picture_buf* buf);
-int  h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* buf, size_t n_blocks);
+/* n_mvs < 0: buf->mv holds the per-4x4 layout described above (16 vectors per macroblock).
+ * n_mvs >= 0: buf->mv holds n_mvs vectors in PARTITION order -- per macroblock, in macroblock order, one vector per
+ * partition as the bitstream carries them (P_L0_16x16 and P_Skip: 1; 16x8, 8x16: 2; P_8x8: per quadrant 0..3 its
+ * sub-macroblock partitions, 8x8: 1, 8x4 / 4x8: 2, 4x4: 4, in raster order; intra: none; mvd loops of
+ * macroblock::Parse, h264/macroblock.cpp:360-398).  The engine derives each macroblock's first vector from
+ * mb_class / sub_mb_type on the device. */
+int  h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* buf, size_t n_blocks, long n_mvs);
 
 /* Marks the picture complete and queues its reconstruction.  Asynchronous; work is issued to the
  * GPU at the next h264r_flush().  Replaces: residual::Decode + macroblock::Calc for every MB of the

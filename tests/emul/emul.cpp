@@ -26,6 +26,7 @@ void fill_desc(PicDesc& pd, const h264r_pic_params* pp, const h264r_mb_hdr* hdr,
     memset(&pd, 0, sizeof(pd));
     pd.hdr = hdr; pd.mv = mv; pd.coeff = coeff; pd.y = y; pd.u = u; pd.v = v;
     pd.blk_mask = nullptr; pd.blk_off = nullptr;        // set by use_dense() / use_packed()
+    pd.mv_off = nullptr;
     for (int i = 0; i < H264R_MAX_REFS; i++) {
         pd.ref_y[i] = ref_y ? ref_y[i] : nullptr;
         pd.ref_u[i] = ref_u ? ref_u[i] : nullptr;
@@ -68,6 +69,26 @@ struct CoeffStore {
         }
         blocks.resize(blocks.size() + 16);       // keeps data() non-null for all-zero pictures
         pd.coeff = blocks.data(); pd.blk_mask = mask.data(); pd.blk_off = off.data();
+    }
+};
+// motion vectors in partition order, as h264r_submit_picture(..., n_mvs >= 0) delivers them
+struct MvStore {
+    std::vector<uint32_t> off;
+    std::vector<int16_t> mvs;
+    void use_packed(PicDesc& pd, int n_mbs, const h264r_mb_hdr* hdr, const int16_t* dense)
+    {
+        off.resize(n_mbs); mvs.clear();
+        for (int a = 0; a < n_mbs; a++) {
+            off[a] = (uint32_t)(mvs.size() / 2);
+            const int n = mv_count(hdr[a].mb_class, hdr[a].sub_mb_type);
+            for (int k = 0; k < n; k++) {
+                int blk = 0;        // first 4x4 block (raster) covered by partition k
+                while (mv_part_index(hdr[a].mb_class, hdr[a].sub_mb_type, blk) != k) blk++;
+                mvs.push_back(dense[(size_t)a * 32 + blk * 2]); mvs.push_back(dense[(size_t)a * 32 + blk * 2 + 1]);
+            }
+        }
+        mvs.resize(mvs.size() + 2);
+        pd.mv = mvs.data(); pd.mv_off = off.data();
     }
 };
 }  // namespace
@@ -146,6 +167,8 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
     fill_desc(pd, pp, hdr, mv, coeff, cur.y(), cur.u(), cur.v(), ry, ru, rv, exc_map);
     CoeffStore cs;
     if (flags & 0x40000000u) cs.use_packed(pd, w_mbs * h_mbs, coeff); else cs.use_dense(pd, w_mbs * h_mbs);      // test switch: bit 30
+    MvStore ms;
+    if ((flags & 0x40000000u) && mv) ms.use_packed(pd, w_mbs * h_mbs, hdr, mv);
     HostExec ex;
     WarpWork ww;
     MbWork& w = ww.mb;

@@ -25,6 +25,7 @@ struct Pending {
     int wave;
     int layout;             // 0 = nothing submitted yet, 1 = dense (h264r_submit_mbs), 2 = packed (h264r_submit_mbs_packed)
     size_t n_blocks;        // packed: coefficient blocks stored so far
+    bool mv_partition;      // vectors in partition order (h264r_submit_picture with n_mvs >= 0)
     uint64_t seq;           // order of frame_end calls (= order of the uploads on the copy stream)
 };
 
@@ -57,9 +58,9 @@ struct h264r_ctx {
     uint32_t* d_exc_counter = nullptr;
     // syntax arena: per slot hdr | mv | coeff
     uint8_t* d_syntax = nullptr;
-    // arena slot = what one upload carries, in this order: descriptor | hdr | mv | blk_mask | coefficient blocks;
-    // then blk_off (written by k_blk_scan, never uploaded)
-    size_t slot_bytes = 0, off_hdr = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_coeff = 0;
+    // arena slot = what the uploads carry, in this order: descriptor | hdr | blk_mask | mv | coefficient blocks;
+    // then blk_off and mv_off (written by k_blk_scan, never uploaded)
+    size_t slot_bytes = 0, off_hdr = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_mvoff = 0, off_coeff = 0;
     // per-flush control block (descriptors + picture lists), pinned host mirror + device copy
     uint8_t* h_ctrl = nullptr;
     size_t ctrl_bytes = 0;
@@ -119,6 +120,7 @@ void fill_desc(h264r_ctx* c, const Pending& p, PicDesc& pd)
         pd.blk_mask = reinterpret_cast<const uint32_t*>(s + c->off_mask);
         pd.blk_off = reinterpret_cast<const uint32_t*>(s + c->off_boff);
     } else { pd.blk_mask = c->d_dense_mask; pd.blk_off = c->d_dense_off; }
+    pd.mv_off = p.mv_partition ? reinterpret_cast<const uint32_t*>(s + c->off_mvoff) : nullptr;
     pd.y = c->frame_y(p.frame_id); pd.u = c->frame_u(p.frame_id); pd.v = c->frame_v(p.frame_id);
     for (int i = 0; i < H264R_MAX_REFS; i++) {
         int r = i < p.pp.num_ref_idx_l0 ? p.pp.ref_list0[i] : -1;
@@ -178,11 +180,12 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     c->c_bytes = (size_t)c->g.pitch_c * (h_mbs * 8 + 2 * PAD_YC);
     c->frame_bytes = align_up(c->y_bytes + 2 * c->c_bytes, 256);
     c->off_hdr = align_up(sizeof(PicDesc), 256);
-    c->off_mv = c->off_hdr + align_up((size_t)c->n_mbs * sizeof(h264r_mb_hdr), 256);
-    c->off_mask = c->off_mv + align_up((size_t)c->n_mbs * H264R_MV_PER_MB * 2, 256);
-    c->off_coeff = c->off_mask + align_up((size_t)c->n_mbs * 4, 256);
+    c->off_mask = c->off_hdr + align_up((size_t)c->n_mbs * sizeof(h264r_mb_hdr), 256);
+    c->off_mv = c->off_mask + align_up((size_t)c->n_mbs * 4, 256);
+    c->off_coeff = c->off_mv + align_up((size_t)c->n_mbs * H264R_MV_PER_MB * 2, 256);
     c->off_boff = c->off_coeff + align_up((size_t)c->n_mbs * H264R_COEFF_PER_MB * 2, 256);
-    c->slot_bytes = c->off_boff + align_up((size_t)c->n_mbs * 4, 256);
+    c->off_mvoff = c->off_boff + align_up((size_t)c->n_mbs * 4, 256);
+    c->slot_bytes = c->off_mvoff + align_up((size_t)c->n_mbs * 4, 256);
     c->ctrl_bytes = align_up((size_t)max_pending * sizeof(PicDesc), 256);      // descriptor table, one entry per arena slot
     auto cleanup = [&](int code) { h264r_destroy(c); return code; };
 #define CUC(call)                                                                                             \
@@ -382,9 +385,10 @@ void h264r_picture_buf_free(h264r_ctx* ctx, h264r_picture_buf* buf)
     memset(buf, 0, sizeof(*buf));
 }
 
-int h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* buf, size_t n_blocks)
+int h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* buf, size_t n_blocks, long n_mvs)
 {
-    if (!ctx || !buf || !buf->base || n_blocks > buf->max_blocks) return fail(ctx, H264R_E_INVAL, "submit_picture: bad argument");
+    if (!ctx || !buf || !buf->base || n_blocks > buf->max_blocks || n_mvs > (long)16 * (ctx ? ctx->n_mbs : 0))
+        return fail(ctx, H264R_E_INVAL, "submit_picture: bad argument");
     Pending* p = find_pending(ctx, frame_id);
     if (!p || p->ended) return fail(ctx, H264R_E_STATE, "submit_picture: no open picture with this frame id");
     if (p->layout || p->n_submitted) return fail(ctx, H264R_E_STATE, "submit_picture: the picture already has macroblocks");
@@ -412,9 +416,19 @@ int h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* 
     p->layout = 2;
     p->n_blocks = n_blocks;
     p->n_submitted = ctx->n_mbs;
-    // descriptor in front, then ONE transfer for descriptor + headers + vectors + masks + the blocks present
+    p->mv_partition = n_mvs >= 0;
+    // descriptor in front; one transfer for descriptor + headers + masks + the vectors present, one for the blocks present
     fill_desc(ctx, *p, *reinterpret_cast<PicDesc*>(buf->base));
-    CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot), buf->base, ctx->off_coeff + n_blocks * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+    const bool is_p = p->pp.slice_type == H264R_SLICE_P;
+    const size_t mv_bytes = !is_p ? 0 : (n_mvs >= 0 ? (size_t)n_mvs * 4 : (size_t)ctx->n_mbs * H264R_MV_PER_MB * 2);
+    if (mv_bytes == (size_t)ctx->n_mbs * H264R_MV_PER_MB * 2)
+        CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot), buf->base, ctx->off_coeff + n_blocks * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+    else {
+        CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot), buf->base, ctx->off_mv + mv_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (n_blocks)
+            CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot) + ctx->off_coeff, static_cast<const uint8_t*>(buf->base) + ctx->off_coeff, n_blocks * 32,
+                               cudaMemcpyHostToDevice, ctx->copy_stream));
+    }
     CU(cudaEventRecord(ctx->ev_copied[p->slot], ctx->copy_stream));
     reinterpret_cast<PicDesc*>(ctx->h_ctrl)[p->slot].deblock_on = reinterpret_cast<const PicDesc*>(buf->base)->deblock_on;
     p->seq = ++ctx->end_seq;

@@ -57,7 +57,8 @@ HD void mb_xy(const Geometry& g, int a, int& mbx, int& mby)
 // Everything a kernel needs to know about one picture of a wave (lives in device memory).
 struct PicDesc {
     const h264r_mb_hdr* hdr;
-    const int16_t* mv;
+    const int16_t* mv;         // motion vectors (x, y): per 4x4 block (16 per macroblock) or per partition (see mv_off)
+    const uint32_t* mv_off;    // null: per-4x4 layout; else per macroblock the index of its first vector, partition order
     const int16_t* coeff;      // coefficient blocks of the picture, 16 levels each, packed (see BlkRef)
     const uint32_t* blk_mask;  // per macroblock: bit b set = block b is stored
     const uint32_t* blk_off;   // per macroblock: index of its first stored block
@@ -113,6 +114,45 @@ HD const int16_t* blk_ptr(const PicDesc& pd, const BlkRef& r, int b)       // nu
     if (!((r.mask >> b) & 1u)) return nullptr;
     return pd.coeff + ((size_t)r.off + popc32(r.mask & ((1u << b) - 1u))) * 16;
 }
+
+// Motion-vector storage.  Per-4x4 layout (h264r_submit_mbs): vector of block b (raster) of macroblock a is entry
+// 16 a + b.  Partition layout (h264r_submit_picture with n_mvs >= 0): the vectors of a macroblock in the order the
+// bitstream carries them -- one per partition (P_L0_16x16: 1, 16x8 / 8x16: 2) or, for P_8x8, per sub-macroblock
+// partition of quadrants 0..3 (8x8: 1, 8x4 / 4x8: 2, 4x4: 4) -- starting at entry mv_off[a]
+// (reference: mvd loops of macroblock::Parse, h264/macroblock.cpp:360-398).
+HD int mv_sub_count(int s) { return (0x4221 >> (4 * s)) & 7; }           // H264R_SUB_8x8, 8x4, 4x8, 4x4
+HD int mv_count(int mb_class, int sub_mb_type)
+{
+    if (mb_class < H264R_MB_P16x16) return 0;
+    if (mb_class == H264R_MB_P16x16) return 1;
+    if (mb_class != H264R_MB_P8x8) return 2;
+    return mv_sub_count(sub_mb_type & 3) + mv_sub_count((sub_mb_type >> 2) & 3) + mv_sub_count((sub_mb_type >> 4) & 3) + mv_sub_count((sub_mb_type >> 6) & 3);
+}
+// index (within the macroblock's vectors) of the partition that covers 4x4 block blk (raster)
+HD int mv_part_index(int mb_class, int sub_mb_type, int blk)
+{
+    const int bx = blk & 3, by = blk >> 2;
+    if (mb_class == H264R_MB_P16x16) return 0;
+    if (mb_class == H264R_MB_P16x8) return by >> 1;
+    if (mb_class == H264R_MB_P8x16) return bx >> 1;
+    const int q = (by >> 1) * 2 + (bx >> 1);
+    int base = 0;
+    if (q > 0) base += mv_sub_count(sub_mb_type & 3);
+    if (q > 1) base += mv_sub_count((sub_mb_type >> 2) & 3);
+    if (q > 2) base += mv_sub_count((sub_mb_type >> 4) & 3);
+    const int s = (sub_mb_type >> (2 * q)) & 3;
+    const int within = s == H264R_SUB_8x8 ? 0 : (s == H264R_SUB_8x4 ? (by & 1) : (s == H264R_SUB_4x8 ? (bx & 1) : (by & 1) * 2 + (bx & 1)));
+    return base + within;
+}
+// vector of 4x4 block blk of macroblock a, packed (x | y << 16)
+HD uint32_t load_mv(const PicDesc& pd, const h264r_mb_hdr& h, int a, int blk)
+{
+    const uint32_t* mv32 = reinterpret_cast<const uint32_t*>(pd.mv);
+    if (pd.mv_off) return H264R_LDG(mv32 + H264R_LDG(pd.mv_off + a) + mv_part_index(h.mb_class, h.sub_mb_type, blk));
+    return H264R_LDG(mv32 + (size_t)a * 16 + blk);
+}
+HD int mv_x(uint32_t v) { return (int)(int16_t)(v & 0xffff); }
+HD int mv_y(uint32_t v) { return (int)v >> 16; }
 
 HD int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 HD int clip1(int v) { return clip3(0, 255, v); }
@@ -368,8 +408,8 @@ HD void phase_inter_luma(MbWork& w, const PicDesc& pd, const Geometry& g, const 
     int ras = lane >> 1, bx = ras & 3, by = ras >> 2, q = (by >> 1) * 2 + (bx >> 1);
     int mbx, mby;
     mb_xy(g, a, mbx, mby);
-    const int16_t* mvp = pd.mv + (size_t)a * H264R_MV_PER_MB + ras * 2;
-    int mvx = H264R_LDG(mvp), mvy = H264R_LDG(mvp + 1);
+    const uint32_t mvw = load_mv(pd, h, a, ras);
+    int mvx = mv_x(mvw), mvy = mv_y(mvw);
     int ri = h.u.ref_idx[q] & 15;
     RefPlane R{pd.ref_y[ri], g.pitch_y, g.w_mbs * 16, g.h_mbs * 16};
     int x0 = mbx * 16 + bx * 4, y0 = mby * 16 + by * 4;
@@ -413,8 +453,8 @@ HD void phase_inter_chroma(MbWork& w, const PicDesc& pd, const Geometry& g, cons
         }
         return;
     }
-    const int16_t* mvp = pd.mv + (size_t)a * H264R_MV_PER_MB + l * 2;
-    int mvx = H264R_LDG(mvp), mvy = H264R_LDG(mvp + 1);
+    const uint32_t mvw = load_mv(pd, h, a, l);
+    int mvx = mv_x(mvw), mvy = mv_y(mvw);
     int ri = h.u.ref_idx[q] & 15;
     const uint8_t* ref = plane ? pd.ref_v[ri] : pd.ref_u[ri];
     int xf = mvx & 7, yf = mvy & 7;
@@ -905,10 +945,9 @@ HD void phase_deblock_bs(MbWork& w, const PicDesc& pd, const Geometry& g, const 
         else {
             int qq = (rasq >> 3) * 2 + ((rasq & 3) >> 1), qp_ = (rasp >> 3) * 2 + ((rasp & 3) >> 1);
             int refq = pd.ref_id[h.u.ref_idx[qq] & 15], refp = pd.ref_id[hn.u.ref_idx[qp_] & 15];
-            const int16_t* mq = pd.mv + (size_t)a * H264R_MV_PER_MB + rasq * 2;
-            const int16_t* mp = pd.mv + (size_t)an * H264R_MV_PER_MB + rasp * 2;
+            const uint32_t mq = load_mv(pd, h, a, rasq), mp = load_mv(pd, hn, an, rasp);
             if (refq != refp) bs = 1;
-            else if (iabs(H264R_LDG(mq) - H264R_LDG(mp)) >= 4 || iabs(H264R_LDG(mq + 1) - H264R_LDG(mp + 1)) >= 4) bs = 1;
+            else if (iabs(mv_x(mq) - mv_x(mp)) >= 4 || iabs(mv_y(mq) - mv_y(mp)) >= 4) bs = 1;
         }
     }
     w.bs[lane] = (uint8_t)bs;

@@ -201,30 +201,47 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_deblock_rows(const DescTable
 }
 
 // ------------------------------------------------------------------------------------------------
-// Packed coefficient storage: blk_off[a] = number of stored blocks before macroblock a = exclusive scan of
-// popcount(blk_mask).  One CTA per picture submitted through h264r_submit_mbs_packed.
+// Packed storage: blk_off[a] = number of stored coefficient blocks before macroblock a = exclusive scan of
+// popcount(blk_mask); mv_off[a] (partition-order vectors only) = exclusive scan of the vector counts that follow
+// from mb_class / sub_mb_type.  One CTA per picture that arrived packed; both scans share the passes
+// (block count in the low, vector count in the high half of a 64-bit word).
 // ------------------------------------------------------------------------------------------------
-struct ScanJob { const uint32_t* mask; uint32_t* off; };
 __global__ void __launch_bounds__(1024) k_blk_scan(const DescTable descs, const __grid_constant__ PicList list, int n_mbs)
 {
-    const PicDesc& pdj = descs[list.slot[blockIdx.x]];
-    const ScanJob job{pdj.blk_mask, const_cast<uint32_t*>(pdj.blk_off)};
+    const PicDesc& pd = descs[list.slot[blockIdx.x]];
+    const uint32_t* mask = pd.blk_mask;
+    uint32_t* off = const_cast<uint32_t*>(pd.blk_off);
+    uint32_t* mvoff = const_cast<uint32_t*>(pd.mv_off);
     const int per = (n_mbs + 1023) >> 10, first = threadIdx.x * per, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t sum = 0;
-    for (int k = 0; k < per; k++) if (first + k < n_mbs) sum += __popc(__ldg(job.mask + first + k) & 0xFFFFFFu);
-    uint32_t incl = sum;
-    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    __shared__ uint32_t wsum[32];
+    auto count = [&](int a) -> unsigned long long {
+        unsigned long long c = (unsigned long long)__popc(__ldg(mask + a) & 0xFFFFFFu);
+        if (mvoff) {
+            const uint32_t* hw = reinterpret_cast<const uint32_t*>(pd.hdr + a);
+            uint32_t w0 = __ldg(hw), w1 = __ldg(hw + 1);            // mb_class = byte 0, sub_mb_type = byte 7
+            c += (unsigned long long)mv_count((int)(w0 & 255u), (int)(w1 >> 24)) << 32;
+        }
+        return c;
+    };
+    unsigned long long sum = 0;
+    for (int k = 0; k < per; k++) if (first + k < n_mbs) sum += count(first + k);
+    unsigned long long incl = sum;
+    for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    __shared__ unsigned long long wsum[32];
     if (lane == 31) wsum[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        uint32_t v = wsum[lane], iv = v;
-        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
+        unsigned long long v = wsum[lane], iv = v;
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
         wsum[lane] = iv - v;
     }
     __syncthreads();
-    uint32_t run = wsum[warp] + incl - sum;
-    for (int k = 0; k < per; k++) if (first + k < n_mbs) { job.off[first + k] = run; run += __popc(__ldg(job.mask + first + k) & 0xFFFFFFu); }
+    unsigned long long run = wsum[warp] + incl - sum;
+    for (int k = 0; k < per; k++)
+        if (first + k < n_mbs) {
+            off[first + k] = (uint32_t)run;
+            if (mvoff) mvoff[first + k] = (uint32_t)(run >> 32);
+            run += count(first + k);
+        }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -212,15 +212,16 @@ HD void load_mvs(const PicDesc& pd, int a, uint32_t mv[16])
         mv[4 * i] = v.x; mv[4 * i + 1] = v.y; mv[4 * i + 2] = v.z; mv[4 * i + 3] = v.w;
     }
 }
-HD int mv_x(uint32_t v) { return (int)(int16_t)(v & 0xffff); }
-HD int mv_y(uint32_t v) { return (int)v >> 16; }
-HD uint32_t load_mv1(const PicDesc& pd, int a, int blk)
-{
-    return H264R_LDG(reinterpret_cast<const uint32_t*>(pd.mv + (size_t)a * H264R_MV_PER_MB) + blk);
-}
 // 0: all sixteen vectors (and reference indices) equal; 1: every 8x8 quadrant uniform; 2: anything else.
 // Under COMPAT a P_8x8 macroblock with a 4x4 sub-partition always takes shape 2: the reference's source-row
 // offset of sub-blocks 2 and 3 (D8, h264/macroblock.cpp:786-789) makes equal vectors read different rows.
+// partition layout of the vectors: the shape follows from the macroblock type alone
+HD int inter_shape_by_type(const h264r_mb_hdr& h)
+{
+    if (h.mb_class == H264R_MB_P16x16) return 0;
+    if (h.mb_class != H264R_MB_P8x8) return 1;
+    return h.sub_mb_type == 0 ? 1 : 2;
+}
 template <bool COMPAT>
 HD int inter_shape(const h264r_mb_hdr& h, const uint32_t mv[16])
 {
@@ -311,31 +312,35 @@ HD void stage_window(uint32_t* dst, const uint8_t* ref, int gpitch, int sx, int 
 template <bool COMPAT>
 HD void phase_inter_stage(InterWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane)
 {
-    uint32_t mv[16];
-    load_mvs(pd, a, mv);
-    const int shape = inter_shape<COMPAT>(h, mv);
+    int shape;
+    if (pd.mv_off) shape = inter_shape_by_type(h);
+    else {
+        uint32_t mv[16];
+        load_mvs(pd, a, mv);
+        shape = inter_shape<COMPAT>(h, mv);
+    }
     if (lane == 0) { w.shape = shape; w.excursions = 0; }
     int mbx, mby;
     mb_xy(g, a, mbx, mby);
     const int W = g.w_mbs * 16, H = g.h_mbs * 16;
     {
-        uint32_t v = load_mv1(pd, a, lane >> 1);
+        uint32_t v = load_mv(pd, h, a, lane >> 1);
         w.need[lane] = (uint8_t)mc_need(mv_x(v) & 3, mv_y(v) & 3);
     }
     if (shape == 0) {
-        const uint32_t v = mv[0];
+        const uint32_t v = load_mv(pd, h, a, 0);
         const uint8_t* ref = pd.ref_y[h.u.ref_idx[0] & 15];
         int xb = clip3(-19, W + 2, mbx * 16 + (mv_x(v) >> 2)), yb = clip3(-19, H + 3, mby * 16 + (mv_y(v) >> 2));
         stage_window<22, 6, 32>(w.win, ref, g.pitch_y, xb - 2, yb - 3, lane);
     } else if (shape == 1) {
         const int q = lane >> 3, b0 = (q >> 1) * 8 + (q & 1) * 2;
-        const uint32_t v = load_mv1(pd, a, b0);
+        const uint32_t v = load_mv(pd, h, a, b0);
         const uint8_t* ref = pd.ref_y[h.u.ref_idx[q] & 15];
         int xb = clip3(-11, W + 2, mbx * 16 + (q & 1) * 8 + (mv_x(v) >> 2)), yb = clip3(-11, H + 3, mby * 16 + (q >> 1) * 8 + (mv_y(v) >> 2));
         stage_window<14, 4, 8>(w.win + q * 56, ref, g.pitch_y, xb - 2, yb - 3, lane & 7);
     } else {
         const int b = lane >> 1, bx = b & 3, by = b >> 2, q = (by >> 1) * 2 + (bx >> 1);
-        const uint32_t v = load_mv1(pd, a, b);
+        const uint32_t v = load_mv(pd, h, a, b);
         const uint8_t* ref = pd.ref_y[h.u.ref_idx[q] & 15];
         int ys = mby * 16 + by * 4;
         // reference's source-row offset for 4x4 sub-partitions 2 and 3 (D8, h264/macroblock.cpp:786-789)
@@ -500,7 +505,7 @@ HD void phase_inter_compute(InterWork& w, const PicDesc& pd, const Geometry& g, 
     if (shape == 0) { wp = w.win + (by * 4 + half * 2) * 6 + bx; pitch = 6; }
     else if (shape == 1) { wp = w.win + q * 56 + ((by & 1) * 4 + half * 2) * 4 + (bx & 1); pitch = 4; }
     else { wp = w.win + b * 30 + half * 2 * 3; pitch = 3; }
-    const uint32_t v = load_mv1(pd, a, b);
+    const uint32_t v = load_mv(pd, h, a, b);
     const McSel m = mc_select(mv_x(v) & 3, mv_y(v) & 3);
     uint32_t pred[2];
     if (wn == 0) mc_patch<COMPAT, 0>(wp, pitch, m, pred);
@@ -536,7 +541,7 @@ HD void phase_inter_compute(InterWork& w, const PicDesc& pd, const Geometry& g, 
                 int cx = cx0 + k, blk = (cy >> 1) * 4 + (cx >> 1), qq = (cy >> 2) * 2 + (cx >> 2);
                 int rc = h.u.ref_idx[qq] & 15;
                 const uint8_t* ref = plane ? pd.ref_v[rc] : pd.ref_u[rc];
-                uint32_t v2 = load_mv1(pd, a, blk);
+                uint32_t v2 = load_mv(pd, h, a, blk);
                 int mvx = mv_x(v2), mvy = mv_y(v2);
                 int xf = mvx & 7, yf = mvy & 7;
                 int xi = mbx * 8 + cx + (mvx >> 3), yi = mby * 8 + cy + (mvy >> 3);

@@ -56,7 +56,7 @@ def load_library():
     L.h264r_picture_buf_alloc.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(PictureBufStruct)]
     L.h264r_picture_buf_free.argtypes = [vp, ctypes.POINTER(PictureBufStruct)]
     L.h264r_picture_buf_free.restype = None
-    L.h264r_submit_picture.argtypes = [vp, ci, ctypes.POINTER(PictureBufStruct), ctypes.c_size_t]
+    L.h264r_submit_picture.argtypes = [vp, ci, ctypes.POINTER(PictureBufStruct), ctypes.c_size_t, ctypes.c_long]
     L.h264r_frame_end.argtypes = [vp, ci]
     L.h264r_flush.argtypes = [vp]
     L.h264r_sync.argtypes = [vp]
@@ -136,11 +136,20 @@ class PictureBuf:
         self.blk_mask = view(self.c.blk_mask, np.uint32, n)
         self.blocks = view(self.c.blocks, np.int16, int(self.c.max_blocks) * 16).reshape(-1, 16)
         self.n_blocks = 0
+        self.n_mvs = -1
 
-    def fill(self, hdr, mv, blk_mask, blocks):
+    def fill(self, hdr, mv, blk_mask, blocks, mv_partition=False):
+        """mv: per-4x4 vectors (n, 32); mv_partition: store them in partition order (pack.pack_mvs_partition)"""
+        from . import pack
         self.hdr[:] = np.ascontiguousarray(hdr).view(abi.MB_HDR_DTYPE).reshape(-1)
+        self.n_mvs = -1
         if mv is not None:
-            self.mv[:] = mv
+            if mv_partition:
+                pm = pack.pack_mvs_partition(hdr, mv)
+                self.n_mvs = int(pm.shape[0])
+                self.mv.reshape(-1, 2)[:self.n_mvs] = pm
+            else:
+                self.mv[:] = mv
         self.blk_mask[:] = blk_mask
         self.n_blocks = int(blocks.shape[0])
         self.blocks[:self.n_blocks] = blocks
@@ -222,7 +231,7 @@ class Engine:
     def submit_picture_buf(self, frame_id, pp, buf):
         """whole picture from a PictureBuf: one DMA, queued at once"""
         self.frame_begin(frame_id, pp)
-        self._check(self.L.h264r_submit_picture(self.ctx, frame_id, ctypes.byref(buf.c), buf.n_blocks))
+        self._check(self.L.h264r_submit_picture(self.ctx, frame_id, ctypes.byref(buf.c), buf.n_blocks, buf.n_mvs))
 
     def flush(self):
         self._check(self.L.h264r_flush(self.ctx))

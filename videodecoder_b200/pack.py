@@ -129,3 +129,45 @@ def unpack_blocks(mask, blocks):
     c = np.zeros((n, 24, 16), dtype=np.int16)
     c[present] = blocks.reshape(-1, 16)
     return c.reshape(n, 384)
+
+
+_SUB_COUNT = np.array([1, 2, 2, 4])
+# first 4x4 block (raster, relative to the quadrant's first block) of each sub-macroblock partition
+_SUB_FIRST = {0: [0], 1: [0, 4], 2: [0, 1], 3: [0, 1, 4, 5]}
+
+
+def pack_mvs_partition(hdr, mv):
+    """Per-4x4 vectors (n, 32) int16 -> partition order, as h264r_submit_picture(..., n_mvs) takes them:
+    one vector per partition / sub-macroblock partition in bitstream order (mvd loops of macroblock::Parse,
+    h264/macroblock.cpp:360-398).  Returns (n_mvs, 2) int16."""
+    hdr = np.ascontiguousarray(hdr).view(abi.MB_HDR_DTYPE).reshape(-1)
+    mv = np.ascontiguousarray(mv, dtype=np.int16).reshape(-1, 16, 2)
+    cls = hdr["mb_class"]
+    out = []
+    # vectorised per class; P_8x8 macroblocks individually ordered afterwards
+    order = np.zeros(hdr.shape[0], dtype=np.int64)
+    counts = np.zeros(hdr.shape[0], dtype=np.int64)
+    counts[cls == abi.MB_P16x16] = 1
+    counts[(cls == abi.MB_P16x8) | (cls == abi.MB_P8x16)] = 2
+    p8 = np.flatnonzero(cls == abi.MB_P8x8)
+    st = hdr["sub_mb_type"]
+    for a in p8:
+        counts[a] = sum(_SUB_COUNT[(int(st[a]) >> (2 * q)) & 3] for q in range(4))
+    off = np.concatenate(([0], np.cumsum(counts)))
+    res = np.zeros((int(off[-1]), 2), dtype=np.int16)
+    m = cls == abi.MB_P16x16
+    res[off[:-1][m]] = mv[m, 0]
+    m = cls == abi.MB_P16x8
+    res[off[:-1][m]] = mv[m, 0]
+    res[off[:-1][m] + 1] = mv[m, 8]
+    m = cls == abi.MB_P8x16
+    res[off[:-1][m]] = mv[m, 0]
+    res[off[:-1][m] + 1] = mv[m, 2]
+    for a in p8:
+        k = int(off[a])
+        for q in range(4):
+            b0 = (q >> 1) * 8 + (q & 1) * 2
+            for rel in _SUB_FIRST[(int(st[a]) >> (2 * q)) & 3]:
+                res[k] = mv[a, b0 + rel]
+                k += 1
+    return res

@@ -230,7 +230,8 @@ def main():
             it = workload.sanitize(lambda n: engine.Engine(W_MBS, H_MBS, max_frames=n, flags=flags, device=local), W_MBS, H_MBS, g)
     log("rank %d: workload ready in %.1f s" % (rank, time.time() - t0))
 
-    eng = engine.Engine(W_MBS, H_MBS, max_frames=G * F, flags=flags, device=local)
+    # digests of every frame are part of the job (GOP-sharded decoding compares them across ranks): K5 runs with each wave
+    eng = engine.Engine(W_MBS, H_MBS, max_frames=G * F, flags=flags | abi.DIGESTS, device=local)
     # pinned host copies of the unique GOPs (what a host parser would hand over)
     packed = args.layout == "packed"
     coded_blocks = 0
@@ -332,8 +333,8 @@ def main():
     eng.set_profiling(True)
     barrier()
     kern_ms = 0.0
-    fam_ms = np.zeros(4)
-    fam_n = np.zeros(4, dtype=np.int64)
+    fam_ms = np.zeros(5)
+    fam_n = np.zeros(5, dtype=np.int64)
     for _ in range(args.steps):
         submit_all()
         eng.wait_uploads()              # inputs are resident in HBM before the timed flush
@@ -378,7 +379,7 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         # dominant kernel family and its roofline (DESIGN.md "Measurement")
-        fam = int(np.argmax(fam_ms))
+        fam = int(np.argmax(fam_ms[:3]))
         names = ["k_inter (K1+K3: dequant/IDCT + motion compensation + reconstruction)",
                  "k_intra (K1+K2: dequant/IDCT + intra wavefront)", "k_deblock (K4)"]
         inter_mbs = sum(inter_mbs_per_pic[(g % U) * F + i] for g in range(G) for i in range(F))
@@ -414,7 +415,7 @@ def main():
             # kernels launched inside the timed regions: the resident steps (one flush each) + the e2e steps (the same
             # kernels, queued round by round, + one digest launch)
             "gpu_launches": int(args.steps * (2 * flush_launches + 1)),
-            "kernel_ms_per_step": {"inter": fam_ms[0] / args.steps, "intra": fam_ms[1] / args.steps, "deblock": fam_ms[2] / args.steps, "pad": fam_ms[3] / args.steps},
+            "kernel_ms_per_step": {"inter": fam_ms[0] / args.steps, "intra": fam_ms[1] / args.steps, "deblock": fam_ms[2] / args.steps, "pad": fam_ms[3] / args.steps, "digest": fam_ms[4] / args.steps},
             "roofline": {"bound": "hbm", "kernel": names[fam], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch,
                          "avg_launch_ms": sec_per_launch * 1000.0},
@@ -422,7 +423,7 @@ def main():
         }
         # per-launch picture of the last timed flush: the first wave holds the I pictures, the others the P pictures
         prof = {}
-        for fam_id, fam_name in ((0, "inter"), (1, "intra"), (2, "deblock"), (3, "pad")):
+        for fam_id, fam_name in ((0, "inter"), (1, "intra"), (2, "deblock"), (3, "pad"), (4, "digest")):
             t = [m for m, f in launch_ms if f == fam_id]
             if t:
                 prof[fam_name] = {"n": len(t), "first_ms": t[0], "rest_avg_ms": (sum(t[1:]) / (len(t) - 1)) if len(t) > 1 else None,

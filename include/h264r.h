@@ -57,6 +57,10 @@ extern "C" {
  * intra prediction and MC, standard interpolation, 8x8 transform, Intra8x8, deblocking.
  */
 #define H264R_REF_COMPAT   0x1u
+/* H264R_DIGESTS: compute the digest of every picture as part of its reconstruction (kernel K5 queued with each wave),
+ * so that h264r_frame_digests() only reads results back.  For pipelines that check or ship digests of every frame
+ * (GOP-sharded decoding across GPUs). */
+#define H264R_DIGESTS      0x2u
 
 /* ---- macroblock classes (h264r_mb_hdr.mb_class) --------------------------------------------
  * Collapsed from the reference's MbTypeName (h264/enums.h:13-73): the Intra16x16 mode/cbp
@@ -264,11 +268,11 @@ int h264r_last_flush_stats(h264r_ctx* ctx, float* kernel_ms, int* launches);
 
 /* Measurement support.  h264r_set_profiling(1) makes h264r_flush() bracket every kernel launch with
  * CUDA events on the context's stream; h264r_last_flush_kernel_ms() then returns, per kernel family
- * (0 = inter K1+K3, 1 = intra K1+K2, 2 = deblock K4, 3 = border replication), the summed device time
+ * (0 = inter K1+K3, 1 = intra K1+K2, 2 = deblock K4, 3 = border replication, 4 = digest K5), the summed device time
  * and the number of launches of the last flush.  h264r_mark()/h264r_elapsed_ms() record and compare user events
  * (slot 0..3) on the same stream, e.g. around a submit..flush..digest sequence. */
 int h264r_set_profiling(h264r_ctx* ctx, int on);
-#define H264R_KERNEL_FAMILIES 4
+#define H264R_KERNEL_FAMILIES 5
 int h264r_last_flush_kernel_ms(h264r_ctx* ctx, float ms[H264R_KERNEL_FAMILIES], int launches[H264R_KERNEL_FAMILIES]);
 /* Per-launch device times of the last flush in issue order (needs h264r_set_profiling(1)): fills ms[] / family[]
  * with up to cap entries and returns the number written (>= 0) or a negative error code. */

@@ -27,6 +27,7 @@ void fill_desc(PicDesc& pd, const h264r_pic_params* pp, const h264r_mb_hdr* hdr,
     pd.hdr = hdr; pd.mv = mv; pd.coeff = coeff; pd.y = y; pd.u = u; pd.v = v;
     pd.blk_mask = nullptr; pd.blk_off = nullptr;        // set by use_dense() / use_packed()
     pd.mv_off = nullptr;
+    pd.residual = nullptr;
     for (int i = 0; i < H264R_MAX_REFS; i++) {
         pd.ref_y[i] = ref_y ? ref_y[i] : nullptr;
         pd.ref_u[i] = ref_u ? ref_u[i] : nullptr;
@@ -43,6 +44,9 @@ void fill_desc(PicDesc& pd, const h264r_pic_params* pp, const h264r_mb_hdr* hdr,
     pd.alpha_off = pp->slice_alpha_c0_offset_div2 * 2;
     pd.beta_off = pp->slice_beta_offset_div2 * 2;
     pd.excursion_map = exc_map;
+    static uint32_t exc_counter;
+    exc_counter = 0;
+    pd.exc_counter = &exc_counter;
 }
 // coefficient storage of a picture as the device sees it
 struct CoeffStore {
@@ -180,7 +184,17 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
     for (int a = 0; a < n; a++) {
         h264r_mb_hdr h = load_hdr(pd, a);
         if (is_intra(h.mb_class)) continue;
-        exc += compat ? seq_inter_any<true>(ex, ww, pd, g, h, a) : seq_inter_any<false>(ex, ww, pd, g, h, a);
+        if (compat) seq_inter_any<true>(ex, ww, pd, g, h, a); else seq_inter_any<false>(ex, ww, pd, g, h, a);
+    }
+    // as on the device: the flat kernels leave the residual of the intra macroblocks in the picture's scratch
+    std::vector<int16_t> scratch((size_t)n * 384);
+    if (use_fast_intra) {
+        pd.residual = scratch.data();
+        for (int a = 0; a < n; a++) {
+            h264r_mb_hdr h = load_hdr(pd, a);
+            if (!is_intra(h.mb_class)) continue;
+            if (compat) seq_residual_scratch<true>(ex, w, pd, h, a); else seq_residual_scratch<false>(ex, w, pd, h, a);
+        }
     }
     static uint16_t lut[INTRA4_LUT_SIZE];
     intra4_lut_fill(lut, 0, 1);
@@ -194,22 +208,26 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
         // as the row warps of k_intra_rows do: the left column comes from the warp's own tile when it has just done a - 1
         bool carry = use_fast_intra && prev == a - 1 && (a % w_mbs) != 0;
         if (!use_fast_intra) { if (compat) seq_intra_mb<true>(ex, w, pd, g, h, a); else seq_intra_mb<false>(ex, w, pd, g, h, a); }
-        else if (compat) seq_intra_any<true>(ex, w, lut, pd, g, h, a, carry); else seq_intra_any<false>(ex, w, lut, pd, g, h, a, carry);
-        exc += w.excursions;
+        else {
+            memcpy(w.res, pd.residual + (size_t)a * 384, 768);
+            if (compat) seq_intra_any<true>(ex, w, lut, pd, g, h, a, carry, true); else seq_intra_any<false>(ex, w, lut, pd, g, h, a, carry, true);
+        }
         prev = a;
     }
     if (!compat && pd.deblock_on)
         for (int a = 0; a < n; a++) seq_deblock_mb(ex, w, pd, g, a);
     cur.store(y, u, v);
+    exc = *pd.exc_counter;
     return exc;
 }
 
 void h264emul_digest(const uint8_t* y, const uint8_t* u, const uint8_t* v, int w, int h, uint32_t out[4])
 {
     uint32_t d[4] = {0, 0, 0, 0}, i = 0;
-    for (int k = 0; k < w * h; k++) digest_accumulate(d, y[k], i++);
-    for (int k = 0; k < w * h / 4; k++) digest_accumulate(d, u[k], i++);
-    for (int k = 0; k < w * h / 4; k++) digest_accumulate(d, v[k], i++);
+    auto word = [](const uint8_t* b) { return (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24); };
+    for (int k = 0; k < w * h / 4; k++) digest_accumulate(d, word(y + 4 * k), i++);
+    for (int k = 0; k < w * h / 16; k++) digest_accumulate(d, word(u + 4 * k), i++);
+    for (int k = 0; k < w * h / 16; k++) digest_accumulate(d, word(v + 4 * k), i++);
     memcpy(out, d, 16);
 }
 }

@@ -5,6 +5,7 @@ import numpy as np
 
 ABI_VERSION = 2
 REF_COMPAT = 0x1
+DIGESTS = 0x2      # digest of every picture as part of its reconstruction
 
 MB_I4x4, MB_I8x8, MB_I16x16 = 0, 1, 2
 MB_P16x16, MB_P16x8, MB_P8x16, MB_P8x8 = 4, 5, 6, 7

@@ -53,14 +53,17 @@ struct h264r_ctx {
     // frame pool: per slot Y, U, V
     uint8_t* d_frames = nullptr;
     size_t y_bytes = 0, c_bytes = 0, frame_bytes = 0;
-    uint32_t* d_digests = nullptr;          // staging for K5 results: max_pending * 4
+    uint32_t* d_digests = nullptr;          // K5 results, 4 words per frame id
+    std::vector<uint8_t> digest_valid;      // per frame id: the table entry belongs to the frame's current picture
+    std::vector<uint32_t> h_digests;        // read-back staging
     uint8_t* d_exc_maps = nullptr;          // max_frames * n_mbs
     uint32_t* d_exc_counter = nullptr;
     // syntax arena: per slot hdr | mv | coeff
     uint8_t* d_syntax = nullptr;
     // arena slot = what the uploads carry, in this order: descriptor | hdr | blk_mask | mv | coefficient blocks;
     // then blk_off and mv_off (written by k_blk_scan, never uploaded)
-    size_t slot_bytes = 0, off_hdr = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_mvoff = 0, off_coeff = 0;
+    // then the residual scratch of the intra macroblocks (device only)
+    size_t slot_bytes = 0, off_hdr = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_mvoff = 0, off_coeff = 0, off_res = 0;
     // per-flush control block (descriptors + picture lists), pinned host mirror + device copy
     uint8_t* h_ctrl = nullptr;
     size_t ctrl_bytes = 0;
@@ -103,6 +106,12 @@ int fail(h264r_ctx* c, int code, const std::string& msg)
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+FramePool digest_pool(const h264r_ctx* c)
+{
+    return FramePool{c->d_frames, c->frame_bytes, (size_t)PAD_Y * c->g.pitch_y + PAD_X, c->y_bytes + (size_t)PAD_YC * c->g.pitch_c + PAD_XC,
+                     c->y_bytes + c->c_bytes + (size_t)PAD_YC * c->g.pitch_c + PAD_XC};
+}
+
 Pending* find_pending(h264r_ctx* c, int frame_id)
 {
     for (auto& p : c->pending) if (p.frame_id == frame_id) return &p;
@@ -121,6 +130,8 @@ void fill_desc(h264r_ctx* c, const Pending& p, PicDesc& pd)
         pd.blk_off = reinterpret_cast<const uint32_t*>(s + c->off_boff);
     } else { pd.blk_mask = c->d_dense_mask; pd.blk_off = c->d_dense_off; }
     pd.mv_off = p.mv_partition ? reinterpret_cast<const uint32_t*>(s + c->off_mvoff) : nullptr;
+    // k_residual_pics leaves the residual of the intra macroblocks here, ahead of the wavefront
+    pd.residual = p.n_intra > 0 ? reinterpret_cast<int16_t*>(s + c->off_res) : nullptr;
     pd.y = c->frame_y(p.frame_id); pd.u = c->frame_u(p.frame_id); pd.v = c->frame_v(p.frame_id);
     for (int i = 0; i < H264R_MAX_REFS; i++) {
         int r = i < p.pp.num_ref_idx_l0 ? p.pp.ref_list0[i] : -1;
@@ -143,6 +154,7 @@ void fill_desc(h264r_ctx* c, const Pending& p, PicDesc& pd)
     pd.alpha_off = p.pp.slice_alpha_c0_offset_div2 * 2;
     pd.beta_off = p.pp.slice_beta_offset_div2 * 2;
     pd.excursion_map = c->d_exc_maps + (size_t)p.frame_id * c->n_mbs;
+    pd.exc_counter = c->d_exc_counter;
     pd.digest = nullptr;
     pd.frame_id = p.frame_id;
 }
@@ -158,7 +170,7 @@ const char* h264r_last_error(h264r_ctx* ctx) { return ctx ? ctx->err.c_str() : g
 int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_frames, int max_pending, uint32_t flags)
 {
     h264r_ctx* ctx = nullptr;      // errors before the context exists go to the thread-local string
-    if (!out || w_mbs <= 0 || h_mbs <= 0 || max_frames <= 0 || max_pending <= 0 || (flags & ~H264R_REF_COMPAT))
+    if (!out || w_mbs <= 0 || h_mbs <= 0 || max_frames <= 0 || max_pending <= 0 || (flags & ~(H264R_REF_COMPAT | H264R_DIGESTS)))
         return fail(nullptr, H264R_E_INVAL, "h264r_create: bad argument");
     *out = nullptr;
     int n_dev = 0;
@@ -185,7 +197,8 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     c->off_coeff = c->off_mv + align_up((size_t)c->n_mbs * H264R_MV_PER_MB * 2, 256);
     c->off_boff = c->off_coeff + align_up((size_t)c->n_mbs * H264R_COEFF_PER_MB * 2, 256);
     c->off_mvoff = c->off_boff + align_up((size_t)c->n_mbs * 4, 256);
-    c->slot_bytes = c->off_mvoff + align_up((size_t)c->n_mbs * 4, 256);
+    c->off_res = c->off_mvoff + align_up((size_t)c->n_mbs * 4, 256);
+    c->slot_bytes = c->off_res + align_up((size_t)c->n_mbs * 768, 256);
     c->ctrl_bytes = align_up((size_t)max_pending * sizeof(PicDesc), 256);      // descriptor table, one entry per arena slot
     auto cleanup = [&](int code) { h264r_destroy(c); return code; };
 #define CUC(call)                                                                                             \
@@ -213,7 +226,9 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     CUC(cudaEventCreate(&c->ev0));
     CUC(cudaEventCreate(&c->ev1));
     CUC(cudaMalloc(&c->d_frames, c->frame_bytes * max_frames));
-    CUC(cudaMalloc(&c->d_digests, (size_t)max_pending * 16));
+    CUC(cudaMalloc(&c->d_digests, (size_t)max_frames * 16));
+    c->digest_valid.assign(max_frames, 0);
+    c->h_digests.assign((size_t)max_frames * 4, 0);
     CUC(cudaMalloc(&c->d_exc_maps, (size_t)max_frames * c->n_mbs));
     CUC(cudaMalloc(&c->d_exc_counter, 256));
     CUC(cudaMalloc(&c->d_syntax, c->slot_bytes * max_pending));
@@ -290,6 +305,7 @@ int h264r_frame_begin(h264r_ctx* ctx, int frame_id, const h264r_pic_params* pp)
     p.pp = *pp;
     ctx->pending.push_back(p);
     ctx->frame_state[frame_id] = FRAME_OPEN;
+    ctx->digest_valid[frame_id] = 0;
     return H264R_OK;
 }
 
@@ -533,8 +549,18 @@ int h264r_flush(h264r_ctx* ctx)
             int cap = (sm_count * 16 * 8 + L.n - 1) / L.n;
             dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)L.n);
             prof_begin(0);
-            if (compat) k_inter<true><<<grid, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g, ctx->d_exc_counter);
-            else k_inter<false><<<grid, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g, ctx->d_exc_counter);
+            if (compat) k_inter<true><<<grid, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g);
+            else k_inter<false><<<grid, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g);
+            prof_end();
+            ctx->last_launches++;
+        });
+        for_chunks(wv, [&](const Pending& p) { return p.n_intra > 0; }, [&](const PicList& L) {
+            int want = (ctx->n_mbs + INTER_WARPS - 1) / INTER_WARPS;
+            int cap = (sm_count * 16 * 8 + L.n - 1) / L.n;
+            dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)L.n);
+            prof_begin(1);
+            if (compat) k_residual_pics<true><<<grid, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g);
+            else k_residual_pics<false><<<grid, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g);
             prof_end();
             ctx->last_launches++;
         });
@@ -543,8 +569,8 @@ int h264r_flush(h264r_ctx* ctx)
             int* prog = progress0 + (size_t)prog_pos * ctx->g.h_mbs;
             prog_pos += L.n;
             prof_begin(1);
-            if (compat) k_intra_rows<true><<<blocks, ROW_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g, prog, tickets0 + ticket_pos, ctx->d_exc_counter);
-            else k_intra_rows<false><<<blocks, ROW_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g, prog, tickets0 + ticket_pos, ctx->d_exc_counter);
+            if (compat) k_intra_rows<true><<<blocks, ROW_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g, prog, tickets0 + ticket_pos);
+            else k_intra_rows<false><<<blocks, ROW_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g, prog, tickets0 + ticket_pos);
             prof_end();
             ticket_pos++;
             ctx->last_launches++;
@@ -566,9 +592,21 @@ int h264r_flush(h264r_ctx* ctx)
             long cap = (long)sm_count * 16;
             int blocks = (int)((warps + 3) / 4 < cap ? (warps + 3) / 4 : cap);
             prof_begin(3);
-            k_pad<<<blocks, 128, 0, ctx->stream>>>(d_desc, L, ctx->g, compat ? 0 : 1);
+            const bool dig = (ctx->flags & H264R_DIGESTS) != 0;
+            k_pad<<<blocks, 128, 0, ctx->stream>>>(d_desc, L, ctx->g, compat ? 0 : 1, dig ? ctx->d_digests : nullptr);
             prof_end();
             ctx->last_launches++;
+            if (dig) {
+                // K5 as part of the reconstruction: frame ids of this chunk
+                PicList F;
+                F.n = L.n;
+                for (int i = 0; i < L.n; i++) F.slot[i] = h_desc[L.slot[i]].frame_id;
+                prof_begin(4);
+                k_digest<<<dim3(DIGEST_CTAS, F.n), 256, 0, ctx->stream>>>(digest_pool(ctx), F, ctx->g, ctx->d_digests);
+                prof_end();
+                ctx->last_launches++;
+                for (int i = 0; i < F.n; i++) ctx->digest_valid[F.slot[i]] = 1;
+            }
         });
     }
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -639,21 +677,26 @@ int h264r_frame_digests(h264r_ctx* ctx, const int* frame_ids, int n, uint8_t* ou
         if (r != H264R_OK) return r;
     }
     CU(cudaSetDevice(ctx->device));
-    // K5 runs on demand, in chunks bounded by the parameter list and by the staging buffer (max_pending digests)
-    FramePool pool{ctx->d_frames, ctx->frame_bytes, (size_t)PAD_Y * ctx->g.pitch_y + PAD_X,
-                   ctx->y_bytes + (size_t)PAD_YC * ctx->g.pitch_c + PAD_XC, ctx->y_bytes + ctx->c_bytes + (size_t)PAD_YC * ctx->g.pitch_c + PAD_XC};
-    const int chunk = ctx->max_pending < PIC_LIST_MAX ? ctx->max_pending : PIC_LIST_MAX;
+    // K5 for the frames whose digest was not produced with their reconstruction (H264R_DIGESTS)
     PicList list;
-    for (int base = 0; base < n; base += chunk) {
-        int m = n - base < chunk ? n - base : chunk;
-        list.n = m;
-        for (int i = 0; i < m; i++) list.slot[i] = frame_ids[base + i];
-        k_digest<<<m, 1024, 0, ctx->stream>>>(pool, list, ctx->g, ctx->d_digests);
-        CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(out + (size_t)base * 16, ctx->d_digests, (size_t)m * 16, cudaMemcpyDeviceToHost, ctx->stream));
-        if (base + chunk < n) CU(cudaStreamSynchronize(ctx->stream));      // d_digests is reused by the next chunk
+    list.n = 0;
+    auto run = [&]() {
+        if (!list.n) return;
+        k_zero_digests<<<1, 256, 0, ctx->stream>>>(list, ctx->d_digests);
+        k_digest<<<dim3(DIGEST_CTAS, list.n), 256, 0, ctx->stream>>>(digest_pool(ctx), list, ctx->g, ctx->d_digests);
+        list.n = 0;
+    };
+    for (int i = 0; i < n; i++) {
+        if (ctx->digest_valid[frame_ids[i]]) continue;
+        ctx->digest_valid[frame_ids[i]] = 1;
+        list.slot[list.n++] = frame_ids[i];
+        if (list.n == PIC_LIST_MAX) run();
     }
+    run();
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ctx->h_digests.data(), ctx->d_digests, (size_t)ctx->max_frames * 16, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; i++) memcpy(out + (size_t)i * 16, &ctx->h_digests[(size_t)frame_ids[i] * 4], 16);
     return H264R_OK;
 }
 

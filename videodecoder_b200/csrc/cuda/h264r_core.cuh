@@ -62,6 +62,8 @@ struct PicDesc {
     const int16_t* coeff;      // coefficient blocks of the picture, 16 levels each, packed (see BlkRef)
     const uint32_t* blk_mask;  // per macroblock: bit b set = block b is stored
     const uint32_t* blk_off;   // per macroblock: index of its first stored block
+    int16_t* residual;         // scratch: residual of the intra macroblocks, 384 int16 each (Y 16x16, U 8x8, V 8x8), produced
+                               // by the flat kernels ahead of the intra wavefront; null = the wavefront computes it itself
     uint8_t* y; uint8_t* u; uint8_t* v;
     const uint8_t* ref_y[H264R_MAX_REFS];
     const uint8_t* ref_u[H264R_MAX_REFS];
@@ -73,6 +75,7 @@ struct PicDesc {
     int16_t chroma_weight[H264R_MAX_REFS][2], chroma_offset[H264R_MAX_REFS][2];
     int32_t deblock_on, alpha_off, beta_off;     // offsets already multiplied by 2
     uint8_t* excursion_map;    // [n_mbs] or null
+    uint32_t* exc_counter;     // luma samples that left [0,255] before the store (see report_excursions)
     uint32_t* digest;          // 4 words
     int32_t frame_id;
     int32_t pad_;
@@ -93,7 +96,6 @@ struct alignas(16) MbWork {
     uint8_t dtile[24 * 24];               // deblocking luma tile x,y=-4..15 at [(y+4)*24 + x+4]
     uint8_t dctile[2][12 * 12];           // deblocking chroma tiles x,y=-2..7 at [(y+2)*12 + x+2]
     uint8_t bs[32];                       // boundary strengths [dir][edge][k]
-    uint32_t excursions;
 };
 
 // Coefficient storage.  Macroblock a owns the blocks whose bit is set in blk_mask[a] (bit b = block b of the 24
@@ -153,6 +155,18 @@ HD uint32_t load_mv(const PicDesc& pd, const h264r_mb_hdr& h, int a, int blk)
 }
 HD int mv_x(uint32_t v) { return (int)(int16_t)(v & 0xffff); }
 HD int mv_y(uint32_t v) { return (int)v >> 16; }
+
+// luma samples of macroblock a that left [0,255] before the store: counted, and the macroblock is marked
+HD void report_excursions(const PicDesc& pd, int a, uint32_t n)
+{
+    if (!n) return;
+#if defined(__CUDA_ARCH__)
+    atomicAdd(pd.exc_counter, n);
+#else
+    *pd.exc_counter += n;
+#endif
+    if (pd.excursion_map) pd.excursion_map[a] = 1;
+}
 
 HD int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 HD int clip1(int v) { return clip3(0, 255, v); }
@@ -230,7 +244,6 @@ HD int sat16(int v) { return clip3(-32768, 32767, v); }
 // Phase R0: lanes 0..23 copy their 4x4 block of levels (32 bytes, two 128-bit loads) into the working set.
 HD void phase_load_coeff(MbWork& w, const PicDesc& pd, int a, int lane)
 {
-    if (lane == 0) w.excursions = 0;
     if (lane < 24) {
         const BlkRef br = load_blkref(pd, a);
         const int4* src = reinterpret_cast<const int4*>(blk_ptr(pd, br, lane));
@@ -425,13 +438,7 @@ HD void phase_inter_luma(MbWork& w, const PicDesc& pd, const Geometry& g, const 
             w.tile[H264R_TI(px, py)] = recon_luma<COMPAT>(v + w.res[py * 16 + px], exc);
         }
     }
-    if (exc) {
-#if defined(__CUDA_ARCH__)
-        atomicAdd(&w.excursions, exc);
-#else
-        w.excursions += exc;
-#endif
-    }
+    report_excursions(pd, a, exc);
 }
 
 // Phase P2: chroma of an inter MB.  Lane -> plane (lane >> 4), 4 samples.
@@ -491,7 +498,6 @@ HD void phase_store(const MbWork& w, const PicDesc& pd, const Geometry& g, int a
         uint2* d = reinterpret_cast<uint2*>((plane ? pd.v : pd.u) + (size_t)(mby * 8 + row) * g.pitch_c + mbx * 8);
         *d = uint2{v0, v1};
     }
-    if (lane == 0 && w.excursions && pd.excursion_map) pd.excursion_map[a] = 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -577,13 +583,7 @@ HD void phase_intra16(MbWork& w, const PicDesc& pd, const Geometry& g, const h26
     // all lanes have read the borders they need before anybody overwrites TL(x>=0, y>=0): the
     // interior is disjoint from the borders, so no extra barrier is required
     for (int k = 0; k < 8; k++) TL(c0 + k, row) = out[k];
-    if (exc) {
-#if defined(__CUDA_ARCH__)
-        atomicAdd(&w.excursions, exc);
-#else
-        w.excursions += exc;
-#endif
-    }
+    report_excursions(pd, a, exc);
 }
 
 // Phase I4(ras): Intra4x4 prediction + reconstruction of the block at raster index ras; lanes 0..15
@@ -591,7 +591,7 @@ HD void phase_intra16(MbWork& w, const PicDesc& pd, const Geometry& g, const h26
 // (h264/macroblock.cpp:973-990, 1037-1365); block order and the up-right substitution rule follow
 // macroblock::Calc / get_4x4Neighbour (h264/macroblock.cpp:28-33, 1092-1110).
 template <bool COMPAT>
-HD void phase_intra4(MbWork& w, const h264r_mb_hdr& h, int ras, int lane)
+HD void phase_intra4(MbWork& w, const PicDesc& pd, const h264r_mb_hdr& h, int a, int ras, int lane)
 {
     if (lane >= 16) return;
     int bx = ras & 3, by = ras >> 2, blk = blk_raster(ras);
@@ -660,13 +660,7 @@ HD void phase_intra4(MbWork& w, const h264r_mb_hdr& h, int ras, int lane)
     uint32_t exc = 0;
     uint8_t s = recon_luma<COMPAT>(v + w.res[(Y + y) * 16 + X + x], exc);
     TL(X + x, Y + y) = s;
-    if (exc) {
-#if defined(__CUDA_ARCH__)
-        atomicAdd(&w.excursions, exc);
-#else
-        w.excursions += exc;
-#endif
-    }
+    report_excursions(pd, a, exc);
 }
 
 // Phase I8a(q): filtered neighbouring samples of 8x8 block q (ITU-T H.264 8.3.2.2.1) into w.e8:
@@ -717,7 +711,7 @@ HD void phase_intra8_filter(MbWork& w, const h264r_mb_hdr& h, int q, int lane)
     w.e8[lane] = (uint8_t)v;
 }
 // Phase I8b(q): Intra8x8 prediction (8.3.2.2.2 - 8.3.2.2.10) + reconstruction, 2 samples per lane.
-HD void phase_intra8(MbWork& w, const h264r_mb_hdr& h, int q, int lane)
+HD void phase_intra8(MbWork& w, const PicDesc& pd, const h264r_mb_hdr& h, int a, int q, int lane)
 {
     bool left_ok, top_ok, tl_ok, tr_ok;
     intra8_avail(h, q, left_ok, top_ok, tl_ok, tr_ok);
@@ -777,13 +771,7 @@ HD void phase_intra8(MbWork& w, const h264r_mb_hdr& h, int q, int lane)
     }
 #undef T8
 #undef L8
-    if (exc) {
-#if defined(__CUDA_ARCH__)
-        atomicAdd(&w.excursions, exc);
-#else
-        w.excursions += exc;
-#endif
-    }
+    report_excursions(pd, a, exc);
 }
 
 // Phase IC: chroma of an intra MB.  COMPAT: sample = residual (D4).  Otherwise ITU-T H.264 8.3.4.
@@ -1071,12 +1059,13 @@ HD uint32_t digest_mix(uint32_t i)
     h ^= h >> 15; h *= 0x85EBCA6Bu; h ^= h >> 13;
     return h;
 }
-HD void digest_accumulate(uint32_t d[4], uint32_t sample, uint32_t index)
+// word = 4 samples, little endian; index = position of the word in Y | U | V (each plane row-major, unpadded)
+HD void digest_accumulate(uint32_t d[4], uint32_t word, uint32_t index)
 {
-    d[0] += sample;
-    d[1] += sample * (index + 1u);
-    d[2] += sample * digest_mix(index);
-    d[3] += (sample ^ 0xA5u) * digest_mix(index ^ 0x5BD1E995u);
+    d[0] += word;
+    d[1] += word * (index + 1u);
+    d[2] += word * digest_mix(index);
+    d[3] += (word ^ 0xA5A5A5A5u) * digest_mix(index ^ 0x5BD1E995u);
 }
 
 }  // namespace h264r

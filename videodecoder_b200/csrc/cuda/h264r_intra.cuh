@@ -205,13 +205,7 @@ HD void phase_intra16_fast(MbWork& w, const PicDesc& pd, const Geometry& g, cons
     exc += add_residual<COMPAT>(p1, &w.res[row * 16 + c0 + 4], p1);
     *reinterpret_cast<uint2*>(&TL(c0, row)) = uint2{p0, p1};
     *reinterpret_cast<uint2*>(pd.y + (size_t)(mby * 16 + row) * g.pitch_y + mbx * 16 + c0) = uint2{p0, p1};
-    if (exc) {
-#if defined(__CUDA_ARCH__)
-        atomicAdd(&w.excursions, exc);
-#else
-        w.excursions += exc;
-#endif
-    }
+    report_excursions(pd, a, exc);
 }
 
 // ---- Intra4x4 ----------------------------------------------------------------------------------------------
@@ -274,7 +268,7 @@ HD void intra4_lut_fill(uint16_t* lut, int first, int stride)
 // takes the block with by = by_min + (lane >> 4); lane & 15 = sample.  Availability and the up-right
 // substitution rule follow macroblock::Calc / get_4x4Neighbour (h264/macroblock.cpp:28-33, 1092-1110).
 template <bool COMPAT>
-HD void phase_intra4_pair(MbWork& w, const h264r_mb_hdr& h, const uint16_t* lut, int d, int lane)
+HD void phase_intra4_pair(MbWork& w, const PicDesc& pd, const h264r_mb_hdr& h, int a, const uint16_t* lut, int d, int lane)
 {
     const int by_min = d > 3 ? (d - 2) >> 1 : 0, by_max = (d >> 1) < 3 ? (d >> 1) : 3;
     const int by = by_min + (lane >> 4);
@@ -314,13 +308,7 @@ HD void phase_intra4_pair(MbWork& w, const h264r_mb_hdr& h, const uint16_t* lut,
     }
     uint32_t exc = 0;
     TL(X + x, Y + y) = recon_luma<COMPAT>(v + w.res[(Y + y) * 16 + X + x], exc);
-    if (exc) {
-#if defined(__CUDA_ARCH__)
-        atomicAdd(&w.excursions, exc);
-#else
-        w.excursions += exc;
-#endif
-    }
+    report_excursions(pd, a, exc);
 }
 
 // ---- stores --------------------------------------------------------------------------------------------------

@@ -51,8 +51,7 @@ __global__ void __launch_bounds__(INTER_WARPS * 32) k_residual(PicDesc pd, int n
 // blockIdx.x strides over its macroblocks.
 // ------------------------------------------------------------------------------------------------
 template <bool COMPAT>
-__global__ void __launch_bounds__(INTER_WARPS * 32, H264R_INTER_MIN_CTAS) k_inter(const DescTable descs, const __grid_constant__ PicList list,
-                                                            Geometry g, uint32_t* excursions)
+__global__ void __launch_bounds__(INTER_WARPS * 32, H264R_INTER_MIN_CTAS) k_inter(const DescTable descs, const __grid_constant__ PicList list, Geometry g)
 {
     __shared__ WarpWork work[INTER_WARPS];
     int warp = threadIdx.x >> 5;
@@ -62,10 +61,27 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, H264R_INTER_MIN_CTAS) k_inte
     const PicDesc& pd = descs[list.slot[blockIdx.y]];
     for (int a = blockIdx.x * INTER_WARPS + warp; a < n_mbs; a += gridDim.x * INTER_WARPS) {
         h264r_mb_hdr h = load_hdr(pd, a);
-        if (is_intra(h.mb_class)) continue;       // warp-uniform
-        uint32_t exc = seq_inter_any<COMPAT>(ex, w, pd, g, h, a);
-        if (ex.lane == 0 && exc) atomicAdd(excursions, exc);
-        __syncwarp();
+        if (is_intra(h.mb_class)) continue;       // warp-uniform; k_intra_rows reconstructs it afterwards
+        seq_inter_any<COMPAT>(ex, w, pd, g, h, a);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 ahead of the intra wavefront for pictures without inter macroblocks (I pictures): residual of every macroblock
+// into the picture's scratch, flat grid like k_inter.  Keeps dequantisation and the transforms off the wavefront's
+// critical path, which is (W + 2H) macroblocks long.
+// ------------------------------------------------------------------------------------------------
+template <bool COMPAT>
+__global__ void __launch_bounds__(INTER_WARPS * 32) k_residual_pics(const DescTable descs, const __grid_constant__ PicList list, Geometry g)
+{
+    __shared__ MbWork work[INTER_WARPS];
+    int warp = threadIdx.x >> 5;
+    WarpExec ex{(int)(threadIdx.x & 31)};
+    const int n_mbs = g.w_mbs * g.h_mbs;
+    const PicDesc& pd = descs[list.slot[blockIdx.y]];
+    for (int a = blockIdx.x * INTER_WARPS + warp; a < n_mbs; a += gridDim.x * INTER_WARPS) {
+        h264r_mb_hdr h = load_hdr(pd, a);
+        if (is_intra(h.mb_class)) seq_residual_scratch<COMPAT>(ex, work[warp], pd, h, a);
     }
 }
 
@@ -118,7 +134,7 @@ __device__ __forceinline__ int row_ticket(int* ticket)
 
 template <bool COMPAT>
 __global__ void __launch_bounds__(ROW_WARPS * 32) k_intra_rows(const DescTable descs, const __grid_constant__ PicList list,
-                                                              Geometry g, int* progress, int* ticket, uint32_t* excursions)
+                                                              Geometry g, int* progress, int* ticket)
 {
     __shared__ MbWork work[ROW_WARPS];
     __shared__ uint32_t s_mask[ROW_WARPS][2][ROW_MASK_WORDS + 1];     // intra bitmaps of this row and of the row above
@@ -155,10 +171,30 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_intra_rows(const DescTable d
     };
     int x = next_intra(0), prev = -2;
     if (ex.lane == 0 && x > 0) st_release_gpu(&prog[row], x);
-    uint32_t exc = 0;
+    // software pipeline: header and residual of the NEXT intra macroblock of the row travel in registers while the
+    // current one is predicted (their latency is off the critical path)
+    const bool have_res = pd.residual != nullptr;
+    int4 hraw = int4{0, 0, 0, 0};
+    uint4 r0 = uint4{0, 0, 0, 0}, r1 = uint4{0, 0, 0, 0};
+    auto fetch = [&](int xn) {
+        if (xn >= W) return;
+        const int an = row * W + xn;
+        hraw = __ldg(reinterpret_cast<const int4*>(pd.hdr + an));
+        if (have_res && ex.lane < 24) {
+            const uint4* src = reinterpret_cast<const uint4*>(pd.residual + (size_t)an * 384) + ex.lane * 2;
+            r0 = __ldg(src); r1 = __ldg(src + 1);
+        }
+    };
+    fetch(x);
     while (x < W) {
         const int a = row * W + x;
-        h264r_mb_hdr h = load_hdr(pd, a);
+        h264r_mb_hdr h = *reinterpret_cast<h264r_mb_hdr*>(&hraw);
+        if (have_res && ex.lane < 24) {           // the previous macroblock ended with __syncwarp(): w.res is free
+            uint4* dst = reinterpret_cast<uint4*>(w.res) + ex.lane * 2;
+            dst[0] = r0; dst[1] = r1;
+        }
+        const int x_next = next_intra(x + 1);
+        fetch(x_next);
         if (row > 0) {
             // B, C, D are final unless they are intra macroblocks the row above has not reached yet: wait for the
             // last intra one among (x-1, x, x+1) of the row above
@@ -167,14 +203,12 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_intra_rows(const DescTable d
                 if (xx < W && ((above[xx >> 5] >> (xx & 31)) & 1)) { last = xx; break; }
             if (last >= 0) wait_progress(&prog[row - 1], last + 1);
         }
-        seq_intra_any<COMPAT>(ex, w, s_lut, pd, g, h, a, prev == x - 1);
-        exc += w.excursions;
+        seq_intra_any<COMPAT>(ex, w, s_lut, pd, g, h, a, prev == x - 1, have_res);
         prev = x;
-        x = next_intra(x + 1);
+        x = x_next;
         // ex() ended with __syncwarp(): every lane's stores precede lane 0's release
         if (ex.lane == 0) st_release_gpu(&prog[row], x);
     }
-    if (ex.lane == 0 && exc) atomicAdd(excursions, exc);
 }
 
 __global__ void __launch_bounds__(ROW_WARPS * 32) k_deblock_rows(const DescTable descs, const __grid_constant__ PicList list,
@@ -249,7 +283,13 @@ __global__ void __launch_bounds__(1024) k_blk_scan(const DescTable descs, const 
 // coordinate clamps).  One warp per padded row; luma always, chroma when `chroma` (spec mode: the
 // reference has no chroma motion compensation, D4).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_pad(const DescTable descs, const __grid_constant__ PicList list, Geometry g, int chroma)
+__global__ void k_zero_digests(const __grid_constant__ PicList frames, uint32_t* table)
+{
+    for (int i = threadIdx.x; i < frames.n * 4; i += blockDim.x) table[4 * (size_t)frames.slot[i >> 2] + (i & 3)] = 0;
+}
+
+__global__ void __launch_bounds__(128) k_pad(const DescTable descs, const __grid_constant__ PicList list, Geometry g, int chroma,
+                                             uint32_t* digest_table)
 {
     const int Wl = g.w_mbs * 16, Hl = g.h_mbs * 16, Wc = Wl >> 1, Hc = Hl >> 1;
     const int rows_l = Hl + 2 * PAD_Y, rows_c = chroma ? Hc + 2 * PAD_YC : 0, rows = rows_l + 2 * rows_c;
@@ -258,6 +298,7 @@ __global__ void __launch_bounds__(128) k_pad(const DescTable descs, const __grid
     for (long i = (long)blockIdx.x * 4 + (threadIdx.x >> 5); i < total; i += (long)gridDim.x * 4) {
         int p = (int)(i / rows), r = (int)(i - (long)p * rows);
         const PicDesc& pd = descs[list.slot[p]];
+        if (digest_table && r == 0 && lane < 4) digest_table[4 * (size_t)pd.frame_id + lane] = 0;     // K5 accumulates into it next
         if (r < rows_l) pad_row_phase(pd.y, g.pitch_y, Wl, Hl, PAD_X, PAD_Y, r - PAD_Y, lane);
         else if (r < rows_l + rows_c) pad_row_phase(pd.u, g.pitch_c, Wc, Hc, PAD_XC, PAD_YC, r - rows_l - PAD_YC, lane);
         else pad_row_phase(pd.v, g.pitch_c, Wc, Hc, PAD_XC, PAD_YC, r - rows_l - rows_c - PAD_YC, lane);
@@ -265,35 +306,37 @@ __global__ void __launch_bounds__(128) k_pad(const DescTable descs, const __grid
 }
 
 // ------------------------------------------------------------------------------------------------
-// K5: frame digest.  One CTA per picture; every thread folds 4-sample words, block reduction, the
-// CTA writes the four sums (no zeroing pass, no atomics on global memory).
+// K5: frame digest (definition: oracle/restate/h264_restate.c:h264o_digest).  Four order-independent sums over
+// the words of the three planes: grid = (DIGEST_CTAS, pictures), every CTA folds a band of rows of each plane,
+// reduces, and adds its four partial sums to the picture's entry (zeroed by the host side before the launch).
 // ------------------------------------------------------------------------------------------------
+constexpr int DIGEST_CTAS = 24;
 struct FramePool { uint8_t* base; size_t frame_bytes, off_y, off_u, off_v; };
-__global__ void __launch_bounds__(1024) k_digest(FramePool pool, const __grid_constant__ PicList frames, Geometry g, uint32_t* out)
+__device__ __forceinline__ void digest_rows(uint32_t d[4], const uint8_t* plane, int pitch, int words_per_row, int rows, uint32_t first_index)
 {
-    struct { const uint8_t* y; const uint8_t* u; const uint8_t* v; uint32_t* digest; } pd;
-    {
-        const uint8_t* f = pool.base + (size_t)frames.slot[blockIdx.x] * pool.frame_bytes;
-        pd.y = f + pool.off_y; pd.u = f + pool.off_u; pd.v = f + pool.off_v; pd.digest = out + 4 * blockIdx.x;
+    const int band = (rows + gridDim.x - 1) / gridDim.x, r0 = blockIdx.x * band, r1 = min(rows, r0 + band);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    const int pairs = words_per_row >> 1;            // plane widths are multiples of 8 samples
+    for (int r = r0 + warp; r < r1; r += n_warps) {
+        const uint2* row = reinterpret_cast<const uint2*>(plane + (size_t)r * pitch);
+        const uint32_t idx0 = first_index + (uint32_t)r * (uint32_t)words_per_row;
+#pragma unroll 4
+        for (int c = lane; c < pairs; c += 32) {
+            const uint2 v = __ldcg(row + c);
+            digest_accumulate(d, v.x, idx0 + 2u * (uint32_t)c);
+            digest_accumulate(d, v.y, idx0 + 2u * (uint32_t)c + 1u);
+        }
     }
+}
+__global__ void __launch_bounds__(256) k_digest(FramePool pool, const __grid_constant__ PicList frames, Geometry g, uint32_t* out)
+{
+    const uint8_t* f = pool.base + (size_t)frames.slot[blockIdx.y] * pool.frame_bytes;
     const int Wl = g.w_mbs * 16, Hl = g.h_mbs * 16, Wc = Wl / 2, Hc = Hl / 2;
     uint32_t d[4] = {0, 0, 0, 0};
-    const int lw = Wl / 4, cw = Wc / 4;
-    const int n_l = lw * Hl, n_c = cw * Hc;
-    for (int i = threadIdx.x; i < n_l + 2 * n_c; i += blockDim.x) {
-        const uint8_t* base; int pitch, wpr, k; uint32_t first;
-        if (i < n_l) { base = pd.y; pitch = g.pitch_y; wpr = lw; k = i; first = 0; }
-        else if (i < n_l + n_c) { base = pd.u; pitch = g.pitch_c; wpr = cw; k = i - n_l; first = (uint32_t)(Wl * Hl); }
-        else { base = pd.v; pitch = g.pitch_c; wpr = cw; k = i - n_l - n_c; first = (uint32_t)(Wl * Hl + Wc * Hc); }
-        int r = k / wpr, c = k - r * wpr;
-        uint32_t v = __ldcg(reinterpret_cast<const uint32_t*>(base + (size_t)r * pitch) + c);
-        uint32_t idx = first + (uint32_t)(r * wpr + c) * 4u;
-        digest_accumulate(d, v & 255u, idx);
-        digest_accumulate(d, (v >> 8) & 255u, idx + 1);
-        digest_accumulate(d, (v >> 16) & 255u, idx + 2);
-        digest_accumulate(d, v >> 24, idx + 3);
-    }
-    __shared__ uint32_t part[32][4];
+    digest_rows(d, f + pool.off_y, g.pitch_y, Wl / 4, Hl, 0u);
+    digest_rows(d, f + pool.off_u, g.pitch_c, Wc / 4, Hc, (uint32_t)(Wl / 4 * Hl));
+    digest_rows(d, f + pool.off_v, g.pitch_c, Wc / 4, Hc, (uint32_t)(Wl / 4 * Hl + Wc / 4 * Hc));
+    __shared__ uint32_t part[8][4];
     for (int k = 0; k < 4; k++)
         for (int o = 16; o > 0; o >>= 1) d[k] += __shfl_xor_sync(0xffffffffu, d[k], o);
     if ((threadIdx.x & 31) == 0) for (int k = 0; k < 4; k++) part[threadIdx.x >> 5][k] = d[k];
@@ -301,7 +344,7 @@ __global__ void __launch_bounds__(1024) k_digest(FramePool pool, const __grid_co
     if (threadIdx.x < 4) {
         uint32_t s = 0;
         for (int wv = 0; wv < (int)(blockDim.x >> 5); wv++) s += part[wv][threadIdx.x];
-        pd.digest[threadIdx.x] = s;
+        atomicAdd(out + 4 * (size_t)frames.slot[blockIdx.y] + threadIdx.x, s);       // table indexed by frame id
     }
 }
 

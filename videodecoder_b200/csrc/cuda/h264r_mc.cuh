@@ -145,9 +145,8 @@ struct alignas(16) InterWork {
     uint32_t win[480];          // staged windows, see phase_inter_stage
     int16_t res[384];           // residual
     uint8_t need[32];           // per lane: NEED_* of its block
-    uint32_t excursions;
     int32_t shape;              // 0: one 16x16 window, 1: four 8x8 windows, 2: sixteen 4x4 windows
-    uint32_t pad_[2];
+    uint32_t pad_[3];
 };
 
 // ---- K1: residual in registers -----------------------------------------------------------------------
@@ -319,7 +318,7 @@ HD void phase_inter_stage(InterWork& w, const PicDesc& pd, const Geometry& g, co
         load_mvs(pd, a, mv);
         shape = inter_shape<COMPAT>(h, mv);
     }
-    if (lane == 0) { w.shape = shape; w.excursions = 0; }
+    if (lane == 0) w.shape = shape;
     int mbx, mby;
     mb_xy(g, a, mbx, mby);
     const int W = g.w_mbs * 16, H = g.h_mbs * 16;
@@ -557,13 +556,7 @@ HD void phase_inter_compute(InterWork& w, const PicDesc& pd, const Geometry& g, 
         }
         *reinterpret_cast<uint32_t*>(cbase) = packed;
     }
-    if (exc) {
-#if defined(__CUDA_ARCH__)
-        atomicAdd(&w.excursions, exc);
-#else
-        w.excursions += exc;
-#endif
-    }
+    report_excursions(pd, a, exc);
 }
 
 // K1+K3 sequence for one inter macroblock (4x4 transform).  8x8-transform macroblocks take seq_inter_mb
@@ -577,9 +570,6 @@ HD void seq_inter_mb_fast(Exec& ex, InterWork& w, const PicDesc& pd, const Geome
         phase_inter_stage<COMPAT>(w, pd, g, h, a, lane);
     });
     ex([&](int lane) { phase_inter_compute<COMPAT>(w, pd, g, h, a, lane, coded); });
-    ex([&](int lane) {
-        if (lane == 0 && w.excursions && pd.excursion_map) pd.excursion_map[a] = 1;
-    });
 }
 
 }  // namespace h264r

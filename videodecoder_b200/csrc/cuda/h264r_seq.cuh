@@ -41,6 +41,26 @@ HD void seq_inter_mb(Exec& ex, MbWork& w, const PicDesc& pd, const Geometry& g, 
     ex([&](int lane) { phase_store(w, pd, g, a, lane); });
 }
 
+// K1 ahead of the intra wavefront: residual of one intra macroblock into the picture's scratch (pd.residual).
+// 4x4 transform: register version of h264r_intra.cuh; 8x8 transform / Intra8x8: generic phases.
+template <bool COMPAT, class Exec>
+HD void seq_residual_scratch(Exec& ex, MbWork& w, const PicDesc& pd, const h264r_mb_hdr& h, int a)
+{
+    if (!COMPAT && (h.mb_class == H264R_MB_I8x8 || (h.flags & H264R_T8x8))) {      // REF_COMPAT has no 8x8 transform
+        ex([&](int lane) { phase_load_coeff(w, pd, a, lane); });
+        ex([&](int lane) { phase_residual<COMPAT>(w, h, lane); });
+    } else {
+        ex([&](int lane) { phase_residual_fast<COMPAT>(w.res, pd, h, a, lane); });
+    }
+    ex([&](int lane) {
+        if (lane < 24) {
+            const uint4* src = reinterpret_cast<const uint4*>(w.res) + lane * 2;
+            uint4* dst = reinterpret_cast<uint4*>(pd.residual + (size_t)a * 384) + lane * 2;
+            dst[0] = src[0]; dst[1] = src[1];
+        }
+    });
+}
+
 // working set of a warp: the generic phases and the fast inter path never run at the same time
 union WarpWork {
     MbWork mb;
@@ -49,16 +69,14 @@ union WarpWork {
 };
 
 // K1 + K3 for any inter macroblock: fast path for the 4x4 transform, generic phases for the 8x8 transform.
-// Returns the number of luma excursions.
 template <bool COMPAT, class Exec>
-HD uint32_t seq_inter_any(Exec& ex, WarpWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a)
+HD void seq_inter_any(Exec& ex, WarpWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a)
 {
     if (!COMPAT && (h.flags & H264R_T8x8)) {
         seq_inter_mb<COMPAT>(ex, w.mb, pd, g, h, a);
-        return w.mb.excursions;
+        return;
     }
     seq_inter_mb_fast<COMPAT>(ex, w.in, pd, g, h, a);
-    return w.in.excursions;
 }
 
 // K1 + K2: one intra macroblock (its neighbours A, B, C, D are complete)
@@ -77,17 +95,17 @@ HD void seq_intra_mb(Exec& ex, MbWork& w, const PicDesc& pd, const Geometry& g, 
         });
     } else if (h.mb_class == H264R_MB_I4x4) {
         ex([&](int lane) {
-            phase_intra4<COMPAT>(w, h, 0, lane);
+            phase_intra4<COMPAT>(w, pd, h, a, 0, lane);
             phase_intra_chroma<COMPAT>(w, h, lane);
         });
-        for (int ras = 1; ras < 16; ras++) ex([&](int lane) { phase_intra4<COMPAT>(w, h, ras, lane); });
+        for (int ras = 1; ras < 16; ras++) ex([&](int lane) { phase_intra4<COMPAT>(w, pd, h, a, ras, lane); });
     } else {
         for (int q = 0; q < 4; q++) {
             ex([&](int lane) {
                 phase_intra8_filter(w, h, q, lane);
                 if (q == 0) phase_intra_chroma<COMPAT>(w, h, lane);
             });
-            ex([&](int lane) { phase_intra8(w, h, q, lane); });
+            ex([&](int lane) { phase_intra8(w, pd, h, a, q, lane); });
         }
     }
     ex([&](int lane) { phase_store(w, pd, g, a, lane); });
@@ -95,16 +113,17 @@ HD void seq_intra_mb(Exec& ex, MbWork& w, const PicDesc& pd, const Geometry& g, 
 
 // K1 + K2, latency version (h264r_intra.cuh) for Intra4x4 / Intra16x16; Intra8x8 takes the generic phases.
 // `carry`: the warp reconstructed the macroblock to the left immediately before (its tiles are still in w).
+// `have_res`: w.res already holds the macroblock's residual (the caller moved it in from pd.residual).
 template <bool COMPAT, class Exec>
-HD void seq_intra_any(Exec& ex, MbWork& w, const uint16_t* lut, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, bool carry)
+HD void seq_intra_any(Exec& ex, MbWork& w, const uint16_t* lut, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, bool carry,
+                      bool have_res = false)
 {
-    if (h.mb_class == H264R_MB_I8x8 || (h.flags & H264R_T8x8)) {
+    if (!COMPAT && (h.mb_class == H264R_MB_I8x8 || (h.flags & H264R_T8x8))) {      // REF_COMPAT has no 8x8 transform
         seq_intra_mb<COMPAT>(ex, w, pd, g, h, a);
         return;
     }
     ex([&](int lane) {
-        if (lane == 0) w.excursions = 0;
-        phase_residual_fast<COMPAT>(w.res, pd, h, a, lane);
+        if (!have_res) phase_residual_fast<COMPAT>(w.res, pd, h, a, lane);
         phase_intra_edges_fast(w, pd, g, h, a, lane, !COMPAT, carry);
     });
     if (h.mb_class == H264R_MB_I16x16) {
@@ -117,7 +136,7 @@ HD void seq_intra_any(Exec& ex, MbWork& w, const uint16_t* lut, const PicDesc& p
     } else {
         for (int d = 0; d < 10; d++)
             ex([&](int lane) {
-                phase_intra4_pair<COMPAT>(w, h, lut, d, lane);
+                phase_intra4_pair<COMPAT>(w, pd, h, a, lut, d, lane);
                 if (d == 0 && !COMPAT) phase_intra_chroma<false>(w, h, lane);
             });
         ex([&](int lane) {
@@ -125,9 +144,6 @@ HD void seq_intra_any(Exec& ex, MbWork& w, const uint16_t* lut, const PicDesc& p
             store_chroma<COMPAT>(w, pd, g, a, lane);
         });
     }
-    ex([&](int lane) {
-        if (lane == 0 && w.excursions && pd.excursion_map) pd.excursion_map[a] = 1;
-    });
 }
 
 // K4: deblock one macroblock in place (its neighbours A, B, C are completely filtered)

@@ -69,7 +69,7 @@ def load_library():
     L.h264r_release.argtypes = [vp, ci]
     L.h264r_last_flush_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ci)]
     L.h264r_set_profiling.argtypes = [vp, ci]
-    L.h264r_last_flush_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 4), ctypes.POINTER(ci * 4)]
+    L.h264r_last_flush_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 5), ctypes.POINTER(ci * 5)]
     L.h264r_last_flush_launch_ms.argtypes = [vp, vp, vp, ci]
     L.h264r_last_flush_launch_ms.restype = ci
     L.h264r_mark.argtypes = [vp, ci]
@@ -291,7 +291,7 @@ class Engine:
         return [(ms[i], fam[i]) for i in range(n)]
 
     def last_flush_kernel_ms(self):
-        ms, n = (ctypes.c_float * 4)(), (ctypes.c_int * 4)()
+        ms, n = (ctypes.c_float * 5)(), (ctypes.c_int * 5)()
         self._check(self.L.h264r_last_flush_kernel_ms(self.ctx, ctypes.byref(ms), ctypes.byref(n)))
         return list(ms), list(n)
 

@@ -877,12 +877,6 @@ void h264o_recon_picture(h264o_pic* p)
 /* position-dependent checksum of the three planes (DESIGN.md "K5 frame digest"): four sums modulo 2^32 over
  * the little-endian 32-bit words (4 samples) of Y, then U, then V, each plane row-major without padding (plane
  * widths are multiples of 8), so that it can be accumulated in any order. */
-static inline uint32_t mix(uint32_t i)
-{
-    uint32_t h = i * 0x9E3779B1u + 0x7F4A7C15u;
-    h ^= h >> 15; h *= 0x85EBCA6Bu; h ^= h >> 13;
-    return h;
-}
 void h264o_digest(const uint8_t* y, const uint8_t* u, const uint8_t* v, int w, int h, uint8_t out[16])
 {
     uint32_t d[4] = {0, 0, 0, 0};
@@ -893,10 +887,11 @@ void h264o_digest(const uint8_t* y, const uint8_t* u, const uint8_t* v, int w, i
         for (uint32_t k = 0; k < sizes[pl]; k++, i++) {
             const uint8_t* b = planes[pl] + 4u * k;
             uint32_t s = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+            uint32_t m = i * 0x9E3779B1u + 0x7F4A7C15u;
             d[0] += s;
             d[1] += s * (i + 1u);
-            d[2] += s * mix(i);
-            d[3] += (s ^ 0xA5A5A5A5u) * mix(i ^ 0x5BD1E995u);
+            d[2] += s * m;
+            d[3] += (s ^ 0xA5A5A5A5u) * (m ^ (m >> 15));
         }
     memcpy(out, d, 16);
 }

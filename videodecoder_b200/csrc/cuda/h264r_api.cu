@@ -555,9 +555,8 @@ int h264r_flush(h264r_ctx* ctx)
             ctx->last_launches++;
         });
         for_chunks(wv, [&](const Pending& p) { return p.n_intra > 0; }, [&](const PicList& L) {
-            int want = (ctx->n_mbs + INTER_WARPS - 1) / INTER_WARPS;
-            int cap = (sm_count * 16 * 8 + L.n - 1) / L.n;
-            dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)L.n);
+            int want = (ctx->n_mbs + INTER_WARPS * 32 - 1) / (INTER_WARPS * 32);       // 32 macroblocks per warp
+            dim3 grid((unsigned)want, (unsigned)L.n);
             prof_begin(1);
             if (compat) k_residual_pics<true><<<grid, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g);
             else k_residual_pics<false><<<grid, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g);

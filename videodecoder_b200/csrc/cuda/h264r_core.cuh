@@ -1053,19 +1053,15 @@ HD void phase_deblock_store(const MbWork& w, const PicDesc& pd, const Geometry& 
 // ------------------------------------------------------------------------------------------------
 // K5: frame digest (same definition as oracle/restate/h264_restate.c:h264o_digest)
 // ------------------------------------------------------------------------------------------------
-HD uint32_t digest_mix(uint32_t i)
-{
-    uint32_t h = i * 0x9E3779B1u + 0x7F4A7C15u;
-    h ^= h >> 15; h *= 0x85EBCA6Bu; h ^= h >> 13;
-    return h;
-}
-// word = 4 samples, little endian; index = position of the word in Y | U | V (each plane row-major, unpadded)
+// word = 4 samples, little endian; index = position of the word in Y | U | V (each plane row-major, unpadded).
+// Four sums modulo 2^32 with position-dependent multipliers: any order of accumulation gives the same digest.
 HD void digest_accumulate(uint32_t d[4], uint32_t word, uint32_t index)
 {
+    const uint32_t m = index * 0x9E3779B1u + 0x7F4A7C15u;
     d[0] += word;
     d[1] += word * (index + 1u);
-    d[2] += word * digest_mix(index);
-    d[3] += (word ^ 0xA5A5A5A5u) * digest_mix(index ^ 0x5BD1E995u);
+    d[2] += word * m;
+    d[3] += (word ^ 0xA5A5A5A5u) * (m ^ (m >> 15));
 }
 
 }  // namespace h264r

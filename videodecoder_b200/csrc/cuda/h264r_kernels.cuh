@@ -79,9 +79,16 @@ __global__ void __launch_bounds__(INTER_WARPS * 32) k_residual_pics(const DescTa
     WarpExec ex{(int)(threadIdx.x & 31)};
     const int n_mbs = g.w_mbs * g.h_mbs;
     const PicDesc& pd = descs[list.slot[blockIdx.y]];
-    for (int a = blockIdx.x * INTER_WARPS + warp; a < n_mbs; a += gridDim.x * INTER_WARPS) {
-        h264r_mb_hdr h = load_hdr(pd, a);
-        if (is_intra(h.mb_class)) seq_residual_scratch<COMPAT>(ex, work[warp], pd, h, a);
+    // a warp looks at 32 macroblocks at a time (one mb_class byte per lane) and transforms the intra ones
+    for (int a0 = (blockIdx.x * INTER_WARPS + warp) * 32; a0 < n_mbs; a0 += gridDim.x * INTER_WARPS * 32) {
+        const int al = a0 + ex.lane;
+        uint32_t m = __ballot_sync(0xffffffffu, al < n_mbs && is_intra(H264R_LDG(&pd.hdr[al].mb_class)));
+        while (m) {
+            const int a = a0 + __ffs(m) - 1;
+            m &= m - 1;
+            h264r_mb_hdr h = load_hdr(pd, a);
+            seq_residual_scratch<COMPAT>(ex, work[warp], pd, h, a);
+        }
     }
 }
 
@@ -246,36 +253,50 @@ __global__ void __launch_bounds__(1024) k_blk_scan(const DescTable descs, const 
     const uint32_t* mask = pd.blk_mask;
     uint32_t* off = const_cast<uint32_t*>(pd.blk_off);
     uint32_t* mvoff = const_cast<uint32_t*>(pd.mv_off);
-    const int per = (n_mbs + 1023) >> 10, first = threadIdx.x * per, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    auto count = [&](int a) -> unsigned long long {
-        unsigned long long c = (unsigned long long)__popc(__ldg(mask + a) & 0xFFFFFFu);
-        if (mvoff) {
-            const uint32_t* hw = reinterpret_cast<const uint32_t*>(pd.hdr + a);
-            uint32_t w0 = __ldg(hw), w1 = __ldg(hw + 1);            // mb_class = byte 0, sub_mb_type = byte 7
-            c += (unsigned long long)mv_count((int)(w0 & 255u), (int)(w1 >> 24)) << 32;
-        }
-        return c;
-    };
-    unsigned long long sum = 0;
-    for (int k = 0; k < per; k++) if (first + k < n_mbs) sum += count(first + k);
-    unsigned long long incl = sum;
-    for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ unsigned long long wsum[32];
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        unsigned long long v = wsum[lane], iv = v;
-        for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
-        wsum[lane] = iv - v;
-    }
-    __syncthreads();
-    unsigned long long run = wsum[warp] + incl - sum;
-    for (int k = 0; k < per; k++)
-        if (first + k < n_mbs) {
-            off[first + k] = (uint32_t)run;
-            if (mvoff) mvoff[first + k] = (uint32_t)(run >> 32);
-            run += count(first + k);
+    __shared__ unsigned long long s_total;
+    unsigned long long base = 0;          // counts of the tiles already done
+    // tiles of 8192 macroblocks: every thread owns 8 consecutive ones, all their loads in flight at once
+    for (int t0 = 0; t0 < n_mbs; t0 += 8192) {
+        const int first = t0 + threadIdx.x * 8;
+        unsigned long long c[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            c[k] = 0;
+            if (first + k < n_mbs) {
+                c[k] = (unsigned long long)__popc(__ldg(mask + first + k) & 0xFFFFFFu);
+                if (mvoff) {
+                    const uint2 hw = __ldg(reinterpret_cast<const uint2*>(pd.hdr + first + k));     // mb_class = byte 0, sub_mb_type = byte 7
+                    c[k] += (unsigned long long)mv_count((int)(hw.x & 255u), (int)(hw.y >> 24)) << 32;
+                }
+            }
         }
+        unsigned long long sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) sum += c[k];
+        unsigned long long incl = sum;
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long v = wsum[lane], iv = v;
+            for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
+            wsum[lane] = iv - v;
+            if (lane == 31) s_total = iv;
+        }
+        __syncthreads();
+        unsigned long long run = base + wsum[warp] + incl - sum;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (first + k < n_mbs) {
+                off[first + k] = (uint32_t)run;
+                if (mvoff) mvoff[first + k] = (uint32_t)(run >> 32);
+                run += c[k];
+            }
+        base += s_total;
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "emul", "emul.cpp")
 OUT = os.path.join(HERE, "emul", "_build", "libh264emul.so")
-DEPS = [SRC] + [os.path.join(ROOT, "videodecoder_b200", "csrc", "cuda", f) for f in ("h264r_core.cuh", "h264r_seq.cuh", "h264r_mc.cuh", "h264r_intra.cuh")] + [
+DEPS = [SRC] + [os.path.join(ROOT, "videodecoder_b200", "csrc", "cuda", f) for f in ("h264r_core.cuh", "h264r_seq.cuh", "h264r_mc.cuh", "h264r_intra.cuh", "h264r_deblock.cuh")] + [
     os.path.join(ROOT, "include", "h264r.h")]
 
 _lib = None

@@ -28,6 +28,7 @@ void fill_desc(PicDesc& pd, const h264r_pic_params* pp, const h264r_mb_hdr* hdr,
     pd.blk_mask = nullptr; pd.blk_off = nullptr;        // set by use_dense() / use_packed()
     pd.mv_off = nullptr;
     pd.residual = nullptr;
+    pd.nzmask = nullptr;
     for (int i = 0; i < H264R_MAX_REFS; i++) {
         pd.ref_y[i] = ref_y ? ref_y[i] : nullptr;
         pd.ref_u[i] = ref_u ? ref_u[i] : nullptr;
@@ -176,6 +177,8 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
     HostExec ex;
     WarpWork ww;
     MbWork& w = ww.mb;
+    std::vector<uint32_t> nzmask((size_t)w_mbs * h_mbs, 0xdeadbeefu);
+    pd.nzmask = nzmask.data();
     unsigned long long exc = 0;
     const bool compat = (flags & H264R_REF_COMPAT) != 0;
     const bool use_fast_intra = !(flags & 0x80000000u);     // test switch: bit 31 selects the generic intra phases
@@ -214,8 +217,18 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
         }
         prev = a;
     }
-    if (!compat && pd.deblock_on)
-        for (int a = 0; a < n; a++) seq_deblock_mb(ex, w, pd, g, a);
+    if (!compat && pd.deblock_on) {
+        if (use_fast_intra) {       // the row kernel's fast path (h264r_deblock.cuh), fed as k_deblock_rows feeds it
+            static DeblockWork dw;
+            for (int a = 0; a < n; a++) {
+                int mbx, mby;
+                mb_xy(g, a, mbx, mby);
+                h264r_mb_hdr h = load_hdr(pd, a), hl = mbx > 0 ? load_hdr(pd, a - 1) : h, ht = mby > 0 ? load_hdr(pd, a - w_mbs) : h;
+                seq_deblock_mb_fast(ex, dw, pd, g, h, hl, ht, pd.nzmask[a], mbx > 0 ? pd.nzmask[a - 1] : 0u, mby > 0 ? pd.nzmask[a - w_mbs] : 0u, a, mbx, mby);
+            }
+        } else
+            for (int a = 0; a < n; a++) seq_deblock_mb(ex, w, pd, g, a);
+    }
     cur.store(y, u, v);
     exc = *pd.exc_counter;
     return exc;

@@ -63,7 +63,7 @@ struct h264r_ctx {
     // arena slot = what the uploads carry, in this order: descriptor | hdr | blk_mask | mv | coefficient blocks;
     // then blk_off and mv_off (written by k_blk_scan, never uploaded)
     // then the residual scratch of the intra macroblocks (device only)
-    size_t slot_bytes = 0, off_hdr = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_mvoff = 0, off_coeff = 0, off_res = 0;
+    size_t slot_bytes = 0, off_hdr = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_mvoff = 0, off_coeff = 0, off_res = 0, off_nz = 0;
     // per-flush control block (descriptors + picture lists), pinned host mirror + device copy
     uint8_t* h_ctrl = nullptr;
     size_t ctrl_bytes = 0;
@@ -129,6 +129,7 @@ void fill_desc(h264r_ctx* c, const Pending& p, PicDesc& pd)
         pd.blk_mask = reinterpret_cast<const uint32_t*>(s + c->off_mask);
         pd.blk_off = reinterpret_cast<const uint32_t*>(s + c->off_boff);
     } else { pd.blk_mask = c->d_dense_mask; pd.blk_off = c->d_dense_off; }
+    pd.nzmask = reinterpret_cast<uint32_t*>(s + c->off_nz);
     pd.mv_off = p.mv_partition ? reinterpret_cast<const uint32_t*>(s + c->off_mvoff) : nullptr;
     // k_residual_pics leaves the residual of the intra macroblocks here, ahead of the wavefront
     pd.residual = p.n_intra > 0 ? reinterpret_cast<int16_t*>(s + c->off_res) : nullptr;
@@ -165,6 +166,21 @@ extern "C" {
 
 int h264r_abi_version(void) { return H264R_ABI_VERSION; }
 
+#ifdef H264R_TRACE
+// development build only: clock stamps of the row kernels (see WarpExecTrace); resets the buffer
+int h264r_debug_trace(long long* out, int cap)
+{
+    int n = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(int));
+    if (n > cap) n = cap;
+    cudaMemcpyFromSymbol(out, g_trace, (size_t)n * sizeof(long long));
+    int zero = 0;
+    cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(int));
+    return n;
+}
+#endif
+
 const char* h264r_last_error(h264r_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_frames, int max_pending, uint32_t flags)
@@ -198,7 +214,8 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     c->off_boff = c->off_coeff + align_up((size_t)c->n_mbs * H264R_COEFF_PER_MB * 2, 256);
     c->off_mvoff = c->off_boff + align_up((size_t)c->n_mbs * 4, 256);
     c->off_res = c->off_mvoff + align_up((size_t)c->n_mbs * 4, 256);
-    c->slot_bytes = c->off_res + align_up((size_t)c->n_mbs * 768, 256);
+    c->off_nz = c->off_res + align_up((size_t)c->n_mbs * 768, 256);
+    c->slot_bytes = c->off_nz + align_up((size_t)c->n_mbs * 4, 256);
     c->ctrl_bytes = align_up((size_t)max_pending * sizeof(PicDesc), 256);      // descriptor table, one entry per arena slot
     auto cleanup = [&](int code) { h264r_destroy(c); return code; };
 #define CUC(call)                                                                                             \

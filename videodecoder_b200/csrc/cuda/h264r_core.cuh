@@ -64,6 +64,8 @@ struct PicDesc {
     const uint32_t* blk_off;   // per macroblock: index of its first stored block
     int16_t* residual;         // scratch: residual of the intra macroblocks, 384 int16 each (Y 16x16, U 8x8, V 8x8), produced
                                // by the flat kernels ahead of the intra wavefront; null = the wavefront computes it itself
+    uint32_t* nzmask;          // spec mode, per inter macroblock: bit r = 4x4 luma block r (raster) has a non-zero level
+                               // (8x8 transform: the four blocks of a quadrant together); written by k_inter for K4
     uint8_t* y; uint8_t* u; uint8_t* v;
     const uint8_t* ref_y[H264R_MAX_REFS];
     const uint8_t* ref_u[H264R_MAX_REFS];
@@ -115,6 +117,21 @@ HD const int16_t* blk_ptr(const PicDesc& pd, const BlkRef& r, int b)       // nu
 {
     if (!((r.mask >> b) & 1u)) return nullptr;
     return pd.coeff + ((size_t)r.off + popc32(r.mask & ((1u << b) - 1u))) * 16;
+}
+
+// Header fields that are indexed at run time.  The record lives in registers; indexing its byte arrays with a run-time
+// index would push it into local memory (an L1 round trip per access, more after every fence), so these read the two
+// 32-bit halves of the union and shift.
+HD uint32_t hdr_word(const h264r_mb_hdr& h, int i)
+{
+    const uint8_t* b = h.u.pred4x4 + 4 * i;
+    return (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+}
+HD int hdr_ref_idx(const h264r_mb_hdr& h, int q) { return (int)((hdr_word(h, 0) >> (8 * q)) & 15u); }       // quadrant q = 0..3
+HD int hdr_pred_mode(const h264r_mb_hdr& h, int blk)                                                       // 4-bit mode of block blk = 0..15
+{
+    const uint32_t w = blk & 8 ? hdr_word(h, 1) : hdr_word(h, 0);
+    return (int)((w >> (4 * (blk & 7))) & 15u);
 }
 
 // Motion-vector storage.  Per-4x4 layout (h264r_submit_mbs): vector of block b (raster) of macroblock a is entry
@@ -423,7 +440,7 @@ HD void phase_inter_luma(MbWork& w, const PicDesc& pd, const Geometry& g, const 
     mb_xy(g, a, mbx, mby);
     const uint32_t mvw = load_mv(pd, h, a, ras);
     int mvx = mv_x(mvw), mvy = mv_y(mvw);
-    int ri = h.u.ref_idx[q] & 15;
+    int ri = hdr_ref_idx(h, q);
     RefPlane R{pd.ref_y[ri], g.pitch_y, g.w_mbs * 16, g.h_mbs * 16};
     int x0 = mbx * 16 + bx * 4, y0 = mby * 16 + by * 4;
     int ys = y0;
@@ -462,7 +479,7 @@ HD void phase_inter_chroma(MbWork& w, const PicDesc& pd, const Geometry& g, cons
     }
     const uint32_t mvw = load_mv(pd, h, a, l);
     int mvx = mv_x(mvw), mvy = mv_y(mvw);
-    int ri = h.u.ref_idx[q] & 15;
+    int ri = hdr_ref_idx(h, q);
     const uint8_t* ref = plane ? pd.ref_v[ri] : pd.ref_u[ri];
     int xf = mvx & 7, yf = mvy & 7;
     for (int k = 0; k < 4; k++) {
@@ -595,7 +612,7 @@ HD void phase_intra4(MbWork& w, const PicDesc& pd, const h264r_mb_hdr& h, int a,
 {
     if (lane >= 16) return;
     int bx = ras & 3, by = ras >> 2, blk = blk_raster(ras);
-    int mode = (h.u.pred4x4[blk >> 1] >> ((blk & 1) * 4)) & 15;
+    int mode = hdr_pred_mode(h, blk);
     bool left_ok = bx > 0 || (h.flags & H264R_AVAIL_A);
     bool top_ok = by > 0 || (h.flags & H264R_AVAIL_B);
     bool tr_ok;
@@ -715,7 +732,7 @@ HD void phase_intra8(MbWork& w, const PicDesc& pd, const h264r_mb_hdr& h, int a,
 {
     bool left_ok, top_ok, tl_ok, tr_ok;
     intra8_avail(h, q, left_ok, top_ok, tl_ok, tr_ok);
-    int mode = (h.u.pred4x4[q >> 1] >> ((q & 1) * 4)) & 15;
+    int mode = hdr_pred_mode(h, q);
     int X = (q & 1) * 8, Y = (q >> 1) * 8;
     const uint8_t* e = w.e8;
 #define T8(k) ((int)e[9 + (k)])
@@ -932,7 +949,7 @@ HD void phase_deblock_bs(MbWork& w, const PicDesc& pd, const Geometry& g, const 
         else if (blk_coded(w, h, rasq) || (mb_edge ? blk_coded_global(pd, hn, an, rasp) : blk_coded(w, h, rasp))) bs = 2;
         else {
             int qq = (rasq >> 3) * 2 + ((rasq & 3) >> 1), qp_ = (rasp >> 3) * 2 + ((rasp & 3) >> 1);
-            int refq = pd.ref_id[h.u.ref_idx[qq] & 15], refp = pd.ref_id[hn.u.ref_idx[qp_] & 15];
+            int refq = pd.ref_id[hdr_ref_idx(h, qq)], refp = pd.ref_id[hdr_ref_idx(hn, qp_)];
             const uint32_t mq = load_mv(pd, h, a, rasq), mp = load_mv(pd, hn, an, rasp);
             if (refq != refp) bs = 1;
             else if (iabs(mv_x(mq) - mv_x(mp)) >= 4 || iabs(mv_y(mq) - mv_y(mp)) >= 4) bs = 1;

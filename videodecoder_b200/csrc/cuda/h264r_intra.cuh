@@ -24,8 +24,9 @@ namespace h264r {
 // (Y 16x16, U 8x8, V 8x8).  Inter / Intra4x4: luma blocks whose coded_block_pattern bit is clear are zero
 // (the reference zero-fills them, h264/residual.cpp:44-46).  Intra16x16: DC levels go through the 4x4
 // Hadamard (reference residual::Decode_Intra16x16, h264/residual.cpp:286-319) and bypass the scaling.
+// nz_flags (optional, 16 bytes): lane b < 16 records whether luma block b has a non-zero level, at its raster index.
 template <bool COMPAT>
-HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane)
+HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane, uint8_t* nz_flags)
 {
     if (lane >= 24) return;
     const BlkRef br = load_blkref(pd, a);
@@ -86,6 +87,7 @@ HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr&
             zero = false;
         }
     }
+    if (nz_flags && luma) nz_flags[blk_raster(lane)] = zero ? 0 : 1;
     // store the block: 4 rows of 4 int16 (8 bytes each)
     int16_t* dst;
     int pitch;
@@ -275,7 +277,7 @@ HD void phase_intra4_pair(MbWork& w, const PicDesc& pd, const h264r_mb_hdr& h, i
     if (by > by_max) return;
     const int bx = d - 2 * by, pos = lane & 15, x = pos & 3, y = pos >> 2;
     const int ras = by * 4 + bx, blk = blk_raster(ras);
-    const int mode = (h.u.pred4x4[blk >> 1] >> ((blk & 1) * 4)) & 15;
+    const int mode = hdr_pred_mode(h, blk);
     const int X = bx * 4, Y = by * 4;
     int v;
     if (mode == 2) {

@@ -14,6 +14,41 @@ struct WarpExec {
     }
 };
 
+#ifdef H264R_TRACE
+// Development build (-DH264R_TRACE): the row kernels time their phases.  The warp of row 0 of the first picture of a
+// launch never waits for anybody, so its clock stamps show what one macroblock costs one warp, phase by phase.
+__device__ long long g_trace[4096];
+__device__ int g_trace_n;
+struct WarpExecTrace {
+    int lane; bool on;
+    long long t[20]; int k;          // stamps of the current macroblock stay in registers until mark(2)
+    template <class F> __device__ __forceinline__ void operator()(F f)
+    {
+        f(lane);
+        __syncwarp();
+        if (on && k < 20) t[k++] = clock64();
+    }
+    __device__ __forceinline__ void mark(long long tag)
+    {
+        if (!on) return;
+        if (tag == 1) { k = 0; t[k++] = clock64(); return; }
+        long long now = clock64();
+        if (lane == 0 && g_trace_n + k + 4 < 4096) {
+            int n = g_trace_n;
+            g_trace[n++] = -1; g_trace[n++] = t[0];
+            for (int i = 1; i < k; i++) g_trace[n++] = t[i];
+            g_trace[n++] = -2; g_trace[n++] = now;
+            g_trace_n = n;
+        }
+    }
+};
+#define ROW_EXEC(flat) WarpExecTrace ex; ex.lane = (int)(threadIdx.x & 31); ex.on = (flat) == 0; ex.k = 0
+#define ROW_MARK(tag) ex.mark(tag)
+#else
+#define ROW_EXEC(flat) WarpExec ex{(int)(threadIdx.x & 31)}
+#define ROW_MARK(tag)
+#endif
+
 // The pictures a launch works on: indices into the device descriptor table (one descriptor per syntax-arena slot),
 // passed BY VALUE in the kernel parameters.  Descriptors are uploaded with their picture's syntax (copy stream), so
 // a flush itself copies nothing: a host-to-device copy issued at flush time would queue behind every syntax upload
@@ -122,9 +157,20 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Polls with relaxed loads (an acquire load invalidates the SM's L1 every time it is issued, for every warp of the
+// SM) and fences once when the value has arrived: relaxed load + fence.acq_rel is an acquire pattern.
 __device__ __forceinline__ void wait_progress(const int* p, int need)
 {
-    while (ld_acquire_gpu(p) < need) __nanosleep(20);
+    if (ld_relaxed_gpu(p) < need) {
+        do { __nanosleep(20); } while (ld_relaxed_gpu(p) < need);
+    }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
 constexpr int ROW_WARPS = 4;          // row warps per CTA of the wavefront kernels
@@ -151,7 +197,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_intra_rows(const DescTable d
     const int flat = row_ticket(ticket);          // __syncthreads() inside: the table is complete
     if (flat >= list.n * H) return;
     const int warp = threadIdx.x >> 5;
-    WarpExec ex{(int)(threadIdx.x & 31)};
+    ROW_EXEC(flat);
     const int p = flat / H, row = flat - p * H;
     const PicDesc& pd = descs[list.slot[p]];
     int* prog = progress + (size_t)p * H;
@@ -210,34 +256,51 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_intra_rows(const DescTable d
                 if (xx < W && ((above[xx >> 5] >> (xx & 31)) & 1)) { last = xx; break; }
             if (last >= 0) wait_progress(&prog[row - 1], last + 1);
         }
+        ROW_MARK(1);
         seq_intra_any<COMPAT>(ex, w, s_lut, pd, g, h, a, prev == x - 1, have_res);
         prev = x;
         x = x_next;
         // ex() ended with __syncwarp(): every lane's stores precede lane 0's release
         if (ex.lane == 0) st_release_gpu(&prog[row], x);
+        ROW_MARK(2);
     }
 }
 
 __global__ void __launch_bounds__(ROW_WARPS * 32) k_deblock_rows(const DescTable descs, const __grid_constant__ PicList list,
                                                                 Geometry g, int* progress, int* ticket)
 {
-    __shared__ MbWork work[ROW_WARPS];
+    __shared__ DeblockWork work[ROW_WARPS];
     const int W = g.w_mbs, H = g.h_mbs;
     const int flat = row_ticket(ticket);
     if (flat >= list.n * H) return;
     const int warp = threadIdx.x >> 5;
-    WarpExec ex{(int)(threadIdx.x & 31)};
+    ROW_EXEC(flat);
     const int p = flat / H, row = flat - p * H;
     const PicDesc& pd = descs[list.slot[p]];
     int* prog = progress + (size_t)p * H;
-    MbWork& w = work[warp];
+    DeblockWork& w = work[warp];
+    // headers and non-zero masks of the macroblock, its upper neighbour (prefetched one macroblock ahead) and its left
+    // neighbour (= the previous macroblock of this warp)
+    auto hdr_at = [&](int a) { int4 raw = __ldg(reinterpret_cast<const int4*>(pd.hdr + a)); return *reinterpret_cast<h264r_mb_hdr*>(&raw); };
+    h264r_mb_hdr h = hdr_at(row * W), ht = row > 0 ? hdr_at((row - 1) * W) : h, hl = h;
+    uint32_t nz = pd.nzmask[row * W], nzt = row > 0 ? pd.nzmask[(row - 1) * W] : 0u, nzl = 0u;
     for (int x = 0; x < W; x++) {
+        const int a = row * W + x;
+        h264r_mb_hdr h_next = h, ht_next = ht;
+        uint32_t nz_next = 0u, nzt_next = 0u;
+        if (x + 1 < W) {
+            h_next = hdr_at(a + 1); nz_next = pd.nzmask[a + 1];
+            if (row > 0) { ht_next = hdr_at(a + 1 - W); nzt_next = pd.nzmask[a + 1 - W]; }
+        }
         if (row > 0) {
             int need = x + 2 < W ? x + 2 : W;
             wait_progress(&prog[row - 1], need);
         }
-        seq_deblock_mb(ex, w, pd, g, row * W + x);
+        ROW_MARK(1);
+        seq_deblock_mb_fast(ex, w, pd, g, h, hl, row > 0 ? ht : h, nz, nzl, nzt, a, x, row);
         if (ex.lane == 0) st_release_gpu(&prog[row], x + 1);
+        ROW_MARK(2);
+        hl = h; nzl = nz; h = h_next; nz = nz_next; ht = ht_next; nzt = nzt_next;
     }
 }
 

@@ -145,9 +145,20 @@ struct alignas(16) InterWork {
     uint32_t win[480];          // staged windows, see phase_inter_stage
     int16_t res[384];           // residual
     uint8_t need[32];           // per lane: NEED_* of its block
+    uint8_t nzf[16];            // spec mode: per luma block (raster) "has a non-zero level", for K4
     int32_t shape;              // 0: one 16x16 window, 1: four 8x8 windows, 2: sixteen 4x4 windows
     uint32_t pad_[3];
 };
+// 16 byte flags -> 16-bit mask
+HD uint32_t nz_pack(const uint8_t* f)
+{
+    const uint4 v = *reinterpret_cast<const uint4*>(f);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) m |= (((w[i] & 1u) | ((w[i] >> 7) & 2u) | ((w[i] >> 14) & 4u) | ((w[i] >> 21) & 8u)) << (4 * i));
+    return m;
+}
 
 // ---- K1: residual in registers -----------------------------------------------------------------------
 struct Dequant {                // per QP: d = (c * mul + add) >> shr for the three position classes
@@ -199,7 +210,7 @@ HD void idct4_fast(const int c[16], const Dequant& q, bool dc_bypass, int r[16])
 
 // K1 for any 4x4-transform macroblock: h264r_intra.cuh
 template <bool COMPAT>
-HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane);
+HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane, uint8_t* nz_flags = nullptr);
 
 // ---- motion vectors, window shape --------------------------------------------------------------------
 HD void load_mvs(const PicDesc& pd, int a, uint32_t mv[16])
@@ -233,7 +244,8 @@ HD int inter_shape(const h264r_mb_hdr& h, const uint32_t mv[16])
         all = all && mv[b0] == mv[0];
     }
     if (!q_uniform) return 2;
-    bool ref_same = h.u.ref_idx[0] == h.u.ref_idx[1] && h.u.ref_idx[0] == h.u.ref_idx[2] && h.u.ref_idx[0] == h.u.ref_idx[3];
+    const uint32_t rw = hdr_word(h, 0);
+    bool ref_same = rw == (rw & 255u) * 0x01010101u;
     return (all && ref_same) ? 0 : 1;
 }
 
@@ -328,19 +340,19 @@ HD void phase_inter_stage(InterWork& w, const PicDesc& pd, const Geometry& g, co
     }
     if (shape == 0) {
         const uint32_t v = load_mv(pd, h, a, 0);
-        const uint8_t* ref = pd.ref_y[h.u.ref_idx[0] & 15];
+        const uint8_t* ref = pd.ref_y[hdr_ref_idx(h, 0)];
         int xb = clip3(-19, W + 2, mbx * 16 + (mv_x(v) >> 2)), yb = clip3(-19, H + 3, mby * 16 + (mv_y(v) >> 2));
         stage_window<22, 6, 32>(w.win, ref, g.pitch_y, xb - 2, yb - 3, lane);
     } else if (shape == 1) {
         const int q = lane >> 3, b0 = (q >> 1) * 8 + (q & 1) * 2;
         const uint32_t v = load_mv(pd, h, a, b0);
-        const uint8_t* ref = pd.ref_y[h.u.ref_idx[q] & 15];
+        const uint8_t* ref = pd.ref_y[hdr_ref_idx(h, q)];
         int xb = clip3(-11, W + 2, mbx * 16 + (q & 1) * 8 + (mv_x(v) >> 2)), yb = clip3(-11, H + 3, mby * 16 + (q >> 1) * 8 + (mv_y(v) >> 2));
         stage_window<14, 4, 8>(w.win + q * 56, ref, g.pitch_y, xb - 2, yb - 3, lane & 7);
     } else {
         const int b = lane >> 1, bx = b & 3, by = b >> 2, q = (by >> 1) * 2 + (bx >> 1);
         const uint32_t v = load_mv(pd, h, a, b);
-        const uint8_t* ref = pd.ref_y[h.u.ref_idx[q] & 15];
+        const uint8_t* ref = pd.ref_y[hdr_ref_idx(h, q)];
         int ys = mby * 16 + by * 4;
         // reference's source-row offset for 4x4 sub-partitions 2 and 3 (D8, h264/macroblock.cpp:786-789)
         if (COMPAT && h.mb_class == H264R_MB_P8x8 && ((h.sub_mb_type >> (2 * q)) & 3) == H264R_SUB_4x4 && (by & 1)) ys -= 3;
@@ -510,7 +522,7 @@ HD void phase_inter_compute(InterWork& w, const PicDesc& pd, const Geometry& g, 
     if (wn == 0) mc_patch<COMPAT, 0>(wp, pitch, m, pred);
     else if (!(wn & NEED_J)) mc_patch<COMPAT, 1>(wp, pitch, m, pred);
     else mc_patch<COMPAT, 2>(wp, pitch, m, pred);
-    const int ri = h.u.ref_idx[q] & 15;
+    const int ri = hdr_ref_idx(h, q);
     if (pd.weighted_pred) {
         pred[0] = weight_packed(pred[0], pd.luma_log2_wd, pd.luma_weight[ri], pd.luma_offset[ri]);
         pred[1] = weight_packed(pred[1], pd.luma_log2_wd, pd.luma_weight[ri], pd.luma_offset[ri]);
@@ -538,7 +550,7 @@ HD void phase_inter_compute(InterWork& w, const PicDesc& pd, const Geometry& g, 
             const int cw = g.w_mbs * 8, ch = g.h_mbs * 8;
             for (int k = 0; k < 4; k++) {
                 int cx = cx0 + k, blk = (cy >> 1) * 4 + (cx >> 1), qq = (cy >> 2) * 2 + (cx >> 2);
-                int rc = h.u.ref_idx[qq] & 15;
+                int rc = hdr_ref_idx(h, qq);
                 const uint8_t* ref = plane ? pd.ref_v[rc] : pd.ref_u[rc];
                 uint32_t v2 = load_mv(pd, h, a, blk);
                 int mvx = mv_x(v2), mvy = mv_y(v2);
@@ -566,10 +578,13 @@ HD void seq_inter_mb_fast(Exec& ex, InterWork& w, const PicDesc& pd, const Geome
 {
     const bool coded = h.cbp != 0;
     ex([&](int lane) {
-        if (coded) phase_residual_fast<COMPAT>(w.res, pd, h, a, lane);
+        if (coded) phase_residual_fast<COMPAT>(w.res, pd, h, a, lane, (!COMPAT && pd.nzmask) ? w.nzf : nullptr);
         phase_inter_stage<COMPAT>(w, pd, g, h, a, lane);
     });
-    ex([&](int lane) { phase_inter_compute<COMPAT>(w, pd, g, h, a, lane, coded); });
+    ex([&](int lane) {
+        if (!COMPAT && pd.nzmask && lane == 0) pd.nzmask[a] = coded ? nz_pack(w.nzf) : 0u;
+        phase_inter_compute<COMPAT>(w, pd, g, h, a, lane, coded);
+    });
 }
 
 }  // namespace h264r

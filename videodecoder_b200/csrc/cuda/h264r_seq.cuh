@@ -8,6 +8,7 @@
 #include "h264r_core.cuh"
 #include "h264r_mc.cuh"
 #include "h264r_intra.cuh"
+#include "h264r_deblock.cuh"
 
 namespace h264r {
 
@@ -33,8 +34,16 @@ template <bool COMPAT, class Exec>
 HD void seq_inter_mb(Exec& ex, MbWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a)
 {
     ex([&](int lane) { phase_load_coeff(w, pd, a, lane); });
-    ex([&](int lane) { phase_residual<COMPAT>(w, h, lane); });
     ex([&](int lane) {
+        phase_residual<COMPAT>(w, h, lane);
+        if (!COMPAT && pd.nzmask && lane < 16) w.bs[lane] = blk_coded(w, h, lane) ? 1 : 0;       // bs[] is free until K4
+    });
+    ex([&](int lane) {
+        if (!COMPAT && pd.nzmask && lane == 0) {
+            uint32_t m = 0;
+            for (int r = 0; r < 16; r++) m |= (uint32_t)w.bs[r] << r;
+            pd.nzmask[a] = m;
+        }
         phase_inter_luma<COMPAT>(w, pd, g, h, a, lane);
         phase_inter_chroma<COMPAT>(w, pd, g, h, a, lane);
     });

@@ -266,50 +266,98 @@ HD void intra4_lut_fill(uint16_t* lut, int first, int stride)
     for (int k = first; k < INTRA4_LUT_SIZE; k += stride) lut[k] = intra4_entry(k >> 4, k & 3, (k >> 2) & 3);
 }
 
-// Step d = 0..9 of the macroblock's inner wavefront: blocks (bx, by) with bx + 2 by = d; half-warp `lane >> 4`
-// takes the block with by = by_min + (lane >> 4); lane & 15 = sample.  Availability and the up-right
-// substitution rule follow macroblock::Calc / get_4x4Neighbour (h264/macroblock.cpp:28-33, 1092-1110).
-template <bool COMPAT>
-HD void phase_intra4_pair(MbWork& w, const PicDesc& pd, const h264r_mb_hdr& h, int a, const uint16_t* lut, int d, int lane)
+// Per-lane state that survives from one phase to the next: a register on the device, one slot per lane in the
+// host emulator (where the lanes of a phase run one after the other).
+template <class T> struct PerLane {
+#if defined(__CUDA_ARCH__)
+    T v;
+    HD T& operator()(int) { return v; }
+#else
+    T v[32];
+    T& operator()(int lane) { return v[lane]; }
+#endif
+};
+
+// The macroblock's inner wavefront: step d = 0..9 handles the blocks (bx, by) with bx + 2 by = d; half-warp
+// `lane >> 4` takes the block with by = by_min + (lane >> 4), lane & 15 = sample.  Everything about a lane's sample
+// of step d that does not depend on sample VALUES -- which block, its mode, the table entry, the three tile
+// offsets with the up-right substitution applied, the residual -- is worked out for all ten steps at once before
+// the first step (ten independent chains), so that a step itself is three byte loads, three multiply-adds, a
+// shift, the residual add and one store.  Availability and the up-right substitution rule follow
+// macroblock::Calc / get_4x4Neighbour (h264/macroblock.cpp:28-33, 1092-1110).
+//   a[d] = o0 | o1 << 10 | o2 << 20 | shift << 30        (tile byte offsets; DC: o0 = top word, o1 = first left sample)
+//   b[d] = out | w0 << 10 | w1 << 12 | w2 << 14 | kind << 16   (kind 0 idle, 1 directional, 2..5 DC with both / left /
+//          top / no neighbours)
+//   r[d >> 1] = residual of steps d (low half) and d + 1 (high half)
+struct I4Plan { uint32_t a[10], b[10], r[5]; };
+
+HD void intra4_plan(const MbWork& w, const h264r_mb_hdr& h, const uint16_t* lut, int lane, I4Plan& pl)
 {
-    const int by_min = d > 3 ? (d - 2) >> 1 : 0, by_max = (d >> 1) < 3 ? (d >> 1) : 3;
-    const int by = by_min + (lane >> 4);
-    if (by > by_max) return;
-    const int bx = d - 2 * by, pos = lane & 15, x = pos & 3, y = pos >> 2;
-    const int ras = by * 4 + bx, blk = blk_raster(ras);
-    const int mode = hdr_pred_mode(h, blk);
-    const int X = bx * 4, Y = by * 4;
-    int v;
-    if (mode == 2) {
-        const bool left_ok = bx > 0 || (h.flags & H264R_AVAIL_A), top_ok = by > 0 || (h.flags & H264R_AVAIL_B);
-        const int st = dp4a_us(*reinterpret_cast<const uint32_t*>(&TL(X, Y - 1)), 0x01010101u, 0);
-        const int sl = (int)TL(X - 1, Y) + (int)TL(X - 1, Y + 1) + (int)TL(X - 1, Y + 2) + (int)TL(X - 1, Y + 3);
-        if (left_ok && top_ok) v = (st + sl + 4) >> 3;
-        else if (left_ok) v = (sl + 2) >> 2;
-        else if (top_ok) v = (st + 2) >> 2;
-        else v = 128;
-    } else {
-        bool tr_ok;
-        if (blk == 3 || blk == 11) tr_ok = false;
-        else if (bx == 3) tr_ok = (by == 0) && (h.flags & H264R_AVAIL_C) && (h.flags & H264R_AVAIL_B);
-        else if (by > 0) tr_ok = true;
-        else tr_ok = (h.flags & H264R_AVAIL_B) != 0;
-        const int trmax = tr_ok ? 7 : 3;
-        const uint32_t e = lut[mode * 16 + pos];
-        const int i0 = (int)(e & 15u);
-        const uint8_t* left = &TL(X - 1, Y + 3), * top = &TL(X, Y - 1);
-        int acc = (1 << ((e >> 10) & 3)) >> 1;
+    const int pos = lane & 15, x = pos & 3, y = pos >> 2;
 #pragma unroll
-        for (int t = 0; t < 3; t++) {
-            const int i = i0 + t, wt = (int)((e >> (4 + 2 * t)) & 3u);
-            const int k = i - 5 < trmax ? i - 5 : trmax;
-            const uint8_t* p = i <= 4 ? left - i * TILE_P : top + k;
-            acc += wt * (int)*p;
+    for (int d = 0; d < 10; d++) {
+        const int by_min = d > 3 ? (d - 2) >> 1 : 0, by_max = (d >> 1) < 3 ? (d >> 1) : 3;
+        const int by = by_min + (lane >> 4);
+        uint32_t A = 0, B = 0;
+        int res = 0;
+        if (by <= by_max) {
+            const int bx = d - 2 * by, ras = by * 4 + bx, blk = blk_raster(ras);
+            const int mode = hdr_pred_mode(h, blk);
+            const int X = bx * 4, Y = by * 4;
+            B = (uint32_t)H264R_TI(X + x, Y + y);
+            res = w.res[(Y + y) * 16 + X + x];
+            if (mode == 2) {
+                const bool left_ok = bx > 0 || (h.flags & H264R_AVAIL_A), top_ok = by > 0 || (h.flags & H264R_AVAIL_B);
+                A = (uint32_t)H264R_TI(X, Y - 1) | ((uint32_t)H264R_TI(X - 1, Y) << 10);
+                B |= (uint32_t)(left_ok ? (top_ok ? 2 : 3) : (top_ok ? 4 : 5)) << 16;
+            } else {
+                bool tr_ok;
+                if (blk == 3 || blk == 11) tr_ok = false;
+                else if (bx == 3) tr_ok = (by == 0) && (h.flags & H264R_AVAIL_C) && (h.flags & H264R_AVAIL_B);
+                else if (by > 0) tr_ok = true;
+                else tr_ok = (h.flags & H264R_AVAIL_B) != 0;
+                const int trmax = tr_ok ? 7 : 3;
+                const uint32_t e = lut[mode * 16 + pos];
+                const int i0 = (int)(e & 15u);
+                const int left = H264R_TI(X - 1, Y + 3), top = H264R_TI(X, Y - 1);
+                uint32_t o[3];
+#pragma unroll
+                for (int t = 0; t < 3; t++) {
+                    const int i = i0 + t;
+                    const int k = i - 5 < trmax ? i - 5 : trmax;
+                    o[t] = (uint32_t)(i <= 4 ? left - i * TILE_P : top + k);
+                }
+                A = o[0] | (o[1] << 10) | (o[2] << 20) | (((e >> 10) & 3u) << 30);
+                B |= (((e >> 4) & 63u) << 10) | (1u << 16);
+            }
         }
-        v = acc >> ((e >> 10) & 3);
+        pl.a[d] = A; pl.b[d] = B;
+        if (d & 1) pl.r[d >> 1] |= (uint32_t)res << 16; else pl.r[d >> 1] = (uint32_t)res & 0xffffu;
     }
+}
+
+template <bool COMPAT, int D>
+HD void phase_intra4_step(MbWork& w, const PicDesc& pd, int a, const I4Plan& pl, int lane)
+{
+    (void)lane;
+    const uint32_t A = pl.a[D], B = pl.b[D];
+    const int kind = (int)((B >> 16) & 7u);
+    if (!kind) return;
+    const uint8_t* t = w.tile;
+    int v;
+    if (kind == 1) {
+        const int sh = (int)(A >> 30);
+        v = ((int)((B >> 10) & 3u) * (int)t[A & 1023u] + (int)((B >> 12) & 3u) * (int)t[(A >> 10) & 1023u] +
+             (int)((B >> 14) & 3u) * (int)t[(A >> 20) & 1023u] + ((1 << sh) >> 1)) >> sh;
+    } else {
+        const uint8_t* l = t + ((A >> 10) & 1023u);
+        const int st = dp4a_us(*reinterpret_cast<const uint32_t*>(t + (A & 1023u)), 0x01010101u, 0);
+        const int sl = (int)l[0] + (int)l[TILE_P] + (int)l[2 * TILE_P] + (int)l[3 * TILE_P];
+        v = kind == 2 ? (st + sl + 4) >> 3 : (kind == 3 ? (sl + 2) >> 2 : (kind == 4 ? (st + 2) >> 2 : 128));
+    }
+    const int res = (int)(int16_t)(pl.r[D >> 1] >> (16 * (D & 1)));
     uint32_t exc = 0;
-    TL(X + x, Y + y) = recon_luma<COMPAT>(v + w.res[(Y + y) * 16 + X + x], exc);
+    w.tile[B & 1023u] = recon_luma<COMPAT>(v + res, exc);
     report_excursions(pd, a, exc);
 }
 

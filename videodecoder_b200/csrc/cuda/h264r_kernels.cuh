@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_intra_rows(const DescTable d
             uint4* dst = reinterpret_cast<uint4*>(w.res) + ex.lane * 2;
             dst[0] = r0; dst[1] = r1;
         }
+        __syncwarp();                             // the first phase already reads w.res (Intra4x4 plan)
         const int x_next = next_intra(x + 1);
         fetch(x_next);
         if (row > 0) {

@@ -131,11 +131,9 @@ HD void seq_intra_any(Exec& ex, MbWork& w, const uint16_t* lut, const PicDesc& p
         seq_intra_mb<COMPAT>(ex, w, pd, g, h, a);
         return;
     }
-    ex([&](int lane) {
-        if (!have_res) phase_residual_fast<COMPAT>(w.res, pd, h, a, lane);
-        phase_intra_edges_fast(w, pd, g, h, a, lane, !COMPAT, carry);
-    });
+    if (!have_res) ex([&](int lane) { phase_residual_fast<COMPAT>(w.res, pd, h, a, lane); });
     if (h.mb_class == H264R_MB_I16x16) {
+        ex([&](int lane) { phase_intra_edges_fast(w, pd, g, h, a, lane, !COMPAT, carry); });
         ex([&](int lane) {
             phase_intra16_fast<COMPAT>(w, pd, g, h, a, lane);
             if (COMPAT) store_chroma<true>(w, pd, g, a, lane);
@@ -143,11 +141,24 @@ HD void seq_intra_any(Exec& ex, MbWork& w, const uint16_t* lut, const PicDesc& p
         });
         if (!COMPAT) ex([&](int lane) { store_chroma<false>(w, pd, g, a, lane); });
     } else {
-        for (int d = 0; d < 10; d++)
-            ex([&](int lane) {
-                phase_intra4_pair<COMPAT>(w, pd, h, a, lut, d, lane);
-                if (d == 0 && !COMPAT) phase_intra_chroma<false>(w, h, lane);
-            });
+        PerLane<I4Plan> plan;
+        ex([&](int lane) {
+            phase_intra_edges_fast(w, pd, g, h, a, lane, !COMPAT, carry);
+            intra4_plan(w, h, lut, lane, plan(lane));
+        });
+        ex([&](int lane) {
+            phase_intra4_step<COMPAT, 0>(w, pd, a, plan(lane), lane);
+            if (!COMPAT) phase_intra_chroma<false>(w, h, lane);
+        });
+        ex([&](int lane) { phase_intra4_step<COMPAT, 1>(w, pd, a, plan(lane), lane); });
+        ex([&](int lane) { phase_intra4_step<COMPAT, 2>(w, pd, a, plan(lane), lane); });
+        ex([&](int lane) { phase_intra4_step<COMPAT, 3>(w, pd, a, plan(lane), lane); });
+        ex([&](int lane) { phase_intra4_step<COMPAT, 4>(w, pd, a, plan(lane), lane); });
+        ex([&](int lane) { phase_intra4_step<COMPAT, 5>(w, pd, a, plan(lane), lane); });
+        ex([&](int lane) { phase_intra4_step<COMPAT, 6>(w, pd, a, plan(lane), lane); });
+        ex([&](int lane) { phase_intra4_step<COMPAT, 7>(w, pd, a, plan(lane), lane); });
+        ex([&](int lane) { phase_intra4_step<COMPAT, 8>(w, pd, a, plan(lane), lane); });
+        ex([&](int lane) { phase_intra4_step<COMPAT, 9>(w, pd, a, plan(lane), lane); });
         ex([&](int lane) {
             store_luma_tile(w, pd, g, a, lane);
             store_chroma<COMPAT>(w, pd, g, a, lane);

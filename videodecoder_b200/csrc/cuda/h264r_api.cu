@@ -3,6 +3,7 @@
 // computes anything launches the sm_100a kernels of h264r_kernels.cuh.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -23,6 +24,7 @@ struct Pending {
     int n_intra;            // intra macroblocks seen by submit
     int n_submitted;
     int wave;
+    int lane;
     int layout;             // 0 = nothing submitted yet, 1 = dense (h264r_submit_mbs), 2 = packed (h264r_submit_mbs_packed)
     size_t n_blocks;        // packed: coefficient blocks stored so far
     bool mv_partition;      // vectors in partition order (h264r_submit_picture with n_mvs >= 0)
@@ -38,6 +40,15 @@ struct h264r_ctx {
     uint32_t flags = 0;
     cudaStream_t stream = nullptr;          // kernels, read-back
     cudaStream_t copy_stream = nullptr;     // syntax uploads: overlap the kernels of earlier waves / flushes
+    int n_lanes = 1;                        // independent kernel pipelines (see h264r_flush)
+    int inter_ctas_per_sm = 6;
+    cudaStream_t lane_stream[8] = {};
+    cudaEvent_t ev_lane[8] = {};
+    cudaEvent_t ev_main = nullptr;
+    bool main_dirty = false;                // the main stream holds work the lanes must wait for
+    int next_lane = 0;
+    std::vector<int> frame_lane;            // lane that produced / last used a frame slot, -1 = never used
+    size_t sync_pos = 0;                    // ring position in d_sync
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> ev_copied;     // per arena slot: its picture's syntax is resident
     cudaEvent_t ev_flush[64] = {};           // ring: all kernels of flush number n are done
@@ -228,6 +239,19 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     } while (0)
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    {
+        const char* e = getenv("H264R_LANES");      // tuning knob; 1 = a single pipeline
+        int nl = e ? atoi(e) : 4;
+        c->n_lanes = nl < 1 ? 1 : (nl > 8 ? 8 : nl);
+        const char* e2 = getenv("H264R_INTER_CTAS");
+        if (e2 && atoi(e2) > 0) c->inter_ctas_per_sm = atoi(e2);
+    }
+    for (int l = 0; l < c->n_lanes; l++) {
+        CUC(cudaStreamCreateWithFlags(&c->lane_stream[l], cudaStreamNonBlocking));
+        CUC(cudaEventCreateWithFlags(&c->ev_lane[l], cudaEventDisableTiming));
+    }
+    CUC(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+    c->frame_lane.assign(max_frames, -1);
     c->ev_copied.assign(max_pending, nullptr);
     for (int i = 0; i < max_pending; i++) CUC(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
     for (int i = 0; i < 64; i++) CUC(cudaEventCreateWithFlags(&c->ev_flush[i], cudaEventDisableTiming));
@@ -252,7 +276,8 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     CUC(cudaMallocHost(&c->h_ctrl, c->ctrl_bytes));
     CUC(cudaMemsetAsync(c->d_exc_counter, 0, 256, c->stream));
     CUC(cudaMemsetAsync(c->d_exc_maps, 0, (size_t)max_frames * c->n_mbs, c->stream));
-    c->sync_ints = (size_t)4 * max_pending * h_mbs + (size_t)2 * max_pending;
+    // ring of hand-over words: in flight are at most max_pending pictures x 2 wavefront kernels x (H + 1) words
+    c->sync_ints = (size_t)8 * max_pending * (h_mbs + 1) + 1024;
     CUC(cudaMalloc(&c->d_sync, c->sync_ints * sizeof(int)));
     CUC(cudaStreamSynchronize(c->stream));
     c->frame_state.assign(max_frames, FRAME_FREE);
@@ -268,7 +293,13 @@ void h264r_destroy(h264r_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    for (int l = 0; l < 8; l++) if (c->lane_stream[l]) cudaStreamSynchronize(c->lane_stream[l]);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int l = 0; l < 8; l++) {
+        if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
+        if (c->ev_lane[l]) cudaEventDestroy(c->ev_lane[l]);
+    }
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
     cudaFree(c->d_dense_mask); cudaFree(c->d_dense_off);
     for (auto e : c->ev_copied) if (e) cudaEventDestroy(e);
     for (auto e : c->ev_flush) if (e) cudaEventDestroy(e);
@@ -499,30 +530,47 @@ int h264r_flush(h264r_ctx* ctx)
     ctx->last_launches = 0;
     ctx->timing_valid = false;
     const bool compat = (ctx->flags & H264R_REF_COMPAT) != 0;
-    // dependency waves
+    const int NL = ctx->n_lanes;
+    // Dependency waves, and the LANE of every picture.  A lane is a CUDA stream that carries whole prediction chains:
+    // a picture goes to the lane of its references (stream order is then its dependency), a picture without
+    // references to the lane its frame slot used before (stream order protects the slot's old readers) or, for a
+    // fresh slot, to the next lane round-robin.  Independent GOPs / streams therefore run as independent pipelines:
+    // the latency-bound wavefront kernels of one lane overlap the throughput-bound kernels of the others.
     int n_waves = 0;
-    for (Pending* p : run) {
-        int wv = 0;
+    std::vector<uint32_t> foreign(run.size(), 0);      // lanes (bit mask) a picture must wait for besides its own
+    for (size_t k = 0; k < run.size(); k++) {
+        Pending* p = run[k];
+        int wv = 0, lane = -1;
         for (int i = 0; i < p->pp.num_ref_idx_l0; i++) {
             int r = p->pp.ref_list0[i];
             if (ctx->frame_state[r] == FRAME_QUEUED && ctx->frame_wave[r] >= 0 && ctx->frame_wave[r] + 1 > wv) wv = ctx->frame_wave[r] + 1;
+            int rl = ctx->frame_lane[r];
+            if (rl >= 0) { if (lane < 0) lane = rl; else if (rl != lane) foreign[k] |= 1u << rl; }
         }
+        int old = ctx->frame_lane[p->frame_id];
+        if (lane < 0) lane = old >= 0 ? old : (ctx->next_lane++ % NL);
+        else if (old >= 0 && old != lane) foreign[k] |= 1u << old;
         p->wave = wv;
+        p->lane = lane;
         ctx->frame_wave[p->frame_id] = wv;
+        ctx->frame_lane[p->frame_id] = lane;
         if (wv + 1 > n_waves) n_waves = wv + 1;
     }
     const int n = (int)run.size();
     const DescTable d_desc{ctx->d_syntax, ctx->slot_bytes};
     const PicDesc* h_desc = reinterpret_cast<const PicDesc*>(ctx->h_ctrl);
-    CU(cudaMemsetAsync(ctx->d_sync, 0, ctx->sync_ints * sizeof(int), ctx->stream));
-    int* const progress0 = ctx->d_sync;
-    int* const tickets0 = ctx->d_sync + (size_t)4 * ctx->max_pending * ctx->g.h_mbs;
-    int prog_pos = 0, ticket_pos = 0;            // next free picture-sized progress region / ticket word
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (ctx->main_dirty) {
+        // something was queued on the main stream that the lanes must not overtake (read-backs, map resets)
+        CU(cudaEventRecord(ctx->ev_main, ctx->stream));
+        for (int l = 0; l < NL; l++) CU(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->ev_main, 0));
+        ctx->main_dirty = false;
+    }
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->device);
     ctx->kev_used = 0;
     ctx->kev_family.clear();
+    cudaStream_t st = nullptr;       // stream of the lane being issued
     auto prof_begin = [&](int family) {
         if (!ctx->profiling) return;
         if ((int)ctx->kev.size() < ctx->kev_used + 2) {
@@ -531,100 +579,132 @@ int h264r_flush(h264r_ctx* ctx)
             ctx->kev.push_back(a); ctx->kev.push_back(b);
         }
         ctx->kev_family.push_back(family);
-        cudaEventRecord(ctx->kev[ctx->kev_used], ctx->stream);
+        cudaEventRecord(ctx->kev[ctx->kev_used], st);
     };
     auto prof_end = [&]() {
         if (!ctx->profiling) return;
-        cudaEventRecord(ctx->kev[ctx->kev_used + 1], ctx->stream);
+        cudaEventRecord(ctx->kev[ctx->kev_used + 1], st);
         ctx->kev_used += 2;
     };
-    // runs f(list) over the pictures of wave wv selected by pred, in chunks that fit the kernel parameters
+    // hand-over words of one wavefront launch: a zeroed region of the ring (a region comes round again only after
+    // far more pictures than can be in flight, see sync_ints)
+    const size_t ring = ctx->sync_ints;
+    auto sync_region = [&](size_t ints) -> int* {
+        if (ctx->sync_pos + ints > ring) ctx->sync_pos = 0;
+        int* r = ctx->d_sync + ctx->sync_pos;
+        ctx->sync_pos += ints;
+        cudaMemsetAsync(r, 0, ints * sizeof(int), st);
+        return r;
+    };
+    // runs f(list) over the pictures of (wave, lane) selected by pred, in chunks that fit the kernel parameters
     PicList list;
-    auto for_chunks = [&](int wv, auto pred, auto f) {
+    int cur_wave = 0, cur_lane = 0;
+    auto for_chunks = [&](auto pred, auto f) {
         list.n = 0;
         for (int i = 0; i < n; i++) {
-            if (run[i]->wave != wv || !pred(*run[i])) continue;
+            if (run[i]->wave != cur_wave || run[i]->lane != cur_lane || !pred(*run[i])) continue;
             list.slot[list.n++] = run[i]->slot;
             if (list.n == PIC_LIST_MAX) { f(list); list.n = 0; }
         }
         if (list.n) f(list);
     };
-    // uploads run on the copy stream in frame_end order: a wave may start when its last-ended picture is resident,
-    // so the upload of later waves overlaps the kernels of earlier ones
-    std::vector<Pending*> wave_last(n_waves, nullptr);
-    for (Pending* p : run) if (!wave_last[p->wave] || p->seq > wave_last[p->wave]->seq) wave_last[p->wave] = p;
+    std::vector<uint8_t> lane_used(NL, 0);
     for (int wv = 0; wv < n_waves; wv++) {
-        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[wave_last[wv]->slot], 0));
-        // block offsets of the pictures that arrived packed
-        for_chunks(wv, [&](const Pending& p) { return p.layout == 2; }, [&](const PicList& L) {
-            k_blk_scan<<<L.n, 1024, 0, ctx->stream>>>(d_desc, L, ctx->n_mbs);
-            ctx->last_launches++;
-        });
-        for_chunks(wv, [&](const Pending& p) { return p.pp.slice_type == H264R_SLICE_P && p.n_intra < ctx->n_mbs; }, [&](const PicList& L) {
-            // grid.y = picture, grid.x strides over its macroblocks; about eight CTA generations in total
-            int want = (ctx->n_mbs + INTER_WARPS - 1) / INTER_WARPS;
-            int cap = (sm_count * 16 * 8 + L.n - 1) / L.n;
-            dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)L.n);
-            prof_begin(0);
-            if (compat) k_inter<true><<<grid, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g);
-            else k_inter<false><<<grid, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g);
-            prof_end();
-            ctx->last_launches++;
-        });
-        for_chunks(wv, [&](const Pending& p) { return p.n_intra > 0; }, [&](const PicList& L) {
-            int want = (ctx->n_mbs + INTER_WARPS * 32 - 1) / (INTER_WARPS * 32);       // 32 macroblocks per warp
-            dim3 grid((unsigned)want, (unsigned)L.n);
-            prof_begin(1);
-            if (compat) k_residual_pics<true><<<grid, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g);
-            else k_residual_pics<false><<<grid, INTER_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g);
-            prof_end();
-            ctx->last_launches++;
-        });
-        for_chunks(wv, [&](const Pending& p) { return p.n_intra > 0; }, [&](const PicList& L) {
-            int rows = L.n * ctx->g.h_mbs, blocks = (rows + ROW_WARPS - 1) / ROW_WARPS;
-            int* prog = progress0 + (size_t)prog_pos * ctx->g.h_mbs;
-            prog_pos += L.n;
-            prof_begin(1);
-            if (compat) k_intra_rows<true><<<blocks, ROW_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g, prog, tickets0 + ticket_pos);
-            else k_intra_rows<false><<<blocks, ROW_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g, prog, tickets0 + ticket_pos);
-            prof_end();
-            ticket_pos++;
-            ctx->last_launches++;
-        });
-        for_chunks(wv, [&](const Pending& p) { return h_desc[p.slot].deblock_on != 0; }, [&](const PicList& L) {
-            int rows = L.n * ctx->g.h_mbs, blocks = (rows + ROW_WARPS - 1) / ROW_WARPS;
-            int* prog = progress0 + (size_t)prog_pos * ctx->g.h_mbs;
-            prog_pos += L.n;
-            prof_begin(2);
-            k_deblock_rows<<<blocks, ROW_WARPS * 32, 0, ctx->stream>>>(d_desc, L, ctx->g, prog, tickets0 + ticket_pos);
-            prof_end();
-            ticket_pos++;
-            ctx->last_launches++;
-        });
-        // border replication of the finished pictures of this wave
-        for_chunks(wv, [&](const Pending&) { return true; }, [&](const PicList& L) {
-            int rows = ctx->g.h_mbs * 16 + 2 * PAD_Y + (compat ? 0 : 2 * (ctx->g.h_mbs * 8 + 2 * PAD_YC));
-            long warps = (long)L.n * rows;
-            long cap = (long)sm_count * 16;
-            int blocks = (int)((warps + 3) / 4 < cap ? (warps + 3) / 4 : cap);
-            prof_begin(3);
-            const bool dig = (ctx->flags & H264R_DIGESTS) != 0;
-            k_pad<<<blocks, 128, 0, ctx->stream>>>(d_desc, L, ctx->g, compat ? 0 : 1, dig ? ctx->d_digests : nullptr);
-            prof_end();
-            ctx->last_launches++;
-            if (dig) {
-                // K5 as part of the reconstruction: frame ids of this chunk
-                PicList F;
-                F.n = L.n;
-                for (int i = 0; i < L.n; i++) F.slot[i] = h_desc[L.slot[i]].frame_id;
-                prof_begin(4);
-                k_digest<<<dim3(DIGEST_CTAS, F.n), 256, 0, ctx->stream>>>(digest_pool(ctx), F, ctx->g, ctx->d_digests);
+        for (int lane = 0; lane < NL; lane++) {
+            cur_wave = wv; cur_lane = lane;
+            st = ctx->lane_stream[lane];
+            // uploads run on the copy stream in frame_end order: the lane waits for the last-ended picture of this
+            // (wave, lane), so the upload of later pictures overlaps the kernels of earlier ones
+            Pending* last = nullptr;
+            uint32_t wait_lanes = 0;
+            for (int i = 0; i < n; i++)
+                if (run[i]->wave == wv && run[i]->lane == lane) {
+                    if (!last || run[i]->seq > last->seq) last = run[i];
+                    wait_lanes |= foreign[i];
+                }
+            if (!last) continue;
+            lane_used[lane] = 1;
+            CU(cudaStreamWaitEvent(st, ctx->ev_copied[last->slot], 0));
+            for (int l = 0; l < NL; l++)
+                if ((wait_lanes >> l) & 1u) {           // references (or the frame slot's old readers) live on another lane
+                    CU(cudaEventRecord(ctx->ev_lane[l], ctx->lane_stream[l]));
+                    CU(cudaStreamWaitEvent(st, ctx->ev_lane[l], 0));
+                }
+            // block / vector offsets of the pictures that arrived packed
+            for_chunks([&](const Pending& p) { return p.layout == 2; }, [&](const PicList& L) {
+                k_blk_scan<<<L.n, 1024, 0, st>>>(d_desc, L, ctx->n_mbs);
+                ctx->last_launches++;
+            });
+            for_chunks([&](const Pending& p) { return p.pp.slice_type == H264R_SLICE_P && p.n_intra < ctx->n_mbs; }, [&](const PicList& L) {
+                // grid.y = picture, grid.x strides over its macroblocks.  With several lanes the grid is persistent and
+                // sized below the SMs' capacity (inter_ctas_per_sm of 8), so that the wavefront kernels of the other
+                // lanes always find room next to it; with one lane about eight CTA generations.
+                int want = (ctx->n_mbs + INTER_WARPS - 1) / INTER_WARPS;
+                int cap = NL > 1 ? (sm_count * ctx->inter_ctas_per_sm + L.n - 1) / L.n : (sm_count * 16 * 8 + L.n - 1) / L.n;
+                dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)L.n);
+                prof_begin(0);
+                if (compat) k_inter<true><<<grid, INTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g);
+                else k_inter<false><<<grid, INTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g);
                 prof_end();
                 ctx->last_launches++;
-                for (int i = 0; i < F.n; i++) ctx->digest_valid[F.slot[i]] = 1;
-            }
-        });
+            });
+            for_chunks([&](const Pending& p) { return p.n_intra > 0; }, [&](const PicList& L) {
+                int want = (ctx->n_mbs + INTER_WARPS * 32 - 1) / (INTER_WARPS * 32);       // 32 macroblocks per warp
+                dim3 grid((unsigned)want, (unsigned)L.n);
+                prof_begin(1);
+                if (compat) k_residual_pics<true><<<grid, INTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g);
+                else k_residual_pics<false><<<grid, INTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g);
+                prof_end();
+                ctx->last_launches++;
+            });
+            for_chunks([&](const Pending& p) { return p.n_intra > 0; }, [&](const PicList& L) {
+                int rows = L.n * ctx->g.h_mbs, blocks = (rows + ROW_WARPS - 1) / ROW_WARPS;
+                int* sync = sync_region((size_t)rows + 1);        // progress words, then the ticket
+                prof_begin(1);
+                if (compat) k_intra_rows<true><<<blocks, ROW_WARPS * 32, 0, st>>>(d_desc, L, ctx->g, sync, sync + rows);
+                else k_intra_rows<false><<<blocks, ROW_WARPS * 32, 0, st>>>(d_desc, L, ctx->g, sync, sync + rows);
+                prof_end();
+                ctx->last_launches++;
+            });
+            for_chunks([&](const Pending& p) { return h_desc[p.slot].deblock_on != 0; }, [&](const PicList& L) {
+                int rows = L.n * ctx->g.h_mbs, blocks = (rows + ROW_WARPS - 1) / ROW_WARPS;
+                int* sync = sync_region((size_t)rows + 1);
+                prof_begin(2);
+                k_deblock_rows<<<blocks, ROW_WARPS * 32, 0, st>>>(d_desc, L, ctx->g, sync, sync + rows);
+                prof_end();
+                ctx->last_launches++;
+            });
+            // border replication (and digest) of the finished pictures
+            for_chunks([&](const Pending&) { return true; }, [&](const PicList& L) {
+                int rows = ctx->g.h_mbs * 16 + 2 * PAD_Y + (compat ? 0 : 2 * (ctx->g.h_mbs * 8 + 2 * PAD_YC));
+                long warps = (long)L.n * rows;
+                long cap = (long)sm_count * 16;
+                int blocks = (int)((warps + 3) / 4 < cap ? (warps + 3) / 4 : cap);
+                prof_begin(3);
+                const bool dig = (ctx->flags & H264R_DIGESTS) != 0;
+                k_pad<<<blocks, 128, 0, st>>>(d_desc, L, ctx->g, compat ? 0 : 1, dig ? ctx->d_digests : nullptr);
+                prof_end();
+                ctx->last_launches++;
+                if (dig) {
+                    // K5 as part of the reconstruction: frame ids of this chunk
+                    PicList F;
+                    F.n = L.n;
+                    for (int i = 0; i < L.n; i++) F.slot[i] = h_desc[L.slot[i]].frame_id;
+                    prof_begin(4);
+                    k_digest<<<dim3(DIGEST_CTAS, F.n), 256, 0, st>>>(digest_pool(ctx), F, ctx->g, ctx->d_digests);
+                    prof_end();
+                    ctx->last_launches++;
+                    for (int i = 0; i < F.n; i++) ctx->digest_valid[F.slot[i]] = 1;
+                }
+            });
+        }
     }
+    // join: the main stream (read-backs, timing, slot reuse) continues when every lane has finished this flush
+    for (int l = 0; l < NL; l++)
+        if (lane_used[l]) {
+            CU(cudaEventRecord(ctx->ev_lane[l], ctx->lane_stream[l]));
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_lane[l], 0));
+        }
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaGetLastError());
     ctx->timing_valid = true;

@@ -186,7 +186,7 @@ __device__ __forceinline__ int row_ticket(int* ticket)
 }
 
 template <bool COMPAT>
-__global__ void __launch_bounds__(ROW_WARPS * 32) k_intra_rows(const DescTable descs, const __grid_constant__ PicList list,
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_intra_rows(const DescTable descs, const __grid_constant__ PicList list,
                                                               Geometry g, int* progress, int* ticket)
 {
     __shared__ MbWork work[ROW_WARPS];
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_intra_rows(const DescTable d
     }
 }
 
-__global__ void __launch_bounds__(ROW_WARPS * 32) k_deblock_rows(const DescTable descs, const __grid_constant__ PicList list,
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_deblock_rows(const DescTable descs, const __grid_constant__ PicList list,
                                                                 Geometry g, int* progress, int* ticket)
 {
     __shared__ DeblockWork work[ROW_WARPS];

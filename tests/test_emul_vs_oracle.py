@@ -10,7 +10,7 @@ from videodecoder_b200 import workload
 
 
 @pytest.mark.parametrize("compat", [True, False])
-@pytest.mark.parametrize("seed,w,h", [(7, 8, 6), (8, 5, 3), (9, 1, 1), (10, 2, 7)])
+@pytest.mark.parametrize("seed,w,h", [(7, 8, 6), (8, 5, 3), (9, 1, 1), (10, 2, 7), (11, 1, 4), (12, 9, 1)])
 def test_gop(built, compat, seed, w, h):
     rng = np.random.default_rng(seed)
     cfg = workload.WorkloadConfig(compat=compat, num_ref=2, p_intra_in_p=0.12, mv_range=90,

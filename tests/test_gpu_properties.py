@@ -1,0 +1,256 @@
+"""GPU tests at BASELINE.json's full sizes and at the edges of the input space, through properties that do not need a
+full-size oracle run for every picture: one flush vs one flush per picture, dense vs packed vs picture-buffer
+transport, any number of lanes, determinism -- all must give identical digests -- plus direct oracle comparison on
+ragged / tiny / large geometries and on the content edge cases of the domain (all-skip pictures, vectors far
+outside the picture, every quarter-sample position, every intra mode, QP extremes, empty residual)."""
+import os
+
+import numpy as np
+import pytest
+
+from common import *  # noqa: F401,F403
+from videodecoder_b200 import engine, workload
+
+pytestmark = pytest.mark.gpu
+
+
+def run_engine(w, h, flags, gops, transport="buf", flush="all", max_frames=None):
+    """gops: list of GOPs (lists of pictures); frame ids are assigned GOP-major.  Returns (digests, planes of the last
+    picture of every GOP, excursions)."""
+    n = sum(len(g) for g in gops)
+    eng = engine.Engine(w, h, max_frames=max_frames or n, flags=flags | abi.DIGESTS)
+    bufs, fid0 = [], 0
+    order = []
+    for g in gops:
+        for i, p in enumerate(g):
+            order.append((fid0 + i, p, fid0))
+        fid0 += len(g)
+    if flush == "round":        # picture i of every GOP, then picture i + 1, ... flushed per round
+        order.sort(key=lambda t: (t[0] - t[2], t[2]))
+    last_round = None
+    for fid, p, base in order:
+        if flush == "round" and last_round is not None and fid - base != last_round:
+            eng.flush()
+        last_round = fid - base
+        pp = abi.PicParams.from_buffer_copy(p["pp"])
+        for k in range(pp.num_ref_idx_l0):
+            pp.ref_list0[k] = base + p["pp"].ref_list0[k]
+        if transport == "dense":
+            eng.submit_picture(fid, pp, p["hdr"], p["mv"], p["coeff"])
+        else:
+            mask, blocks = pack.pack_blocks(p["coeff"])
+            if transport == "packed":
+                eng.submit_picture_packed(fid, pp, np.ascontiguousarray(p["hdr"]), p["mv"], mask, blocks)
+            else:
+                b = eng.picture_buf(max(1, blocks.shape[0]))
+                b.fill(p["hdr"], p["mv"], mask, blocks, mv_partition=transport == "bufmv")
+                bufs.append(b)
+                eng.submit_picture_buf(fid, pp, b)
+        if flush == "each":
+            eng.sync()
+    eng.sync()
+    dig = eng.digests(list(range(n)))
+    lasts, k = [], 0
+    for g in gops:
+        k += len(g)
+        lasts.append(eng.read_planes(k - 1))
+    exc = eng.range_excursions()
+    for b in bufs:
+        b.free()
+    eng.close()
+    return dig, lasts, exc
+
+
+def oracle_gop(w, h, flags, gop):
+    return run_sequence(oracle.recon_picture, w, h, flags, gop)
+
+
+def check_vs_oracle(w, h, flags, gop, **kw):
+    dig, lasts, _ = run_engine(w, h, flags, [gop], **kw)
+    want = oracle_gop(w, h, flags, gop)
+    for i, o in enumerate(want):
+        assert bytes(dig[i]) == oracle.digest(o["y"], o["u"], o["v"]), "picture %d digest" % i
+    for k, pl in zip("yuv", lasts[0]):
+        assert np.array_equal(pl, want[-1][k]), "last picture plane %s" % k
+
+
+# ---- geometries ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("compat", [True, False])
+@pytest.mark.parametrize("w,h", [(1, 1), (1, 5), (7, 1), (2, 2), (33, 3), (45, 36)])
+def test_ragged_geometries(built, compat, w, h):
+    """one macroblock, single rows / columns, widths that are not multiples of the 32-macroblock scan words"""
+    rng = np.random.default_rng(w * 100 + h)
+    cfg = workload.WorkloadConfig(compat=compat, p_intra_in_p=0.15, mv_range=80, num_ref=2, p_t8x8=0.0 if compat else 0.4,
+                                  p_i8x8=0.0 if compat else 0.4, p_sub=(0.4, 0, 0.3, 0.3) if compat else (0.25, 0.25, 0.25, 0.25))
+    gop = workload.make_gop(rng, w, h, 4, cfg)
+    flags = abi.REF_COMPAT if compat else 0
+    if compat:
+        sanitize_with_oracle(w, h, gop)
+    check_vs_oracle(w, h, flags, gop, transport="bufmv")
+
+
+def test_4k_pictures_vs_oracle(built):
+    """BASELINE config 5 geometry (3840x2160 = 240x135 MBs): I + 2 P against the oracle"""
+    w, h = 240, 135
+    rng = np.random.default_rng(5)
+    cfg = workload.WorkloadConfig(compat=True)
+    gop = workload.make_gop(rng, w, h, 3, cfg)
+    sanitize_with_oracle(w, h, gop)
+    check_vs_oracle(w, h, abi.REF_COMPAT, gop, transport="bufmv")
+
+
+# ---- full-size invariants ----------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def hd_gops():
+    """BASELINE config 4 shape, shortened: 1080p, 4 GOPs x 6 pictures (content model of bench.py)"""
+    w, h = 120, 68
+    rng = np.random.default_rng(44)
+    cfg = workload.WorkloadConfig(compat=True)
+    gops = [workload.make_gop(rng, w, h, 6, cfg) for _ in range(2)]
+    for g in gops:
+        workload.sanitize(lambda n: engine.Engine(w, h, max_frames=n, flags=abi.REF_COMPAT), w, h, g)
+    return w, h, [gops[0], gops[1], gops[0], gops[1]]
+
+
+def test_1080p_transport_and_flush_invariance(built, hd_gops):
+    """dense / packed / picture-buffer transports, one flush / per picture / per round: identical digests, and the
+    first GOP equals the oracle"""
+    w, h, gops = hd_gops
+    ref, lasts, exc = run_engine(w, h, abi.REF_COMPAT, gops, transport="dense", flush="all")
+    assert exc == 0
+    for transport, flush in (("packed", "all"), ("buf", "each"), ("bufmv", "round"), ("bufmv", "all")):
+        dig, _, exc = run_engine(w, h, abi.REF_COMPAT, gops, transport=transport, flush=flush)
+        assert exc == 0
+        assert np.array_equal(dig, ref), (transport, flush)
+    want = oracle_gop(w, h, abi.REF_COMPAT, gops[0])
+    for i, o in enumerate(want):
+        assert bytes(ref[i]) == oracle.digest(o["y"], o["u"], o["v"])
+    assert np.array_equal(ref[:6], ref[12:18]) and np.array_equal(ref[6:12], ref[18:24])      # equal GOPs, equal digests
+    for k, pl in zip("yuv", lasts[0]):
+        assert np.array_equal(pl, want[-1][k])
+
+
+@pytest.mark.parametrize("lanes", ["1", "3", "8"])
+def test_1080p_lane_count_invariance(built, hd_gops, lanes):
+    w, h, gops = hd_gops
+    old = os.environ.get("H264R_LANES")
+    try:
+        os.environ["H264R_LANES"] = "4"
+        ref, _, _ = run_engine(w, h, abi.REF_COMPAT, gops, transport="bufmv", flush="round")
+        os.environ["H264R_LANES"] = lanes
+        dig, _, _ = run_engine(w, h, abi.REF_COMPAT, gops, transport="bufmv", flush="round")
+    finally:
+        if old is None:
+            os.environ.pop("H264R_LANES", None)
+        else:
+            os.environ["H264R_LANES"] = old
+    assert np.array_equal(dig, ref)
+
+
+def test_frame_slot_reuse_across_gops(built, hd_gops):
+    """a frame pool smaller than the job: slots are released and reused GOP after GOP (Decoder::ctrl_Memory's role)"""
+    w, h, gops = hd_gops
+    want, _, _ = run_engine(w, h, abi.REF_COMPAT, gops[:2], transport="bufmv")
+    eng = engine.Engine(w, h, max_frames=6, max_pending=6, flags=abi.REF_COMPAT | abi.DIGESTS)
+    got = []
+    for g in gops[:2]:
+        for i, p in enumerate(g):
+            eng.submit_picture(i, p["pp"], p["hdr"], p["mv"], p["coeff"])
+        eng.flush()
+        got.append(eng.digests(list(range(len(g)))))
+        for i in range(len(g)):
+            eng.release(i)
+    eng.close()
+    assert np.array_equal(np.concatenate(got), want)
+
+
+# ---- content edge cases ------------------------------------------------------------------------------------------
+def test_all_skip_picture_is_a_copy(built):
+    """P picture of P_Skip macroblocks with zero vectors: every plane equals the reference picture (COMPAT: luma)"""
+    w, h = 12, 9
+    rng = np.random.default_rng(8)
+    cfg = workload.WorkloadConfig(compat=True)
+    gop = workload.make_gop(rng, w, h, 2, cfg)
+    sanitize_with_oracle(w, h, gop[:1])
+    p = gop[1]
+    p["hdr"]["mb_class"] = abi.MB_P16x16
+    p["hdr"]["flags"] |= abi.SKIP
+    p["hdr"]["cbp"] = 0
+    p["hdr"]["sub_mb_type"] = 0
+    p["hdr"]["u"][:] = 0
+    p["mv"][:] = 0
+    p["coeff"][:] = 0
+    dig, lasts, exc = run_engine(w, h, abi.REF_COMPAT, [gop], transport="bufmv")
+    want = oracle_gop(w, h, abi.REF_COMPAT, gop)
+    assert exc == 0
+    assert np.array_equal(lasts[0][0], want[0]["y"]) and np.array_equal(lasts[0][0], want[1]["y"])
+
+
+@pytest.mark.parametrize("compat", [True, False])
+def test_every_fractional_position_and_far_vectors(built, compat):
+    """16x16 macroblocks sweeping all 16 quarter-sample positions, with vectors up to 300 samples outside the picture
+    (coordinate clamp of h264/macroblock.cpp:828-830 = replicated border + clamped block position)"""
+    w, h = 16, 4
+    rng = np.random.default_rng(12)
+    cfg = workload.WorkloadConfig(compat=compat, p_intra_in_p=0.0, p_skip=0.0)
+    gop = workload.make_gop(rng, w, h, 2, cfg)
+    if compat:
+        sanitize_with_oracle(w, h, gop[:1])
+    p = gop[1]
+    n = w * h
+    p["hdr"]["mb_class"] = abi.MB_P16x16
+    p["hdr"]["cbp"] = 0
+    p["hdr"]["sub_mb_type"] = 0
+    p["hdr"]["flags"] &= ~np.uint8(abi.T8x8)
+    p["hdr"]["u"][:] = 0
+    p["coeff"][:] = 0
+    far = np.array([0, 1200, -1200, 37, -41, 600, -600, 5], dtype=np.int16)
+    mv = np.zeros((n, 16, 2), dtype=np.int16)
+    for a in range(n):
+        mv[a, :, 0] = (a % 16) % 4 + 4 * far[(a // 4) % 8]
+        mv[a, :, 1] = (a % 16) // 4 + 4 * far[(a // 7) % 8]
+    p["mv"][:] = mv.reshape(n, 32)
+    check_vs_oracle(w, h, abi.REF_COMPAT if compat else 0, gop, transport="bufmv")
+
+
+@pytest.mark.parametrize("qp", [0, 1, 23, 24, 51])
+def test_qp_extremes(built, qp):
+    """both branches of the dequantisation shift (qP < 24 rounds, qP >= 24 shifts left) and the ends of the tables"""
+    w, h = 6, 4
+    rng = np.random.default_rng(qp)
+    cfg = workload.WorkloadConfig(compat=False, qp=qp, max_amp=30.0)
+    gop = workload.make_gop(rng, w, h, 3, cfg)
+    for p in gop:
+        p["hdr"]["qp_y"] = qp
+        p["hdr"]["qp_cb"] = abi.chroma_qp(p["hdr"]["qp_y"])
+        p["hdr"]["qp_cr"] = abi.chroma_qp(p["hdr"]["qp_y"])
+    check_vs_oracle(w, h, 0, gop, transport="bufmv")
+
+
+def test_empty_residual_i_picture(built):
+    """an I picture with no coefficient at all (every block absent in the packed transport)"""
+    w, h = 5, 4
+    rng = np.random.default_rng(2)
+    gop = workload.make_gop(rng, w, h, 1, workload.WorkloadConfig(compat=True))
+    gop[0]["coeff"][:] = 0
+    gop[0]["hdr"]["cbp"] = 0
+    check_vs_oracle(w, h, abi.REF_COMPAT, gop, transport="bufmv")
+
+
+def test_api_errors_on_device(built):
+    """error behaviour of the calls added for the packed transport"""
+    eng = engine.Engine(4, 3, max_frames=2, flags=abi.REF_COMPAT)
+    rng = np.random.default_rng(1)
+    gop = workload.make_gop(rng, 4, 3, 2, workload.WorkloadConfig(compat=True))
+    p = gop[0]
+    mask, blocks = pack.pack_blocks(p["coeff"])
+    eng.frame_begin(0, p["pp"])
+    with pytest.raises(engine.H264RError):      # dense after packed within one picture
+        eng.submit_mbs_packed(0, np.ascontiguousarray(p["hdr"][:6]), None, mask[:6], pack.pack_blocks(p["coeff"][:6])[1], n_mbs=6)
+        eng.submit_mbs(0, np.ascontiguousarray(p["hdr"][6:]), None, np.ascontiguousarray(p["coeff"][6:]), first_mb=6, n_mbs=6)
+    eng.close()
+    eng = engine.Engine(4, 3, max_frames=2, flags=abi.REF_COMPAT)
+    eng.frame_begin(0, p["pp"])
+    with pytest.raises(engine.H264RError):      # packed chunks out of macroblock order
+        eng.submit_mbs_packed(0, np.ascontiguousarray(p["hdr"][6:]), None, mask[6:], pack.pack_blocks(p["coeff"][6:])[1], first_mb=6, n_mbs=6)
+    eng.close()

@@ -597,16 +597,17 @@ int h264r_flush(h264r_ctx* ctx)
         return r;
     };
     // runs f(list) over the pictures of (wave, lane) selected by pred, in chunks that fit the kernel parameters
-    PicList list;
+    PicList list, list_frames;       // arena slots of a chunk, and the frame ids of the same pictures
     int cur_wave = 0, cur_lane = 0;
     auto for_chunks = [&](auto pred, auto f) {
         list.n = 0;
         for (int i = 0; i < n; i++) {
             if (run[i]->wave != cur_wave || run[i]->lane != cur_lane || !pred(*run[i])) continue;
+            list_frames.slot[list.n] = run[i]->frame_id;
             list.slot[list.n++] = run[i]->slot;
-            if (list.n == PIC_LIST_MAX) { f(list); list.n = 0; }
+            if (list.n == PIC_LIST_MAX) { list_frames.n = list.n; f(list); list.n = 0; }
         }
-        if (list.n) f(list);
+        if (list.n) { list_frames.n = list.n; f(list); }
     };
     std::vector<uint8_t> lane_used(NL, 0);
     for (int wv = 0; wv < n_waves; wv++) {
@@ -687,9 +688,7 @@ int h264r_flush(h264r_ctx* ctx)
                 ctx->last_launches++;
                 if (dig) {
                     // K5 as part of the reconstruction: frame ids of this chunk
-                    PicList F;
-                    F.n = L.n;
-                    for (int i = 0; i < L.n; i++) F.slot[i] = h_desc[L.slot[i]].frame_id;
+                    const PicList& F = list_frames;
                     prof_begin(4);
                     k_digest<<<dim3(DIGEST_CTAS, F.n), 256, 0, st>>>(digest_pool(ctx), F, ctx->g, ctx->d_digests);
                     prof_end();

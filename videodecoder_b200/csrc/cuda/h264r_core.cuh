@@ -38,10 +38,11 @@ struct Geometry {
     int w_mbs, h_mbs;
     int pitch_y, pitch_c;      // bytes per row of the luma / chroma planes
     uint32_t w_magic;          // ceil(2^32 / w_mbs): a / w_mbs = umulhi(a, w_magic) for every macroblock address a
+                               // (0 for w_mbs = 1, where the quotient is a itself)
 };
 HD Geometry make_geometry(int w_mbs, int h_mbs, int pitch_y, int pitch_c)
 {
-    return Geometry{w_mbs, h_mbs, pitch_y, pitch_c, (uint32_t)((0x100000000ull + (uint32_t)w_mbs - 1) / (uint32_t)w_mbs)};
+    return Geometry{w_mbs, h_mbs, pitch_y, pitch_c, w_mbs == 1 ? 0u : (uint32_t)((0x100000000ull + (uint32_t)w_mbs - 1) / (uint32_t)w_mbs)};
 }
 // macroblock address -> (column, row)
 HD void mb_xy(const Geometry& g, int a, int& mbx, int& mby)
@@ -51,6 +52,7 @@ HD void mb_xy(const Geometry& g, int a, int& mbx, int& mby)
 #else
     mby = (int)(((uint64_t)(uint32_t)a * g.w_magic) >> 32);
 #endif
+    if (g.w_magic == 0) mby = a;
     mbx = a - mby * g.w_mbs;
 }
 

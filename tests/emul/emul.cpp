@@ -29,6 +29,7 @@ void fill_desc(PicDesc& pd, const h264r_pic_params* pp, const h264r_mb_hdr* hdr,
     pd.mv_off = nullptr;
     pd.residual = nullptr;
     pd.nzmask = nullptr;
+    pd.tmaps = nullptr;
     for (int i = 0; i < H264R_MAX_REFS; i++) {
         pd.ref_y[i] = ref_y ? ref_y[i] : nullptr;
         pd.ref_u[i] = ref_u ? ref_u[i] : nullptr;
@@ -187,7 +188,7 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
     for (int a = 0; a < n; a++) {
         h264r_mb_hdr h = load_hdr(pd, a);
         if (is_intra(h.mb_class)) continue;
-        if (compat) seq_inter_any<true>(ex, ww, pd, g, h, a); else seq_inter_any<false>(ex, ww, pd, g, h, a);
+        if (compat) seq_inter_any<true, false>(ex, ww, pd, g, h, a); else seq_inter_any<false, false>(ex, ww, pd, g, h, a);
     }
     // as on the device: the flat kernels leave the residual of the intra macroblocks in the picture's scratch
     std::vector<int16_t> scratch((size_t)n * 384);

@@ -147,6 +147,28 @@ def test_1080p_lane_count_invariance(built, hd_gops, lanes):
     assert np.array_equal(dig, ref)
 
 
+def test_1080p_tma_window_staging(built, hd_gops):
+    """k_inter<.., TMA>: reference windows by cp.async.bulk.tensor (16-byte aligned boxes + consumer-side shift) give the
+    same pictures as load staging"""
+    w, h, gops = hd_gops
+    old = os.environ.get("H264R_TMA")
+    try:
+        os.environ["H264R_TMA"] = "0"
+        ref, _, _ = run_engine(w, h, abi.REF_COMPAT, gops, transport="bufmv")
+        os.environ["H264R_TMA"] = "1"
+        dig, _, exc = run_engine(w, h, abi.REF_COMPAT, gops, transport="bufmv")
+        assert exc == 0 and np.array_equal(dig, ref)
+        rng = np.random.default_rng(77)         # spec mode, small picture, vectors far outside, against the oracle
+        cfg = workload.WorkloadConfig(compat=False, mv_range=200, num_ref=2, p_t8x8=0.3)
+        gop = workload.make_gop(rng, 9, 5, 4, cfg)
+        check_vs_oracle(9, 5, 0, gop, transport="bufmv")
+    finally:
+        if old is None:
+            os.environ.pop("H264R_TMA", None)
+        else:
+            os.environ["H264R_TMA"] = old
+
+
 def test_frame_slot_reuse_across_gops(built, hd_gops):
     """a frame pool smaller than the job: slots are released and reused GOP after GOP (Decoder::ctrl_Memory's role)"""
     w, h, gops = hd_gops

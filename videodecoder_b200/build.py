@@ -73,7 +73,7 @@ def build_cuda(force=False):
             if os.path.exists(target):
                 return target          # GPU box without a toolkit: use the prebuilt library
             raise RuntimeError("nvcc not found and no prebuilt libh264r.so")
-        _run([nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include")] + srcs + ["-o", target, "-lcudart", "-lcuda"],
+        _run([nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include")] + srcs + ["-o", target, "-lcudart"],
              log=os.path.join(LIB, "nvcc_build.log"))
     return target
 

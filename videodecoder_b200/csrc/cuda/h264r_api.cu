@@ -1,6 +1,7 @@
 // h264r_api.cu -- the C ABI of include/h264r.h: context, device frame pool, syntax arena,
 // dependency-wave scheduler and kernel launches.  There is no CPU path: every entry point that
 // computes anything launches the sm_100a kernels of h264r_kernels.cuh.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -54,6 +55,7 @@ struct h264r_ctx {
     cudaEvent_t ev_flush[64] = {};           // ring: all kernels of flush number n are done
     uint64_t flush_seq = 0, copy_waited_seq = 0, end_seq = 0;
     std::vector<uint64_t> slot_flush_seq;   // flush that last read the slot
+    void* d_tmaps = nullptr;                // TMA tensor maps of the luma planes: [frame][2] (box 32x22, box 16x14), 128 B each
     uint32_t* d_dense_mask = nullptr;       // blk_mask / blk_off of the dense layout (shared by all dense pictures)
     uint32_t* d_dense_off = nullptr;
     bool profiling = false;
@@ -141,6 +143,7 @@ void fill_desc(h264r_ctx* c, const Pending& p, PicDesc& pd)
         pd.blk_off = reinterpret_cast<const uint32_t*>(s + c->off_boff);
     } else { pd.blk_mask = c->d_dense_mask; pd.blk_off = c->d_dense_off; }
     pd.nzmask = reinterpret_cast<uint32_t*>(s + c->off_nz);
+    pd.tmaps = c->d_tmaps;
     pd.mv_off = p.mv_partition ? reinterpret_cast<const uint32_t*>(s + c->off_mvoff) : nullptr;
     // k_residual_pics leaves the residual of the intra macroblocks here, ahead of the wavefront
     pd.residual = p.n_intra > 0 ? reinterpret_cast<int16_t*>(s + c->off_res) : nullptr;
@@ -268,6 +271,43 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     CUC(cudaEventCreate(&c->ev1));
     CUC(cudaMalloc(&c->d_frames, c->frame_bytes * max_frames));
     CUC(cudaMalloc(&c->d_digests, (size_t)max_frames * 16));
+    // TMA staging of the reference windows is implemented and parity-green, but not yet the default: without a
+    // one-macroblock-ahead prefetch its latency is exposed and it measures slower than load staging
+    if (getenv("H264R_TMA") && atoi(getenv("H264R_TMA")) != 0) {
+        // one tensor map per frame slot and window shape over the PADDED luma plane (u8, pitch x rows); k_inter issues
+        // cp.async.bulk.tensor copies of 48 x 22 (16x16 blocks) and 32 x 14 (8x8 quadrants) boxes from them
+        // the encoder is a driver entry point: resolved through the runtime so that the library itself does not link
+        // libcuda (it must load, for symbol checks, on machines without a driver)
+        typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        CUC(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+        if (!fn || qr != cudaDriverEntryPointSuccess) {
+            fail(nullptr, 0, "h264r_create: the driver does not provide cuTensorMapEncodeTiled");
+            return cleanup(H264R_E_CUDA);
+        }
+        const EncodeTiled encode = reinterpret_cast<EncodeTiled>(fn);
+        std::vector<CUtensorMap> maps((size_t)max_frames * 2);
+        const cuuint64_t dims[2] = {(cuuint64_t)c->g.pitch_y, (cuuint64_t)(h_mbs * 16 + 2 * PAD_Y)};
+        const cuuint64_t strides[1] = {(cuuint64_t)c->g.pitch_y};
+        const cuuint32_t estr[2] = {1, 1};
+        for (int f = 0; f < max_frames; f++)
+            for (int k = 0; k < 2; k++) {
+                const cuuint32_t box[2] = {k == 0 ? (cuuint32_t)TMA0_W : (cuuint32_t)TMA1_W, k == 0 ? (cuuint32_t)TMA0_H : (cuuint32_t)TMA1_H};
+                CUresult r = encode(&maps[(size_t)f * 2 + k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->d_frames + (size_t)f * c->frame_bytes,
+                                                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) {
+                    fail(nullptr, 0, "h264r_create: cuTensorMapEncodeTiled failed");
+                    return cleanup(H264R_E_CUDA);
+                }
+            }
+        static_assert(sizeof(CUtensorMap) == 128, "tensor maps are indexed as 128-byte records on the device");
+        CUC(cudaMalloc(&c->d_tmaps, maps.size() * sizeof(CUtensorMap)));
+        CUC(cudaMemcpy(c->d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    }
     c->digest_valid.assign(max_frames, 0);
     c->h_digests.assign((size_t)max_frames * 4, 0);
     CUC(cudaMalloc(&c->d_exc_maps, (size_t)max_frames * c->n_mbs));
@@ -300,7 +340,7 @@ void h264r_destroy(h264r_ctx* c)
         if (c->ev_lane[l]) cudaEventDestroy(c->ev_lane[l]);
     }
     if (c->ev_main) cudaEventDestroy(c->ev_main);
-    cudaFree(c->d_dense_mask); cudaFree(c->d_dense_off);
+    cudaFree(c->d_dense_mask); cudaFree(c->d_dense_off); cudaFree(c->d_tmaps);
     for (auto e : c->ev_copied) if (e) cudaEventDestroy(e);
     for (auto e : c->ev_flush) if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -644,8 +684,9 @@ int h264r_flush(h264r_ctx* ctx)
                 int cap = NL > 1 ? (sm_count * ctx->inter_ctas_per_sm + L.n - 1) / L.n : (sm_count * 16 * 8 + L.n - 1) / L.n;
                 dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)L.n);
                 prof_begin(0);
-                if (compat) k_inter<true><<<grid, INTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g);
-                else k_inter<false><<<grid, INTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g);
+                const bool tma = ctx->d_tmaps != nullptr;
+                if (compat) { if (tma) k_inter<true, true><<<grid, INTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); else k_inter<true, false><<<grid, INTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); }
+                else { if (tma) k_inter<false, true><<<grid, INTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); else k_inter<false, false><<<grid, INTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); }
                 prof_end();
                 ctx->last_launches++;
             });

@@ -66,6 +66,8 @@ struct PicDesc {
     const uint32_t* blk_off;   // per macroblock: index of its first stored block
     int16_t* residual;         // scratch: residual of the intra macroblocks, 384 int16 each (Y 16x16, U 8x8, V 8x8), produced
                                // by the flat kernels ahead of the intra wavefront; null = the wavefront computes it itself
+    const void* tmaps;         // device array of TMA tensor maps of the frame pool's luma planes, [frame id][2]: box 48 x 22
+                               // (16x16 blocks) and 32 x 14 (8x8 quadrants); null = windows are staged with loads
     uint32_t* nzmask;          // spec mode, per inter macroblock: bit r = 4x4 luma block r (raster) has a non-zero level
                                // (8x8 transform: the four blocks of a quadrant together); written by k_inter for K4
     uint8_t* y; uint8_t* u; uint8_t* v;

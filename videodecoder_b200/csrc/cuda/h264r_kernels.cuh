@@ -85,19 +85,24 @@ __global__ void __launch_bounds__(INTER_WARPS * 32) k_residual(PicDesc pd, int n
 // references are complete pictures), so this is a flat grid: one warp per MB, blockIdx.y = picture,
 // blockIdx.x strides over its macroblocks.
 // ------------------------------------------------------------------------------------------------
-template <bool COMPAT>
+// TMA: reference windows of 16x16 / 8x8-quadrant blocks arrive by cp.async.bulk.tensor (h264r_mc.cuh) instead of loads.
+template <bool COMPAT, bool TMA>
 __global__ void __launch_bounds__(INTER_WARPS * 32, H264R_INTER_MIN_CTAS) k_inter(const DescTable descs, const __grid_constant__ PicList list, Geometry g)
 {
     __shared__ WarpWork work[INTER_WARPS];
     int warp = threadIdx.x >> 5;
     WarpExec ex{(int)(threadIdx.x & 31)};
     WarpWork& w = work[warp];
+    if (TMA) {
+        if (ex.lane == 0) { w.tma.parity = 1u; mbar_init(&w.tma.mbar, 1); }       // first use waits for parity 0
+        __syncwarp();
+    }
     const int n_mbs = g.w_mbs * g.h_mbs;
     const PicDesc& pd = descs[list.slot[blockIdx.y]];
     for (int a = blockIdx.x * INTER_WARPS + warp; a < n_mbs; a += gridDim.x * INTER_WARPS) {
         h264r_mb_hdr h = load_hdr(pd, a);
         if (is_intra(h.mb_class)) continue;       // warp-uniform; k_intra_rows reconstructs it afterwards
-        seq_inter_any<COMPAT>(ex, w, pd, g, h, a);
+        seq_inter_any<COMPAT, TMA>(ex, w, pd, g, h, a);
     }
 }
 

@@ -141,14 +141,26 @@ HD void pad_row_phase(uint8_t* org, int pitch, int W, int H, int padx, int pady,
 }
 
 // Working set of the inter path (one per warp)
-struct alignas(16) InterWork {
-    uint32_t win[480];          // staged windows, see phase_inter_stage
+struct alignas(128) InterWork {
+    uint32_t win[512];          // staged windows, see phase_inter_stage (TMA destination: 128-byte aligned)
     int16_t res[384];           // residual
     uint8_t need[32];           // per lane: NEED_* of its block
     uint8_t nzf[16];            // spec mode: per luma block (raster) "has a non-zero level", for K4
     int32_t shape;              // 0: one 16x16 window, 1: four 8x8 windows, 2: sixteen 4x4 windows
-    uint32_t pad_[3];
 };
+static_assert(sizeof(InterWork) % 128 == 0, "TMA destinations of consecutive warps must stay 128-byte aligned");
+// mbarrier of a warp's TMA loads and the phase parity its current macroblock completes (lives next to, not inside,
+// the working sets: the generic phases reuse their memory)
+struct TmaState { unsigned long long mbar; uint32_t parity; uint32_t pad_; };
+// window layouts (words), load-staged: shape 0: 22 rows, pitch 6 (conflict-free for the 4x2 patches); shape 1: window q
+// at 56 q, 14 rows, pitch 4; shape 2: window b at 30 b, 10 rows, pitch 3
+constexpr int WIN0_PITCH = 6, WIN1_STRIDE = 56, WIN1_PITCH = 4;
+// TMA windows.  A tensor copy must start on a 16-byte boundary of the innermost dimension (measured on B200: any
+// other start coordinate raises an illegal-instruction fault), while a prediction window starts at an arbitrary byte.
+// The box is therefore widened to the enclosing 16-byte columns -- 48 x 22 bytes for a 16x16 block, 32 x 14 for an
+// 8x8 quadrant -- and the consumer applies the remaining offset: whole words through its row pointer, 0..3 bytes
+// with one funnel shift per word (mc_groups_shifted).
+constexpr int TMA0_W = 48, TMA0_H = 22, TMA0_PITCH = 12, TMA1_W = 32, TMA1_H = 14, TMA1_PITCH = 8, TMA1_STRIDE = 128;
 // 16 byte flags -> 16-bit mask
 HD uint32_t nz_pack(const uint8_t* f)
 {
@@ -295,7 +307,7 @@ HD int mc_need(int xf, int yf)
 // Items first, first + STRIDE, ... of a window of NROWS x NWORDS words whose top-left byte is (sx, sy) of the padded
 // reference plane.  A staged word = 4 bytes at any alignment = funnel shift of two aligned words; the alignment is
 // the same for every word of a window (the pitch is a multiple of 4), and the source address advances incrementally.
-template <int NROWS, int NWORDS, int STRIDE>
+template <int NROWS, int NWORDS, int STRIDE, int DPITCH>
 HD void stage_window(uint32_t* dst, const uint8_t* ref, int gpitch, int sx, int sy, int first)
 {
     constexpr int DR = STRIDE / NWORDS, DJ = STRIDE % NWORDS;       // one step = DR rows + DJ words
@@ -307,22 +319,53 @@ HD void stage_window(uint32_t* dst, const uint8_t* ref, int gpitch, int sx, int 
 #pragma unroll
     for (int i = 0; i < (NROWS * NWORDS + STRIDE - 1) / STRIDE; i++) {
         const int it = first + i * STRIDE;
-        if (it < NROWS * NWORDS) dst[it] = funnel_r(H264R_LDG(q), H264R_LDG(q + 1), sh);
+        if (it < NROWS * NWORDS) dst[DPITCH == NWORDS ? it : row * DPITCH + j] = funnel_r(H264R_LDG(q), H264R_LDG(q + 1), sh);
         q += DR * wpitch + DJ;
+        if (DPITCH != NWORDS) row += DR;
         if (DJ) {
             j += DJ;
-            if (j >= NWORDS) { j -= NWORDS; q += wpitch - NWORDS; }
+            if (j >= NWORDS) { j -= NWORDS; if (DPITCH != NWORDS) row++; q += wpitch - NWORDS; }
         }
     }
 }
+
+#if defined(__CUDACC__)
+// ---- TMA: one cp.async.bulk.tensor per window, completion on the warp's mbarrier -----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(b);
+    uint32_t done = 0;
+    for (int spin = 0; !done; spin++) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (spin > (1 << 22)) __trap();       // a load that never lands must not hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int x, int y, unsigned long long* b)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(b)) : "memory");
+}
+#endif
 
 // Phase M0: shape of the macroblock, this lane's NEED bits, and the windows.
 // Window of a bw x bh block at integer position (xb, yb): bytes xb-2 .. and rows yb-3 .. yb+bh+2
 // (the reference's j reaches row -3, D7).  Block positions are clamped to [-(bw+3), W+2] x [-(bh+3), H+3],
 // which gives every sample the value of the reference's per-sample coordinate clamp.
-template <bool COMPAT>
-HD void phase_inter_stage(InterWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane)
+template <bool COMPAT, bool TMA>
+HD void phase_inter_stage(InterWork& w, TmaState& ts, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane)
 {
+    (void)ts;
     int shape;
     if (pd.mv_off) shape = inter_shape_by_type(h);
     else {
@@ -338,17 +381,43 @@ HD void phase_inter_stage(InterWork& w, const PicDesc& pd, const Geometry& g, co
         uint32_t v = load_mv(pd, h, a, lane >> 1);
         w.need[lane] = (uint8_t)mc_need(mv_x(v) & 3, mv_y(v) & 3);
     }
+#if defined(__CUDA_ARCH__)
+    if (TMA && shape < 2) {
+        // reference-frame tiles by TMA: lane 0 posts the byte count and one tensor copy per window; every lane waits on
+        // the warp's mbarrier at the start of the compute phase.  Tensor coordinates are relative to the padded plane.
+        if (lane == 0) {
+            ts.parity ^= 1u;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the windows were last read through the generic proxy
+            const char* maps = static_cast<const char*>(pd.tmaps);
+            if (shape == 0) {
+                const uint32_t v = load_mv(pd, h, a, 0);
+                const int xb = clip3(-19, W + 2, mbx * 16 + (mv_x(v) >> 2)), yb = clip3(-19, H + 3, mby * 16 + (mv_y(v) >> 2));
+                mbar_expect_tx(&ts.mbar, (uint32_t)(TMA0_W * TMA0_H));
+                tma_load_2d(w.win, maps + ((size_t)pd.ref_id[hdr_ref_idx(h, 0)] * 2) * 128, (PAD_X + xb - 2) & ~15, PAD_Y + yb - 3, &ts.mbar);
+            } else {
+                mbar_expect_tx(&ts.mbar, (uint32_t)(4 * TMA1_W * TMA1_H));
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t v = load_mv(pd, h, a, (q >> 1) * 8 + (q & 1) * 2);
+                    const int xb = clip3(-11, W + 2, mbx * 16 + (q & 1) * 8 + (mv_x(v) >> 2)), yb = clip3(-11, H + 3, mby * 16 + (q >> 1) * 8 + (mv_y(v) >> 2));
+                    tma_load_2d(w.win + q * TMA1_STRIDE, maps + ((size_t)pd.ref_id[hdr_ref_idx(h, q)] * 2 + 1) * 128, (PAD_X + xb - 2) & ~15, PAD_Y + yb - 3, &ts.mbar);
+                }
+            }
+        }
+        return;
+    }
+#endif
     if (shape == 0) {
         const uint32_t v = load_mv(pd, h, a, 0);
         const uint8_t* ref = pd.ref_y[hdr_ref_idx(h, 0)];
         int xb = clip3(-19, W + 2, mbx * 16 + (mv_x(v) >> 2)), yb = clip3(-19, H + 3, mby * 16 + (mv_y(v) >> 2));
-        stage_window<22, 6, 32>(w.win, ref, g.pitch_y, xb - 2, yb - 3, lane);
+        stage_window<22, 6, 32, WIN0_PITCH>(w.win, ref, g.pitch_y, xb - 2, yb - 3, lane);
     } else if (shape == 1) {
         const int q = lane >> 3, b0 = (q >> 1) * 8 + (q & 1) * 2;
         const uint32_t v = load_mv(pd, h, a, b0);
         const uint8_t* ref = pd.ref_y[hdr_ref_idx(h, q)];
         int xb = clip3(-11, W + 2, mbx * 16 + (q & 1) * 8 + (mv_x(v) >> 2)), yb = clip3(-11, H + 3, mby * 16 + (q >> 1) * 8 + (mv_y(v) >> 2));
-        stage_window<14, 4, 8>(w.win + q * 56, ref, g.pitch_y, xb - 2, yb - 3, lane & 7);
+        stage_window<14, 4, 8, WIN1_PITCH>(w.win + q * WIN1_STRIDE, ref, g.pitch_y, xb - 2, yb - 3, lane & 7);
     } else {
         const int b = lane >> 1, bx = b & 3, by = b >> 2, q = (by >> 1) * 2 + (bx >> 1);
         const uint32_t v = load_mv(pd, h, a, b);
@@ -357,7 +426,7 @@ HD void phase_inter_stage(InterWork& w, const PicDesc& pd, const Geometry& g, co
         // reference's source-row offset for 4x4 sub-partitions 2 and 3 (D8, h264/macroblock.cpp:786-789)
         if (COMPAT && h.mb_class == H264R_MB_P8x8 && ((h.sub_mb_type >> (2 * q)) & 3) == H264R_SUB_4x4 && (by & 1)) ys -= 3;
         int xb = clip3(-7, W + 2, mbx * 16 + bx * 4 + (mv_x(v) >> 2)), yb = clip3(-7, H + 3, ys + (mv_y(v) >> 2));
-        stage_window<10, 3, 2>(w.win + b * 30, ref, g.pitch_y, xb - 2, yb - 3, lane & 1);
+        stage_window<10, 3, 2, 3>(w.win + b * 30, ref, g.pitch_y, xb - 2, yb - 3, lane & 1);
     }
 }
 
@@ -443,22 +512,27 @@ HD uint32_t mc_finish(const McSel& m, const McAcc& c)
     return avg_u8x4(P, Q);
 }
 
-// A[0..7] of one window row from its three words
-HD void mc_groups(const uint32_t* row, uint32_t A[8])
+// A[0..7] of one window row from its three words; SH: the row starts `sh` bits into its first word (TMA windows)
+template <bool SH>
+HD void mc_groups(const uint32_t* row, int sh, uint32_t A[8])
 {
     uint32_t w0 = row[0], w1 = row[1], w2 = row[2];
+    if (SH) {
+        const uint32_t w3 = row[3];
+        w0 = funnel_r(w0, w1, sh); w1 = funnel_r(w1, w2, sh); w2 = funnel_r(w2, w3, sh);
+    }
     A[0] = w0; A[1] = prmt(w0, w1, 0x4321); A[2] = prmt(w0, w1, 0x5432); A[3] = prmt(w0, w1, 0x6543);
     A[4] = w1; A[5] = prmt(w1, w2, 0x4321); A[6] = prmt(w1, w2, 0x5432); A[7] = prmt(w1, w2, 0x6543);
 }
 
 // the lane's 4x2 patch: wp = first of its 8 window rows (row -3 of output row 0), pitch in words
-template <bool COMPAT, int CLS>
-HD void mc_patch(const uint32_t* wp, int pitch, const McSel& m, uint32_t out[2])
+template <bool COMPAT, int CLS, bool SH>
+HD void mc_patch(const uint32_t* wp, int pitch, int sh, const McSel& m, uint32_t out[2])
 {
     McAcc c0, c1;
     uint32_t A[8];
 #define MC_ROW(RR)                                       \
-    mc_groups(wp + (RR) * pitch, A);                     \
+    mc_groups<SH>(wp + (RR) * pitch, sh, A);             \
     mc_accum<COMPAT, CLS, (RR) - 3>(A, m, c0);           \
     mc_accum<COMPAT, CLS, (RR) - 4>(A, m, c1);
     if (CLS == 0) {
@@ -495,9 +569,10 @@ HD uint32_t weight_packed(uint32_t pred, int logwd, int wgt, int off)
 
 // Phase M1: compute and store the macroblock (luma from the staged windows; chroma: COMPAT = residual
 // only, D4; spec = bilinear from the padded reference planes, ITU-T H.264 8.4.2.2.2).
-template <bool COMPAT>
-HD void phase_inter_compute(InterWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane, bool coded)
+template <bool COMPAT, bool TMA>
+HD void phase_inter_compute(InterWork& w, TmaState& ts, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane, bool coded)
 {
+    (void)ts;
     int mbx, mby;
     mb_xy(g, a, mbx, mby);
     // warp-wide union of the NEED bits
@@ -513,15 +588,39 @@ HD void phase_inter_compute(InterWork& w, const PicDesc& pd, const Geometry& g, 
     const int shape = w.shape;
     const uint32_t* wp;
     int pitch;
-    if (shape == 0) { wp = w.win + (by * 4 + half * 2) * 6 + bx; pitch = 6; }
-    else if (shape == 1) { wp = w.win + q * 56 + ((by & 1) * 4 + half * 2) * 4 + (bx & 1); pitch = 4; }
+    bool tma = false;
+    int sh = 0;
+#if defined(__CUDA_ARCH__)
+    tma = TMA && shape < 2;
+    if (tma) {
+        // where the window starts inside its 16-byte aligned box: same block position as in phase M0
+        int mbx_, mby_;
+        mb_xy(g, a, mbx_, mby_);
+        const uint32_t vw = load_mv(pd, h, a, shape == 0 ? 0 : (q >> 1) * 8 + (q & 1) * 2);
+        const int bw = shape == 0 ? 16 : 8;
+        const int xb = clip3(-(bw + 3), g.w_mbs * 16 + 2, mbx_ * 16 + (shape == 0 ? 0 : (q & 1) * 8) + (mv_x(vw) >> 2));
+        const int o = (PAD_X + xb - 2) & 15;
+        sh = (o & 3) * 8;
+        if (shape == 0) { wp = w.win + (by * 4 + half * 2) * TMA0_PITCH + (o >> 2) + bx; pitch = TMA0_PITCH; }
+        else { wp = w.win + q * TMA1_STRIDE + ((by & 1) * 4 + half * 2) * TMA1_PITCH + (o >> 2) + (bx & 1); pitch = TMA1_PITCH; }
+        mbar_wait(&ts.mbar, ts.parity);      // the windows posted in phase M0 have landed
+    } else
+#endif
+    if (shape == 0) { wp = w.win + (by * 4 + half * 2) * WIN0_PITCH + bx; pitch = WIN0_PITCH; }
+    else if (shape == 1) { wp = w.win + q * WIN1_STRIDE + ((by & 1) * 4 + half * 2) * WIN1_PITCH + (bx & 1); pitch = WIN1_PITCH; }
     else { wp = w.win + b * 30 + half * 2 * 3; pitch = 3; }
     const uint32_t v = load_mv(pd, h, a, b);
     const McSel m = mc_select(mv_x(v) & 3, mv_y(v) & 3);
     uint32_t pred[2];
-    if (wn == 0) mc_patch<COMPAT, 0>(wp, pitch, m, pred);
-    else if (!(wn & NEED_J)) mc_patch<COMPAT, 1>(wp, pitch, m, pred);
-    else mc_patch<COMPAT, 2>(wp, pitch, m, pred);
+    if (TMA && tma) {
+        if (wn == 0) mc_patch<COMPAT, 0, TMA>(wp, pitch, sh, m, pred);
+        else if (!(wn & NEED_J)) mc_patch<COMPAT, 1, TMA>(wp, pitch, sh, m, pred);
+        else mc_patch<COMPAT, 2, TMA>(wp, pitch, sh, m, pred);
+    } else {
+        if (wn == 0) mc_patch<COMPAT, 0, false>(wp, pitch, 0, m, pred);
+        else if (!(wn & NEED_J)) mc_patch<COMPAT, 1, false>(wp, pitch, 0, m, pred);
+        else mc_patch<COMPAT, 2, false>(wp, pitch, 0, m, pred);
+    }
     const int ri = hdr_ref_idx(h, q);
     if (pd.weighted_pred) {
         pred[0] = weight_packed(pred[0], pd.luma_log2_wd, pd.luma_weight[ri], pd.luma_offset[ri]);
@@ -573,17 +672,17 @@ HD void phase_inter_compute(InterWork& w, const PicDesc& pd, const Geometry& g, 
 
 // K1+K3 sequence for one inter macroblock (4x4 transform).  8x8-transform macroblocks take seq_inter_mb
 // of h264r_seq.cuh.
-template <bool COMPAT, class Exec>
-HD void seq_inter_mb_fast(Exec& ex, InterWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a)
+template <bool COMPAT, bool TMA, class Exec>
+HD void seq_inter_mb_fast(Exec& ex, InterWork& w, TmaState& ts, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a)
 {
     const bool coded = h.cbp != 0;
     ex([&](int lane) {
         if (coded) phase_residual_fast<COMPAT>(w.res, pd, h, a, lane, (!COMPAT && pd.nzmask) ? w.nzf : nullptr);
-        phase_inter_stage<COMPAT>(w, pd, g, h, a, lane);
+        phase_inter_stage<COMPAT, TMA>(w, ts, pd, g, h, a, lane);
     });
     ex([&](int lane) {
         if (!COMPAT && pd.nzmask && lane == 0) pd.nzmask[a] = coded ? nz_pack(w.nzf) : 0u;
-        phase_inter_compute<COMPAT>(w, pd, g, h, a, lane, coded);
+        phase_inter_compute<COMPAT, TMA>(w, ts, pd, g, h, a, lane, coded);
     });
 }
 

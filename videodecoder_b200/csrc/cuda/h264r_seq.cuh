@@ -71,21 +71,24 @@ HD void seq_residual_scratch(Exec& ex, MbWork& w, const PicDesc& pd, const h264r
 }
 
 // working set of a warp: the generic phases and the fast inter path never run at the same time
-union WarpWork {
-    MbWork mb;
-    InterWork in;
+struct WarpWork {
+    union {
+        MbWork mb;
+        InterWork in;
+    };
+    TmaState tma;
     HD WarpWork() {}
 };
 
 // K1 + K3 for any inter macroblock: fast path for the 4x4 transform, generic phases for the 8x8 transform.
-template <bool COMPAT, class Exec>
+template <bool COMPAT, bool TMA, class Exec>
 HD void seq_inter_any(Exec& ex, WarpWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a)
 {
     if (!COMPAT && (h.flags & H264R_T8x8)) {
         seq_inter_mb<COMPAT>(ex, w.mb, pd, g, h, a);
         return;
     }
-    seq_inter_mb_fast<COMPAT>(ex, w.in, pd, g, h, a);
+    seq_inter_mb_fast<COMPAT, TMA>(ex, w.in, w.tma, pd, g, h, a);
 }
 
 // K1 + K2: one intra macroblock (its neighbours A, B, C, D are complete)

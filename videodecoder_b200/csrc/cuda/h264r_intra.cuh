@@ -26,9 +26,9 @@ namespace h264r {
 // Hadamard (reference residual::Decode_Intra16x16, h264/residual.cpp:286-319) and bypass the scaling.
 // nz_flags (optional, 16 bytes): lane b < 16 records whether luma block b has a non-zero level, at its raster index.
 template <bool COMPAT>
-HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane, uint8_t* nz_flags)
+HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane, uint8_t* nz_flags, bool chroma_only)
 {
-    if (lane >= 24) return;
+    if (lane >= 24 || (chroma_only && lane < 16)) return;
     const BlkRef br = load_blkref(pd, a);
     const int cbp_l = h.cbp & 15, cbp_c = (h.cbp >> 4) & 3;
     const bool luma = lane < 16, i16 = h.mb_class == H264R_MB_I16x16;

@@ -145,7 +145,9 @@ struct alignas(128) InterWork {
     uint32_t win[512];          // staged windows, see phase_inter_stage (TMA destination: 128-byte aligned)
     int16_t res[384];           // residual
     uint8_t need[32];           // per lane: NEED_* of its block
-    uint8_t nzf[16];            // spec mode: per luma block (raster) "has a non-zero level", for K4
+    uint8_t nzf[32];            // spec mode: "has a non-zero level" per luma block (raster; 4x4 transform) or per (quadrant, row) of
+                                // the 8x8 transform, for K4
+    int32_t t8[4 * 72];         // 8x8 transform: the four blocks after the row pass, block q at 72 q
     int32_t shape;              // 0: one 16x16 window, 1: four 8x8 windows, 2: sixteen 4x4 windows
 };
 static_assert(sizeof(InterWork) % 128 == 0, "TMA destinations of consecutive warps must stay 128-byte aligned");
@@ -161,6 +163,18 @@ constexpr int WIN0_PITCH = 6, WIN1_STRIDE = 56, WIN1_PITCH = 4;
 // 8x8 quadrant -- and the consumer applies the remaining offset: whole words through its row pointer, 0..3 bytes
 // with one funnel shift per word (mc_groups_shifted).
 constexpr int TMA0_W = 48, TMA0_H = 22, TMA0_PITCH = 12, TMA1_W = 32, TMA1_H = 14, TMA1_PITCH = 8, TMA1_STRIDE = 128;
+// 8x8 transform: 32 (quadrant, row) flags -> 16-bit mask (the four 4x4 blocks of a quadrant share its flag)
+HD uint32_t nz_pack8(const uint8_t* f)
+{
+    const uint2* v = reinterpret_cast<const uint2*>(f);
+    uint32_t m = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint2 w = v[q];
+        if (w.x | w.y) m |= 0x33u << ((q >> 1) * 8 + (q & 1) * 2);     // raster blocks b0, b0+1, b0+4, b0+5
+    }
+    return m;
+}
 // 16 byte flags -> 16-bit mask
 HD uint32_t nz_pack(const uint8_t* f)
 {
@@ -222,7 +236,67 @@ HD void idct4_fast(const int c[16], const Dequant& q, bool dc_bypass, int r[16])
 
 // K1 for any 4x4-transform macroblock: h264r_intra.cuh
 template <bool COMPAT>
-HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane, uint8_t* nz_flags = nullptr);
+HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane, uint8_t* nz_flags = nullptr,
+                            bool chroma_only = false);
+
+// ---- K1 with the 8x8 transform (ITU-T H.264 8.5.13, flat scaling lists; the reference has no 8x8 transform) ------------
+// LevelScale8x8 / 16 for position (i, j), qP % 6 = m: six classes of positions, one byte per class and m
+HD int level_scale8_fast(int m, int i, int j)
+{
+    int k;
+    if ((i & 3) == 0 && (j & 3) == 0) k = 0;
+    else if ((i & 1) && (j & 1)) k = 1;
+    else if ((i & 3) == 2 && (j & 3) == 2) k = 2;
+    else if (((i & 3) == 0 && (j & 1)) || ((i & 1) && (j & 3) == 0)) k = 3;
+    else if (((i & 3) == 0 && (j & 3) == 2) || ((i & 3) == 2 && (j & 3) == 0)) k = 4;
+    else k = 5;
+    // normAdjust8x8 columns {20,18,32,19,25,24} {22,19,35,21,28,26} {26,23,42,24,33,31} {28,25,45,26,35,33} {32,28,51,30,40,38}
+    // {36,32,58,34,46,43} as one 64-bit word per m, class k in byte k
+    const uint64_t t = m == 0 ? 0x181913201214ull : (m == 1 ? 0x1A1C15231316ull : (m == 2 ? 0x1F21182A171Aull :
+                       (m == 3 ? 0x21231A2D191Cull : (m == 4 ? 0x26281E331C20ull : 0x2B2E223A2024ull))));
+    return 16 * (int)((t >> (8 * k)) & 255u);
+}
+// Row pass: lane (q = lane >> 3, r = lane & 7) dequantises and transforms row r of 8x8 block q into t8.
+HD void phase_residual8_rows(InterWork& w, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane)
+{
+    const int q = lane >> 3, r = lane & 7;
+    const BlkRef br = load_blkref(pd, a);
+    const int4* src = reinterpret_cast<const int4*>(blk_ptr(pd, br, q * 4 + (r >> 1)));
+    int x[8];
+    int nz = 0;
+    if (src && ((h.cbp >> q) & 1)) {
+        const int4 v = H264R_LDG(src + (r & 1));
+        const int wv[4] = {v.x, v.y, v.z, v.w};
+        const int qp = h.qp_y, s = (qp * 43) >> 8, m = qp - 6 * s;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int c0 = (int)(int16_t)(wv[k] & 0xffff), c1 = wv[k] >> 16;
+            nz |= c0 | c1;
+            const int l0 = level_scale8_fast(m, r, 2 * k), l1 = level_scale8_fast(m, r, 2 * k + 1);
+            x[2 * k] = s >= 6 ? (c0 * l0) * (1 << (s - 6)) : ((c0 * l0 + (1 << (5 - s))) >> (6 - s));
+            x[2 * k + 1] = s >= 6 ? (c1 * l1) * (1 << (s - 6)) : ((c1 * l1 + (1 << (5 - s))) >> (6 - s));
+        }
+        idct8_1d(x);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) x[k] = 0;
+    }
+    w.nzf[lane] = nz ? 1 : 0;
+    int4* dst = reinterpret_cast<int4*>(&w.t8[q * 72 + r * 8]);
+    dst[0] = int4{x[0], x[1], x[2], x[3]};
+    dst[1] = int4{x[4], x[5], x[6], x[7]};
+}
+// Column pass: lane (q, c) transforms column c of block q and writes the residual.
+HD void phase_residual8_cols(InterWork& w, int lane)
+{
+    const int q = lane >> 3, c = lane & 7;
+    int x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = w.t8[q * 72 + i * 8 + c];
+    idct8_1d(x);
+#pragma unroll
+    for (int i = 0; i < 8; i++) w.res[((q >> 1) * 8 + i) * 16 + (q & 1) * 8 + c] = (int16_t)sat16((x[i] + 32) >> 6);
+}
 
 // ---- motion vectors, window shape --------------------------------------------------------------------
 HD void load_mvs(const PicDesc& pd, int a, uint32_t mv[16])
@@ -676,12 +750,17 @@ template <bool COMPAT, bool TMA, class Exec>
 HD void seq_inter_mb_fast(Exec& ex, InterWork& w, TmaState& ts, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a)
 {
     const bool coded = h.cbp != 0;
+    const bool t8 = !COMPAT && coded && (h.flags & H264R_T8x8);        // REF_COMPAT has no 8x8 transform
     ex([&](int lane) {
-        if (coded) phase_residual_fast<COMPAT>(w.res, pd, h, a, lane, (!COMPAT && pd.nzmask) ? w.nzf : nullptr);
+        if (t8) {
+            phase_residual8_rows(w, pd, h, a, lane);
+            phase_residual_fast<COMPAT>(w.res, pd, h, a, lane, nullptr, true);
+        } else if (coded) phase_residual_fast<COMPAT>(w.res, pd, h, a, lane, (!COMPAT && pd.nzmask) ? w.nzf : nullptr);
         phase_inter_stage<COMPAT, TMA>(w, ts, pd, g, h, a, lane);
     });
+    if (t8) ex([&](int lane) { phase_residual8_cols(w, lane); });
     ex([&](int lane) {
-        if (!COMPAT && pd.nzmask && lane == 0) pd.nzmask[a] = coded ? nz_pack(w.nzf) : 0u;
+        if (!COMPAT && pd.nzmask && lane == 0) pd.nzmask[a] = !coded ? 0u : (t8 ? nz_pack8(w.nzf) : nz_pack(w.nzf));
         phase_inter_compute<COMPAT, TMA>(w, ts, pd, g, h, a, lane, coded);
     });
 }

@@ -84,10 +84,6 @@ struct WarpWork {
 template <bool COMPAT, bool TMA, class Exec>
 HD void seq_inter_any(Exec& ex, WarpWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a)
 {
-    if (!COMPAT && (h.flags & H264R_T8x8)) {
-        seq_inter_mb<COMPAT>(ex, w.mb, pd, g, h, a);
-        return;
-    }
     seq_inter_mb_fast<COMPAT, TMA>(ex, w.in, w.tma, pd, g, h, a);
 }
 

@@ -30,6 +30,7 @@ void fill_desc(PicDesc& pd, const h264r_pic_params* pp, const h264r_mb_hdr* hdr,
     pd.residual = nullptr;
     pd.nzmask = nullptr;
     pd.tmaps = nullptr;
+    pd.dbrec = nullptr;
     for (int i = 0; i < H264R_MAX_REFS; i++) {
         pd.ref_y[i] = ref_y ? ref_y[i] : nullptr;
         pd.ref_u[i] = ref_u ? ref_u[i] : nullptr;
@@ -219,13 +220,24 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
         prev = a;
     }
     if (!compat && pd.deblock_on) {
-        if (use_fast_intra) {       // the row kernel's fast path (h264r_deblock.cuh), fed as k_deblock_rows feeds it
-            static DeblockWork dw;
+        if (use_fast_intra) {       // k_deblock_prep, then the row kernel's fast path (h264r_deblock.cuh), fed as k_deblock_rows feeds it
+            std::vector<uint8_t> dbrec((size_t)n * DBREC_BYTES);
+            pd.dbrec = dbrec.data();
             for (int a = 0; a < n; a++) {
                 int mbx, mby;
                 mb_xy(g, a, mbx, mby);
                 h264r_mb_hdr h = load_hdr(pd, a), hl = mbx > 0 ? load_hdr(pd, a - 1) : h, ht = mby > 0 ? load_hdr(pd, a - w_mbs) : h;
-                seq_deblock_mb_fast(ex, dw, pd, g, h, hl, ht, pd.nzmask[a], mbx > 0 ? pd.nzmask[a - 1] : 0u, mby > 0 ? pd.nzmask[a - w_mbs] : 0u, a, mbx, mby);
+                for (int lane = 0; lane < 32; lane++)
+                    phase_deblock_prep(pd.dbrec + (size_t)a * DBREC_BYTES, pd, g, h, hl, ht, pd.nzmask[a], mbx > 0 ? pd.nzmask[a - 1] : 0u,
+                                       mby > 0 ? pd.nzmask[a - w_mbs] : 0u, a, mbx, mby, lane);
+            }
+            static DeblockWork dw;
+            static PerLane<DeblockIn> in;
+            for (int a = 0; a < n; a++) {
+                int mbx, mby;
+                mb_xy(g, a, mbx, mby);
+                for (int lane = 0; lane < 32; lane++) in(lane) = deblock_fetch(pd, g, pd.dbrec, a, mbx, mby, lane);
+                seq_deblock_mb_fast(ex, dw, pd, g, in, mbx > 0, mbx, mby);
             }
         } else
             for (int a = 0; a < n; a++) seq_deblock_mb(ex, w, pd, g, a);

@@ -76,7 +76,7 @@ struct h264r_ctx {
     // arena slot = what the uploads carry, in this order: descriptor | hdr | blk_mask | mv | coefficient blocks;
     // then blk_off and mv_off (written by k_blk_scan, never uploaded)
     // then the residual scratch of the intra macroblocks (device only)
-    size_t slot_bytes = 0, off_hdr = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_mvoff = 0, off_coeff = 0, off_res = 0, off_nz = 0;
+    size_t slot_bytes = 0, off_hdr = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_mvoff = 0, off_coeff = 0, off_res = 0, off_nz = 0, off_dbrec = 0;
     // per-flush control block (descriptors + picture lists), pinned host mirror + device copy
     uint8_t* h_ctrl = nullptr;
     size_t ctrl_bytes = 0;
@@ -143,6 +143,7 @@ void fill_desc(h264r_ctx* c, const Pending& p, PicDesc& pd)
         pd.blk_off = reinterpret_cast<const uint32_t*>(s + c->off_boff);
     } else { pd.blk_mask = c->d_dense_mask; pd.blk_off = c->d_dense_off; }
     pd.nzmask = reinterpret_cast<uint32_t*>(s + c->off_nz);
+    pd.dbrec = s + c->off_dbrec;
     pd.tmaps = c->d_tmaps;
     pd.mv_off = p.mv_partition ? reinterpret_cast<const uint32_t*>(s + c->off_mvoff) : nullptr;
     // k_residual_pics leaves the residual of the intra macroblocks here, ahead of the wavefront
@@ -229,7 +230,8 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     c->off_mvoff = c->off_boff + align_up((size_t)c->n_mbs * 4, 256);
     c->off_res = c->off_mvoff + align_up((size_t)c->n_mbs * 4, 256);
     c->off_nz = c->off_res + align_up((size_t)c->n_mbs * 768, 256);
-    c->slot_bytes = c->off_nz + align_up((size_t)c->n_mbs * 4, 256);
+    c->off_dbrec = c->off_nz + align_up((size_t)c->n_mbs * 4, 256);
+    c->slot_bytes = c->off_dbrec + ((flags & H264R_REF_COMPAT) ? 0 : align_up((size_t)c->n_mbs * DBREC_BYTES, 256));
     c->ctrl_bytes = align_up((size_t)max_pending * sizeof(PicDesc), 256);      // descriptor table, one entry per arena slot
     auto cleanup = [&](int code) { h264r_destroy(c); return code; };
 #define CUC(call)                                                                                             \
@@ -709,6 +711,14 @@ int h264r_flush(h264r_ctx* ctx)
                 ctx->last_launches++;
             });
             for_chunks([&](const Pending& p) { return h_desc[p.slot].deblock_on != 0; }, [&](const PicList& L) {
+                {
+                    int want = (ctx->n_mbs + 3) / 4;
+                    int cap = (sm_count * 16 * 4 + L.n - 1) / L.n;
+                    prof_begin(2);
+                    k_deblock_prep<<<dim3((unsigned)(want < cap ? want : cap), (unsigned)L.n), 128, 0, st>>>(d_desc, L, ctx->g);
+                    prof_end();
+                    ctx->last_launches++;
+                }
                 int rows = L.n * ctx->g.h_mbs, blocks = (rows + ROW_WARPS - 1) / ROW_WARPS;
                 int* sync = sync_region((size_t)rows + 1);
                 prof_begin(2);

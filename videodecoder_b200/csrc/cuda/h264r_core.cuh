@@ -68,6 +68,8 @@ struct PicDesc {
                                // by the flat kernels ahead of the intra wavefront; null = the wavefront computes it itself
     const void* tmaps;         // device array of TMA tensor maps of the frame pool's luma planes, [frame id][2]: box 48 x 22
                                // (16x16 blocks) and 32 x 14 (8x8 quadrants); null = windows are staged with loads
+    uint8_t* dbrec;            // spec mode: K4 records (boundary strengths + filter parameters), DBREC_BYTES per macroblock,
+                               // written by k_deblock_prep
     uint32_t* nzmask;          // spec mode, per inter macroblock: bit r = 4x4 luma block r (raster) has a non-zero level
                                // (8x8 transform: the four blocks of a quadrant together); written by k_inter for K4
     uint8_t* y; uint8_t* u; uint8_t* v;

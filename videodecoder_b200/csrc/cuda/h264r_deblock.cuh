@@ -15,27 +15,33 @@
 //   * a direction whose 16 strengths are all zero is skipped by the whole warp.
 // Per-lane phases only (cross-lane traffic through shared memory): the host emulator runs this code too.
 #pragma once
-#include "h264r_mc.cuh"
+#include "h264r_intra.cuh"
 
 namespace h264r {
+
+// Per-macroblock record written by the flat kernel k_deblock_prep (nothing in it depends on sample values):
+//   bytes 0..31                              bs[dir*16 + edge*4 + k]                                   (8.7.2.1)
+//   bytes 32 + 8*((plane*2 + dir)*2 + kind)  alpha, beta, tc0 for bS 1, 2, 3 of that plane / direction  (8.7.2.2)
+//                                            kind 0 = the macroblock edge (QP averaged with the neighbour), 1 = inner edges
+constexpr int DBREC_BYTES = 128;
 
 // luma tile: sample (x, y), x = -4..15, y = -4..15; chroma tiles: x = -4..7 (only -2.. used), y = -2..7
 constexpr int DB_P = 32, DB_X0 = 16, DBC_P = 16, DBC_X0 = 8;
 struct alignas(16) DeblockWork {
     uint8_t tile[20 * DB_P];
     uint8_t ctile[2][10 * DBC_P];
-    uint8_t bs[32];             // [dir][edge][k]
+    uint8_t rec[DBREC_BYTES];
 };
 #define DBT(x, y) w.tile[((y) + 4) * DB_P + (x) + DB_X0]
 #define DBC(p, x, y) w.ctile[p][((y) + 2) * DBC_P + (x) + DBC_X0]
 
 HD bool nz_bit(uint32_t nz, int ras) { return (nz >> ras) & 1u; }
 
-// Phase D0: boundary strengths (lane = dir*16 + edge*4 + k, ITU-T H.264 8.7.2.1) and the rows above the
-// macroblock into the tiles (lanes 0..3 luma rows -4..-1, lanes 4..7 chroma rows -2..-1).
-// h / hl / ht: headers of the macroblock, its left and its upper neighbour; nz*: their non-zero masks.
-HD void phase_deblock_bs_fast(DeblockWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, const h264r_mb_hdr& hl,
-                              const h264r_mb_hdr& ht, uint32_t nz, uint32_t nzl, uint32_t nzt, int a, int mbx, int mby, int lane)
+// K4 preparation, one warp per macroblock: boundary strengths (lane = dir*16 + edge*4 + k, ITU-T H.264 8.7.2.1) and the
+// filter parameters (lanes 0..11) into the macroblock's record.  h / hl / ht: headers of the macroblock, its left and
+// its upper neighbour; nz*: their non-zero masks (PicDesc::nzmask).
+HD void phase_deblock_prep(uint8_t* rec, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, const h264r_mb_hdr& hl,
+                           const h264r_mb_hdr& ht, uint32_t nz, uint32_t nzl, uint32_t nzt, int a, int mbx, int mby, int lane)
 {
     const int dir = lane >> 4, e = (lane >> 2) & 3, k = lane & 3;
     const bool t8 = (h.flags & H264R_T8x8) != 0;
@@ -70,114 +76,152 @@ HD void phase_deblock_bs_fast(DeblockWork& w, const PicDesc& pd, const Geometry&
             }
         }
     }
-    w.bs[lane] = (uint8_t)bs;
-    if (mby > 0) {
-        if (lane < 4) {
-            const int r = lane - 4;
-            *reinterpret_cast<uint4*>(&DBT(0, r)) = H264R_LDCG(reinterpret_cast<const uint4*>(pd.y + (ptrdiff_t)(mby * 16 + r) * g.pitch_y + mbx * 16));
-        } else if (lane < 8) {
-            const int p = (lane - 4) >> 1, r = ((lane - 4) & 1) - 2;
-            const uint8_t* c = p ? pd.v : pd.u;
-            *reinterpret_cast<uint2*>(&DBC(p, 0, r)) = H264R_LDCG(reinterpret_cast<const uint2*>(c + (ptrdiff_t)(mby * 8 + r) * g.pitch_c + mbx * 8));
-        }
+    rec[lane] = (uint8_t)bs;
+    if (lane < 12) {
+        const int pl = lane >> 2, d = (lane >> 1) & 1, kind = lane & 1;
+        const h264r_mb_hdr hq = d == 0 ? hl : ht;
+        const int qp_q = pl == 0 ? h.qp_y : (pl == 1 ? h.qp_cb : h.qp_cr), qp_n = pl == 0 ? hq.qp_y : (pl == 1 ? hq.qp_cb : hq.qp_cr);
+        const int qpav = kind == 0 ? (qp_q + qp_n + 1) >> 1 : qp_q;
+        const DeblockTables& T = deblock_tables();
+        const int ia = clip3(0, 51, qpav + pd.alpha_off), ib = clip3(0, 51, qpav + pd.beta_off);
+        uint8_t* o = rec + 32 + 8 * lane;
+        o[0] = T.alpha[ia]; o[1] = T.beta[ib]; o[2] = T.tc0[ia][0]; o[3] = T.tc0[ia][1]; o[4] = T.tc0[ia][2]; o[5] = 0; o[6] = 0; o[7] = 0;
     }
 }
 
-// alpha, beta, tc0 of one edge (8.7.2.2): qp = average QP of the two sides
-struct DbParams { int alpha, beta, tc0; };
-HD DbParams db_params(const PicDesc& pd, int qpav, int bs)
+// One line across one edge, luma or chroma (chromaEdgeFlag): ITU-T H.264 8.7.2.3 (bS < 4) and 8.7.2.4 (bS = 4).
+// p[0..7] = p3 p2 p1 p0 q0 q1 q2 q3.  Same arithmetic as deblock_luma_line / deblock_chroma_line of h264r_core.cuh.
+HD void deblock_line(int* p, int bs, int alpha, int beta, int tc0, bool chroma)
 {
-    const DeblockTables& T = deblock_tables();
-    const int ia = clip3(0, 51, qpav + pd.alpha_off), ib = clip3(0, 51, qpav + pd.beta_off);
-    return DbParams{T.alpha[ia], T.beta[ib], bs < 4 ? T.tc0[ia][bs > 0 ? bs - 1 : 0] : 0};
+    const int P2 = p[1], P1 = p[2], P0 = p[3], Q0 = p[4], Q1 = p[5], Q2 = p[6];
+    if (!(iabs(P0 - Q0) < alpha && iabs(P1 - P0) < beta && iabs(Q1 - Q0) < beta)) return;
+    const bool apb = !chroma && iabs(P2 - P0) < beta, aqb = !chroma && iabs(Q2 - Q0) < beta;
+    if (bs < 4) {
+        const int tc = tc0 + (chroma ? 1 : (int)apb + (int)aqb);
+        const int delta = clip3(-tc, tc, (((Q0 - P0) * 4) + (P1 - Q1) + 4) >> 3);
+        p[3] = clip1(P0 + delta); p[4] = clip1(Q0 - delta);
+        if (apb) p[2] = P1 + clip3(-tc0, tc0, (P2 + ((P0 + Q0 + 1) >> 1) - (P1 * 2)) >> 1);
+        if (aqb) p[5] = Q1 + clip3(-tc0, tc0, (Q2 + ((P0 + Q0 + 1) >> 1) - (Q1 * 2)) >> 1);
+    } else {
+        const bool small = iabs(P0 - Q0) < ((alpha >> 2) + 2);
+        if (apb && small) {
+            p[3] = (P2 + 2 * P1 + 2 * P0 + 2 * Q0 + Q1 + 4) >> 3;
+            p[2] = (P2 + P1 + P0 + Q0 + 2) >> 2;
+            p[1] = (2 * p[0] + 3 * P2 + P1 + P0 + Q0 + 4) >> 3;
+        } else p[3] = (2 * P1 + P0 + Q1 + 2) >> 2;
+        if (aqb && small) {
+            p[4] = (P1 + 2 * P0 + 2 * Q0 + 2 * Q1 + Q2 + 4) >> 3;
+            p[5] = (P0 + Q0 + Q1 + Q2 + 2) >> 2;
+            p[6] = (2 * p[7] + 3 * Q2 + Q1 + Q0 + P0 + 4) >> 3;
+        } else p[4] = (2 * Q1 + Q0 + P1 + 2) >> 2;
+    }
 }
-
-// the edges of one luma line held in s[0..19] (positions -4..15 along the filtering direction); bs4[e] = strength
-// of edge e for this line; qp_n = QP'Y of the neighbouring macroblock across edge 0
-HD void deblock_luma_line4(int s[20], const uint8_t bs4[4], const PicDesc& pd, int qp, int qp_n)
+// The edges of one line in edge order.  s[0..19] = positions -4..15 along the filtering direction; a chroma line sits
+// in the same array with its two edges where luma edges 0 and 2 are (positions -2..1 at s[2..5], 2..5 at s[10..13]), so
+// that both kinds of lines run the same instruction stream.  k = which of the four strength columns the line uses.
+HD void deblock_line_edges(int s[20], const uint8_t* rec, int dir, int k, int plane)
 {
+    const bool chroma = plane != 0;
+    // everything the four edges need, fetched up front (independent loads), then the edges in order
+    int bs[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) bs[e] = (chroma && (e & 1)) ? 0 : rec[dir * 16 + e * 4 + k];
+    const uint2 pm = *reinterpret_cast<const uint2*>(rec + 32 + 8 * ((plane * 2 + dir) * 2));          // macroblock edge
+    const uint2 pi = *reinterpret_cast<const uint2*>(rec + 32 + 8 * ((plane * 2 + dir) * 2 + 1));      // inner edges
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-        const int bs = bs4[e];
-        if (!bs) continue;
-        const DbParams P = db_params(pd, e == 0 ? (qp + qp_n + 1) >> 1 : qp, bs);
-        int* p = s + e * 4;         // p[0..3] = p3..p0, p[4..7] = q0..q3
-        deblock_luma_line(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], bs, P.alpha, P.beta, P.tc0);
-    }
-}
-// chroma: positions -2..7 in s[0..9], edges at 0 (s[2]) and 4 (s[6])
-HD void deblock_chroma_line2(int s[10], int bs0, int bs2, const PicDesc& pd, int qp, int qp_n)
-{
-    if (bs0) {
-        const DbParams P = db_params(pd, (qp + qp_n + 1) >> 1, bs0);
-        deblock_chroma_line(s[0], s[1], s[2], s[3], bs0, P.alpha, P.beta, P.tc0);
-    }
-    if (bs2) {
-        const DbParams P = db_params(pd, qp, bs2);
-        deblock_chroma_line(s[4], s[5], s[6], s[7], bs2, P.alpha, P.beta, P.tc0);
+        if (!bs[e]) continue;
+        const uint2 par = e == 0 ? pm : pi;
+        const int alpha = (int)(par.x & 255u), beta = (int)((par.x >> 8) & 255u);
+        const int tc0 = bs[e] == 1 ? (int)((par.x >> 16) & 255u) : (bs[e] == 2 ? (int)(par.x >> 24) : (bs[e] == 3 ? (int)(par.y & 255u) : 0));
+        deblock_line(s + e * 4, bs[e], alpha, beta, tc0, chroma);
     }
 }
 HD void unpack4(uint32_t v, int* d) { d[0] = (int)(v & 255u); d[1] = (int)((v >> 8) & 255u); d[2] = (int)((v >> 16) & 255u); d[3] = (int)(v >> 24); }
 HD uint32_t pack4(const int* s) { return (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24); }
 
-// Phase D1: vertical edges.  Lanes 0..15: luma row `lane` straight from the frame (x = -4..15), filtered in
-// registers, into the tile.  Lanes 16..31: chroma plane (lane-16)>>3, row (lane-16)&7 (x = -2..7).
-HD void phase_deblock_vert(DeblockWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, const h264r_mb_hdr& hl, int mbx, int mby,
-                           int lane)
+// Phase D0: the macroblock's record into shared memory (rec4: lane < 8 holds 16 bytes of it) and the carry: the last
+// four columns of the macroblock this warp has just filtered are the left neighbour's columns -4..-1.
+HD void phase_deblock_stage(DeblockWork& w, uint4 rec4, bool carry, int lane)
 {
-    if (lane < 16) {
-        const uint8_t* row = pd.y + (ptrdiff_t)(mby * 16 + lane) * g.pitch_y + mbx * 16;
-        const uint4 v = H264R_LDCG(reinterpret_cast<const uint4*>(row));
-        const uint32_t vl = mbx > 0 ? H264R_LDCG(reinterpret_cast<const uint32_t*>(row - 4)) : 0u;
-        int s[20];
-        unpack4(vl, s); unpack4(v.x, s + 4); unpack4(v.y, s + 8); unpack4(v.z, s + 12); unpack4(v.w, s + 16);
-        uint8_t bs4[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) bs4[e] = w.bs[e * 4 + (lane >> 2)];
-        deblock_luma_line4(s, bs4, pd, h.qp_y, hl.qp_y);
-        *reinterpret_cast<uint32_t*>(&DBT(-4, lane)) = pack4(s);
-        *reinterpret_cast<uint4*>(&DBT(0, lane)) = uint4{pack4(s + 4), pack4(s + 8), pack4(s + 12), pack4(s + 16)};
-    } else {
-        const int p = (lane - 16) >> 3, r = (lane - 16) & 7;
-        const uint8_t* row = (p ? pd.v : pd.u) + (ptrdiff_t)(mby * 8 + r) * g.pitch_c + mbx * 8;
-        const uint2 v = H264R_LDCG(reinterpret_cast<const uint2*>(row));
-        const uint32_t vl = mbx > 0 ? H264R_LDCG(reinterpret_cast<const uint32_t*>(row - 4)) : 0u;
-        int t[4], s[10];
-        unpack4(vl, t); s[0] = t[2]; s[1] = t[3];
-        unpack4(v.x, s + 2); unpack4(v.y, s + 6);
-        deblock_chroma_line2(s, w.bs[r >> 1], w.bs[8 + (r >> 1)], pd, p ? h.qp_cr : h.qp_cb, p ? hl.qp_cr : hl.qp_cb);
-        t[2] = s[0]; t[3] = s[1];
-        *reinterpret_cast<uint32_t*>(&DBC(p, -4, r)) = pack4(t);
-        *reinterpret_cast<uint2*>(&DBC(p, 0, r)) = uint2{pack4(s + 2), pack4(s + 6)};
+    if (lane < 8) *reinterpret_cast<uint4*>(&w.rec[lane * 16]) = rec4;
+    if (carry) {
+        if (lane < 16) *reinterpret_cast<uint32_t*>(&DBT(-4, lane)) = *reinterpret_cast<const uint32_t*>(&DBT(12, lane));
+        else { const int p = (lane - 16) >> 3, r = (lane - 16) & 7; *reinterpret_cast<uint32_t*>(&DBC(p, -4, r)) = *reinterpret_cast<const uint32_t*>(&DBC(p, 4, r)); }
     }
 }
 
-// Phase D2: horizontal edges.  Lanes 0..15: luma column `lane` (y = -4..15) out of the tile, filtered in
-// registers, rows -3..15 back.  Lanes 16..31: chroma column.
-HD void phase_deblock_horz(DeblockWork& w, const PicDesc& pd, const h264r_mb_hdr& h, const h264r_mb_hdr& ht, int lane)
+// Phase D1: vertical edges.  Lanes 0..15: luma row `lane` (own samples in own_y, the four to the left from the
+// carry), lanes 16..31: chroma plane (lane-16)>>3, row (lane-16)&7 (own samples in own_c) -- filtered in registers,
+// into the tiles.  Lanes 0..7 also fetch the rows above the macroblock for phase D2; their latency hides behind the
+// filtering.  any: some strength of the macroblock is non-zero (otherwise the tiles are just filled).
+HD void phase_deblock_vert(DeblockWork& w, const PicDesc& pd, const Geometry& g, uint4 own_y, uint2 own_c, bool any, int mbx, int mby, int lane)
 {
-    if (lane < 16) {
-        uint8_t bs4[4];
-        int any = 0;
-#pragma unroll
-        for (int e = 0; e < 4; e++) { bs4[e] = w.bs[16 + e * 4 + (lane >> 2)]; any |= bs4[e]; }
-        if (!any) return;
-        int s[20];
-#pragma unroll
-        for (int i = 0; i < 20; i++) s[i] = DBT(lane, i - 4);
-        deblock_luma_line4(s, bs4, pd, h.qp_y, ht.qp_y);
-#pragma unroll
-        for (int i = 1; i < 20; i++) DBT(lane, i - 4) = (uint8_t)s[i];
+    uint4 top = uint4{0, 0, 0, 0};
+    if (any && mby > 0 && lane < 8) {
+        if (lane < 4) top = H264R_LDCG(reinterpret_cast<const uint4*>(pd.y + (ptrdiff_t)(mby * 16 + lane - 4) * g.pitch_y + mbx * 16));
+        else {
+            const int p = (lane - 4) >> 1, r = ((lane - 4) & 1) - 2;
+            const uint2 t2 = H264R_LDCG(reinterpret_cast<const uint2*>((p ? pd.v : pd.u) + (ptrdiff_t)(mby * 8 + r) * g.pitch_c + mbx * 8));
+            top.x = t2.x; top.y = t2.y;
+        }
+    }
+    // the line into s[20] (luma: positions -4..15; chroma: see deblock_line_edges), ONE filter call for both kinds of
+    // lanes, then back
+    const bool luma = lane < 16;
+    const int p = luma ? 0 : (lane - 16) >> 3, r = luma ? lane : (lane - 16) & 7;
+    int s[20], t[4], c[8];
+    if (luma) {
+        unpack4(*reinterpret_cast<const uint32_t*>(&DBT(-4, r)), s);
+        unpack4(own_y.x, s + 4); unpack4(own_y.y, s + 8); unpack4(own_y.z, s + 12); unpack4(own_y.w, s + 16);
     } else {
-        const int p = (lane - 16) >> 3, c = (lane - 16) & 7;
-        const int bs0 = w.bs[16 + (c >> 1)], bs2 = w.bs[16 + 8 + (c >> 1)];
-        if (!(bs0 | bs2)) return;
-        int s[10];
+        unpack4(*reinterpret_cast<const uint32_t*>(&DBC(p, -4, r)), t);
+        unpack4(own_c.x, c); unpack4(own_c.y, c + 4);
 #pragma unroll
-        for (int i = 0; i < 10; i++) s[i] = DBC(p, c, i - 2);
-        deblock_chroma_line2(s, bs0, bs2, pd, p ? h.qp_cr : h.qp_cb, p ? ht.qp_cr : ht.qp_cb);
+        for (int i = 0; i < 20; i++) s[i] = 0;
+        s[2] = t[2]; s[3] = t[3]; s[4] = c[0]; s[5] = c[1]; s[10] = c[2]; s[11] = c[3]; s[12] = c[4]; s[13] = c[5];
+    }
+    if (any) deblock_line_edges(s, w.rec, 0, luma ? r >> 2 : r >> 1, luma ? 0 : 1 + p);
+    if (luma) {
+        *reinterpret_cast<uint32_t*>(&DBT(-4, r)) = pack4(s);
+        *reinterpret_cast<uint4*>(&DBT(0, r)) = uint4{pack4(s + 4), pack4(s + 8), pack4(s + 12), pack4(s + 16)};
+    } else {
+        t[2] = s[2]; t[3] = s[3]; c[0] = s[4]; c[1] = s[5]; c[2] = s[10]; c[3] = s[11]; c[4] = s[12]; c[5] = s[13];
+        *reinterpret_cast<uint32_t*>(&DBC(p, -4, r)) = pack4(t);
+        *reinterpret_cast<uint2*>(&DBC(p, 0, r)) = uint2{pack4(c), pack4(c + 4)};
+    }
+    if (any && mby > 0 && lane < 8) {
+        if (lane < 4) *reinterpret_cast<uint4*>(&DBT(0, lane - 4)) = top;
+        else { const int pt = (lane - 4) >> 1, rt = ((lane - 4) & 1) - 2; *reinterpret_cast<uint2*>(&DBC(pt, 0, rt)) = uint2{top.x, top.y}; }
+    }
+}
+
+// Phase D2: horizontal edges.  Lanes 0..15: luma column `lane` (y = -4..15) out of the tile, filtered in registers,
+// rows -3..15 back.  Lanes 16..31: chroma column (y = -2..5; p0 / q0 of its two edges back).
+HD void phase_deblock_horz(DeblockWork& w, int lane)
+{
+    const bool luma = lane < 16;
+    const int p = luma ? 0 : (lane - 16) >> 3, c = luma ? lane : (lane - 16) & 7, k = luma ? c >> 2 : c >> 1;
+    uint32_t anyb = 0;
 #pragma unroll
-        for (int i = 1; i < 10; i++) DBC(p, c, i - 2) = (uint8_t)s[i];
+    for (int e = 0; e < 4; e++) anyb |= w.rec[16 + e * 4 + k];
+    if (!anyb) return;
+    int s[20];
+    if (luma) {
+#pragma unroll
+        for (int i = 0; i < 20; i++) s[i] = DBT(c, i - 4);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 20; i++) s[i] = 0;
+        s[2] = DBC(p, c, -2); s[3] = DBC(p, c, -1); s[4] = DBC(p, c, 0); s[5] = DBC(p, c, 1);
+        s[10] = DBC(p, c, 2); s[11] = DBC(p, c, 3); s[12] = DBC(p, c, 4); s[13] = DBC(p, c, 5);
+    }
+    deblock_line_edges(s, w.rec, 1, k, luma ? 0 : 1 + p);
+    if (luma) {
+#pragma unroll
+        for (int i = 1; i < 20; i++) DBT(c, i - 4) = (uint8_t)s[i];
+    } else {
+        DBC(p, c, -1) = (uint8_t)s[3]; DBC(p, c, 0) = (uint8_t)s[4]; DBC(p, c, 3) = (uint8_t)s[11]; DBC(p, c, 4) = (uint8_t)s[12];
     }
 }
 
@@ -205,14 +249,34 @@ HD void phase_deblock_store_fast(const DeblockWork& w, const PicDesc& pd, const 
 #undef DBT
 #undef DBC
 
-// K4 for one macroblock: its neighbours A, B, C are completely filtered.  hl / ht / nz*: see phase_deblock_bs_fast.
-template <class Exec>
-HD void seq_deblock_mb_fast(Exec& ex, DeblockWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, const h264r_mb_hdr& hl,
-                            const h264r_mb_hdr& ht, uint32_t nz, uint32_t nzl, uint32_t nzt, int a, int mbx, int mby)
+// K4 for one macroblock: its neighbours A, B, C are completely filtered.  rec4 / own_y / own_c: the macroblock's record
+// and its own (unfiltered) samples, fetched by the caller before it waited for the neighbours; carry: the warp's tiles
+// still hold the macroblock to the left.
+struct DeblockIn { uint4 rec4, own_y; uint2 own_c; };
+// what lane `lane` fetches for macroblock (mbx, mby): 16 bytes of the record (lanes 0..7), its luma row (lanes 0..15) or
+// its chroma row (lanes 16..31).  None of it depends on the neighbours' filtering.
+HD DeblockIn deblock_fetch(const PicDesc& pd, const Geometry& g, const uint8_t* dbrec, int a, int mbx, int mby, int lane)
 {
-    ex([&](int lane) { phase_deblock_bs_fast(w, pd, g, h, hl, ht, nz, nzl, nzt, a, mbx, mby, lane); });
-    ex([&](int lane) { phase_deblock_vert(w, pd, g, h, hl, mbx, mby, lane); });
-    ex([&](int lane) { phase_deblock_horz(w, pd, h, ht, lane); });
+    DeblockIn in;
+    in.rec4 = uint4{0, 0, 0, 0}; in.own_y = uint4{0, 0, 0, 0}; in.own_c = uint2{0, 0};
+    if (lane < 8) in.rec4 = H264R_LDG(reinterpret_cast<const uint4*>(dbrec + (size_t)a * DBREC_BYTES) + lane);
+    if (lane < 16) in.own_y = H264R_LDG(reinterpret_cast<const uint4*>(pd.y + (ptrdiff_t)(mby * 16 + lane) * g.pitch_y + mbx * 16));
+    else {
+        const int p = (lane - 16) >> 3, r = (lane - 16) & 7;
+        in.own_c = H264R_LDG(reinterpret_cast<const uint2*>((p ? pd.v : pd.u) + (ptrdiff_t)(mby * 8 + r) * g.pitch_c + mbx * 8));
+    }
+    return in;
+}
+template <class Exec>
+HD void seq_deblock_mb_fast(Exec& ex, DeblockWork& w, const PicDesc& pd, const Geometry& g, PerLane<DeblockIn>& in, bool carry, int mbx, int mby)
+{
+    ex([&](int lane) { phase_deblock_stage(w, in(lane).rec4, carry, lane); });
+    // every lane sees the same record: warp-uniform
+    uint32_t any = 0;
+    for (int i = 0; i < 8; i++) any |= reinterpret_cast<const uint32_t*>(w.rec)[i];
+    ex([&](int lane) { phase_deblock_vert(w, pd, g, in(lane).own_y, in(lane).own_c, any != 0, mbx, mby, lane); });
+    if (!any) return;
+    ex([&](int lane) { phase_deblock_horz(w, lane); });
     ex([&](int lane) { phase_deblock_store_fast(w, pd, g, mbx, mby, lane); });
 }
 

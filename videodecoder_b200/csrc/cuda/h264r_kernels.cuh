@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_intra_rows(const DescTabl
 }
 
 __global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_deblock_rows(const DescTable descs, const __grid_constant__ PicList list,
-                                                                Geometry g, int* progress, int* ticket)
+                                                                   Geometry g, int* progress, int* ticket)
 {
     __shared__ DeblockWork work[ROW_WARPS];
     const int W = g.w_mbs, H = g.h_mbs;
@@ -285,28 +285,37 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_deblock_rows(const DescTa
     const PicDesc& pd = descs[list.slot[p]];
     int* prog = progress + (size_t)p * H;
     DeblockWork& w = work[warp];
-    // headers and non-zero masks of the macroblock, its upper neighbour (prefetched one macroblock ahead) and its left
-    // neighbour (= the previous macroblock of this warp)
-    auto hdr_at = [&](int a) { int4 raw = __ldg(reinterpret_cast<const int4*>(pd.hdr + a)); return *reinterpret_cast<h264r_mb_hdr*>(&raw); };
-    h264r_mb_hdr h = hdr_at(row * W), ht = row > 0 ? hdr_at((row - 1) * W) : h, hl = h;
-    uint32_t nz = pd.nzmask[row * W], nzt = row > 0 ? pd.nzmask[(row - 1) * W] : 0u, nzl = 0u;
+    PerLane<DeblockIn> in;
+    // the macroblock's record and its own samples do not depend on the neighbours: fetched one macroblock ahead
+    DeblockIn next = deblock_fetch(pd, g, pd.dbrec, row * W, 0, row, ex.lane);
     for (int x = 0; x < W; x++) {
         const int a = row * W + x;
-        h264r_mb_hdr h_next = h, ht_next = ht;
-        uint32_t nz_next = 0u, nzt_next = 0u;
-        if (x + 1 < W) {
-            h_next = hdr_at(a + 1); nz_next = pd.nzmask[a + 1];
-            if (row > 0) { ht_next = hdr_at(a + 1 - W); nzt_next = pd.nzmask[a + 1 - W]; }
-        }
+        in(ex.lane) = next;
+        if (x + 1 < W) next = deblock_fetch(pd, g, pd.dbrec, a + 1, x + 1, row, ex.lane);
         if (row > 0) {
             int need = x + 2 < W ? x + 2 : W;
             wait_progress(&prog[row - 1], need);
         }
         ROW_MARK(1);
-        seq_deblock_mb_fast(ex, w, pd, g, h, hl, row > 0 ? ht : h, nz, nzl, nzt, a, x, row);
+        seq_deblock_mb_fast(ex, w, pd, g, in, x > 0, x, row);
         if (ex.lane == 0) st_release_gpu(&prog[row], x + 1);
         ROW_MARK(2);
-        hl = h; nzl = nz; h = h_next; nz = nz_next; ht = ht_next; nzt = nzt_next;
+    }
+}
+
+// K4 preparation: boundary strengths and filter parameters of every macroblock of the listed pictures (flat grid like
+// k_inter; nothing here depends on sample values, so it stays off the wavefront's critical path).
+__global__ void __launch_bounds__(128) k_deblock_prep(const DescTable descs, const __grid_constant__ PicList list, Geometry g)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_mbs = g.w_mbs * g.h_mbs;
+    const PicDesc& pd = descs[list.slot[blockIdx.y]];
+    for (int a = blockIdx.x * 4 + warp; a < n_mbs; a += gridDim.x * 4) {
+        int mbx, mby;
+        mb_xy(g, a, mbx, mby);
+        const h264r_mb_hdr h = load_hdr(pd, a), hl = mbx > 0 ? load_hdr(pd, a - 1) : h, ht = mby > 0 ? load_hdr(pd, a - g.w_mbs) : h;
+        phase_deblock_prep(pd.dbrec + (size_t)a * DBREC_BYTES, pd, g, h, hl, ht, pd.nzmask[a], mbx > 0 ? pd.nzmask[a - 1] : 0u,
+                           mby > 0 ? pd.nzmask[a - g.w_mbs] : 0u, a, mbx, mby, lane);
     }
 }
 

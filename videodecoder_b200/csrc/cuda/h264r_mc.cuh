@@ -377,6 +377,14 @@ HD int mc_need(int xf, int yf)
     return (int)(((sel & 8 ? hi : lo) >> (4 * (sel & 7))) & 15u);
 }
 
+// bytes (x .. x+3, y) of a padded reference plane, x of any alignment
+HD uint32_t ref_word(const uint8_t* ref, int gpitch, int x, int y)
+{
+    const uintptr_t ad = reinterpret_cast<uintptr_t>(ref + (ptrdiff_t)y * gpitch + x);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(ad & ~(uintptr_t)3);
+    return funnel_r(H264R_LDG(q), H264R_LDG(q + 1), (int)(ad & 3) * 8);
+}
+
 // ---- window staging ----------------------------------------------------------------------------------------
 // Items first, first + STRIDE, ... of a window of NROWS x NWORDS words whose top-left byte is (sx, sy) of the padded
 // reference plane.  A staged word = 4 bytes at any alignment = funnel shift of two aligned words; the alignment is
@@ -720,23 +728,31 @@ HD void phase_inter_compute(InterWork& w, TmaState& ts, const PicDesc& pd, const
                 packed = prmt(r.x, r.y, 0x6420);
             }
         } else {
+            // ITU-T H.264 8.4.2.2.2.  The lane's four samples are two pairs; a pair lies in one 4x4 luma block's 2x2 chroma
+            // block and shares its vector, so it needs 3 reference samples from each of 2 rows: per row one unaligned word
+            // (two aligned loads + funnel).  The pair's position is clamped as a whole, which the replicated border makes
+            // equal to the per-sample clamp of the coordinates.
             const int cw = g.w_mbs * 8, ch = g.h_mbs * 8;
-            for (int k = 0; k < 4; k++) {
-                int cx = cx0 + k, blk = (cy >> 1) * 4 + (cx >> 1), qq = (cy >> 2) * 2 + (cx >> 2);
-                int rc = hdr_ref_idx(h, qq);
+#pragma unroll
+            for (int k2 = 0; k2 < 2; k2++) {
+                const int cx = cx0 + 2 * k2, blk = (cy >> 1) * 4 + (cx >> 1), qq = (cy >> 2) * 2 + (cx >> 2);
+                const int rc = hdr_ref_idx(h, qq);
                 const uint8_t* ref = plane ? pd.ref_v[rc] : pd.ref_u[rc];
-                uint32_t v2 = load_mv(pd, h, a, blk);
-                int mvx = mv_x(v2), mvy = mv_y(v2);
-                int xf = mvx & 7, yf = mvy & 7;
-                int xi = mbx * 8 + cx + (mvx >> 3), yi = mby * 8 + cy + (mvy >> 3);
-                // the replicated border makes a clamp to [-8, size+7] equal to the clamp to the picture
-                int xa = clip3(-8, cw + 7, xi), xb = clip3(-8, cw + 7, xi + 1), ya = clip3(-8, ch + 7, yi), yb = clip3(-8, ch + 7, yi + 1);
-                int A = H264R_LDG(ref + (ptrdiff_t)ya * g.pitch_c + xa), B = H264R_LDG(ref + (ptrdiff_t)ya * g.pitch_c + xb);
-                int C = H264R_LDG(ref + (ptrdiff_t)yb * g.pitch_c + xa), D = H264R_LDG(ref + (ptrdiff_t)yb * g.pitch_c + xb);
-                int pv = ((8 - xf) * (8 - yf) * A + xf * (8 - yf) * B + (8 - xf) * yf * C + xf * yf * D + 32) >> 6;
-                if (pd.weighted_pred) pv = weight_pred(pv, pd.chroma_log2_wd, pd.chroma_weight[rc][plane], pd.chroma_offset[rc][plane]);
-                if (coded) pv += w.res[256 + plane * 64 + cy * 8 + cx];
-                packed |= (uint32_t)clip1(pv) << (8 * k);
+                const uint32_t v2 = load_mv(pd, h, a, blk);
+                const int mvx = mv_x(v2), mvy = mv_y(v2);
+                const int xf = mvx & 7, yf = mvy & 7;
+                const int xi = clip3(-8, cw + 5, mbx * 8 + cx + (mvx >> 3)), yi = clip3(-8, ch + 6, mby * 8 + cy + (mvy >> 3));
+                const uint32_t r0 = ref_word(ref, g.pitch_c, xi, yi), r1 = ref_word(ref, g.pitch_c, xi, yi + 1);
+                const int w00 = (8 - xf) * (8 - yf), w01 = xf * (8 - yf), w10 = (8 - xf) * yf, w11 = xf * yf;
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const int A = (int)((r0 >> (8 * k)) & 255u), B = (int)((r0 >> (8 * k + 8)) & 255u);
+                    const int C = (int)((r1 >> (8 * k)) & 255u), D = (int)((r1 >> (8 * k + 8)) & 255u);
+                    int pv = (w00 * A + w01 * B + w10 * C + w11 * D + 32) >> 6;
+                    if (pd.weighted_pred) pv = weight_pred(pv, pd.chroma_log2_wd, pd.chroma_weight[rc][plane], pd.chroma_offset[rc][plane]);
+                    if (coded) pv += w.res[256 + plane * 64 + cy * 8 + cx + k];
+                    packed |= (uint32_t)clip1(pv) << (8 * (2 * k2 + k));
+                }
             }
         }
         *reinterpret_cast<uint32_t*>(cbase) = packed;

@@ -409,21 +409,37 @@ __global__ void __launch_bounds__(128) k_pad(const DescTable descs, const __grid
 // the words of the three planes: grid = (DIGEST_CTAS, pictures), every CTA folds a band of rows of each plane,
 // reduces, and adds its four partial sums to the picture's entry (zeroed by the host side before the launch).
 // ------------------------------------------------------------------------------------------------
-constexpr int DIGEST_CTAS = 24;
+constexpr int DIGEST_CTAS = 48;
 struct FramePool { uint8_t* base; size_t frame_bytes, off_y, off_u, off_v; };
+// One plane's share of this CTA: a band of rows.  A thread owns a column of 8-byte pairs and walks down the band eight
+// rows at a time, so that every thread keeps eight independent loads in flight (the kernel is pure streaming: what
+// bounds it is bytes in flight per SM, not arithmetic).  The planes were written by earlier launches: plain loads.
 __device__ __forceinline__ void digest_rows(uint32_t d[4], const uint8_t* plane, int pitch, int words_per_row, int rows, uint32_t first_index)
 {
     const int band = (rows + gridDim.x - 1) / gridDim.x, r0 = blockIdx.x * band, r1 = min(rows, r0 + band);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
     const int pairs = words_per_row >> 1;            // plane widths are multiples of 8 samples
-    for (int r = r0 + warp; r < r1; r += n_warps) {
-        const uint2* row = reinterpret_cast<const uint2*>(plane + (size_t)r * pitch);
-        const uint32_t idx0 = first_index + (uint32_t)r * (uint32_t)words_per_row;
-#pragma unroll 4
-        for (int c = lane; c < pairs; c += 32) {
-            const uint2 v = __ldcg(row + c);
-            digest_accumulate(d, v.x, idx0 + 2u * (uint32_t)c);
-            digest_accumulate(d, v.y, idx0 + 2u * (uint32_t)c + 1u);
+    const int cols = min(pairs, (int)blockDim.x), rpp = blockDim.x / cols;      // thread grid: rpp rows x cols pairs per pass
+    const int tr = threadIdx.x / cols, tc = threadIdx.x - tr * cols;
+    if (tr >= rpp) return;
+    for (int c = tc; c < pairs; c += cols) {
+        const uint8_t* col = plane + (size_t)c * 8;
+        int r = r0 + tr;
+        for (; r + 7 * rpp < r1; r += 8 * rpp) {
+            uint2 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = __ldg(reinterpret_cast<const uint2*>(col + (size_t)(r + k * rpp) * pitch));
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t idx = first_index + (uint32_t)(r + k * rpp) * (uint32_t)words_per_row + 2u * (uint32_t)c;
+                digest_accumulate(d, v[k].x, idx);
+                digest_accumulate(d, v[k].y, idx + 1u);
+            }
+        }
+        for (; r < r1; r += rpp) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(col + (size_t)r * pitch));
+            const uint32_t idx = first_index + (uint32_t)r * (uint32_t)words_per_row + 2u * (uint32_t)c;
+            digest_accumulate(d, v.x, idx);
+            digest_accumulate(d, v.y, idx + 1u);
         }
     }
 }

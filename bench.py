@@ -275,7 +275,7 @@ def main():
             pps.append(pp2)
     h2d = 0
     # bytes of one picture-buffer transfer: descriptor + headers + vectors + masks (fixed) + the blocks present
-    upload_fixed = (pinned[0][0][0].c.mv - pinned[0][0][0].c.base) if packed else 0
+    upload_fixed = (pinned[0][0][0].c.blocks - pinned[0][0][0].c.mv_end) if packed else 0
     for g in range(G):
         for i in range(F):
             hb, mb, cb, kb = pinned[g if packed else g % U][i]

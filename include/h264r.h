@@ -196,7 +196,10 @@ int h264r_submit_mbs_packed(h264r_ctx* ctx, int frame_id, int first_mb, int n_mb
  * h264r_sync() (or a read-back of the picture) returns, and may then be refilled.  max_blocks = 0 sizes for the worst case (24 per MB). */
 typedef struct h264r_picture_buf {
     h264r_mb_hdr* hdr;        /* [n_mbs]                    */
-    int16_t*      mv;         /* [n_mbs * H264R_MV_PER_MB] (room for either vector layout) */
+    int16_t*      mv;         /* per-4x4 layout: [n_mbs * H264R_MV_PER_MB], forward from here                        */
+    int16_t*      mv_end;     /* partition layout: vector i is written at mv_end[-2(i+1)] (x), mv_end[-2(i+1)+1] (y):
+                                 the stream grows backward, so that it ends where the headers begin and the picture
+                                 is one contiguous range                                                            */
     uint32_t*     blk_mask;   /* [n_mbs]                    */
     int16_t*      blocks;     /* [max_blocks * 16]          */
     size_t        max_blocks;
@@ -207,7 +210,7 @@ typedef struct h264r_picture_buf {
 int  h264r_picture_buf_alloc(h264r_ctx* ctx, size_t max_blocks, h264r_picture_buf* out);
 void h264r_picture_buf_free(h264r_ctx* ctx, h264r_picture_buf* buf);
 /* n_mvs < 0: buf->mv holds the per-4x4 layout described above (16 vectors per macroblock).
- * n_mvs >= 0: buf->mv holds n_mvs vectors in PARTITION order -- per macroblock, in macroblock order, one vector per
+ * n_mvs >= 0: n_mvs vectors in PARTITION order, stored backward from buf->mv_end -- per macroblock, in macroblock order, one vector per
  * partition as the bitstream carries them (P_L0_16x16 and P_Skip: 1; 16x8, 8x16: 2; P_8x8: per quadrant 0..3 its
  * sub-macroblock partitions, 8x8: 1, 8x4 / 4x8: 2, 4x4: 4, in raster order; intra: none; mvd loops of
  * macroblock::Parse, h264/macroblock.cpp:360-398).  The engine derives each macroblock's first vector from

@@ -94,8 +94,12 @@ struct MvStore {
                 mvs.push_back(dense[(size_t)a * 32 + blk * 2]); mvs.push_back(dense[(size_t)a * 32 + blk * 2 + 1]);
             }
         }
-        mvs.resize(mvs.size() + 2);
-        pd.mv = mvs.data(); pd.mv_off = off.data();
+        // the stream grows backward from pd.mv: vector i at pd.mv[-2(i+1)]
+        std::vector<int16_t> rev(mvs.size() + 2, 0);
+        const size_t nv = mvs.size() / 2;
+        for (size_t i = 0; i < nv; i++) { rev[2 * (nv - 1 - i)] = mvs[2 * i]; rev[2 * (nv - 1 - i) + 1] = mvs[2 * i + 1]; }
+        mvs.swap(rev);
+        pd.mv = mvs.data() + 2 * nv; pd.mv_off = off.data();
     }
 };
 }  // namespace

@@ -76,7 +76,7 @@ struct h264r_ctx {
     // arena slot = what the uploads carry, in this order: descriptor | hdr | blk_mask | mv | coefficient blocks;
     // then blk_off and mv_off (written by k_blk_scan, never uploaded)
     // then the residual scratch of the intra macroblocks (device only)
-    size_t slot_bytes = 0, off_hdr = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_mvoff = 0, off_coeff = 0, off_res = 0, off_nz = 0, off_dbrec = 0;
+    size_t slot_bytes = 0, off_desc = 0, off_hdr = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_mvoff = 0, off_coeff = 0, off_res = 0, off_nz = 0, off_dbrec = 0;
     // per-flush control block (descriptors + picture lists), pinned host mirror + device copy
     uint8_t* h_ctrl = nullptr;
     size_t ctrl_bytes = 0;
@@ -136,7 +136,7 @@ void fill_desc(h264r_ctx* c, const Pending& p, PicDesc& pd)
     memset(&pd, 0, sizeof(pd));
     uint8_t* s = c->slot_ptr(p.slot);
     pd.hdr = reinterpret_cast<const h264r_mb_hdr*>(s + c->off_hdr);
-    pd.mv = reinterpret_cast<const int16_t*>(s + c->off_mv);
+    pd.mv = reinterpret_cast<const int16_t*>(s + (p.mv_partition ? c->off_desc : c->off_mv));
     pd.coeff = reinterpret_cast<const int16_t*>(s + c->off_coeff);
     if (p.layout == 2) {
         pd.blk_mask = reinterpret_cast<const uint32_t*>(s + c->off_mask);
@@ -222,10 +222,11 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     c->y_bytes = (size_t)c->g.pitch_y * (h_mbs * 16 + 2 * PAD_Y);
     c->c_bytes = (size_t)c->g.pitch_c * (h_mbs * 8 + 2 * PAD_YC);
     c->frame_bytes = align_up(c->y_bytes + 2 * c->c_bytes, 256);
-    c->off_hdr = align_up(sizeof(PicDesc), 256);
+    c->off_mv = 0;
+    c->off_desc = align_up((size_t)c->n_mbs * H264R_MV_PER_MB * 2, 256);
+    c->off_hdr = c->off_desc + align_up(sizeof(PicDesc), 256);
     c->off_mask = c->off_hdr + align_up((size_t)c->n_mbs * sizeof(h264r_mb_hdr), 256);
-    c->off_mv = c->off_mask + align_up((size_t)c->n_mbs * 4, 256);
-    c->off_coeff = c->off_mv + align_up((size_t)c->n_mbs * H264R_MV_PER_MB * 2, 256);
+    c->off_coeff = c->off_mask + align_up((size_t)c->n_mbs * 4, 256);
     c->off_boff = c->off_coeff + align_up((size_t)c->n_mbs * H264R_COEFF_PER_MB * 2, 256);
     c->off_mvoff = c->off_boff + align_up((size_t)c->n_mbs * 4, 256);
     c->off_res = c->off_mvoff + align_up((size_t)c->n_mbs * 4, 256);
@@ -475,6 +476,7 @@ int h264r_picture_buf_alloc(h264r_ctx* ctx, size_t max_blocks, h264r_picture_buf
     memset(b, 0, ctx->off_coeff);
     out->hdr = reinterpret_cast<h264r_mb_hdr*>(b + ctx->off_hdr);
     out->mv = reinterpret_cast<int16_t*>(b + ctx->off_mv);
+    out->mv_end = reinterpret_cast<int16_t*>(b + ctx->off_desc);
     out->blk_mask = reinterpret_cast<uint32_t*>(b + ctx->off_mask);
     out->blocks = reinterpret_cast<int16_t*>(b + ctx->off_coeff);
     out->max_blocks = max_blocks;
@@ -523,20 +525,15 @@ int h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* 
     p->n_blocks = n_blocks;
     p->n_submitted = ctx->n_mbs;
     p->mv_partition = n_mvs >= 0;
-    // descriptor in front; one transfer for descriptor + headers + masks + the vectors present, one for the blocks present
-    fill_desc(ctx, *p, *reinterpret_cast<PicDesc*>(buf->base));
+    // ONE transfer: the vectors present (backward from the descriptor), descriptor, headers, masks, the blocks present
+    uint8_t* hb = static_cast<uint8_t*>(buf->base);
+    fill_desc(ctx, *p, *reinterpret_cast<PicDesc*>(hb + ctx->off_desc));
     const bool is_p = p->pp.slice_type == H264R_SLICE_P;
-    const size_t mv_bytes = !is_p ? 0 : (n_mvs >= 0 ? (size_t)n_mvs * 4 : (size_t)ctx->n_mbs * H264R_MV_PER_MB * 2);
-    if (mv_bytes == (size_t)ctx->n_mbs * H264R_MV_PER_MB * 2)
-        CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot), buf->base, ctx->off_coeff + n_blocks * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
-    else {
-        CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot), buf->base, ctx->off_mv + mv_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
-        if (n_blocks)
-            CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot) + ctx->off_coeff, static_cast<const uint8_t*>(buf->base) + ctx->off_coeff, n_blocks * 32,
-                               cudaMemcpyHostToDevice, ctx->copy_stream));
-    }
+    const size_t mv_bytes = !is_p ? 0 : (n_mvs >= 0 ? (size_t)n_mvs * 4 : ctx->off_desc);      // per-4x4 layout: the whole area
+    const size_t first = ctx->off_desc - mv_bytes;
+    CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot) + first, hb + first, ctx->off_coeff + n_blocks * 32 - first, cudaMemcpyHostToDevice, ctx->copy_stream));
     CU(cudaEventRecord(ctx->ev_copied[p->slot], ctx->copy_stream));
-    reinterpret_cast<PicDesc*>(ctx->h_ctrl)[p->slot].deblock_on = reinterpret_cast<const PicDesc*>(buf->base)->deblock_on;
+    reinterpret_cast<PicDesc*>(ctx->h_ctrl)[p->slot].deblock_on = reinterpret_cast<const PicDesc*>(hb + ctx->off_desc)->deblock_on;
     p->seq = ++ctx->end_seq;
     p->ended = true;
     ctx->frame_state[frame_id] = FRAME_QUEUED;
@@ -553,7 +550,7 @@ int h264r_frame_end(h264r_ctx* ctx, int frame_id)
     // the picture's descriptor travels with its syntax (see PicList in h264r_kernels.cuh)
     PicDesc* h_desc = reinterpret_cast<PicDesc*>(ctx->h_ctrl);
     fill_desc(ctx, *p, h_desc[p->slot]);
-    CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot), &h_desc[p->slot], sizeof(PicDesc), cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot) + ctx->off_desc, &h_desc[p->slot], sizeof(PicDesc), cudaMemcpyHostToDevice, ctx->copy_stream));
     CU(cudaEventRecord(ctx->ev_copied[p->slot], ctx->copy_stream));
     p->seq = ++ctx->end_seq;
     p->ended = true;
@@ -599,7 +596,7 @@ int h264r_flush(h264r_ctx* ctx)
         if (wv + 1 > n_waves) n_waves = wv + 1;
     }
     const int n = (int)run.size();
-    const DescTable d_desc{ctx->d_syntax, ctx->slot_bytes};
+    const DescTable d_desc{ctx->d_syntax + ctx->off_desc, ctx->slot_bytes};
     const PicDesc* h_desc = reinterpret_cast<const PicDesc*>(ctx->h_ctrl);
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     if (ctx->main_dirty) {

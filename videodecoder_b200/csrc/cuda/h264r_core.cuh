@@ -59,7 +59,8 @@ HD void mb_xy(const Geometry& g, int a, int& mbx, int& mby)
 // Everything a kernel needs to know about one picture of a wave (lives in device memory).
 struct PicDesc {
     const h264r_mb_hdr* hdr;
-    const int16_t* mv;         // motion vectors (x, y): per 4x4 block (16 per macroblock) or per partition (see mv_off)
+    const int16_t* mv;         // motion vectors (x, y): per 4x4 block (16 per macroblock, forward from here) or per partition
+                               // (stored BACKWARD from here: vector i at mv[-2(i+1)], see mv_off)
     const uint32_t* mv_off;    // null: per-4x4 layout; else per macroblock the index of its first vector, partition order
     const int16_t* coeff;      // coefficient blocks of the picture, 16 levels each, packed (see BlkRef)
     const uint32_t* blk_mask;  // per macroblock: bit b set = block b is stored
@@ -144,7 +145,9 @@ HD int hdr_pred_mode(const h264r_mb_hdr& h, int blk)                            
 // 16 a + b.  Partition layout (h264r_submit_picture with n_mvs >= 0): the vectors of a macroblock in the order the
 // bitstream carries them -- one per partition (P_L0_16x16: 1, 16x8 / 8x16: 2) or, for P_8x8, per sub-macroblock
 // partition of quadrants 0..3 (8x8: 1, 8x4 / 4x8: 2, 4x4: 4) -- starting at entry mv_off[a]
-// (reference: mvd loops of macroblock::Parse, h264/macroblock.cpp:360-398).
+// (reference: mvd loops of macroblock::Parse, h264/macroblock.cpp:360-398).  This stream grows BACKWARD from pd.mv
+// (entry i at word -(i+1)): it then ends where the picture's fixed-size syntax begins, and vectors + headers + masks +
+// coefficient blocks are one contiguous range = one DMA.
 HD int mv_sub_count(int s) { return (0x4221 >> (4 * s)) & 7; }           // H264R_SUB_8x8, 8x4, 4x8, 4x4
 HD int mv_count(int mb_class, int sub_mb_type)
 {
@@ -173,7 +176,7 @@ HD int mv_part_index(int mb_class, int sub_mb_type, int blk)
 HD uint32_t load_mv(const PicDesc& pd, const h264r_mb_hdr& h, int a, int blk)
 {
     const uint32_t* mv32 = reinterpret_cast<const uint32_t*>(pd.mv);
-    if (pd.mv_off) return H264R_LDG(mv32 + H264R_LDG(pd.mv_off + a) + mv_part_index(h.mb_class, h.sub_mb_type, blk));
+    if (pd.mv_off) return H264R_LDG(mv32 - 1 - (ptrdiff_t)(H264R_LDG(pd.mv_off + a) + (uint32_t)mv_part_index(h.mb_class, h.sub_mb_type, blk)));
     return H264R_LDG(mv32 + (size_t)a * 16 + blk);
 }
 HD int mv_x(uint32_t v) { return (int)(int16_t)(v & 0xffff); }

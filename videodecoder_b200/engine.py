@@ -11,7 +11,7 @@ import numpy as np
 from . import abi, build
 
 class PictureBufStruct(ctypes.Structure):
-    _fields_ = [("hdr", ctypes.c_void_p), ("mv", ctypes.c_void_p), ("blk_mask", ctypes.c_void_p), ("blocks", ctypes.c_void_p),
+    _fields_ = [("hdr", ctypes.c_void_p), ("mv", ctypes.c_void_p), ("mv_end", ctypes.c_void_p), ("blk_mask", ctypes.c_void_p), ("blocks", ctypes.c_void_p),
                 ("max_blocks", ctypes.c_size_t), ("n_intra", ctypes.c_int32), ("base", ctypes.c_void_p)]
 
 
@@ -133,6 +133,7 @@ class PictureBuf:
             return np.frombuffer(buf, dtype=dt, count=count)
         self.hdr = view(self.c.hdr, abi.MB_HDR_DTYPE, n)
         self.mv = view(self.c.mv, np.int16, n * 32).reshape(n, 32)
+        self.mv_tail = view(self.c.mv_end - n * 64, np.int16, n * 32).reshape(-1, 2)     # ends at mv_end: partition-order stream
         self.blk_mask = view(self.c.blk_mask, np.uint32, n)
         self.blocks = view(self.c.blocks, np.int16, int(self.c.max_blocks) * 16).reshape(-1, 16)
         self.n_blocks = 0
@@ -147,7 +148,8 @@ class PictureBuf:
             if mv_partition:
                 pm = pack.pack_mvs_partition(hdr, mv)
                 self.n_mvs = int(pm.shape[0])
-                self.mv.reshape(-1, 2)[:self.n_mvs] = pm
+                if self.n_mvs:
+                    self.mv_tail[-self.n_mvs:] = pm[::-1]     # vector i at mv_end[-2(i+1)]: the stream grows backward
             else:
                 self.mv[:] = mv
         self.blk_mask[:] = blk_mask
@@ -157,7 +159,7 @@ class PictureBuf:
 
     def free(self):
         if self.c.base:
-            self.hdr = self.mv = self.blk_mask = self.blocks = None
+            self.hdr = self.mv = self.mv_tail = self.blk_mask = self.blocks = None
             self.engine.L.h264r_picture_buf_free(self.engine.ctx, ctypes.byref(self.c))
 
 

@@ -280,7 +280,7 @@ def main():
         for i in range(F):
             hb, mb, cb, kb = pinned[g if packed else g % U][i]
             if packed:
-                h2d += upload_fixed + max(0, hb.n_mvs) * 4 + hb.n_blocks * 32
+                h2d += upload_fixed + max(0, hb.n_mvs) * 4 + hb.n_blocks * 16 * hb.c.level_bytes
             else:
                 h2d += hb.nbytes + cb.nbytes + (mb.nbytes if mb else 0)
     all_ids = list(range(G * F))

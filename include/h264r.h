@@ -205,6 +205,9 @@ typedef struct h264r_picture_buf {
     size_t        max_blocks;
     int32_t       n_intra;    /* number of intra macroblocks in hdr[], as counted by the parser; -1 = unknown: the
                                  library then walks hdr[] itself (and validates mb_class while there)            */
+    int32_t       level_bytes;/* 2 (default): blocks[] holds int16 levels, 32 bytes per block; 1: the parser wrote int8 levels,
+                                 16 bytes per block, through (int8_t*)blocks -- allowed when every level of the picture is in
+                                 [-128, 127] (the common case at the QPs video is coded at), and half the bytes on the wire   */
     void*         base;       /* owned by the library       */
 } h264r_picture_buf;
 int  h264r_picture_buf_alloc(h264r_ctx* ctx, size_t max_blocks, h264r_picture_buf* out);

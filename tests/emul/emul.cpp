@@ -26,6 +26,7 @@ void fill_desc(PicDesc& pd, const h264r_pic_params* pp, const h264r_mb_hdr* hdr,
     memset(&pd, 0, sizeof(pd));
     pd.hdr = hdr; pd.mv = mv; pd.coeff = coeff; pd.y = y; pd.u = u; pd.v = v;
     pd.blk_mask = nullptr; pd.blk_off = nullptr;        // set by use_dense() / use_packed()
+    pd.level8 = 0;
     pd.mv_off = nullptr;
     pd.residual = nullptr;
     pd.nzmask = nullptr;
@@ -76,7 +77,16 @@ struct CoeffStore {
         }
         blocks.resize(blocks.size() + 16);       // keeps data() non-null for all-zero pictures
         pd.coeff = blocks.data(); pd.blk_mask = mask.data(); pd.blk_off = off.data();
+        // int8 transport when every level fits (h264r_picture_buf::level_bytes = 1)
+        bool fits = true;
+        for (int16_t v : blocks) fits = fits && v >= -128 && v <= 127;
+        if (fits) {
+            narrow.assign(blocks.begin(), blocks.end());
+            pd.coeff = reinterpret_cast<const int16_t*>(narrow.data());
+            pd.level8 = 1;
+        }
     }
+    std::vector<int8_t> narrow;
 };
 // motion vectors in partition order, as h264r_submit_picture(..., n_mvs >= 0) delivers them
 struct MvStore {

@@ -29,6 +29,7 @@ struct Pending {
     int layout;             // 0 = nothing submitted yet, 1 = dense (h264r_submit_mbs), 2 = packed (h264r_submit_mbs_packed)
     size_t n_blocks;        // packed: coefficient blocks stored so far
     bool mv_partition;      // vectors in partition order (h264r_submit_picture with n_mvs >= 0)
+    int level_bytes;        // 2: int16 levels (32-byte blocks); 1: int8 levels (16-byte blocks, picture buffers only)
     uint64_t seq;           // order of frame_end calls (= order of the uploads on the copy stream)
 };
 
@@ -138,6 +139,7 @@ void fill_desc(h264r_ctx* c, const Pending& p, PicDesc& pd)
     pd.hdr = reinterpret_cast<const h264r_mb_hdr*>(s + c->off_hdr);
     pd.mv = reinterpret_cast<const int16_t*>(s + (p.mv_partition ? c->off_desc : c->off_mv));
     pd.coeff = reinterpret_cast<const int16_t*>(s + c->off_coeff);
+    pd.level8 = p.level_bytes == 1;
     if (p.layout == 2) {
         pd.blk_mask = reinterpret_cast<const uint32_t*>(s + c->off_mask);
         pd.blk_off = reinterpret_cast<const uint32_t*>(s + c->off_boff);
@@ -387,6 +389,7 @@ int h264r_frame_begin(h264r_ctx* ctx, int frame_id, const h264r_pic_params* pp)
     }
     if (ctx->free_head >= ctx->free_slots.size()) return fail(ctx, H264R_E_CAPACITY, "frame_begin: max_pending pictures already queued; call h264r_flush");
     Pending p{};
+    p.level_bytes = 2;
     p.frame_id = frame_id;
     p.slot = ctx->free_slots[ctx->free_head++];
     if (ctx->free_head > 4096 && ctx->free_head * 2 > ctx->free_slots.size()) {
@@ -481,6 +484,7 @@ int h264r_picture_buf_alloc(h264r_ctx* ctx, size_t max_blocks, h264r_picture_buf
     out->blocks = reinterpret_cast<int16_t*>(b + ctx->off_coeff);
     out->max_blocks = max_blocks;
     out->n_intra = -1;
+    out->level_bytes = 2;
     out->base = b;
     return H264R_OK;
 }
@@ -495,7 +499,8 @@ void h264r_picture_buf_free(h264r_ctx* ctx, h264r_picture_buf* buf)
 
 int h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* buf, size_t n_blocks, long n_mvs)
 {
-    if (!ctx || !buf || !buf->base || n_blocks > buf->max_blocks || n_mvs > (long)16 * (ctx ? ctx->n_mbs : 0))
+    if (!ctx || !buf || !buf->base || n_blocks > buf->max_blocks || n_mvs > (long)16 * (ctx ? ctx->n_mbs : 0) ||
+        (buf->level_bytes != 1 && buf->level_bytes != 2))
         return fail(ctx, H264R_E_INVAL, "submit_picture: bad argument");
     Pending* p = find_pending(ctx, frame_id);
     if (!p || p->ended) return fail(ctx, H264R_E_STATE, "submit_picture: no open picture with this frame id");
@@ -525,13 +530,15 @@ int h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* 
     p->n_blocks = n_blocks;
     p->n_submitted = ctx->n_mbs;
     p->mv_partition = n_mvs >= 0;
+    p->level_bytes = buf->level_bytes;
     // ONE transfer: the vectors present (backward from the descriptor), descriptor, headers, masks, the blocks present
     uint8_t* hb = static_cast<uint8_t*>(buf->base);
     fill_desc(ctx, *p, *reinterpret_cast<PicDesc*>(hb + ctx->off_desc));
     const bool is_p = p->pp.slice_type == H264R_SLICE_P;
     const size_t mv_bytes = !is_p ? 0 : (n_mvs >= 0 ? (size_t)n_mvs * 4 : ctx->off_desc);      // per-4x4 layout: the whole area
     const size_t first = ctx->off_desc - mv_bytes;
-    CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot) + first, hb + first, ctx->off_coeff + n_blocks * 32 - first, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot) + first, hb + first, ctx->off_coeff + n_blocks * 16 * (size_t)buf->level_bytes - first,
+                       cudaMemcpyHostToDevice, ctx->copy_stream));
     CU(cudaEventRecord(ctx->ev_copied[p->slot], ctx->copy_stream));
     reinterpret_cast<PicDesc*>(ctx->h_ctrl)[p->slot].deblock_on = reinterpret_cast<const PicDesc*>(hb + ctx->off_desc)->deblock_on;
     p->seq = ++ctx->end_seq;

@@ -63,6 +63,7 @@ struct PicDesc {
                                // (stored BACKWARD from here: vector i at mv[-2(i+1)], see mv_off)
     const uint32_t* mv_off;    // null: per-4x4 layout; else per macroblock the index of its first vector, partition order
     const int16_t* coeff;      // coefficient blocks of the picture, 16 levels each, packed (see BlkRef)
+    int32_t level8;            // 1: the levels are int8 (16 bytes per block) instead of int16 (32 bytes)
     const uint32_t* blk_mask;  // per macroblock: bit b set = block b is stored
     const uint32_t* blk_off;   // per macroblock: index of its first stored block
     int16_t* residual;         // scratch: residual of the intra macroblocks, 384 int16 each (Y 16x16, U 8x8, V 8x8), produced
@@ -120,10 +121,26 @@ HD int popc32(uint32_t v)
 #endif
 }
 HD BlkRef load_blkref(const PicDesc& pd, int a) { return BlkRef{H264R_LDG(pd.blk_mask + a), H264R_LDG(pd.blk_off + a)}; }
-HD const int16_t* blk_ptr(const PicDesc& pd, const BlkRef& r, int b)       // nullptr: block b is zero
+HD const uint8_t* blk_ptr(const PicDesc& pd, const BlkRef& r, int b)       // nullptr: block b is zero
 {
     if (!((r.mask >> b) & 1u)) return nullptr;
-    return pd.coeff + ((size_t)r.off + popc32(r.mask & ((1u << b) - 1u))) * 16;
+    return reinterpret_cast<const uint8_t*>(pd.coeff) + ((size_t)r.off + popc32(r.mask & ((1u << b) - 1u))) * (pd.level8 ? 16 : 32);
+}
+// levels [first, first + 8) of a stored block (first = 0 or 8) as four words of two int16 each, whatever the storage width
+HD int4 blk_levels8(const PicDesc& pd, const uint8_t* p, int first)
+{
+    if (!pd.level8) return H264R_LDG(reinterpret_cast<const int4*>(p) + (first >> 3));
+    const uint2 v = H264R_LDG(reinterpret_cast<const uint2*>(p) + (first >> 3));
+    auto pair = [](uint32_t w, int k) -> int {      // bytes 2k, 2k+1 of w, sign-extended, as (lo | hi << 16)
+        const int lo = (int)(int8_t)(w >> (16 * k)), hi = (int)(int8_t)(w >> (16 * k + 8));
+        return (int)(((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16));
+    };
+    return int4{pair(v.x, 0), pair(v.x, 1), pair(v.y, 0), pair(v.y, 1)};
+}
+// level 0 of a stored block (Intra16x16 / chroma DC slot)
+HD int blk_level0(const PicDesc& pd, const uint8_t* p)
+{
+    return pd.level8 ? (int)(int8_t)H264R_LDG(p) : (int)H264R_LDG(reinterpret_cast<const int16_t*>(p));
 }
 
 // Header fields that are indexed at run time.  The record lives in registers; indexing its byte arrays with a run-time
@@ -272,9 +289,9 @@ HD void phase_load_coeff(MbWork& w, const PicDesc& pd, int a, int lane)
 {
     if (lane < 24) {
         const BlkRef br = load_blkref(pd, a);
-        const int4* src = reinterpret_cast<const int4*>(blk_ptr(pd, br, lane));
+        const uint8_t* src = blk_ptr(pd, br, lane);
         int4 v0 = int4{0, 0, 0, 0}, v1 = int4{0, 0, 0, 0};
-        if (src) { v0 = H264R_LDG(src); v1 = H264R_LDG(src + 1); }
+        if (src) { v0 = blk_levels8(pd, src, 0); v1 = blk_levels8(pd, src, 8); }
         int4* dst = reinterpret_cast<int4*>(&w.coef[lane][0]);
         dst[0] = v0; dst[1] = v1;
     }
@@ -897,9 +914,9 @@ HD bool blk_coded_global(const PicDesc& pd, const h264r_mb_hdr& h, int a, int ra
     if (h.flags & H264R_T8x8) { first = ((ras >> 3) * 2 + ((ras & 3) >> 1)) * 4; n = 4; }
     else { first = blk_raster(ras); n = 1; }
     for (int k = 0; k < n; k++) {
-        const int4* p = reinterpret_cast<const int4*>(blk_ptr(pd, br, first + k));
+        const uint8_t* p = blk_ptr(pd, br, first + k);
         if (!p) continue;
-        int4 v0 = H264R_LDG(p), v1 = H264R_LDG(p + 1);
+        int4 v0 = blk_levels8(pd, p, 0), v1 = blk_levels8(pd, p, 8);
         if (v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) return true;
     }
     return false;

@@ -36,9 +36,9 @@ HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr&
     int r[16];
     bool zero = true;
     if (active) {
-        const int4* src = reinterpret_cast<const int4*>(blk_ptr(pd, br, lane));
+        const uint8_t* src = blk_ptr(pd, br, lane);
         int4 v0 = int4{0, 0, 0, 0}, v1 = int4{0, 0, 0, 0};
-        if (src) { v0 = H264R_LDG(src); if (luma || cbp_c == 2) v1 = H264R_LDG(src + 1); }
+        if (src) { v0 = blk_levels8(pd, src, 0); if (luma || cbp_c == 2) v1 = blk_levels8(pd, src, 8); }
         if (!luma && cbp_c != 2) { v0.x &= 0xffff; v0.y = v0.z = v0.w = 0; }        // DC only: AC levels are not coded
         int c[16];
         const int w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -55,8 +55,8 @@ HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr&
                 int t = 0;
 #pragma unroll
                 for (int l = 0; l < 4; l++) {
-                    const int16_t* dp = blk_ptr(pd, br, blk_raster(k * 4 + l));
-                    int dc = dp ? H264R_LDG(dp) : 0;
+                    const uint8_t* dp = blk_ptr(pd, br, blk_raster(k * 4 + l));
+                    int dc = dp ? blk_level0(pd, dp) : 0;
                     t += ((0xA6C0 >> (l * 4 + j)) & 1) ? -dc : dc;       // T rows {++++},{++--},{+--+},{+-+-}: bit = minus
                 }
                 f += ((0xA6C0 >> (i * 4 + k)) & 1) ? -t : t;
@@ -68,9 +68,9 @@ HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr&
         if (!luma) {
             int plane = (lane - 16) >> 2, b = (lane - 16) & 3;
             qp = plane ? h.qp_cr : h.qp_cb;
-            const int16_t* d0 = blk_ptr(pd, br, 16 + plane * 4), * d1 = blk_ptr(pd, br, 17 + plane * 4);
-            const int16_t* d2 = blk_ptr(pd, br, 18 + plane * 4), * d3 = blk_ptr(pd, br, 19 + plane * 4);
-            int c0 = d0 ? H264R_LDG(d0) : 0, c1 = d1 ? H264R_LDG(d1) : 0, c2 = d2 ? H264R_LDG(d2) : 0, c3 = d3 ? H264R_LDG(d3) : 0;
+            const uint8_t* d0 = blk_ptr(pd, br, 16 + plane * 4), * d1 = blk_ptr(pd, br, 17 + plane * 4);
+            const uint8_t* d2 = blk_ptr(pd, br, 18 + plane * 4), * d3 = blk_ptr(pd, br, 19 + plane * 4);
+            int c0 = d0 ? blk_level0(pd, d0) : 0, c1 = d1 ? blk_level0(pd, d1) : 0, c2 = d2 ? blk_level0(pd, d2) : 0, c3 = d3 ? blk_level0(pd, d3) : 0;
             int f;
             if (COMPAT) f = (b == 0 || b == 3) ? c3 : -c3;      // reference's chroma DC product (h264/matrix.cpp:150-171)
             else f = c0 + ((b & 1) ? -c1 : c1) + ((b & 2) ? -c2 : c2) + ((b == 1 || b == 2) ? -c3 : c3);

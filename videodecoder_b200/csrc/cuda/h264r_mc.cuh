@@ -261,11 +261,11 @@ HD void phase_residual8_rows(InterWork& w, const PicDesc& pd, const h264r_mb_hdr
 {
     const int q = lane >> 3, r = lane & 7;
     const BlkRef br = load_blkref(pd, a);
-    const int4* src = reinterpret_cast<const int4*>(blk_ptr(pd, br, q * 4 + (r >> 1)));
+    const uint8_t* src = blk_ptr(pd, br, q * 4 + (r >> 1));
     int x[8];
     int nz = 0;
     if (src && ((h.cbp >> q) & 1)) {
-        const int4 v = H264R_LDG(src + (r & 1));
+        const int4 v = blk_levels8(pd, src, (r & 1) * 8);
         const int wv[4] = {v.x, v.y, v.z, v.w};
         const int qp = h.qp_y, s = (qp * 43) >> 8, m = qp - 6 * s;
 #pragma unroll

@@ -12,7 +12,7 @@ from . import abi, build
 
 class PictureBufStruct(ctypes.Structure):
     _fields_ = [("hdr", ctypes.c_void_p), ("mv", ctypes.c_void_p), ("mv_end", ctypes.c_void_p), ("blk_mask", ctypes.c_void_p), ("blocks", ctypes.c_void_p),
-                ("max_blocks", ctypes.c_size_t), ("n_intra", ctypes.c_int32), ("base", ctypes.c_void_p)]
+                ("max_blocks", ctypes.c_size_t), ("n_intra", ctypes.c_int32), ("level_bytes", ctypes.c_int32), ("base", ctypes.c_void_p)]
 
 
 _lib = None
@@ -139,7 +139,7 @@ class PictureBuf:
         self.n_blocks = 0
         self.n_mvs = -1
 
-    def fill(self, hdr, mv, blk_mask, blocks, mv_partition=False):
+    def fill(self, hdr, mv, blk_mask, blocks, mv_partition=False, level8=None):
         """mv: per-4x4 vectors (n, 32); mv_partition: store them in partition order (pack.pack_mvs_partition)"""
         from . import pack
         self.hdr[:] = np.ascontiguousarray(hdr).view(abi.MB_HDR_DTYPE).reshape(-1)
@@ -154,7 +154,14 @@ class PictureBuf:
                 self.mv[:] = mv
         self.blk_mask[:] = blk_mask
         self.n_blocks = int(blocks.shape[0])
-        self.blocks[:self.n_blocks] = blocks
+        if level8 is None:
+            level8 = self.n_blocks > 0 and int(blocks.min()) >= -128 and int(blocks.max()) <= 127
+        if level8:      # int8 transport: 16 bytes per block through the same area
+            self.blocks.view(np.int8).reshape(-1, 16)[:self.n_blocks] = blocks.astype(np.int8)
+            self.c.level_bytes = 1
+        else:
+            self.blocks[:self.n_blocks] = blocks
+            self.c.level_bytes = 2
         self.c.n_intra = int((self.hdr["mb_class"] <= abi.MB_I16x16).sum())       # a parser counts this as it goes
 
     def free(self):

@@ -99,8 +99,14 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, H264R_INTER_MIN_CTAS) k_inte
     }
     const int n_mbs = g.w_mbs * g.h_mbs;
     const PicDesc& pd = descs[list.slot[blockIdx.y]];
-    for (int a = blockIdx.x * INTER_WARPS + warp; a < n_mbs; a += gridDim.x * INTER_WARPS) {
-        h264r_mb_hdr h = load_hdr(pd, a);
+    // the header of the warp's NEXT macroblock is fetched while the current one is reconstructed: it heads the
+    // dependent chain header -> vectors -> window addresses -> reference loads
+    const int stride = gridDim.x * INTER_WARPS;
+    int a = blockIdx.x * INTER_WARPS + warp;
+    int4 hraw = a < n_mbs ? __ldg(reinterpret_cast<const int4*>(pd.hdr + a)) : int4{0, 0, 0, 0};
+    for (; a < n_mbs; a += stride) {
+        h264r_mb_hdr h = *reinterpret_cast<h264r_mb_hdr*>(&hraw);
+        if (a + stride < n_mbs) hraw = __ldg(reinterpret_cast<const int4*>(pd.hdr + a + stride));
         if (is_intra(h.mb_class)) continue;       // warp-uniform; k_intra_rows reconstructs it afterwards
         seq_inter_any<COMPAT, TMA>(ex, w, pd, g, h, a);
     }

@@ -330,25 +330,37 @@ def main():
 
     clocks = ClockSampler(local) if rank == 0 else None
     # ---- resident: kernels only, syntax already in HBM ------------------------------------------------
-    eng.set_profiling(not os.environ.get("H264R_BENCH_NOPROF"))       # per-launch events can be switched off to check they cost nothing
     barrier()
     torch.cuda.cudart().cudaProfilerStart()       # `ncu --profile-from-start off` sees exactly the timed resident steps
     kern_ms = 0.0
-    fam_ms = np.zeros(5)
-    fam_n = np.zeros(5, dtype=np.int64)
     for _ in range(args.steps):
         submit_all()
         eng.wait_uploads()              # inputs are resident in HBM before the timed flush
         eng.flush()
-        ms, flush_launches = eng.last_flush_stats()
+        ms, flush_launches = eng.last_flush_stats()       # events on the engine's stream around the whole flush
         kern_ms += ms
+    torch.cuda.cudart().cudaProfilerStop()
+    barrier()
+    # ---- per-kernel times: the same steps on ONE lane with an event pair around every launch.  (In the timed steps
+    # the kernels of the four lanes overlap, so their individual durations say nothing about a kernel.)
+    eng.set_lanes(1)
+    eng.set_profiling(True)
+    fam_ms = np.zeros(5)
+    fam_n = np.zeros(5, dtype=np.int64)
+    serial_ms = 0.0
+    prof_steps = min(args.steps, 3)
+    for _ in range(prof_steps):
+        submit_all()
+        eng.wait_uploads()
+        eng.flush()
+        serial_ms += eng.last_flush_stats()[0]
         fm, fn = eng.last_flush_kernel_ms()
         launch_ms = eng.last_flush_launch_ms()
         fam_ms += np.array(fm)
         fam_n += np.array(fn)
-    torch.cuda.cudart().cudaProfilerStop()
-    barrier()
     eng.set_profiling(False)
+    eng.set_lanes(int(os.environ.get("H264R_LANES", "4")))
+    barrier()
     # ---- e2e: host buffers in, digests out -------------------------------------------------------------
     barrier()
     e2e_ms = 0.0
@@ -392,7 +404,7 @@ def main():
             units = G * F * N_MBS - inter_mbs
         else:
             units = G * F * N_MBS
-        bytes_per_launch = per_mb[fam] * units / max(1, fam_n[fam] / args.steps)
+        bytes_per_launch = per_mb[fam] * units / max(1, fam_n[fam] / prof_steps)
         sec_per_launch = fam_ms[fam] / 1000.0 / max(1, fam_n[fam])
         achieved = bytes_per_launch / sec_per_launch / 1e9 if sec_per_launch > 0 else 0.0
         traffic = None
@@ -417,7 +429,9 @@ def main():
             # kernels launched inside the timed regions: the resident steps (one flush each) + the e2e steps (the same
             # kernels, queued round by round, + one digest launch)
             "gpu_launches": int(args.steps * (2 * flush_launches + 1)),
-            "kernel_ms_per_step": {"inter": fam_ms[0] / args.steps, "intra": fam_ms[1] / args.steps, "deblock": fam_ms[2] / args.steps, "pad": fam_ms[3] / args.steps, "digest": fam_ms[4] / args.steps},
+            "kernel_ms_per_step": {"inter": fam_ms[0] / prof_steps, "intra": fam_ms[1] / prof_steps, "deblock": fam_ms[2] / prof_steps, "pad": fam_ms[3] / prof_steps, "digest": fam_ms[4] / prof_steps,
+                                   "step_on_one_lane": serial_ms / prof_steps,
+                                   "note": "per-launch events, one lane, %d extra steps after the timed ones; the timed steps run four lanes whose kernels overlap" % prof_steps},
             "roofline": {"bound": "hbm", "kernel": names[fam], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch,
                          "avg_launch_ms": sec_per_launch * 1000.0},

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,7 +43,8 @@ struct h264r_ctx {
     uint32_t flags = 0;
     cudaStream_t stream = nullptr;          // kernels, read-back
     cudaStream_t copy_stream = nullptr;     // syntax uploads: overlap the kernels of earlier waves / flushes
-    int n_lanes = 1;                        // independent kernel pipelines (see h264r_flush)
+    int n_lanes = 1;                        // independent kernel pipelines (see h264r_flush) in use
+    int n_lanes_created = 1;
     int inter_ctas_per_sm = 6;
     cudaStream_t lane_stream[8] = {};
     cudaEvent_t ev_lane[8] = {};
@@ -251,6 +253,7 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
         const char* e = getenv("H264R_LANES");      // tuning knob; 1 = a single pipeline
         int nl = e ? atoi(e) : 4;
         c->n_lanes = nl < 1 ? 1 : (nl > 8 ? 8 : nl);
+        c->n_lanes_created = c->n_lanes;
         const char* e2 = getenv("H264R_INTER_CTAS");
         if (e2 && atoi(e2) > 0) c->inter_ctas_per_sm = atoi(e2);
     }
@@ -784,6 +787,18 @@ int h264r_sync(h264r_ctx* ctx)
     if (r != H264R_OK) return r;
     CU(cudaStreamSynchronize(ctx->copy_stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return H264R_OK;
+}
+
+int h264r_set_lanes(h264r_ctx* ctx, int lanes)
+{
+    if (!ctx || lanes < 1) return fail(ctx, H264R_E_INVAL, "set_lanes: bad argument");
+    int r = h264r_sync(ctx);
+    if (r != H264R_OK) return r;
+    for (int l = 0; l < ctx->n_lanes_created; l++) CU(cudaStreamSynchronize(ctx->lane_stream[l]));
+    ctx->n_lanes = lanes < ctx->n_lanes_created ? lanes : ctx->n_lanes_created;
+    std::fill(ctx->frame_lane.begin(), ctx->frame_lane.end(), -1);      // everything is complete: no stream order to preserve
+    ctx->next_lane = 0;
     return H264R_OK;
 }
 

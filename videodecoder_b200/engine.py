@@ -53,6 +53,7 @@ def load_library():
     L.h264r_submit_mbs.argtypes = [vp, ci, ci, ci, vp, vp, vp]
     L.h264r_submit_mbs_packed.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, ctypes.c_size_t]
     L.h264r_wait_uploads.argtypes = [vp]
+    L.h264r_set_lanes.argtypes = [vp, ci]
     L.h264r_picture_buf_alloc.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(PictureBufStruct)]
     L.h264r_picture_buf_free.argtypes = [vp, ctypes.POINTER(PictureBufStruct)]
     L.h264r_picture_buf_free.restype = None
@@ -82,7 +83,7 @@ def load_library():
 
 EXPORTS = [
     "h264r_abi_version", "h264r_last_error", "h264r_create", "h264r_destroy", "h264r_host_alloc", "h264r_host_free",
-    "h264r_frame_begin", "h264r_submit_mbs", "h264r_submit_mbs_packed", "h264r_wait_uploads", "h264r_picture_buf_alloc", "h264r_picture_buf_free", "h264r_submit_picture", "h264r_frame_end", "h264r_flush", "h264r_sync", "h264r_read_planes",
+    "h264r_frame_begin", "h264r_submit_mbs", "h264r_submit_mbs_packed", "h264r_wait_uploads", "h264r_set_lanes", "h264r_picture_buf_alloc", "h264r_picture_buf_free", "h264r_submit_picture", "h264r_frame_end", "h264r_flush", "h264r_sync", "h264r_read_planes",
     "h264r_frame_digest", "h264r_frame_digests", "h264r_range_excursions", "h264r_excursion_map",
     "h264r_residual_mbs", "h264r_release", "h264r_last_flush_stats", "h264r_set_profiling",
     "h264r_last_flush_kernel_ms", "h264r_last_flush_launch_ms", "h264r_mark", "h264r_elapsed_ms",
@@ -213,6 +214,9 @@ class Engine:
         n_blocks = 0 if blocks is None else int(blocks.size // 16)
         self._check(self.L.h264r_submit_mbs_packed(self.ctx, frame_id, first_mb, n, _ptr(hdr), _ptr(mv), _ptr(blk_mask), _ptr(blocks),
                                                    n_blocks))
+
+    def set_lanes(self, lanes):
+        self._check(self.L.h264r_set_lanes(self.ctx, lanes))
 
     def wait_uploads(self):
         self._check(self.L.h264r_wait_uploads(self.ctx))

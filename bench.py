@@ -342,7 +342,8 @@ def main():
     torch.cuda.cudart().cudaProfilerStop()
     barrier()
     # ---- per-kernel times: the same steps on ONE lane with an event pair around every launch.  (In the timed steps
-    # the kernels of the four lanes overlap, so their individual durations say nothing about a kernel.)
+    # launches follow each other without events in between -- an event pair costs a short kernel tens of microseconds --
+    # and, with H264R_LANES > 1, the kernels of the lanes overlap.)
     eng.set_lanes(1)
     eng.set_profiling(True)
     fam_ms = np.zeros(5)
@@ -359,7 +360,7 @@ def main():
         fam_ms += np.array(fm)
         fam_n += np.array(fn)
     eng.set_profiling(False)
-    eng.set_lanes(int(os.environ.get("H264R_LANES", "4")))
+    eng.set_lanes(int(os.environ.get("H264R_LANES", "1")))
     barrier()
     # ---- e2e: host buffers in, digests out -------------------------------------------------------------
     barrier()
@@ -431,7 +432,7 @@ def main():
             "gpu_launches": int(args.steps * (2 * flush_launches + 1)),
             "kernel_ms_per_step": {"inter": fam_ms[0] / prof_steps, "intra": fam_ms[1] / prof_steps, "deblock": fam_ms[2] / prof_steps, "pad": fam_ms[3] / prof_steps, "digest": fam_ms[4] / prof_steps,
                                    "step_on_one_lane": serial_ms / prof_steps,
-                                   "note": "per-launch events, one lane, %d extra steps after the timed ones; the timed steps run four lanes whose kernels overlap" % prof_steps},
+                                   "note": "per-launch events, one lane, %d extra steps after the timed ones; event pairs inflate the short launches" % prof_steps},
             "roofline": {"bound": "hbm", "kernel": names[fam], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch,
                          "avg_launch_ms": sec_per_launch * 1000.0},

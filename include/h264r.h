@@ -234,7 +234,7 @@ int h264r_sync(h264r_ctx* ctx);
 
 /* Number of independent kernel pipelines ("lanes", one CUDA stream each) the scheduler spreads prediction chains over;
  * 1 = every kernel of a flush in one stream, in order (what per-kernel timing wants).  Clamped to the number the
- * context was created with (4 unless H264R_LANES says otherwise).  Synchronises the context. */
+ * context was created with (1 unless H264R_LANES says otherwise).  Synchronises the context. */
 int h264r_set_lanes(h264r_ctx* ctx, int lanes);
 
 /* Waits until every syntax buffer submitted so far is resident in device memory (uploads run on their own

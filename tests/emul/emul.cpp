@@ -256,6 +256,14 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
         } else
             for (int a = 0; a < n; a++) seq_deblock_mb(ex, w, pd, g, a);
     }
+    if (compat && use_fast_intra) {
+        // REF_COMPAT: the warps of the border macroblocks wrote the luma border themselves (phase_pad_mb_luma, device
+        // sequences only: the generic intra phases are not run by any kernel in this mode); it must be what k_pad would
+        // have written
+        PaddedFrame chk = cur;
+        chk.pad();
+        if (chk.buf_y != cur.buf_y) { fprintf(stderr, "fused border replication disagrees with pad_row_phase\n"); abort(); }
+    }
     cur.store(y, u, v);
     exc = *pd.exc_counter;
     return exc;

@@ -45,9 +45,22 @@ struct h264r_ctx {
     cudaStream_t copy_stream = nullptr;     // syntax uploads: overlap the kernels of earlier waves / flushes
     int n_lanes = 1;                        // independent kernel pipelines (see h264r_flush) in use
     int n_lanes_created = 1;
-    int inter_ctas_per_sm = 6;
+    int inter_ctas_per_sm = 8;
+    bool sparse_intra = true;               // k_intra_sparse for P pictures with few intra macroblocks (H264R_SPARSE_INTRA=0: row wavefront)
     cudaStream_t lane_stream[8] = {};
     cudaEvent_t ev_lane[8] = {};
+    // side streams: work that nothing in a lane's chain picture -> next picture waits for stays out of the lanes.
+    // prep: block / vector offset scans of uploaded pictures (run ahead of the lanes, behind the uploads);
+    // dig: K5 of finished pictures (runs behind the lanes)
+    cudaStream_t prep_stream = nullptr, dig_stream = nullptr;
+    cudaEvent_t ev_scan[8] = {}, ev_wave[8] = {};
+    cudaEvent_t ev_tok = nullptr;           // the k_inter launches of the lanes take turns (see h264r_flush)
+    bool inter_token = true;
+    int inter_generations = 1;              // k_inter grid = SMs x inter_ctas_per_sm x this (1: persistent warps)
+    cudaEvent_t ev_dig[64] = {};            // ring: digest launch number n is done
+    uint64_t dig_seq = 0;
+    uint64_t lane_dig_waited[8] = {};
+    std::vector<uint64_t> frame_dig_seq;    // digest launch that last READ a frame slot (a new picture in the slot waits for it)
     cudaEvent_t ev_main = nullptr;
     bool main_dirty = false;                // the main stream holds work the lanes must wait for
     int next_lane = 0;
@@ -79,7 +92,8 @@ struct h264r_ctx {
     // arena slot = what the uploads carry, in this order: descriptor | hdr | blk_mask | mv | coefficient blocks;
     // then blk_off and mv_off (written by k_blk_scan, never uploaded)
     // then the residual scratch of the intra macroblocks (device only)
-    size_t slot_bytes = 0, off_desc = 0, off_hdr = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_mvoff = 0, off_coeff = 0, off_res = 0, off_nz = 0, off_dbrec = 0;
+    size_t slot_bytes = 0, off_desc = 0, off_hdr = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_mvoff = 0, off_coeff = 0, off_res = 0, off_nz = 0, off_dbrec = 0, off_ilist = 0, off_idone = 0;
+    int sparse_stamp = 0;                   // launch stamp of k_intra_list (intra_done words of older launches are smaller)
     // per-flush control block (descriptors + picture lists), pinned host mirror + device copy
     uint8_t* h_ctrl = nullptr;
     size_t ctrl_bytes = 0;
@@ -150,6 +164,9 @@ void fill_desc(h264r_ctx* c, const Pending& p, PicDesc& pd)
     pd.dbrec = s + c->off_dbrec;
     pd.tmaps = c->d_tmaps;
     pd.mv_off = p.mv_partition ? reinterpret_cast<const uint32_t*>(s + c->off_mvoff) : nullptr;
+    pd.packed = p.layout == 2;
+    pd.intra_list = reinterpret_cast<uint32_t*>(s + c->off_ilist);
+    pd.intra_done = reinterpret_cast<int32_t*>(s + c->off_idone);
     // k_residual_pics leaves the residual of the intra macroblocks here, ahead of the wavefront
     pd.residual = p.n_intra > 0 ? reinterpret_cast<int16_t*>(s + c->off_res) : nullptr;
     pd.y = c->frame_y(p.frame_id); pd.u = c->frame_u(p.frame_id); pd.v = c->frame_v(p.frame_id);
@@ -236,7 +253,9 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     c->off_res = c->off_mvoff + align_up((size_t)c->n_mbs * 4, 256);
     c->off_nz = c->off_res + align_up((size_t)c->n_mbs * 768, 256);
     c->off_dbrec = c->off_nz + align_up((size_t)c->n_mbs * 4, 256);
-    c->slot_bytes = c->off_dbrec + ((flags & H264R_REF_COMPAT) ? 0 : align_up((size_t)c->n_mbs * DBREC_BYTES, 256));
+    c->off_ilist = c->off_dbrec + ((flags & H264R_REF_COMPAT) ? 0 : align_up((size_t)c->n_mbs * DBREC_BYTES, 256));
+    c->off_idone = c->off_ilist + align_up((size_t)(c->n_mbs + 1) * 4, 256);
+    c->slot_bytes = c->off_idone + align_up((size_t)c->n_mbs * 4, 256);
     c->ctrl_bytes = align_up((size_t)max_pending * sizeof(PicDesc), 256);      // descriptor table, one entry per arena slot
     auto cleanup = [&](int code) { h264r_destroy(c); return code; };
 #define CUC(call)                                                                                             \
@@ -251,9 +270,15 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     {
         const char* e = getenv("H264R_LANES");      // tuning knob; 1 = a single pipeline
-        int nl = e ? atoi(e) : 4;
+        int nl = e ? atoi(e) : 1;
         c->n_lanes = nl < 1 ? 1 : (nl > 8 ? 8 : nl);
         c->n_lanes_created = c->n_lanes;
+        const char* e4 = getenv("H264R_INTER_TOKEN");
+        if (e4) c->inter_token = atoi(e4) != 0;
+        const char* e5 = getenv("H264R_INTER_GENS");
+        if (e5 && atoi(e5) > 0) c->inter_generations = atoi(e5);
+        const char* e3 = getenv("H264R_SPARSE_INTRA");
+        if (e3) c->sparse_intra = atoi(e3) != 0;
         const char* e2 = getenv("H264R_INTER_CTAS");
         if (e2 && atoi(e2) > 0) c->inter_ctas_per_sm = atoi(e2);
     }
@@ -262,6 +287,15 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
         CUC(cudaEventCreateWithFlags(&c->ev_lane[l], cudaEventDisableTiming));
     }
     CUC(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+    CUC(cudaStreamCreateWithFlags(&c->prep_stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->dig_stream, cudaStreamNonBlocking));
+    for (int l = 0; l < 8; l++) {
+        CUC(cudaEventCreateWithFlags(&c->ev_scan[l], cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&c->ev_wave[l], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < 64; i++) CUC(cudaEventCreateWithFlags(&c->ev_dig[i], cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&c->ev_tok, cudaEventDisableTiming));
+    c->frame_dig_seq.assign(max_frames, 0);
     c->frame_lane.assign(max_frames, -1);
     c->ev_copied.assign(max_pending, nullptr);
     for (int i = 0; i < max_pending; i++) CUC(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
@@ -323,6 +357,7 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     CUC(cudaMalloc(&c->d_syntax, c->slot_bytes * max_pending));
     CUC(cudaMallocHost(&c->h_ctrl, c->ctrl_bytes));
     CUC(cudaMemsetAsync(c->d_exc_counter, 0, 256, c->stream));
+    for (int s = 0; s < max_pending; s++) CUC(cudaMemsetAsync(c->slot_ptr(s) + c->off_idone, 0, (size_t)c->n_mbs * 4, c->stream));
     CUC(cudaMemsetAsync(c->d_exc_maps, 0, (size_t)max_frames * c->n_mbs, c->stream));
     // ring of hand-over words: in flight are at most max_pending pictures x 2 wavefront kernels x (H + 1) words
     c->sync_ints = (size_t)8 * max_pending * (h_mbs + 1) + 1024;
@@ -342,11 +377,19 @@ void h264r_destroy(h264r_ctx* c)
     cudaSetDevice(c->device);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     for (int l = 0; l < 8; l++) if (c->lane_stream[l]) cudaStreamSynchronize(c->lane_stream[l]);
+    if (c->prep_stream) cudaStreamSynchronize(c->prep_stream);
+    if (c->dig_stream) cudaStreamSynchronize(c->dig_stream);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int l = 0; l < 8; l++) {
         if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
         if (c->ev_lane[l]) cudaEventDestroy(c->ev_lane[l]);
+        if (c->ev_scan[l]) cudaEventDestroy(c->ev_scan[l]);
+        if (c->ev_wave[l]) cudaEventDestroy(c->ev_wave[l]);
     }
+    for (auto e : c->ev_dig) if (e) cudaEventDestroy(e);
+    if (c->ev_tok) cudaEventDestroy(c->ev_tok);
+    if (c->prep_stream) cudaStreamDestroy(c->prep_stream);
+    if (c->dig_stream) cudaStreamDestroy(c->dig_stream);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     cudaFree(c->d_dense_mask); cudaFree(c->d_dense_off); cudaFree(c->d_tmaps);
     for (auto e : c->ev_copied) if (e) cudaEventDestroy(e);
@@ -620,6 +663,7 @@ int h264r_flush(h264r_ctx* ctx)
     ctx->kev_used = 0;
     ctx->kev_family.clear();
     cudaStream_t st = nullptr;       // stream of the lane being issued
+    cudaStream_t prof_st = nullptr;  // stream of the launch being timed (null: the lane's)
     auto prof_begin = [&](int family) {
         if (!ctx->profiling) return;
         if ((int)ctx->kev.size() < ctx->kev_used + 2) {
@@ -628,11 +672,11 @@ int h264r_flush(h264r_ctx* ctx)
             ctx->kev.push_back(a); ctx->kev.push_back(b);
         }
         ctx->kev_family.push_back(family);
-        cudaEventRecord(ctx->kev[ctx->kev_used], st);
+        cudaEventRecord(ctx->kev[ctx->kev_used], prof_st ? prof_st : st);
     };
     auto prof_end = [&]() {
         if (!ctx->profiling) return;
-        cudaEventRecord(ctx->kev[ctx->kev_used + 1], st);
+        cudaEventRecord(ctx->kev[ctx->kev_used + 1], prof_st ? prof_st : st);
         ctx->kev_used += 2;
     };
     // hand-over words of one wavefront launch: a zeroed region of the ring (a region comes round again only after
@@ -659,6 +703,7 @@ int h264r_flush(h264r_ctx* ctx)
         if (list.n) { list_frames.n = list.n; f(list); }
     };
     std::vector<uint8_t> lane_used(NL, 0);
+    bool dig_used = false, tok_valid = false;
     for (int wv = 0; wv < n_waves; wv++) {
         for (int lane = 0; lane < NL; lane++) {
             cur_wave = wv; cur_lane = lane;
@@ -674,32 +719,80 @@ int h264r_flush(h264r_ctx* ctx)
                 }
             if (!last) continue;
             lane_used[lane] = 1;
-            CU(cudaStreamWaitEvent(st, ctx->ev_copied[last->slot], 0));
+            // block / vector offsets of the pictures that arrived packed: on the prep stream, behind the uploads and
+            // ahead of the lanes (in a resident batch the scans of all waves are done while wave 0 computes)
+            bool scanned = false;
+            auto sparse = [&](const Pending& p) { return ctx->sparse_intra && p.pp.slice_type == H264R_SLICE_P && p.n_intra > 0 && p.n_intra * 8 < ctx->n_mbs; };
+            for_chunks([&](const Pending& p) { return p.layout == 2 || sparse(p); }, [&](const PicList& L) {
+                if (!scanned) cudaStreamWaitEvent(ctx->prep_stream, ctx->ev_copied[last->slot], 0);
+                scanned = true;
+                k_blk_scan<<<L.n, 1024, 0, ctx->prep_stream>>>(d_desc, L, ctx->n_mbs);
+                ctx->last_launches++;
+            });
+            if (scanned) {
+                CU(cudaEventRecord(ctx->ev_scan[lane], ctx->prep_stream));
+                CU(cudaStreamWaitEvent(st, ctx->ev_scan[lane], 0));
+            } else CU(cudaStreamWaitEvent(st, ctx->ev_copied[last->slot], 0));
+            // a frame slot whose previous picture is still being digested (dig stream) must not be overwritten
+            {
+                uint64_t need = 0;
+                for (int i = 0; i < n; i++)
+                    if (run[i]->wave == wv && run[i]->lane == lane) need = std::max(need, ctx->frame_dig_seq[run[i]->frame_id]);
+                if (need > ctx->lane_dig_waited[lane]) {
+                    CU(cudaStreamWaitEvent(st, ctx->ev_dig[need & 63], 0));
+                    ctx->lane_dig_waited[lane] = need;
+                }
+            }
             for (int l = 0; l < NL; l++)
                 if ((wait_lanes >> l) & 1u) {           // references (or the frame slot's old readers) live on another lane
                     CU(cudaEventRecord(ctx->ev_lane[l], ctx->lane_stream[l]));
                     CU(cudaStreamWaitEvent(st, ctx->ev_lane[l], 0));
                 }
-            // block / vector offsets of the pictures that arrived packed
-            for_chunks([&](const Pending& p) { return p.layout == 2; }, [&](const PicList& L) {
-                k_blk_scan<<<L.n, 1024, 0, st>>>(d_desc, L, ctx->n_mbs);
-                ctx->last_launches++;
-            });
             for_chunks([&](const Pending& p) { return p.pp.slice_type == H264R_SLICE_P && p.n_intra < ctx->n_mbs; }, [&](const PicList& L) {
                 // grid.y = picture, grid.x strides over its macroblocks.  With several lanes the grid is persistent and
                 // sized below the SMs' capacity (inter_ctas_per_sm of 8), so that the wavefront kernels of the other
                 // lanes always find room next to it; with one lane about eight CTA generations.
                 int want = (ctx->n_mbs + INTER_WARPS - 1) / INTER_WARPS;
-                int cap = NL > 1 ? (sm_count * ctx->inter_ctas_per_sm + L.n - 1) / L.n : (sm_count * 16 * 8 + L.n - 1) / L.n;
+                int cap = (sm_count * ctx->inter_ctas_per_sm * ctx->inter_generations + L.n - 1) / L.n;
                 dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)L.n);
+                // the throughput-bound launches of the lanes take turns (they would only share the SMs); what overlaps
+                // them is the latency-bound tail (intra macroblocks) of the OTHER lanes
+                if (NL > 1 && ctx->inter_token && tok_valid) cudaStreamWaitEvent(st, ctx->ev_tok, 0);      // (errors surface at the flush's cudaGetLastError)
                 prof_begin(0);
                 const bool tma = ctx->d_tmaps != nullptr;
                 if (compat) { if (tma) k_inter<true, true><<<grid, INTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); else k_inter<true, false><<<grid, INTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); }
                 else { if (tma) k_inter<false, true><<<grid, INTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); else k_inter<false, false><<<grid, INTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); }
                 prof_end();
+                if (NL > 1 && ctx->inter_token) { cudaEventRecord(ctx->ev_tok, st); tok_valid = true; }
                 ctx->last_launches++;
             });
-            for_chunks([&](const Pending& p) { return p.n_intra > 0; }, [&](const PicList& L) {
+            // intra macroblocks.  Few and scattered (P pictures): one launch, a warp ticket per macroblock of the lists
+            // k_blk_scan made.  Otherwise the residual pre-pass and the row wavefront.
+            {
+                SparseList SL;
+                SL.n = 0; SL.cum[0] = 0;
+                auto launch = [&]() {
+                    if (!SL.n) return;
+                    const int total = SL.cum[SL.n];
+                    int blocks = std::min((total + ROW_WARPS - 1) / ROW_WARPS, sm_count * 4);      // persistent warps
+                    int* sync = sync_region(1);       // the ticket
+                    ctx->sparse_stamp++;
+                    prof_begin(1);
+                    if (compat) k_intra_list<true><<<blocks, ROW_WARPS * 32, 0, st>>>(d_desc, SL, ctx->g, sync, ctx->sparse_stamp);
+                    else k_intra_list<false><<<blocks, ROW_WARPS * 32, 0, st>>>(d_desc, SL, ctx->g, sync, ctx->sparse_stamp);
+                    prof_end();
+                    ctx->last_launches++;
+                    SL.n = 0;
+                };
+                for (int i = 0; i < n; i++) {
+                    if (run[i]->wave != wv || run[i]->lane != lane || !sparse(*run[i])) continue;
+                    SL.slot[SL.n] = run[i]->slot;
+                    SL.cum[SL.n + 1] = SL.cum[SL.n] + run[i]->n_intra;
+                    if (++SL.n == SPARSE_PICS) launch();
+                }
+                launch();
+            }
+            for_chunks([&](const Pending& p) { return p.n_intra > 0 && !sparse(p); }, [&](const PicList& L) {
                 int want = (ctx->n_mbs + INTER_WARPS * 32 - 1) / (INTER_WARPS * 32);       // 32 macroblocks per warp
                 dim3 grid((unsigned)want, (unsigned)L.n);
                 prof_begin(1);
@@ -708,7 +801,7 @@ int h264r_flush(h264r_ctx* ctx)
                 prof_end();
                 ctx->last_launches++;
             });
-            for_chunks([&](const Pending& p) { return p.n_intra > 0; }, [&](const PicList& L) {
+            for_chunks([&](const Pending& p) { return p.n_intra > 0 && !sparse(p); }, [&](const PicList& L) {
                 int rows = L.n * ctx->g.h_mbs, blocks = (rows + ROW_WARPS - 1) / ROW_WARPS;
                 int* sync = sync_region((size_t)rows + 1);        // progress words, then the ticket
                 prof_begin(1);
@@ -733,27 +826,38 @@ int h264r_flush(h264r_ctx* ctx)
                 prof_end();
                 ctx->last_launches++;
             });
-            // border replication (and digest) of the finished pictures
-            for_chunks([&](const Pending&) { return true; }, [&](const PicList& L) {
-                int rows = ctx->g.h_mbs * 16 + 2 * PAD_Y + (compat ? 0 : 2 * (ctx->g.h_mbs * 8 + 2 * PAD_YC));
-                long warps = (long)L.n * rows;
-                long cap = (long)sm_count * 16;
-                int blocks = (int)((warps + 3) / 4 < cap ? (warps + 3) / 4 : cap);
-                prof_begin(3);
-                const bool dig = (ctx->flags & H264R_DIGESTS) != 0;
-                k_pad<<<blocks, 128, 0, st>>>(d_desc, L, ctx->g, compat ? 0 : 1, dig ? ctx->d_digests : nullptr);
-                prof_end();
-                ctx->last_launches++;
-                if (dig) {
-                    // K5 as part of the reconstruction: frame ids of this chunk
-                    const PicList& F = list_frames;
-                    prof_begin(4);
-                    k_digest<<<dim3(DIGEST_CTAS, F.n), 256, 0, st>>>(digest_pool(ctx), F, ctx->g, ctx->d_digests);
+            // border replication of the finished pictures.  REF_COMPAT: the warps of the border macroblocks wrote it
+            // (phase_pad_mb_luma), nothing to launch.
+            if (!compat)
+                for_chunks([&](const Pending&) { return true; }, [&](const PicList& L) {
+                    int rows = ctx->g.h_mbs * 16 + 2 * PAD_Y + 2 * (ctx->g.h_mbs * 8 + 2 * PAD_YC);
+                    long warps = (long)L.n * rows;
+                    long cap = (long)sm_count * 16;
+                    int blocks = (int)((warps + 3) / 4 < cap ? (warps + 3) / 4 : cap);
+                    prof_begin(3);
+                    k_pad<<<blocks, 128, 0, st>>>(d_desc, L, ctx->g, 1, nullptr);
                     prof_end();
                     ctx->last_launches++;
-                    for (int i = 0; i < F.n; i++) ctx->digest_valid[F.slot[i]] = 1;
-                }
-            });
+                });
+            // K5 as part of the reconstruction, on the dig stream: nothing in the lane waits for it
+            if (ctx->flags & H264R_DIGESTS) {
+                CU(cudaEventRecord(ctx->ev_wave[lane], st));
+                CU(cudaStreamWaitEvent(ctx->dig_stream, ctx->ev_wave[lane], 0));
+                prof_st = ctx->dig_stream;
+                for_chunks([&](const Pending&) { return true; }, [&](const PicList&) {
+                    const PicList& F = list_frames;      // frame ids of this chunk
+                    k_zero_digests<<<1, 256, 0, ctx->dig_stream>>>(F, ctx->d_digests);
+                    prof_begin(4);
+                    k_digest<<<dim3(DIGEST_CTAS, F.n), 256, 0, ctx->dig_stream>>>(digest_pool(ctx), F, ctx->g, ctx->d_digests);
+                    prof_end();
+                    ctx->last_launches += 2;
+                    ctx->dig_seq++;
+                    cudaEventRecord(ctx->ev_dig[ctx->dig_seq & 63], ctx->dig_stream);
+                    for (int i = 0; i < F.n; i++) { ctx->digest_valid[F.slot[i]] = 1; ctx->frame_dig_seq[F.slot[i]] = ctx->dig_seq; }
+                });
+                prof_st = nullptr;
+                dig_used = true;
+            }
         }
     }
     // join: the main stream (read-backs, timing, slot reuse) continues when every lane has finished this flush
@@ -762,6 +866,7 @@ int h264r_flush(h264r_ctx* ctx)
             CU(cudaEventRecord(ctx->ev_lane[l], ctx->lane_stream[l]));
             CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_lane[l], 0));
         }
+    if (dig_used) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_dig[ctx->dig_seq & 63], 0));      // the dig stream runs in order: its last launch
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaGetLastError());
     ctx->timing_valid = true;

@@ -88,7 +88,10 @@ struct PicDesc {
     uint32_t* exc_counter;     // luma samples that left [0,255] before the store (see report_excursions)
     uint32_t* digest;          // 4 words
     int32_t frame_id;
-    int32_t pad_;
+    int32_t packed;            // 1: blk_off / mv_off belong to this picture and k_blk_scan fills them
+    uint32_t* intra_list;      // device only, written by k_blk_scan: [0] = number of intra macroblocks, then their addresses in
+                               // ascending order (work list of k_intra_list)
+    int32_t* intra_done;       // device only, per macroblock: the launch stamp of the k_intra_list launch that finished it
 };
 
 // Shared working set of one warp (one macroblock in flight).

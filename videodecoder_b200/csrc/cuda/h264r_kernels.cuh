@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, H264R_INTER_MIN_CTAS) k_inte
     for (; a < n_mbs; a += stride) {
         h264r_mb_hdr h = *reinterpret_cast<h264r_mb_hdr*>(&hraw);
         if (a + stride < n_mbs) hraw = __ldg(reinterpret_cast<const int4*>(pd.hdr + a + stride));
-        if (is_intra(h.mb_class)) continue;       // warp-uniform; k_intra_rows reconstructs it afterwards
+        if (is_intra(h.mb_class)) continue;       // warp-uniform; the intra kernels reconstruct it afterwards
         seq_inter_any<COMPAT, TMA>(ex, w, pd, g, h, a);
     }
 }
@@ -179,7 +179,11 @@ __device__ __forceinline__ int ld_relaxed_gpu(const int* p)
 __device__ __forceinline__ void wait_progress(const int* p, int need)
 {
     if (ld_relaxed_gpu(p) < need) {
-        do { __nanosleep(20); } while (ld_relaxed_gpu(p) < need);
+        int spins = 0;
+        do {
+            __nanosleep(20);
+            if (++spins > (1 << 24)) __trap();       // seconds: a hand-over that never comes must end the launch, not hang the GPU
+        } while (ld_relaxed_gpu(p) < need);
     }
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
@@ -278,6 +282,73 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_intra_rows(const DescTabl
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1+K2 for the intra macroblocks of P pictures, where they are few and scattered: one warp TICKET per intra
+// macroblock instead of one warp per row.  k_blk_scan (prep stream, long before) left every picture's intra
+// macroblocks as a list in address order; tickets run over the lists of the launch's pictures, so a warp
+// reconstructs one macroblock -- residual included: k_residual_pics and the scratch round trip disappear for these
+// pictures -- and takes the next ticket.  The inter macroblocks are final (k_inter ran before this launch); an intra
+// neighbour A, D, B, C has a LOWER address, hence a lower ticket: it is finished or held by a running warp, which
+// stamps intra_done[address] with the launch's stamp when it is through (only if one of the four macroblocks that read
+// its samples is an intra macroblock -- otherwise nobody will ask).  With 3 % intra macroblocks nearly all of them
+// start at once and the launch lasts about two macroblocks.
+// ------------------------------------------------------------------------------------------------
+constexpr int SPARSE_PICS = 64;
+struct SparseList { int n; int slot[SPARSE_PICS]; int cum[SPARSE_PICS + 1]; };      // cum[i] = tickets before picture i
+template <bool COMPAT>
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_intra_list(const DescTable descs, const __grid_constant__ SparseList list,
+                                                              Geometry g, int* ticket, int stamp)
+{
+    __shared__ MbWork work[ROW_WARPS];
+    __shared__ uint16_t s_lut[INTRA4_LUT_SIZE];
+    intra4_lut_fill(s_lut, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int W = g.w_mbs, H = g.h_mbs, total = list.cum[list.n];
+    WarpExec ex{(int)(threadIdx.x & 31)};
+    MbWork& w = work[threadIdx.x >> 5];
+    int p = 0;
+    for (;;) {
+        int t = 0;
+        if (ex.lane == 0) t = atomicAdd(ticket, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= total) break;
+        while (t >= list.cum[p + 1]) p++;          // tickets only grow
+        const PicDesc& pd = descs[list.slot[p]];
+        const int idx = t - list.cum[p];
+        if (idx >= (int)H264R_LDG(pd.intra_list)) continue;      // the host's count was an upper bound
+        const int a = (int)H264R_LDG(pd.intra_list + 1 + idx);
+        const h264r_mb_hdr h = load_hdr(pd, a);
+
+        int mbx, mby;
+        mb_xy(g, a, mbx, mby);
+        // lanes 0..3 look at A, D, B, C (an intra one must have been stamped), lanes 4..7 at the four macroblocks that
+        // read this one's samples (if none is intra, the stamp -- a fence -- is skipped)
+        bool publish;
+        {
+            const int l = ex.lane & 3;
+            const bool up = ex.lane < 4;
+            const int d = l == 0 ? 1 : (l == 1 ? W + 1 : (l == 2 ? W : W - 1));
+            const int nb = up ? a - d : a + d;
+            bool exists;
+            if (up) exists = l == 0 ? mbx > 0 : (l == 1 ? mbx > 0 && mby > 0 : (l == 2 ? mby > 0 : mby > 0 && mbx < W - 1));
+            else exists = l == 0 ? mbx < W - 1 : (l == 1 ? mbx < W - 1 && mby < H - 1 : (l == 2 ? mby < H - 1 : mby < H - 1 && mbx > 0));
+            const bool hit = ex.lane < 8 && exists && is_intra(H264R_LDG(&pd.hdr[nb].mb_class));
+            const uint32_t hm = __ballot_sync(0xffffffffu, hit);
+            publish = (hm & 0xf0u) != 0;
+            uint32_t wm = hm & 0xfu;
+            while (wm) {          // every lane waits (one address per neighbour): its own acquire orders its own loads
+                const int j = __ffs(wm) - 1;
+                wm &= wm - 1;
+                const int nbj = __shfl_sync(0xffffffffu, nb, j);
+                wait_progress(pd.intra_done + nbj, stamp);
+            }
+        }
+        seq_intra_any<COMPAT>(ex, w, s_lut, pd, g, h, a, false, false);
+        // ex() ended with __syncwarp(): every lane's stores precede lane 0's release
+        if (publish && ex.lane == 0) st_release_gpu(pd.intra_done + a, stamp);
+    }
+}
+
 __global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_deblock_rows(const DescTable descs, const __grid_constant__ PicList list,
                                                                    Geometry g, int* progress, int* ticket)
 {
@@ -326,61 +397,88 @@ __global__ void __launch_bounds__(128) k_deblock_prep(const DescTable descs, con
 }
 
 // ------------------------------------------------------------------------------------------------
-// Packed storage: blk_off[a] = number of stored coefficient blocks before macroblock a = exclusive scan of
-// popcount(blk_mask); mv_off[a] (partition-order vectors only) = exclusive scan of the vector counts that follow
-// from mb_class / sub_mb_type.  One CTA per picture that arrived packed; both scans share the passes
-// (block count in the low, vector count in the high half of a 64-bit word).
+// Per-picture index structures, one CTA per picture, on the prep stream (behind the picture's upload, ahead of the
+// kernels that read them):
+//   packed storage: blk_off[a] = number of stored coefficient blocks before macroblock a = exclusive scan of
+//     popcount(blk_mask); mv_off[a] (partition-order vectors only) = exclusive scan of the vector counts that follow
+//     from mb_class / sub_mb_type;
+//   intra_list (P pictures that go to k_intra_list): the addresses of the intra macroblocks in ascending order, their
+//     number in front.
+// The three scans share the passes (block count in the low, vector count in the high half of a 64-bit word; intra
+// count in a second word).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_blk_scan(const DescTable descs, const __grid_constant__ PicList list, int n_mbs)
 {
     const PicDesc& pd = descs[list.slot[blockIdx.x]];
     const uint32_t* mask = pd.blk_mask;
-    uint32_t* off = const_cast<uint32_t*>(pd.blk_off);
-    uint32_t* mvoff = const_cast<uint32_t*>(pd.mv_off);
+    uint32_t* off = pd.packed ? const_cast<uint32_t*>(pd.blk_off) : nullptr;
+    uint32_t* mvoff = pd.packed ? const_cast<uint32_t*>(pd.mv_off) : nullptr;
+    uint32_t* ilist = pd.intra_list;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ unsigned long long wsum[32];
+    __shared__ uint32_t isum[32];
     __shared__ unsigned long long s_total;
+    __shared__ uint32_t s_itotal;
     unsigned long long base = 0;          // counts of the tiles already done
+    uint32_t ibase = 0;
     // tiles of 8192 macroblocks: every thread owns 8 consecutive ones, all their loads in flight at once
     for (int t0 = 0; t0 < n_mbs; t0 += 8192) {
         const int first = t0 + threadIdx.x * 8;
         unsigned long long c[8];
+        uint32_t intra_bits = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             c[k] = 0;
             if (first + k < n_mbs) {
-                c[k] = (unsigned long long)__popc(__ldg(mask + first + k) & 0xFFFFFFu);
-                if (mvoff) {
+                if (off) c[k] = (unsigned long long)__popc(__ldg(mask + first + k) & 0xFFFFFFu);
+                if (mvoff || ilist) {
                     const uint2 hw = __ldg(reinterpret_cast<const uint2*>(pd.hdr + first + k));     // mb_class = byte 0, sub_mb_type = byte 7
-                    c[k] += (unsigned long long)mv_count((int)(hw.x & 255u), (int)(hw.y >> 24)) << 32;
+                    if (mvoff) c[k] += (unsigned long long)mv_count((int)(hw.x & 255u), (int)(hw.y >> 24)) << 32;
+                    if (is_intra((int)(hw.x & 255u))) intra_bits |= 1u << k;
                 }
             }
         }
         unsigned long long sum = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) sum += c[k];
+        const uint32_t isumv = (uint32_t)__popc(intra_bits);
         unsigned long long incl = sum;
-        for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        if (lane == 31) wsum[warp] = incl;
+        uint32_t iincl = isumv;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            uint32_t ti = __shfl_up_sync(0xffffffffu, iincl, o);
+            if (lane >= o) { incl += t; iincl += ti; }
+        }
+        if (lane == 31) { wsum[warp] = incl; isum[warp] = iincl; }
         __syncthreads();
         if (warp == 0) {
             unsigned long long v = wsum[lane], iv = v;
-            for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
+            uint32_t vi = isum[lane], ivi = vi;
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long t = __shfl_up_sync(0xffffffffu, iv, o);
+                uint32_t ti = __shfl_up_sync(0xffffffffu, ivi, o);
+                if (lane >= o) { iv += t; ivi += ti; }
+            }
             wsum[lane] = iv - v;
-            if (lane == 31) s_total = iv;
+            isum[lane] = ivi - vi;
+            if (lane == 31) { s_total = iv; s_itotal = ivi; }
         }
         __syncthreads();
         unsigned long long run = base + wsum[warp] + incl - sum;
+        uint32_t irun = ibase + isum[warp] + iincl - isumv;
 #pragma unroll
         for (int k = 0; k < 8; k++)
             if (first + k < n_mbs) {
-                off[first + k] = (uint32_t)run;
+                if (off) off[first + k] = (uint32_t)run;
                 if (mvoff) mvoff[first + k] = (uint32_t)(run >> 32);
                 run += c[k];
+                if (ilist && ((intra_bits >> k) & 1u)) ilist[1 + irun++] = (uint32_t)(first + k);
             }
         base += s_total;
+        ibase += s_itotal;
         __syncthreads();
     }
+    if (ilist && threadIdx.x == 0) ilist[0] = ibase;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -140,6 +140,39 @@ HD void pad_row_phase(uint8_t* org, int pitch, int W, int H, int padx, int pady,
     }
 }
 
+// The same border written by the warp that reconstructed a BORDER macroblock (REF_COMPAT luma: nothing modifies a
+// sample after its macroblock's store, so the replication need not wait for the whole picture and k_pad's launch
+// disappears from the chain picture -> next picture).  Runs as its own phase after the macroblock's stores: the
+// samples are read back through L2.  Left / right: the macroblock's 16 rows x PAD_X bytes; top / bottom: PAD_Y copies of
+// its first / last row, and next to a corner macroblock the PAD_X x PAD_Y corner block.  All stores are 16 bytes
+// (plane origin, pitch, PAD_X and macroblock columns are multiples of 16).
+HD void phase_pad_mb_luma(uint8_t* org, int pitch, int w_mbs, int h_mbs, int mbx, int mby, int lane)
+{
+    const int W = w_mbs * 16, H = h_mbs * 16, x0 = mbx * 16, y0 = mby * 16;
+    const bool left = mbx == 0, right = mbx == w_mbs - 1;
+    auto splat = [&](int x, int y) -> uint4 {
+        const uint32_t s = (uint32_t)H264R_LDCG(org + (ptrdiff_t)y * pitch + x) * 0x01010101u;
+        return uint4{s, s, s, s};
+    };
+    if (left || right) {
+        const int r = y0 + (lane >> 1), k = (lane & 1) * 16;
+        if (left) *reinterpret_cast<uint4*>(org + (ptrdiff_t)r * pitch - PAD_X + k) = splat(0, r);
+        if (right) *reinterpret_cast<uint4*>(org + (ptrdiff_t)r * pitch + W + k) = splat(W - 1, r);
+    }
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        if (side == 0 ? mby != 0 : mby != h_mbs - 1) continue;
+        const int ys = side == 0 ? 0 : H - 1;
+        if (lane < PAD_Y) {
+            uint8_t* dst = org + (ptrdiff_t)(side == 0 ? -1 - lane : H + lane) * pitch;
+            *reinterpret_cast<uint4*>(dst + x0) = H264R_LDCG(reinterpret_cast<const uint4*>(org + (ptrdiff_t)ys * pitch + x0));
+            if (left) { const uint4 s = splat(0, ys); *reinterpret_cast<uint4*>(dst - PAD_X) = s; *reinterpret_cast<uint4*>(dst - PAD_X + 16) = s; }
+            if (right) { const uint4 s = splat(W - 1, ys); *reinterpret_cast<uint4*>(dst + W) = s; *reinterpret_cast<uint4*>(dst + W + 16) = s; }
+        }
+    }
+}
+HD bool is_border_mb(const Geometry& g, int mbx, int mby) { return mbx == 0 || mby == 0 || mbx == g.w_mbs - 1 || mby == g.h_mbs - 1; }
+
 // Working set of the inter path (one per warp)
 struct alignas(128) InterWork {
     uint32_t win[512];          // staged windows, see phase_inter_stage (TMA destination: 128-byte aligned)
@@ -779,6 +812,11 @@ HD void seq_inter_mb_fast(Exec& ex, InterWork& w, TmaState& ts, const PicDesc& p
         if (!COMPAT && pd.nzmask && lane == 0) pd.nzmask[a] = !coded ? 0u : (t8 ? nz_pack8(w.nzf) : nz_pack(w.nzf));
         phase_inter_compute<COMPAT, TMA>(w, ts, pd, g, h, a, lane, coded);
     });
+    if (COMPAT) {        // border macroblocks replicate their samples into the frame's border (see phase_pad_mb_luma)
+        int mbx, mby;
+        mb_xy(g, a, mbx, mby);
+        if (is_border_mb(g, mbx, mby)) ex([&](int lane) { phase_pad_mb_luma(pd.y, g.pitch_y, g.w_mbs, g.h_mbs, mbx, mby, lane); });
+    }
 }
 
 }  // namespace h264r

@@ -163,6 +163,11 @@ HD void seq_intra_any(Exec& ex, MbWork& w, const uint16_t* lut, const PicDesc& p
             store_chroma<COMPAT>(w, pd, g, a, lane);
         });
     }
+    if (COMPAT) {        // as in seq_inter_mb_fast: the frame border next to a border macroblock
+        int mbx, mby;
+        mb_xy(g, a, mbx, mby);
+        if (is_border_mb(g, mbx, mby)) ex([&](int lane) { phase_pad_mb_luma(pd.y, g.pitch_y, g.w_mbs, g.h_mbs, mbx, mby, lane); });
+    }
 }
 
 // K4: deblock one macroblock in place (its neighbours A, B, C are completely filtered)

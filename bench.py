@@ -248,7 +248,7 @@ def main():
                 pb = eng.picture_buf(max(1, blocks.shape[0]))
                 pb.fill(p["hdr"], p["mv"], mask, blocks, mv_partition=True)
                 if g < U:
-                    coded_blocks += pb.n_blocks
+                    coded_blocks += int(blocks.shape[0])
                 frames.append((pb, None, None, None))
             pinned.append(frames)
     else:
@@ -280,7 +280,7 @@ def main():
         for i in range(F):
             hb, mb, cb, kb = pinned[g if packed else g % U][i]
             if packed:
-                h2d += upload_fixed + max(0, hb.n_mvs) * 4 + hb.n_blocks * 16 * hb.c.level_bytes
+                h2d += upload_fixed + max(0, hb.n_mvs) * 4 + hb.n_blocks * {2: 32, 1: 16, 3: 8}[hb.c.level_bytes]
             else:
                 h2d += hb.nbytes + cb.nbytes + (mb.nbytes if mb else 0)
     all_ids = list(range(G * F))
@@ -422,7 +422,7 @@ def main():
             "config": {"workload": "1080p 120x68 MBs, %d GOPs/GPU x %d pictures (1 I + %d P), %s" % (
                 G, F, F - 1, "REF_COMPAT (what the reference decoder computes: 4x4 transform, luma prediction, no deblock)" if compat
                 else "spec mode (chroma prediction + MC, 8x8 transform, Intra8x8, deblocking)"),
-                "mode": args.mode, "layout": args.layout + (" (%.2f of 24 coefficient blocks per macroblock present)" % (coded_blocks / float(U * F * N_MBS)) if packed else ""),
+                "mode": args.mode, "layout": args.layout + (" (%.2f of 24 coefficient blocks per macroblock present; int8 levels in 8-byte units: significance map + levels)" % (coded_blocks / float(U * F * N_MBS)) if packed else ""),
                 "gops_per_gpu": G, "gop_len": F, "unique_gops": U, "sharding": "one GOP set per rank, no data-path collective",
                 "l2_policy": "inputs (%.1f GB of syntax per step) exceed the 126 MB L2 and are re-uploaded between timed steps" % (h2d / 1e9)},
             "e2e": {"value": frames_per_step * args.steps / (e2e_ms / 1000.0), "unit": "frames/s", "ms_per_step": e2e_ms / args.steps,

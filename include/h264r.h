@@ -194,6 +194,10 @@ int h264r_submit_mbs_packed(h264r_ctx* ctx, int frame_id, int first_mb, int n_mb
  * formats as h264r_submit_mbs_packed, whole picture, macroblock order) and h264r_submit_picture() ships it with a
  * single DMA and queues the picture (no h264r_frame_end).  The buffer must stay untouched until the next
  * h264r_sync() (or a read-back of the picture) returns, and may then be refilled.  max_blocks = 0 sizes for the worst case (24 per MB). */
+#define H264R_LEVELS_INT16   2
+#define H264R_LEVELS_INT8    1
+#define H264R_LEVELS_COMPACT 3
+#define H264R_BLK_COMPACT    (1u << 24)     /* in blk_mask[a], H264R_LEVELS_COMPACT only */
 typedef struct h264r_picture_buf {
     h264r_mb_hdr* hdr;        /* [n_mbs]                    */
     int16_t*      mv;         /* per-4x4 layout: [n_mbs * H264R_MV_PER_MB], forward from here                        */
@@ -205,9 +209,18 @@ typedef struct h264r_picture_buf {
     size_t        max_blocks;
     int32_t       n_intra;    /* number of intra macroblocks in hdr[], as counted by the parser; -1 = unknown: the
                                  library then walks hdr[] itself (and validates mb_class while there)            */
-    int32_t       level_bytes;/* 2 (default): blocks[] holds int16 levels, 32 bytes per block; 1: the parser wrote int8 levels,
-                                 16 bytes per block, through (int8_t*)blocks -- allowed when every level of the picture is in
-                                 [-128, 127] (the common case at the QPs video is coded at), and half the bytes on the wire   */
+    int32_t       level_bytes;/* storage of blocks[], one of H264R_LEVELS_*:
+                                 _INT16 (2, default): int16 levels, 32 bytes per block;
+                                 _INT8 (1): the parser wrote int8 levels, 16 bytes per block, through (int8_t*)blocks -- allowed
+                                   when every level of the picture is in [-128, 127] (the common case at the QPs video is
+                                   coded at), and half the bytes on the wire;
+                                 _COMPACT (3): int8 levels in 8-byte units.  A macroblock whose blocks all have at most six
+                                   levels sets H264R_BLK_COMPACT in its blk_mask word and stores each present block as ONE
+                                   unit: bytes 0-1 the significance map (bit k = position k, raster, holds a level -- what
+                                   significant_coeff_flag says after the inverse scan), bytes 2-7 the levels of the set
+                                   positions in ascending position order.  Any other macroblock stores its blocks as in
+                                   _INT8, two units each.  n_blocks of h264r_submit_picture counts UNITS.  A quarter of the
+                                   _INT16 bytes at two levels per block                                                   */
     void*         base;       /* owned by the library       */
 } h264r_picture_buf;
 int  h264r_picture_buf_alloc(h264r_ctx* ctx, size_t max_blocks, h264r_picture_buf* out);

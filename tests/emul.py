@@ -18,6 +18,7 @@ DEPS = [SRC] + [os.path.join(ROOT, "videodecoder_b200", "csrc", "cuda", f) for f
 _lib = None
 # test switches of the emulator (upper bits of `flags`, never seen by the engine)
 PACKED = 0x40000000          # store coefficients packed (mask + offset + non-zero blocks) as h264r_submit_mbs_packed does
+COMPACT = 0x20000000         # with PACKED: H264R_LEVELS_COMPACT storage (8-byte units, significance map + levels)
 GENERIC_INTRA = 0x80000000   # run the generic intra phases of h264r_core.cuh instead of h264r_intra.cuh
 
 

@@ -26,7 +26,7 @@ void fill_desc(PicDesc& pd, const h264r_pic_params* pp, const h264r_mb_hdr* hdr,
     memset(&pd, 0, sizeof(pd));
     pd.hdr = hdr; pd.mv = mv; pd.coeff = coeff; pd.y = y; pd.u = u; pd.v = v;
     pd.blk_mask = nullptr; pd.blk_off = nullptr;        // set by use_dense() / use_packed()
-    pd.level8 = 0;
+    pd.level_fmt = H264R_LEVELS_INT16;
     pd.mv_off = nullptr;
     pd.residual = nullptr;
     pd.nzmask = nullptr;
@@ -63,7 +63,7 @@ struct CoeffStore {
         pd.blk_mask = mask.data(); pd.blk_off = off.data();
     }
     // what a host parser would submit through h264r_submit_mbs_packed: only the blocks with a non-zero level
-    void use_packed(PicDesc& pd, int n_mbs, const int16_t* dense)
+    void use_packed(PicDesc& pd, int n_mbs, const int16_t* dense, bool compact = false)
     {
         mask.assign(n_mbs, 0); off.resize(n_mbs); blocks.clear();
         for (int a = 0; a < n_mbs; a++) {
@@ -83,10 +83,42 @@ struct CoeffStore {
         if (fits) {
             narrow.assign(blocks.begin(), blocks.end());
             pd.coeff = reinterpret_cast<const int16_t*>(narrow.data());
-            pd.level8 = 1;
+            pd.level_fmt = H264R_LEVELS_INT8;
+        }
+        if (fits && compact) {
+            // H264R_LEVELS_COMPACT: 8-byte units; macroblocks whose blocks all have at most six levels store a significance
+            // map + the levels per block (one unit), the others int8 blocks (two units)
+            units.clear();
+            size_t blk = 0;
+            for (int a = 0; a < n_mbs; a++) {
+                const int nb = __builtin_popcount(mask[a]);
+                bool ok = nb > 0;
+                for (int b = 0; b < nb; b++) {
+                    int nz = 0;
+                    for (int k = 0; k < 16; k++) nz += blocks[(blk + b) * 16 + k] != 0;
+                    ok = ok && nz <= 6;
+                }
+                off[a] = (uint32_t)(units.size() / 8);
+                for (int b = 0; b < nb; b++) {
+                    const int16_t* p = &blocks[(blk + b) * 16];
+                    if (ok) {
+                        uint8_t u[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                        int n = 0;
+                        for (int k = 0; k < 16; k++) if (p[k]) { u[k >> 3] |= (uint8_t)(1u << (k & 7)); u[2 + n++] = (uint8_t)(int8_t)p[k]; }
+                        units.insert(units.end(), u, u + 8);
+                    } else
+                        for (int k = 0; k < 16; k++) units.push_back((uint8_t)(int8_t)p[k]);
+                }
+                if (ok) mask[a] |= H264R_BLK_COMPACT;
+                blk += nb;
+            }
+            units.resize(units.size() + 16);
+            pd.coeff = reinterpret_cast<const int16_t*>(units.data());
+            pd.level_fmt = H264R_LEVELS_COMPACT;
         }
     }
     std::vector<int8_t> narrow;
+    std::vector<uint8_t> units;
 };
 // motion vectors in partition order, as h264r_submit_picture(..., n_mvs >= 0) delivers them
 struct MvStore {
@@ -187,7 +219,7 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
     PicDesc pd;
     fill_desc(pd, pp, hdr, mv, coeff, cur.y(), cur.u(), cur.v(), ry, ru, rv, exc_map);
     CoeffStore cs;
-    if (flags & 0x40000000u) cs.use_packed(pd, w_mbs * h_mbs, coeff); else cs.use_dense(pd, w_mbs * h_mbs);      // test switch: bit 30
+    if (flags & 0x40000000u) cs.use_packed(pd, w_mbs * h_mbs, coeff, (flags & 0x20000000u) != 0); else cs.use_dense(pd, w_mbs * h_mbs);      // test switches: bits 30, 29
     MvStore ms;
     if ((flags & 0x40000000u) && mv) ms.use_packed(pd, w_mbs * h_mbs, hdr, mv);
     HostExec ex;

@@ -43,8 +43,9 @@ def run_engine(w, h, flags, gops, transport="buf", flush="all", max_frames=None)
                 eng.submit_picture_packed(fid, pp, np.ascontiguousarray(p["hdr"]), p["mv"], mask, blocks)
             else:
                 b = eng.picture_buf(max(1, blocks.shape[0]))
-                b.fill(p["hdr"], p["mv"], mask, blocks, mv_partition=transport in ("bufmv", "bufmv16"),
-                       level8=False if transport == "bufmv16" else None)
+                # bufmv: the narrowest storage (compact units); bufmv8: int8 blocks; bufmv16: int16 blocks
+                b.fill(p["hdr"], p["mv"], mask, blocks, mv_partition=transport in ("bufmv", "bufmv8", "bufmv16"),
+                       level8=False if transport == "bufmv16" else None, compact=False if transport == "bufmv8" else None)
                 bufs.append(b)
                 eng.submit_picture_buf(fid, pp, b)
         if flush == "each":
@@ -119,7 +120,7 @@ def test_1080p_transport_and_flush_invariance(built, hd_gops):
     w, h, gops = hd_gops
     ref, lasts, exc = run_engine(w, h, abi.REF_COMPAT, gops, transport="dense", flush="all")
     assert exc == 0
-    for transport, flush in (("packed", "all"), ("buf", "each"), ("bufmv", "round"), ("bufmv", "all"), ("bufmv16", "all")):
+    for transport, flush in (("packed", "all"), ("buf", "each"), ("bufmv", "round"), ("bufmv", "all"), ("bufmv8", "all"), ("bufmv16", "all")):
         dig, _, exc = run_engine(w, h, abi.REF_COMPAT, gops, transport=transport, flush=flush)
         assert exc == 0
         assert np.array_equal(dig, ref), (transport, flush)

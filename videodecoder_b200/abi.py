@@ -13,6 +13,8 @@ AVAIL_A, AVAIL_B, AVAIL_C, AVAIL_D, T8x8, SKIP = 0x01, 0x02, 0x04, 0x08, 0x10, 0
 SUB_8x8, SUB_8x4, SUB_4x8, SUB_4x4 = 0, 1, 2, 3
 SLICE_P, SLICE_I = 0, 2
 COEFF_PER_MB, MV_PER_MB, MAX_REFS = 384, 32, 16
+LEVELS_INT16, LEVELS_INT8, LEVELS_COMPACT = 2, 1, 3      # h264r_picture_buf.level_bytes
+BLK_COMPACT = 1 << 24
 
 E_INVAL, E_CUDA, E_NOMEM, E_STATE, E_NODEVICE, E_CAPACITY = -1, -2, -3, -4, -5, -6
 

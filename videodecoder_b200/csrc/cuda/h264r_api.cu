@@ -30,7 +30,7 @@ struct Pending {
     int layout;             // 0 = nothing submitted yet, 1 = dense (h264r_submit_mbs), 2 = packed (h264r_submit_mbs_packed)
     size_t n_blocks;        // packed: coefficient blocks stored so far
     bool mv_partition;      // vectors in partition order (h264r_submit_picture with n_mvs >= 0)
-    int level_bytes;        // 2: int16 levels (32-byte blocks); 1: int8 levels (16-byte blocks, picture buffers only)
+    int level_bytes;        // H264R_LEVELS_*: int16 levels (32-byte blocks); picture buffers only: int8 levels (16-byte blocks), compact (8-byte units)
     uint64_t seq;           // order of frame_end calls (= order of the uploads on the copy stream)
 };
 
@@ -155,7 +155,7 @@ void fill_desc(h264r_ctx* c, const Pending& p, PicDesc& pd)
     pd.hdr = reinterpret_cast<const h264r_mb_hdr*>(s + c->off_hdr);
     pd.mv = reinterpret_cast<const int16_t*>(s + (p.mv_partition ? c->off_desc : c->off_mv));
     pd.coeff = reinterpret_cast<const int16_t*>(s + c->off_coeff);
-    pd.level8 = p.level_bytes == 1;
+    pd.level_fmt = p.level_bytes;
     if (p.layout == 2) {
         pd.blk_mask = reinterpret_cast<const uint32_t*>(s + c->off_mask);
         pd.blk_off = reinterpret_cast<const uint32_t*>(s + c->off_boff);
@@ -545,8 +545,8 @@ void h264r_picture_buf_free(h264r_ctx* ctx, h264r_picture_buf* buf)
 
 int h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* buf, size_t n_blocks, long n_mvs)
 {
-    if (!ctx || !buf || !buf->base || n_blocks > buf->max_blocks || n_mvs > (long)16 * (ctx ? ctx->n_mbs : 0) ||
-        (buf->level_bytes != 1 && buf->level_bytes != 2))
+    if (!ctx || !buf || !buf->base || n_blocks > buf->max_blocks * (buf->level_bytes == H264R_LEVELS_COMPACT ? 4 : 1) || n_mvs > (long)16 * (ctx ? ctx->n_mbs : 0) ||
+        (buf->level_bytes != H264R_LEVELS_INT8 && buf->level_bytes != H264R_LEVELS_INT16 && buf->level_bytes != H264R_LEVELS_COMPACT))
         return fail(ctx, H264R_E_INVAL, "submit_picture: bad argument");
     Pending* p = find_pending(ctx, frame_id);
     if (!p || p->ended) return fail(ctx, H264R_E_STATE, "submit_picture: no open picture with this frame id");
@@ -583,7 +583,8 @@ int h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* 
     const bool is_p = p->pp.slice_type == H264R_SLICE_P;
     const size_t mv_bytes = !is_p ? 0 : (n_mvs >= 0 ? (size_t)n_mvs * 4 : ctx->off_desc);      // per-4x4 layout: the whole area
     const size_t first = ctx->off_desc - mv_bytes;
-    CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot) + first, hb + first, ctx->off_coeff + n_blocks * 16 * (size_t)buf->level_bytes - first,
+    const size_t unit_bytes = buf->level_bytes == H264R_LEVELS_INT16 ? 32 : (buf->level_bytes == H264R_LEVELS_INT8 ? 16 : 8);
+    CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot) + first, hb + first, ctx->off_coeff + n_blocks * unit_bytes - first,
                        cudaMemcpyHostToDevice, ctx->copy_stream));
     CU(cudaEventRecord(ctx->ev_copied[p->slot], ctx->copy_stream));
     reinterpret_cast<PicDesc*>(ctx->h_ctrl)[p->slot].deblock_on = reinterpret_cast<const PicDesc*>(hb + ctx->off_desc)->deblock_on;
@@ -1009,6 +1010,7 @@ int h264r_residual_mbs(h264r_ctx* ctx, int n_mbs, const h264r_mb_hdr* hdr, const
     memset(&pd, 0, sizeof(pd));
     pd.hdr = reinterpret_cast<const h264r_mb_hdr*>(d);
     pd.coeff = reinterpret_cast<const int16_t*>(d + hb);
+    pd.level_fmt = H264R_LEVELS_INT16;
     // dense layout; the context's table covers n_mbs of a picture, larger calls get their own
     uint32_t* d_ref = nullptr;
     if (n_mbs <= ctx->n_mbs) { pd.blk_mask = ctx->d_dense_mask; pd.blk_off = ctx->d_dense_off; }

@@ -63,7 +63,7 @@ struct PicDesc {
                                // (stored BACKWARD from here: vector i at mv[-2(i+1)], see mv_off)
     const uint32_t* mv_off;    // null: per-4x4 layout; else per macroblock the index of its first vector, partition order
     const int16_t* coeff;      // coefficient blocks of the picture, 16 levels each, packed (see BlkRef)
-    int32_t level8;            // 1: the levels are int8 (16 bytes per block) instead of int16 (32 bytes)
+    int32_t level_fmt;         // H264R_LEVELS_INT16: 32-byte blocks; _INT8: 16-byte blocks; _COMPACT: 8-byte units, see BlkRef
     const uint32_t* blk_mask;  // per macroblock: bit b set = block b is stored
     const uint32_t* blk_off;   // per macroblock: index of its first stored block
     int16_t* residual;         // scratch: residual of the intra macroblocks, 384 int16 each (Y 16x16, U 8x8, V 8x8), produced
@@ -112,7 +112,11 @@ struct alignas(16) MbWork {
 };
 
 // Coefficient storage.  Macroblock a owns the blocks whose bit is set in blk_mask[a] (bit b = block b of the 24
-// of include/h264r.h), stored back to back from block index blk_off[a]; a block that is not stored is all zero.
+// of include/h264r.h), stored back to back from unit index blk_off[a]; a block that is not stored is all zero.
+// A unit is one block of 32 bytes (int16 levels) or 16 bytes (int8 levels).  H264R_LEVELS_COMPACT: a unit is 8 bytes
+// and a macroblock's blocks are either all PLAIN -- int8 levels, two units each -- or, when bit 24 of blk_mask[a]
+// (H264R_BLK_COMPACT) is set, all COMPACT, one unit each: a 16-bit significance map (bit k = position k, raster, holds
+// a level) followed by the levels of the set positions in ascending position order, int8, at most six.
 // The dense layout of h264r_submit_mbs is the special case mask = 0xFFFFFF, off = 24 a.
 struct BlkRef { uint32_t mask, off; };
 HD int popc32(uint32_t v)
@@ -124,15 +128,54 @@ HD int popc32(uint32_t v)
 #endif
 }
 HD BlkRef load_blkref(const PicDesc& pd, int a) { return BlkRef{H264R_LDG(pd.blk_mask + a), H264R_LDG(pd.blk_off + a)}; }
+HD bool blk_compact(const PicDesc& pd, const BlkRef& r) { return pd.level_fmt == H264R_LEVELS_COMPACT && ((r.mask >> 24) & 1u); }
 HD const uint8_t* blk_ptr(const PicDesc& pd, const BlkRef& r, int b)       // nullptr: block b is zero
 {
     if (!((r.mask >> b) & 1u)) return nullptr;
-    return reinterpret_cast<const uint8_t*>(pd.coeff) + ((size_t)r.off + popc32(r.mask & ((1u << b) - 1u))) * (pd.level8 ? 16 : 32);
+    const uint32_t k = (uint32_t)popc32(r.mask & ((1u << b) - 1u));
+    if (pd.level_fmt == H264R_LEVELS_COMPACT) return reinterpret_cast<const uint8_t*>(pd.coeff) + ((size_t)r.off + (((r.mask >> 24) & 1u) ? k : 2u * k)) * 8;
+    return reinterpret_cast<const uint8_t*>(pd.coeff) + ((size_t)r.off + k) * (pd.level_fmt == H264R_LEVELS_INT8 ? 16 : 32);
 }
-// levels [first, first + 8) of a stored block (first = 0 or 8) as four words of two int16 each, whatever the storage width
-HD int4 blk_levels8(const PicDesc& pd, const uint8_t* p, int first)
+// byte permute with sign replication: result byte i = byte (nibble i & 7) of the pool {a, b}, or, when bit 3 of the nibble is
+// set, 0x00 / 0xff after that byte's sign
+HD uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel)
 {
-    if (!pd.level8) return H264R_LDG(reinterpret_cast<const int4*>(p) + (first >> 3));
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+#else
+    const uint64_t pool = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        const uint32_t n = (sel >> (4 * i)) & 15u;
+        uint32_t byte = (uint32_t)((pool >> (8 * (n & 7u))) & 255u);
+        if (n & 8u) byte = (byte & 0x80u) ? 0xffu : 0u;
+        r |= byte << (8 * i);
+    }
+    return r;
+#endif
+}
+// levels [first, first + 8) of a stored block (first = 0 or 8) as four words of two int16 each, whatever the storage
+HD int4 blk_levels8(const PicDesc& pd, const BlkRef& br, const uint8_t* p, int first)
+{
+    if (pd.level_fmt == H264R_LEVELS_INT16) return H264R_LDG(reinterpret_cast<const int4*>(p) + (first >> 3));
+    if (blk_compact(pd, br)) {
+        // position q holds level number popc(map below q); one byte permute with sign replication yields two
+        // neighbouring positions as a pair of int16
+        const uint2 v = H264R_LDG(reinterpret_cast<const uint2*>(p));
+        const uint32_t map = v.x & 0xffffu, lo = (v.x >> 16) | (v.y << 16), hi = v.y >> 16;
+        int out[4];
+        uint32_t i0 = (uint32_t)popc32(map & ((1u << first) - 1u));
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t b0 = (map >> (first + 2 * k)) & 1u, b1 = (map >> (first + 2 * k + 1)) & 1u, i1 = i0 + b0;
+            const uint32_t w = prmt_sx(lo, hi, (i0 & 7u) | (((i0 & 7u) | 8u) << 4) | ((i1 & 7u) << 8) | (((i1 & 7u) | 8u) << 12));
+            out[k] = (int)(w & ((b0 ? 0xffffu : 0u) | (b1 ? 0xffff0000u : 0u)));
+            i0 = i1 + b1;
+        }
+        return int4{out[0], out[1], out[2], out[3]};
+    }
     const uint2 v = H264R_LDG(reinterpret_cast<const uint2*>(p) + (first >> 3));
     auto pair = [](uint32_t w, int k) -> int {      // bytes 2k, 2k+1 of w, sign-extended, as (lo | hi << 16)
         const int lo = (int)(int8_t)(w >> (16 * k)), hi = (int)(int8_t)(w >> (16 * k + 8));
@@ -141,9 +184,14 @@ HD int4 blk_levels8(const PicDesc& pd, const uint8_t* p, int first)
     return int4{pair(v.x, 0), pair(v.x, 1), pair(v.y, 0), pair(v.y, 1)};
 }
 // level 0 of a stored block (Intra16x16 / chroma DC slot)
-HD int blk_level0(const PicDesc& pd, const uint8_t* p)
+HD int blk_level0(const PicDesc& pd, const BlkRef& br, const uint8_t* p)
 {
-    return pd.level8 ? (int)(int8_t)H264R_LDG(p) : (int)H264R_LDG(reinterpret_cast<const int16_t*>(p));
+    if (pd.level_fmt == H264R_LEVELS_INT16) return (int)H264R_LDG(reinterpret_cast<const int16_t*>(p));
+    if (blk_compact(pd, br)) {
+        const uint32_t w = H264R_LDG(reinterpret_cast<const uint32_t*>(p));
+        return (w & 1u) ? (int)(int8_t)(w >> 16) : 0;
+    }
+    return (int)(int8_t)H264R_LDG(p);
 }
 
 // Header fields that are indexed at run time.  The record lives in registers; indexing its byte arrays with a run-time
@@ -294,7 +342,7 @@ HD void phase_load_coeff(MbWork& w, const PicDesc& pd, int a, int lane)
         const BlkRef br = load_blkref(pd, a);
         const uint8_t* src = blk_ptr(pd, br, lane);
         int4 v0 = int4{0, 0, 0, 0}, v1 = int4{0, 0, 0, 0};
-        if (src) { v0 = blk_levels8(pd, src, 0); v1 = blk_levels8(pd, src, 8); }
+        if (src) { v0 = blk_levels8(pd, br, src, 0); v1 = blk_levels8(pd, br, src, 8); }
         int4* dst = reinterpret_cast<int4*>(&w.coef[lane][0]);
         dst[0] = v0; dst[1] = v1;
     }
@@ -919,7 +967,7 @@ HD bool blk_coded_global(const PicDesc& pd, const h264r_mb_hdr& h, int a, int ra
     for (int k = 0; k < n; k++) {
         const uint8_t* p = blk_ptr(pd, br, first + k);
         if (!p) continue;
-        int4 v0 = blk_levels8(pd, p, 0), v1 = blk_levels8(pd, p, 8);
+        int4 v0 = blk_levels8(pd, br, p, 0), v1 = blk_levels8(pd, br, p, 8);
         if (v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) return true;
     }
     return false;

@@ -35,10 +35,37 @@ HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr&
     bool active = luma ? (i16 || ((cbp_l >> (lane >> 2)) & 1) != 0) : cbp_c != 0;
     int r[16];
     bool zero = true;
+    // where the block's residual goes: 4 rows of 4 int16 (8 bytes each), private to this lane during the phase
+    int16_t* dst;
+    int pitch;
+    if (luma) { int ras = blk_raster(lane); dst = res + (ras >> 2) * 64 + (ras & 3) * 4; pitch = 16; }
+    else { int plane = (lane - 16) >> 2, b = (lane - 16) & 3; dst = res + 256 + plane * 64 + (b >> 1) * 32 + (b & 1) * 4; pitch = 8; }
     if (active) {
         const uint8_t* src = blk_ptr(pd, br, lane);
         int4 v0 = int4{0, 0, 0, 0}, v1 = int4{0, 0, 0, 0};
-        if (src) { v0 = blk_levels8(pd, src, 0); if (luma || cbp_c == 2) v1 = blk_levels8(pd, src, 8); }
+        if (src && blk_compact(pd, br)) {
+            // compact block: the levels are scattered into the lane's own (zeroed) 4x4 field of res[], which has the
+            // raster shape of a block, and read back as rows
+            const uint2 v = H264R_LDG(reinterpret_cast<const uint2*>(src));
+            uint32_t map = v.x & 0xffffu;
+            unsigned long long lv = ((unsigned long long)v.y << 16) | (v.x >> 16);
+#pragma unroll
+            for (int i = 0; i < 4; i++) *reinterpret_cast<uint2*>(dst + i * pitch) = uint2{0u, 0u};
+            while (map) {
+#if defined(__CUDA_ARCH__)
+                const int q = __ffs((int)map) - 1;
+#else
+                const int q = __builtin_ctz(map);
+#endif
+                map &= map - 1;
+                dst[(q >> 2) * pitch + (q & 3)] = (int16_t)(int8_t)(lv & 255u);
+                lv >>= 8;
+            }
+            const uint2 r0 = *reinterpret_cast<const uint2*>(dst), r1 = *reinterpret_cast<const uint2*>(dst + pitch);
+            const uint2 r2 = *reinterpret_cast<const uint2*>(dst + 2 * pitch), r3 = *reinterpret_cast<const uint2*>(dst + 3 * pitch);
+            v0 = int4{(int)r0.x, (int)r0.y, (int)r1.x, (int)r1.y};
+            if (luma || cbp_c == 2) v1 = int4{(int)r2.x, (int)r2.y, (int)r3.x, (int)r3.y};
+        } else if (src) { v0 = blk_levels8(pd, br, src, 0); if (luma || cbp_c == 2) v1 = blk_levels8(pd, br, src, 8); }
         if (!luma && cbp_c != 2) { v0.x &= 0xffff; v0.y = v0.z = v0.w = 0; }        // DC only: AC levels are not coded
         int c[16];
         const int w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -56,7 +83,7 @@ HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr&
 #pragma unroll
                 for (int l = 0; l < 4; l++) {
                     const uint8_t* dp = blk_ptr(pd, br, blk_raster(k * 4 + l));
-                    int dc = dp ? blk_level0(pd, dp) : 0;
+                    int dc = dp ? blk_level0(pd, br, dp) : 0;
                     t += ((0xA6C0 >> (l * 4 + j)) & 1) ? -dc : dc;       // T rows {++++},{++--},{+--+},{+-+-}: bit = minus
                 }
                 f += ((0xA6C0 >> (i * 4 + k)) & 1) ? -t : t;
@@ -70,7 +97,7 @@ HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr&
             qp = plane ? h.qp_cr : h.qp_cb;
             const uint8_t* d0 = blk_ptr(pd, br, 16 + plane * 4), * d1 = blk_ptr(pd, br, 17 + plane * 4);
             const uint8_t* d2 = blk_ptr(pd, br, 18 + plane * 4), * d3 = blk_ptr(pd, br, 19 + plane * 4);
-            int c0 = d0 ? blk_level0(pd, d0) : 0, c1 = d1 ? blk_level0(pd, d1) : 0, c2 = d2 ? blk_level0(pd, d2) : 0, c3 = d3 ? blk_level0(pd, d3) : 0;
+            int c0 = d0 ? blk_level0(pd, br, d0) : 0, c1 = d1 ? blk_level0(pd, br, d1) : 0, c2 = d2 ? blk_level0(pd, br, d2) : 0, c3 = d3 ? blk_level0(pd, br, d3) : 0;
             int f;
             if (COMPAT) f = (b == 0 || b == 3) ? c3 : -c3;      // reference's chroma DC product (h264/matrix.cpp:150-171)
             else f = c0 + ((b & 1) ? -c1 : c1) + ((b & 2) ? -c2 : c2) + ((b == 1 || b == 2) ? -c3 : c3);
@@ -88,11 +115,7 @@ HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr&
         }
     }
     if (nz_flags && luma) nz_flags[blk_raster(lane)] = zero ? 0 : 1;
-    // store the block: 4 rows of 4 int16 (8 bytes each)
-    int16_t* dst;
-    int pitch;
-    if (luma) { int ras = blk_raster(lane); dst = res + (ras >> 2) * 64 + (ras & 3) * 4; pitch = 16; }
-    else { int plane = (lane - 16) >> 2, b = (lane - 16) & 3; dst = res + 256 + plane * 64 + (b >> 1) * 32 + (b & 1) * 4; pitch = 8; }
+    // store the block
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         uint32_t lo = 0, hi = 0;

@@ -430,7 +430,10 @@ __global__ void __launch_bounds__(1024) k_blk_scan(const DescTable descs, const 
         for (int k = 0; k < 8; k++) {
             c[k] = 0;
             if (first + k < n_mbs) {
-                if (off) c[k] = (unsigned long long)__popc(__ldg(mask + first + k) & 0xFFFFFFu);
+                if (off) {
+                    const uint32_t mw = __ldg(mask + first + k);       // units: one per block, or two for the plain blocks of a compact picture
+                    c[k] = (unsigned long long)(__popc(mw & 0xFFFFFFu) << ((pd.level_fmt == H264R_LEVELS_COMPACT && !(mw & H264R_BLK_COMPACT)) ? 1 : 0));
+                }
                 if (mvoff || ilist) {
                     const uint2 hw = __ldg(reinterpret_cast<const uint2*>(pd.hdr + first + k));     // mb_class = byte 0, sub_mb_type = byte 7
                     if (mvoff) c[k] += (unsigned long long)mv_count((int)(hw.x & 255u), (int)(hw.y >> 24)) << 32;

@@ -298,7 +298,7 @@ HD void phase_residual8_rows(InterWork& w, const PicDesc& pd, const h264r_mb_hdr
     int x[8];
     int nz = 0;
     if (src && ((h.cbp >> q) & 1)) {
-        const int4 v = blk_levels8(pd, src, (r & 1) * 8);
+        const int4 v = blk_levels8(pd, br, src, (r & 1) * 8);
         const int wv[4] = {v.x, v.y, v.z, v.w};
         const int qp = h.qp_y, s = (qp * 43) >> 8, m = qp - 6 * s;
 #pragma unroll

@@ -140,8 +140,10 @@ class PictureBuf:
         self.n_blocks = 0
         self.n_mvs = -1
 
-    def fill(self, hdr, mv, blk_mask, blocks, mv_partition=False, level8=None):
-        """mv: per-4x4 vectors (n, 32); mv_partition: store them in partition order (pack.pack_mvs_partition)"""
+    def fill(self, hdr, mv, blk_mask, blocks, mv_partition=False, level8=None, compact=None):
+        """mv: per-4x4 vectors (n, 32); mv_partition: store them in partition order (pack.pack_mvs_partition).
+        level8 / compact: level storage (None: the narrowest that holds the picture -- H264R_LEVELS_COMPACT when every
+        level fits int8, else int16)"""
         from . import pack
         self.hdr[:] = np.ascontiguousarray(hdr).view(abi.MB_HDR_DTYPE).reshape(-1)
         self.n_mvs = -1
@@ -157,12 +159,20 @@ class PictureBuf:
         self.n_blocks = int(blocks.shape[0])
         if level8 is None:
             level8 = self.n_blocks > 0 and int(blocks.min()) >= -128 and int(blocks.max()) <= 127
-        if level8:      # int8 transport: 16 bytes per block through the same area
+        if compact is None:
+            compact = level8
+        if level8 and compact:      # 8-byte units: significance map + levels where a macroblock's blocks are sparse
+            mask, units = pack.pack_compact(blk_mask, blocks)
+            self.blk_mask[:] = mask
+            self.n_blocks = int(units.shape[0])       # what h264r_submit_picture is told: units
+            self.blocks.view(np.uint8).reshape(-1, 8)[:self.n_blocks] = units
+            self.c.level_bytes = abi.LEVELS_COMPACT
+        elif level8:      # int8 transport: 16 bytes per block through the same area
             self.blocks.view(np.int8).reshape(-1, 16)[:self.n_blocks] = blocks.astype(np.int8)
-            self.c.level_bytes = 1
+            self.c.level_bytes = abi.LEVELS_INT8
         else:
             self.blocks[:self.n_blocks] = blocks
-            self.c.level_bytes = 2
+            self.c.level_bytes = abi.LEVELS_INT16
         self.c.n_intra = int((self.hdr["mb_class"] <= abi.MB_I16x16).sum())       # a parser counts this as it goes
 
     def free(self):

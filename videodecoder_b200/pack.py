@@ -171,3 +171,48 @@ def pack_mvs_partition(hdr, mv):
                 res[k] = mv[a, b0 + rel]
                 k += 1
     return res
+
+
+def pack_compact(blk_mask, blocks):
+    """H264R_LEVELS_COMPACT storage of include/h264r.h from the packed form (blk_mask [n_mbs] uint32, blocks
+    [n_blocks, 16] int16 with every level in [-128, 127]): 8-byte units.  A macroblock whose blocks all have at most six
+    levels gets H264R_BLK_COMPACT in its mask word and one unit per block (significance map, then the levels in
+    position order); any other macroblock two units per block (int8 raster).  Returns (mask, units [n_units, 8] uint8)."""
+    blk_mask = np.asarray(blk_mask, dtype=np.uint32)
+    blocks = np.asarray(blocks, dtype=np.int16).reshape(-1, 16)
+    n_blocks = blocks.shape[0]
+    per_mb = np.array([bin(int(m) & 0xFFFFFF).count("1") for m in blk_mask], dtype=np.int64) if blk_mask.size < 64 else \
+        np.unpackbits((blk_mask & 0xFFFFFF).view(np.uint8).reshape(-1, 4), axis=1).sum(axis=1).astype(np.int64)
+    assert int(per_mb.sum()) == n_blocks
+    nz = blocks != 0
+    nnz = nz.sum(axis=1)
+    mb_of_block = np.repeat(np.arange(blk_mask.size), per_mb)
+    too_many = np.zeros(blk_mask.size, dtype=np.int64)
+    np.add.at(too_many, mb_of_block, (nnz > 6).astype(np.int64))
+    mb_compact = (too_many == 0) & (per_mb > 0)
+    mask = blk_mask.copy()
+    mask[mb_compact] |= np.uint32(1 << 24)
+    blk_compact = mb_compact[mb_of_block]
+    units_per_block = np.where(blk_compact, 1, 2)
+    first_unit = np.concatenate(([0], np.cumsum(units_per_block)))[:-1]
+    n_units = int(units_per_block.sum())
+    units = np.zeros((n_units, 8), dtype=np.uint8)
+    # compact blocks: significance map + levels in position order
+    cb = np.nonzero(blk_compact)[0]
+    if cb.size:
+        nzc = nz[cb]
+        sig = (nzc.astype(np.uint32) << np.arange(16, dtype=np.uint32)).sum(axis=1).astype(np.uint16)
+        order = np.argsort(~nzc, axis=1, kind="stable")[:, :6]             # positions of the levels first, ascending
+        lv = np.take_along_axis(blocks[cb], order, axis=1).astype(np.int8)
+        lv[np.arange(6)[None, :] >= nnz[cb][:, None]] = 0
+        u = units[first_unit[cb]]
+        u[:, 0] = sig & 0xFF
+        u[:, 1] = sig >> 8
+        u[:, 2:8] = lv.view(np.uint8)
+        units[first_unit[cb]] = u
+    pb = np.nonzero(~blk_compact)[0]
+    if pb.size:
+        raw = blocks[pb].astype(np.int8).view(np.uint8)
+        units[first_unit[pb]] = raw[:, :8]
+        units[first_unit[pb] + 1] = raw[:, 8:]
+    return mask, units

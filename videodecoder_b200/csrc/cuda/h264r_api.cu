@@ -55,8 +55,8 @@ struct h264r_ctx {
     cudaStream_t prep_stream = nullptr, dig_stream = nullptr;
     cudaEvent_t ev_scan[8] = {}, ev_wave[8] = {};
     cudaEvent_t ev_tok = nullptr;           // the k_inter launches of the lanes take turns (see h264r_flush)
-    bool inter_token = true;
-    int inter_generations = 1;              // k_inter grid = SMs x inter_ctas_per_sm x this (1: persistent warps)
+    bool inter_token = false;
+    int inter_generations = 4;              // k_inter grid = SMs x inter_ctas_per_sm x this: a few CTA generations balance the tail
     cudaEvent_t ev_dig[64] = {};            // ring: digest launch number n is done
     uint64_t dig_seq = 0;
     uint64_t lane_dig_waited[8] = {};
@@ -750,14 +750,13 @@ int h264r_flush(h264r_ctx* ctx)
                     CU(cudaStreamWaitEvent(st, ctx->ev_lane[l], 0));
                 }
             for_chunks([&](const Pending& p) { return p.pp.slice_type == H264R_SLICE_P && p.n_intra < ctx->n_mbs; }, [&](const PicList& L) {
-                // grid.y = picture, grid.x strides over its macroblocks.  With several lanes the grid is persistent and
-                // sized below the SMs' capacity (inter_ctas_per_sm of 8), so that the wavefront kernels of the other
-                // lanes always find room next to it; with one lane about eight CTA generations.
+                // grid.y = picture, grid.x strides over its macroblocks: inter_ctas_per_sm CTAs per SM (the register file holds
+                // 8) times a few generations, i.e. every warp reconstructs a handful of macroblocks (its next header and
+                // offsets are always in flight) and late CTAs even out the tail.
                 int want = (ctx->n_mbs + INTER_WARPS - 1) / INTER_WARPS;
                 int cap = (sm_count * ctx->inter_ctas_per_sm * ctx->inter_generations + L.n - 1) / L.n;
                 dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)L.n);
-                // the throughput-bound launches of the lanes take turns (they would only share the SMs); what overlaps
-                // them is the latency-bound tail (intra macroblocks) of the OTHER lanes
+                // H264R_INTER_TOKEN=1 (experiment, measured slower): the k_inter launches of the lanes take turns
                 if (NL > 1 && ctx->inter_token && tok_valid) cudaStreamWaitEvent(st, ctx->ev_tok, 0);      // (errors surface at the flush's cudaGetLastError)
                 prof_begin(0);
                 const bool tma = ctx->d_tmaps != nullptr;

@@ -247,6 +247,20 @@ HD uint32_t load_mv(const PicDesc& pd, const h264r_mb_hdr& h, int a, int blk)
     if (pd.mv_off) return H264R_LDG(mv32 - 1 - (ptrdiff_t)(H264R_LDG(pd.mv_off + a) + (uint32_t)mv_part_index(h.mb_class, h.sub_mb_type, blk)));
     return H264R_LDG(mv32 + (size_t)a * 16 + blk);
 }
+// What a macroblock's phases read first and what depends on nothing but its address: fetched one macroblock ahead by
+// the flat kernels (next to the header), so that the chains mv_off -> vector -> window addresses and blk_off -> levels
+// start one memory round trip later
+struct MbPre { uint32_t mv_off, blk_mask, blk_off; };
+HD MbPre load_pre(const PicDesc& pd, int a)
+{
+    return MbPre{pd.mv_off ? H264R_LDG(pd.mv_off + a) : 0u, H264R_LDG(pd.blk_mask + a), H264R_LDG(pd.blk_off + a)};
+}
+HD uint32_t load_mv_pre(const PicDesc& pd, const h264r_mb_hdr& h, int a, int blk, const MbPre& pre)
+{
+    const uint32_t* mv32 = reinterpret_cast<const uint32_t*>(pd.mv);
+    if (pd.mv_off) return H264R_LDG(mv32 - 1 - (ptrdiff_t)(pre.mv_off + (uint32_t)mv_part_index(h.mb_class, h.sub_mb_type, blk)));
+    return H264R_LDG(mv32 + (size_t)a * 16 + blk);
+}
 HD int mv_x(uint32_t v) { return (int)(int16_t)(v & 0xffff); }
 HD int mv_y(uint32_t v) { return (int)v >> 16; }
 
@@ -261,6 +275,18 @@ HD void report_excursions(const PicDesc& pd, int a, uint32_t n)
 #endif
     if (pd.excursion_map) pd.excursion_map[a] = 1;
 }
+
+// Per-lane state that survives from one phase to the next: a register on the device, one slot per lane in the
+// host emulator (where the lanes of a phase run one after the other).
+template <class T> struct PerLane {
+#if defined(__CUDA_ARCH__)
+    T v;
+    HD T& operator()(int) { return v; }
+#else
+    T v[32];
+    T& operator()(int lane) { return v[lane]; }
+#endif
+};
 
 HD int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 HD int clip1(int v) { return clip3(0, 255, v); }

@@ -26,10 +26,11 @@ namespace h264r {
 // Hadamard (reference residual::Decode_Intra16x16, h264/residual.cpp:286-319) and bypass the scaling.
 // nz_flags (optional, 16 bytes): lane b < 16 records whether luma block b has a non-zero level, at its raster index.
 template <bool COMPAT>
-HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane, uint8_t* nz_flags, bool chroma_only)
+HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane, uint8_t* nz_flags, bool chroma_only,
+                            const MbPre* pre)
 {
     if (lane >= 24 || (chroma_only && lane < 16)) return;
-    const BlkRef br = load_blkref(pd, a);
+    const BlkRef br = pre ? BlkRef{pre->blk_mask, pre->blk_off} : load_blkref(pd, a);
     const int cbp_l = h.cbp & 15, cbp_c = (h.cbp >> 4) & 3;
     const bool luma = lane < 16, i16 = h.mb_class == H264R_MB_I16x16;
     bool active = luma ? (i16 || ((cbp_l >> (lane >> 2)) & 1) != 0) : cbp_c != 0;
@@ -288,18 +289,6 @@ HD void intra4_lut_fill(uint16_t* lut, int first, int stride)
 {
     for (int k = first; k < INTRA4_LUT_SIZE; k += stride) lut[k] = intra4_entry(k >> 4, k & 3, (k >> 2) & 3);
 }
-
-// Per-lane state that survives from one phase to the next: a register on the device, one slot per lane in the
-// host emulator (where the lanes of a phase run one after the other).
-template <class T> struct PerLane {
-#if defined(__CUDA_ARCH__)
-    T v;
-    HD T& operator()(int) { return v; }
-#else
-    T v[32];
-    T& operator()(int lane) { return v[lane]; }
-#endif
-};
 
 // The macroblock's inner wavefront: step d = 0..9 handles the blocks (bx, by) with bx + 2 by = d; half-warp
 // `lane >> 4` takes the block with by = by_min + (lane >> 4), lane & 15 = sample.  Everything about a lane's sample

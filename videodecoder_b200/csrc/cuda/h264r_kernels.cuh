@@ -104,11 +104,16 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, H264R_INTER_MIN_CTAS) k_inte
     const int stride = gridDim.x * INTER_WARPS;
     int a = blockIdx.x * INTER_WARPS + warp;
     int4 hraw = a < n_mbs ? __ldg(reinterpret_cast<const int4*>(pd.hdr + a)) : int4{0, 0, 0, 0};
+    MbPre pre_next = a < n_mbs ? load_pre(pd, a) : MbPre{0u, 0u, 0u};
     for (; a < n_mbs; a += stride) {
         h264r_mb_hdr h = *reinterpret_cast<h264r_mb_hdr*>(&hraw);
-        if (a + stride < n_mbs) hraw = __ldg(reinterpret_cast<const int4*>(pd.hdr + a + stride));
+        const MbPre pre = pre_next;
+        if (a + stride < n_mbs) {
+            hraw = __ldg(reinterpret_cast<const int4*>(pd.hdr + a + stride));
+            pre_next = load_pre(pd, a + stride);
+        }
         if (is_intra(h.mb_class)) continue;       // warp-uniform; the intra kernels reconstruct it afterwards
-        seq_inter_any<COMPAT, TMA>(ex, w, pd, g, h, a);
+        seq_inter_any<COMPAT, TMA>(ex, w, pd, g, h, a, pre);
     }
 }
 

@@ -270,7 +270,7 @@ HD void idct4_fast(const int c[16], const Dequant& q, bool dc_bypass, int r[16])
 // K1 for any 4x4-transform macroblock: h264r_intra.cuh
 template <bool COMPAT>
 HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane, uint8_t* nz_flags = nullptr,
-                            bool chroma_only = false);
+                            bool chroma_only = false, const MbPre* pre = nullptr);
 
 // ---- K1 with the 8x8 transform (ITU-T H.264 8.5.13, flat scaling lists; the reference has no 8x8 transform) ------------
 // LevelScale8x8 / 16 for position (i, j), qP % 6 = m: six classes of positions, one byte per class and m
@@ -478,7 +478,8 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int x, 
 // (the reference's j reaches row -3, D7).  Block positions are clamped to [-(bw+3), W+2] x [-(bh+3), H+3],
 // which gives every sample the value of the reference's per-sample coordinate clamp.
 template <bool COMPAT, bool TMA>
-HD void phase_inter_stage(InterWork& w, TmaState& ts, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane)
+HD void phase_inter_stage(InterWork& w, TmaState& ts, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane, uint32_t& mv_own,
+                          const MbPre& pre)
 {
     (void)ts;
     int shape;
@@ -492,10 +493,11 @@ HD void phase_inter_stage(InterWork& w, TmaState& ts, const PicDesc& pd, const G
     int mbx, mby;
     mb_xy(g, a, mbx, mby);
     const int W = g.w_mbs * 16, H = g.h_mbs * 16;
-    {
-        uint32_t v = load_mv(pd, h, a, lane >> 1);
-        w.need[lane] = (uint8_t)mc_need(mv_x(v) & 3, mv_y(v) & 3);
-    }
+    // the vector of the lane's own 4x4 block (lane >> 1): fetched once per macroblock, it serves the NEED bits, the window
+    // position below (a window's lanes are lanes of its blocks, which share the vector) and the compute phase
+    const uint32_t v = load_mv_pre(pd, h, a, lane >> 1, pre);
+    mv_own = v;
+    w.need[lane] = (uint8_t)mc_need(mv_x(v) & 3, mv_y(v) & 3);
 #if defined(__CUDA_ARCH__)
     if (TMA && shape < 2) {
         // reference-frame tiles by TMA: lane 0 posts the byte count and one tensor copy per window; every lane waits on
@@ -523,19 +525,17 @@ HD void phase_inter_stage(InterWork& w, TmaState& ts, const PicDesc& pd, const G
     }
 #endif
     if (shape == 0) {
-        const uint32_t v = load_mv(pd, h, a, 0);
         const uint8_t* ref = pd.ref_y[hdr_ref_idx(h, 0)];
         int xb = clip3(-19, W + 2, mbx * 16 + (mv_x(v) >> 2)), yb = clip3(-19, H + 3, mby * 16 + (mv_y(v) >> 2));
         stage_window<22, 6, 32, WIN0_PITCH>(w.win, ref, g.pitch_y, xb - 2, yb - 3, lane);
     } else if (shape == 1) {
-        const int q = lane >> 3, b0 = (q >> 1) * 8 + (q & 1) * 2;
-        const uint32_t v = load_mv(pd, h, a, b0);
+        // quadrant q is staged by the eight lanes of its four blocks
+        const int b = lane >> 1, bx = b & 3, by = b >> 2, q = (by >> 1) * 2 + (bx >> 1);
         const uint8_t* ref = pd.ref_y[hdr_ref_idx(h, q)];
         int xb = clip3(-11, W + 2, mbx * 16 + (q & 1) * 8 + (mv_x(v) >> 2)), yb = clip3(-11, H + 3, mby * 16 + (q >> 1) * 8 + (mv_y(v) >> 2));
-        stage_window<14, 4, 8, WIN1_PITCH>(w.win + q * WIN1_STRIDE, ref, g.pitch_y, xb - 2, yb - 3, lane & 7);
+        stage_window<14, 4, 8, WIN1_PITCH>(w.win + q * WIN1_STRIDE, ref, g.pitch_y, xb - 2, yb - 3, ((by & 1) * 2 + (bx & 1)) * 2 + (lane & 1));
     } else {
         const int b = lane >> 1, bx = b & 3, by = b >> 2, q = (by >> 1) * 2 + (bx >> 1);
-        const uint32_t v = load_mv(pd, h, a, b);
         const uint8_t* ref = pd.ref_y[hdr_ref_idx(h, q)];
         int ys = mby * 16 + by * 4;
         // reference's source-row offset for 4x4 sub-partitions 2 and 3 (D8, h264/macroblock.cpp:786-789)
@@ -685,7 +685,8 @@ HD uint32_t weight_packed(uint32_t pred, int logwd, int wgt, int off)
 // Phase M1: compute and store the macroblock (luma from the staged windows; chroma: COMPAT = residual
 // only, D4; spec = bilinear from the padded reference planes, ITU-T H.264 8.4.2.2.2).
 template <bool COMPAT, bool TMA>
-HD void phase_inter_compute(InterWork& w, TmaState& ts, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane, bool coded)
+HD void phase_inter_compute(InterWork& w, TmaState& ts, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane, bool coded,
+                            uint32_t mv_own)
 {
     (void)ts;
     int mbx, mby;
@@ -724,7 +725,7 @@ HD void phase_inter_compute(InterWork& w, TmaState& ts, const PicDesc& pd, const
     if (shape == 0) { wp = w.win + (by * 4 + half * 2) * WIN0_PITCH + bx; pitch = WIN0_PITCH; }
     else if (shape == 1) { wp = w.win + q * WIN1_STRIDE + ((by & 1) * 4 + half * 2) * WIN1_PITCH + (bx & 1); pitch = WIN1_PITCH; }
     else { wp = w.win + b * 30 + half * 2 * 3; pitch = 3; }
-    const uint32_t v = load_mv(pd, h, a, b);
+    const uint32_t v = mv_own;
     const McSel m = mc_select(mv_x(v) & 3, mv_y(v) & 3);
     uint32_t pred[2];
     if (TMA && tma) {
@@ -796,21 +797,22 @@ HD void phase_inter_compute(InterWork& w, TmaState& ts, const PicDesc& pd, const
 // K1+K3 sequence for one inter macroblock (4x4 transform).  8x8-transform macroblocks take seq_inter_mb
 // of h264r_seq.cuh.
 template <bool COMPAT, bool TMA, class Exec>
-HD void seq_inter_mb_fast(Exec& ex, InterWork& w, TmaState& ts, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a)
+HD void seq_inter_mb_fast(Exec& ex, InterWork& w, TmaState& ts, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, const MbPre& pre)
 {
     const bool coded = h.cbp != 0;
     const bool t8 = !COMPAT && coded && (h.flags & H264R_T8x8);        // REF_COMPAT has no 8x8 transform
+    PerLane<uint32_t> mv_own;
     ex([&](int lane) {
         if (t8) {
             phase_residual8_rows(w, pd, h, a, lane);
-            phase_residual_fast<COMPAT>(w.res, pd, h, a, lane, nullptr, true);
-        } else if (coded) phase_residual_fast<COMPAT>(w.res, pd, h, a, lane, (!COMPAT && pd.nzmask) ? w.nzf : nullptr);
-        phase_inter_stage<COMPAT, TMA>(w, ts, pd, g, h, a, lane);
+            phase_residual_fast<COMPAT>(w.res, pd, h, a, lane, nullptr, true, &pre);
+        } else if (coded) phase_residual_fast<COMPAT>(w.res, pd, h, a, lane, (!COMPAT && pd.nzmask) ? w.nzf : nullptr, false, &pre);
+        phase_inter_stage<COMPAT, TMA>(w, ts, pd, g, h, a, lane, mv_own(lane), pre);
     });
     if (t8) ex([&](int lane) { phase_residual8_cols(w, lane); });
     ex([&](int lane) {
         if (!COMPAT && pd.nzmask && lane == 0) pd.nzmask[a] = !coded ? 0u : (t8 ? nz_pack8(w.nzf) : nz_pack(w.nzf));
-        phase_inter_compute<COMPAT, TMA>(w, ts, pd, g, h, a, lane, coded);
+        phase_inter_compute<COMPAT, TMA>(w, ts, pd, g, h, a, lane, coded, mv_own(lane));
     });
     if (COMPAT) {        // border macroblocks replicate their samples into the frame's border (see phase_pad_mb_luma)
         int mbx, mby;

@@ -753,15 +753,15 @@ int h264r_flush(h264r_ctx* ctx)
                 // grid.y = picture, grid.x strides over its macroblocks: inter_ctas_per_sm CTAs per SM (the register file holds
                 // 8) times a few generations, i.e. every warp reconstructs a handful of macroblocks (its next header and
                 // offsets are always in flight) and late CTAs even out the tail.
-                int want = (ctx->n_mbs + INTER_WARPS - 1) / INTER_WARPS;
-                int cap = (sm_count * ctx->inter_ctas_per_sm * ctx->inter_generations + L.n - 1) / L.n;
+                int want = (ctx->n_mbs + KINTER_WARPS - 1) / KINTER_WARPS;
+                int cap = (sm_count * ctx->inter_ctas_per_sm * (4 / KINTER_WARPS) * ctx->inter_generations + L.n - 1) / L.n;      // inter_ctas_per_sm counts four warps
                 dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)L.n);
                 // H264R_INTER_TOKEN=1 (experiment, measured slower): the k_inter launches of the lanes take turns
                 if (NL > 1 && ctx->inter_token && tok_valid) cudaStreamWaitEvent(st, ctx->ev_tok, 0);      // (errors surface at the flush's cudaGetLastError)
                 prof_begin(0);
                 const bool tma = ctx->d_tmaps != nullptr;
-                if (compat) { if (tma) k_inter<true, true><<<grid, INTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); else k_inter<true, false><<<grid, INTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); }
-                else { if (tma) k_inter<false, true><<<grid, INTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); else k_inter<false, false><<<grid, INTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); }
+                if (compat) { if (tma) k_inter<true, true><<<grid, KINTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); else k_inter<true, false><<<grid, KINTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); }
+                else { if (tma) k_inter<false, true><<<grid, KINTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); else k_inter<false, false><<<grid, KINTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); }
                 prof_end();
                 if (NL > 1 && ctx->inter_token) { cudaEventRecord(ctx->ev_tok, st); tok_valid = true; }
                 ctx->last_launches++;

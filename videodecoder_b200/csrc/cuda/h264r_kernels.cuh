@@ -64,7 +64,11 @@ struct DescTable {
 #ifndef H264R_INTER_MIN_CTAS
 #define H264R_INTER_MIN_CTAS 8       // resident CTAs per SM the inter kernel is compiled for (register cap 65536 / (128 * this))
 #endif
-constexpr int INTER_WARPS = 4;       // warps per CTA of the inter / residual kernels
+constexpr int INTER_WARPS = 4;       // warps per CTA of the residual kernels
+#ifndef H264R_KINTER_WARPS
+#define H264R_KINTER_WARPS 1         // warps per CTA of k_inter.  1: the warp's working set is THE shared block of its CTA, a constant
+#endif                               // address -- with several warps per CTA the compiler recomputes `work + warp * size` from
+constexpr int KINTER_WARPS = H264R_KINTER_WARPS;      // threadIdx.x dozens of times per macroblock (it will not spend a register on it)
 
 // ------------------------------------------------------------------------------------------------
 // K1 alone: dequant + inverse transform of n_mbs macroblocks -> int16 residual (384 per MB).
@@ -87,11 +91,11 @@ __global__ void __launch_bounds__(INTER_WARPS * 32) k_residual(PicDesc pd, int n
 // ------------------------------------------------------------------------------------------------
 // TMA: reference windows of 16x16 / 8x8-quadrant blocks arrive by cp.async.bulk.tensor (h264r_mc.cuh) instead of loads.
 template <bool COMPAT, bool TMA>
-__global__ void __launch_bounds__(INTER_WARPS * 32, H264R_INTER_MIN_CTAS) k_inter(const DescTable descs, const __grid_constant__ PicList list, Geometry g)
+__global__ void __launch_bounds__(KINTER_WARPS * 32, H264R_INTER_MIN_CTAS * 4 / KINTER_WARPS) k_inter(const DescTable descs, const __grid_constant__ PicList list, Geometry g)
 {
-    __shared__ WarpWork work[INTER_WARPS];
-    int warp = threadIdx.x >> 5;
-    WarpExec ex{(int)(threadIdx.x & 31)};
+    __shared__ WarpWork work[KINTER_WARPS];
+    const int warp = KINTER_WARPS == 1 ? 0 : (int)(threadIdx.x >> 5);
+    WarpExec ex{KINTER_WARPS == 1 ? (int)threadIdx.x : (int)(threadIdx.x & 31)};
     WarpWork& w = work[warp];
     if (TMA) {
         if (ex.lane == 0) { w.tma.parity = 1u; mbar_init(&w.tma.mbar, 1); }       // first use waits for parity 0
@@ -101,8 +105,8 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, H264R_INTER_MIN_CTAS) k_inte
     const PicDesc& pd = descs[list.slot[blockIdx.y]];
     // the header of the warp's NEXT macroblock is fetched while the current one is reconstructed: it heads the
     // dependent chain header -> vectors -> window addresses -> reference loads
-    const int stride = gridDim.x * INTER_WARPS;
-    int a = blockIdx.x * INTER_WARPS + warp;
+    const int stride = gridDim.x * KINTER_WARPS;
+    int a = blockIdx.x * KINTER_WARPS + warp;
     int4 hraw = a < n_mbs ? __ldg(reinterpret_cast<const int4*>(pd.hdr + a)) : int4{0, 0, 0, 0};
     MbPre pre_next = a < n_mbs ? load_pre(pd, a) : MbPre{0u, 0u, 0u};
     for (; a < n_mbs; a += stride) {

@@ -32,6 +32,7 @@ struct Pending {
     bool mv_partition;      // vectors in partition order (h264r_submit_picture with n_mvs >= 0)
     int level_bytes;        // H264R_LEVELS_*: int16 levels (32-byte blocks); picture buffers only: int8 levels (16-byte blocks), compact (8-byte units)
     uint64_t seq;           // order of frame_end calls (= order of the uploads on the copy stream)
+    bool early;             // flush: the upload had landed when the flush began (index structures made up front, nothing to wait for)
 };
 
 }  // namespace
@@ -56,6 +57,8 @@ struct h264r_ctx {
     cudaEvent_t ev_scan[8] = {}, ev_wave[8] = {};
     cudaEvent_t ev_tok = nullptr;           // the k_inter launches of the lanes take turns (see h264r_flush)
     bool inter_token = false;
+    int digest_every = 1;                   // K5 launches cover this many waves of a flush (H264R_DIGEST_EVERY; measured: 1 is best)
+    bool pdl = true;                        // programmatic dependent launch of the P-wave kernels (H264R_PDL=0: plain launches)
     int inter_generations = 4;              // k_inter grid = SMs x inter_ctas_per_sm x this: a few CTA generations balance the tail
     cudaEvent_t ev_dig[64] = {};            // ring: digest launch number n is done
     uint64_t dig_seq = 0;
@@ -135,6 +138,22 @@ int fail(h264r_ctx* c, int code, const std::string& msg)
     } while (0)
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Launch with programmatic stream serialisation: the kernel may be scheduled while the kernel before it in the stream
+// is still draining; it runs what does not depend on that kernel (headers, residual, work lists) and meets it at
+// griddepcontrol.wait (grid_dependency_wait() in h264r_kernels.cuh).  The kernels of a P wave -- k_inter, k_intra_list,
+// then k_inter of the next wave -- follow each other this way: their launch latencies and tails overlap.
+template <class... KArgs, class... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 FramePool digest_pool(const h264r_ctx* c)
 {
@@ -277,6 +296,10 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
         if (e4) c->inter_token = atoi(e4) != 0;
         const char* e5 = getenv("H264R_INTER_GENS");
         if (e5 && atoi(e5) > 0) c->inter_generations = atoi(e5);
+        const char* e7 = getenv("H264R_DIGEST_EVERY");
+        if (e7 && atoi(e7) > 0) c->digest_every = atoi(e7);
+        const char* e8 = getenv("H264R_PDL");
+        if (e8) c->pdl = atoi(e8) != 0;
         const char* e3 = getenv("H264R_SPARSE_INTRA");
         if (e3) c->sparse_intra = atoi(e3) != 0;
         const char* e2 = getenv("H264R_INTER_CTAS");
@@ -362,6 +385,7 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     // ring of hand-over words: in flight are at most max_pending pictures x 2 wavefront kernels x (H + 1) words
     c->sync_ints = (size_t)8 * max_pending * (h_mbs + 1) + 1024;
     CUC(cudaMalloc(&c->d_sync, c->sync_ints * sizeof(int)));
+    CUC(cudaMemsetAsync(c->d_sync, 0, c->sync_ints * sizeof(int), c->stream));
     CUC(cudaStreamSynchronize(c->stream));
     c->frame_state.assign(max_frames, FRAME_FREE);
     c->frame_wave.assign(max_frames, -1);
@@ -624,6 +648,7 @@ int h264r_flush(h264r_ctx* ctx)
     ctx->timing_valid = false;
     const bool compat = (ctx->flags & H264R_REF_COMPAT) != 0;
     const int NL = ctx->n_lanes;
+    const bool pdl = ctx->pdl && !ctx->profiling;      // per-launch events sit between the kernels anyway
     // Dependency waves, and the LANE of every picture.  A lane is a CUDA stream that carries whole prediction chains:
     // a picture goes to the lane of its references (stream order is then its dependency), a picture without
     // references to the lane its frame slot used before (stream order protects the slot's old readers) or, for a
@@ -683,20 +708,25 @@ int h264r_flush(h264r_ctx* ctx)
     // hand-over words of one wavefront launch: a zeroed region of the ring (a region comes round again only after
     // far more pictures than can be in flight, see sync_ints)
     const size_t ring = ctx->sync_ints;
+    // Regions are clean when handed out: the whole ring is zeroed at creation and what a flush used is zeroed again
+    // behind its kernels (end of this function) -- no memset between two kernels of a lane, which would undo their
+    // programmatic overlap (see launch_pdl).
+    std::vector<std::pair<size_t, size_t>> sync_used;
     auto sync_region = [&](size_t ints) -> int* {
         if (ctx->sync_pos + ints > ring) ctx->sync_pos = 0;
         int* r = ctx->d_sync + ctx->sync_pos;
+        if (!sync_used.empty() && sync_used.back().first + sync_used.back().second == ctx->sync_pos) sync_used.back().second += ints;
+        else sync_used.push_back({ctx->sync_pos, ints});
         ctx->sync_pos += ints;
-        cudaMemsetAsync(r, 0, ints * sizeof(int), st);
         return r;
     };
     // runs f(list) over the pictures of (wave, lane) selected by pred, in chunks that fit the kernel parameters
     PicList list, list_frames;       // arena slots of a chunk, and the frame ids of the same pictures
-    int cur_wave = 0, cur_lane = 0;
+    int cur_wave = 0, cur_lane = 0, cur_wave_lo = -1;      // cur_wave_lo >= 0: waves cur_wave_lo .. cur_wave
     auto for_chunks = [&](auto pred, auto f) {
         list.n = 0;
         for (int i = 0; i < n; i++) {
-            if (run[i]->wave != cur_wave || run[i]->lane != cur_lane || !pred(*run[i])) continue;
+            if (run[i]->wave > cur_wave || run[i]->wave < (cur_wave_lo >= 0 ? cur_wave_lo : cur_wave) || run[i]->lane != cur_lane || !pred(*run[i])) continue;
             list_frames.slot[list.n] = run[i]->frame_id;
             list.slot[list.n++] = run[i]->slot;
             if (list.n == PIC_LIST_MAX) { list_frames.n = list.n; f(list); list.n = 0; }
@@ -705,35 +735,75 @@ int h264r_flush(h264r_ctx* ctx)
     };
     std::vector<uint8_t> lane_used(NL, 0);
     bool dig_used = false, tok_valid = false;
+    auto sparse = [&](const Pending& p) { return ctx->sparse_intra && p.pp.slice_type == H264R_SLICE_P && p.n_intra > 0 && p.n_intra * 8 < ctx->n_mbs; };
+    // Pictures whose upload has landed already (all of them in a resident batch): their index structures in one go, ahead
+    // of every wave, and no per-wave wait later -- stream operations between the kernels of two waves would serialise
+    // what launch_pdl lets overlap.
+    {
+        PicList EL;
+        EL.n = 0;
+        bool any = false;
+        auto launch = [&]() {
+            if (!EL.n) return;
+            k_blk_scan<<<EL.n, 1024, 0, ctx->prep_stream>>>(d_desc, EL, ctx->n_mbs);
+            ctx->last_launches++;
+            any = true;
+            EL.n = 0;
+        };
+        // uploads complete in submission order (one copy stream): a binary search over that order finds how many have landed
+        std::vector<Pending*> by_seq(run.begin(), run.end());
+        std::sort(by_seq.begin(), by_seq.end(), [](const Pending* x, const Pending* y) { return x->seq < y->seq; });
+        int lo = 0, hi = n;        // pictures [0, lo) have landed, [hi, n) have not
+        while (lo < hi) {
+            const int mid = lo == 0 ? hi - 1 : (lo + hi) / 2;       // first probe: the last picture (resident batches end here)
+            if (cudaEventQuery(ctx->ev_copied[by_seq[mid]->slot]) == cudaSuccess) lo = mid + 1; else hi = mid;
+        }
+        for (int i = 0; i < n; i++) by_seq[i]->early = i < lo;
+        for (int i = 0; i < n; i++) {
+            Pending* p = run[i];
+            if (p->early && (p->layout == 2 || sparse(*p))) {
+                EL.slot[EL.n++] = p->slot;
+                if (EL.n == PIC_LIST_MAX) launch();
+            }
+        }
+        launch();
+        (void)cudaGetLastError();       // cudaErrorNotReady of the queries is not an error
+        if (any) {
+            CU(cudaEventRecord(ctx->ev_scan[0], ctx->prep_stream));
+            for (int l = 0; l < NL; l++) CU(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->ev_scan[0], 0));
+        }
+    }
+    const int dig_every = ctx->digest_every;
     for (int wv = 0; wv < n_waves; wv++) {
         for (int lane = 0; lane < NL; lane++) {
             cur_wave = wv; cur_lane = lane;
             st = ctx->lane_stream[lane];
             // uploads run on the copy stream in frame_end order: the lane waits for the last-ended picture of this
             // (wave, lane), so the upload of later pictures overlaps the kernels of earlier ones
-            Pending* last = nullptr;
+            Pending* last = nullptr;       // last-ended picture of this (wave, lane) whose upload is still on its way
+            bool any_pic = false;
             uint32_t wait_lanes = 0;
             for (int i = 0; i < n; i++)
                 if (run[i]->wave == wv && run[i]->lane == lane) {
-                    if (!last || run[i]->seq > last->seq) last = run[i];
+                    any_pic = true;
+                    if (!run[i]->early && (!last || run[i]->seq > last->seq)) last = run[i];
                     wait_lanes |= foreign[i];
                 }
-            if (!last) continue;
+            if (!any_pic) continue;
             lane_used[lane] = 1;
             // block / vector offsets of the pictures that arrived packed: on the prep stream, behind the uploads and
             // ahead of the lanes (in a resident batch the scans of all waves are done while wave 0 computes)
             bool scanned = false;
-            auto sparse = [&](const Pending& p) { return ctx->sparse_intra && p.pp.slice_type == H264R_SLICE_P && p.n_intra > 0 && p.n_intra * 8 < ctx->n_mbs; };
-            for_chunks([&](const Pending& p) { return p.layout == 2 || sparse(p); }, [&](const PicList& L) {
+            for_chunks([&](const Pending& p) { return !p.early && (p.layout == 2 || sparse(p)); }, [&](const PicList& L) {
                 if (!scanned) cudaStreamWaitEvent(ctx->prep_stream, ctx->ev_copied[last->slot], 0);
                 scanned = true;
                 k_blk_scan<<<L.n, 1024, 0, ctx->prep_stream>>>(d_desc, L, ctx->n_mbs);
                 ctx->last_launches++;
             });
             if (scanned) {
-                CU(cudaEventRecord(ctx->ev_scan[lane], ctx->prep_stream));
-                CU(cudaStreamWaitEvent(st, ctx->ev_scan[lane], 0));
-            } else CU(cudaStreamWaitEvent(st, ctx->ev_copied[last->slot], 0));
+                CU(cudaEventRecord(ctx->ev_scan[1 + (lane & 3)], ctx->prep_stream));
+                CU(cudaStreamWaitEvent(st, ctx->ev_scan[1 + (lane & 3)], 0));
+            } else if (last) CU(cudaStreamWaitEvent(st, ctx->ev_copied[last->slot], 0));
             // a frame slot whose previous picture is still being digested (dig stream) must not be overwritten
             {
                 uint64_t need = 0;
@@ -760,8 +830,9 @@ int h264r_flush(h264r_ctx* ctx)
                 if (NL > 1 && ctx->inter_token && tok_valid) cudaStreamWaitEvent(st, ctx->ev_tok, 0);      // (errors surface at the flush's cudaGetLastError)
                 prof_begin(0);
                 const bool tma = ctx->d_tmaps != nullptr;
-                if (compat) { if (tma) k_inter<true, true><<<grid, KINTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); else k_inter<true, false><<<grid, KINTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); }
-                else { if (tma) k_inter<false, true><<<grid, KINTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); else k_inter<false, false><<<grid, KINTER_WARPS * 32, 0, st>>>(d_desc, L, ctx->g); }
+                const dim3 blk(KINTER_WARPS * 32);
+                if (compat) { if (tma) launch_pdl(k_inter<true, true>, grid, blk, st, pdl, d_desc, L, ctx->g); else launch_pdl(k_inter<true, false>, grid, blk, st, pdl, d_desc, L, ctx->g); }
+                else { if (tma) launch_pdl(k_inter<false, true>, grid, blk, st, pdl, d_desc, L, ctx->g); else launch_pdl(k_inter<false, false>, grid, blk, st, pdl, d_desc, L, ctx->g); }
                 prof_end();
                 if (NL > 1 && ctx->inter_token) { cudaEventRecord(ctx->ev_tok, st); tok_valid = true; }
                 ctx->last_launches++;
@@ -778,8 +849,8 @@ int h264r_flush(h264r_ctx* ctx)
                     int* sync = sync_region(1);       // the ticket
                     ctx->sparse_stamp++;
                     prof_begin(1);
-                    if (compat) k_intra_list<true><<<blocks, ROW_WARPS * 32, 0, st>>>(d_desc, SL, ctx->g, sync, ctx->sparse_stamp);
-                    else k_intra_list<false><<<blocks, ROW_WARPS * 32, 0, st>>>(d_desc, SL, ctx->g, sync, ctx->sparse_stamp);
+                    if (compat) launch_pdl(k_intra_list<true>, dim3(blocks), dim3(ROW_WARPS * 32), st, pdl, d_desc, SL, ctx->g, sync, ctx->sparse_stamp);
+                    else launch_pdl(k_intra_list<false>, dim3(blocks), dim3(ROW_WARPS * 32), st, pdl, d_desc, SL, ctx->g, sync, ctx->sparse_stamp);
                     prof_end();
                     ctx->last_launches++;
                     SL.n = 0;
@@ -840,7 +911,8 @@ int h264r_flush(h264r_ctx* ctx)
                     ctx->last_launches++;
                 });
             // K5 as part of the reconstruction, on the dig stream: nothing in the lane waits for it
-            if (ctx->flags & H264R_DIGESTS) {
+            if ((ctx->flags & H264R_DIGESTS) && (wv % dig_every == dig_every - 1 || wv == n_waves - 1)) {
+                cur_wave_lo = wv - wv % dig_every;
                 CU(cudaEventRecord(ctx->ev_wave[lane], st));
                 CU(cudaStreamWaitEvent(ctx->dig_stream, ctx->ev_wave[lane], 0));
                 prof_st = ctx->dig_stream;
@@ -856,6 +928,7 @@ int h264r_flush(h264r_ctx* ctx)
                     for (int i = 0; i < F.n; i++) { ctx->digest_valid[F.slot[i]] = 1; ctx->frame_dig_seq[F.slot[i]] = ctx->dig_seq; }
                 });
                 prof_st = nullptr;
+                cur_wave_lo = -1;
                 dig_used = true;
             }
         }
@@ -867,6 +940,7 @@ int h264r_flush(h264r_ctx* ctx)
             CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_lane[l], 0));
         }
     if (dig_used) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_dig[ctx->dig_seq & 63], 0));      // the dig stream runs in order: its last launch
+    for (auto& u : sync_used) CU(cudaMemsetAsync(ctx->d_sync + u.first, 0, u.second * sizeof(int), ctx->stream));
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaGetLastError());
     ctx->timing_valid = true;

@@ -5,6 +5,12 @@
 
 namespace h264r {
 
+// Programmatic dependent launch (see launch_pdl in h264r_api.cu).  launch_dependents: the next kernel of the stream may be
+// scheduled from now on.  wait: everything the previous kernel of the stream wrote is complete and visible (returns at once
+// when the launch was not programmatic).
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct WarpExec {
     int lane;
     template <class F> __device__ __forceinline__ void operator()(F f)
@@ -109,6 +115,9 @@ __global__ void __launch_bounds__(KINTER_WARPS * 32, H264R_INTER_MIN_CTAS * 4 / 
     int a = blockIdx.x * KINTER_WARPS + warp;
     int4 hraw = a < n_mbs ? __ldg(reinterpret_cast<const int4*>(pd.hdr + a)) : int4{0, 0, 0, 0};
     MbPre pre_next = a < n_mbs ? load_pre(pd, a) : MbPre{0u, 0u, 0u};
+    // syntax does not depend on the previous kernel of the stream, reference pictures do
+    grid_launch_dependents();
+    grid_dependency_wait();
     for (; a < n_mbs; a += stride) {
         h264r_mb_hdr h = *reinterpret_cast<h264r_mb_hdr*>(&hraw);
         const MbPre pre = pre_next;
@@ -310,6 +319,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_intra_list(const DescTabl
 {
     __shared__ MbWork work[ROW_WARPS];
     __shared__ uint16_t s_lut[INTRA4_LUT_SIZE];
+    grid_launch_dependents();
     intra4_lut_fill(s_lut, threadIdx.x, blockDim.x);
     __syncthreads();
     const int W = g.w_mbs, H = g.h_mbs, total = list.cum[list.n];
@@ -327,9 +337,9 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_intra_list(const DescTabl
         if (idx >= (int)H264R_LDG(pd.intra_list)) continue;      // the host's count was an upper bound
         const int a = (int)H264R_LDG(pd.intra_list + 1 + idx);
         const h264r_mb_hdr h = load_hdr(pd, a);
-
         int mbx, mby;
         mb_xy(g, a, mbx, mby);
+        grid_dependency_wait();       // k_inter's samples (the first ticket pays, later calls return at once)
         // lanes 0..3 look at A, D, B, C (an intra one must have been stamped), lanes 4..7 at the four macroblocks that
         // read this one's samples (if none is intra, the stamp -- a fence -- is skipped)
         bool publish;

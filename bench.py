@@ -408,11 +408,15 @@ def main():
         bytes_per_launch = per_mb[fam] * units / max(1, fam_n[fam] / prof_steps)
         sec_per_launch = fam_ms[fam] / 1000.0 / max(1, fam_n[fam])
         achieved = bytes_per_launch / sec_per_launch / 1e9 if sec_per_launch > 0 else 0.0
+        # DRAM bytes per launch of that kernel from the committed ncu --set full capture of this very workload (null when
+        # the launch size differs from the captured one)
         traffic = None
-        tj = os.path.join(ROOT, "profiles", "traffic.json")
+        tj = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
         if os.path.exists(tj):
             try:
-                traffic = json.load(open(tj)).get(["k_inter", "k_intra", "k_deblock"][fam])
+                tr = json.load(open(tj))
+                if tr.get("_pictures_per_launch") == G:
+                    traffic = tr[args.mode][["k_inter", "k_intra_rows", "k_deblock_rows"][fam]]["dram_bytes_per_launch"]
             except Exception:
                 traffic = None
         line = {

@@ -207,8 +207,9 @@ typedef struct h264r_picture_buf {
     uint32_t*     blk_mask;   /* [n_mbs]                    */
     int16_t*      blocks;     /* [max_blocks * 16]          */
     size_t        max_blocks;
-    int32_t       n_intra;    /* number of intra macroblocks in hdr[], as counted by the parser; -1 = unknown: the
-                                 library then walks hdr[] itself (and validates mb_class while there)            */
+    int32_t       n_intra;    /* EXACT number of intra macroblocks in hdr[], as counted by the parser (it sizes the work
+                                 list of the intra kernel: macroblocks beyond the count would not be reconstructed);
+                                 -1 = unknown: the library then walks hdr[] itself (and validates mb_class while there) */
     int32_t       level_bytes;/* storage of blocks[], one of H264R_LEVELS_*:
                                  _INT16 (2, default): int16 levels, 32 bytes per block;
                                  _INT8 (1): the parser wrote int8 levels, 16 bytes per block, through (int8_t*)blocks -- allowed

@@ -14,7 +14,7 @@ for rep in sys.argv[1:]:
     h, units = r[0], r[1]
     for row in r[2:]:
         name = row[h.index("Kernel Name")]
-        name = re.sub(r"\(.*", "", name).replace("void ", "").replace("h264r::", "").replace("(bool)", "")
+        name = re.sub(r"\(.*", "", name).replace("void ", "").replace("h264r::", "").replace("(bool)", "").replace(", ", ";")
         v = [name, row[h.index("launch__grid_size")], row[h.index("launch__block_size")]]
         for _, k in cols:
             x = row[h.index(k)] if k in h else ""

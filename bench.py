@@ -130,6 +130,24 @@ def reference_available():
     return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "h264ref_harness"))
 
 
+def bind_to_gpu_node(index):
+    """CPU affinity of this process := the CPUs NVML reports as local to GPU `index`.  Returns a note for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "host thread bound to the %d CPUs local to GPU %d" % (len(cpus), index)
+    except Exception as e:      # no NVML, no permission: run unbound
+        return "unbound (%s)" % type(e).__name__
+    return "unbound"
+
+
 def cpu_baseline(sample_frames=4):
     cores = os.cpu_count() or 1
     sp, qp = reference_sample(sample_frames)
@@ -214,6 +232,11 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
     torch.cuda.set_device(local)
+    # The rank's host thread and its pinned picture buffers belong on the NUMA node of its GPU (what a decoding service
+    # does with numactl): with 8 ranks the uploads otherwise cross the socket interconnect.  Restored before the CPU
+    # baseline, which is to use every core.
+    affinity_before = os.sched_getaffinity(0)
+    numa_note = bind_to_gpu_node(local) if world > 1 and not os.environ.get("H264R_BENCH_NO_BIND") else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -451,6 +474,9 @@ def main():
                                   "max_ms": max(t)}
         line["launch_profile"] = prof
         line["e2e_probe"] = e2e_probe
+        if numa_note:
+            line["config"]["host_binding"] = numa_note
+        os.sched_setaffinity(0, affinity_before)
         if world == 1 and not args.no_cpu_baseline and reference_available():
             try:
                 line["cpu_baseline"] = cpu_baseline(args.sample_frames)

@@ -131,3 +131,21 @@ def sanitize_with_oracle(w_mbs, h_mbs, gop, max_iter=40):
             raise RuntimeError("no convergence")
         outs.append(o)
     return gop
+
+
+def densify_levels(rng, gop, p_block=0.4, big=True):
+    """Makes the coefficient blocks of a GOP (spec-mode content: Clip1 keeps any value legal) dense and varied: a share of
+    the blocks that carry AC levels gets 7..15 of them, a few levels sit at the int8 limits, so that compact, plain-int8
+    and mixed macroblocks all occur in the compact transport.  Only positions 1..15 of blocks that already have an AC level
+    are touched: those are legal whatever the macroblock type and coded_block_pattern say."""
+    for p in gop:
+        c = p["coeff"].reshape(-1, 24, 16)
+        has_ac = (c[:, :, 1:] != 0).any(axis=2)
+        for a, b in zip(*np.nonzero(has_ac)):
+            if rng.random() < p_block:
+                n = int(rng.integers(7, 16))
+                pos = 1 + rng.choice(15, size=n, replace=False)
+                c[a, b, pos] = rng.choice([-3, -2, -1, 1, 2, 3], size=n)
+            elif big and rng.random() < 0.1:
+                c[a, b, 1 + int(rng.integers(0, 15))] = int(rng.choice([-128, 127]))
+    return gop

@@ -50,6 +50,22 @@ def test_gop_variants(built, compat, variant):
         assert a["excursions"] == b["excursions"]
 
 
+def test_compact_storage_dense_and_extreme_levels(built):
+    """the kernels' block readers on H264R_LEVELS_COMPACT storage with compact, plain and mixed macroblocks (7..16 levels
+    per block, levels at the int8 limits), fast and generic phases"""
+    from common import densify_levels
+    rng = np.random.default_rng(78)
+    w, h = 6, 4
+    cfg = workload.WorkloadConfig(compat=False, p_intra_in_p=0.25, num_ref=2, p_t8x8=0.3, p_i8x8=0.3, p_sub=(0.25, 0.25, 0.25, 0.25))
+    gop = densify_levels(rng, workload.make_gop(rng, w, h, 3, cfg))
+    want = run_sequence(oracle.recon_picture, w, h, 0, gop)
+    for variant in (emul.PACKED | emul.COMPACT, emul.PACKED | emul.COMPACT | emul.GENERIC_INTRA):
+        got = run_sequence(emul.recon_picture, w, h, variant, gop)
+        for i, (a, b) in enumerate(zip(want, got)):
+            for k in "yuv":
+                assert np.array_equal(a[k], b[k]), "variant %x picture %d plane %s" % (variant, i, k)
+
+
 def test_deblock_offsets_and_qp_extremes(built):
     """alpha/beta offsets and QPs at both ends of the tables"""
     for qp, offs in ((2, (0, 6, 6)), (50, (0, -6, -6)), (30, (0, 3, -3))):

@@ -91,6 +91,25 @@ def test_ragged_geometries(built, compat, w, h):
     check_vs_oracle(w, h, flags, gop, transport="bufmv")
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("transport", ["bufmv", "bufmv8", "packed"])
+def test_compact_transport_dense_and_extreme_levels(built, transport):
+    """H264R_LEVELS_COMPACT with macroblocks of every kind: all blocks sparse (one unit per block), blocks with 7..16 levels
+    (plain int8 blocks, two units), levels at -128 / 127; Intra16x16 and chroma DC levels read through the compact form.
+    Spec mode (Clip1 keeps any residual legal), against the oracle."""
+    from common import densify_levels
+    w, h = 13, 7
+    rng = np.random.default_rng(77)
+    cfg = workload.WorkloadConfig(compat=False, p_intra_in_p=0.2, num_ref=2, p_sub=(0.25, 0.25, 0.25, 0.25))
+    gop = densify_levels(rng, workload.make_gop(rng, w, h, 3, cfg))
+    if transport != "packed":
+        mask, blocks = pack.pack_blocks(gop[1]["coeff"])
+        cmask, units = pack.pack_compact(mask, blocks)
+        compact = (cmask & abi.BLK_COMPACT) != 0
+        assert compact.any() and (~compact & (mask != 0)).any()        # both kinds of macroblock are on the wire
+    check_vs_oracle(w, h, 0, gop, transport=transport)
+
+
 def test_4k_pictures_vs_oracle(built):
     """BASELINE config 5 geometry (3840x2160 = 240x135 MBs): I + 2 P against the oracle"""
     w, h = 240, 135

@@ -58,6 +58,7 @@ struct h264r_ctx {
     cudaEvent_t ev_tok = nullptr;           // the k_inter launches of the lanes take turns (see h264r_flush)
     bool inter_token = false;
     int digest_every = 1;                   // K5 launches cover this many waves of a flush (H264R_DIGEST_EVERY; measured: 1 is best)
+    bool lean_inter = true;                 // k_inter<LEAN> for pictures that qualify (H264R_LEAN=0: the generic instantiation)
     bool pdl = true;                        // programmatic dependent launch of the P-wave kernels (H264R_PDL=0: plain launches)
     int inter_generations = 4;              // k_inter grid = SMs x inter_ctas_per_sm x this: a few CTA generations balance the tail
     cudaEvent_t ev_dig[64] = {};            // ring: digest launch number n is done
@@ -298,6 +299,8 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
         if (e5 && atoi(e5) > 0) c->inter_generations = atoi(e5);
         const char* e7 = getenv("H264R_DIGEST_EVERY");
         if (e7 && atoi(e7) > 0) c->digest_every = atoi(e7);
+        const char* e9 = getenv("H264R_LEAN");
+        if (e9) c->lean_inter = atoi(e9) != 0;
         const char* e8 = getenv("H264R_PDL");
         if (e8) c->pdl = atoi(e8) != 0;
         const char* e3 = getenv("H264R_SPARSE_INTRA");
@@ -819,7 +822,10 @@ int h264r_flush(h264r_ctx* ctx)
                     CU(cudaEventRecord(ctx->ev_lane[l], ctx->lane_stream[l]));
                     CU(cudaStreamWaitEvent(st, ctx->ev_lane[l], 0));
                 }
-            for_chunks([&](const Pending& p) { return p.pp.slice_type == H264R_SLICE_P && p.n_intra < ctx->n_mbs; }, [&](const PicList& L) {
+            // lean pictures (picture buffers with partition-order vectors and compact levels, no weighting) and the others: see k_inter
+            auto lean_pic = [&](const Pending& p) { return ctx->lean_inter && p.layout == 2 && p.mv_partition && p.level_bytes == H264R_LEVELS_COMPACT && !p.pp.weighted_pred; };
+            for (int lean = 1; lean >= 0; lean--)
+            for_chunks([&](const Pending& p) { return p.pp.slice_type == H264R_SLICE_P && p.n_intra < ctx->n_mbs && (int)lean_pic(p) == lean; }, [&](const PicList& L) {
                 // grid.y = picture, grid.x strides over its macroblocks: inter_ctas_per_sm CTAs per SM (the register file holds
                 // 8) times a few generations, i.e. every warp reconstructs a handful of macroblocks (its next header and
                 // offsets are always in flight) and late CTAs even out the tail.
@@ -831,8 +837,13 @@ int h264r_flush(h264r_ctx* ctx)
                 prof_begin(0);
                 const bool tma = ctx->d_tmaps != nullptr;
                 const dim3 blk(KINTER_WARPS * 32);
-                if (compat) { if (tma) launch_pdl(k_inter<true, true>, grid, blk, st, pdl, d_desc, L, ctx->g); else launch_pdl(k_inter<true, false>, grid, blk, st, pdl, d_desc, L, ctx->g); }
-                else { if (tma) launch_pdl(k_inter<false, true>, grid, blk, st, pdl, d_desc, L, ctx->g); else launch_pdl(k_inter<false, false>, grid, blk, st, pdl, d_desc, L, ctx->g); }
+                if (lean) {
+                    if (compat) { if (tma) launch_pdl(k_inter<true, true, true>, grid, blk, st, pdl, d_desc, L, ctx->g); else launch_pdl(k_inter<true, false, true>, grid, blk, st, pdl, d_desc, L, ctx->g); }
+                    else { if (tma) launch_pdl(k_inter<false, true, true>, grid, blk, st, pdl, d_desc, L, ctx->g); else launch_pdl(k_inter<false, false, true>, grid, blk, st, pdl, d_desc, L, ctx->g); }
+                } else {
+                    if (compat) { if (tma) launch_pdl(k_inter<true, true, false>, grid, blk, st, pdl, d_desc, L, ctx->g); else launch_pdl(k_inter<true, false, false>, grid, blk, st, pdl, d_desc, L, ctx->g); }
+                    else { if (tma) launch_pdl(k_inter<false, true, false>, grid, blk, st, pdl, d_desc, L, ctx->g); else launch_pdl(k_inter<false, false, false>, grid, blk, st, pdl, d_desc, L, ctx->g); }
+                }
                 prof_end();
                 if (NL > 1 && ctx->inter_token) { cudaEventRecord(ctx->ev_tok, st); tok_valid = true; }
                 ctx->last_launches++;

@@ -128,14 +128,17 @@ HD int popc32(uint32_t v)
 #endif
 }
 HD BlkRef load_blkref(const PicDesc& pd, int a) { return BlkRef{H264R_LDG(pd.blk_mask + a), H264R_LDG(pd.blk_off + a)}; }
-HD bool blk_compact(const PicDesc& pd, const BlkRef& r) { return pd.level_fmt == H264R_LEVELS_COMPACT && ((r.mask >> 24) & 1u); }
-HD const uint8_t* blk_ptr(const PicDesc& pd, const BlkRef& r, int b)       // nullptr: block b is zero
+// (`fmt` = pd.level_fmt, passed explicitly: the lean instantiation of k_inter knows it at compile time)
+HD bool blk_compact(int fmt, const BlkRef& r) { return fmt == H264R_LEVELS_COMPACT && ((r.mask >> 24) & 1u); }
+HD bool blk_compact(const PicDesc& pd, const BlkRef& r) { return blk_compact(pd.level_fmt, r); }
+HD const uint8_t* blk_ptr(const PicDesc& pd, const BlkRef& r, int b, int fmt)       // nullptr: block b is zero
 {
     if (!((r.mask >> b) & 1u)) return nullptr;
     const uint32_t k = (uint32_t)popc32(r.mask & ((1u << b) - 1u));
-    if (pd.level_fmt == H264R_LEVELS_COMPACT) return reinterpret_cast<const uint8_t*>(pd.coeff) + ((size_t)r.off + (((r.mask >> 24) & 1u) ? k : 2u * k)) * 8;
-    return reinterpret_cast<const uint8_t*>(pd.coeff) + ((size_t)r.off + k) * (pd.level_fmt == H264R_LEVELS_INT8 ? 16 : 32);
+    if (fmt == H264R_LEVELS_COMPACT) return reinterpret_cast<const uint8_t*>(pd.coeff) + ((size_t)r.off + (((r.mask >> 24) & 1u) ? k : 2u * k)) * 8;
+    return reinterpret_cast<const uint8_t*>(pd.coeff) + ((size_t)r.off + k) * (fmt == H264R_LEVELS_INT8 ? 16 : 32);
 }
+HD const uint8_t* blk_ptr(const PicDesc& pd, const BlkRef& r, int b) { return blk_ptr(pd, r, b, pd.level_fmt); }
 // byte permute with sign replication: result byte i = byte (nibble i & 7) of the pool {a, b}, or, when bit 3 of the nibble is
 // set, 0x00 / 0xff after that byte's sign
 HD uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel)
@@ -157,10 +160,11 @@ HD uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel)
 #endif
 }
 // levels [first, first + 8) of a stored block (first = 0 or 8) as four words of two int16 each, whatever the storage
-HD int4 blk_levels8(const PicDesc& pd, const BlkRef& br, const uint8_t* p, int first)
+HD int4 blk_levels8(const PicDesc& pd, const BlkRef& br, const uint8_t* p, int first, int fmt)
 {
-    if (pd.level_fmt == H264R_LEVELS_INT16) return H264R_LDG(reinterpret_cast<const int4*>(p) + (first >> 3));
-    if (blk_compact(pd, br)) {
+    (void)pd;
+    if (fmt == H264R_LEVELS_INT16) return H264R_LDG(reinterpret_cast<const int4*>(p) + (first >> 3));
+    if (blk_compact(fmt, br)) {
         // position q holds level number popc(map below q); one byte permute with sign replication yields two
         // neighbouring positions as a pair of int16
         const uint2 v = H264R_LDG(reinterpret_cast<const uint2*>(p));
@@ -183,16 +187,19 @@ HD int4 blk_levels8(const PicDesc& pd, const BlkRef& br, const uint8_t* p, int f
     };
     return int4{pair(v.x, 0), pair(v.x, 1), pair(v.y, 0), pair(v.y, 1)};
 }
+HD int4 blk_levels8(const PicDesc& pd, const BlkRef& br, const uint8_t* p, int first) { return blk_levels8(pd, br, p, first, pd.level_fmt); }
 // level 0 of a stored block (Intra16x16 / chroma DC slot)
-HD int blk_level0(const PicDesc& pd, const BlkRef& br, const uint8_t* p)
+HD int blk_level0(const PicDesc& pd, const BlkRef& br, const uint8_t* p, int fmt)
 {
-    if (pd.level_fmt == H264R_LEVELS_INT16) return (int)H264R_LDG(reinterpret_cast<const int16_t*>(p));
-    if (blk_compact(pd, br)) {
+    (void)pd;
+    if (fmt == H264R_LEVELS_INT16) return (int)H264R_LDG(reinterpret_cast<const int16_t*>(p));
+    if (blk_compact(fmt, br)) {
         const uint32_t w = H264R_LDG(reinterpret_cast<const uint32_t*>(p));
         return (w & 1u) ? (int)(int8_t)(w >> 16) : 0;
     }
     return (int)(int8_t)H264R_LDG(p);
 }
+HD int blk_level0(const PicDesc& pd, const BlkRef& br, const uint8_t* p) { return blk_level0(pd, br, p, pd.level_fmt); }
 
 // Header fields that are indexed at run time.  The record lives in registers; indexing its byte arrays with a run-time
 // index would push it into local memory (an L1 round trip per access, more after every fence), so these read the two
@@ -255,10 +262,10 @@ HD MbPre load_pre(const PicDesc& pd, int a)
 {
     return MbPre{pd.mv_off ? H264R_LDG(pd.mv_off + a) : 0u, H264R_LDG(pd.blk_mask + a), H264R_LDG(pd.blk_off + a)};
 }
-HD uint32_t load_mv_pre(const PicDesc& pd, const h264r_mb_hdr& h, int a, int blk, const MbPre& pre)
+HD uint32_t load_mv_pre(const PicDesc& pd, const h264r_mb_hdr& h, int a, int blk, const MbPre& pre, bool partition_layout)
 {
     const uint32_t* mv32 = reinterpret_cast<const uint32_t*>(pd.mv);
-    if (pd.mv_off) return H264R_LDG(mv32 - 1 - (ptrdiff_t)(pre.mv_off + (uint32_t)mv_part_index(h.mb_class, h.sub_mb_type, blk)));
+    if (partition_layout) return H264R_LDG(mv32 - 1 - (ptrdiff_t)(pre.mv_off + (uint32_t)mv_part_index(h.mb_class, h.sub_mb_type, blk)));
     return H264R_LDG(mv32 + (size_t)a * 16 + blk);
 }
 HD int mv_x(uint32_t v) { return (int)(int16_t)(v & 0xffff); }

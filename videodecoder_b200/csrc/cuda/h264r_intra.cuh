@@ -25,14 +25,15 @@ namespace h264r {
 // (the reference zero-fills them, h264/residual.cpp:44-46).  Intra16x16: DC levels go through the 4x4
 // Hadamard (reference residual::Decode_Intra16x16, h264/residual.cpp:286-319) and bypass the scaling.
 // nz_flags (optional, 16 bytes): lane b < 16 records whether luma block b has a non-zero level, at its raster index.
-template <bool COMPAT>
+template <bool COMPAT, bool LEAN, bool INTER>
 HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane, uint8_t* nz_flags, bool chroma_only,
                             const MbPre* pre)
 {
     if (lane >= 24 || (chroma_only && lane < 16)) return;
+    const int fmt = LEAN ? H264R_LEVELS_COMPACT : pd.level_fmt;       // LEAN: see k_inter
     const BlkRef br = pre ? BlkRef{pre->blk_mask, pre->blk_off} : load_blkref(pd, a);
     const int cbp_l = h.cbp & 15, cbp_c = (h.cbp >> 4) & 3;
-    const bool luma = lane < 16, i16 = h.mb_class == H264R_MB_I16x16;
+    const bool luma = lane < 16, i16 = INTER ? false : h.mb_class == H264R_MB_I16x16;      // INTER: the caller only has inter macroblocks
     bool active = luma ? (i16 || ((cbp_l >> (lane >> 2)) & 1) != 0) : cbp_c != 0;
     int r[16];
     bool zero = true;
@@ -42,9 +43,9 @@ HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr&
     if (luma) { int ras = blk_raster(lane); dst = res + (ras >> 2) * 64 + (ras & 3) * 4; pitch = 16; }
     else { int plane = (lane - 16) >> 2, b = (lane - 16) & 3; dst = res + 256 + plane * 64 + (b >> 1) * 32 + (b & 1) * 4; pitch = 8; }
     if (active) {
-        const uint8_t* src = blk_ptr(pd, br, lane);
+        const uint8_t* src = blk_ptr(pd, br, lane, fmt);
         int4 v0 = int4{0, 0, 0, 0}, v1 = int4{0, 0, 0, 0};
-        if (src && blk_compact(pd, br)) {
+        if (src && blk_compact(fmt, br)) {
             // compact block: the levels are scattered into the lane's own (zeroed) 4x4 field of res[], which has the
             // raster shape of a block, and read back as rows
             const uint2 v = H264R_LDG(reinterpret_cast<const uint2*>(src));
@@ -66,7 +67,7 @@ HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr&
             const uint2 r2 = *reinterpret_cast<const uint2*>(dst + 2 * pitch), r3 = *reinterpret_cast<const uint2*>(dst + 3 * pitch);
             v0 = int4{(int)r0.x, (int)r0.y, (int)r1.x, (int)r1.y};
             if (luma || cbp_c == 2) v1 = int4{(int)r2.x, (int)r2.y, (int)r3.x, (int)r3.y};
-        } else if (src) { v0 = blk_levels8(pd, br, src, 0); if (luma || cbp_c == 2) v1 = blk_levels8(pd, br, src, 8); }
+        } else if (src) { v0 = blk_levels8(pd, br, src, 0, fmt); if (luma || cbp_c == 2) v1 = blk_levels8(pd, br, src, 8, fmt); }
         if (!luma && cbp_c != 2) { v0.x &= 0xffff; v0.y = v0.z = v0.w = 0; }        // DC only: AC levels are not coded
         int c[16];
         const int w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -83,8 +84,8 @@ HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr&
                 int t = 0;
 #pragma unroll
                 for (int l = 0; l < 4; l++) {
-                    const uint8_t* dp = blk_ptr(pd, br, blk_raster(k * 4 + l));
-                    int dc = dp ? blk_level0(pd, br, dp) : 0;
+                    const uint8_t* dp = blk_ptr(pd, br, blk_raster(k * 4 + l), fmt);
+                    int dc = dp ? blk_level0(pd, br, dp, fmt) : 0;
                     t += ((0xA6C0 >> (l * 4 + j)) & 1) ? -dc : dc;       // T rows {++++},{++--},{+--+},{+-+-}: bit = minus
                 }
                 f += ((0xA6C0 >> (i * 4 + k)) & 1) ? -t : t;
@@ -96,9 +97,9 @@ HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr&
         if (!luma) {
             int plane = (lane - 16) >> 2, b = (lane - 16) & 3;
             qp = plane ? h.qp_cr : h.qp_cb;
-            const uint8_t* d0 = blk_ptr(pd, br, 16 + plane * 4), * d1 = blk_ptr(pd, br, 17 + plane * 4);
-            const uint8_t* d2 = blk_ptr(pd, br, 18 + plane * 4), * d3 = blk_ptr(pd, br, 19 + plane * 4);
-            int c0 = d0 ? blk_level0(pd, br, d0) : 0, c1 = d1 ? blk_level0(pd, br, d1) : 0, c2 = d2 ? blk_level0(pd, br, d2) : 0, c3 = d3 ? blk_level0(pd, br, d3) : 0;
+            const uint8_t* d0 = blk_ptr(pd, br, 16 + plane * 4, fmt), * d1 = blk_ptr(pd, br, 17 + plane * 4, fmt);
+            const uint8_t* d2 = blk_ptr(pd, br, 18 + plane * 4, fmt), * d3 = blk_ptr(pd, br, 19 + plane * 4, fmt);
+            int c0 = d0 ? blk_level0(pd, br, d0, fmt) : 0, c1 = d1 ? blk_level0(pd, br, d1, fmt) : 0, c2 = d2 ? blk_level0(pd, br, d2, fmt) : 0, c3 = d3 ? blk_level0(pd, br, d3, fmt) : 0;
             int f;
             if (COMPAT) f = (b == 0 || b == 3) ? c3 : -c3;      // reference's chroma DC product (h264/matrix.cpp:150-171)
             else f = c0 + ((b & 1) ? -c1 : c1) + ((b & 2) ? -c2 : c2) + ((b == 1 || b == 2) ? -c3 : c3);

@@ -96,7 +96,11 @@ __global__ void __launch_bounds__(INTER_WARPS * 32) k_residual(PicDesc pd, int n
 // blockIdx.x strides over its macroblocks.
 // ------------------------------------------------------------------------------------------------
 // TMA: reference windows of 16x16 / 8x8-quadrant blocks arrive by cp.async.bulk.tensor (h264r_mc.cuh) instead of loads.
-template <bool COMPAT, bool TMA>
+// LEAN: every picture of the launch arrived as a picture buffer with partition-order vectors and compact levels and
+// without weighted prediction (what a host parser produces for ordinary P pictures; the scheduler checks).  The other
+// storages and the weighting then compile away: 300 instructions less in a kernel whose hot code does not fit the 32 KB
+// L1.5 instruction cache (ncu: "no instruction" is its second largest stall).
+template <bool COMPAT, bool TMA, bool LEAN>
 __global__ void __launch_bounds__(KINTER_WARPS * 32, H264R_INTER_MIN_CTAS * 4 / KINTER_WARPS) k_inter(const DescTable descs, const __grid_constant__ PicList list, Geometry g)
 {
     __shared__ WarpWork work[KINTER_WARPS];
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(KINTER_WARPS * 32, H264R_INTER_MIN_CTAS * 4 / 
             pre_next = load_pre(pd, a + stride);
         }
         if (is_intra(h.mb_class)) continue;       // warp-uniform; the intra kernels reconstruct it afterwards
-        seq_inter_any<COMPAT, TMA>(ex, w, pd, g, h, a, pre);
+        seq_inter_any<COMPAT, TMA, LEAN>(ex, w, pd, g, h, a, pre);
     }
 }
 

@@ -171,6 +171,21 @@ HD void phase_pad_mb_luma(uint8_t* org, int pitch, int w_mbs, int h_mbs, int mbx
         }
     }
 }
+// out of line on the device: one macroblock in twenty takes it, and the inter kernel's hot code should stay small
+#if defined(__CUDACC__)
+__device__ __noinline__ void pad_mb_luma_dev(uint8_t* org, int pitch, int w_mbs, int h_mbs, int mbx, int mby, int lane)
+{
+    phase_pad_mb_luma(org, pitch, w_mbs, h_mbs, mbx, mby, lane);
+}
+#endif
+HD void pad_mb_luma_cold(uint8_t* org, int pitch, int w_mbs, int h_mbs, int mbx, int mby, int lane)
+{
+#if defined(__CUDA_ARCH__)
+    pad_mb_luma_dev(org, pitch, w_mbs, h_mbs, mbx, mby, lane);
+#else
+    phase_pad_mb_luma(org, pitch, w_mbs, h_mbs, mbx, mby, lane);
+#endif
+}
 HD bool is_border_mb(const Geometry& g, int mbx, int mby) { return mbx == 0 || mby == 0 || mbx == g.w_mbs - 1 || mby == g.h_mbs - 1; }
 
 // Working set of the inter path (one per warp)
@@ -268,7 +283,7 @@ HD void idct4_fast(const int c[16], const Dequant& q, bool dc_bypass, int r[16])
 }
 
 // K1 for any 4x4-transform macroblock: h264r_intra.cuh
-template <bool COMPAT>
+template <bool COMPAT, bool LEAN = false, bool INTER = false>
 HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane, uint8_t* nz_flags = nullptr,
                             bool chroma_only = false, const MbPre* pre = nullptr);
 
@@ -477,13 +492,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int x, 
 // Window of a bw x bh block at integer position (xb, yb): bytes xb-2 .. and rows yb-3 .. yb+bh+2
 // (the reference's j reaches row -3, D7).  Block positions are clamped to [-(bw+3), W+2] x [-(bh+3), H+3],
 // which gives every sample the value of the reference's per-sample coordinate clamp.
-template <bool COMPAT, bool TMA>
+template <bool COMPAT, bool TMA, bool LEAN>
 HD void phase_inter_stage(InterWork& w, TmaState& ts, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane, uint32_t& mv_own,
                           const MbPre& pre)
 {
     (void)ts;
+    const bool partition_layout = LEAN ? true : pd.mv_off != nullptr;
     int shape;
-    if (pd.mv_off) shape = inter_shape_by_type(h);
+    if (partition_layout) shape = inter_shape_by_type(h);
     else {
         uint32_t mv[16];
         load_mvs(pd, a, mv);
@@ -495,7 +511,7 @@ HD void phase_inter_stage(InterWork& w, TmaState& ts, const PicDesc& pd, const G
     const int W = g.w_mbs * 16, H = g.h_mbs * 16;
     // the vector of the lane's own 4x4 block (lane >> 1): fetched once per macroblock, it serves the NEED bits, the window
     // position below (a window's lanes are lanes of its blocks, which share the vector) and the compute phase
-    const uint32_t v = load_mv_pre(pd, h, a, lane >> 1, pre);
+    const uint32_t v = load_mv_pre(pd, h, a, lane >> 1, pre, partition_layout);
     mv_own = v;
     w.need[lane] = (uint8_t)mc_need(mv_x(v) & 3, mv_y(v) & 3);
 #if defined(__CUDA_ARCH__)
@@ -684,11 +700,12 @@ HD uint32_t weight_packed(uint32_t pred, int logwd, int wgt, int off)
 
 // Phase M1: compute and store the macroblock (luma from the staged windows; chroma: COMPAT = residual
 // only, D4; spec = bilinear from the padded reference planes, ITU-T H.264 8.4.2.2.2).
-template <bool COMPAT, bool TMA>
+template <bool COMPAT, bool TMA, bool LEAN>
 HD void phase_inter_compute(InterWork& w, TmaState& ts, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane, bool coded,
                             uint32_t mv_own)
 {
     (void)ts;
+    const bool weighted = LEAN ? false : pd.weighted_pred != 0;
     int mbx, mby;
     mb_xy(g, a, mbx, mby);
     // warp-wide union of the NEED bits
@@ -738,7 +755,7 @@ HD void phase_inter_compute(InterWork& w, TmaState& ts, const PicDesc& pd, const
         else mc_patch<COMPAT, 2, false>(wp, pitch, 0, m, pred);
     }
     const int ri = hdr_ref_idx(h, q);
-    if (pd.weighted_pred) {
+    if (weighted) {
         pred[0] = weight_packed(pred[0], pd.luma_log2_wd, pd.luma_weight[ri], pd.luma_offset[ri]);
         pred[1] = weight_packed(pred[1], pd.luma_log2_wd, pd.luma_weight[ri], pd.luma_offset[ri]);
     }
@@ -783,7 +800,7 @@ HD void phase_inter_compute(InterWork& w, TmaState& ts, const PicDesc& pd, const
                     const int A = (int)((r0 >> (8 * k)) & 255u), B = (int)((r0 >> (8 * k + 8)) & 255u);
                     const int C = (int)((r1 >> (8 * k)) & 255u), D = (int)((r1 >> (8 * k + 8)) & 255u);
                     int pv = (w00 * A + w01 * B + w10 * C + w11 * D + 32) >> 6;
-                    if (pd.weighted_pred) pv = weight_pred(pv, pd.chroma_log2_wd, pd.chroma_weight[rc][plane], pd.chroma_offset[rc][plane]);
+                    if (weighted) pv = weight_pred(pv, pd.chroma_log2_wd, pd.chroma_weight[rc][plane], pd.chroma_offset[rc][plane]);
                     if (coded) pv += w.res[256 + plane * 64 + cy * 8 + cx + k];
                     packed |= (uint32_t)clip1(pv) << (8 * (2 * k2 + k));
                 }
@@ -796,7 +813,7 @@ HD void phase_inter_compute(InterWork& w, TmaState& ts, const PicDesc& pd, const
 
 // K1+K3 sequence for one inter macroblock (4x4 transform).  8x8-transform macroblocks take seq_inter_mb
 // of h264r_seq.cuh.
-template <bool COMPAT, bool TMA, class Exec>
+template <bool COMPAT, bool TMA, bool LEAN, class Exec>
 HD void seq_inter_mb_fast(Exec& ex, InterWork& w, TmaState& ts, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, const MbPre& pre)
 {
     const bool coded = h.cbp != 0;
@@ -805,19 +822,19 @@ HD void seq_inter_mb_fast(Exec& ex, InterWork& w, TmaState& ts, const PicDesc& p
     ex([&](int lane) {
         if (t8) {
             phase_residual8_rows(w, pd, h, a, lane);
-            phase_residual_fast<COMPAT>(w.res, pd, h, a, lane, nullptr, true, &pre);
-        } else if (coded) phase_residual_fast<COMPAT>(w.res, pd, h, a, lane, (!COMPAT && pd.nzmask) ? w.nzf : nullptr, false, &pre);
-        phase_inter_stage<COMPAT, TMA>(w, ts, pd, g, h, a, lane, mv_own(lane), pre);
+            phase_residual_fast<COMPAT, LEAN, true>(w.res, pd, h, a, lane, nullptr, true, &pre);
+        } else if (coded) phase_residual_fast<COMPAT, LEAN, true>(w.res, pd, h, a, lane, (!COMPAT && pd.nzmask) ? w.nzf : nullptr, false, &pre);
+        phase_inter_stage<COMPAT, TMA, LEAN>(w, ts, pd, g, h, a, lane, mv_own(lane), pre);
     });
     if (t8) ex([&](int lane) { phase_residual8_cols(w, lane); });
     ex([&](int lane) {
         if (!COMPAT && pd.nzmask && lane == 0) pd.nzmask[a] = !coded ? 0u : (t8 ? nz_pack8(w.nzf) : nz_pack(w.nzf));
-        phase_inter_compute<COMPAT, TMA>(w, ts, pd, g, h, a, lane, coded, mv_own(lane));
+        phase_inter_compute<COMPAT, TMA, LEAN>(w, ts, pd, g, h, a, lane, coded, mv_own(lane));
     });
     if (COMPAT) {        // border macroblocks replicate their samples into the frame's border (see phase_pad_mb_luma)
         int mbx, mby;
         mb_xy(g, a, mbx, mby);
-        if (is_border_mb(g, mbx, mby)) ex([&](int lane) { phase_pad_mb_luma(pd.y, g.pitch_y, g.w_mbs, g.h_mbs, mbx, mby, lane); });
+        if (is_border_mb(g, mbx, mby)) ex([&](int lane) { pad_mb_luma_cold(pd.y, g.pitch_y, g.w_mbs, g.h_mbs, mbx, mby, lane); });
     }
 }
 

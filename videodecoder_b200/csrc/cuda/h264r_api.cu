@@ -60,7 +60,7 @@ struct h264r_ctx {
     int digest_every = 1;                   // K5 launches cover this many waves of a flush (H264R_DIGEST_EVERY; measured: 1 is best)
     bool lean_inter = true;                 // k_inter<LEAN> for pictures that qualify (H264R_LEAN=0: the generic instantiation)
     bool pdl = true;                        // programmatic dependent launch of the P-wave kernels (H264R_PDL=0: plain launches)
-    int inter_generations = 4;              // k_inter grid = SMs x inter_ctas_per_sm x this: a few CTA generations balance the tail
+    int inter_generations = 8;              // k_inter grid = SMs x inter_ctas_per_sm x this: a few CTA generations balance the tail
     cudaEvent_t ev_dig[64] = {};            // ring: digest launch number n is done
     uint64_t dig_seq = 0;
     uint64_t lane_dig_waited[8] = {};

@@ -343,6 +343,10 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_intra_list(const DescTabl
         const h264r_mb_hdr h = load_hdr(pd, a);
         int mbx, mby;
         mb_xy(g, a, mbx, mby);
+        // the residual needs no sample: computed before this launch's dependency on k_inter is awaited (the generic
+        // phases of the 8x8 transform compute their own)
+        const bool res_early = COMPAT || !(h.mb_class == H264R_MB_I8x8 || (h.flags & H264R_T8x8));
+        if (res_early) ex([&](int lane) { phase_residual_fast<COMPAT>(w.res, pd, h, a, lane); });
         grid_dependency_wait();       // k_inter's samples (the first ticket pays, later calls return at once)
         // lanes 0..3 look at A, D, B, C (an intra one must have been stamped), lanes 4..7 at the four macroblocks that
         // read this one's samples (if none is intra, the stamp -- a fence -- is skipped)
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_intra_list(const DescTabl
                 wait_progress(pd.intra_done + nbj, stamp);
             }
         }
-        seq_intra_any<COMPAT>(ex, w, s_lut, pd, g, h, a, false, false);
+        seq_intra_any<COMPAT>(ex, w, s_lut, pd, g, h, a, false, res_early);
         // ex() ended with __syncwarp(): every lane's stores precede lane 0's release
         if (publish && ex.lane == 0) st_release_gpu(pd.intra_done + a, stamp);
     }

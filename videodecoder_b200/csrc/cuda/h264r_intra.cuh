@@ -122,8 +122,8 @@ HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr&
     for (int i = 0; i < 4; i++) {
         uint32_t lo = 0, hi = 0;
         if (!zero) {
-            lo = (uint32_t)(sat16(r[i * 4]) & 0xffff) | ((uint32_t)sat16(r[i * 4 + 1]) << 16);
-            hi = (uint32_t)(sat16(r[i * 4 + 2]) & 0xffff) | ((uint32_t)sat16(r[i * 4 + 3]) << 16);
+            lo = pack_sat_s16x2(r[i * 4], r[i * 4 + 1]);
+            hi = pack_sat_s16x2(r[i * 4 + 2], r[i * 4 + 3]);
         }
         *reinterpret_cast<uint2*>(dst + i * pitch) = uint2{lo, hi};
     }

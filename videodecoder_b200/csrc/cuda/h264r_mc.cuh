@@ -72,6 +72,17 @@ HD uint32_t pack_sat_u8(int v0, int v1, int v2, int v3)
     return (uint32_t)clip1(v0) | ((uint32_t)clip1(v1) << 8) | ((uint32_t)clip1(v2) << 16) | ((uint32_t)clip1(v3) << 24);
 #endif
 }
+// {sat16(lo), sat16(hi)} as two 16-bit halves, sat16 = clamp to [-32768, 32767]
+HD uint32_t pack_sat_s16x2(int lo, int hi)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(r) : "r"(hi), "r"(lo));
+    return r;
+#else
+    return (uint32_t)(clip3(-32768, 32767, lo) & 0xffff) | ((uint32_t)clip3(-32768, 32767, hi) << 16);
+#endif
+}
 // per byte (a + b + 1) >> 1
 HD uint32_t avg_u8x4(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) & 0xfefefefeu) >> 1); }
 // per 16-bit half a + b (wrapping)

@@ -516,7 +516,7 @@ HD void phase_inter_stage(InterWork& w, TmaState& ts, const PicDesc& pd, const G
         load_mvs(pd, a, mv);
         shape = inter_shape<COMPAT>(h, mv);
     }
-    if (lane == 0) w.shape = shape;
+    if (!LEAN && lane == 0) w.shape = shape;
     int mbx, mby;
     mb_xy(g, a, mbx, mby);
     const int W = g.w_mbs * 16, H = g.h_mbs * 16;
@@ -524,6 +524,9 @@ HD void phase_inter_stage(InterWork& w, TmaState& ts, const PicDesc& pd, const G
     // position below (a window's lanes are lanes of its blocks, which share the vector) and the compute phase
     const uint32_t v = load_mv_pre(pd, h, a, lane >> 1, pre, partition_layout);
     mv_own = v;
+#if defined(__CUDA_ARCH__)
+    if (TMA)        // (the load-staged device path takes the union of the NEED bits with one warp reduction, see phase_inter_compute)
+#endif
     w.need[lane] = (uint8_t)mc_need(mv_x(v) & 3, mv_y(v) & 3);
 #if defined(__CUDA_ARCH__)
     if (TMA && shape < 2) {
@@ -721,6 +724,10 @@ HD void phase_inter_compute(InterWork& w, TmaState& ts, const PicDesc& pd, const
     mb_xy(g, a, mbx, mby);
     // warp-wide union of the NEED bits
     int wn;
+#if defined(__CUDA_ARCH__)
+    if (!TMA) wn = (int)__reduce_or_sync(0xffffffffu, (unsigned)mc_need(mv_x(mv_own) & 3, mv_y(mv_own) & 3));      // every lane of the warp runs this phase
+    else
+#endif
     {
         const uint4* np = reinterpret_cast<const uint4*>(w.need);
         uint4 n0 = np[0], n1 = np[1];
@@ -729,7 +736,7 @@ HD void phase_inter_compute(InterWork& w, TmaState& ts, const PicDesc& pd, const
         wn = (int)(o & 15u);
     }
     const int b = lane >> 1, half = lane & 1, bx = b & 3, by = b >> 2, q = (by >> 1) * 2 + (bx >> 1);
-    const int shape = w.shape;
+    const int shape = LEAN ? inter_shape_by_type(h) : w.shape;       // (partition layout: the type says it)
     const uint32_t* wp;
     int pitch;
     bool tma = false;

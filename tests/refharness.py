@@ -10,6 +10,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "h264ref_harness")
+ADAPTER = os.path.join(ROOT, "oracle", "_ref", "h264ref_adapter")      # reference host side + INTEGRATION.md's binding + libh264r.so
 
 HDR_INTS = 25
 MB_REC_INTS = 34 + 32 + 256 + 64 + 64 + 256
@@ -39,6 +40,42 @@ def run_reference(stream, queue, level=2, keep=None):
                 os.remove(p)
         os.rmdir(d)
     return pics, stats
+
+
+def have_adapter():
+    return os.path.exists(ADAPTER)
+
+
+def run_adapter(stream, queue, n_mbs=None, pack_only=False):
+    """Runs the reference-side binding (oracle/shims/adapter_main.cpp).  pack_only: returns the packed buffers per picture
+    [(hdr (n,16) u8, mv (n,32) i16, coeff (n,384) i16)...] without touching the GPU; else the adapter's verdict (dict)."""
+    d = tempfile.mkdtemp(prefix="h264ada_")
+    sp, qp, op = (os.path.join(d, n) for n in ("s.264", "q.bin", "pack.bin"))
+    try:
+        with open(sp, "wb") as f:
+            f.write(stream)
+        np.asarray(queue, dtype=np.int32).tofile(qp)
+        r = subprocess.run([ADAPTER, sp, qp] + (["--pack-only", op] if pack_only else []), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        if r.returncode not in (0, 1):
+            raise RuntimeError("adapter failed (%d): %s" % (r.returncode, r.stderr[-2000:]))
+        verdict = json.loads(r.stdout.strip().splitlines()[-1])
+        verdict["returncode"] = r.returncode
+        if not pack_only:
+            return verdict
+        raw = np.fromfile(op, dtype=np.uint8)
+        per = n_mbs * (16 + 64 + 768)
+        assert raw.size == per * verdict["pictures"]
+        out = []
+        for i in range(verdict["pictures"]):
+            b = raw[i * per:(i + 1) * per]
+            out.append((b[:n_mbs * 16].reshape(n_mbs, 16), b[n_mbs * 16:n_mbs * 80].view(np.int16).reshape(n_mbs, 32),
+                        b[n_mbs * 80:].view(np.int16).reshape(n_mbs, 384)))
+        return out
+    finally:
+        for p in (sp, qp, op):
+            if os.path.exists(p):
+                os.remove(p)
+        os.rmdir(d)
 
 
 def parse_dump(path):

@@ -1,0 +1,140 @@
+/* h264r_writer.h -- host-side helper for C / C++ parsers: fills an h264r_picture_buf macroblock by macroblock in the
+ * transport formats of h264r.h (block masks, partition-order vectors growing backward from mv_end, present blocks as
+ * H264R_LEVELS_COMPACT units or int16 blocks), so that a parser that has a macroblock's syntax the way the reference
+ * has it -- one final vector per 4x4 block, 24 x 16 levels, raster inside the block (see "Coefficients" in h264r.h) --
+ * gets the one-DMA transport without knowing its byte layout.  Header-only, plain C99, no dependency on the library.
+ *
+ *   h264r_writer w;
+ *   h264r_writer_begin(&w, &buf, n_mbs, H264R_LEVELS_COMPACT);
+ *   for every macroblock in address order:
+ *       rc = h264r_writer_mb(&w, &hdr, mv, coeff);      (mv: 32 int16 or NULL for intra; coeff: 384 int16)
+ *       rc == H264R_E_INVAL on a level outside int8 in a COMPACT picture: begin again with H264R_LEVELS_INT16
+ *   h264r_writer_end(&w, &n_blocks, &n_mvs);
+ *   h264r_submit_picture(ctx, frame_id, &buf, n_blocks, n_mvs);
+ *
+ * Replaces, on the reference's side, nothing: it is what Slice::PraseSliceDataer (h264/slice.cpp:357-367) would call per
+ * macroblock instead of macroblock::Calc once macroblock::Parse has filled the macroblock; the Python
+ * twin is videodecoder_b200/pack.py (pack_blocks, pack_compact, pack_mvs_partition) and tests/test_adapter.py compares
+ * the two byte for byte.
+ */
+#ifndef H264R_WRITER_H
+#define H264R_WRITER_H
+
+#include <string.h>
+#include "h264r.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct h264r_writer {
+    h264r_picture_buf* buf;
+    int    n_mbs, next_mb;
+    int    level_fmt;        /* H264R_LEVELS_COMPACT or H264R_LEVELS_INT16 */
+    size_t n_units;          /* 8-byte units (COMPACT) or 32-byte blocks (INT16) written so far */
+    long   n_mvs;
+    int    n_intra;
+} h264r_writer;
+
+static inline void h264r_writer_begin(h264r_writer* w, h264r_picture_buf* buf, int n_mbs, int level_fmt)
+{
+    w->buf = buf; w->n_mbs = n_mbs; w->next_mb = 0; w->level_fmt = level_fmt;
+    w->n_units = 0; w->n_mvs = 0; w->n_intra = 0;
+}
+
+/* number of vectors the bitstream carries for a macroblock (mvd loops of macroblock::Parse, h264/macroblock.cpp:360-398) and
+ * the first 4x4 block (raster) of each of them */
+static inline int h264r_writer_partitions(const h264r_mb_hdr* h, int first_block[16])
+{
+    static const int sub_count[4] = {1, 2, 2, 4};                                   /* H264R_SUB_8x8, 8x4, 4x8, 4x4 */
+    static const int sub_first[4][4] = {{0, 0, 0, 0}, {0, 4, 0, 0}, {0, 1, 0, 0}, {0, 1, 4, 5}};
+    int n = 0, q, k;
+    switch (h->mb_class) {
+    case H264R_MB_P16x16: first_block[n++] = 0; break;
+    case H264R_MB_P16x8:  first_block[n++] = 0; first_block[n++] = 8; break;
+    case H264R_MB_P8x16:  first_block[n++] = 0; first_block[n++] = 2; break;
+    case H264R_MB_P8x8:
+        for (q = 0; q < 4; q++) {
+            const int s = (h->sub_mb_type >> (2 * q)) & 3, b0 = (q >> 1) * 8 + (q & 1) * 2;
+            for (k = 0; k < sub_count[s]; k++) first_block[n++] = b0 + sub_first[s][k];
+        }
+        break;
+    default: break;                                                                 /* intra: none */
+    }
+    return n;
+}
+
+/* One macroblock: hdr as it goes on the wire; mv = the final vector of each 4x4 block (32 int16, raster) or NULL for an intra
+ * macroblock; coeff = 24 blocks x 16 levels as described under "Coefficients" in h264r.h.  Returns H264R_OK, H264R_E_STATE
+ * (more macroblocks than begun with), H264R_E_CAPACITY (the buffer's block area is full) or H264R_E_INVAL (a level outside
+ * [-128, 127] in a COMPACT picture). */
+static inline int h264r_writer_mb(h264r_writer* w, const h264r_mb_hdr* hdr, const int16_t* mv, const int16_t* coeff)
+{
+    h264r_picture_buf* b = w->buf;
+    uint32_t mask = 0;
+    int blk, k, n_present = 0, compact = 1, part[16], n_part;
+    if (w->next_mb >= w->n_mbs) return H264R_E_STATE;
+    for (blk = 0; blk < 24; blk++) {
+        int nz = 0;
+        for (k = 0; k < 16; k++) {
+            const int v = coeff[blk * 16 + k];
+            if (v) {
+                nz++;
+                if (w->level_fmt == H264R_LEVELS_COMPACT && (v < -128 || v > 127)) return H264R_E_INVAL;
+            }
+        }
+        if (nz) { mask |= 1u << blk; n_present++; if (nz > 6) compact = 0; }
+    }
+    if (w->level_fmt == H264R_LEVELS_COMPACT) {
+        uint8_t* units = (uint8_t*)b->blocks;
+        const size_t need = (size_t)n_present * (compact ? 1 : 2);
+        if (w->n_units + need > b->max_blocks * 4) return H264R_E_CAPACITY;
+        for (blk = 0; blk < 24; blk++) {
+            uint8_t* u = units + w->n_units * 8;
+            const int16_t* c = coeff + blk * 16;
+            if (!((mask >> blk) & 1u)) continue;
+            if (compact) {                     /* significance map, then the levels in position order */
+                int n = 0;
+                memset(u, 0, 8);
+                for (k = 0; k < 16; k++)
+                    if (c[k]) { u[k >> 3] |= (uint8_t)(1u << (k & 7)); u[2 + n++] = (uint8_t)(int8_t)c[k]; }
+                w->n_units += 1;
+            } else {                           /* int8 levels, raster: two units */
+                for (k = 0; k < 16; k++) u[k] = (uint8_t)(int8_t)c[k];
+                w->n_units += 2;
+            }
+        }
+        if (compact && n_present) mask |= H264R_BLK_COMPACT;
+    } else {
+        if (w->n_units + (size_t)n_present > b->max_blocks) return H264R_E_CAPACITY;
+        for (blk = 0; blk < 24; blk++)
+            if ((mask >> blk) & 1u) { memcpy(b->blocks + w->n_units * 16, coeff + blk * 16, 32); w->n_units++; }
+    }
+    b->hdr[w->next_mb] = *hdr;
+    b->blk_mask[w->next_mb] = mask;
+    n_part = mv ? h264r_writer_partitions(hdr, part) : 0;
+    for (k = 0; k < n_part; k++) {             /* vector i of the picture at mv_end[-2(i+1)], mv_end[-2(i+1)+1] */
+        b->mv_end[-2 * (w->n_mvs + 1)] = mv[part[k] * 2];
+        b->mv_end[-2 * (w->n_mvs + 1) + 1] = mv[part[k] * 2 + 1];
+        w->n_mvs++;
+    }
+    if (hdr->mb_class <= H264R_MB_I16x16) w->n_intra++;
+    w->next_mb++;
+    return H264R_OK;
+}
+
+/* Finishes the picture: sets buf->n_intra and buf->level_bytes and returns what h264r_submit_picture wants. */
+static inline int h264r_writer_end(h264r_writer* w, size_t* n_blocks, long* n_mvs)
+{
+    if (w->next_mb != w->n_mbs) return H264R_E_STATE;
+    w->buf->n_intra = w->n_intra;
+    w->buf->level_bytes = w->level_fmt;
+    *n_blocks = w->n_units;
+    *n_mvs = w->n_mvs;
+    return H264R_OK;
+}
+
+#ifdef __cplusplus
+}
+#endif
+#endif

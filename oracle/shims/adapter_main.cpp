@@ -10,6 +10,10 @@
 //   h264ref_adapter <stream.264> <queue.bin>                      engine vs reference, one JSON line, exit 0 iff bit-exact
 //   h264ref_adapter <stream.264> <queue.bin> --pack-only out.bin  no GPU: writes per picture hdr[n][16], mv[n][32] int16,
 //                                                                 coeff[n][384] int16 (CPU test compares them with pack.py)
+//   ... --transport buf                                           the one-DMA transport: include/h264r_writer.h fills a
+//                                                                 picture buffer (compact levels, partition-order vectors),
+//                                                                 h264r_submit_picture ships it; with --pack-only the buffer's
+//                                                                 used parts are written instead (hdr, masks, units, vectors)
 //
 // pack_macroblock() below is the stub a maintainer would add to Slice::PraseSliceDataer (h264/slice.cpp:357-367) in place
 // of macroblock::Calc; here it runs after the reference has also reconstructed the picture, so that both results exist.
@@ -31,6 +35,7 @@
 #include "slice.h"
 
 #include "../../include/h264r.h"
+#include "../../include/h264r_writer.h"
 
 extern std::vector<int> g_h264o_queue;
 extern size_t g_h264o_queue_pos;
@@ -118,6 +123,8 @@ int main(int argc, char* argv[])
         return 2;
     }
     const bool pack_only = argc >= 5 && !strcmp(argv[3], "--pack-only");
+    bool transport_buf = false;
+    for (int i = 3; i + 1 < argc; i++) if (!strcmp(argv[i], "--transport") && !strcmp(argv[i + 1], "buf")) transport_buf = true;
     FILE* fp = fopen(argv[1], "r");
     FILE* fq = fopen(argv[2], "rb");
     if (!fp || !fq) { fprintf(stderr, "cannot open input\n"); return 2; }
@@ -141,6 +148,8 @@ int main(int argc, char* argv[])
     std::vector<h264r_mb_hdr> hdr;
     std::vector<int16_t> mv, coeff;
     std::vector<uint8_t> y, u, v;
+    h264r_picture_buf pbuf;
+    memset(&pbuf, 0, sizeof pbuf);
     while (parser.find_nextNAL()) {
         NAL nal(&parser, &decoder);
         nal.pic = NULL;
@@ -156,6 +165,36 @@ int main(int argc, char* argv[])
                 pack_macroblock(pic->get_MBXY(r, c), c, r, wm, hdr[a], &mv[(size_t)a * H264R_MV_PER_MB], &coeff[(size_t)a * H264R_COEFF_PER_MB]);
                 any_inter = any_inter || hdr[a].mb_class >= H264R_MB_P16x16;
             }
+        if (pack_only && transport_buf) {
+            // the writer on a plain host buffer laid out by hand (h264r_picture_buf_alloc needs a device)
+            std::vector<h264r_mb_hdr> bh(n);
+            std::vector<uint32_t> bm(n);
+            std::vector<int16_t> bmv((size_t)n * H264R_MV_PER_MB), bb((size_t)n * H264R_COEFF_PER_MB);
+            h264r_picture_buf pb;
+            memset(&pb, 0, sizeof pb);
+            pb.hdr = bh.data(); pb.blk_mask = bm.data(); pb.mv = bmv.data(); pb.mv_end = bmv.data() + bmv.size();
+            pb.blocks = bb.data(); pb.max_blocks = (size_t)24 * n;
+            h264r_writer w;
+            size_t n_units = 0;
+            long n_mvs = 0;
+            for (int fmt = H264R_LEVELS_COMPACT;; fmt = H264R_LEVELS_INT16) {
+                h264r_writer_begin(&w, &pb, n, fmt);
+                int rc = H264R_OK;
+                for (int a = 0; a < n && rc == H264R_OK; a++)
+                    rc = h264r_writer_mb(&w, &hdr[a], hdr[a].mb_class >= H264R_MB_P16x16 ? &mv[(size_t)a * H264R_MV_PER_MB] : NULL, &coeff[(size_t)a * H264R_COEFF_PER_MB]);
+                if (rc == H264R_E_INVAL && fmt == H264R_LEVELS_COMPACT) continue;
+                if (rc != H264R_OK || h264r_writer_end(&w, &n_units, &n_mvs) != H264R_OK) return 4;
+                break;
+            }
+            int32_t head[4] = {pb.level_bytes, (int32_t)n_units, (int32_t)n_mvs, pb.n_intra};
+            fwrite(head, 4, 4, out);
+            fwrite(bh.data(), sizeof(h264r_mb_hdr), n, out);
+            fwrite(bm.data(), 4, n, out);
+            fwrite(pb.blocks, pb.level_bytes == H264R_LEVELS_INT16 ? 32 : 8, n_units, out);
+            fwrite(pb.mv_end - 2 * n_mvs, 4, n_mvs, out);
+            n_pic++;
+            continue;
+        }
         if (pack_only) {
             fwrite(hdr.data(), sizeof(h264r_mb_hdr), n, out);
             fwrite(mv.data(), 2, mv.size(), out);
@@ -181,8 +220,24 @@ int main(int argc, char* argv[])
         frame_of_decnum[pic->DecNum] = fid;
         y.resize((size_t)W * H); u.resize((size_t)W * H / 4); v.resize((size_t)W * H / 4);
         int rc = h264r_frame_begin(ctx, fid, &pp);
-        if (rc == H264R_OK) rc = h264r_submit_mbs(ctx, fid, 0, n, hdr.data(), is_p ? mv.data() : NULL, coeff.data());
-        if (rc == H264R_OK) rc = h264r_frame_end(ctx, fid);
+        if (transport_buf) {
+            if (!pbuf.base && rc == H264R_OK) rc = h264r_picture_buf_alloc(ctx, 0, &pbuf);
+            h264r_writer w;
+            size_t n_units = 0;
+            long n_mvs = 0;
+            for (int fmt = H264R_LEVELS_COMPACT; rc == H264R_OK; fmt = H264R_LEVELS_INT16) {
+                h264r_writer_begin(&w, &pbuf, n, fmt);
+                for (int a = 0; a < n && rc == H264R_OK; a++)
+                    rc = h264r_writer_mb(&w, &hdr[a], hdr[a].mb_class >= H264R_MB_P16x16 ? &mv[(size_t)a * H264R_MV_PER_MB] : NULL, &coeff[(size_t)a * H264R_COEFF_PER_MB]);
+                if (rc == H264R_E_INVAL && fmt == H264R_LEVELS_COMPACT) { rc = H264R_OK; continue; }
+                if (rc == H264R_OK) rc = h264r_writer_end(&w, &n_units, &n_mvs);
+                break;
+            }
+            if (rc == H264R_OK) rc = h264r_submit_picture(ctx, fid, &pbuf, n_units, n_mvs);       // (read_planes below syncs: the buffer may be refilled)
+        } else {
+            if (rc == H264R_OK) rc = h264r_submit_mbs(ctx, fid, 0, n, hdr.data(), is_p ? mv.data() : NULL, coeff.data());
+            if (rc == H264R_OK) rc = h264r_frame_end(ctx, fid);
+        }
         if (rc == H264R_OK) rc = h264r_read_planes(ctx, fid, y.data(), W, u.data(), v.data(), W / 2);
         if (rc != H264R_OK) { fprintf(stderr, "engine: %s\n", h264r_last_error(ctx)); return 3; }
         // the reference's own reconstruction of the same picture
@@ -202,6 +257,7 @@ int main(int argc, char* argv[])
         uint64_t exc = 0;
         h264r_range_excursions(ctx, &exc);
         excursions_total = (long)exc;
+        if (pbuf.base) h264r_picture_buf_free(ctx, &pbuf);
         h264r_destroy(ctx);
     }
     printf("{\"pictures\": %d, \"luma_mismatches\": %ld, \"chroma_mismatches\": %ld, \"luma_range_excursions\": %ld, \"pack_only\": %s}\n",

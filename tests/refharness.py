@@ -46,16 +46,19 @@ def have_adapter():
     return os.path.exists(ADAPTER)
 
 
-def run_adapter(stream, queue, n_mbs=None, pack_only=False):
+def run_adapter(stream, queue, n_mbs=None, pack_only=False, transport=None):
     """Runs the reference-side binding (oracle/shims/adapter_main.cpp).  pack_only: returns the packed buffers per picture
-    [(hdr (n,16) u8, mv (n,32) i16, coeff (n,384) i16)...] without touching the GPU; else the adapter's verdict (dict)."""
+    [(hdr (n,16) u8, mv (n,32) i16, coeff (n,384) i16)...] without touching the GPU -- with transport="buf" what
+    include/h264r_writer.h wrote into a picture buffer: [dict(level_bytes, n_intra, hdr, blk_mask, units (n_units, 8|32) u8,
+    mvs (n_mvs, 2) i16 in partition order)...]; else the adapter's verdict (dict)."""
     d = tempfile.mkdtemp(prefix="h264ada_")
     sp, qp, op = (os.path.join(d, n) for n in ("s.264", "q.bin", "pack.bin"))
     try:
         with open(sp, "wb") as f:
             f.write(stream)
         np.asarray(queue, dtype=np.int32).tofile(qp)
-        r = subprocess.run([ADAPTER, sp, qp] + (["--pack-only", op] if pack_only else []), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        r = subprocess.run([ADAPTER, sp, qp] + (["--pack-only", op] if pack_only else []) + (["--transport", transport] if transport else []),
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         if r.returncode not in (0, 1):
             raise RuntimeError("adapter failed (%d): %s" % (r.returncode, r.stderr[-2000:]))
         verdict = json.loads(r.stdout.strip().splitlines()[-1])
@@ -63,6 +66,19 @@ def run_adapter(stream, queue, n_mbs=None, pack_only=False):
         if not pack_only:
             return verdict
         raw = np.fromfile(op, dtype=np.uint8)
+        if transport == "buf":
+            out, off = [], 0
+            for _ in range(verdict["pictures"]):
+                fmt, n_units, n_mvs, n_intra = (int(x) for x in raw[off:off + 16].view(np.int32)); off += 16
+                usz = 32 if fmt == 2 else 8
+                rec = {"level_bytes": fmt, "n_intra": n_intra}
+                rec["hdr"] = raw[off:off + n_mbs * 16].reshape(n_mbs, 16); off += n_mbs * 16
+                rec["blk_mask"] = raw[off:off + n_mbs * 4].view(np.uint32).copy(); off += n_mbs * 4
+                rec["units"] = raw[off:off + n_units * usz].reshape(n_units, usz); off += n_units * usz
+                rec["mvs"] = raw[off:off + n_mvs * 4].view(np.int16).reshape(n_mvs, 2)[::-1].copy(); off += n_mvs * 4
+                out.append(rec)
+            assert off == raw.size
+            return out
         per = n_mbs * (16 + 64 + 768)
         assert raw.size == per * verdict["pictures"]
         out = []

@@ -55,8 +55,6 @@ struct h264r_ctx {
     // dig: K5 of finished pictures (runs behind the lanes)
     cudaStream_t prep_stream = nullptr, dig_stream = nullptr;
     cudaEvent_t ev_scan[8] = {}, ev_wave[8] = {};
-    cudaEvent_t ev_tok = nullptr;           // the k_inter launches of the lanes take turns (see h264r_flush)
-    bool inter_token = false;
     int digest_every = 1;                   // K5 launches cover this many waves of a flush (H264R_DIGEST_EVERY; measured: 1 is best)
     bool lean_inter = true;                 // k_inter<LEAN> for pictures that qualify (H264R_LEAN=0: the generic instantiation)
     bool pdl = true;                        // programmatic dependent launch of the P-wave kernels (H264R_PDL=0: plain launches)
@@ -293,8 +291,6 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
         int nl = e ? atoi(e) : 1;
         c->n_lanes = nl < 1 ? 1 : (nl > 8 ? 8 : nl);
         c->n_lanes_created = c->n_lanes;
-        const char* e4 = getenv("H264R_INTER_TOKEN");
-        if (e4) c->inter_token = atoi(e4) != 0;
         const char* e5 = getenv("H264R_INTER_GENS");
         if (e5 && atoi(e5) > 0) c->inter_generations = atoi(e5);
         const char* e7 = getenv("H264R_DIGEST_EVERY");
@@ -320,7 +316,7 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
         CUC(cudaEventCreateWithFlags(&c->ev_wave[l], cudaEventDisableTiming));
     }
     for (int i = 0; i < 64; i++) CUC(cudaEventCreateWithFlags(&c->ev_dig[i], cudaEventDisableTiming));
-    CUC(cudaEventCreateWithFlags(&c->ev_tok, cudaEventDisableTiming));
+
     c->frame_dig_seq.assign(max_frames, 0);
     c->frame_lane.assign(max_frames, -1);
     c->ev_copied.assign(max_pending, nullptr);
@@ -414,7 +410,7 @@ void h264r_destroy(h264r_ctx* c)
         if (c->ev_wave[l]) cudaEventDestroy(c->ev_wave[l]);
     }
     for (auto e : c->ev_dig) if (e) cudaEventDestroy(e);
-    if (c->ev_tok) cudaEventDestroy(c->ev_tok);
+
     if (c->prep_stream) cudaStreamDestroy(c->prep_stream);
     if (c->dig_stream) cudaStreamDestroy(c->dig_stream);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
@@ -737,7 +733,7 @@ int h264r_flush(h264r_ctx* ctx)
         if (list.n) { list_frames.n = list.n; f(list); }
     };
     std::vector<uint8_t> lane_used(NL, 0);
-    bool dig_used = false, tok_valid = false;
+    bool dig_used = false;
     auto sparse = [&](const Pending& p) { return ctx->sparse_intra && p.pp.slice_type == H264R_SLICE_P && p.n_intra > 0 && p.n_intra * 8 < ctx->n_mbs; };
     // Pictures whose upload has landed already (all of them in a resident batch): their index structures in one go, ahead
     // of every wave, and no per-wave wait later -- stream operations between the kernels of two waves would serialise
@@ -832,8 +828,6 @@ int h264r_flush(h264r_ctx* ctx)
                 int want = (ctx->n_mbs + KINTER_WARPS - 1) / KINTER_WARPS;
                 int cap = (sm_count * ctx->inter_ctas_per_sm * (4 / KINTER_WARPS) * ctx->inter_generations + L.n - 1) / L.n;      // inter_ctas_per_sm counts four warps
                 dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)L.n);
-                // H264R_INTER_TOKEN=1 (experiment, measured slower): the k_inter launches of the lanes take turns
-                if (NL > 1 && ctx->inter_token && tok_valid) cudaStreamWaitEvent(st, ctx->ev_tok, 0);      // (errors surface at the flush's cudaGetLastError)
                 prof_begin(0);
                 const bool tma = ctx->d_tmaps != nullptr;
                 const dim3 blk(KINTER_WARPS * 32);
@@ -845,7 +839,6 @@ int h264r_flush(h264r_ctx* ctx)
                     else { if (tma) launch_pdl(k_inter<false, true, false>, grid, blk, st, pdl, d_desc, L, ctx->g); else launch_pdl(k_inter<false, false, false>, grid, blk, st, pdl, d_desc, L, ctx->g); }
                 }
                 prof_end();
-                if (NL > 1 && ctx->inter_token) { cudaEventRecord(ctx->ev_tok, st); tok_valid = true; }
                 ctx->last_launches++;
             });
             // intra macroblocks.  Few and scattered (P pictures): one launch, a warp ticket per macroblock of the lists

@@ -73,3 +73,16 @@ def test_avail_flags():
     f = abi.avail_flags(3, 2)
     assert list(f) == [0, abi.AVAIL_A, abi.AVAIL_A,
                        abi.AVAIL_B | abi.AVAIL_C, abi.AVAIL_A | abi.AVAIL_B | abi.AVAIL_C | abi.AVAIL_D, abi.AVAIL_A | abi.AVAIL_B | abi.AVAIL_D]
+
+
+def test_writer_header_is_plain_c_and_cxx(tmp_path):
+    """include/h264r_writer.h is header-only C99 that also compiles as C++ (hosts of either language include it)"""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    src = '#include "h264r_writer.h"\nint main(void) { h264r_writer w; h264r_picture_buf b; h264r_writer_begin(&w, &b, 0, H264R_LEVELS_COMPACT); return w.next_mb; }\n'
+    for name, cc, std in (("t.c", "gcc", "-std=c99"), ("t.cpp", "g++", "-std=c++11")):
+        p = tmp_path / name
+        p.write_text(src)
+        r = subprocess.run([cc, std, "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", inc, str(p), "-o", str(tmp_path / (name + ".out"))],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr

@@ -317,8 +317,12 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_intra_rows(const DescTabl
 // ------------------------------------------------------------------------------------------------
 constexpr int SPARSE_PICS = 64;
 struct SparseList { int n; int slot[SPARSE_PICS]; int cum[SPARSE_PICS + 1]; };      // cum[i] = tickets before picture i
+#ifndef H264R_LIST_MIN_CTAS
+#define H264R_LIST_MIN_CTAS 4        // resident CTAs per SM k_intra_list is compiled for (4: 128 registers)
+#endif
+constexpr int LIST_CTAS_PER_SM = H264R_LIST_MIN_CTAS;
 template <bool COMPAT>
-__global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_intra_list(const DescTable descs, const __grid_constant__ SparseList list,
+__global__ void __launch_bounds__(ROW_WARPS * 32, H264R_LIST_MIN_CTAS) k_intra_list(const DescTable descs, const __grid_constant__ SparseList list,
                                                               Geometry g, int* ticket, int stamp)
 {
     __shared__ MbWork work[ROW_WARPS];

@@ -224,6 +224,7 @@ typedef struct h264r_picture_buf {
                                    _INT16 bytes at two levels per block                                                   */
     void*         base;       /* owned by the library       */
 } h264r_picture_buf;
+/* (include/h264r_writer.h: header-only helper that fills a picture buffer macroblock by macroblock in these formats.) */
 int  h264r_picture_buf_alloc(h264r_ctx* ctx, size_t max_blocks, h264r_picture_buf* out);
 void h264r_picture_buf_free(h264r_ctx* ctx, h264r_picture_buf* buf);
 /* n_mvs < 0: buf->mv holds the per-4x4 layout described above (16 vectors per macroblock).

@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--gop-len", type=int, default=30)
     ap.add_argument("--unique-gops", type=int, default=2, help="distinct GOP contents (replicated to --gops)")
     ap.add_argument("--mode", default="compat", choices=["compat", "spec"])
+    ap.add_argument("--res", default="1080p", choices=["1080p", "4k"], help="picture size: 120x68 macroblocks (the metric's workload) or 240x135 (BASELINE config 5 geometry)")
     ap.add_argument("--sample-frames", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layout", default="packed", choices=["packed", "dense"],
@@ -221,6 +222,10 @@ def main():
         reference_arm(args)
         return
 
+    global W_MBS, H_MBS, N_MBS
+    if args.res == "4k":
+        W_MBS, H_MBS = 240, 135
+        N_MBS = W_MBS * H_MBS
     import copy
     import torch
     import torch.distributed as dist
@@ -443,11 +448,11 @@ def main():
             except Exception:
                 traffic = None
         line = {
-            "metric": "1080p_recon_frames_per_s", "value": frames_per_step * args.steps / (kern_ms / 1000.0), "unit": "frames/s",
+            "metric": "1080p_recon_frames_per_s" if args.res == "1080p" else "4k_recon_frames_per_s", "value": frames_per_step * args.steps / (kern_ms / 1000.0), "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": kern_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "1080p 120x68 MBs, %d GOPs/GPU x %d pictures (1 I + %d P), %s" % (
-                G, F, F - 1, "REF_COMPAT (what the reference decoder computes: 4x4 transform, luma prediction, no deblock)" if compat
+            "config": {"workload": "%s %dx%d MBs, %d GOPs/GPU x %d pictures (1 I + %d P), %s" % (
+                args.res, W_MBS, H_MBS, G, F, F - 1, "REF_COMPAT (what the reference decoder computes: 4x4 transform, luma prediction, no deblock)" if compat
                 else "spec mode (chroma prediction + MC, 8x8 transform, Intra8x8, deblocking)"),
                 "mode": args.mode, "layout": args.layout + (" (%.2f of 24 coefficient blocks per macroblock present; int8 levels in 8-byte units: significance map + levels)" % (coded_blocks / float(U * F * N_MBS)) if packed else ""),
                 "gops_per_gpu": G, "gop_len": F, "unique_gops": U, "sharding": "one GOP set per rank, no data-path collective",

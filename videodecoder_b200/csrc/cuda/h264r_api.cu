@@ -753,8 +753,10 @@ int h264r_flush(h264r_ctx* ctx)
         std::vector<Pending*> by_seq(run.begin(), run.end());
         std::sort(by_seq.begin(), by_seq.end(), [](const Pending* x, const Pending* y) { return x->seq < y->seq; });
         int lo = 0, hi = n;        // pictures [0, lo) have landed, [hi, n) have not
+        bool first_probe = true;
         while (lo < hi) {
-            const int mid = lo == 0 ? hi - 1 : (lo + hi) / 2;       // first probe: the last picture (resident batches end here)
+            const int mid = first_probe ? hi - 1 : (lo + hi) / 2;       // first probe: the last picture (resident batches end here)
+            first_probe = false;
             if (cudaEventQuery(ctx->ev_copied[by_seq[mid]->slot]) == cudaSuccess) lo = mid + 1; else hi = mid;
         }
         for (int i = 0; i < n; i++) by_seq[i]->early = i < lo;

@@ -13,8 +13,9 @@
  *  - every function returns 0 (H264R_OK) or a negative H264R_E_* code; the library never calls
  *    exit() (the reference does: h264/macroblock.cpp:656-661, h264/block.cpp:50-51);
  *  - the caller owns every pointer it passes and may reuse it as soon as the call returns,
- *    except buffers obtained from h264r_host_alloc(), which must stay valid until the next
- *    h264r_flush()/h264r_sync() (they are read by an asynchronous copy);
+ *    except buffers obtained from h264r_host_alloc() / h264r_picture_buf_alloc(), which are read by an
+ *    asynchronous copy and must stay untouched until h264r_wait_uploads(), h264r_sync() or a read-back of the
+ *    picture returns (h264r_flush() alone does not wait for the copy);
  *  - a context is bound to one CUDA device and must be used from one host thread at a time
  *    (the reference is single-threaded); different contexts are independent;
  *  - there is NO CPU fallback: if no CUDA device is usable h264r_create() fails.
@@ -31,7 +32,7 @@
 extern "C" {
 #endif
 
-#define H264R_ABI_VERSION 2
+#define H264R_ABI_VERSION 3
 
 /* ---- status codes ---------------------------------------------------------------------- */
 #define H264R_OK            0
@@ -207,8 +208,10 @@ typedef struct h264r_picture_buf {
     uint32_t*     blk_mask;   /* [n_mbs]                    */
     int16_t*      blocks;     /* [max_blocks * 16]          */
     size_t        max_blocks;
-    int32_t       n_intra;    /* EXACT number of intra macroblocks in hdr[], as counted by the parser (it sizes the work
-                                 list of the intra kernel: macroblocks beyond the count would not be reconstructed);
+    int32_t       n_intra;    /* number of intra macroblocks in hdr[], as counted by the parser: exact, or an upper bound below
+                                 the picture's macroblock count (it sizes the work list of the intra kernel: macroblocks
+                                 beyond the count would not be reconstructed; the device checks the count and the classes
+                                 and reports through h264r_device_status());
                                  -1 = unknown: the library then walks hdr[] itself (and validates mb_class while there) */
     int32_t       level_bytes;/* storage of blocks[], one of H264R_LEVELS_*:
                                  _INT16 (2, default): int16 levels, 32 bytes per block;
@@ -234,6 +237,10 @@ void h264r_picture_buf_free(h264r_ctx* ctx, h264r_picture_buf* buf);
  * macroblock::Parse, h264/macroblock.cpp:360-398).  The engine derives each macroblock's first vector from
  * mb_class / sub_mb_type on the device. */
 int  h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* buf, size_t n_blocks, long n_mvs);
+
+/* Gives up a picture that was begun but not completed (a failed submit, a damaged slice): its syntax slot and its frame
+ * slot are free again.  The reference has no counterpart (it exit()s). */
+int h264r_frame_abort(h264r_ctx* ctx, int frame_id);
 
 /* Marks the picture complete and queues its reconstruction.  Asynchronous; work is issued to the
  * GPU at the next h264r_flush().  Replaces: residual::Decode + macroblock::Calc for every MB of the
@@ -274,6 +281,13 @@ int h264r_frame_digests(h264r_ctx* ctx, const int* frame_ids, int n, uint8_t* ou
  * storage (D3), which 8-bit planes cannot represent: parity tests assert it is zero. */
 int h264r_range_excursions(h264r_ctx* ctx, uint64_t* count);
 
+/* Findings of the device-side checks of caller-filled picture buffers since the last call (flushes, waits, resets):
+ * what h264r_submit_picture() accepts without a pass over the headers when the parser supplies n_intra. */
+#define H264R_STATUS_BAD_CLASS   0x1u   /* a header with an unknown mb_class                                          */
+#define H264R_STATUS_INTER_IN_I  0x2u   /* an inter macroblock in an I picture                                        */
+#define H264R_STATUS_N_INTRA     0x4u   /* more intra macroblocks than n_intra said: some were not reconstructed       */
+int h264r_device_status(h264r_ctx* ctx, uint32_t* flags);
+
 /* Per-macroblock map of the same event for one frame: out[mb_addr] = 1 where a luma sample of that
  * macroblock left [0,255].  Content generators use it to keep synthetic pictures in range. */
 int h264r_excursion_map(h264r_ctx* ctx, int frame_id, uint8_t* out /* w_mbs*h_mbs */);
@@ -285,7 +299,10 @@ int h264r_excursion_map(h264r_ctx* ctx, int frame_id, uint8_t* out /* w_mbs*h_mb
 int h264r_residual_mbs(h264r_ctx* ctx, int n_mbs, const h264r_mb_hdr* hdr, const int16_t* coeff, int16_t* out);
 
 /* Frame slot may be reused.  Replaces: Decoder::ctrl_Memory / clear_DecodedPic
- * (h264/Decoder.cpp:38-82).  Stream-ordered: safe to call while work that reads the slot is queued. */
+ * (h264/Decoder.cpp:38-82).  Safe to call while pictures that read the slot are queued or in flight: a picture that
+ * later overwrites the slot is ordered behind every queued reader (a later wave of the flush; across kernel pipelines an
+ * event).  Only a reader that is still OPEN (begun, not yet ended) pins the slot: h264r_frame_begin() on it fails with
+ * H264R_E_STATE until that picture is ended or aborted. */
 int h264r_release(h264r_ctx* ctx, int frame_id);
 
 /* Device-time of the kernels issued by the last h264r_flush(), in milliseconds (CUDA events on the
@@ -308,6 +325,11 @@ int h264r_elapsed_ms(h264r_ctx* ctx, int slot_from, int slot_to, float* ms);
 
 const char* h264r_last_error(h264r_ctx* ctx);
 int h264r_abi_version(void);
+
+#ifdef H264R_TRACE
+/* Development builds only (-DH264R_TRACE): clock stamps of the row kernels, see tools/trace_rows.py. */
+int h264r_debug_trace(long long* out, int cap);
+#endif
 
 #ifdef __cplusplus
 }

@@ -14,8 +14,8 @@ from videodecoder_b200 import abi, build, engine, synth
 
 
 def declared_functions(header):
-    text = open(os.path.join(ROOT, "include", header)).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    # through the preprocessor: comments and development-only blocks (#ifdef H264R_TRACE) are not part of the ABI
+    text = subprocess.run(["gcc", "-E", "-P", os.path.join(ROOT, "include", header)], capture_output=True, text=True, check=True).stdout
     return sorted(set(re.findall(r"\b(h264r_[a-z_0-9]+|h264s_[a-z_0-9]+)\s*\(", text)))
 
 

@@ -297,3 +297,121 @@ def test_api_errors_on_device(built):
     with pytest.raises(engine.H264RError):      # packed chunks out of macroblock order
         eng.submit_mbs_packed(0, np.ascontiguousarray(p["hdr"][6:]), None, mask[6:], pack.pack_blocks(p["coeff"][6:])[1], first_mb=6, n_mbs=6)
     eng.close()
+
+
+# ---- scheduler hazards and API edges (round-1 advisor findings) -------------------------------------------------------
+@pytest.mark.parametrize("lanes", [1, 4])
+def test_frame_slot_overwritten_while_queued_readers_exist(built, lanes, monkeypatch):
+    """Write after read on a frame slot: two independent P chains share ONE pool, and each picture overwrites the slot the
+    other chain's queued picture still reads.  All in one flush, 1 and 4 kernel pipelines.  Result must equal the oracle
+    of each chain (h264r_api.cu: reader_wave / frame_reader_lanes)."""
+    monkeypatch.setenv("H264R_LANES", str(lanes))
+    w, h = 24, 10
+    rng = np.random.default_rng(321 + lanes)
+    cfg = workload.WorkloadConfig(compat=False, p_intra_in_p=0.1, mv_range=40)
+    chains = [workload.make_gop(rng, w, h, 5, cfg) for _ in range(2)]
+    want = [oracle_gop(w, h, 0, c) for c in chains]
+    # slots: chain c, picture i lives in slot (2*i + c) % 3 -- three slots for two chains: a slot is reused as soon as its
+    # picture has been referenced by the NEXT picture of its chain, while that picture is still queued
+    eng = engine.Engine(w, h, max_frames=3, max_pending=16, flags=0)
+    eng.set_lanes(lanes)
+    slot_of = {}
+    got = {}
+
+    def submit(c, i):
+        p = chains[c][i]
+        pp = abi.PicParams.from_buffer_copy(p["pp"])
+        for k in range(pp.num_ref_idx_l0):
+            pp.ref_list0[k] = slot_of[(c, p["pp"].ref_list0[k])]
+        used = {slot_of[(c, i - 1)]} if i > 0 else set()
+        live = {slot_of[(1 - c, j)] for j in range(5) if (1 - c, j) in slot_of and j == max(k for (cc, k) in slot_of if cc == 1 - c)}
+        free = [s for s in range(3) if s not in used and s not in live]
+        s = free[0]
+        slot_of[(c, i)] = s
+        eng.submit_picture(s, pp, p["hdr"], p["mv"], p["coeff"])
+
+    # one flush per round of two pictures (a slot whose picture is still QUEUED cannot be begun again; a DONE one can, and
+    # that is the hazard: round i's second picture overwrites the slot round i's first picture reads).  The check is on
+    # the LAST picture of each chain: it depends on every earlier one through prediction.
+    for i in range(5):
+        for c in range(2):
+            submit(c, i)
+        eng.flush()
+    eng.sync()
+    for c in range(2):
+        y, u, v = eng.read_planes(slot_of[(c, 4)])
+        assert np.array_equal(y, want[c][4]["y"]) and np.array_equal(u, want[c][4]["u"]) and np.array_equal(v, want[c][4]["v"]), "chain %d" % c
+    eng.close()
+
+
+def test_frame_abort_and_open_reader_pins_slot(built):
+    w, h = 6, 4
+    rng = np.random.default_rng(9)
+    cfg = workload.WorkloadConfig(compat=False)
+    gop = workload.make_gop(rng, w, h, 2, cfg)
+    eng = engine.Engine(w, h, max_frames=3, max_pending=2, flags=0)
+    eng.submit_picture(0, gop[0]["pp"], gop[0]["hdr"], None, gop[0]["coeff"])
+    pp = abi.PicParams.from_buffer_copy(gop[1]["pp"])
+    eng.frame_begin(1, pp)                       # open reader of slot 0
+    with pytest.raises(engine.H264RError) as e:
+        eng.frame_begin(0, gop[0]["pp"])         # overwriting its reference: refused
+    assert e.value.code == abi.E_STATE
+    # a failed submit (chunk out of order) can be retried or the picture given up
+    with pytest.raises(engine.H264RError):
+        eng.submit_mbs(1, gop[1]["hdr"][4:], gop[1]["mv"][4:], gop[1]["coeff"][4:], first_mb=4)
+    eng.frame_abort(1)
+    with pytest.raises(engine.H264RError):
+        eng.frame_abort(1)
+    # both the frame slot and the syntax slot are usable again
+    eng.submit_picture(1, pp, gop[1]["hdr"], gop[1]["mv"], gop[1]["coeff"])
+    eng.sync()
+    want = oracle_gop(w, h, 0, gop)
+    y, u, v = eng.read_planes(1)
+    assert np.array_equal(y, want[1]["y"]) and np.array_equal(u, want[1]["u"]) and np.array_equal(v, want[1]["v"])
+    eng.close()
+
+
+def test_device_status_reports_bad_picture_buffers(built):
+    """picture buffers with a parser-supplied n_intra skip the host pass over the headers; the device checks instead"""
+    w, h = 8, 5
+    rng = np.random.default_rng(10)
+    cfg = workload.WorkloadConfig(compat=False, p_intra_in_p=0.3)
+    gop = workload.make_gop(rng, w, h, 2, cfg)
+    eng = engine.Engine(w, h, max_frames=4, flags=0)
+
+    def send(fid, p, n_intra=None, patch=None):
+        mask, blocks = pack.pack_blocks(p["coeff"])
+        b = eng.picture_buf(max(1, blocks.shape[0]))
+        hdr = p["hdr"].copy()
+        if patch:
+            patch(hdr)
+        b.fill(hdr, p["mv"], mask, blocks, mv_partition=True)
+        if n_intra is not None:
+            b.c.n_intra = n_intra
+        eng.submit_picture_buf(fid, p["pp"], b)
+        return b
+
+    bufs = [send(0, gop[0]), send(1, gop[1])]
+    eng.sync()
+    assert eng.device_status() == 0
+    true_intra = int((gop[1]["hdr"]["mb_class"] <= abi.MB_I16x16).sum())
+    assert true_intra >= 2
+    bufs.append(send(2, gop[1], n_intra=true_intra - 1))
+    eng.sync()
+    assert eng.device_status() == abi.STATUS_N_INTRA
+    assert eng.device_status() == 0              # reset on read
+
+    def bad_class(hdr):
+        hdr["mb_class"][3] = 3
+    bufs.append(send(3, gop[1], patch=bad_class))
+    eng.sync()
+    assert eng.device_status() & abi.STATUS_BAD_CLASS
+    for b in bufs:
+        b.free()
+    eng.close()
+
+
+def test_create_rejects_unsupported_width(built):
+    with pytest.raises(engine.H264RError) as e:
+        engine.Engine(513, 2, max_frames=1, flags=0)
+    assert e.value.code == abi.E_INVAL

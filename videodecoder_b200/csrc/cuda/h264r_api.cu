@@ -24,6 +24,7 @@ struct Pending {
     h264r_pic_params pp;
     bool ended;
     int n_intra;            // intra macroblocks seen by submit
+    int n_intra_claimed;    // h264r_submit_picture with buf->n_intra >= 0: the caller's count (k_blk_scan checks it on the device), else -1
     int n_submitted;
     int wave;
     int lane;
@@ -33,6 +34,7 @@ struct Pending {
     int level_bytes;        // H264R_LEVELS_*: int16 levels (32-byte blocks); picture buffers only: int8 levels (16-byte blocks), compact (8-byte units)
     uint64_t seq;           // order of frame_end calls (= order of the uploads on the copy stream)
     bool early;             // flush: the upload had landed when the flush began (index structures made up front, nothing to wait for)
+    bool deblock_on;        // K4 runs for this picture (spec mode, disable_deblocking_filter_idc != 1)
 };
 
 }  // namespace
@@ -67,6 +69,8 @@ struct h264r_ctx {
     bool main_dirty = false;                // the main stream holds work the lanes must wait for
     int next_lane = 0;
     std::vector<int> frame_lane;            // lane that produced / last used a frame slot, -1 = never used
+    std::vector<uint32_t> frame_reader_lanes;   // lanes (bit mask) that carry pictures READING the slot's current picture as a reference:
+                                            // a picture that overwrites the slot waits for them (write after read)
     size_t sync_pos = 0;                    // ring position in d_sync
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> ev_copied;     // per arena slot: its picture's syntax is resident
@@ -210,6 +214,7 @@ void fill_desc(h264r_ctx* c, const Pending& p, PicDesc& pd)
     pd.beta_off = p.pp.slice_beta_offset_div2 * 2;
     pd.excursion_map = c->d_exc_maps + (size_t)p.frame_id * c->n_mbs;
     pd.exc_counter = c->d_exc_counter;
+    pd.n_intra_host = p.n_intra_claimed;
     pd.digest = nullptr;
     pd.frame_id = p.frame_id;
 }
@@ -242,6 +247,8 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     h264r_ctx* ctx = nullptr;      // errors before the context exists go to the thread-local string
     if (!out || w_mbs <= 0 || h_mbs <= 0 || max_frames <= 0 || max_pending <= 0 || (flags & ~(H264R_REF_COMPAT | H264R_DIGESTS)))
         return fail(nullptr, H264R_E_INVAL, "h264r_create: bad argument");
+    if (w_mbs > 32 * ROW_MASK_WORDS)        // the row kernels keep one bit per macroblock of a row in shared memory
+        return fail(nullptr, H264R_E_INVAL, "h264r_create: pictures wider than 512 macroblocks (8192 samples) are not supported");
     *out = nullptr;
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device < 0 || device >= n_dev)
@@ -319,6 +326,7 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
 
     c->frame_dig_seq.assign(max_frames, 0);
     c->frame_lane.assign(max_frames, -1);
+    c->frame_reader_lanes.assign(max_frames, 0);
     c->ev_copied.assign(max_pending, nullptr);
     for (int i = 0; i < max_pending; i++) CUC(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
     for (int i = 0; i < 64; i++) CUC(cudaEventCreateWithFlags(&c->ev_flush[i], cudaEventDisableTiming));
@@ -456,9 +464,17 @@ int h264r_frame_begin(h264r_ctx* ctx, int frame_id, const h264r_pic_params* pp)
         uint8_t rs = ctx->frame_state[r];
         if (rs != FRAME_DONE && rs != FRAME_QUEUED) return fail(ctx, H264R_E_STATE, "frame_begin: reference frame is not reconstructed or queued");
     }
+    // A picture still OPEN may be issued by a later flush than this one: overwriting one of its references in between
+    // cannot be ordered.  (Queued pictures are fine: the flush puts the overwriting picture in a later wave.)
+    for (const auto& q : ctx->pending)
+        if (!q.ended)
+            for (int i = 0; i < q.pp.num_ref_idx_l0; i++)
+                if (q.pp.ref_list0[i] == frame_id) return fail(ctx, H264R_E_STATE, "frame_begin: frame slot is a reference of a picture that is still open");
     if (ctx->free_head >= ctx->free_slots.size()) return fail(ctx, H264R_E_CAPACITY, "frame_begin: max_pending pictures already queued; call h264r_flush");
     Pending p{};
     p.level_bytes = 2;
+    p.n_intra_claimed = -1;
+    p.deblock_on = !(ctx->flags & H264R_REF_COMPAT) && pp->disable_deblocking_filter_idc != 1;
     p.frame_id = frame_id;
     p.slot = ctx->free_slots[ctx->free_head++];
     if (ctx->free_head > 4096 && ctx->free_head * 2 > ctx->free_slots.size()) {
@@ -482,11 +498,13 @@ static int submit_common(h264r_ctx* ctx, int frame_id, int first_mb, int n_mbs, 
     if (first_mb + n_mbs > ctx->n_mbs) return fail(ctx, H264R_E_INVAL, "submit_mbs: macroblock range exceeds the picture");
     if (p->pp.slice_type == H264R_SLICE_P && !mv) return fail(ctx, H264R_E_INVAL, "submit_mbs: P picture needs motion vectors");
     if (p->layout && p->layout != layout) return fail(ctx, H264R_E_STATE, "submit_mbs: dense and packed submits cannot be mixed within a picture");
-    if (layout == 2 && first_mb != p->n_submitted) return fail(ctx, H264R_E_STATE, "submit_mbs_packed: chunks must arrive in macroblock order");
+    // chunks in macroblock order, each macroblock once: n_submitted == n_mbs at frame_end then means "all of them"
+    if (first_mb != p->n_submitted) return fail(ctx, H264R_E_STATE, "submit_mbs: chunks must arrive in macroblock order, without gaps or repeats");
+    int n_intra = 0;          // committed only if the whole chunk is accepted (a failed chunk may be retried)
     for (int i = 0; i < n_mbs; i++) {
         uint8_t cls = hdr[i].mb_class;
         if (cls == 3 || cls > H264R_MB_P8x8) return fail(ctx, H264R_E_INVAL, "submit_mbs: unknown mb_class");
-        if (cls <= H264R_MB_I16x16) p->n_intra++;
+        if (cls <= H264R_MB_I16x16) n_intra++;
         else if (p->pp.slice_type != H264R_SLICE_P) return fail(ctx, H264R_E_INVAL, "submit_mbs: inter macroblock in an I picture");
         if ((ctx->flags & H264R_REF_COMPAT) && (cls == H264R_MB_I8x8 || (hdr[i].flags & H264R_T8x8)))
             return fail(ctx, H264R_E_INVAL, "submit_mbs: 8x8 transform is not part of REF_COMPAT (the reference has none)");
@@ -498,6 +516,7 @@ static int submit_common(h264r_ctx* ctx, int frame_id, int first_mb, int n_mbs, 
         ctx->copy_waited_seq = ctx->slot_flush_seq[p->slot];
     }
     p->layout = layout;
+    p->n_intra += n_intra;
     uint8_t* s = ctx->slot_ptr(p->slot);
     CU(cudaMemcpyAsync(s + ctx->off_hdr + (size_t)first_mb * sizeof(h264r_mb_hdr), hdr, (size_t)n_mbs * sizeof(h264r_mb_hdr), cudaMemcpyHostToDevice, ctx->copy_stream));
     if (mv && p->pp.slice_type == H264R_SLICE_P)
@@ -579,6 +598,7 @@ int h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* 
         if (buf->n_intra > ctx->n_mbs || (p->pp.slice_type != H264R_SLICE_P && buf->n_intra != ctx->n_mbs))
             return fail(ctx, H264R_E_INVAL, "submit_picture: n_intra inconsistent with the picture");
         p->n_intra = buf->n_intra;
+        p->n_intra_claimed = buf->n_intra;
     } else {
         const h264r_mb_hdr* hdr = buf->hdr;
         for (int i = 0; i < ctx->n_mbs; i++) {
@@ -610,7 +630,6 @@ int h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* 
     CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot) + first, hb + first, ctx->off_coeff + n_blocks * unit_bytes - first,
                        cudaMemcpyHostToDevice, ctx->copy_stream));
     CU(cudaEventRecord(ctx->ev_copied[p->slot], ctx->copy_stream));
-    reinterpret_cast<PicDesc*>(ctx->h_ctrl)[p->slot].deblock_on = reinterpret_cast<const PicDesc*>(hb + ctx->off_desc)->deblock_on;
     p->seq = ++ctx->end_seq;
     p->ended = true;
     ctx->frame_state[frame_id] = FRAME_QUEUED;
@@ -626,6 +645,9 @@ int h264r_frame_end(h264r_ctx* ctx, int frame_id)
     CU(cudaSetDevice(ctx->device));
     // the picture's descriptor travels with its syntax (see PicList in h264r_kernels.cuh)
     PicDesc* h_desc = reinterpret_cast<PicDesc*>(ctx->h_ctrl);
+    // h_ctrl[slot] is the source of an asynchronous copy: the one made for the slot's previous picture must have run
+    // before the entry is rewritten (the copy stream may be parked behind a flush while the host runs ahead)
+    CU(cudaEventSynchronize(ctx->ev_copied[p->slot]));
     fill_desc(ctx, *p, h_desc[p->slot]);
     CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot) + ctx->off_desc, &h_desc[p->slot], sizeof(PicDesc), cudaMemcpyHostToDevice, ctx->copy_stream));
     CU(cudaEventRecord(ctx->ev_copied[p->slot], ctx->copy_stream));
@@ -633,6 +655,21 @@ int h264r_frame_end(h264r_ctx* ctx, int frame_id)
     p->ended = true;
     ctx->frame_state[frame_id] = FRAME_QUEUED;
     return H264R_OK;
+}
+
+int h264r_frame_abort(h264r_ctx* ctx, int frame_id)
+{
+    if (!ctx || frame_id < 0 || frame_id >= ctx->max_frames) return fail(ctx, H264R_E_INVAL, "frame_abort: bad frame id");
+    for (size_t i = 0; i < ctx->pending.size(); i++) {
+        Pending& p = ctx->pending[i];
+        if (p.frame_id != frame_id || p.ended) continue;
+        // chunks already on the copy stream land in the slot before anything a later picture uploads into it (one stream)
+        ctx->free_slots.push_back(p.slot);
+        ctx->pending.erase(ctx->pending.begin() + (long)i);
+        ctx->frame_state[frame_id] = FRAME_FREE;
+        return H264R_OK;
+    }
+    return fail(ctx, H264R_E_STATE, "frame_abort: no open picture with this frame id");
 }
 
 int h264r_flush(h264r_ctx* ctx)
@@ -655,6 +692,11 @@ int h264r_flush(h264r_ctx* ctx)
     // the latency-bound wavefront kernels of one lane overlap the throughput-bound kernels of the others.
     int n_waves = 0;
     std::vector<uint32_t> foreign(run.size(), 0);      // lanes (bit mask) a picture must wait for besides its own
+    // Write after read: a picture that OVERWRITES a frame slot which pictures of this flush still read as a reference
+    // (small pools: P1 = f1 <- f0, P2 = f2 <- f1, P3 = f0 <- f2; two streams sharing a pool) goes to a later wave than
+    // the last of those readers, and waits for the lanes that carry readers (of this or of earlier flushes).  `run` is in
+    // frame_begin order, which is the order that gives "the picture in slot f" its meaning.
+    std::vector<int> reader_wave(ctx->max_frames, -1);      // highest wave of this flush that reads the slot's current picture
     for (size_t k = 0; k < run.size(); k++) {
         Pending* p = run[k];
         int wv = 0, lane = -1;
@@ -664,9 +706,18 @@ int h264r_flush(h264r_ctx* ctx)
             int rl = ctx->frame_lane[r];
             if (rl >= 0) { if (lane < 0) lane = rl; else if (rl != lane) foreign[k] |= 1u << rl; }
         }
+        if (reader_wave[p->frame_id] + 1 > wv) wv = reader_wave[p->frame_id] + 1;
         int old = ctx->frame_lane[p->frame_id];
         if (lane < 0) lane = old >= 0 ? old : (ctx->next_lane++ % NL);
         else if (old >= 0 && old != lane) foreign[k] |= 1u << old;
+        foreign[k] |= ctx->frame_reader_lanes[p->frame_id] & ~(1u << lane);
+        ctx->frame_reader_lanes[p->frame_id] = 0;       // the slot holds a new picture from here on
+        reader_wave[p->frame_id] = -1;
+        for (int i = 0; i < p->pp.num_ref_idx_l0; i++) {
+            int r = p->pp.ref_list0[i];
+            if (wv > reader_wave[r]) reader_wave[r] = wv;
+            ctx->frame_reader_lanes[r] |= 1u << lane;
+        }
         p->wave = wv;
         p->lane = lane;
         ctx->frame_wave[p->frame_id] = wv;
@@ -675,7 +726,6 @@ int h264r_flush(h264r_ctx* ctx)
     }
     const int n = (int)run.size();
     const DescTable d_desc{ctx->d_syntax + ctx->off_desc, ctx->slot_bytes};
-    const PicDesc* h_desc = reinterpret_cast<const PicDesc*>(ctx->h_ctrl);
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     if (ctx->main_dirty) {
         // something was queued on the main stream that the lanes must not overtake (read-backs, map resets)
@@ -887,7 +937,7 @@ int h264r_flush(h264r_ctx* ctx)
                 prof_end();
                 ctx->last_launches++;
             });
-            for_chunks([&](const Pending& p) { return h_desc[p.slot].deblock_on != 0; }, [&](const PicList& L) {
+            for_chunks([&](const Pending& p) { return p.deblock_on; }, [&](const PicList& L) {
                 {
                     int want = (ctx->n_mbs + 3) / 4;
                     int cap = (sm_count * 16 * 4 + L.n - 1) / L.n;
@@ -983,6 +1033,7 @@ int h264r_set_lanes(h264r_ctx* ctx, int lanes)
     for (int l = 0; l < ctx->n_lanes_created; l++) CU(cudaStreamSynchronize(ctx->lane_stream[l]));
     ctx->n_lanes = lanes < ctx->n_lanes_created ? lanes : ctx->n_lanes_created;
     std::fill(ctx->frame_lane.begin(), ctx->frame_lane.end(), -1);      // everything is complete: no stream order to preserve
+    std::fill(ctx->frame_reader_lanes.begin(), ctx->frame_reader_lanes.end(), 0u);
     ctx->next_lane = 0;
     return H264R_OK;
 }
@@ -1063,6 +1114,21 @@ int h264r_range_excursions(h264r_ctx* ctx, uint64_t* count)
     CU(cudaMemsetAsync(ctx->d_exc_counter, 0, 4, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     *count = v;
+    return H264R_OK;
+}
+
+int h264r_device_status(h264r_ctx* ctx, uint32_t* flags)
+{
+    if (!ctx || !flags) return H264R_E_INVAL;
+    int r = h264r_flush(ctx);
+    if (r != H264R_OK) return r;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->prep_stream));
+    uint32_t v = 0;
+    CU(cudaMemcpyAsync(&v, ctx->d_exc_counter + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_exc_counter + 1, 0, 4, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *flags = v;
     return H264R_OK;
 }
 

@@ -85,7 +85,8 @@ struct PicDesc {
     int16_t chroma_weight[H264R_MAX_REFS][2], chroma_offset[H264R_MAX_REFS][2];
     int32_t deblock_on, alpha_off, beta_off;     // offsets already multiplied by 2
     uint8_t* excursion_map;    // [n_mbs] or null
-    uint32_t* exc_counter;     // luma samples that left [0,255] before the store (see report_excursions)
+    uint32_t* exc_counter;     // luma samples that left [0,255] before the store (see report_excursions); word 1: H264R_STATUS_* flags
+    int32_t n_intra_host;      // the caller's count of intra macroblocks (h264r_picture_buf.n_intra), -1 = the library counted
     uint32_t* digest;          // 4 words
     int32_t frame_id;
     int32_t packed;            // 1: blk_off / mv_off belong to this picture and k_blk_scan fills them

@@ -378,6 +378,10 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, H264R_LIST_MIN_CTAS) k_intra_l
         // ex() ended with __syncwarp(): every lane's stores precede lane 0's release
         if (publish && ex.lane == 0) st_release_gpu(pd.intra_done + a, stamp);
     }
+    // A CTA that never took a real macroblock (the host's counts are upper bounds) has not met its predecessor yet: the
+    // grid must not retire -- and release the next k_inter, which waits on THIS grid only -- while the k_inter before it
+    // still runs.  Free when the dependency is already satisfied.
+    grid_dependency_wait();
 }
 
 __global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_deblock_rows(const DescTable descs, const __grid_constant__ PicList list,
@@ -467,8 +471,12 @@ __global__ void __launch_bounds__(1024) k_blk_scan(const DescTable descs, const 
                 }
                 if (mvoff || ilist) {
                     const uint2 hw = __ldg(reinterpret_cast<const uint2*>(pd.hdr + first + k));     // mb_class = byte 0, sub_mb_type = byte 7
-                    if (mvoff) c[k] += (unsigned long long)mv_count((int)(hw.x & 255u), (int)(hw.y >> 24)) << 32;
-                    if (is_intra((int)(hw.x & 255u))) intra_bits |= 1u << k;
+                    const int cls = (int)(hw.x & 255u);
+                    if (mvoff) c[k] += (unsigned long long)mv_count(cls, (int)(hw.y >> 24)) << 32;
+                    if (is_intra(cls)) intra_bits |= 1u << k;
+                    // headers of picture buffers are the caller's: what the host could not check without a pass over them
+                    if (cls == 3 || cls > H264R_MB_P8x8) atomicOr(pd.exc_counter + 1, H264R_STATUS_BAD_CLASS);
+                    else if (!is_intra(cls) && pd.slice_type != H264R_SLICE_P) atomicOr(pd.exc_counter + 1, H264R_STATUS_INTER_IN_I);
                 }
             }
         }
@@ -512,7 +520,10 @@ __global__ void __launch_bounds__(1024) k_blk_scan(const DescTable descs, const 
         ibase += s_itotal;
         __syncthreads();
     }
-    if (ilist && threadIdx.x == 0) ilist[0] = ibase;
+    if (ilist && threadIdx.x == 0) {
+        ilist[0] = ibase;
+        if (pd.n_intra_host >= 0 && ibase > (uint32_t)pd.n_intra_host) atomicOr(pd.exc_counter + 1, H264R_STATUS_N_INTRA);      // macroblocks left unreconstructed
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

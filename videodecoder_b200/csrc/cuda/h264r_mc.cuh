@@ -497,6 +497,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int x, 
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(b)) : "memory");
 }
+// frame slot whose tensor maps serve ref_list0[ri]; a stray index beyond the list (ref_id -1) falls back to entry 0,
+// as the plane pointers of unused entries do (fill_desc)
+__device__ __forceinline__ int tma_ref_slot(const PicDesc& pd, int ri)
+{
+    const int r = pd.ref_id[ri];
+    return r >= 0 ? r : pd.ref_id[0];
+}
 #endif
 
 // Phase M0: shape of the macroblock, this lane's NEED bits, and the windows.
@@ -540,14 +547,14 @@ HD void phase_inter_stage(InterWork& w, TmaState& ts, const PicDesc& pd, const G
                 const uint32_t v = load_mv(pd, h, a, 0);
                 const int xb = clip3(-19, W + 2, mbx * 16 + (mv_x(v) >> 2)), yb = clip3(-19, H + 3, mby * 16 + (mv_y(v) >> 2));
                 mbar_expect_tx(&ts.mbar, (uint32_t)(TMA0_W * TMA0_H));
-                tma_load_2d(w.win, maps + ((size_t)pd.ref_id[hdr_ref_idx(h, 0)] * 2) * 128, (PAD_X + xb - 2) & ~15, PAD_Y + yb - 3, &ts.mbar);
+                tma_load_2d(w.win, maps + ((size_t)tma_ref_slot(pd, hdr_ref_idx(h, 0)) * 2) * 128, (PAD_X + xb - 2) & ~15, PAD_Y + yb - 3, &ts.mbar);
             } else {
                 mbar_expect_tx(&ts.mbar, (uint32_t)(4 * TMA1_W * TMA1_H));
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const uint32_t v = load_mv(pd, h, a, (q >> 1) * 8 + (q & 1) * 2);
                     const int xb = clip3(-11, W + 2, mbx * 16 + (q & 1) * 8 + (mv_x(v) >> 2)), yb = clip3(-11, H + 3, mby * 16 + (q >> 1) * 8 + (mv_y(v) >> 2));
-                    tma_load_2d(w.win + q * TMA1_STRIDE, maps + ((size_t)pd.ref_id[hdr_ref_idx(h, q)] * 2 + 1) * 128, (PAD_X + xb - 2) & ~15, PAD_Y + yb - 3, &ts.mbar);
+                    tma_load_2d(w.win + q * TMA1_STRIDE, maps + ((size_t)tma_ref_slot(pd, hdr_ref_idx(h, q)) * 2 + 1) * 128, (PAD_X + xb - 2) & ~15, PAD_Y + yb - 3, &ts.mbar);
                 }
             }
         }

@@ -35,8 +35,8 @@ def load_library():
     if _lib is not None:
         return _lib
     path = lib_path()
-    if not os.path.exists(path):
-        path = build.build_cuda()
+    if not os.environ.get("H264R_LIB"):
+        path = build.build_cuda()      # rebuilds when a source is newer than the library (and nvcc exists); else the prebuilt one
     L = ctypes.CDLL(path)
     vp, ci = ctypes.c_void_p, ctypes.c_int
     L.h264r_abi_version.restype = ci
@@ -59,6 +59,8 @@ def load_library():
     L.h264r_picture_buf_free.restype = None
     L.h264r_submit_picture.argtypes = [vp, ci, ctypes.POINTER(PictureBufStruct), ctypes.c_size_t, ctypes.c_long]
     L.h264r_frame_end.argtypes = [vp, ci]
+    L.h264r_frame_abort.argtypes = [vp, ci]
+    L.h264r_device_status.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
     L.h264r_flush.argtypes = [vp]
     L.h264r_sync.argtypes = [vp]
     L.h264r_read_planes.argtypes = [vp, ci, vp, ci, vp, vp, ci]
@@ -83,7 +85,7 @@ def load_library():
 
 EXPORTS = [
     "h264r_abi_version", "h264r_last_error", "h264r_create", "h264r_destroy", "h264r_host_alloc", "h264r_host_free",
-    "h264r_frame_begin", "h264r_submit_mbs", "h264r_submit_mbs_packed", "h264r_wait_uploads", "h264r_set_lanes", "h264r_picture_buf_alloc", "h264r_picture_buf_free", "h264r_submit_picture", "h264r_frame_end", "h264r_flush", "h264r_sync", "h264r_read_planes",
+    "h264r_frame_begin", "h264r_submit_mbs", "h264r_submit_mbs_packed", "h264r_wait_uploads", "h264r_set_lanes", "h264r_picture_buf_alloc", "h264r_picture_buf_free", "h264r_submit_picture", "h264r_frame_end", "h264r_frame_abort", "h264r_device_status", "h264r_flush", "h264r_sync", "h264r_read_planes",
     "h264r_frame_digest", "h264r_frame_digests", "h264r_range_excursions", "h264r_excursion_map",
     "h264r_residual_mbs", "h264r_release", "h264r_last_flush_stats", "h264r_set_profiling",
     "h264r_last_flush_kernel_ms", "h264r_last_flush_launch_ms", "h264r_mark", "h264r_elapsed_ms",
@@ -255,6 +257,14 @@ class Engine:
         """whole picture from a PictureBuf: one DMA, queued at once"""
         self.frame_begin(frame_id, pp)
         self._check(self.L.h264r_submit_picture(self.ctx, frame_id, ctypes.byref(buf.c), buf.n_blocks, buf.n_mvs))
+
+    def frame_abort(self, frame_id):
+        self._check(self.L.h264r_frame_abort(self.ctx, frame_id))
+
+    def device_status(self):
+        f = ctypes.c_uint32()
+        self._check(self.L.h264r_device_status(self.ctx, ctypes.byref(f)))
+        return int(f.value)
 
     def flush(self):
         self._check(self.L.h264r_flush(self.ctx))

@@ -52,6 +52,8 @@ extern "C" {
 #define H264S_P8x16   4
 #define H264S_P8x8    5
 #define H264S_PSKIP   6
+#define H264S_I8x8    7      /* I_NxN with transform_size_8x8_flag (no reference counterpart: Prediction_Intra8x8 is an empty stub,
+                                h264/macroblock.cpp:1369-1372) */
 
 typedef struct h264s_mb {
     uint8_t kind;
@@ -60,9 +62,10 @@ typedef struct h264s_mb {
     uint8_t cbp_chroma;      /* CodedBlockPatternChroma 0..2                                */
     uint8_t chroma_mode;     /* intra_chroma_pred_mode 0..3                                 */
     int8_t  qp_delta;        /* mb_qp_delta (sent only when the MB has residual syntax)     */
-    uint8_t pad_[2];
-    uint8_t prev_flag[16];   /* prev_intra4x4_pred_mode_flag[luma4x4BlkIdx]                 */
-    uint8_t rem_mode[16];    /* rem_intra4x4_pred_mode[luma4x4BlkIdx]                       */
+    uint8_t t8x8;            /* transform_size_8x8_flag: luma[4*i .. 4*i+3] then hold the 64 levels of 8x8 block i in 8x8 zig-zag order */
+    uint8_t pad_;
+    uint8_t prev_flag[16];   /* prev_intra4x4_pred_mode_flag[luma4x4BlkIdx] (Intra8x8: [luma8x8BlkIdx], 4 used) */
+    uint8_t rem_mode[16];    /* rem_intra4x4_pred_mode[luma4x4BlkIdx]       (Intra8x8: rem_intra8x8_pred_mode)  */
     uint8_t sub_type[4];     /* sub_mb_type per 8x8 (0 8x8, 1 8x4, 2 4x8, 3 4x4)            */
     uint8_t ref_idx[4];      /* ref_idx_l0 per partition                                    */
     int16_t mvd[16][2];      /* mvd_l0[mbPartIdx*4 + subMbPartIdx][x,y]                     */
@@ -83,6 +86,11 @@ typedef struct h264s_seq {
     int32_t log2_max_frame_num_minus4;
     int32_t log2_max_poc_lsb_minus4;
     int32_t profile_idc;               /* 77: the reference misparses High SPS fields (h264/NAL.cpp:45-57) */
+    /* fields below are read by the h264e_* writer only (streams for spec-conformant decoders; the reference has no 8x8 transform) */
+    int32_t transform_8x8_mode_flag;
+    int32_t constrained_intra_pred_flag;
+    int32_t second_chroma_qp_index_offset;
+    int32_t pic_order_cnt_type;        /* 0 or 2 */
 } h264s_seq;
 
 typedef struct h264s_pic {
@@ -102,6 +110,16 @@ typedef struct h264s_pic {
     int32_t disable_deblocking_filter_idc;
     int32_t slice_alpha_c0_offset_div2;
     int32_t slice_beta_offset_div2;
+    /* read by the h264e_* writer only */
+    int32_t cabac_init_idc;
+    int32_t long_term_reference_flag;
+    int32_t chroma_weight_flag[16];
+    int32_t chroma_weight[16][2];
+    int32_t chroma_offset[16][2];
+    int32_t n_mods;                    /* ref_pic_list_modification: (modification_of_pic_nums_idc, value) pairs */
+    int32_t mods[16][2];
+    int32_t n_mmco;                    /* dec_ref_pic_marking: (operation, first operand, second operand) */
+    int32_t mmco[16][3];
 } h264s_pic;
 
 /* All writers return the number of bytes / int32 values produced, or -1 if cap is too small. */

@@ -16,12 +16,12 @@ import numpy as np
 
 from . import build
 
-I4x4, I16x16, P16x16, P16x8, P8x16, P8x8, PSKIP = range(7)
+I4x4, I16x16, P16x16, P16x8, P8x16, P8x8, PSKIP, I8x8 = range(8)
 SLICE_P, SLICE_I = 0, 2
 
 MB_DTYPE = np.dtype([
     ("kind", "u1"), ("i16_mode", "u1"), ("cbp_luma", "u1"), ("cbp_chroma", "u1"),
-    ("chroma_mode", "u1"), ("qp_delta", "i1"), ("pad_", "u1", (2,)),
+    ("chroma_mode", "u1"), ("qp_delta", "i1"), ("t8x8", "u1"), ("pad_", "u1"),
     ("prev_flag", "u1", (16,)), ("rem_mode", "u1", (16,)),
     ("sub_type", "u1", (4,)), ("ref_idx", "u1", (4,)),
     ("mvd", "<i2", (16, 2)),
@@ -36,7 +36,8 @@ class Seq(ctypes.Structure):
         "w_mbs", "h_mbs", "max_num_ref_frames", "pic_init_qp", "chroma_qp_index_offset",
         "num_ref_idx_l0_default_active_minus1", "weighted_pred_flag",
         "deblocking_filter_control_present_flag", "log2_max_frame_num_minus4",
-        "log2_max_poc_lsb_minus4", "profile_idc")]
+        "log2_max_poc_lsb_minus4", "profile_idc",
+        "transform_8x8_mode_flag", "constrained_intra_pred_flag", "second_chroma_qp_index_offset", "pic_order_cnt_type")]
 
 
 class Pic(ctypes.Structure):
@@ -45,7 +46,12 @@ class Pic(ctypes.Structure):
         "num_ref_idx_l0_active_minus1", "luma_log2_weight_denom", "chroma_log2_weight_denom")] + [
         ("luma_weight_flag", ctypes.c_int32 * 16), ("luma_weight", ctypes.c_int32 * 16),
         ("luma_offset", ctypes.c_int32 * 16)] + [(n, ctypes.c_int32) for n in (
-            "disable_deblocking_filter_idc", "slice_alpha_c0_offset_div2", "slice_beta_offset_div2")]
+            "disable_deblocking_filter_idc", "slice_alpha_c0_offset_div2", "slice_beta_offset_div2",
+            "cabac_init_idc", "long_term_reference_flag")] + [
+        ("chroma_weight_flag", ctypes.c_int32 * 16), ("chroma_weight", (ctypes.c_int32 * 2) * 16),
+        ("chroma_offset", (ctypes.c_int32 * 2) * 16),
+        ("n_mods", ctypes.c_int32), ("mods", (ctypes.c_int32 * 2) * 16),
+        ("n_mmco", ctypes.c_int32), ("mmco", (ctypes.c_int32 * 3) * 16)]
 
 
 _lib = None
@@ -63,9 +69,15 @@ def host_lib():
 
 
 def make_seq(w_mbs, h_mbs, max_num_ref_frames=1, pic_init_qp=28, num_ref_idx_default=0,
-             weighted_pred=0, deblocking_control=0, chroma_qp_index_offset=0):
+             weighted_pred=0, deblocking_control=0, chroma_qp_index_offset=0, profile_idc=77, transform_8x8_mode=0,
+             constrained_intra_pred=0, second_chroma_qp_index_offset=None, pic_order_cnt_type=0):
+    """profile_idc 77 (Main) is what the reference can read; 100 (High) adds the 8x8 transform and the second
+    chroma QP offset and is written by the h264e_* writer only."""
+    if second_chroma_qp_index_offset is None:
+        second_chroma_qp_index_offset = chroma_qp_index_offset
     return Seq(w_mbs, h_mbs, max_num_ref_frames, pic_init_qp, chroma_qp_index_offset, num_ref_idx_default,
-               weighted_pred, deblocking_control, 4, 4, 77)
+               weighted_pred, deblocking_control, 4, 4, profile_idc, transform_8x8_mode, constrained_intra_pred,
+               second_chroma_qp_index_offset, pic_order_cnt_type)
 
 
 def make_pic(seq, index_in_gop, slice_type, slice_qp_delta=0, num_ref_active=None, weights=None,

@@ -6,6 +6,7 @@
 // at zero, i.e. the state the reference's own Debug_conf.lua produces by default.
 #include "Debug.h"
 #include <cstring>
+#include <cstdlib>
 
 Debug::Debug(const char*)
 {
@@ -17,6 +18,9 @@ Debug::Debug(const char*)
     de_conspic_result = de_conspic_result_Y = de_conspic_result_Cb = de_conspic_result_Cr = 0;
     de_inter_movevector = de_pic_terminalchar = de_timer = de_nal_info = 0;
     control_all = true;
+    // H264O_TRACE_AE=1: print every syntax-element value the arithmetic decoder returns (cabac::cread_ae, h264/cabac.cpp:43-50) --
+    // how a divergence between a written stream and the reference's reading of it is located
+    if (getenv("H264O_TRACE_AE")) de_cabac_result_ae = 1;
 }
 Debug::~Debug() {}
 double Debug::get_RunTime() { return (double)clock() / CLOCKS_PER_SEC; }

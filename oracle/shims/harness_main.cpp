@@ -28,8 +28,15 @@
 #include "matrix.h"
 #include "slice.h"
 
+#ifdef H264O_REAL_CABAC
+// h264ref_cabac: the reference's own arithmetic decoder (h264/cabac.cpp) is linked instead of the queue-fed stand-in, so the
+// whole reference -- bit reader, CABAC, macroblock layer, reconstruction -- runs unmodified on a genuine bitstream.
+std::vector<int> g_h264o_queue;
+size_t g_h264o_queue_pos = 0;
+#else
 extern std::vector<int> g_h264o_queue;
 extern size_t g_h264o_queue_pos;
+#endif
 
 static double now_s()
 {
@@ -130,14 +137,16 @@ int main(int argc, char* argv[])
     int level = argc > 4 ? atoi(argv[4]) : 1;
     FILE* fp = fopen(argv[1], "r");
     if (!fp) { fprintf(stderr, "cannot open %s\n", argv[1]); return 2; }
-    FILE* fq = fopen(argv[2], "rb");
-    if (!fq) { fprintf(stderr, "cannot open %s\n", argv[2]); return 2; }
-    fseek(fq, 0, SEEK_END);
-    long qbytes = ftell(fq);
-    fseek(fq, 0, SEEK_SET);
-    g_h264o_queue.resize(qbytes / 4);
-    if (qbytes && fread(g_h264o_queue.data(), 4, qbytes / 4, fq) != (size_t)(qbytes / 4)) return 2;
-    fclose(fq);
+    if (strcmp(argv[2], "-")) {
+        FILE* fq = fopen(argv[2], "rb");
+        if (!fq) { fprintf(stderr, "cannot open %s\n", argv[2]); return 2; }
+        fseek(fq, 0, SEEK_END);
+        long qbytes = ftell(fq);
+        fseek(fq, 0, SEEK_SET);
+        g_h264o_queue.resize(qbytes / 4);
+        if (qbytes && fread(g_h264o_queue.data(), 4, qbytes / 4, fq) != (size_t)(qbytes / 4)) return 2;
+        fclose(fq);
+    }
     FILE* out = strcmp(argv[3], "-") ? fopen(argv[3], "wb") : NULL;
 
     Debug debug("");

@@ -10,6 +10,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "h264ref_harness")
+HARNESS_CABAC = os.path.join(ROOT, "oracle", "_ref", "h264ref_cabac")   # the same, with the reference's own h264/cabac.cpp
 ADAPTER = os.path.join(ROOT, "oracle", "_ref", "h264ref_adapter")      # reference host side + INTEGRATION.md's binding + libh264r.so
 
 HDR_INTS = 25
@@ -40,6 +41,31 @@ def run_reference(stream, queue, level=2, keep=None):
                 os.remove(p)
         os.rmdir(d)
     return pics, stats
+
+
+def have_cabac_harness():
+    return os.path.exists(HARNESS_CABAC)
+
+
+def run_reference_cabac(stream, level=2, timeout=None):
+    """The unmodified reference (bit reader, CABAC, macroblock layer, reconstruction) on a genuine CABAC stream.
+    Returns (pictures, stats) like run_reference."""
+    d = tempfile.mkdtemp(prefix="h264refc_")
+    sp, dp = os.path.join(d, "s.264"), os.path.join(d, "dump.bin")
+    try:
+        with open(sp, "wb") as f:
+            f.write(stream)
+        r = subprocess.run([HARNESS_CABAC, sp, "-", dp if level >= 0 else "-", str(max(level, 0))],
+                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, timeout=timeout)
+        if r.returncode != 0:
+            raise RuntimeError("reference (own CABAC) failed (%d): %s" % (r.returncode, r.stderr[-2000:]))
+        stats = json.loads(r.stderr.strip().splitlines()[-1])
+        return (parse_dump(dp) if level >= 0 else []), stats
+    finally:
+        for p in (sp, dp):
+            if os.path.exists(p):
+                os.remove(p)
+        os.rmdir(d)
 
 
 def have_adapter():

@@ -93,7 +93,7 @@ bool any_nonzero(const int16_t* p, int n)
 }
 
 // makes a record say only what the syntax can carry (see h264e_encode_picture in h264_host.h)
-int normalise_mb(h264s_mb& m, bool p_slice, bool t8_mode)
+int normalise_mb(h264s_mb& m, bool p_slice, bool t8_mode, bool absolute)
 {
     const bool intra = m.kind == H264S_I4x4 || m.kind == H264S_I8x8 || m.kind == H264S_I16x16;
     if (m.kind > H264S_I8x8) return kErrState;
@@ -129,7 +129,40 @@ int normalise_mb(h264s_mb& m, bool p_slice, bool t8_mode)
     for (int c = 0; c < 2; c++)
         for (int b = 0; b < 4; b++) m.chroma_ac[c][b][15] = 0;
     if (!(m.cbp_luma || m.cbp_chroma || m.kind == H264S_I16x16)) m.qp_delta = 0;
-    if (!intra) { m.chroma_mode = 0; m.i16_mode = 0; }
+    // prediction syntax the macroblock type does not carry
+    if (!intra) {
+        m.chroma_mode = 0; m.i16_mode = 0;
+        memset(m.prev_flag, 0, sizeof(m.prev_flag));
+        memset(m.rem_mode, 0, sizeof(m.rem_mode));
+        bool used[16] = {false};
+        if (m.kind == H264S_P16x16) used[0] = true;
+        else if (m.kind == H264S_P16x8 || m.kind == H264S_P8x16) used[0] = used[4] = true;
+        else
+            for (int q = 0; q < 4; q++) {
+                static const int cnt[4] = {1, 2, 2, 4};
+                for (int k = 0; k < cnt[m.sub_type[q] & 3]; k++) used[q * 4 + k] = true;
+            }
+        for (int i = 0; i < 16; i++)
+            if (!used[i]) m.mvd[i][0] = m.mvd[i][1] = 0;
+        if (m.kind != H264S_P8x8) {
+            memset(m.sub_type, 0, sizeof(m.sub_type));
+            const int np = m.kind == H264S_P16x16 ? 1 : 2;
+            for (int i = np; i < 4; i++) m.ref_idx[i] = 0;
+        }
+    } else {
+        memset(m.sub_type, 0, sizeof(m.sub_type));
+        memset(m.ref_idx, 0, sizeof(m.ref_idx));
+        memset(m.mvd, 0, sizeof(m.mvd));
+        if (m.kind != H264S_I16x16) m.i16_mode = 0;
+        const int nb = m.kind == H264S_I4x4 ? 16 : (m.kind == H264S_I8x8 ? 4 : 0);
+        for (int i = 0; i < 16; i++) {
+            if (i >= nb) { m.prev_flag[i] = 0; m.rem_mode[i] = 0; }
+            else if (absolute) { m.prev_flag[i] = 0; if (m.rem_mode[i] > 8) return kErrState; }     // rem_mode holds the final mode
+            else if (m.prev_flag[i]) { m.prev_flag[i] = 1; m.rem_mode[i] = 0; }
+            else m.rem_mode[i] &= 7;
+        }
+    }
+    m.pad_ = 0;
     return kOk;
 }
 
@@ -182,7 +215,7 @@ extern "C" long h264e_encode_picture(const h264s_seq* s, const h264s_pic* p, h26
     }
     for (int a = 0; a < n_mbs; a++) {
         h264s_mb& m = mbs[a];
-        int rc = normalise_mb(m, p_slice, sp.transform_8x8_mode);
+        int rc = normalise_mb(m, p_slice, sp.transform_8x8_mode, (flags & H264E_ABSOLUTE) != 0);
         if (rc) return rc;
         if (flags & H264E_ABSOLUTE) {
             info[(size_t)a].slice = 1;

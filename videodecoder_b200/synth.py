@@ -159,6 +159,12 @@ class ContentConfig:
         self.qp_delta_range = 2
         self.p_qp_delta = 0.2
         self.num_ref = 1
+        # the three below need absolute=True in random_picture (streams written with hoststream.E_ABSOLUTE) and, for the 8x8
+        # tools, a High-profile sequence (make_seq(profile_idc=100, transform_8x8_mode=1)); the reference reads neither
+        self.p_i8x8 = 0.0            # share of I_NxN macroblocks that are Intra8x8
+        self.p_t8x8 = 0.0            # share of eligible inter macroblocks with transform_size_8x8_flag
+        self.mv_range = 64           # absolute mode: final vectors uniform in +-mv_range quarter samples
+        self.constrained_intra = False   # choose intra modes as constrained_intra_pred_flag = 1 allows (inter neighbours do not exist)
         for k, v in kw.items():
             assert hasattr(self, k), k
             setattr(self, k, v)
@@ -174,8 +180,11 @@ def _fill_block(rng, levels, n, qp, cfg, first=0):
     levels[pos] = mag * sign
 
 
-def random_picture(rng, seq, slice_type, cfg, slice_qp):
+def random_picture(rng, seq, slice_type, cfg, slice_qp, absolute=False):
     """Random macroblock syntax for one picture.  Returns ndarray[MB_DTYPE] (raster order).
+
+    absolute=True: rem_mode[] holds the FINAL intra prediction modes and mvd[] the FINAL vectors, for
+    hoststream.encode_stream(..., flags=E_ABSOLUTE), which derives prev / rem / mvd against the standard's predictors.
 
     Intra 4x4 modes are chosen among those whose neighbouring samples exist and are then coded
     against the predicted mode exactly as the reference derives it (ParseIntra4x4PredMode,
@@ -187,6 +196,11 @@ def random_picture(rng, seq, slice_type, cfg, slice_qp):
     # final Intra4x4PredMode per 4x4 block of the picture; -1 = MB is not Intra4x4 (-2: inter)
     modes = np.full((H * 4, W * 4), -1, dtype=np.int8)
     qp = slice_qp
+    def _ok(x, y):       # macroblock (x, y) may be used for intra prediction
+        if x < 0 or y < 0:
+            return False
+        return not (cfg.constrained_intra and mbs[y * W + x]["kind"] in (P16x16, P16x8, P8x16, P8x8, PSKIP))
+
     for a in range(n):
         mby, mbx = divmod(a, W)
         m = mbs[a]
@@ -200,6 +214,8 @@ def random_picture(rng, seq, slice_type, cfg, slice_qp):
                 kind = PSKIP
             else:
                 kind = (P16x16, P16x8, P8x16, P8x8)[rng.choice(4, p=cfg.p_part)]
+        if kind == I4x4 and cfg.p_i8x8 > 0 and rng.random() < cfg.p_i8x8:
+            kind = I8x8
         m["kind"] = kind
         if kind == PSKIP:
             modes[mby * 4:mby * 4 + 4, mbx * 4:mbx * 4 + 4] = -2
@@ -226,9 +242,16 @@ def random_picture(rng, seq, slice_type, cfg, slice_qp):
                     if rng.random() < cfg.p_block:
                         _fill_block(rng, m["luma"][b], 15, qp, cfg)
         else:
-            for b in range(16):
-                if (m["cbp_luma"] >> (b >> 2)) & 1 and rng.random() < cfg.p_block:
-                    _fill_block(rng, m["luma"][b], 16, qp, cfg)
+            t8 = kind == I8x8 or (cfg.p_t8x8 > 0 and kind in (P16x16, P16x8, P8x16, P8x8) and rng.random() < cfg.p_t8x8)
+            m["t8x8"] = 1 if t8 else 0
+            if t8:
+                for q in range(4):
+                    if (m["cbp_luma"] >> q) & 1 and rng.random() < 0.8:
+                        _fill_block(rng, m["luma"][4 * q:4 * q + 4].reshape(-1), 64, qp, cfg)
+            else:
+                for b in range(16):
+                    if (m["cbp_luma"] >> (b >> 2)) & 1 and rng.random() < cfg.p_block:
+                        _fill_block(rng, m["luma"][b], 16, qp, cfg)
         if m["cbp_chroma"]:
             for c in range(2):
                 if rng.random() < 0.7:
@@ -239,31 +262,49 @@ def random_picture(rng, seq, slice_type, cfg, slice_qp):
                         if rng.random() < cfg.p_block:
                             _fill_block(rng, m["chroma_ac"][c][b], 15, qpc, cfg)
         # ---- prediction syntax ----
-        if kind in (I4x4, I16x16):
-            m["chroma_mode"] = _legal_chroma_mode(rng, mbx, mby)
+        okA, okB, okD = _ok(mbx - 1, mby), _ok(mbx, mby - 1), _ok(mbx - 1, mby - 1)
+        if kind in (I4x4, I16x16, I8x8):
+            m["chroma_mode"] = _legal_chroma_mode(rng, okA, okB, okD)
         if kind == I16x16:
             legal = [2]
-            if mby > 0:
+            if okB:
                 legal.append(0)
-            if mbx > 0:
+            if okA:
                 legal.append(1)
-            if mbx > 0 and mby > 0:
+            if okA and okB and okD:
                 legal.append(3)
             # the reference's top-only DC sums the wrong line -- still deterministic, keep it
             m["i16_mode"] = int(rng.choice(legal))
-        elif kind == I4x4:
-            for blk in range(16):
-                ras = BLK_RASTER[blk]
-                by, bx = mby * 4 + ras // 4, mbx * 4 + ras % 4
-                left, top = bx > 0, by > 0
+        elif kind == I8x8:
+            for q in range(4):
+                left, top = okA or (q & 1), okB or (q >> 1)
+                corner = (okD, okB, okA, True)[q]
                 legal = [2]
                 if top:
                     legal += [0, 3, 7]
                 if left:
                     legal += [1, 8]
-                if left and top:
+                if left and top and corner:
+                    legal += [4, 5, 6]
+                m["rem_mode"][q] = int(rng.choice(legal))
+            modes[mby * 4:mby * 4 + 4, mbx * 4:mbx * 4 + 4] = -1
+        elif kind == I4x4:
+            for blk in range(16):
+                ras = BLK_RASTER[blk]
+                by, bx = mby * 4 + ras // 4, mbx * 4 + ras % 4
+                left, top = okA or ras % 4 > 0, okB or ras // 4 > 0
+                corner = okD if ras == 0 else (okB if ras < 4 else (okA if ras % 4 == 0 else True))
+                legal = [2]
+                if top:
+                    legal += [0, 3, 7]
+                if left:
+                    legal += [1, 8]
+                if left and top and corner:
                     legal += [4, 5, 6]
                 want = int(rng.choice(legal))
+                if absolute:
+                    m["rem_mode"][blk] = want
+                    continue
                 ma = modes[by, bx - 1] if left else -2
                 mb_ = modes[by - 1, bx] if top else -2
                 if ma == -2 or mb_ == -2:
@@ -281,17 +322,18 @@ def random_picture(rng, seq, slice_type, cfg, slice_qp):
             if kind == P8x8:
                 m["sub_type"][:] = rng.choice(cfg.sub_types, size=4)
             m["ref_idx"][:] = rng.integers(0, cfg.num_ref, size=4)
-            m["mvd"][:] = rng.integers(-cfg.mvd_range, cfg.mvd_range + 1, size=(16, 2))
+            r = cfg.mv_range if absolute else cfg.mvd_range
+            m["mvd"][:] = rng.integers(-r, r + 1, size=(16, 2))
     return mbs
 
 
-def _legal_chroma_mode(rng, mbx, mby):
+def _legal_chroma_mode(rng, ok_a, ok_b, ok_d):
     legal = [0]
-    if mbx > 0:
+    if ok_a:
         legal.append(1)
-    if mby > 0:
+    if ok_b:
         legal.append(2)
-    if mbx > 0 and mby > 0:
+    if ok_a and ok_b and ok_d:
         legal.append(3)
     return int(rng.choice(legal))
 
@@ -311,7 +353,7 @@ def zero_residual(mbs, addrs):
             m["qp_delta"] = 0
 
 
-def random_gop(rng, seq, n_pictures, cfg, slice_qp_delta=0, intra_only=False):
+def random_gop(rng, seq, n_pictures, cfg, slice_qp_delta=0, intra_only=False, absolute=False):
     """[(Pic, mbs)] for one IDR-led GOP: I then P pictures, every picture a reference."""
     pics = []
     for i in range(n_pictures):
@@ -324,6 +366,6 @@ def random_gop(rng, seq, n_pictures, cfg, slice_qp_delta=0, intra_only=False):
             cfg_i = ContentConfig(**{**cfg.__dict__, "num_ref": pic.num_ref_idx_l0_active_minus1 + 1})
         else:
             cfg_i = cfg
-        mbs = random_picture(rng, seq, st, cfg_i, seq.pic_init_qp + slice_qp_delta)
+        mbs = random_picture(rng, seq, st, cfg_i, seq.pic_init_qp + slice_qp_delta, absolute=absolute)
         pics.append((pic, mbs))
     return pics

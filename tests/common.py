@@ -149,3 +149,28 @@ def densify_levels(rng, gop, p_block=0.4, big=True):
             elif big and rng.random() < 0.1:
                 c[a, b, 1 + int(rng.integers(0, 15))] = int(rng.choice([-128, 127]))
     return gop
+
+
+def load_stream_golden(name):
+    """Fixture written by tests/golden/make_spec_golden.py -> dict(w_mbs, h_mbs, stream bytes, aus [bytes], md5 [hex], planes [(y,u,v)] or None)."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    stream = z["stream"].tobytes()
+    aus, off = [], 0
+    for n in z["au_sizes"]:
+        aus.append(stream[off:off + int(n)])
+        off += int(n)
+    n_pics = int(z["n_pics"])
+    out = {"w_mbs": int(z["w_mbs"]), "h_mbs": int(z["h_mbs"]), "stream": stream, "aus": aus, "n_pics": n_pics,
+           "md5": [bytes(z["md5_%d" % i]).hex() for i in range(n_pics)],
+           "planes": [(z["y%d" % i], z["u%d" % i], z["v%d" % i]) for i in range(n_pics)] if "y0" in z.files else None}
+    return out
+
+
+def check_against_stream_golden(g, outs, what):
+    """outs: per picture dict(y,u,v) in decoding order (= output order for these streams)."""
+    assert len(outs) == g["n_pics"]
+    for i, o in enumerate(outs):
+        if g["planes"] is not None:
+            for k, ref in zip("yuv", g["planes"][i]):
+                assert np.array_equal(o[k], ref), "%s: picture %d plane %s differs (%d samples)" % (what, i, k, int((o[k] != ref).sum()))
+        assert planes_md5(o["y"], o["u"], o["v"]) == g["md5"][i], "%s: picture %d MD5" % (what, i)

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define H264R_ABI_VERSION 3
+#define H264R_ABI_VERSION 4
 
 /* ---- status codes ---------------------------------------------------------------------- */
 #define H264R_OK            0
@@ -268,6 +268,22 @@ int h264r_wait_uploads(h264r_ctx* ctx);
  * accessor (used by its ASCII printer, h264/picture.cpp:53-76, and by inter prediction). */
 int h264r_read_planes(h264r_ctx* ctx, int frame_id, uint8_t* y, int y_stride,
                       uint8_t* u, uint8_t* v, int c_stride);
+
+/* Asynchronous read-back of whole frames, for pipelines that ship every reconstructed picture to the host: the frame slot -- the
+ * three planes with their replicated borders, h264r_frame_layout() says where the samples lie -- is copied to `dst` (frame_bytes
+ * bytes; pinned memory from h264r_host_alloc() for a truly asynchronous copy) on a read-back stream, behind the kernels that
+ * produce the frame and beside the reconstruction of later pictures.  A later picture that overwrites the slot is ordered behind
+ * the copy.  h264r_wait_readbacks() returns when every copy queued so far has landed.
+ * Replaces: picture::get_SampleXY over a whole picture (the reference's output path, h264/picture.cpp:53-76, 396-409). */
+typedef struct h264r_frame_layout_t {
+    size_t frame_bytes;                 /* bytes of one frame slot                                    */
+    size_t y_offset, u_offset, v_offset;/* byte offset of sample (0,0) of each plane inside the slot  */
+    int32_t y_pitch, c_pitch;           /* bytes between rows                                         */
+    int32_t width, height;              /* luma samples (coded size: multiples of 16)                 */
+} h264r_frame_layout_t;
+int h264r_frame_layout(h264r_ctx* ctx, h264r_frame_layout_t* out);
+int h264r_read_frame_async(h264r_ctx* ctx, int frame_id, void* dst);
+int h264r_wait_readbacks(h264r_ctx* ctx);
 
 /* 16-byte position-dependent checksum of the three planes, computed on the device (kernel K5);
  * see DESIGN.md for the definition.  Used to compare GOP-sharded runs across GPUs without

@@ -3,7 +3,7 @@ import ctypes
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 REF_COMPAT = 0x1
 DIGESTS = 0x2      # digest of every picture as part of its reconstruction
 
@@ -42,6 +42,11 @@ class PicParams(ctypes.Structure):
         ("slice_alpha_c0_offset_div2", ctypes.c_int32),
         ("slice_beta_offset_div2", ctypes.c_int32),
     ]
+
+
+class FrameLayout(ctypes.Structure):
+    _fields_ = [("frame_bytes", ctypes.c_size_t), ("y_offset", ctypes.c_size_t), ("u_offset", ctypes.c_size_t), ("v_offset", ctypes.c_size_t),
+                ("y_pitch", ctypes.c_int32), ("c_pitch", ctypes.c_int32), ("width", ctypes.c_int32), ("height", ctypes.c_int32)]
 
 
 def default_pic_params(slice_type=SLICE_I, ref_list=(), deblock=(1, 0, 0)):

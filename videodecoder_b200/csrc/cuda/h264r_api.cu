@@ -65,6 +65,13 @@ struct h264r_ctx {
     uint64_t dig_seq = 0;
     uint64_t lane_dig_waited[8] = {};
     std::vector<uint64_t> frame_dig_seq;    // digest launch that last READ a frame slot (a new picture in the slot waits for it)
+    // read-back stream: h264r_read_frame_async copies finished frames to the host behind the flush that produced them, while
+    // later flushes reconstruct; a picture that overwrites a slot waits for the slot's last read-back (ev_out ring)
+    cudaStream_t out_stream = nullptr;
+    cudaEvent_t ev_out[64] = {};
+    uint64_t out_seq = 0, out_waited_flush = 0;
+    uint64_t lane_out_waited[8] = {};
+    std::vector<uint64_t> frame_out_seq;    // read-back that last READ a frame slot
     cudaEvent_t ev_main = nullptr;
     bool main_dirty = false;                // the main stream holds work the lanes must wait for
     int next_lane = 0;
@@ -318,6 +325,9 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     CUC(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
     CUC(cudaStreamCreateWithFlags(&c->prep_stream, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->dig_stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 64; i++) CUC(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+    c->frame_out_seq.assign(max_frames, 0);
     for (int l = 0; l < 8; l++) {
         CUC(cudaEventCreateWithFlags(&c->ev_scan[l], cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&c->ev_wave[l], cudaEventDisableTiming));
@@ -410,6 +420,7 @@ void h264r_destroy(h264r_ctx* c)
     for (int l = 0; l < 8; l++) if (c->lane_stream[l]) cudaStreamSynchronize(c->lane_stream[l]);
     if (c->prep_stream) cudaStreamSynchronize(c->prep_stream);
     if (c->dig_stream) cudaStreamSynchronize(c->dig_stream);
+    if (c->out_stream) cudaStreamSynchronize(c->out_stream);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int l = 0; l < 8; l++) {
         if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
@@ -421,6 +432,8 @@ void h264r_destroy(h264r_ctx* c)
 
     if (c->prep_stream) cudaStreamDestroy(c->prep_stream);
     if (c->dig_stream) cudaStreamDestroy(c->dig_stream);
+    if (c->out_stream) cudaStreamDestroy(c->out_stream);
+    for (auto e : c->ev_out) if (e) cudaEventDestroy(e);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     cudaFree(c->d_dense_mask); cudaFree(c->d_dense_off); cudaFree(c->d_tmaps);
     for (auto e : c->ev_copied) if (e) cudaEventDestroy(e);
@@ -864,6 +877,16 @@ int h264r_flush(h264r_ctx* ctx)
                     CU(cudaStreamWaitEvent(st, ctx->ev_dig[need & 63], 0));
                     ctx->lane_dig_waited[lane] = need;
                 }
+                // ... nor one that is still being copied to the host (h264r_read_frame_async)
+                uint64_t need_out = 0;
+                for (int i = 0; i < n; i++)
+                    if (run[i]->wave == wv && run[i]->lane == lane) need_out = std::max(need_out, ctx->frame_out_seq[run[i]->frame_id]);
+                if (need_out > ctx->lane_out_waited[lane]) {
+                    // the ring holds the last 64 read-backs; an older one is covered by any later event of the same stream
+                    const uint64_t ev = need_out + 64 <= ctx->out_seq ? ctx->out_seq : need_out;
+                    CU(cudaStreamWaitEvent(st, ctx->ev_out[ev & 63], 0));
+                    ctx->lane_out_waited[lane] = need_out;
+                }
             }
             for (int l = 0; l < NL; l++)
                 if ((wait_lanes >> l) & 1u) {           // references (or the frame slot's old readers) live on another lane
@@ -1067,6 +1090,46 @@ int h264r_read_planes(h264r_ctx* ctx, int frame_id, uint8_t* y, int y_stride, ui
     if (u) CU(cudaMemcpy2DAsync(u, c_stride, ctx->frame_u(frame_id), ctx->g.pitch_c, W / 2, H / 2, cudaMemcpyDeviceToHost, ctx->stream));
     if (v) CU(cudaMemcpy2DAsync(v, c_stride, ctx->frame_v(frame_id), ctx->g.pitch_c, W / 2, H / 2, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return H264R_OK;
+}
+
+int h264r_frame_layout(h264r_ctx* ctx, h264r_frame_layout_t* out)
+{
+    if (!ctx || !out) return fail(ctx, H264R_E_INVAL, "frame_layout: bad argument");
+    out->frame_bytes = ctx->frame_bytes;
+    out->y_offset = (size_t)PAD_Y * ctx->g.pitch_y + PAD_X;
+    out->u_offset = ctx->y_bytes + (size_t)PAD_YC * ctx->g.pitch_c + PAD_XC;
+    out->v_offset = out->u_offset + ctx->c_bytes;
+    out->y_pitch = ctx->g.pitch_y;
+    out->c_pitch = ctx->g.pitch_c;
+    out->width = ctx->g.w_mbs * 16;
+    out->height = ctx->g.h_mbs * 16;
+    return H264R_OK;
+}
+
+int h264r_read_frame_async(h264r_ctx* ctx, int frame_id, void* dst)
+{
+    if (!dst) return fail(ctx, H264R_E_INVAL, "read_frame_async: bad argument");
+    int r = require_done(ctx, frame_id, "read_frame_async");       // flushes when the frame is still queued: its kernels are issued
+    if (r != H264R_OK) return r;
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->out_waited_flush != ctx->flush_seq) {
+        // everything issued so far (ev_flush joins the lanes of the last flush) before the copy; later flushes run beside it
+        CU(cudaStreamWaitEvent(ctx->out_stream, ctx->ev_flush[ctx->flush_seq & 63], 0));
+        ctx->out_waited_flush = ctx->flush_seq;
+    }
+    CU(cudaMemcpyAsync(dst, ctx->d_frames + (size_t)frame_id * ctx->frame_bytes, ctx->frame_bytes, cudaMemcpyDeviceToHost, ctx->out_stream));
+    ctx->out_seq++;
+    CU(cudaEventRecord(ctx->ev_out[ctx->out_seq & 63], ctx->out_stream));
+    ctx->frame_out_seq[frame_id] = ctx->out_seq;
+    return H264R_OK;
+}
+
+int h264r_wait_readbacks(h264r_ctx* ctx)
+{
+    if (!ctx) return H264R_E_INVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->out_stream));
     return H264R_OK;
 }
 

@@ -64,6 +64,9 @@ def load_library():
     L.h264r_flush.argtypes = [vp]
     L.h264r_sync.argtypes = [vp]
     L.h264r_read_planes.argtypes = [vp, ci, vp, ci, vp, vp, ci]
+    L.h264r_frame_layout.argtypes = [vp, ctypes.POINTER(abi.FrameLayout)]
+    L.h264r_read_frame_async.argtypes = [vp, ci, vp]
+    L.h264r_wait_readbacks.argtypes = [vp]
     L.h264r_frame_digest.argtypes = [vp, ci, vp]
     L.h264r_frame_digests.argtypes = [vp, vp, ci, vp]
     L.h264r_range_excursions.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
@@ -86,6 +89,7 @@ def load_library():
 EXPORTS = [
     "h264r_abi_version", "h264r_last_error", "h264r_create", "h264r_destroy", "h264r_host_alloc", "h264r_host_free",
     "h264r_frame_begin", "h264r_submit_mbs", "h264r_submit_mbs_packed", "h264r_wait_uploads", "h264r_set_lanes", "h264r_picture_buf_alloc", "h264r_picture_buf_free", "h264r_submit_picture", "h264r_frame_end", "h264r_frame_abort", "h264r_device_status", "h264r_flush", "h264r_sync", "h264r_read_planes",
+    "h264r_frame_layout", "h264r_read_frame_async", "h264r_wait_readbacks",
     "h264r_frame_digest", "h264r_frame_digests", "h264r_range_excursions", "h264r_excursion_map",
     "h264r_residual_mbs", "h264r_release", "h264r_last_flush_stats", "h264r_set_profiling",
     "h264r_last_flush_kernel_ms", "h264r_last_flush_launch_ms", "h264r_mark", "h264r_elapsed_ms",
@@ -278,6 +282,27 @@ class Engine:
         u = np.empty((H // 2, W // 2), dtype=np.uint8)
         v = np.empty((H // 2, W // 2), dtype=np.uint8)
         self._check(self.L.h264r_read_planes(self.ctx, frame_id, _ptr(y), W, _ptr(u), _ptr(v), W // 2))
+        return y, u, v
+
+    def frame_layout(self):
+        lay = abi.FrameLayout()
+        self._check(self.L.h264r_frame_layout(self.ctx, ctypes.byref(lay)))
+        return lay
+
+    def read_frame_async(self, frame_id, dst_ptr):
+        """dst_ptr: address of frame_layout().frame_bytes bytes (pinned: PinnedBuffer.ptr + offset)"""
+        self._check(self.L.h264r_read_frame_async(self.ctx, frame_id, ctypes.c_void_p(dst_ptr)))
+
+    def wait_readbacks(self):
+        self._check(self.L.h264r_wait_readbacks(self.ctx))
+
+    @staticmethod
+    def planes_of(lay, buf):
+        """views of the three planes inside a frame image read by read_frame_async (buf: uint8 array of frame_bytes)"""
+        W, H = lay.width, lay.height
+        y = np.lib.stride_tricks.as_strided(buf[lay.y_offset:], shape=(H, W), strides=(lay.y_pitch, 1))
+        u = np.lib.stride_tricks.as_strided(buf[lay.u_offset:], shape=(H // 2, W // 2), strides=(lay.c_pitch, 1))
+        v = np.lib.stride_tricks.as_strided(buf[lay.v_offset:], shape=(H // 2, W // 2), strides=(lay.c_pitch, 1))
         return y, u, v
 
     def digests(self, frame_ids):

@@ -216,3 +216,87 @@ def pack_compact(blk_mask, blocks):
         units[first_unit[pb]] = raw[:, :8]
         units[first_unit[pb] + 1] = raw[:, 8:]
     return mask, units
+
+
+_ZZ8 = np.array([0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63])
+
+
+def syntax_from_buffers(hdr, mv, coeff, slice_qp):
+    """Inverse of the host derivation (csrc/host/h264_derive.h): h264r buffers of one picture -> abstract syntax records
+    (synth.MB_DTYPE) in ABSOLUTE form -- mvd[] holds the final vectors, rem_mode[] the final intra modes -- for
+    hoststream.encode_stream(..., flags=E_ABSOLUTE), which turns them into a genuine CABAC bitstream.  Lets content that was
+    generated directly in buffer form (workload.py: the benchmark's GOPs) be fed to the reference decoder and to libavcodec.
+
+    What a bitstream cannot carry is normalised the way the syntax demands: QP changes only at macroblocks with residual syntax
+    (the others inherit the running QP, which nothing reads in REF_COMPAT); a P_Skip flag is dropped (the macroblock is written as
+    P_L0_16x16 without residual, so that it keeps its vector instead of the inferred one)."""
+    hdr = np.ascontiguousarray(hdr).view(abi.MB_HDR_DTYPE).reshape(-1)
+    n = hdr.shape[0]
+    c = np.ascontiguousarray(coeff, dtype=np.int16).reshape(n, 24, 16)
+    m = np.zeros(n, dtype=synth.MB_DTYPE)
+    cls = hdr["mb_class"]
+    kind = np.select([cls == abi.MB_I4x4, cls == abi.MB_I8x8, cls == abi.MB_I16x16, cls == abi.MB_P16x16, cls == abi.MB_P16x8,
+                      cls == abi.MB_P8x16, cls == abi.MB_P8x8],
+                     [synth.I4x4, synth.I8x8, synth.I16x16, synth.P16x16, synth.P16x8, synth.P8x16, synth.P8x8])
+    m["kind"] = kind
+    i16 = kind == synth.I16x16
+    intra = cls <= abi.MB_I16x16
+    m["cbp_luma"] = hdr["cbp"] & 15
+    m["cbp_chroma"] = hdr["cbp"] >> 4
+    m["i16_mode"] = np.where(i16, hdr["intra_modes"] & 3, 0)
+    m["chroma_mode"] = np.where(intra, (hdr["intra_modes"] >> 2) & 3, 0)
+    t8 = (hdr["flags"] & abi.T8x8) != 0
+    m["t8x8"] = t8
+    # ---- levels: raster inside the block -> scan order
+    luma = c[:, :16]
+    scan4 = luma[:, :, ZZ]                                   # [n, blk, k] = level at scan position k
+    m["luma"] = np.where(i16[:, None, None], np.concatenate([luma[:, :, ZZ[1:]], np.zeros((n, 16, 1), np.int16)], axis=2), scan4)
+    if t8.any():
+        l8 = luma.reshape(n, 4, 64)[:, :, _ZZ8].reshape(n, 16, 16)
+        m["luma"][t8] = l8[t8]
+    m["luma_dc"] = np.where(i16[:, None], luma[:, BLK_RASTER[ZZ], 0], 0)
+    ch = c[:, 16:].reshape(n, 2, 4, 16)
+    m["chroma_dc"] = ch[:, :, :, 0]
+    m["chroma_ac"][:, :, :, :15] = ch[:, :, :, ZZ[1:]]
+    # ---- intra modes (final)
+    u = hdr["u"]
+    nib = np.stack([u & 15, u >> 4], axis=2).reshape(n, 16)    # mode of block 2j in the low nibble of byte j
+    is4, is8 = kind == synth.I4x4, kind == synth.I8x8
+    m["rem_mode"][is4] = nib[is4]
+    m["rem_mode"][is8, :4] = nib[is8, :4]
+    # ---- inter: sub types, reference indices per partition, final vector per partition
+    st = hdr["sub_mb_type"]
+    p88 = kind == synth.P8x8
+    for q in range(4):
+        m["sub_type"][:, q] = np.where(p88, (st >> (2 * q)) & 3, 0)
+    ref = u[:, :4]
+    m["ref_idx"][:, 0] = np.where(~intra, ref[:, 0], 0)
+    m["ref_idx"][:, 1] = np.select([kind == synth.P16x8, kind == synth.P8x16, p88], [ref[:, 2], ref[:, 1], ref[:, 1]], 0)
+    m["ref_idx"][:, 2] = np.where(p88, ref[:, 2], 0)
+    m["ref_idx"][:, 3] = np.where(p88, ref[:, 3], 0)
+    if mv is not None:
+        v = np.ascontiguousarray(mv, dtype=np.int16).reshape(n, 16, 2)
+        inter = ~intra
+        m["mvd"][inter, 0] = v[inter, 0]
+        k = kind == synth.P16x8
+        m["mvd"][k, 4] = v[k, 8]
+        k = kind == synth.P8x16
+        m["mvd"][k, 4] = v[k, 2]
+        for a in np.flatnonzero(p88):
+            for q in range(4):
+                b0 = (q >> 1) * 8 + (q & 1) * 2
+                for j, rel in enumerate(_SUB_FIRST[int(m["sub_type"][a, q])]):
+                    m["mvd"][a, q * 4 + j] = v[a, b0 + rel]
+    # ---- QP chain: mb_qp_delta exists only with residual syntax
+    coded = (m["cbp_luma"] != 0) | (m["cbp_chroma"] != 0) | i16
+    qp = hdr["qp_y"].astype(np.int64)
+    prev = slice_qp
+    dq = np.zeros(n, dtype=np.int64)
+    for a in np.flatnonzero(coded):
+        d = int(qp[a]) - prev
+        assert -26 <= d <= 25, "QP step outside mb_qp_delta"
+        dq[a] = d
+        prev = int(qp[a])
+    m["qp_delta"] = dq
+    return m

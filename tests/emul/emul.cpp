@@ -32,6 +32,7 @@ void fill_desc(PicDesc& pd, const h264r_pic_params* pp, const h264r_mb_hdr* hdr,
     pd.nzmask = nullptr;
     pd.tmaps = nullptr;
     pd.dbrec = nullptr;
+    pd.mbox = nullptr;
     for (int i = 0; i < H264R_MAX_REFS; i++) {
         pd.ref_y[i] = ref_y ? ref_y[i] : nullptr;
         pd.ref_u[i] = ref_u ? ref_u[i] : nullptr;
@@ -279,11 +280,22 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
             }
             static DeblockWork dw;
             static PerLane<DeblockIn> in;
+            // hand-over records of the wavefront (rows run one after the other here, so a record is complete when it is read: the
+            // poll checks the stamp once and aborts if the protocol left a word unwritten)
+            std::vector<uint32_t> mbox((size_t)n * MBOX_WORDS, 0u);
+            pd.mbox = mbox.data();
+            const uint32_t stamp = 7;
             for (int a = 0; a < n; a++) {
                 int mbx, mby;
                 mb_xy(g, a, mbx, mby);
                 for (int lane = 0; lane < 32; lane++) in(lane) = deblock_fetch(pd, g, pd.dbrec, a, mbx, mby, lane);
-                seq_deblock_mb_fast(ex, dw, pd, g, in, mbx > 0, mbx, mby);
+                auto poll = [&](int lane) -> uint32_t {
+                    if (lane >= 24) return 0u;
+                    const uint2 v = mbox_load(pd.mbox + (size_t)(a - w_mbs) * MBOX_WORDS + 2 * lane);
+                    if (v.y != stamp) { fprintf(stderr, "deblock hand-over: macroblock %d word %d was never published\n", a - w_mbs, lane); abort(); }
+                    return v.x;
+                };
+                seq_deblock_mb_fast(ex, dw, pd, g, in, mbx > 0, mbx, mby, stamp, poll);
             }
         } else
             for (int a = 0; a < n; a++) seq_deblock_mb(ex, w, pd, g, a);

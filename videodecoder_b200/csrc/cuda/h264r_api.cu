@@ -105,7 +105,8 @@ struct h264r_ctx {
     // arena slot = what the uploads carry, in this order: descriptor | hdr | blk_mask | mv | coefficient blocks;
     // then blk_off and mv_off (written by k_blk_scan, never uploaded)
     // then the residual scratch of the intra macroblocks (device only)
-    size_t slot_bytes = 0, off_desc = 0, off_hdr = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_mvoff = 0, off_coeff = 0, off_res = 0, off_nz = 0, off_dbrec = 0, off_ilist = 0, off_idone = 0;
+    size_t slot_bytes = 0, off_desc = 0, off_hdr = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_mvoff = 0, off_coeff = 0, off_res = 0, off_nz = 0, off_dbrec = 0, off_ilist = 0, off_idone = 0, off_mbox = 0;
+    uint32_t mbox_stamp = 0;                // launch number of k_deblock_rows (stamp of its hand-over records)
     int sparse_stamp = 0;                   // launch stamp of k_intra_list (intra_done words of older launches are smaller)
     // per-flush control block (descriptors + picture lists), pinned host mirror + device copy
     uint8_t* h_ctrl = nullptr;
@@ -196,6 +197,7 @@ void fill_desc(h264r_ctx* c, const Pending& p, PicDesc& pd)
     pd.packed = p.layout == 2;
     pd.intra_list = reinterpret_cast<uint32_t*>(s + c->off_ilist);
     pd.intra_done = reinterpret_cast<int32_t*>(s + c->off_idone);
+    pd.mbox = (c->flags & H264R_REF_COMPAT) ? nullptr : reinterpret_cast<uint32_t*>(s + c->off_mbox);
     // k_residual_pics leaves the residual of the intra macroblocks here, ahead of the wavefront
     pd.residual = p.n_intra > 0 ? reinterpret_cast<int16_t*>(s + c->off_res) : nullptr;
     pd.y = c->frame_y(p.frame_id); pd.u = c->frame_u(p.frame_id); pd.v = c->frame_v(p.frame_id);
@@ -287,7 +289,8 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     c->off_dbrec = c->off_nz + align_up((size_t)c->n_mbs * 4, 256);
     c->off_ilist = c->off_dbrec + ((flags & H264R_REF_COMPAT) ? 0 : align_up((size_t)c->n_mbs * DBREC_BYTES, 256));
     c->off_idone = c->off_ilist + align_up((size_t)(c->n_mbs + 1) * 4, 256);
-    c->slot_bytes = c->off_idone + align_up((size_t)c->n_mbs * 4, 256);
+    c->off_mbox = c->off_idone + align_up((size_t)c->n_mbs * 4, 256);
+    c->slot_bytes = c->off_mbox + ((flags & H264R_REF_COMPAT) ? 0 : align_up((size_t)c->n_mbs * MBOX_WORDS * 4, 256));
     c->ctrl_bytes = align_up((size_t)max_pending * sizeof(PicDesc), 256);      // descriptor table, one entry per arena slot
     auto cleanup = [&](int code) { h264r_destroy(c); return code; };
 #define CUC(call)                                                                                             \
@@ -398,6 +401,8 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     CUC(cudaMallocHost(&c->h_ctrl, c->ctrl_bytes));
     CUC(cudaMemsetAsync(c->d_exc_counter, 0, 256, c->stream));
     for (int s = 0; s < max_pending; s++) CUC(cudaMemsetAsync(c->slot_ptr(s) + c->off_idone, 0, (size_t)c->n_mbs * 4, c->stream));
+    if (!(flags & H264R_REF_COMPAT))        // stamps of the deblocking hand-over records: launch numbers start at 1
+        for (int s = 0; s < max_pending; s++) CUC(cudaMemsetAsync(c->slot_ptr(s) + c->off_mbox, 0, (size_t)c->n_mbs * MBOX_WORDS * 4, c->stream));
     CUC(cudaMemsetAsync(c->d_exc_maps, 0, (size_t)max_frames * c->n_mbs, c->stream));
     // ring of hand-over words: in flight are at most max_pending pictures x 2 wavefront kernels x (H + 1) words
     c->sync_ints = (size_t)8 * max_pending * (h_mbs + 1) + 1024;
@@ -970,9 +975,9 @@ int h264r_flush(h264r_ctx* ctx)
                     ctx->last_launches++;
                 }
                 int rows = L.n * ctx->g.h_mbs, blocks = (rows + ROW_WARPS - 1) / ROW_WARPS;
-                int* sync = sync_region((size_t)rows + 1);
+                int* sync = sync_region(1);       // the ticket
                 prof_begin(2);
-                k_deblock_rows<<<blocks, ROW_WARPS * 32, 0, st>>>(d_desc, L, ctx->g, sync, sync + rows);
+                k_deblock_rows<<<blocks, ROW_WARPS * 32, 0, st>>>(d_desc, L, ctx->g, ++ctx->mbox_stamp, sync);
                 prof_end();
                 ctx->last_launches++;
             });

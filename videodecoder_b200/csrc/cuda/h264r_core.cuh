@@ -93,6 +93,8 @@ struct PicDesc {
     uint32_t* intra_list;      // device only, written by k_blk_scan: [0] = number of intra macroblocks, then their addresses in
                                // ascending order (work list of k_intra_list)
     int32_t* intra_done;       // device only, per macroblock: the launch stamp of the k_intra_list launch that finished it
+    uint32_t* mbox;            // device only, spec mode: hand-over records of the deblocking wavefront, MBOX_WORDS per macroblock
+                               // (see h264r_deblock.cuh: what the row below needs of a macroblock, every 4 bytes with a launch stamp)
 };
 
 // Shared working set of one warp (one macroblock in flight).

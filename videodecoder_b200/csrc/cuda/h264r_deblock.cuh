@@ -31,7 +31,36 @@ struct alignas(16) DeblockWork {
     uint8_t tile[20 * DB_P];
     uint8_t ctile[2][10 * DBC_P];
     uint8_t rec[DBREC_BYTES];
+    uint32_t stage[24];          // hand-over payload being assembled (see MBOX below)
 };
+
+// ---- hand-over between the rows of the wavefront ------------------------------------------------------------------------------
+// What the row below needs of macroblock (x, y) -- luma rows 12..15 (p3..p0 of its top edge) and chroma rows 6, 7 of both planes,
+// 96 bytes -- travels through a per-macroblock record in global memory, NOT through the frame: 24 pairs {4 payload bytes, stamp}
+// written with 8-byte stores (8-byte accesses are single-copy atomic), stamp = the launch's number.  The consumer polls the
+// pairs themselves until every stamp is this launch's: data and flag arrive together, so neither side needs a fence, and no
+// L1 invalidation (fence.acq_rel.gpu) hits the other warps of the SM.  Payload bytes 0..63: luma rows 12..15, 16 bytes each;
+// 64..79: Cb rows 6, 7; 80..95: Cr rows 6, 7.  Consequence for the frame: rows 13..15 (chroma row 7) of a macroblock are
+// WRITTEN by the row below (after its top edge), never by the macroblock's own row -- except in the last row.
+constexpr int MBOX_WORDS = 48;
+HD uint2 mbox_load(const uint32_t* p)
+{
+#if defined(__CUDA_ARCH__)
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+#else
+    return uint2{p[0], p[1]};
+#endif
+}
+HD void mbox_store(uint32_t* p, uint32_t payload, uint32_t stamp)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(stamp) : "memory");
+#else
+    p[0] = payload; p[1] = stamp;
+#endif
+}
 #define DBT(x, y) w.tile[((y) + 4) * DB_P + (x) + DB_X0]
 #define DBC(p, x, y) w.ctile[p][((y) + 2) * DBC_P + (x) + DBC_X0]
 
@@ -151,51 +180,6 @@ HD void phase_deblock_stage(DeblockWork& w, uint4 rec4, bool carry, int lane)
     }
 }
 
-// Phase D1: vertical edges.  Lanes 0..15: luma row `lane` (own samples in own_y, the four to the left from the
-// carry), lanes 16..31: chroma plane (lane-16)>>3, row (lane-16)&7 (own samples in own_c) -- filtered in registers,
-// into the tiles.  Lanes 0..7 also fetch the rows above the macroblock for phase D2; their latency hides behind the
-// filtering.  any: some strength of the macroblock is non-zero (otherwise the tiles are just filled).
-HD void phase_deblock_vert(DeblockWork& w, const PicDesc& pd, const Geometry& g, uint4 own_y, uint2 own_c, bool any, int mbx, int mby, int lane)
-{
-    uint4 top = uint4{0, 0, 0, 0};
-    if (any && mby > 0 && lane < 8) {
-        if (lane < 4) top = H264R_LDCG(reinterpret_cast<const uint4*>(pd.y + (ptrdiff_t)(mby * 16 + lane - 4) * g.pitch_y + mbx * 16));
-        else {
-            const int p = (lane - 4) >> 1, r = ((lane - 4) & 1) - 2;
-            const uint2 t2 = H264R_LDCG(reinterpret_cast<const uint2*>((p ? pd.v : pd.u) + (ptrdiff_t)(mby * 8 + r) * g.pitch_c + mbx * 8));
-            top.x = t2.x; top.y = t2.y;
-        }
-    }
-    // the line into s[20] (luma: positions -4..15; chroma: see deblock_line_edges), ONE filter call for both kinds of
-    // lanes, then back
-    const bool luma = lane < 16;
-    const int p = luma ? 0 : (lane - 16) >> 3, r = luma ? lane : (lane - 16) & 7;
-    int s[20], t[4], c[8];
-    if (luma) {
-        unpack4(*reinterpret_cast<const uint32_t*>(&DBT(-4, r)), s);
-        unpack4(own_y.x, s + 4); unpack4(own_y.y, s + 8); unpack4(own_y.z, s + 12); unpack4(own_y.w, s + 16);
-    } else {
-        unpack4(*reinterpret_cast<const uint32_t*>(&DBC(p, -4, r)), t);
-        unpack4(own_c.x, c); unpack4(own_c.y, c + 4);
-#pragma unroll
-        for (int i = 0; i < 20; i++) s[i] = 0;
-        s[2] = t[2]; s[3] = t[3]; s[4] = c[0]; s[5] = c[1]; s[10] = c[2]; s[11] = c[3]; s[12] = c[4]; s[13] = c[5];
-    }
-    if (any) deblock_line_edges(s, w.rec, 0, luma ? r >> 2 : r >> 1, luma ? 0 : 1 + p);
-    if (luma) {
-        *reinterpret_cast<uint32_t*>(&DBT(-4, r)) = pack4(s);
-        *reinterpret_cast<uint4*>(&DBT(0, r)) = uint4{pack4(s + 4), pack4(s + 8), pack4(s + 12), pack4(s + 16)};
-    } else {
-        t[2] = s[2]; t[3] = s[3]; c[0] = s[4]; c[1] = s[5]; c[2] = s[10]; c[3] = s[11]; c[4] = s[12]; c[5] = s[13];
-        *reinterpret_cast<uint32_t*>(&DBC(p, -4, r)) = pack4(t);
-        *reinterpret_cast<uint2*>(&DBC(p, 0, r)) = uint2{pack4(c), pack4(c + 4)};
-    }
-    if (any && mby > 0 && lane < 8) {
-        if (lane < 4) *reinterpret_cast<uint4*>(&DBT(0, lane - 4)) = top;
-        else { const int pt = (lane - 4) >> 1, rt = ((lane - 4) & 1) - 2; *reinterpret_cast<uint2*>(&DBC(pt, 0, rt)) = uint2{top.x, top.y}; }
-    }
-}
-
 // Phase D2: horizontal edges.  Lanes 0..15: luma column `lane` (y = -4..15) out of the tile, filtered in registers,
 // rows -3..15 back.  Lanes 16..31: chroma column (y = -2..5; p0 / q0 of its two edges back).
 HD void phase_deblock_horz(DeblockWork& w, int lane)
@@ -225,33 +209,11 @@ HD void phase_deblock_horz(DeblockWork& w, int lane)
     }
 }
 
-// Phase D3: write back what this macroblock may have changed: luma rows 0..15 x columns -4..15 and rows -3..-1 x
-// columns 0..15; chroma rows 0..7 x columns -4..7 (of which -1 may have changed) and row -1 x columns 0..7.
-HD void phase_deblock_store_fast(const DeblockWork& w, const PicDesc& pd, const Geometry& g, int mbx, int mby, int lane)
-{
-    for (int t = lane; t < 19 + 18; t += 32) {
-        if (t < 19) {
-            const int r = t < 16 ? t : t - 19;          // 0..15, then -3..-1
-            if (r < 0 && mby == 0) continue;
-            uint8_t* row = pd.y + (ptrdiff_t)(mby * 16 + r) * g.pitch_y + mbx * 16;
-            *reinterpret_cast<uint4*>(row) = *reinterpret_cast<const uint4*>(&DBT(0, r));
-            if (r >= 0 && mbx > 0) *reinterpret_cast<uint32_t*>(row - 4) = *reinterpret_cast<const uint32_t*>(&DBT(-4, r));
-        } else {
-            const int u = t - 19, p = u / 9, k = u - p * 9, r = k < 8 ? k : -1;
-            if (r < 0 && mby == 0) continue;
-            uint8_t* row = (p ? pd.v : pd.u) + (ptrdiff_t)(mby * 8 + r) * g.pitch_c + mbx * 8;
-            *reinterpret_cast<uint2*>(row) = *reinterpret_cast<const uint2*>(&DBC(p, 0, r));
-            if (r >= 0 && mbx > 0) *reinterpret_cast<uint32_t*>(row - 4) = *reinterpret_cast<const uint32_t*>(&DBC(p, -4, r));
-        }
-    }
-}
-
 #undef DBT
 #undef DBC
 
-// K4 for one macroblock: its neighbours A, B, C are completely filtered.  rec4 / own_y / own_c: the macroblock's record
-// and its own (unfiltered) samples, fetched by the caller before it waited for the neighbours; carry: the warp's tiles
-// still hold the macroblock to the left.
+// K4 for one macroblock of a row of the wavefront.  rec4 / own_y / own_c: the macroblock's record and its own (unfiltered)
+// samples, fetched by the caller one macroblock ahead; carry: the warp's tiles still hold the macroblock to the left.
 struct DeblockIn { uint4 rec4, own_y; uint2 own_c; };
 // what lane `lane` fetches for macroblock (mbx, mby): 16 bytes of the record (lanes 0..7), its luma row (lanes 0..15) or
 // its chroma row (lanes 16..31).  None of it depends on the neighbours' filtering.
@@ -267,17 +229,112 @@ HD DeblockIn deblock_fetch(const PicDesc& pd, const Geometry& g, const uint8_t* 
     }
     return in;
 }
-template <class Exec>
-HD void seq_deblock_mb_fast(Exec& ex, DeblockWork& w, const PicDesc& pd, const Geometry& g, PerLane<DeblockIn>& in, bool carry, int mbx, int mby)
+
+#define DBT(x, y) w.tile[((y) + 4) * DB_P + (x) + DB_X0]
+#define DBC(p, x, y) w.ctile[p][((y) + 2) * DBC_P + (x) + DBC_X0]
+// Phase D1 without the fetch of the rows above (they arrive through the hand-over record): vertical edges into the tiles.
+HD void phase_deblock_vert2(DeblockWork& w, uint4 own_y, uint2 own_c, bool any, int lane)
 {
+    const bool luma = lane < 16;
+    const int p = luma ? 0 : (lane - 16) >> 3, r = luma ? lane : (lane - 16) & 7;
+    int s[20], t[4], c[8];
+    if (luma) {
+        unpack4(*reinterpret_cast<const uint32_t*>(&DBT(-4, r)), s);
+        unpack4(own_y.x, s + 4); unpack4(own_y.y, s + 8); unpack4(own_y.z, s + 12); unpack4(own_y.w, s + 16);
+    } else {
+        unpack4(*reinterpret_cast<const uint32_t*>(&DBC(p, -4, r)), t);
+        unpack4(own_c.x, c); unpack4(own_c.y, c + 4);
+#pragma unroll
+        for (int i = 0; i < 20; i++) s[i] = 0;
+        s[2] = t[2]; s[3] = t[3]; s[4] = c[0]; s[5] = c[1]; s[10] = c[2]; s[11] = c[3]; s[12] = c[4]; s[13] = c[5];
+    }
+    if (any) deblock_line_edges(s, w.rec, 0, luma ? r >> 2 : r >> 1, luma ? 0 : 1 + p);
+    if (luma) {
+        *reinterpret_cast<uint32_t*>(&DBT(-4, r)) = pack4(s);
+        *reinterpret_cast<uint4*>(&DBT(0, r)) = uint4{pack4(s + 4), pack4(s + 8), pack4(s + 12), pack4(s + 16)};
+    } else {
+        t[2] = s[2]; t[3] = s[3]; c[0] = s[4]; c[1] = s[5]; c[2] = s[10]; c[3] = s[11]; c[4] = s[12]; c[5] = s[13];
+        *reinterpret_cast<uint32_t*>(&DBC(p, -4, r)) = pack4(t);
+        *reinterpret_cast<uint2*>(&DBC(p, 0, r)) = uint2{pack4(c), pack4(c + 4)};
+    }
+}
+// The hand-over payload of the macroblock in the tiles (its own columns): luma rows 12..15, chroma rows 6, 7 -> w.stage.
+HD void phase_mbox_stage(DeblockWork& w, int lane)
+{
+    if (lane < 4) *reinterpret_cast<uint4*>(&w.stage[lane * 4]) = *reinterpret_cast<const uint4*>(&DBT(0, 12 + lane));
+    else if (lane < 8) { const int p = (lane - 4) >> 1, r = 6 + ((lane - 4) & 1); *reinterpret_cast<uint2*>(&w.stage[16 + (lane - 4) * 2]) = *reinterpret_cast<const uint2*>(&DBC(p, 0, r)); }
+}
+// The left macroblock's payload was staged before this macroblock's left edge touched its last columns: they are the carry
+// columns of the tiles now (luma columns 12..15 = tile columns -4..-1; chroma 4..7 likewise).
+HD void phase_mbox_patch(DeblockWork& w, int lane)
+{
+    if (lane < 4) w.stage[lane * 4 + 3] = *reinterpret_cast<const uint32_t*>(&DBT(-4, 12 + lane));
+    else if (lane < 8) { const int p = (lane - 4) >> 1, r = 6 + ((lane - 4) & 1); w.stage[16 + (lane - 4) * 2 + 1] = *reinterpret_cast<const uint32_t*>(&DBC(p, -4, r)); }
+}
+HD void phase_mbox_publish(const DeblockWork& w, uint32_t* mbox_mb, uint32_t stamp, int lane)
+{
+    if (lane < 24) mbox_store(mbox_mb + 2 * lane, w.stage[lane], stamp);
+}
+// The rows above (payload word `lane` < 24 in `top`) into the tiles: luma rows -4..-1, chroma rows -2, -1.
+HD void phase_mbox_unpack(DeblockWork& w, uint32_t top, int lane)
+{
+    if (lane < 16) *reinterpret_cast<uint32_t*>(&DBT((lane & 3) * 4, (lane >> 2) - 4)) = top;
+    else if (lane < 24) { const int k = lane - 16, p = k >> 2, r = ((k >> 1) & 1) - 2; *reinterpret_cast<uint32_t*>(&DBC(p, (k & 1) * 4, r)) = top; }
+}
+// Phase D3 under the hand-over rule: this row writes its own rows 0..12 (chroma 0..6) -- all of them in the picture's last row
+// -- with the four columns to the left, and ALWAYS the rows -3..-1 (chroma -1) of the macroblock above, which that row left to it.
+// own: the macroblock itself changed (some strength non-zero); else only the rows above are written.
+HD void phase_deblock_store2(const DeblockWork& w, const PicDesc& pd, const Geometry& g, int mbx, int mby, bool own, bool last_row, int lane)
+{
+    for (int t = lane; t < 19 + 18; t += 32) {
+        if (t < 19) {
+            const int r = t < 16 ? t : t - 19;          // 0..15, then -3..-1
+            if (r < 0 ? mby == 0 : (!own || (r > 12 && !last_row))) continue;
+            uint8_t* row = pd.y + (ptrdiff_t)(mby * 16 + r) * g.pitch_y + mbx * 16;
+            *reinterpret_cast<uint4*>(row) = *reinterpret_cast<const uint4*>(&DBT(0, r));
+            if (r >= 0 && mbx > 0) *reinterpret_cast<uint32_t*>(row - 4) = *reinterpret_cast<const uint32_t*>(&DBT(-4, r));
+        } else {
+            const int u = t - 19, p = u / 9, k = u - p * 9, r = k < 8 ? k : -1;
+            if (r < 0 ? mby == 0 : (!own || (r > 6 && !last_row))) continue;
+            uint8_t* row = (p ? pd.v : pd.u) + (ptrdiff_t)(mby * 8 + r) * g.pitch_c + mbx * 8;
+            *reinterpret_cast<uint2*>(row) = *reinterpret_cast<const uint2*>(&DBC(p, 0, r));
+            if (r >= 0 && mbx > 0) *reinterpret_cast<uint32_t*>(row - 4) = *reinterpret_cast<const uint32_t*>(&DBC(p, -4, r));
+        }
+    }
+}
+#undef DBT
+#undef DBC
+
+// The sequence for macroblock (mbx, mby).  top_poll(lane): the caller's way of obtaining payload word `lane` of the macroblock
+// above once its stamp is this launch's (the kernel polls global memory; the emulator, which runs rows in order, just reads).
+// own_changed_left: the left macroblock's own-row store is still owed its last columns -- they are stored with this one's.
+template <class Exec, class Poll>
+HD void seq_deblock_mb_fast(Exec& ex, DeblockWork& w, const PicDesc& pd, const Geometry& g, PerLane<DeblockIn>& in, bool carry, int mbx, int mby,
+                            uint32_t stamp, Poll&& top_poll)
+{
+    const int a = mby * g.w_mbs + mbx;
+    const bool last_row = mby == g.h_mbs - 1, last_col = mbx == g.w_mbs - 1;
     ex([&](int lane) { phase_deblock_stage(w, in(lane).rec4, carry, lane); });
     // every lane sees the same record: warp-uniform
     uint32_t any = 0;
     for (int i = 0; i < 8; i++) any |= reinterpret_cast<const uint32_t*>(w.rec)[i];
-    ex([&](int lane) { phase_deblock_vert(w, pd, g, in(lane).own_y, in(lane).own_c, any != 0, mbx, mby, lane); });
-    if (!any) return;
-    ex([&](int lane) { phase_deblock_horz(w, lane); });
-    ex([&](int lane) { phase_deblock_store_fast(w, pd, g, mbx, mby, lane); });
+    ex([&](int lane) { phase_deblock_vert2(w, in(lane).own_y, in(lane).own_c, any != 0, lane); });
+    // the macroblock to the left is final now: its hand-over record
+    if (carry && !last_row) {
+        ex([&](int lane) { phase_mbox_patch(w, lane); });
+        ex([&](int lane) { phase_mbox_publish(w, pd.mbox + (size_t)(a - 1) * MBOX_WORDS, stamp, lane); });
+    }
+    if (mby > 0) {
+        PerLane<uint32_t> top;
+        ex([&](int lane) { top(lane) = top_poll(lane); });
+        ex([&](int lane) { phase_mbox_unpack(w, top(lane), lane); });
+    }
+    if (any) ex([&](int lane) { phase_deblock_horz(w, lane); });
+    ex([&](int lane) {
+        phase_deblock_store2(w, pd, g, mbx, mby, any != 0, last_row, lane);
+        if (!last_row) phase_mbox_stage(w, lane);
+    });
+    if (last_col && !last_row) ex([&](int lane) { phase_mbox_publish(w, pd.mbox + (size_t)a * MBOX_WORDS, stamp, lane); });
 }
 
 }  // namespace h264r

@@ -384,8 +384,12 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, H264R_LIST_MIN_CTAS) k_intra_l
     grid_dependency_wait();
 }
 
+// K4, row wavefront: one warp per macroblock row, all pictures of the launch side by side.  Rows hand over through stamped
+// per-macroblock records (h264r_deblock.cuh, MBOX): the row below polls the record of the macroblock above, which its row
+// publishes as soon as the macroblock to ITS right has filtered its left edge -- no progress counters, no fences.  Tickets are
+// taken in (picture, row) order, so the row a warp waits for is always running.
 __global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_deblock_rows(const DescTable descs, const __grid_constant__ PicList list,
-                                                                   Geometry g, int* progress, int* ticket)
+                                                                   Geometry g, uint32_t stamp, int* ticket)
 {
     __shared__ DeblockWork work[ROW_WARPS];
     const int W = g.w_mbs, H = g.h_mbs;
@@ -395,7 +399,6 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_deblock_rows(const DescTa
     ROW_EXEC(flat);
     const int p = flat / H, row = flat - p * H;
     const PicDesc& pd = descs[list.slot[p]];
-    int* prog = progress + (size_t)p * H;
     DeblockWork& w = work[warp];
     PerLane<DeblockIn> in;
     // the macroblock's record and its own samples do not depend on the neighbours: fetched one macroblock ahead
@@ -404,13 +407,22 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_deblock_rows(const DescTa
         const int a = row * W + x;
         in(ex.lane) = next;
         if (x + 1 < W) next = deblock_fetch(pd, g, pd.dbrec, a + 1, x + 1, row, ex.lane);
-        if (row > 0) {
-            int need = x + 2 < W ? x + 2 : W;
-            wait_progress(&prog[row - 1], need);
-        }
+        // first look at the record of the macroblock above, issued before the vertical edges so that its round trip hides
+        // behind them; the poll inside the sequence takes over if it has not been published yet
+        const uint32_t* top = pd.mbox + (size_t)(a - W) * MBOX_WORDS + 2 * (ex.lane < 24 ? ex.lane : 0);
+        uint2 first = uint2{0u, 0u};
+        if (row > 0 && ex.lane < 24) first = mbox_load(top);
+        auto poll = [&](int lane) -> uint32_t {
+            if (lane >= 24) return 0u;
+            uint2 v = first;
+            for (int spins = 0; v.y != stamp; spins++) {
+                if (spins > (1 << 22)) __trap();       // a hand-over that never comes must end the launch, not hang the GPU
+                v = mbox_load(top);
+            }
+            return v.x;
+        };
         ROW_MARK(1);
-        seq_deblock_mb_fast(ex, w, pd, g, in, x > 0, x, row);
-        if (ex.lane == 0) st_release_gpu(&prog[row], x + 1);
+        seq_deblock_mb_fast(ex, w, pd, g, in, x > 0, x, row, stamp, poll);
         ROW_MARK(2);
     }
 }

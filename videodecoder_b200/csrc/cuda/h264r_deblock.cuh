@@ -122,74 +122,64 @@ HD void phase_deblock_prep(uint8_t* rec, const PicDesc& pd, const Geometry& g, c
 // p[0..7] = p3 p2 p1 p0 q0 q1 q2 q3.  Same arithmetic as deblock_luma_line / deblock_chroma_line of h264r_core.cuh.
 HD void deblock_line(int* p, int bs, int alpha, int beta, int tc0, bool chroma)
 {
-    const int P2 = p[1], P1 = p[2], P0 = p[3], Q0 = p[4], Q1 = p[5], Q2 = p[6];
-    if (!(iabs(P0 - Q0) < alpha && iabs(P1 - P0) < beta && iabs(Q1 - Q0) < beta)) return;
-    const bool apb = !chroma && iabs(P2 - P0) < beta, aqb = !chroma && iabs(Q2 - Q0) < beta;
-    if (bs < 4) {
-        const int tc = tc0 + (chroma ? 1 : (int)apb + (int)aqb);
-        const int delta = clip3(-tc, tc, (((Q0 - P0) * 4) + (P1 - Q1) + 4) >> 3);
-        p[3] = clip1(P0 + delta); p[4] = clip1(Q0 - delta);
-        if (apb) p[2] = P1 + clip3(-tc0, tc0, (P2 + ((P0 + Q0 + 1) >> 1) - (P1 * 2)) >> 1);
-        if (aqb) p[5] = Q1 + clip3(-tc0, tc0, (Q2 + ((P0 + Q0 + 1) >> 1) - (Q1 * 2)) >> 1);
-    } else {
-        const bool small = iabs(P0 - Q0) < ((alpha >> 2) + 2);
-        if (apb && small) {
-            p[3] = (P2 + 2 * P1 + 2 * P0 + 2 * Q0 + Q1 + 4) >> 3;
-            p[2] = (P2 + P1 + P0 + Q0 + 2) >> 2;
-            p[1] = (2 * p[0] + 3 * P2 + P1 + P0 + Q0 + 4) >> 3;
-        } else p[3] = (2 * P1 + P0 + Q1 + 2) >> 2;
-        if (aqb && small) {
-            p[4] = (P1 + 2 * P0 + 2 * Q0 + 2 * Q1 + Q2 + 4) >> 3;
-            p[5] = (P0 + Q0 + Q1 + Q2 + 2) >> 2;
-            p[6] = (2 * p[7] + 3 * Q2 + Q1 + Q0 + P0 + 4) >> 3;
-        } else p[4] = (2 * Q1 + Q0 + P1 + 2) >> 2;
-    }
+    // Branch-free: both filters are evaluated and the results selected, so that the two sides and the two filter kinds form
+    // independent instruction streams (one warp works on a macroblock alone: latency, not issue slots, is what counts) and
+    // lanes with different strengths do not serialise.  bs = 0: nothing changes.
+    const int P3 = p[0], P2 = p[1], P1 = p[2], P0 = p[3], Q0 = p[4], Q1 = p[5], Q2 = p[6], Q3 = p[7];
+    const int dpq = iabs(P0 - Q0);
+    const bool on = (bs != 0) & (dpq < alpha) & (iabs(P1 - P0) < beta) & (iabs(Q1 - Q0) < beta);
+    const bool apb = !chroma & (iabs(P2 - P0) < beta), aqb = !chroma & (iabs(Q2 - Q0) < beta);
+    // 8.7.2.3 (bS < 4)
+    const int tc = tc0 + (chroma ? 1 : (int)apb + (int)aqb);
+    const int delta = clip3(-tc, tc, (((Q0 - P0) * 4) + (P1 - Q1) + 4) >> 3);
+    const int avg = (P0 + Q0 + 1) >> 1;
+    const int n_p0 = clip1(P0 + delta), n_q0 = clip1(Q0 - delta);
+    const int n_p1 = P1 + clip3(-tc0, tc0, (P2 + avg - (P1 * 2)) >> 1), n_q1 = Q1 + clip3(-tc0, tc0, (Q2 + avg - (Q1 * 2)) >> 1);
+    // 8.7.2.4 (bS = 4)
+    const bool small = dpq < ((alpha >> 2) + 2);
+    const bool sp = apb & small, sq = aqb & small;
+    const int s_p0 = sp ? (P2 + 2 * P1 + 2 * P0 + 2 * Q0 + Q1 + 4) >> 3 : (2 * P1 + P0 + Q1 + 2) >> 2;
+    const int s_q0 = sq ? (P1 + 2 * P0 + 2 * Q0 + 2 * Q1 + Q2 + 4) >> 3 : (2 * Q1 + Q0 + P1 + 2) >> 2;
+    const int s_p1 = (P2 + P1 + P0 + Q0 + 2) >> 2, s_q1 = (P0 + Q0 + Q1 + Q2 + 2) >> 2;
+    const int s_p2 = (2 * P3 + 3 * P2 + P1 + P0 + Q0 + 4) >> 3, s_q2 = (2 * Q3 + 3 * Q2 + Q1 + Q0 + P0 + 4) >> 3;
+    const bool strong = bs == 4;
+    p[3] = on ? (strong ? s_p0 : n_p0) : P0;
+    p[4] = on ? (strong ? s_q0 : n_q0) : Q0;
+    p[2] = (on & (strong ? sp : apb)) ? (strong ? s_p1 : n_p1) : P1;
+    p[5] = (on & (strong ? sq : aqb)) ? (strong ? s_q1 : n_q1) : Q1;
+    p[1] = (on & strong & sp) ? s_p2 : P2;
+    p[6] = (on & strong & sq) ? s_q2 : Q2;
 }
 // The edges of one line in edge order.  s[0..19] = positions -4..15 along the filtering direction; a chroma line sits
 // in the same array with its two edges where luma edges 0 and 2 are (positions -2..1 at s[2..5], 2..5 at s[10..13]), so
 // that both kinds of lines run the same instruction stream.  k = which of the four strength columns the line uses.
-HD void deblock_line_edges(int s[20], const uint8_t* rec, int dir, int k, int plane)
+HD void deblock_line_edges(int s[20], uint4 bsd, uint4 par, int k, bool chroma)
 {
-    const bool chroma = plane != 0;
-    // everything the four edges need, fetched up front (independent loads), then the edges in order
+    // bsd: the 16 strengths of the direction (byte e*4 + k = edge e, column k); par: {macroblock edge, inner edges} x {alpha | beta << 8
+    // | tc0(bS 1) << 16 | tc0(bS 2) << 24, tc0(bS 3)} of the lane's plane and direction
+    const uint32_t bw[4] = {bsd.x, bsd.y, bsd.z, bsd.w};
     int bs[4];
 #pragma unroll
-    for (int e = 0; e < 4; e++) bs[e] = (chroma && (e & 1)) ? 0 : rec[dir * 16 + e * 4 + k];
-    const uint2 pm = *reinterpret_cast<const uint2*>(rec + 32 + 8 * ((plane * 2 + dir) * 2));          // macroblock edge
-    const uint2 pi = *reinterpret_cast<const uint2*>(rec + 32 + 8 * ((plane * 2 + dir) * 2 + 1));      // inner edges
+    for (int e = 0; e < 4; e++) bs[e] = (chroma && (e & 1)) ? 0 : (int)((bw[e] >> (8 * k)) & 255u);
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-        if (!bs[e]) continue;
-        const uint2 par = e == 0 ? pm : pi;
-        const int alpha = (int)(par.x & 255u), beta = (int)((par.x >> 8) & 255u);
-        const int tc0 = bs[e] == 1 ? (int)((par.x >> 16) & 255u) : (bs[e] == 2 ? (int)(par.x >> 24) : (bs[e] == 3 ? (int)(par.y & 255u) : 0));
+        if (!bw[e]) continue;            // no line of the macroblock crosses this edge with a non-zero strength: warp-uniform
+        const uint32_t px = e == 0 ? par.x : par.z, py = e == 0 ? par.y : par.w;
+        const int alpha = (int)(px & 255u), beta = (int)((px >> 8) & 255u);
+        const int tc0 = bs[e] == 1 ? (int)((px >> 16) & 255u) : (bs[e] == 2 ? (int)(px >> 24) : (bs[e] == 3 ? (int)(py & 255u) : 0));
         deblock_line(s + e * 4, bs[e], alpha, beta, tc0, chroma);
     }
 }
 HD void unpack4(uint32_t v, int* d) { d[0] = (int)(v & 255u); d[1] = (int)((v >> 8) & 255u); d[2] = (int)((v >> 16) & 255u); d[3] = (int)(v >> 24); }
 HD uint32_t pack4(const int* s) { return (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24); }
 
-// Phase D0: the macroblock's record into shared memory (rec4: lane < 8 holds 16 bytes of it) and the carry: the last
-// four columns of the macroblock this warp has just filtered are the left neighbour's columns -4..-1.
-HD void phase_deblock_stage(DeblockWork& w, uint4 rec4, bool carry, int lane)
-{
-    if (lane < 8) *reinterpret_cast<uint4*>(&w.rec[lane * 16]) = rec4;
-    if (carry) {
-        if (lane < 16) *reinterpret_cast<uint32_t*>(&DBT(-4, lane)) = *reinterpret_cast<const uint32_t*>(&DBT(12, lane));
-        else { const int p = (lane - 16) >> 3, r = (lane - 16) & 7; *reinterpret_cast<uint32_t*>(&DBC(p, -4, r)) = *reinterpret_cast<const uint32_t*>(&DBC(p, 4, r)); }
-    }
-}
-
 // Phase D2: horizontal edges.  Lanes 0..15: luma column `lane` (y = -4..15) out of the tile, filtered in registers,
 // rows -3..15 back.  Lanes 16..31: chroma column (y = -2..5; p0 / q0 of its two edges back).
-HD void phase_deblock_horz(DeblockWork& w, int lane)
+HD void phase_deblock_horz(DeblockWork& w, uint4 bsh, uint4 par_h, int lane)
 {
     const bool luma = lane < 16;
     const int p = luma ? 0 : (lane - 16) >> 3, c = luma ? lane : (lane - 16) & 7, k = luma ? c >> 2 : c >> 1;
-    uint32_t anyb = 0;
-#pragma unroll
-    for (int e = 0; e < 4; e++) anyb |= w.rec[16 + e * 4 + k];
-    if (!anyb) return;
+    if (!(((bsh.x | bsh.y | bsh.z | bsh.w) >> (8 * k)) & 255u)) return;
     int s[20];
     if (luma) {
 #pragma unroll
@@ -200,7 +190,7 @@ HD void phase_deblock_horz(DeblockWork& w, int lane)
         s[2] = DBC(p, c, -2); s[3] = DBC(p, c, -1); s[4] = DBC(p, c, 0); s[5] = DBC(p, c, 1);
         s[10] = DBC(p, c, 2); s[11] = DBC(p, c, 3); s[12] = DBC(p, c, 4); s[13] = DBC(p, c, 5);
     }
-    deblock_line_edges(s, w.rec, 1, k, luma ? 0 : 1 + p);
+    deblock_line_edges(s, bsh, par_h, k, !luma);
     if (luma) {
 #pragma unroll
         for (int i = 1; i < 20; i++) DBT(c, i - 4) = (uint8_t)s[i];
@@ -212,16 +202,20 @@ HD void phase_deblock_horz(DeblockWork& w, int lane)
 #undef DBT
 #undef DBC
 
-// K4 for one macroblock of a row of the wavefront.  rec4 / own_y / own_c: the macroblock's record and its own (unfiltered)
-// samples, fetched by the caller one macroblock ahead; carry: the warp's tiles still hold the macroblock to the left.
-struct DeblockIn { uint4 rec4, own_y; uint2 own_c; };
-// what lane `lane` fetches for macroblock (mbx, mby): 16 bytes of the record (lanes 0..7), its luma row (lanes 0..15) or
-// its chroma row (lanes 16..31).  None of it depends on the neighbours' filtering.
+// K4 for one macroblock of a row of the wavefront.  What a lane needs of the macroblock that does not depend on the neighbours'
+// filtering is fetched by the caller one macroblock ahead, straight into registers: the strengths of both directions (the same 32
+// bytes for every lane: one transaction), the filter parameters of the lane's plane, and the lane's own line of (unfiltered) samples.
+struct DeblockIn { uint4 bsv, bsh, par_v, par_h, own_y; uint2 own_c; };
 HD DeblockIn deblock_fetch(const PicDesc& pd, const Geometry& g, const uint8_t* dbrec, int a, int mbx, int mby, int lane)
 {
     DeblockIn in;
-    in.rec4 = uint4{0, 0, 0, 0}; in.own_y = uint4{0, 0, 0, 0}; in.own_c = uint2{0, 0};
-    if (lane < 8) in.rec4 = H264R_LDG(reinterpret_cast<const uint4*>(dbrec + (size_t)a * DBREC_BYTES) + lane);
+    const uint4* rec = reinterpret_cast<const uint4*>(dbrec + (size_t)a * DBREC_BYTES);
+    const int plane = lane < 16 ? 0 : 1 + ((lane - 16) >> 3);
+    in.bsv = H264R_LDG(rec);
+    in.bsh = H264R_LDG(rec + 1);
+    in.par_v = H264R_LDG(rec + 2 + plane * 2);          // bytes 32 + 8 * ((plane * 2 + dir) * 2): 16 bytes per (plane, dir)
+    in.par_h = H264R_LDG(rec + 2 + plane * 2 + 1);
+    in.own_y = uint4{0, 0, 0, 0}; in.own_c = uint2{0, 0};
     if (lane < 16) in.own_y = H264R_LDG(reinterpret_cast<const uint4*>(pd.y + (ptrdiff_t)(mby * 16 + lane) * g.pitch_y + mbx * 16));
     else {
         const int p = (lane - 16) >> 3, r = (lane - 16) & 7;
@@ -232,23 +226,25 @@ HD DeblockIn deblock_fetch(const PicDesc& pd, const Geometry& g, const uint8_t* 
 
 #define DBT(x, y) w.tile[((y) + 4) * DB_P + (x) + DB_X0]
 #define DBC(p, x, y) w.ctile[p][((y) + 2) * DBC_P + (x) + DBC_X0]
-// Phase D1 without the fetch of the rows above (they arrive through the hand-over record): vertical edges into the tiles.
-HD void phase_deblock_vert2(DeblockWork& w, uint4 own_y, uint2 own_c, bool any, int lane)
+// Phase D1: vertical edges into the tiles.  Lanes 0..15: luma row `lane`, lanes 16..31: chroma plane (lane-16)>>3, row (lane-16)&7.
+// The four samples to the left are the last columns of the macroblock the warp filtered just before (carry), which the lane
+// itself wrote: no hand-over inside the warp.  The rows above arrive through the hand-over record (phase_mbox_top).
+HD void phase_deblock_vert2(DeblockWork& w, const DeblockIn& in, bool carry, bool any, int lane)
 {
     const bool luma = lane < 16;
     const int p = luma ? 0 : (lane - 16) >> 3, r = luma ? lane : (lane - 16) & 7;
     int s[20], t[4], c[8];
     if (luma) {
-        unpack4(*reinterpret_cast<const uint32_t*>(&DBT(-4, r)), s);
-        unpack4(own_y.x, s + 4); unpack4(own_y.y, s + 8); unpack4(own_y.z, s + 12); unpack4(own_y.w, s + 16);
+        unpack4(carry ? *reinterpret_cast<const uint32_t*>(&DBT(12, r)) : 0u, s);
+        unpack4(in.own_y.x, s + 4); unpack4(in.own_y.y, s + 8); unpack4(in.own_y.z, s + 12); unpack4(in.own_y.w, s + 16);
     } else {
-        unpack4(*reinterpret_cast<const uint32_t*>(&DBC(p, -4, r)), t);
-        unpack4(own_c.x, c); unpack4(own_c.y, c + 4);
+        unpack4(carry ? *reinterpret_cast<const uint32_t*>(&DBC(p, 4, r)) : 0u, t);
+        unpack4(in.own_c.x, c); unpack4(in.own_c.y, c + 4);
 #pragma unroll
         for (int i = 0; i < 20; i++) s[i] = 0;
         s[2] = t[2]; s[3] = t[3]; s[4] = c[0]; s[5] = c[1]; s[10] = c[2]; s[11] = c[3]; s[12] = c[4]; s[13] = c[5];
     }
-    if (any) deblock_line_edges(s, w.rec, 0, luma ? r >> 2 : r >> 1, luma ? 0 : 1 + p);
+    if (any) deblock_line_edges(s, in.bsv, in.par_v, luma ? r >> 2 : r >> 1, !luma);
     if (luma) {
         *reinterpret_cast<uint32_t*>(&DBT(-4, r)) = pack4(s);
         *reinterpret_cast<uint4*>(&DBT(0, r)) = uint4{pack4(s + 4), pack4(s + 8), pack4(s + 12), pack4(s + 16)};
@@ -264,12 +260,16 @@ HD void phase_mbox_stage(DeblockWork& w, int lane)
     if (lane < 4) *reinterpret_cast<uint4*>(&w.stage[lane * 4]) = *reinterpret_cast<const uint4*>(&DBT(0, 12 + lane));
     else if (lane < 8) { const int p = (lane - 4) >> 1, r = 6 + ((lane - 4) & 1); *reinterpret_cast<uint2*>(&w.stage[16 + (lane - 4) * 2]) = *reinterpret_cast<const uint2*>(&DBC(p, 0, r)); }
 }
-// The left macroblock's payload was staged before this macroblock's left edge touched its last columns: they are the carry
-// columns of the tiles now (luma columns 12..15 = tile columns -4..-1; chroma 4..7 likewise).
-HD void phase_mbox_patch(DeblockWork& w, int lane)
+// Publishes the record of the macroblock to the LEFT (mbox_mb), final now that this macroblock's left edge is through: the payload
+// staged at the end of its own turn, except its last four columns, which are the carry columns of the tiles (luma columns 12..15
+// = tile columns -4..-1; chroma 4..7 likewise).
+HD void phase_mbox_publish_left(const DeblockWork& w, uint32_t* mbox_mb, uint32_t stamp, int lane)
 {
-    if (lane < 4) w.stage[lane * 4 + 3] = *reinterpret_cast<const uint32_t*>(&DBT(-4, 12 + lane));
-    else if (lane < 8) { const int p = (lane - 4) >> 1, r = 6 + ((lane - 4) & 1); w.stage[16 + (lane - 4) * 2 + 1] = *reinterpret_cast<const uint32_t*>(&DBC(p, -4, r)); }
+    if (lane >= 24) return;
+    uint32_t v = w.stage[lane];
+    if (lane < 16) { if ((lane & 3) == 3) v = *reinterpret_cast<const uint32_t*>(&DBT(-4, 12 + (lane >> 2))); }
+    else if (lane & 1) { const int j = (lane - 16) >> 1; v = *reinterpret_cast<const uint32_t*>(&DBC(j >> 1, -4, 6 + (j & 1))); }
+    mbox_store(mbox_mb + 2 * lane, v, stamp);
 }
 HD void phase_mbox_publish(const DeblockWork& w, uint32_t* mbox_mb, uint32_t stamp, int lane)
 {
@@ -283,55 +283,54 @@ HD void phase_mbox_unpack(DeblockWork& w, uint32_t top, int lane)
 }
 // Phase D3 under the hand-over rule: this row writes its own rows 0..12 (chroma 0..6) -- all of them in the picture's last row
 // -- with the four columns to the left, and ALWAYS the rows -3..-1 (chroma -1) of the macroblock above, which that row left to it.
-// own: the macroblock itself changed (some strength non-zero); else only the rows above are written.
+// own: the macroblock itself changed (some strength non-zero); else only the rows above are written.  Lanes 0..15: luma row
+// `lane`, 16..31: chroma rows; then lanes 0..2 / 16, 17 the rows above.
 HD void phase_deblock_store2(const DeblockWork& w, const PicDesc& pd, const Geometry& g, int mbx, int mby, bool own, bool last_row, int lane)
 {
-    for (int t = lane; t < 19 + 18; t += 32) {
-        if (t < 19) {
-            const int r = t < 16 ? t : t - 19;          // 0..15, then -3..-1
-            if (r < 0 ? mby == 0 : (!own || (r > 12 && !last_row))) continue;
-            uint8_t* row = pd.y + (ptrdiff_t)(mby * 16 + r) * g.pitch_y + mbx * 16;
-            *reinterpret_cast<uint4*>(row) = *reinterpret_cast<const uint4*>(&DBT(0, r));
-            if (r >= 0 && mbx > 0) *reinterpret_cast<uint32_t*>(row - 4) = *reinterpret_cast<const uint32_t*>(&DBT(-4, r));
-        } else {
-            const int u = t - 19, p = u / 9, k = u - p * 9, r = k < 8 ? k : -1;
-            if (r < 0 ? mby == 0 : (!own || (r > 6 && !last_row))) continue;
-            uint8_t* row = (p ? pd.v : pd.u) + (ptrdiff_t)(mby * 8 + r) * g.pitch_c + mbx * 8;
-            *reinterpret_cast<uint2*>(row) = *reinterpret_cast<const uint2*>(&DBC(p, 0, r));
-            if (r >= 0 && mbx > 0) *reinterpret_cast<uint32_t*>(row - 4) = *reinterpret_cast<const uint32_t*>(&DBC(p, -4, r));
+    if (lane < 16) {
+        uint8_t* row = pd.y + (ptrdiff_t)(mby * 16 + lane) * g.pitch_y + mbx * 16;
+        if (own && (lane <= 12 || last_row)) {
+            *reinterpret_cast<uint4*>(row) = *reinterpret_cast<const uint4*>(&DBT(0, lane));
+            if (mbx > 0) *reinterpret_cast<uint32_t*>(row - 4) = *reinterpret_cast<const uint32_t*>(&DBT(-4, lane));
         }
+        if (mby > 0 && lane < 3) {
+            const int r = lane - 3;
+            *reinterpret_cast<uint4*>(row - (ptrdiff_t)3 * g.pitch_y) = *reinterpret_cast<const uint4*>(&DBT(0, r));      // row (lane - 3): three rows up from row `lane`
+        }
+    } else {
+        const int p = (lane - 16) >> 3, r = (lane - 16) & 7;
+        uint8_t* row = (p ? pd.v : pd.u) + (ptrdiff_t)(mby * 8 + r) * g.pitch_c + mbx * 8;
+        if (own && (r <= 6 || last_row)) {
+            *reinterpret_cast<uint2*>(row) = *reinterpret_cast<const uint2*>(&DBC(p, 0, r));
+            if (mbx > 0) *reinterpret_cast<uint32_t*>(row - 4) = *reinterpret_cast<const uint32_t*>(&DBC(p, -4, r));
+        }
+        if (mby > 0 && r == 0) *reinterpret_cast<uint2*>(row - g.pitch_c) = *reinterpret_cast<const uint2*>(&DBC(p, 0, -1));
     }
 }
 #undef DBT
 #undef DBC
 
-// The sequence for macroblock (mbx, mby).  top_poll(lane): the caller's way of obtaining payload word `lane` of the macroblock
-// above once its stamp is this launch's (the kernel polls global memory; the emulator, which runs rows in order, just reads).
-// own_changed_left: the left macroblock's own-row store is still owed its last columns -- they are stored with this one's.
+// The sequence for macroblock (mbx, mby): four phases.  top_poll(lane): the caller's way of obtaining payload word `lane` of the
+// macroblock above once its stamp is this launch's (the kernel polls global memory; the emulator, which runs rows in order, reads).
 template <class Exec, class Poll>
 HD void seq_deblock_mb_fast(Exec& ex, DeblockWork& w, const PicDesc& pd, const Geometry& g, PerLane<DeblockIn>& in, bool carry, int mbx, int mby,
                             uint32_t stamp, Poll&& top_poll)
 {
     const int a = mby * g.w_mbs + mbx;
     const bool last_row = mby == g.h_mbs - 1, last_col = mbx == g.w_mbs - 1;
-    ex([&](int lane) { phase_deblock_stage(w, in(lane).rec4, carry, lane); });
-    // every lane sees the same record: warp-uniform
-    uint32_t any = 0;
-    for (int i = 0; i < 8; i++) any |= reinterpret_cast<const uint32_t*>(w.rec)[i];
-    ex([&](int lane) { phase_deblock_vert2(w, in(lane).own_y, in(lane).own_c, any != 0, lane); });
-    // the macroblock to the left is final now: its hand-over record
-    if (carry && !last_row) {
-        ex([&](int lane) { phase_mbox_patch(w, lane); });
-        ex([&](int lane) { phase_mbox_publish(w, pd.mbox + (size_t)(a - 1) * MBOX_WORDS, stamp, lane); });
-    }
-    if (mby > 0) {
-        PerLane<uint32_t> top;
-        ex([&](int lane) { top(lane) = top_poll(lane); });
-        ex([&](int lane) { phase_mbox_unpack(w, top(lane), lane); });
-    }
-    if (any) ex([&](int lane) { phase_deblock_horz(w, lane); });
+    // every lane holds the same strengths: warp-uniform
+    const DeblockIn& i0 = in(0);
+    const bool any = (i0.bsv.x | i0.bsv.y | i0.bsv.z | i0.bsv.w | i0.bsh.x | i0.bsh.y | i0.bsh.z | i0.bsh.w) != 0;
+    ex([&](int lane) { phase_deblock_vert2(w, in(lane), carry, any, lane); });
+    // the macroblock to the left is final now: its record goes out BEFORE this one waits for the row above
+    if ((carry && !last_row) || mby > 0)
+        ex([&](int lane) {
+            if (carry && !last_row) phase_mbox_publish_left(w, pd.mbox + (size_t)(a - 1) * MBOX_WORDS, stamp, lane);
+            if (mby > 0) phase_mbox_unpack(w, top_poll(lane), lane);
+        });
+    if (any) ex([&](int lane) { phase_deblock_horz(w, in(lane).bsh, in(lane).par_h, lane); });
     ex([&](int lane) {
-        phase_deblock_store2(w, pd, g, mbx, mby, any != 0, last_row, lane);
+        phase_deblock_store2(w, pd, g, mbx, mby, any, last_row, lane);
         if (!last_row) phase_mbox_stage(w, lane);
     });
     if (last_col && !last_row) ex([&](int lane) { phase_mbox_publish(w, pd.mbox + (size_t)a * MBOX_WORDS, stamp, lane); });

@@ -48,7 +48,10 @@ struct WarpExecTrace {
         }
     }
 };
-#define ROW_EXEC(flat) WarpExecTrace ex; ex.lane = (int)(threadIdx.x & 31); ex.on = (flat) == 0; ex.k = 0
+#ifndef H264R_TRACE_ROW
+#define H264R_TRACE_ROW 0      // which row of the first picture is timed (0: never waits; others show the hand-over)
+#endif
+#define ROW_EXEC(flat) WarpExecTrace ex; ex.lane = (int)(threadIdx.x & 31); ex.on = (flat) == H264R_TRACE_ROW; ex.k = 0
 #define ROW_MARK(tag) ex.mark(tag)
 #else
 #define ROW_EXEC(flat) WarpExec ex{(int)(threadIdx.x & 31)}

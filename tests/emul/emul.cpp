@@ -248,7 +248,7 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
             if (compat) seq_residual_scratch<true>(ex, w, pd, h, a); else seq_residual_scratch<false>(ex, w, pd, h, a);
         }
     }
-    static uint16_t lut[INTRA4_LUT_SIZE];
+    static uint2 lut[INTRA4_LUT_SIZE];
     intra4_lut_fill(lut, 0, 1);
     for (int xf = 0; xf < 4; xf++)
         for (int yf = 0; yf < 4; yf++)
@@ -262,7 +262,7 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
         if (!use_fast_intra) { if (compat) seq_intra_mb<true>(ex, w, pd, g, h, a); else seq_intra_mb<false>(ex, w, pd, g, h, a); }
         else {
             memcpy(w.res, pd.residual + (size_t)a * 384, 768);
-            if (compat) seq_intra_any<true>(ex, w, lut, pd, g, h, a, carry, true); else seq_intra_any<false>(ex, w, lut, pd, g, h, a, carry, true);
+            if (compat) seq_intra_any<true>(ex, w, lut, pd, g, h, a, carry ? w.colx : nullptr, true); else seq_intra_any<false>(ex, w, lut, pd, g, h, a, carry ? w.colx : nullptr, true);
         }
         prev = a;
     }

@@ -958,10 +958,10 @@ int h264r_flush(h264r_ctx* ctx)
             });
             for_chunks([&](const Pending& p) { return p.n_intra > 0 && !sparse(p); }, [&](const PicList& L) {
                 int rows = L.n * ctx->g.h_mbs, blocks = (rows + ROW_WARPS - 1) / ROW_WARPS;
-                int* sync = sync_region((size_t)rows + 1);        // progress words, then the ticket
+                int* sync = sync_region((size_t)rows * 2 + 1);    // two progress words per row (one per warp of its pair), then the ticket
                 prof_begin(1);
-                if (compat) k_intra_rows<true><<<blocks, ROW_WARPS * 32, 0, st>>>(d_desc, L, ctx->g, sync, sync + rows);
-                else k_intra_rows<false><<<blocks, ROW_WARPS * 32, 0, st>>>(d_desc, L, ctx->g, sync, sync + rows);
+                if (compat) k_intra_rows<true><<<blocks, ROW_WARPS * 64, 0, st>>>(d_desc, L, ctx->g, sync, sync + rows * 2);
+                else k_intra_rows<false><<<blocks, ROW_WARPS * 64, 0, st>>>(d_desc, L, ctx->g, sync, sync + rows * 2);
                 prof_end();
                 ctx->last_launches++;
             });

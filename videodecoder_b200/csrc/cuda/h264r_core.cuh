@@ -112,6 +112,8 @@ struct alignas(16) MbWork {
     uint8_t dtile[24 * 24];               // deblocking luma tile x,y=-4..15 at [(y+4)*24 + x+4]
     uint8_t dctile[2][12 * 12];           // deblocking chroma tiles x,y=-2..7 at [(y+2)*12 + x+2]
     uint8_t bs[32];                       // boundary strengths [dir][edge][k]
+    uint8_t colx[32];                     // the macroblock's right column as soon as it is final: luma rows 0..15, Cb rows 0..7, Cr rows
+                                          // 0..7 -- the left neighbours of the next macroblock of the row, which another warp may reconstruct
 };
 
 // Coefficient storage.  Macroblock a owns the blocks whose bit is set in blk_mask[a] (bit b = block b of the 24
@@ -944,6 +946,7 @@ HD void phase_intra_chroma(MbWork& w, const h264r_mb_hdr& h, int lane)
         }
     }
     for (int k = 0; k < 4; k++) CT(x0 + k, y) = (uint8_t)out[k];
+    if (!COMPAT && x0 == 4) w.colx[16 + plane * 8 + y] = (uint8_t)out[3];
 #undef CT
 }
 

@@ -137,12 +137,17 @@ HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr&
 // y = 0..15 (lanes 8..23), chroma borders when `chroma` (top: lanes 24..29, left: lanes 8..23).  Unavailable
 // neighbours read as 0.  `carry`: the warp's tiles still hold the macroblock to the left, whose last column
 // is the left neighbour.  Other neighbours were written by other warps of the same kernel: ld.global.cg.
-HD void phase_intra_edges_fast(MbWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane, bool chroma, bool carry)
+// left_col: the right column of the macroblock to the left as its warp left it in MbWork::colx (this warp's own or the partner
+// warp's of a row pair), or null: from the frame.
+// parts: 1 = the row above (B, C, D), 2 = the left column, 3 = both.
+HD void phase_intra_edges_fast(MbWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane, bool chroma, const uint8_t* left_col,
+                               int parts = 3)
 {
     int mbx, mby;
     mb_xy(g, a, mbx, mby);
     const bool A = h.flags & H264R_AVAIL_A, B = h.flags & H264R_AVAIL_B, C = h.flags & H264R_AVAIL_C, D = h.flags & H264R_AVAIL_D;
     if (lane < 7) {
+        if (!(parts & 1)) return;
         const int x = lane * 4 - 4;
         const bool ok = lane == 0 ? D : (lane <= 4 ? B : C);
         uint32_t v = 0;
@@ -150,18 +155,20 @@ HD void phase_intra_edges_fast(MbWork& w, const PicDesc& pd, const Geometry& g, 
         if (lane == 0) v &= 0xff000000u;
         *reinterpret_cast<uint32_t*>(&TL(x, -1)) = v;
     } else if (lane >= 8 && lane < 24) {
+        if (!(parts & 2)) return;
         const int yy = lane - 8;
         uint8_t v = 0;
-        if (A) v = carry ? TL(15, yy) : H264R_LDCG(pd.y + (ptrdiff_t)(mby * 16 + yy) * g.pitch_y + mbx * 16 - 1);
+        if (A) v = left_col ? left_col[yy] : H264R_LDCG(pd.y + (ptrdiff_t)(mby * 16 + yy) * g.pitch_y + mbx * 16 - 1);
         TL(-1, yy) = v;
         if (chroma) {
             const int p = yy >> 3, r = yy & 7;
             const uint8_t* c = p ? pd.v : pd.u;
             uint8_t cv = 0;
-            if (A) cv = carry ? CTP(p, 7, r) : H264R_LDCG(c + (ptrdiff_t)(mby * 8 + r) * g.pitch_c + mbx * 8 - 1);
+            if (A) cv = left_col ? left_col[16 + yy] : H264R_LDCG(c + (ptrdiff_t)(mby * 8 + r) * g.pitch_c + mbx * 8 - 1);
             CTP(p, -1, r) = cv;
         }
     } else if (chroma && lane >= 24 && lane < 30) {
+        if (!(parts & 1)) return;
         const int p = (lane - 24) / 3, k = (lane - 24) - p * 3, x = k * 4 - 4;
         const uint8_t* c = p ? pd.v : pd.u;
         const bool ok = k == 0 ? D : B;
@@ -231,6 +238,7 @@ HD void phase_intra16_fast(MbWork& w, const PicDesc& pd, const Geometry& g, cons
     uint32_t exc = add_residual<COMPAT>(p0, &w.res[row * 16 + c0], p0);
     exc += add_residual<COMPAT>(p1, &w.res[row * 16 + c0 + 4], p1);
     *reinterpret_cast<uint2*>(&TL(c0, row)) = uint2{p0, p1};
+    if (lane & 1) w.colx[row] = (uint8_t)(p1 >> 24);
     *reinterpret_cast<uint2*>(pd.y + (size_t)(mby * 16 + row) * g.pitch_y + mbx * 16 + c0) = uint2{p0, p1};
     report_excursions(pd, a, exc);
 }
@@ -285,10 +293,27 @@ HD uint16_t intra4_entry(int mode, int x, int y)
     }
     return (uint16_t)(i0 | (w0 << 4) | (w1 << 6) | (w2 << 8) | (sh << 10));
 }
-constexpr int INTRA4_LUT_SIZE = 9 * 16;
-HD void intra4_lut_fill(uint16_t* lut, int first, int stride)
+// The table the plan reads: for (mode, up-right samples usable, sample position) the two plan words of a block at the tile's
+// origin -- a: the three tile offsets and the shift, b: output offset, weights and kind (see I4Plan).  A block at (X, Y) adds its
+// origin to every offset field.  Built once per CTA in shared memory.
+constexpr int INTRA4_LUT_SIZE = 9 * 2 * 16;
+HD uint2 intra4_plan_entry(int mode, int tr_ok, int pos)
 {
-    for (int k = first; k < INTRA4_LUT_SIZE; k += stride) lut[k] = intra4_entry(k >> 4, k & 3, (k >> 2) & 3);
+    const int x = pos & 3, y = pos >> 2;
+    const uint32_t e = intra4_entry(mode, x, y);
+    const int i0 = (int)(e & 15u), trmax = tr_ok ? 7 : 3;
+    const int left = H264R_TI(-1, 3), top = H264R_TI(0, -1);
+    uint32_t o[3];
+    for (int t = 0; t < 3; t++) {
+        const int i = i0 + t;
+        const int k = i - 5 < trmax ? i - 5 : trmax;
+        o[t] = (uint32_t)(i <= 4 ? left - i * TILE_P : top + k);
+    }
+    return uint2{o[0] | (o[1] << 10) | (o[2] << 20) | (((e >> 10) & 3u) << 30), (uint32_t)H264R_TI(x, y) | (((e >> 4) & 63u) << 10) | (1u << 16)};
+}
+HD void intra4_lut_fill(uint2* lut, int first, int stride)
+{
+    for (int k = first; k < INTRA4_LUT_SIZE; k += stride) lut[k] = intra4_plan_entry(k >> 5, (k >> 4) & 1, k & 15);
 }
 
 // The macroblock's inner wavefront: step d = 0..9 handles the blocks (bx, by) with bx + 2 by = d; half-warp
@@ -300,13 +325,14 @@ HD void intra4_lut_fill(uint16_t* lut, int first, int stride)
 // macroblock::Calc / get_4x4Neighbour (h264/macroblock.cpp:28-33, 1092-1110).
 //   a[d] = o0 | o1 << 10 | o2 << 20 | shift << 30        (tile byte offsets; DC: o0 = top word, o1 = first left sample)
 //   b[d] = out | w0 << 10 | w1 << 12 | w2 << 14 | kind << 16   (kind 0 idle, 1 directional, 2..5 DC with both / left /
-//          top / no neighbours)
+//          top / no neighbours) | column-15 flag << 19 | row << 20
 //   r[d >> 1] = residual of steps d (low half) and d + 1 (high half)
 struct I4Plan { uint32_t a[10], b[10], r[5]; };
 
-HD void intra4_plan(const MbWork& w, const h264r_mb_hdr& h, const uint16_t* lut, int lane, I4Plan& pl)
+HD void intra4_plan(const MbWork& w, const h264r_mb_hdr& h, const uint2* lut, int lane, I4Plan& pl)
 {
     const int pos = lane & 15, x = pos & 3, y = pos >> 2;
+    const bool avA = (h.flags & H264R_AVAIL_A) != 0, avB = (h.flags & H264R_AVAIL_B) != 0, avC = (h.flags & H264R_AVAIL_C) != 0;
 #pragma unroll
     for (int d = 0; d < 10; d++) {
         const int by_min = d > 3 ? (d - 2) >> 1 : 0, by_max = (d >> 1) < 3 ? (d >> 1) : 3;
@@ -317,32 +343,23 @@ HD void intra4_plan(const MbWork& w, const h264r_mb_hdr& h, const uint16_t* lut,
             const int bx = d - 2 * by, ras = by * 4 + bx, blk = blk_raster(ras);
             const int mode = hdr_pred_mode(h, blk);
             const int X = bx * 4, Y = by * 4;
-            B = (uint32_t)H264R_TI(X + x, Y + y);
+            const uint32_t org = (uint32_t)(Y * TILE_P + X);
             res = w.res[(Y + y) * 16 + X + x];
             if (mode == 2) {
-                const bool left_ok = bx > 0 || (h.flags & H264R_AVAIL_A), top_ok = by > 0 || (h.flags & H264R_AVAIL_B);
+                const bool left_ok = bx > 0 || avA, top_ok = by > 0 || avB;
                 A = (uint32_t)H264R_TI(X, Y - 1) | ((uint32_t)H264R_TI(X - 1, Y) << 10);
-                B |= (uint32_t)(left_ok ? (top_ok ? 2 : 3) : (top_ok ? 4 : 5)) << 16;
+                B = (uint32_t)H264R_TI(X + x, Y + y) | ((uint32_t)(left_ok ? (top_ok ? 2 : 3) : (top_ok ? 4 : 5)) << 16);
             } else {
                 bool tr_ok;
                 if (blk == 3 || blk == 11) tr_ok = false;
-                else if (bx == 3) tr_ok = (by == 0) && (h.flags & H264R_AVAIL_C) && (h.flags & H264R_AVAIL_B);
+                else if (bx == 3) tr_ok = (by == 0) && avC && avB;
                 else if (by > 0) tr_ok = true;
-                else tr_ok = (h.flags & H264R_AVAIL_B) != 0;
-                const int trmax = tr_ok ? 7 : 3;
-                const uint32_t e = lut[mode * 16 + pos];
-                const int i0 = (int)(e & 15u);
-                const int left = H264R_TI(X - 1, Y + 3), top = H264R_TI(X, Y - 1);
-                uint32_t o[3];
-#pragma unroll
-                for (int t = 0; t < 3; t++) {
-                    const int i = i0 + t;
-                    const int k = i - 5 < trmax ? i - 5 : trmax;
-                    o[t] = (uint32_t)(i <= 4 ? left - i * TILE_P : top + k);
-                }
-                A = o[0] | (o[1] << 10) | (o[2] << 20) | (((e >> 10) & 3u) << 30);
-                B |= (((e >> 4) & 63u) << 10) | (1u << 16);
+                else tr_ok = avB;
+                const uint2 e = lut[(mode * 2 + (tr_ok ? 1 : 0)) * 16 + pos];
+                A = e.x + org * 0x00100401u;          // the origin into each of the three 10-bit offsets
+                B = e.y + org;
             }
+            if (X + x == 15) B |= (1u << 19) | ((uint32_t)(Y + y) << 20);      // column 15 also goes to MbWork::colx
         }
         pl.a[d] = A; pl.b[d] = B;
         if (d & 1) pl.r[d >> 1] |= (uint32_t)res << 16; else pl.r[d >> 1] = (uint32_t)res & 0xffffu;
@@ -370,7 +387,9 @@ HD void phase_intra4_step(MbWork& w, const PicDesc& pd, int a, const I4Plan& pl,
     }
     const int res = (int)(int16_t)(pl.r[D >> 1] >> (16 * (D & 1)));
     uint32_t exc = 0;
-    w.tile[B & 1023u] = recon_luma<COMPAT>(v + res, exc);
+    const uint8_t s = recon_luma<COMPAT>(v + res, exc);
+    w.tile[B & 1023u] = s;
+    if (B & (1u << 19)) w.colx[(B >> 20) & 15u] = s;
     report_excursions(pd, a, exc);
 }
 
@@ -398,6 +417,20 @@ HD void store_chroma(const MbWork& w, const PicDesc& pd, const Geometry& g, int 
         v = uint2{prmt(r.x, r.y, 0x6420), prmt(r.z, r.w, 0x6420)};
     } else v = *reinterpret_cast<const uint2*>(&CTP(p, 0, row));
     *reinterpret_cast<uint2*>((p ? pd.v : pd.u) + (size_t)(mby * 8 + row) * g.pitch_c + mbx * 8) = v;
+}
+
+// the left neighbours of the tiles from a column another warp left in its MbWork::colx (generic sequences: their edge phase reads
+// the frame, where that macroblock may not have arrived yet)
+HD void patch_left_col(MbWork& w, const uint8_t* left_col, bool chroma, int lane)
+{
+    if (lane < 16) TL(-1, lane) = left_col[lane];
+    else if (chroma) { const int p = (lane - 16) >> 3, r = (lane - 16) & 7; CTP(p, -1, r) = left_col[lane]; }
+}
+// the right column of the macroblock in the tiles -> MbWork::colx (the generic sequences do not write it as they go)
+HD void save_right_col(MbWork& w, int lane)
+{
+    if (lane < 16) w.colx[lane] = TL(15, lane);
+    else { const int p = (lane - 16) >> 3, r = (lane - 16) & 7; w.colx[lane] = CTP(p, 7, r); }
 }
 
 #undef TL

@@ -224,24 +224,80 @@ __device__ __forceinline__ int row_ticket(int* ticket)
     __syncthreads();
     return s_ticket * ROW_WARPS + (int)(threadIdx.x >> 5);
 }
+// the same for CTAs whose rows are not one per warp: returns the flat index of the CTA's first row
+__device__ __forceinline__ int row_ticket(int* ticket, int rows_per_cta)
+{
+    __shared__ int s_ticket2;
+    if (threadIdx.x == 0) s_ticket2 = atomicAdd(ticket, 1);
+    __syncthreads();
+    return s_ticket2 * rows_per_cta;
+}
+
+// Two warps share a macroblock row and take its intra macroblocks in turn (warp `half` the even / odd ones of the row's list):
+// while one runs the dependent part of macroblock n -- neighbour samples, the ten prediction steps -- the other stores
+// macroblock n - 1 and prepares n + 1 (header, residual, Intra4x4 plan), so a row advances one macroblock per "steps" time
+// instead of per whole macroblock.  The right column of a finished macroblock goes to the partner through MbWork::colx in shared
+// memory; two counters per warp order the pair (all in shared memory, no fences beyond the CTA):
+//   done   macroblocks whose right column is in colx (set right after the last step, before the stores)
+//   edges  macroblocks whose neighbour samples have been read (the partner may overwrite its colx again)
+// Each warp publishes its own progress word to the row below: "every macroblock of MINE left of this x is final".
+struct RowPairFlags { int done[2], edges[2]; };
+__device__ __forceinline__ void pair_wait(const volatile int* p, int need)
+{
+    for (int spins = 0; *p < need; spins++)
+        if (spins > (1 << 26)) __trap();       // a partner that never arrives must end the launch, not hang the GPU
+    __threadfence_block();
+}
+struct RowPairSync {
+    volatile RowPairFlags* f;
+    int half, k, need_other, lane;
+    const int* up0; const int* up1; int up_need;      // progress words of the row above and how far it must be (0: nothing to wait for)
+    const uint8_t* partner_col; bool left_is_partner;
+    __device__ __forceinline__ void plan_done()
+    {
+        if (up_need > 0) { wait_progress(up0, up_need); wait_progress(up1, up_need); }
+    }
+    // the macroblock to the left, if it is the partner's previous one: its column comes through shared memory
+    __device__ __forceinline__ const uint8_t* top_done(const uint8_t*)
+    {
+        if (!left_is_partner) return nullptr;
+        pair_wait(&f->done[half ^ 1], need_other);
+        return partner_col;
+    }
+    __device__ __forceinline__ void set(volatile int* p, int v)
+    {
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) *p = v;
+    }
+    __device__ __forceinline__ void edges_done()
+    {
+        set(&f->edges[half], k + 1);
+        pair_wait(&f->edges[half ^ 1], need_other);      // the partner has read this warp's last column: colx may be rewritten
+    }
+    __device__ __forceinline__ void tile_final() { set(&f->done[half], k + 1); }
+};
 
 template <bool COMPAT>
-__global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_intra_rows(const DescTable descs, const __grid_constant__ PicList list,
+__global__ void __launch_bounds__(ROW_WARPS * 64, 2) k_intra_rows(const DescTable descs, const __grid_constant__ PicList list,
                                                               Geometry g, int* progress, int* ticket)
 {
-    __shared__ MbWork work[ROW_WARPS];
-    __shared__ uint32_t s_mask[ROW_WARPS][2][ROW_MASK_WORDS + 1];     // intra bitmaps of this row and of the row above
-    __shared__ uint16_t s_lut[INTRA4_LUT_SIZE];
+    __shared__ MbWork work[ROW_WARPS * 2];
+    __shared__ uint32_t s_mask[ROW_WARPS * 2][2][ROW_MASK_WORDS + 1];     // intra bitmaps of this row and of the row above (per warp)
+    __shared__ uint2 s_lut[INTRA4_LUT_SIZE];
+    __shared__ RowPairFlags s_pair[ROW_WARPS];
     intra4_lut_fill(s_lut, threadIdx.x, blockDim.x);
+    if (threadIdx.x < ROW_WARPS) s_pair[threadIdx.x] = RowPairFlags{{0, 0}, {0, 0}};
     const int W = g.w_mbs, H = g.h_mbs;
-    const int flat = row_ticket(ticket);          // __syncthreads() inside: the table is complete
+    const int warp = threadIdx.x >> 5, slot = warp >> 1, half = warp & 1;
+    const int flat = row_ticket(ticket, ROW_WARPS) + slot;          // __syncthreads() inside: table and flags are complete
     if (flat >= list.n * H) return;
-    const int warp = threadIdx.x >> 5;
-    ROW_EXEC(flat);
+    ROW_EXEC(flat * 2 + half);
     const int p = flat / H, row = flat - p * H;
     const PicDesc& pd = descs[list.slot[p]];
-    int* prog = progress + (size_t)p * H;
+    int* prog = progress + ((size_t)p * H) * 2;              // two words per row: one per warp of the pair
     MbWork& w = work[warp];
+    const MbWork& partner = work[warp ^ 1];
     uint32_t* mask = s_mask[warp][0];
     uint32_t* above = s_mask[warp][1];
     const int n_words = (W + 31) >> 5;
@@ -262,10 +318,12 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_intra_rows(const DescTabl
         }
         return W;
     };
-    int x = next_intra(0), prev = -2;
-    if (ex.lane == 0 && x > 0) st_release_gpu(&prog[row], x);
-    // software pipeline: header and residual of the NEXT intra macroblock of the row travel in registers while the
-    // current one is predicted (their latency is off the critical path)
+    // this warp's macroblocks: entries half, half + 2, ... of the row's list; prev_x = the entry before (the partner's)
+    int prev_x = -2, x = next_intra(0);
+    if (half) { prev_x = x; x = x < W ? next_intra(x + 1) : W; }
+    if (ex.lane == 0 && x > 0) st_release_gpu(&prog[row * 2 + half], x);
+    // software pipeline: header and residual of this warp's NEXT macroblock travel in registers while the current one is
+    // predicted (their latency is off the critical path)
     const bool have_res = pd.residual != nullptr;
     int4 hraw = int4{0, 0, 0, 0};
     uint4 r0 = uint4{0, 0, 0, 0}, r1 = uint4{0, 0, 0, 0};
@@ -279,7 +337,9 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_intra_rows(const DescTabl
         }
     };
     fetch(x);
-    while (x < W) {
+    RowPairSync rs;
+    rs.f = &s_pair[slot]; rs.half = half; rs.lane = ex.lane;
+    for (int k = 0; x < W; k++) {
         const int a = row * W + x;
         h264r_mb_hdr h = *reinterpret_cast<h264r_mb_hdr*>(&hraw);
         if (have_res && ex.lane < 24) {           // the previous macroblock ended with __syncwarp(): w.res is free
@@ -287,22 +347,29 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) k_intra_rows(const DescTabl
             dst[0] = r0; dst[1] = r1;
         }
         __syncwarp();                             // the first phase already reads w.res (Intra4x4 plan)
-        const int x_next = next_intra(x + 1);
+        const int x_mid = next_intra(x + 1);      // the partner's next macroblock
+        const int x_next = x_mid < W ? next_intra(x_mid + 1) : W;
         fetch(x_next);
+        rs.up_need = 0;
         if (row > 0) {
-            // B, C, D are final unless they are intra macroblocks the row above has not reached yet: wait for the
-            // last intra one among (x-1, x, x+1) of the row above
+            // B, C, D are final unless they are intra macroblocks the row above has not reached yet: the sequence waits (after
+            // its plan) for the last intra one among (x-1, x, x+1) of the row above -- on both warps of that row
             int last = -1;
             for (int xx = x + 1; xx >= x - 1 && xx >= 0; xx--)
                 if (xx < W && ((above[xx >> 5] >> (xx & 31)) & 1)) { last = xx; break; }
-            if (last >= 0) wait_progress(&prog[row - 1], last + 1);
+            rs.up_need = last + 1;
+            rs.up0 = &prog[(row - 1) * 2]; rs.up1 = &prog[(row - 1) * 2 + 1];
         }
+        rs.k = k;
+        rs.need_other = half ? k + 1 : k;         // how many macroblocks the partner has finished when its entry before mine is done
+        rs.left_is_partner = prev_x == x - 1 && rs.need_other > 0;
+        rs.partner_col = partner.colx;
         ROW_MARK(1);
-        seq_intra_any<COMPAT>(ex, w, s_lut, pd, g, h, a, prev == x - 1, have_res);
-        prev = x;
+        seq_intra_any<COMPAT>(ex, w, s_lut, pd, g, h, a, nullptr, have_res, rs);
+        prev_x = x_mid;
         x = x_next;
-        // ex() ended with __syncwarp(): every lane's stores precede lane 0's release
-        if (ex.lane == 0) st_release_gpu(&prog[row], x);
+        // ex() ended with __syncwarp(): every lane's stores precede lane 0's release; the partner learns that the samples are in the frame
+        if (ex.lane == 0) st_release_gpu(&prog[row * 2 + half], x);
         ROW_MARK(2);
     }
 }
@@ -329,7 +396,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, H264R_LIST_MIN_CTAS) k_intra_l
                                                               Geometry g, int* ticket, int stamp)
 {
     __shared__ MbWork work[ROW_WARPS];
-    __shared__ uint16_t s_lut[INTRA4_LUT_SIZE];
+    __shared__ uint2 s_lut[INTRA4_LUT_SIZE];
     grid_launch_dependents();
     intra4_lut_fill(s_lut, threadIdx.x, blockDim.x);
     __syncthreads();
@@ -377,7 +444,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, H264R_LIST_MIN_CTAS) k_intra_l
                 wait_progress(pd.intra_done + nbj, stamp);
             }
         }
-        seq_intra_any<COMPAT>(ex, w, s_lut, pd, g, h, a, false, res_early);
+        seq_intra_any<COMPAT>(ex, w, s_lut, pd, g, h, a, nullptr, res_early);
         // ex() ended with __syncwarp(): every lane's stores precede lane 0's release
         if (publish && ex.lane == 0) st_release_gpu(pd.intra_done + a, stamp);
     }

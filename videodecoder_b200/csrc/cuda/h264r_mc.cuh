@@ -597,8 +597,10 @@ HD void phase_inter_stage(InterWork& w, TmaState& ts, const PicDesc& pd, const G
 // vertical tap * row filter = (F(-2) + F(3)) - 5 (F(-1) + F(2)) + 20 b1 + 20 s1, accumulated in QJ / QJ5.
 struct McAcc { int QH[4], QS[4], QV[4], QJ[4], QJ5[4]; uint32_t P, Q; };
 
+// wn: union over the warp of the lanes' NEED bits (warp-uniform): a quantity no lane needs is neither accumulated nor finished.
+// The rounding constant of (x + 16) >> 5 rides in the first tap of QH / QS / QV (j1 takes it out again, see mc_finish).
 template <bool COMPAT, int CLS, int DY>
-HD void mc_accum(const uint32_t A[8], const McSel& m, McAcc& c)
+HD void mc_accum(const uint32_t A[8], const McSel& m, McAcc& c, int wn)
 {
     constexpr uint32_t TA = taps4(1, -5, 20, 20), TB = taps4(-5, 1, 0, 0);
     if (DY < -3 || DY > 3) return;
@@ -608,19 +610,26 @@ HD void mc_accum(const uint32_t A[8], const McSel& m, McAcc& c)
     }
     if (DY == 1) c.P |= A[2] & m.pM;
     if (CLS == 0) return;
+    (void)wn;
+    constexpr bool nh = true, ns = true, nv = true;      // (gating quantities by the warp's NEED bits at run time was measured: the extra
+                                                         // branches and spills cost more than the skipped taps save -- 0.197 against 0.152 ms per launch)
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        if (DY == 0) c.QH[k] = dp4a_us(A[k + 4], TB, dp4a_us(A[k], TA, 0));
-        if (COMPAT) {
-            if (DY == -1) c.QS[k] = dp4a_us(A[k], taps4(1, 0, 0, 0), 0);
-            if (DY == 1) c.QS[k] = dp4a_us(A[k + 4], TB, dp4a_us(A[k], taps4(0, -5, 20, 20), c.QS[k]));
-        } else {
-            if (DY == 1) c.QS[k] = dp4a_us(A[k + 4], TB, dp4a_us(A[k], TA, 0));
+        if (DY == 0 && nh) c.QH[k] = dp4a_us(A[k + 4], TB, dp4a_us(A[k], TA, 16));
+        if (ns) {
+            if (COMPAT) {
+                if (DY == -1) c.QS[k] = dp4a_us(A[k], taps4(1, 0, 0, 0), 16);
+                if (DY == 1) c.QS[k] = dp4a_us(A[k + 4], TB, dp4a_us(A[k], taps4(0, -5, 20, 20), c.QS[k]));
+            } else {
+                if (DY == 1) c.QS[k] = dp4a_us(A[k + 4], TB, dp4a_us(A[k], TA, 16));
+            }
         }
-        if (DY == -2) c.QV[k] = dp4a_us(A[k], m.tv1, 0);
-        if (DY == -1 || DY == 2) c.QV[k] = dp4a_us(A[k], m.tv5, c.QV[k]);
-        if (DY == 0 || DY == 1) c.QV[k] = dp4a_us(A[k], m.tv20, c.QV[k]);
-        if (DY == 3) c.QV[k] = dp4a_us(A[k], m.tv1, c.QV[k]);
+        if (nv) {
+            if (DY == -2) c.QV[k] = dp4a_us(A[k], m.tv1, 16);
+            if (DY == -1 || DY == 2) c.QV[k] = dp4a_us(A[k], m.tv5, c.QV[k]);
+            if (DY == 0 || DY == 1) c.QV[k] = dp4a_us(A[k], m.tv20, c.QV[k]);
+            if (DY == 3) c.QV[k] = dp4a_us(A[k], m.tv1, c.QV[k]);
+        }
         if (CLS == 2) {
             if (COMPAT) {
                 if (DY == -3) c.QJ[k] = dp4a_us(A[k + 4], TB, 0);
@@ -640,13 +649,14 @@ HD void mc_accum(const uint32_t A[8], const McSel& m, McAcc& c)
 
 // the four prediction samples of one output row, packed
 template <bool COMPAT, int CLS>
-HD uint32_t mc_finish(const McSel& m, const McAcc& c)
+HD uint32_t mc_finish(const McSel& m, const McAcc& c, int wn)
 {
     uint32_t P = c.P, Q = c.Q;
     if (CLS >= 1) {
-        uint32_t b = pack_sat_u8((c.QH[0] + 16) >> 5, (c.QH[1] + 16) >> 5, (c.QH[2] + 16) >> 5, (c.QH[3] + 16) >> 5);
-        uint32_t s = pack_sat_u8((c.QS[0] + 16) >> 5, (c.QS[1] + 16) >> 5, (c.QS[2] + 16) >> 5, (c.QS[3] + 16) >> 5);
-        uint32_t v = pack_sat_u8((c.QV[0] + 16) >> 5, (c.QV[1] + 16) >> 5, (c.QV[2] + 16) >> 5, (c.QV[3] + 16) >> 5);
+        (void)wn;
+        const uint32_t b = pack_sat_u8(c.QH[0] >> 5, c.QH[1] >> 5, c.QH[2] >> 5, c.QH[3] >> 5);
+        const uint32_t s = pack_sat_u8(c.QS[0] >> 5, c.QS[1] >> 5, c.QS[2] >> 5, c.QS[3] >> 5);
+        const uint32_t v = pack_sat_u8(c.QV[0] >> 5, c.QV[1] >> 5, c.QV[2] >> 5, c.QV[3] >> 5);
         P |= (b & m.pb) | (v & m.pv);
         Q |= (b & m.qb) | (v & m.qv) | (s & m.qs);
     }
@@ -654,7 +664,7 @@ HD uint32_t mc_finish(const McSel& m, const McAcc& c)
         int j1[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            j1[k] = c.QJ[k] + 20 * (c.QH[k] + c.QS[k]) + 512;
+            j1[k] = c.QJ[k] + 20 * (c.QH[k] + c.QS[k]) + (512 - 20 * 32);      // QH and QS carry +16 each
             if (!COMPAT) j1[k] -= 5 * c.QJ5[k];
         }
         uint32_t j = pack_sat_u8(j1[0] >> 10, j1[1] >> 10, j1[2] >> 10, j1[3] >> 10);
@@ -679,14 +689,14 @@ HD void mc_groups(const uint32_t* row, int sh, uint32_t A[8])
 
 // the lane's 4x2 patch: wp = first of its 8 window rows (row -3 of output row 0), pitch in words
 template <bool COMPAT, int CLS, bool SH>
-HD void mc_patch(const uint32_t* wp, int pitch, int sh, const McSel& m, uint32_t out[2])
+HD void mc_patch(const uint32_t* wp, int pitch, int sh, const McSel& m, uint32_t out[2], int wn)
 {
     McAcc c0, c1;
     uint32_t A[8];
 #define MC_ROW(RR)                                       \
     mc_groups<SH>(wp + (RR) * pitch, sh, A);             \
-    mc_accum<COMPAT, CLS, (RR) - 3>(A, m, c0);           \
-    mc_accum<COMPAT, CLS, (RR) - 4>(A, m, c1);
+    mc_accum<COMPAT, CLS, (RR) - 3>(A, m, c0, wn);       \
+    mc_accum<COMPAT, CLS, (RR) - 4>(A, m, c1, wn);
     if (CLS == 0) {
         // every lane of the warp sits on a full-sample position: row 0 of both output rows
         MC_ROW(3) MC_ROW(4)
@@ -695,8 +705,8 @@ HD void mc_patch(const uint32_t* wp, int pitch, int sh, const McSel& m, uint32_t
         MC_ROW(1) MC_ROW(2) MC_ROW(3) MC_ROW(4) MC_ROW(5) MC_ROW(6) MC_ROW(7)
     }
 #undef MC_ROW
-    out[0] = mc_finish<COMPAT, CLS>(m, c0);
-    out[1] = mc_finish<COMPAT, CLS>(m, c1);
+    out[0] = mc_finish<COMPAT, CLS>(m, c0, wn);
+    out[1] = mc_finish<COMPAT, CLS>(m, c1, wn);
 }
 
 // packed prediction + residual -> packed samples; returns the number of samples that left [0,255]
@@ -771,13 +781,13 @@ HD void phase_inter_compute(InterWork& w, TmaState& ts, const PicDesc& pd, const
     const McSel m = mc_select(mv_x(v) & 3, mv_y(v) & 3);
     uint32_t pred[2];
     if (TMA && tma) {
-        if (wn == 0) mc_patch<COMPAT, 0, TMA>(wp, pitch, sh, m, pred);
-        else if (!(wn & NEED_J)) mc_patch<COMPAT, 1, TMA>(wp, pitch, sh, m, pred);
-        else mc_patch<COMPAT, 2, TMA>(wp, pitch, sh, m, pred);
+        if (wn == 0) mc_patch<COMPAT, 0, TMA>(wp, pitch, sh, m, pred, wn);
+        else if (!(wn & NEED_J)) mc_patch<COMPAT, 1, TMA>(wp, pitch, sh, m, pred, wn);
+        else mc_patch<COMPAT, 2, TMA>(wp, pitch, sh, m, pred, wn);
     } else {
-        if (wn == 0) mc_patch<COMPAT, 0, false>(wp, pitch, 0, m, pred);
-        else if (!(wn & NEED_J)) mc_patch<COMPAT, 1, false>(wp, pitch, 0, m, pred);
-        else mc_patch<COMPAT, 2, false>(wp, pitch, 0, m, pred);
+        if (wn == 0) mc_patch<COMPAT, 0, false>(wp, pitch, 0, m, pred, wn);
+        else if (!(wn & NEED_J)) mc_patch<COMPAT, 1, false>(wp, pitch, 0, m, pred, wn);
+        else mc_patch<COMPAT, 2, false>(wp, pitch, 0, m, pred, wn);
     }
     const int ri = hdr_ref_idx(h, q);
     if (weighted) {

@@ -93,14 +93,19 @@ HD void seq_inter_any(Exec& ex, WarpWork& w, const PicDesc& pd, const Geometry& 
 }
 
 // K1 + K2: one intra macroblock (its neighbours A, B, C, D are complete)
-template <bool COMPAT, class Exec>
-HD void seq_intra_mb(Exec& ex, MbWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a)
+template <bool COMPAT, class Exec, class RowSync>
+HD void seq_intra_mb(Exec& ex, MbWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, RowSync& rs)
 {
+    rs.plan_done();
     ex([&](int lane) {
         phase_load_coeff(w, pd, a, lane);
         phase_intra_edges(w, pd, g, h, a, lane, !COMPAT);
     });
     ex([&](int lane) { phase_residual<COMPAT>(w, h, lane); });
+    // a left neighbour reconstructed by another warp of the row: its column replaces what the edge phase read from the frame
+    const uint8_t* left_col = rs.top_done(nullptr);
+    if (left_col && (h.flags & H264R_AVAIL_A)) ex([&](int lane) { patch_left_col(w, left_col, !COMPAT, lane); });
+    rs.edges_done();
     if (h.mb_class == H264R_MB_I16x16) {
         ex([&](int lane) {
             phase_intra16<COMPAT>(w, pd, g, h, a, lane);
@@ -124,32 +129,58 @@ HD void seq_intra_mb(Exec& ex, MbWork& w, const PicDesc& pd, const Geometry& g, 
     ex([&](int lane) { phase_store(w, pd, g, a, lane); });
 }
 
-// K1 + K2, latency version (h264r_intra.cuh) for Intra4x4 / Intra16x16; Intra8x8 takes the generic phases.
-// `carry`: the warp reconstructed the macroblock to the left immediately before (its tiles are still in w).
-// `have_res`: w.res already holds the macroblock's residual (the caller moved it in from pd.residual).
+// Hooks of a row pair (k_intra_rows: two warps take the intra macroblocks of a row in turn): called by every lane between phases.
+struct NoRowSync {
+    HD void plan_done() {}                                             // next: the samples of the row above are read
+    HD const uint8_t* top_done(const uint8_t* left_col) { return left_col; }  // next: the left column is read, from what this returns
+    HD void edges_done() {}                                            // the left neighbour's column has been read
+    HD void tile_final() {}                                            // MbWork::colx holds this macroblock's right column
+};
+
 template <bool COMPAT, class Exec>
-HD void seq_intra_any(Exec& ex, MbWork& w, const uint16_t* lut, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, bool carry,
-                      bool have_res = false)
+HD void seq_intra_mb(Exec& ex, MbWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a)
+{
+    NoRowSync rs;
+    seq_intra_mb<COMPAT>(ex, w, pd, g, h, a, rs);
+}
+
+// K1 + K2, latency version (h264r_intra.cuh) for Intra4x4 / Intra16x16; Intra8x8 takes the generic phases.
+// left_col: MbWork::colx of the warp that reconstructed the macroblock to the left immediately before, or null (from the frame).
+// `have_res`: w.res already holds the macroblock's residual (the caller moved it in from pd.residual).
+template <bool COMPAT, class Exec, class RowSync>
+HD void seq_intra_any(Exec& ex, MbWork& w, const uint2* lut, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, const uint8_t* left_col,
+                      bool have_res, RowSync& rs)
 {
     if (!COMPAT && (h.mb_class == H264R_MB_I8x8 || (h.flags & H264R_T8x8))) {      // REF_COMPAT has no 8x8 transform
-        seq_intra_mb<COMPAT>(ex, w, pd, g, h, a);
+        seq_intra_mb<COMPAT>(ex, w, pd, g, h, a, rs);
+        ex([&](int lane) { save_right_col(w, lane); });
+        rs.tile_final();
         return;
     }
     if (!have_res) ex([&](int lane) { phase_residual_fast<COMPAT>(w.res, pd, h, a, lane); });
     if (h.mb_class == H264R_MB_I16x16) {
-        ex([&](int lane) { phase_intra_edges_fast(w, pd, g, h, a, lane, !COMPAT, carry); });
+        rs.plan_done();
+        ex([&](int lane) { phase_intra_edges_fast(w, pd, g, h, a, lane, !COMPAT, nullptr, 1); });
+        left_col = rs.top_done(left_col);
+        ex([&](int lane) { phase_intra_edges_fast(w, pd, g, h, a, lane, !COMPAT, left_col, 2); });
+        rs.edges_done();
         ex([&](int lane) {
             phase_intra16_fast<COMPAT>(w, pd, g, h, a, lane);
             if (COMPAT) store_chroma<true>(w, pd, g, a, lane);
             else phase_intra_chroma<false>(w, h, lane);
         });
+        rs.tile_final();
         if (!COMPAT) ex([&](int lane) { store_chroma<false>(w, pd, g, a, lane); });
     } else {
+        // everything that does not depend on the neighbours first: the plan; then the row above; then the left column, the
+        // last thing to become final (the macroblock to the left is the previous link of the row's chain)
         PerLane<I4Plan> plan;
-        ex([&](int lane) {
-            phase_intra_edges_fast(w, pd, g, h, a, lane, !COMPAT, carry);
-            intra4_plan(w, h, lut, lane, plan(lane));
-        });
+        ex([&](int lane) { intra4_plan(w, h, lut, lane, plan(lane)); });
+        rs.plan_done();
+        ex([&](int lane) { phase_intra_edges_fast(w, pd, g, h, a, lane, !COMPAT, nullptr, 1); });
+        left_col = rs.top_done(left_col);
+        ex([&](int lane) { phase_intra_edges_fast(w, pd, g, h, a, lane, !COMPAT, left_col, 2); });
+        rs.edges_done();
         ex([&](int lane) {
             phase_intra4_step<COMPAT, 0>(w, pd, a, plan(lane), lane);
             if (!COMPAT) phase_intra_chroma<false>(w, h, lane);
@@ -163,6 +194,7 @@ HD void seq_intra_any(Exec& ex, MbWork& w, const uint16_t* lut, const PicDesc& p
         ex([&](int lane) { phase_intra4_step<COMPAT, 7>(w, pd, a, plan(lane), lane); });
         ex([&](int lane) { phase_intra4_step<COMPAT, 8>(w, pd, a, plan(lane), lane); });
         ex([&](int lane) { phase_intra4_step<COMPAT, 9>(w, pd, a, plan(lane), lane); });
+        rs.tile_final();
         ex([&](int lane) {
             store_luma_tile(w, pd, g, a, lane);
             store_chroma<COMPAT>(w, pd, g, a, lane);
@@ -173,6 +205,13 @@ HD void seq_intra_any(Exec& ex, MbWork& w, const uint16_t* lut, const PicDesc& p
         mb_xy(g, a, mbx, mby);
         if (is_border_mb(g, mbx, mby)) ex([&](int lane) { phase_pad_mb_luma(pd.y, g.pitch_y, g.w_mbs, g.h_mbs, mbx, mby, lane); });
     }
+}
+template <bool COMPAT, class Exec>
+HD void seq_intra_any(Exec& ex, MbWork& w, const uint2* lut, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, const uint8_t* left_col,
+                      bool have_res = false)
+{
+    NoRowSync rs;
+    seq_intra_any<COMPAT>(ex, w, lut, pd, g, h, a, left_col, have_res, rs);
 }
 
 // K4: deblock one macroblock in place (its neighbours A, B, C are completely filtered)

@@ -150,3 +150,122 @@ def ref_cif_ip(n_pictures=6, w=22, h=18, seed=201, sanitize=None):
 
 SPEC_RECIPES = {"spec_qcif_i": spec_qcif_i, "spec_cif_ip": spec_cif_ip, "spec_qcif_wp": spec_qcif_wp, "spec_dpb": spec_dpb,
                 "spec_hd1080_ip": spec_hd1080_ip}
+
+
+# ---- known-answer streams: one tool at a time (each intra mode, each boundary-strength class) ------------------------
+def _levels(rng, m, qp, p=0.5):
+    """a few low-frequency levels in every coded block of record m (cbp and transform flags already set)"""
+    cfg = synth.ContentConfig(nnz_max=3, max_amp=12.0)
+    if m["kind"] == synth.I16x16:
+        synth._fill_block(rng, m["luma_dc"], 16, qp, cfg)
+        m["luma_dc"] //= 2
+    for q in range(4):
+        if not (int(m["cbp_luma"]) >> q) & 1:
+            continue
+        if m["t8x8"]:
+            synth._fill_block(rng, m["luma"][4 * q:4 * q + 4].reshape(-1), 64, qp, cfg)
+        else:
+            for b in range(4 * q, 4 * q + 4):
+                if rng.random() < p:
+                    synth._fill_block(rng, m["luma"][b], 15 if m["kind"] == synth.I16x16 else 16, qp, cfg)
+    if m["cbp_chroma"]:
+        for c in range(2):
+            synth._fill_block(rng, m["chroma_dc"][c], 4, qp, cfg)
+            if m["cbp_chroma"] == 2:
+                for b in range(4):
+                    if rng.random() < p:
+                        synth._fill_block(rng, m["chroma_ac"][c][b], 15, qp, cfg)
+
+
+def kat_intra_modes():
+    """One IDR picture per mode: Intra4x4 modes 0..8, Intra8x8 modes 0..8, Intra16x16 modes 0..3 -- every block of every macroblock
+    uses the picture's mode wherever its neighbours allow it (DC elsewhere); intra_chroma_pred_mode cycles 0..3 over the pictures."""
+    rng = np.random.default_rng(301)
+    W, H = 6, 5
+    seq = _high_seq(W, H)
+    pics = []
+    plan = [(synth.I4x4, m) for m in range(9)] + [(synth.I8x8, m) for m in range(9)] + [(synth.I16x16, m) for m in range(4)]
+    for i, (kind, mode) in enumerate(plan):
+        pic = synth.make_pic(seq, 0, synth.SLICE_I)
+        pic.idr_pic_id = i
+        pic.disable_deblocking_filter_idc = 1 if i % 2 else 0
+        mbs = np.zeros(W * H, dtype=synth.MB_DTYPE)
+        for a in range(W * H):
+            mby, mbx = divmod(a, W)
+            m = mbs[a]
+            m["kind"] = kind
+            cm = i % 4
+            if (cm == 1 and mbx == 0) or (cm == 2 and mby == 0) or (cm == 3 and (mbx == 0 or mby == 0)):
+                cm = 0
+            m["chroma_mode"] = cm
+            m["cbp_chroma"] = int(rng.integers(0, 3))
+            if kind == synth.I16x16:
+                ok = {0: mby > 0, 1: mbx > 0, 2: True, 3: mbx > 0 and mby > 0}[mode]
+                m["i16_mode"] = mode if ok else 2
+                m["cbp_luma"] = 15 if rng.random() < 0.5 else 0
+            else:
+                m["cbp_luma"] = int(rng.integers(0, 16))
+                m["t8x8"] = 1 if kind == synth.I8x8 else 0
+                nb, step = (16, 1) if kind == synth.I4x4 else (4, 2)
+                for b in range(nb):
+                    ras = synth.BLK_RASTER[b] if kind == synth.I4x4 else (b >> 1) * 8 + (b & 1) * 2
+                    bx, by = (ras % 4), (ras // 4)
+                    left, top = mbx > 0 or bx > 0, mby > 0 or by > 0
+                    need_top, need_left = mode in (0, 3, 7, 4, 5, 6), mode in (1, 8, 4, 5, 6)
+                    m["rem_mode"][b] = mode if (not need_top or top) and (not need_left or left) else 2
+            _levels(rng, m, seq.pic_init_qp)
+        pics.append((pic, mbs))
+    return _encode(seq, pics)
+
+
+def kat_deblock_strengths():
+    """P pictures built so that each boundary-strength class of 8.7.2.1 dominates one picture: bS 0 (same vector, same reference, no
+    levels), bS 1 by vector difference >= 4 quarter samples, bS 1 by different reference pictures, bS 2 (levels on one side of the edge,
+    4x4 and 8x8 transform), bS 3 / 4 (intra macroblocks inside the P picture); filterOffsets -6 .. +6 and a QP step across macroblocks."""
+    rng = np.random.default_rng(302)
+    W, H = 8, 5
+    seq = _high_seq(W, H, num_ref=2)
+    n = W * H
+
+    def p_picture(i, vec, ref, coded, intra=(), t8=False, offs=(0, 0)):
+        pic = synth.make_pic(seq, i, synth.SLICE_P, num_ref_active=2 if i >= 2 else 1)
+        pic.disable_deblocking_filter_idc = 0
+        pic.slice_alpha_c0_offset_div2, pic.slice_beta_offset_div2 = offs
+        mbs = np.zeros(n, dtype=synth.MB_DTYPE)
+        for a in range(n):
+            m = mbs[a]
+            mby, mbx = divmod(a, W)
+            if a in intra:
+                m["kind"] = synth.I16x16 if a % 2 else synth.I4x4
+                m["i16_mode"] = 2
+                m["rem_mode"][:] = 2
+                m["cbp_luma"] = 15 if a % 2 else 5
+                m["cbp_chroma"] = 1
+            else:
+                m["kind"] = (synth.P16x16, synth.P16x8, synth.P8x16, synth.P8x8)[a % 4 if vec == "mixed" else 0]
+                m["sub_type"][:] = (a // 4) % 4 if m["kind"] == synth.P8x8 else 0
+                m["ref_idx"][:] = ref(a) if i >= 2 else 0
+                v = {"same": (8, -4), "steps": (8 + 5 * (mbx % 3), -4 + 6 * (mby % 2)), "mixed": None}[vec]
+                m["mvd"][:] = v if v is not None else rng.integers(-20, 21, size=(16, 2))
+                if coded(a):
+                    m["cbp_luma"] = int(rng.integers(1, 16))
+                    m["cbp_chroma"] = int(rng.integers(0, 3))
+                    m["t8x8"] = 1 if t8 and (m["kind"] != synth.P8x8 or not m["sub_type"].any()) else 0
+                    m["qp_delta"] = int(rng.integers(-3, 4))
+            _levels(rng, m, seq.pic_init_qp, p=0.7)
+        return pic, mbs
+
+    pic0 = synth.make_pic(seq, 0, synth.SLICE_I)
+    pic0.disable_deblocking_filter_idc = 0
+    mbs0 = synth.random_picture(rng, seq, synth.SLICE_I, synth.ContentConfig(p_i8x8=0.3), seq.pic_init_qp, absolute=True)
+    pics = [(pic0, mbs0),
+            p_picture(1, "same", lambda a: 0, lambda a: False),                                  # bS 0 everywhere
+            p_picture(2, "steps", lambda a: 0, lambda a: False, offs=(3, -2)),                   # bS 1: vector differences
+            p_picture(3, "same", lambda a: a % 2, lambda a: False, offs=(-6, 6)),                # bS 1: different reference pictures
+            p_picture(4, "same", lambda a: 0, lambda a: (a + a // W) % 2 == 0, offs=(6, -6)),    # bS 2, 4x4 transform, QP steps
+            p_picture(5, "same", lambda a: 0, lambda a: a % 3 == 0, t8=True),                    # bS 2, 8x8 transform
+            p_picture(6, "mixed", lambda a: a % 2, lambda a: a % 2 == 0, intra={5, 6, 13, 14, 22, 27, 33}, t8=True, offs=(2, 2))]   # bS 3 / 4 and everything
+    return _encode(seq, pics)
+
+
+KAT_RECIPES = {"kat_intra_modes": kat_intra_modes, "kat_deblock_strengths": kat_deblock_strengths}

@@ -83,3 +83,42 @@ def test_dpb_slot_reuse_on_the_engine(built):
     outs, _, status = engine_on_stream(g["stream"], flags=0, transport="compact", pool=6)
     assert status == 0
     check_against_stream_golden(g, outs, "engine with a pool of 6 vs libavcodec")
+
+
+@pytest.mark.parametrize("name", ["kat_intra_modes", "kat_deblock_strengths"])
+def test_known_answer_streams(built, name):
+    """the per-mode / per-boundary-strength streams (pinned against libavcodec by the CPU suite): engine == oracle"""
+    import streams
+    s = streams.KAT_RECIPES[name]()
+    pics, _ = hoststream.decode_stream(s["stream"])
+    want = run_sequence(oracle.recon_picture, pics[0]["w_mbs"], pics[0]["h_mbs"], 0, pics)
+    outs, _, status = engine_on_stream(s["stream"], flags=0, transport="compact")
+    assert status == 0
+    for i, (w, o) in enumerate(zip(want, outs)):
+        for k in "yuv":
+            assert np.array_equal(w[k], o[k]), "%s picture %d plane %s" % (name, i, k)
+
+
+def test_more_pictures_than_one_launch_list_holds(built):
+    """a flush with more pictures per wave than a kernel's by-value picture list (PIC_LIST_MAX = 940) and than the intra work list of
+    one k_intra_list launch (SPARSE_PICS = 64) holds: the scheduler splits the waves into several launches"""
+    from videodecoder_b200 import workload
+    W, H, N = 3, 3, 960
+    rng = np.random.default_rng(77)
+    cfg = workload.WorkloadConfig(p_intra_in_p=0.1, p_skip=0.2)
+    eng = engine.Engine(W, H, max_frames=2 * N, max_pending=2 * N, flags=abi.REF_COMPAT)
+    gops = [workload.make_gop(rng, W, H, 2, cfg) for _ in range(8)]
+    for g in range(N):
+        i_pic, p_pic = gops[g % 8]
+        eng.submit_picture(2 * g, i_pic["pp"], i_pic["hdr"], None, i_pic["coeff"])
+        pp = abi.PicParams.from_buffer_copy(p_pic["pp"])
+        pp.ref_list0[0] = 2 * g
+        mask, blocks = pack.pack_blocks(p_pic["coeff"])
+        eng.submit_picture_packed(2 * g + 1, pp, np.ascontiguousarray(p_pic["hdr"]), p_pic["mv"], mask, blocks)
+    eng.sync()
+    want = [run_sequence(oracle.recon_picture, W, H, abi.REF_COMPAT, gop) for gop in gops]
+    for g in list(range(0, N, 37)) + [N - 1]:
+        for k in range(2):
+            y, u, v = eng.read_planes(2 * g + k)
+            assert np.array_equal(y, want[g % 8][k]["y"]) and np.array_equal(u, want[g % 8][k]["u"]), "GOP %d picture %d" % (g, k)
+    eng.close()

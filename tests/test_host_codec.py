@@ -208,3 +208,29 @@ def test_host_decoder_throughput_is_reported(built):
     g = load_stream_golden("spec_cif_ip")
     n, sec = hoststream.benchmark(g["stream"], repeat=2)
     assert n == 2 * g["n_pics"] and sec > 0
+
+
+@need_lavc
+@pytest.mark.parametrize("name", sorted(streams.KAT_RECIPES))
+def test_known_answer_streams_against_libavcodec(built, name):
+    """one tool at a time (every Intra4x4 / Intra8x8 / Intra16x16 / chroma mode; every boundary-strength class of the deblocking
+    filter): libavcodec's planes == host decoder + spec-mode oracle"""
+    s = streams.KAT_RECIPES[name]()
+    frames = lavc.decode(s["aus"])
+    pics, outs = oracle_on_stream(s["stream"])
+    assert len(frames) == len(outs) == len(s["pics"])
+    for i, (f, o) in enumerate(zip(frames, outs)):
+        for k, ref in zip("yuv", f):
+            assert np.array_equal(o[k], ref), "%s picture %d plane %s" % (name, i, k)
+    if name == "kat_intra_modes":       # the stream really carries every mode
+        seen4, seen8, seen16 = set(), set(), set()
+        for p in pics:
+            for h in p["hdr"]:
+                nib = [(int(h["u"][b >> 1]) >> (4 * (b & 1))) & 15 for b in range(16)]
+                if h["mb_class"] == abi.MB_I4x4:
+                    seen4.update(nib)
+                elif h["mb_class"] == abi.MB_I8x8:
+                    seen8.update(nib[:4])
+                elif h["mb_class"] == abi.MB_I16x16:
+                    seen16.add(int(h["intra_modes"]) & 3)
+        assert seen4 == set(range(9)) and seen8 == set(range(9)) and seen16 == set(range(4))

@@ -12,13 +12,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "emul", "emul.cpp")
 OUT = os.path.join(HERE, "emul", "_build", "libh264emul.so")
-DEPS = [SRC] + [os.path.join(ROOT, "videodecoder_b200", "csrc", "cuda", f) for f in ("h264r_core.cuh", "h264r_seq.cuh", "h264r_mc.cuh", "h264r_intra.cuh", "h264r_deblock.cuh")] + [
+DEPS = [SRC] + [os.path.join(ROOT, "videodecoder_b200", "csrc", "cuda", f) for f in ("h264r_core.cuh", "h264r_seq.cuh", "h264r_mc.cuh", "h264r_mcgrp.cuh", "h264r_intra.cuh", "h264r_deblock.cuh")] + [
     os.path.join(ROOT, "include", "h264r.h")]
 
 _lib = None
 # test switches of the emulator (upper bits of `flags`, never seen by the engine)
 PACKED = 0x40000000          # store coefficients packed (mask + offset + non-zero blocks) as h264r_submit_mbs_packed does
 COMPACT = 0x20000000         # with PACKED: H264R_LEVELS_COMPACT storage (8-byte units, significance map + levels)
+GROUP = 0x10000000           # with PACKED | COMPACT under REF_COMPAT: inter macroblocks through the group sequence of k_inter_grp
 GENERIC_INTRA = 0x80000000   # run the generic intra phases of h264r_core.cuh instead of h264r_intra.cuh
 
 

@@ -7,6 +7,7 @@
 // test-suite compare the kernels' arithmetic with the oracle without a GPU.  It is NOT a CPU
 // fallback: nothing in the product loads it.
 #include "../../videodecoder_b200/csrc/cuda/h264r_seq.cuh"
+#include "../../videodecoder_b200/csrc/cuda/h264r_mcgrp.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -233,6 +234,15 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
     const bool use_fast_intra = !(flags & 0x80000000u);     // test switch: bit 31 selects the generic intra phases
     int n = w_mbs * h_mbs;
     // same order as the device: all inter MBs of the picture first, then the intra MBs
+    if ((flags & 0x10000000u) && mv && !(compat && pd.level_fmt == H264R_LEVELS_COMPACT && pd.mv_off)) {
+        fprintf(stderr, "the group sequence needs REF_COMPAT, compact levels and partition-order vectors\n");
+        abort();
+    }
+    if ((flags & 0x10000000u) && mv) {
+        // test switch bit 28: the group sequence of k_inter_grp (h264r_mcgrp.cuh), GRP_MBS macroblocks per step
+        static GroupWork gw;
+        for (int a0 = 0; a0 < n; a0 += GRP_MBS) seq_inter_group<true>(ex, gw, pd, g, a0, n, []() {});
+    } else
     for (int a = 0; a < n; a++) {
         h264r_mb_hdr h = load_hdr(pd, a);
         if (is_intra(h.mb_class)) continue;

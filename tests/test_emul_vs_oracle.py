@@ -50,6 +50,29 @@ def test_gop_variants(built, compat, variant):
         assert a["excursions"] == b["excursions"]
 
 
+@pytest.mark.parametrize("seed,w,h,dense", [(31, 7, 5, False), (32, 11, 3, False), (33, 3, 3, True), (34, 1, 1, False), (35, 9, 2, True), (36, 17, 1, False)])
+def test_group_sequence(built, seed, w, h, dense):
+    """the group sequence of k_inter_grp (h264r_mcgrp.cuh: residual of the coded blocks of eight macroblocks in dense passes, then
+    staging + interpolation per macroblock) gives the oracle's pictures; picture sizes that leave partial groups, content dense
+    enough that a group's coded blocks exceed the residual slots (the group is then taken in parts), intra macroblocks between
+    the inter ones, weighted prediction off (the lean path)"""
+    rng = np.random.default_rng(seed)
+    cfg = workload.WorkloadConfig(compat=True, num_ref=2, p_intra_in_p=0.15, mv_range=80, p_sub=(0.4, 0, 0.3, 0.3), qp=int(rng.integers(16, 40)))
+    if dense:       # nearly every block of every macroblock coded, small amplitudes
+        cfg = workload.WorkloadConfig(compat=True, num_ref=2, p_intra_in_p=0.1, mv_range=80, p_sub=(0.4, 0, 0.3, 0.3), qp=30, p_skip=0.05,
+                                      p_cbp8=0.95, p_block=0.95, p_chroma=(0.1, 0.2, 0.7), max_amp=3.0)
+    gop = workload.make_gop(rng, w, h, 4, cfg)
+    sanitize_with_oracle(w, h, gop)
+    if dense:
+        assert max(int((p["coeff"].reshape(-1, 24, 16) != 0).any(axis=2).reshape(-1, 24)[:8].sum()) for p in gop[1:]) > 64
+    want = run_sequence(oracle.recon_picture, w, h, abi.REF_COMPAT, gop)
+    got = run_sequence(emul.recon_picture, w, h, abi.REF_COMPAT | emul.PACKED | emul.COMPACT | emul.GROUP, gop)
+    for i, (a, b) in enumerate(zip(want, got)):
+        for k in "yuv":
+            assert np.array_equal(a[k], b[k]), "picture %d plane %s" % (i, k)
+        assert a["excursions"] == b["excursions"]
+
+
 def test_compact_storage_dense_and_extreme_levels(built):
     """the kernels' block readers on H264R_LEVELS_COMPACT storage with compact, plain and mixed macroblocks (7..16 levels
     per block, levels at the int8 limits), fast and generic phases"""

@@ -60,6 +60,8 @@ struct h264r_ctx {
     int digest_every = 1;                   // K5 launches cover this many waves of a flush (H264R_DIGEST_EVERY; measured: 1 is best)
     bool lean_inter = true;                 // k_inter<LEAN> for pictures that qualify (H264R_LEAN=0: the generic instantiation)
     bool pdl = true;                        // programmatic dependent launch of the P-wave kernels (H264R_PDL=0: plain launches)
+    bool inter_group = true;                // k_inter_grp for REF_COMPAT launches of lean pictures (H264R_INTER_GROUP=0: k_inter<LEAN>)
+    int inter_group_gens = 4;               // its grid = SMs x 32 x this (H264R_GROUP_GENS)
     int inter_generations = 8;              // k_inter grid = SMs x inter_ctas_per_sm x this: a few CTA generations balance the tail
     cudaEvent_t ev_dig[64] = {};            // ring: digest launch number n is done
     uint64_t dig_seq = 0;
@@ -312,6 +314,10 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
         if (e5 && atoi(e5) > 0) c->inter_generations = atoi(e5);
         const char* e7 = getenv("H264R_DIGEST_EVERY");
         if (e7 && atoi(e7) > 0) c->digest_every = atoi(e7);
+        const char* e10 = getenv("H264R_INTER_GROUP");
+        if (e10) c->inter_group = atoi(e10) != 0;
+        const char* e11 = getenv("H264R_GROUP_GENS");
+        if (e11 && atoi(e11) > 0) c->inter_group_gens = atoi(e11);
         const char* e9 = getenv("H264R_LEAN");
         if (e9) c->lean_inter = atoi(e9) != 0;
         const char* e8 = getenv("H264R_PDL");
@@ -911,7 +917,12 @@ int h264r_flush(h264r_ctx* ctx)
                 prof_begin(0);
                 const bool tma = ctx->d_tmaps != nullptr;
                 const dim3 blk(KINTER_WARPS * 32);
-                if (lean) {
+                if (lean && compat && !tma && ctx->inter_group) {
+                    // group kernel: one warp per CTA, GRP_MBS macroblocks per step, inter_group_gens CTA generations
+                    const int groups = (ctx->n_mbs + GRP_MBS - 1) / GRP_MBS;
+                    const int gcap = (sm_count * H264R_GRP_MIN_CTAS * ctx->inter_group_gens + L.n - 1) / L.n;
+                    launch_pdl(k_inter_grp<true>, dim3((unsigned)(groups < gcap ? groups : gcap), (unsigned)L.n), dim3(32), st, pdl, d_desc, L, ctx->g);
+                } else if (lean) {
                     if (compat) { if (tma) launch_pdl(k_inter<true, true, true>, grid, blk, st, pdl, d_desc, L, ctx->g); else launch_pdl(k_inter<true, false, true>, grid, blk, st, pdl, d_desc, L, ctx->g); }
                     else { if (tma) launch_pdl(k_inter<false, true, true>, grid, blk, st, pdl, d_desc, L, ctx->g); else launch_pdl(k_inter<false, false, true>, grid, blk, st, pdl, d_desc, L, ctx->g); }
                 } else {

@@ -2,6 +2,7 @@
 // dependencies, synchronisation) around the per-macroblock phase sequences of h264r_seq.cuh.
 #pragma once
 #include "h264r_seq.cuh"
+#include "h264r_mcgrp.cuh"
 
 namespace h264r {
 
@@ -135,6 +136,29 @@ __global__ void __launch_bounds__(KINTER_WARPS * 32, H264R_INTER_MIN_CTAS * 4 / 
         if (is_intra(h.mb_class)) continue;       // warp-uniform; the intra kernels reconstruct it afterwards
         seq_inter_any<COMPAT, TMA, LEAN>(ex, w, pd, g, h, a, pre);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1+K3, group version (h264r_mcgrp.cuh): REF_COMPAT launches whose pictures are all lean (see k_inter).  One warp per CTA takes
+// GRP_MBS consecutive macroblocks at a time; blockIdx.y = picture, blockIdx.x strides over its groups.  Header decoding runs with
+// lane = macroblock, the residual with lane = coded block (dense passes), both before the dependency on the previous kernel of
+// the stream is awaited: only staging reads reference samples.
+// ------------------------------------------------------------------------------------------------
+#ifndef H264R_GRP_MIN_CTAS
+#define H264R_GRP_MIN_CTAS 32        // resident CTAs (= warps) per SM k_inter_grp is compiled for (32: 64 registers)
+#endif
+template <bool COMPAT>
+__global__ void __launch_bounds__(32, H264R_GRP_MIN_CTAS) k_inter_grp(const DescTable descs, const __grid_constant__ PicList list, Geometry g)
+{
+    __shared__ GroupWork w;
+    WarpExec ex{(int)threadIdx.x};
+    const int n_mbs = g.w_mbs * g.h_mbs;
+    const PicDesc& pd = descs[list.slot[blockIdx.y]];
+    grid_launch_dependents();
+    bool waited = false;
+    for (int a0 = (int)blockIdx.x * GRP_MBS; a0 < n_mbs; a0 += (int)gridDim.x * GRP_MBS)
+        seq_inter_group<COMPAT>(ex, w, pd, g, a0, n_mbs, [&]() { if (!waited) { grid_dependency_wait(); waited = true; } });
+    if (!waited) grid_dependency_wait();      // the grid must not retire before its predecessor (see k_intra_list)
 }
 
 // ------------------------------------------------------------------------------------------------

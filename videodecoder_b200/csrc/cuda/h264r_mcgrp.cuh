@@ -1,0 +1,333 @@
+// h264r_mcgrp.cuh -- K1+K3 for inter macroblocks, GROUP version (REF_COMPAT, lean pictures: picture buffers with
+// partition-order vectors and compact levels, no weighting).
+//
+// k_inter (h264r_mc.cuh) spends a warp per macroblock on everything, and ncu's source page shows where that hurts
+// (profiles/r2_ncu_kernels.csv, 908 warp instructions per macroblock): the residual phase runs with lane = block while
+// 3.8 of a macroblock's 24 blocks are coded (about 210 instructions per macroblock for 16 % useful lanes), and the
+// warp-uniform part -- header fields, offsets, coordinates, shape -- costs every lane the same instructions again.
+// Here a warp takes GRP_MBS consecutive macroblocks at a time:
+//   G0  lane i reads header + offsets of macroblock i and works out which of its blocks carry a residual
+//       (ACTIVE blocks: stored luma blocks whose coded_block_pattern bit is set; the four blocks of a chroma plane
+//       that has a stored block -- the chroma DC transform spreads over the plane), its coordinates, its record;
+//   G1  the active blocks of the group become a dense item list (macroblock, block), slot = position in the list;
+//   G2  lane = ITEM: dequantisation + inverse transform of 32 coded blocks at a time, every lane busy, into the
+//       group's residual slots (reference residual::Decode and callees, h264/residual.cpp:184-434) -- none of this
+//       reads a sample, so under programmatic stream serialisation it runs before the previous kernel has drained;
+//   then per macroblock the window staging and the interpolation of h264r_mc.cuh (mc_patch), the residual rows
+//       coming from the slots (a lane finds its block's slot with one popcount).
+// Same arithmetic as seq_inter_mb_fast; the CPU test-suite runs this sequence in the host emulator against the oracle.
+#pragma once
+#include "h264r_mc.cuh"
+
+namespace h264r {
+
+constexpr int GRP_MBS = 8;          // macroblocks a warp takes at a time
+constexpr int GRP_SLOTS = 64;       // residual blocks the working set holds; a group with more active blocks is taken in parts
+
+struct alignas(16) GrpMb {          // record of one macroblock of the group, written by its lane in G0
+    h264r_mb_hdr h;
+    uint32_t mv_off, blk_mask, blk_off, active;     // active: bit b = block b has a residual slot
+    int32_t mbx, mby, slot0, n_items;               // slot0: slot of its first active block (G1)
+};
+struct alignas(128) GroupWork {
+    uint32_t win[512];              // staged windows, layouts of h264r_mc.cuh (phase_inter_stage)
+    uint4 slots[GRP_SLOTS * 2];     // residual blocks: 16 int16 each, raster 4x4
+    GrpMb mb[GRP_MBS];
+    uint8_t items[GRP_SLOTS];       // item -> macroblock of the group << 5 | block
+    uint8_t need[32];               // host emulation of the warp reduction over the lanes' NEED bits
+};
+
+// bit q of a 4-bit coded_block_pattern -> nibble q (luma4x4BlkIdx 4q..4q+3 belong to 8x8 block q)
+HD uint32_t cbp_luma_blocks(uint32_t cbp_l)
+{
+    const uint32_t x = (cbp_l | (cbp_l << 3) | (cbp_l << 6) | (cbp_l << 9)) & 0x1111u;
+    return x * 15u;
+}
+
+// G0: lane i < GRP_MBS prepares macroblock a0 + i.  A macroblock beyond the picture or an intra one gets no items and is
+// skipped by the sequence (the intra kernels reconstruct it afterwards).
+HD void phase_grp_load(GroupWork& w, const PicDesc& pd, const Geometry& g, int a0, int n_mbs, int lane)
+{
+    if (lane >= GRP_MBS) return;
+    GrpMb m;
+    const int a = a0 + lane;
+    if (a >= n_mbs) {
+        const int4 z = int4{0, 0, 0, 0};
+        m.h = *reinterpret_cast<const h264r_mb_hdr*>(&z);        // mb_class 0: an intra class
+        m.mv_off = m.blk_mask = m.blk_off = m.active = 0u;
+        m.mbx = m.mby = m.slot0 = m.n_items = 0;
+        w.mb[lane] = m;
+        return;
+    }
+    const int4 raw = H264R_LDG(reinterpret_cast<const int4*>(pd.hdr + a));
+    m.h = *reinterpret_cast<const h264r_mb_hdr*>(&raw);
+    m.mv_off = H264R_LDG(pd.mv_off + a);
+    m.blk_mask = H264R_LDG(pd.blk_mask + a);
+    m.blk_off = H264R_LDG(pd.blk_off + a);
+    uint32_t active = 0u;
+    if (!is_intra(m.h.mb_class)) {
+        const uint32_t cbp_l = m.h.cbp & 15u, cbp_c = (m.h.cbp >> 4) & 3u;
+        active = m.blk_mask & cbp_luma_blocks(cbp_l);
+        if (cbp_c) {
+            if (m.blk_mask & 0x0F0000u) active |= 0x0F0000u;
+            if (m.blk_mask & 0xF00000u) active |= 0xF00000u;
+        }
+    }
+    m.active = active;
+    m.n_items = popc32(active);
+    m.slot0 = 0;
+    mb_xy(g, a, m.mbx, m.mby);
+    w.mb[lane] = m;
+}
+
+// G1: the part of the group taken now = the longest run of macroblocks from `first` whose active blocks fit the slots
+// (one macroblock has at most 24); lane i of the part numbers the items of macroblock i.
+HD void phase_grp_items(GroupWork& w, int first, int lane, int& take_end_out, int& n_items_out)
+{
+    int cum = 0, take_end = first, slot0 = 0;
+#pragma unroll
+    for (int k = 0; k < GRP_MBS; k++) {
+        const int c = w.mb[k].n_items;
+        if (k >= first && take_end == k && cum + c <= GRP_SLOTS) {
+            if (k == lane) slot0 = cum;
+            cum += c;
+            take_end = k + 1;
+        }
+    }
+    if (lane >= first && lane < take_end) {
+        w.mb[lane].slot0 = slot0;
+        uint32_t act = w.mb[lane].active;
+        int s = slot0;
+        while (act) {
+#if defined(__CUDA_ARCH__)
+            const int b = __ffs((int)act) - 1;
+#else
+            const int b = __builtin_ctz(act);
+#endif
+            act &= act - 1;
+            w.items[s++] = (uint8_t)((lane << 5) | b);
+        }
+    }
+    take_end_out = take_end;       // the same in every lane
+    n_items_out = cum;
+}
+
+// G2: lane = item.  Residual of one active block into its slot; arithmetic of phase_residual_fast (h264r_intra.cuh) for
+// an inter macroblock with compact storage.
+template <bool COMPAT>
+HD void phase_grp_residual(GroupWork& w, const PicDesc& pd, int item, int n_items)
+{
+    if (item >= n_items) return;
+    const int code = w.items[item], i = code >> 5, b = code & 31;
+    const GrpMb& m = w.mb[i];
+    const BlkRef br{m.blk_mask, m.blk_off};
+    const int fmt = H264R_LEVELS_COMPACT;
+    const bool luma = b < 16;
+    const int cbp_c = (m.h.cbp >> 4) & 3;
+    int16_t* dst = reinterpret_cast<int16_t*>(&w.slots[item * 2]);       // 4 rows of 4 int16, private to this lane
+    const uint8_t* src = blk_ptr(pd, br, b, fmt);
+    int4 v0 = int4{0, 0, 0, 0}, v1 = int4{0, 0, 0, 0};
+    if (src && blk_compact(fmt, br)) {
+        // compact block: the levels are scattered into the (zeroed) slot, which has the raster shape of a block, and read back as rows
+        const uint2 v = H264R_LDG(reinterpret_cast<const uint2*>(src));
+        uint32_t map = v.x & 0xffffu;
+        unsigned long long lv = ((unsigned long long)v.y << 16) | (v.x >> 16);
+        w.slots[item * 2] = uint4{0u, 0u, 0u, 0u};
+        w.slots[item * 2 + 1] = uint4{0u, 0u, 0u, 0u};
+        while (map) {
+#if defined(__CUDA_ARCH__)
+            const int q = __ffs((int)map) - 1;
+#else
+            const int q = __builtin_ctz(map);
+#endif
+            map &= map - 1;
+            dst[q] = (int16_t)(int8_t)(lv & 255u);
+            lv >>= 8;
+        }
+        const uint4 r0 = w.slots[item * 2], r1 = w.slots[item * 2 + 1];
+        v0 = int4{(int)r0.x, (int)r0.y, (int)r0.z, (int)r0.w};
+        if (luma || cbp_c == 2) v1 = int4{(int)r1.x, (int)r1.y, (int)r1.z, (int)r1.w};
+    } else if (src) {
+        v0 = blk_levels8(pd, br, src, 0, fmt);
+        if (luma || cbp_c == 2) v1 = blk_levels8(pd, br, src, 8, fmt);
+    }
+    if (!luma && cbp_c != 2) { v0.x &= 0xffff; v0.y = v0.z = v0.w = 0; }        // DC only: AC levels are not coded
+    int c[16];
+    const int wv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int k = 0; k < 8; k++) { c[2 * k] = (int)(int16_t)(wv[k] & 0xffff); c[2 * k + 1] = wv[k] >> 16; }
+    int qp = m.h.qp_y;
+    bool bypass = false;
+    if (!luma) {
+        const int plane = (b - 16) >> 2, cb = (b - 16) & 3;
+        qp = plane ? m.h.qp_cr : m.h.qp_cb;
+        int f;
+        const uint8_t* d3 = blk_ptr(pd, br, 19 + plane * 4, fmt);
+        const int c3 = d3 ? blk_level0(pd, br, d3, fmt) : 0;
+        if (COMPAT) f = (cb == 0 || cb == 3) ? c3 : -c3;      // reference's chroma DC product (h264/matrix.cpp:150-171)
+        else {
+            const uint8_t* d0 = blk_ptr(pd, br, 16 + plane * 4, fmt), * d1 = blk_ptr(pd, br, 17 + plane * 4, fmt), * d2 = blk_ptr(pd, br, 18 + plane * 4, fmt);
+            const int c0 = d0 ? blk_level0(pd, br, d0, fmt) : 0, c1 = d1 ? blk_level0(pd, br, d1, fmt) : 0, c2 = d2 ? blk_level0(pd, br, d2, fmt) : 0;
+            f = c0 + ((cb & 1) ? -c1 : c1) + ((cb & 2) ? -c2 : c2) + ((cb == 1 || cb == 2) ? -c3 : c3);
+        }
+        const int s = (qp * 43) >> 8, mq = qp - 6 * s;
+        c[0] = ((f * 16 * norm_adjust_dc(mq)) * (1 << s)) >> 5;
+        bypass = true;
+    }
+    int nz = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) nz |= c[k];
+    uint4 o0 = uint4{0u, 0u, 0u, 0u}, o1 = o0;
+    if (nz) {
+        int r[16];
+        const Dequant q = make_dequant(qp);
+        idct4_fast(c, q, bypass, r);
+        o0 = uint4{pack_sat_s16x2(r[0], r[1]), pack_sat_s16x2(r[2], r[3]), pack_sat_s16x2(r[4], r[5]), pack_sat_s16x2(r[6], r[7])};
+        o1 = uint4{pack_sat_s16x2(r[8], r[9]), pack_sat_s16x2(r[10], r[11]), pack_sat_s16x2(r[12], r[13]), pack_sat_s16x2(r[14], r[15])};
+    }
+    w.slots[item * 2] = o0;
+    w.slots[item * 2 + 1] = o1;
+}
+
+// the lane's own vector (block lane >> 1) of macroblock m
+HD uint32_t grp_load_mv(const PicDesc& pd, const GrpMb& m, int lane)
+{
+    const uint32_t* mv32 = reinterpret_cast<const uint32_t*>(pd.mv);
+    return H264R_LDG(mv32 - 1 - (ptrdiff_t)(m.mv_off + (uint32_t)mv_part_index(m.h.mb_class, m.h.sub_mb_type, lane >> 1)));
+}
+
+// M0: windows of macroblock m (load staging of phase_inter_stage, coordinates from the record)
+template <bool COMPAT>
+HD void phase_grp_stage(GroupWork& w, const PicDesc& pd, const Geometry& g, const GrpMb& m, int lane, uint32_t v)
+{
+    const h264r_mb_hdr& h = m.h;
+    const int shape = inter_shape_by_type(h);
+    const int W = g.w_mbs * 16, H = g.h_mbs * 16, mbx = m.mbx, mby = m.mby;
+#if !defined(__CUDA_ARCH__)
+    w.need[lane] = (uint8_t)mc_need(mv_x(v) & 3, mv_y(v) & 3);
+#endif
+    if (shape == 0) {
+        const uint8_t* ref = pd.ref_y[hdr_ref_idx(h, 0)];
+        const int xb = clip3(-19, W + 2, mbx * 16 + (mv_x(v) >> 2)), yb = clip3(-19, H + 3, mby * 16 + (mv_y(v) >> 2));
+        stage_window<22, 6, 32, WIN0_PITCH>(w.win, ref, g.pitch_y, xb - 2, yb - 3, lane);
+    } else if (shape == 1) {
+        const int b = lane >> 1, bx = b & 3, by = b >> 2, q = (by >> 1) * 2 + (bx >> 1);
+        const uint8_t* ref = pd.ref_y[hdr_ref_idx(h, q)];
+        const int xb = clip3(-11, W + 2, mbx * 16 + (q & 1) * 8 + (mv_x(v) >> 2)), yb = clip3(-11, H + 3, mby * 16 + (q >> 1) * 8 + (mv_y(v) >> 2));
+        stage_window<14, 4, 8, WIN1_PITCH>(w.win + q * WIN1_STRIDE, ref, g.pitch_y, xb - 2, yb - 3, ((by & 1) * 2 + (bx & 1)) * 2 + (lane & 1));
+    } else {
+        const int b = lane >> 1, bx = b & 3, by = b >> 2, q = (by >> 1) * 2 + (bx >> 1);
+        const uint8_t* ref = pd.ref_y[hdr_ref_idx(h, q)];
+        int ys = mby * 16 + by * 4;
+        // reference's source-row offset for 4x4 sub-partitions 2 and 3 (D8, h264/macroblock.cpp:786-789)
+        if (COMPAT && h.mb_class == H264R_MB_P8x8 && ((h.sub_mb_type >> (2 * q)) & 3) == H264R_SUB_4x4 && (by & 1)) ys -= 3;
+        const int xb = clip3(-7, W + 2, mbx * 16 + bx * 4 + (mv_x(v) >> 2)), yb = clip3(-7, H + 3, ys + (mv_y(v) >> 2));
+        stage_window<10, 3, 2, 3>(w.win + b * 30, ref, g.pitch_y, xb - 2, yb - 3, lane & 1);
+    }
+}
+
+// packed prediction + two residual pairs -> packed samples; returns the number of samples that left [0,255]
+template <bool COMPAT>
+HD uint32_t add_residual_words(uint32_t pred, uint32_t rx, uint32_t ry, uint32_t& packed)
+{
+    if (!COMPAT) { rx = clamp_s16x2(rx); ry = clamp_s16x2(ry); }
+    uint32_t s0 = add_s16x2(prmt(pred, 0u, 0x4140), rx), s1 = add_s16x2(prmt(pred, 0u, 0x4342), ry);
+    uint32_t n = 0;
+    if ((s0 | s1) & 0xff00ff00u)
+        n = ((s0 & 0xff00u) != 0) + ((s0 & 0xff000000u) != 0) + ((s1 & 0xff00u) != 0) + ((s1 & 0xff000000u) != 0);
+    if (!COMPAT) { s0 = clip255_s16x2(s0); s1 = clip255_s16x2(s1); }
+    packed = prmt(s0, s1, 0x6420);          // COMPAT: the plane keeps the low 8 bits (D3)
+    return n;
+}
+
+// M1: interpolation, residual from the slots, stores (REF_COMPAT: chroma = residual, D4)
+template <bool COMPAT>
+HD void phase_grp_compute(GroupWork& w, const PicDesc& pd, const Geometry& g, const GrpMb& m, int a, int lane, uint32_t v)
+{
+    static_assert(COMPAT, "the group path covers REF_COMPAT");
+    const h264r_mb_hdr& h = m.h;
+    int wn;
+#if defined(__CUDA_ARCH__)
+    wn = (int)__reduce_or_sync(0xffffffffu, (unsigned)mc_need(mv_x(v) & 3, mv_y(v) & 3));
+#else
+    {
+        const uint4* np = reinterpret_cast<const uint4*>(w.need);
+        const uint4 n0 = np[0], n1 = np[1];
+        uint32_t o = n0.x | n0.y | n0.z | n0.w | n1.x | n1.y | n1.z | n1.w;
+        o |= o >> 16; o |= o >> 8;
+        wn = (int)(o & 15u);
+    }
+#endif
+    const int b = lane >> 1, half = lane & 1, bx = b & 3, by = b >> 2, q = (by >> 1) * 2 + (bx >> 1);
+    const int shape = inter_shape_by_type(h);
+    const uint32_t* wp;
+    int pitch;
+    if (shape == 0) { wp = w.win + (by * 4 + half * 2) * WIN0_PITCH + bx; pitch = WIN0_PITCH; }
+    else if (shape == 1) { wp = w.win + q * WIN1_STRIDE + ((by & 1) * 4 + half * 2) * WIN1_PITCH + (bx & 1); pitch = WIN1_PITCH; }
+    else { wp = w.win + b * 30 + half * 2 * 3; pitch = 3; }
+    const McSel sel = mc_select(mv_x(v) & 3, mv_y(v) & 3);
+    uint32_t pred[2];
+    if (wn == 0) mc_patch<COMPAT, 0, false>(wp, pitch, 0, sel, pred, wn);
+    else if (!(wn & NEED_J)) mc_patch<COMPAT, 1, false>(wp, pitch, 0, sel, pred, wn);
+    else mc_patch<COMPAT, 2, false>(wp, pitch, 0, sel, pred, wn);
+    const int row = by * 4 + half * 2, col = bx * 4;
+    uint8_t* yp = pd.y + (size_t)(m.mby * 16 + row) * g.pitch_y + m.mbx * 16 + col;
+    uint32_t exc = 0;
+    uint32_t chroma = 0;
+    if (m.active) {          // warp-uniform
+        // luma: block b (raster) = luma4x4BlkIdx blk_raster(b); its slot holds rows 0..3, this lane takes rows 2 half, 2 half + 1
+        const int bi = blk_raster(b);
+        if ((m.active >> bi) & 1u) {
+            const uint4 r = w.slots[(m.slot0 + popc32(m.active & ((1u << bi) - 1u))) * 2 + half];
+            exc += add_residual_words<COMPAT>(pred[0], r.x, r.y, pred[0]);
+            exc += add_residual_words<COMPAT>(pred[1], r.z, r.w, pred[1]);
+        }
+        // chroma: lane -> plane (lane >> 4), row cy, 4 samples at cx0: chroma block (cy >> 2) * 2 + (cx0 >> 2), its row cy & 3
+        const int plane = lane >> 4, l = lane & 15, cy = l >> 1, ci = 16 + plane * 4 + (cy >> 2) * 2 + (l & 1);
+        if ((m.active >> ci) & 1u) {
+            const uint2* rows = reinterpret_cast<const uint2*>(&w.slots[(m.slot0 + popc32(m.active & ((1u << ci) - 1u))) * 2]);
+            const uint2 r = rows[cy & 3];
+            chroma = prmt(r.x, r.y, 0x6420);
+        }
+    }
+    *reinterpret_cast<uint32_t*>(yp) = pred[0];
+    *reinterpret_cast<uint32_t*>(yp + g.pitch_y) = pred[1];
+    {
+        const int plane = lane >> 4, l = lane & 15, cy = l >> 1, cx0 = (l & 1) * 4;
+        uint8_t* cbase = (plane ? pd.v : pd.u) + (size_t)(m.mby * 8 + cy) * g.pitch_c + m.mbx * 8 + cx0;
+        *reinterpret_cast<uint32_t*>(cbase) = chroma;
+    }
+    report_excursions(pd, a, exc);
+}
+
+// K1+K3 for the inter macroblocks among a0 .. a0 + GRP_MBS - 1.  `before_samples` runs once, after the residual of the
+// first part and before the first reference sample is read (the kernel awaits its predecessor there).
+template <bool COMPAT, class Exec, class Before>
+HD void seq_inter_group(Exec& ex, GroupWork& w, const PicDesc& pd, const Geometry& g, int a0, int n_mbs, Before before_samples)
+{
+    ex([&](int lane) { phase_grp_load(w, pd, g, a0, n_mbs, lane); });
+    int first = 0;
+    while (first < GRP_MBS) {
+        PerLane<int> te, ni;
+        ex([&](int lane) { phase_grp_items(w, first, lane, te(lane), ni(lane)); });
+        const int take_end = te(0), n_items = ni(0);      // macroblocks [first, take_end) of the group are in this part, with n_items active blocks
+        for (int base = 0; base < n_items; base += 32) ex([&](int lane) { phase_grp_residual<COMPAT>(w, pd, base + lane, n_items); });
+        if (first == 0) before_samples();
+        for (int i = first; i < take_end; i++) {
+            const GrpMb m = w.mb[i];
+            if (is_intra(m.h.mb_class)) continue;       // warp-uniform
+            const int a = a0 + i;
+            PerLane<uint32_t> mv_own;
+            ex([&](int lane) {
+                mv_own(lane) = grp_load_mv(pd, m, lane);
+                phase_grp_stage<COMPAT>(w, pd, g, m, lane, mv_own(lane));
+            });
+            ex([&](int lane) { phase_grp_compute<COMPAT>(w, pd, g, m, a, lane, mv_own(lane)); });
+            if (COMPAT && is_border_mb(g, m.mbx, m.mby))
+                ex([&](int lane) { pad_mb_luma_cold(pd.y, g.pitch_y, g.w_mbs, g.h_mbs, m.mbx, m.mby, lane); });
+        }
+        first = take_end;
+    }
+}
+
+}  // namespace h264r

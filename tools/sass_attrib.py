@@ -21,7 +21,7 @@ for (t, op), r in zip(tags, data):
     byline[t] += int(r[ie]); bys[t] += int(r[ss]); byop[op.split()[0].split('.')[0]] += int(r[ie])
 src = {}
 import os
-for f in ['h264r_core.cuh', 'h264r_kernels.cuh', 'h264r_intra.cuh', 'h264r_mc.cuh', 'h264r_seq.cuh']:
+for f in ['h264r_core.cuh', 'h264r_kernels.cuh', 'h264r_intra.cuh', 'h264r_mc.cuh', 'h264r_mcgrp.cuh', 'h264r_seq.cuh']:
     src[f] = open(os.path.join(os.path.dirname(__file__), '../videodecoder_b200/csrc/cuda', f)).read().split('\n')
 ts = sum(bys.values())
 byfile = collections.Counter()

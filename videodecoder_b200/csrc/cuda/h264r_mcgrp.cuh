@@ -27,8 +27,16 @@ constexpr int GRP_SLOTS = 64;       // residual blocks the working set holds; a 
 struct alignas(16) GrpMb {          // record of one macroblock of the group, written by its lane in G0
     h264r_mb_hdr h;
     uint32_t mv_off, blk_mask, blk_off, active;     // active: bit b = block b has a residual slot
-    int32_t mbx, mby, slot0, n_items;               // slot0: slot of its first active block (G1)
+    int32_t yoff, coff;                             // byte offset of the macroblock's first luma / chroma sample from the plane origin
+    uint32_t xy;                                    // mbx | mby << 16
+    uint32_t meta;                                  // GRP_* fields below
 };
+// GrpMb::meta: slot of the first active block (G1, bits 0-7), number of active blocks (8-15), window shape (16-17), on the picture's
+// border (18), inter macroblock inside the picture (19)
+constexpr uint32_t GRP_BORDER = 1u << 18, GRP_INTER = 1u << 19;
+HD int grp_slot0(uint32_t meta) { return (int)(meta & 255u); }
+HD int grp_n_items(uint32_t meta) { return (int)((meta >> 8) & 255u); }
+HD int grp_shape(uint32_t meta) { return (int)((meta >> 16) & 3u); }
 struct alignas(128) GroupWork {
     uint32_t win[512];              // staged windows, layouts of h264r_mc.cuh (phase_inter_stage)
     uint4 slots[GRP_SLOTS * 2];     // residual blocks: 16 int16 each, raster 4x4
@@ -53,9 +61,10 @@ HD void phase_grp_load(GroupWork& w, const PicDesc& pd, const Geometry& g, int a
     const int a = a0 + lane;
     if (a >= n_mbs) {
         const int4 z = int4{0, 0, 0, 0};
-        m.h = *reinterpret_cast<const h264r_mb_hdr*>(&z);        // mb_class 0: an intra class
+        m.h = *reinterpret_cast<const h264r_mb_hdr*>(&z);
         m.mv_off = m.blk_mask = m.blk_off = m.active = 0u;
-        m.mbx = m.mby = m.slot0 = m.n_items = 0;
+        m.yoff = m.coff = 0;
+        m.xy = m.meta = 0u;
         w.mb[lane] = m;
         return;
     }
@@ -64,7 +73,7 @@ HD void phase_grp_load(GroupWork& w, const PicDesc& pd, const Geometry& g, int a
     m.mv_off = H264R_LDG(pd.mv_off + a);
     m.blk_mask = H264R_LDG(pd.blk_mask + a);
     m.blk_off = H264R_LDG(pd.blk_off + a);
-    uint32_t active = 0u;
+    uint32_t active = 0u, meta = 0u;
     if (!is_intra(m.h.mb_class)) {
         const uint32_t cbp_l = m.h.cbp & 15u, cbp_c = (m.h.cbp >> 4) & 3u;
         active = m.blk_mask & cbp_luma_blocks(cbp_l);
@@ -72,11 +81,16 @@ HD void phase_grp_load(GroupWork& w, const PicDesc& pd, const Geometry& g, int a
             if (m.blk_mask & 0x0F0000u) active |= 0x0F0000u;
             if (m.blk_mask & 0xF00000u) active |= 0xF00000u;
         }
+        meta = GRP_INTER | ((uint32_t)inter_shape_by_type(m.h) << 16);
     }
+    int mbx, mby;
+    mb_xy(g, a, mbx, mby);
+    if (is_border_mb(g, mbx, mby)) meta |= GRP_BORDER;
     m.active = active;
-    m.n_items = popc32(active);
-    m.slot0 = 0;
-    mb_xy(g, a, m.mbx, m.mby);
+    m.meta = meta | ((uint32_t)popc32(active) << 8);
+    m.xy = (uint32_t)mbx | ((uint32_t)mby << 16);
+    m.yoff = mby * 16 * g.pitch_y + mbx * 16;
+    m.coff = mby * 8 * g.pitch_c + mbx * 8;
     w.mb[lane] = m;
 }
 
@@ -87,7 +101,7 @@ HD void phase_grp_items(GroupWork& w, int first, int lane, int& take_end_out, in
     int cum = 0, take_end = first, slot0 = 0;
 #pragma unroll
     for (int k = 0; k < GRP_MBS; k++) {
-        const int c = w.mb[k].n_items;
+        const int c = grp_n_items(w.mb[k].meta);
         if (k >= first && take_end == k && cum + c <= GRP_SLOTS) {
             if (k == lane) slot0 = cum;
             cum += c;
@@ -95,7 +109,7 @@ HD void phase_grp_items(GroupWork& w, int first, int lane, int& take_end_out, in
         }
     }
     if (lane >= first && lane < take_end) {
-        w.mb[lane].slot0 = slot0;
+        w.mb[lane].meta |= (uint32_t)slot0;
         uint32_t act = w.mb[lane].active;
         int s = slot0;
         while (act) {
@@ -201,27 +215,27 @@ template <bool COMPAT>
 HD void phase_grp_stage(GroupWork& w, const PicDesc& pd, const Geometry& g, const GrpMb& m, int lane, uint32_t v)
 {
     const h264r_mb_hdr& h = m.h;
-    const int shape = inter_shape_by_type(h);
-    const int W = g.w_mbs * 16, H = g.h_mbs * 16, mbx = m.mbx, mby = m.mby;
+    const int shape = grp_shape(m.meta);
+    const int W = g.w_mbs * 16, H = g.h_mbs * 16, x0 = (int)(m.xy & 0xffffu) * 16, y0 = (int)(m.xy >> 16) * 16;
 #if !defined(__CUDA_ARCH__)
     w.need[lane] = (uint8_t)mc_need(mv_x(v) & 3, mv_y(v) & 3);
 #endif
     if (shape == 0) {
         const uint8_t* ref = pd.ref_y[hdr_ref_idx(h, 0)];
-        const int xb = clip3(-19, W + 2, mbx * 16 + (mv_x(v) >> 2)), yb = clip3(-19, H + 3, mby * 16 + (mv_y(v) >> 2));
+        const int xb = clip3(-19, W + 2, x0 + (mv_x(v) >> 2)), yb = clip3(-19, H + 3, y0 + (mv_y(v) >> 2));
         stage_window<22, 6, 32, WIN0_PITCH>(w.win, ref, g.pitch_y, xb - 2, yb - 3, lane);
     } else if (shape == 1) {
         const int b = lane >> 1, bx = b & 3, by = b >> 2, q = (by >> 1) * 2 + (bx >> 1);
         const uint8_t* ref = pd.ref_y[hdr_ref_idx(h, q)];
-        const int xb = clip3(-11, W + 2, mbx * 16 + (q & 1) * 8 + (mv_x(v) >> 2)), yb = clip3(-11, H + 3, mby * 16 + (q >> 1) * 8 + (mv_y(v) >> 2));
+        const int xb = clip3(-11, W + 2, x0 + (q & 1) * 8 + (mv_x(v) >> 2)), yb = clip3(-11, H + 3, y0 + (q >> 1) * 8 + (mv_y(v) >> 2));
         stage_window<14, 4, 8, WIN1_PITCH>(w.win + q * WIN1_STRIDE, ref, g.pitch_y, xb - 2, yb - 3, ((by & 1) * 2 + (bx & 1)) * 2 + (lane & 1));
     } else {
         const int b = lane >> 1, bx = b & 3, by = b >> 2, q = (by >> 1) * 2 + (bx >> 1);
         const uint8_t* ref = pd.ref_y[hdr_ref_idx(h, q)];
-        int ys = mby * 16 + by * 4;
+        int ys = y0 + by * 4;
         // reference's source-row offset for 4x4 sub-partitions 2 and 3 (D8, h264/macroblock.cpp:786-789)
         if (COMPAT && h.mb_class == H264R_MB_P8x8 && ((h.sub_mb_type >> (2 * q)) & 3) == H264R_SUB_4x4 && (by & 1)) ys -= 3;
-        const int xb = clip3(-7, W + 2, mbx * 16 + bx * 4 + (mv_x(v) >> 2)), yb = clip3(-7, H + 3, ys + (mv_y(v) >> 2));
+        const int xb = clip3(-7, W + 2, x0 + bx * 4 + (mv_x(v) >> 2)), yb = clip3(-7, H + 3, ys + (mv_y(v) >> 2));
         stage_window<10, 3, 2, 3>(w.win + b * 30, ref, g.pitch_y, xb - 2, yb - 3, lane & 1);
     }
 }
@@ -245,7 +259,6 @@ template <bool COMPAT>
 HD void phase_grp_compute(GroupWork& w, const PicDesc& pd, const Geometry& g, const GrpMb& m, int a, int lane, uint32_t v)
 {
     static_assert(COMPAT, "the group path covers REF_COMPAT");
-    const h264r_mb_hdr& h = m.h;
     int wn;
 #if defined(__CUDA_ARCH__)
     wn = (int)__reduce_or_sync(0xffffffffu, (unsigned)mc_need(mv_x(v) & 3, mv_y(v) & 3));
@@ -259,7 +272,7 @@ HD void phase_grp_compute(GroupWork& w, const PicDesc& pd, const Geometry& g, co
     }
 #endif
     const int b = lane >> 1, half = lane & 1, bx = b & 3, by = b >> 2, q = (by >> 1) * 2 + (bx >> 1);
-    const int shape = inter_shape_by_type(h);
+    const int shape = grp_shape(m.meta);
     const uint32_t* wp;
     int pitch;
     if (shape == 0) { wp = w.win + (by * 4 + half * 2) * WIN0_PITCH + bx; pitch = WIN0_PITCH; }
@@ -271,21 +284,22 @@ HD void phase_grp_compute(GroupWork& w, const PicDesc& pd, const Geometry& g, co
     else if (!(wn & NEED_J)) mc_patch<COMPAT, 1, false>(wp, pitch, 0, sel, pred, wn);
     else mc_patch<COMPAT, 2, false>(wp, pitch, 0, sel, pred, wn);
     const int row = by * 4 + half * 2, col = bx * 4;
-    uint8_t* yp = pd.y + (size_t)(m.mby * 16 + row) * g.pitch_y + m.mbx * 16 + col;
+    uint8_t* yp = pd.y + (m.yoff + row * g.pitch_y + col);
     uint32_t exc = 0;
     uint32_t chroma = 0;
     if (m.active) {          // warp-uniform
+        const int slot0 = grp_slot0(m.meta);
         // luma: block b (raster) = luma4x4BlkIdx blk_raster(b); its slot holds rows 0..3, this lane takes rows 2 half, 2 half + 1
         const int bi = blk_raster(b);
         if ((m.active >> bi) & 1u) {
-            const uint4 r = w.slots[(m.slot0 + popc32(m.active & ((1u << bi) - 1u))) * 2 + half];
+            const uint4 r = w.slots[(slot0 + popc32(m.active & ((1u << bi) - 1u))) * 2 + half];
             exc += add_residual_words<COMPAT>(pred[0], r.x, r.y, pred[0]);
             exc += add_residual_words<COMPAT>(pred[1], r.z, r.w, pred[1]);
         }
         // chroma: lane -> plane (lane >> 4), row cy, 4 samples at cx0: chroma block (cy >> 2) * 2 + (cx0 >> 2), its row cy & 3
         const int plane = lane >> 4, l = lane & 15, cy = l >> 1, ci = 16 + plane * 4 + (cy >> 2) * 2 + (l & 1);
         if ((m.active >> ci) & 1u) {
-            const uint2* rows = reinterpret_cast<const uint2*>(&w.slots[(m.slot0 + popc32(m.active & ((1u << ci) - 1u))) * 2]);
+            const uint2* rows = reinterpret_cast<const uint2*>(&w.slots[(slot0 + popc32(m.active & ((1u << ci) - 1u))) * 2]);
             const uint2 r = rows[cy & 3];
             chroma = prmt(r.x, r.y, 0x6420);
         }
@@ -294,7 +308,7 @@ HD void phase_grp_compute(GroupWork& w, const PicDesc& pd, const Geometry& g, co
     *reinterpret_cast<uint32_t*>(yp + g.pitch_y) = pred[1];
     {
         const int plane = lane >> 4, l = lane & 15, cy = l >> 1, cx0 = (l & 1) * 4;
-        uint8_t* cbase = (plane ? pd.v : pd.u) + (size_t)(m.mby * 8 + cy) * g.pitch_c + m.mbx * 8 + cx0;
+        uint8_t* cbase = (plane ? pd.v : pd.u) + (m.coff + cy * g.pitch_c + cx0);
         *reinterpret_cast<uint32_t*>(cbase) = chroma;
     }
     report_excursions(pd, a, exc);
@@ -314,8 +328,8 @@ HD void seq_inter_group(Exec& ex, GroupWork& w, const PicDesc& pd, const Geometr
         for (int base = 0; base < n_items; base += 32) ex([&](int lane) { phase_grp_residual<COMPAT>(w, pd, base + lane, n_items); });
         if (first == 0) before_samples();
         for (int i = first; i < take_end; i++) {
-            const GrpMb m = w.mb[i];
-            if (is_intra(m.h.mb_class)) continue;       // warp-uniform
+            const GrpMb& m = w.mb[i];
+            if (!(m.meta & GRP_INTER)) continue;       // warp-uniform: intra (the intra kernels reconstruct it afterwards) or beyond the picture
             const int a = a0 + i;
             PerLane<uint32_t> mv_own;
             ex([&](int lane) {
@@ -323,8 +337,8 @@ HD void seq_inter_group(Exec& ex, GroupWork& w, const PicDesc& pd, const Geometr
                 phase_grp_stage<COMPAT>(w, pd, g, m, lane, mv_own(lane));
             });
             ex([&](int lane) { phase_grp_compute<COMPAT>(w, pd, g, m, a, lane, mv_own(lane)); });
-            if (COMPAT && is_border_mb(g, m.mbx, m.mby))
-                ex([&](int lane) { pad_mb_luma_cold(pd.y, g.pitch_y, g.w_mbs, g.h_mbs, m.mbx, m.mby, lane); });
+            if (COMPAT && (m.meta & GRP_BORDER))
+                ex([&](int lane) { pad_mb_luma_cold(pd.y, g.pitch_y, g.w_mbs, g.h_mbs, (int)(m.xy & 0xffffu), (int)(m.xy >> 16), lane); });
         }
         first = take_end;
     }

@@ -118,7 +118,7 @@ def config_of(args):
                 args.res, w, h, args.gop_len, args.gop_len - 1, args.gops,
                 "REF_COMPAT (what the reference decoder computes: 4x4 transform, luma prediction, no deblock)" if compat
                 else "spec mode (chroma prediction + MC, 8x8 transform, Intra8x8, deblocking)", WORKLOAD_SEED),
-            "mode": args.mode, "layout": args.layout, "gops_per_gpu": args.gops, "gop_len": args.gop_len, "unique_gops": min(args.unique_gops, args.gops),
+            "mode": args.mode, "layout": args.layout, "headers": "8-byte (h264r_mb_hdr8)" if (args.hdr == "short" and args.layout == "packed") else "16-byte", "gops_per_gpu": args.gops, "gop_len": args.gop_len, "unique_gops": min(args.unique_gops, args.gops),
             "sharding": "one GOP set per rank, no data-path collective",
             "l2_policy": "the syntax of a step exceeds the 126 MB L2 and is re-uploaded between timed steps"}
 
@@ -324,7 +324,7 @@ def measure(a, rank, world, local, dist, torch, extras=True):
             for i, p in enumerate(gops[g % U]):
                 mask, blocks = packed_src[g % U][i]
                 pb = eng.picture_buf(max(1, blocks.shape[0]))
-                pb.fill(p["hdr"], p["mv"], mask, blocks, mv_partition=True)
+                pb.fill(p["hdr"], p["mv"], mask, blocks, mv_partition=True, short_hdr=a.hdr == "short")
                 if g < U:
                     coded_blocks += int(blocks.shape[0])
                     level_stats[0] += int((blocks != 0).sum())
@@ -359,7 +359,7 @@ def measure(a, rank, world, local, dist, torch, extras=True):
         for i in range(F):
             hb, mb, cb, kb = pinned[g if packed else g % U][i]
             if packed:
-                h2d += upload_fixed + max(0, hb.n_mvs) * 4 + hb.n_blocks * {2: 32, 1: 16, 3: 8}[hb.c.level_bytes]
+                h2d += (hb.c.blocks - hb.c.mv_end) + max(0, hb.n_mvs) * 4 + hb.n_blocks * {2: 32, 1: 16, 3: 8}[hb.c.level_bytes]
             else:
                 h2d += hb.nbytes + cb.nbytes + (mb.nbytes if mb else 0)
     all_ids = list(range(G * F))
@@ -592,7 +592,7 @@ def config4(rank, world, local, dist, torch):
         for i, p in enumerate(gop):
             mask, blocks = pack.pack_blocks(p["coeff"])
             pb = eng.picture_buf(max(1, blocks.shape[0]))
-            pb.fill(p["hdr"], p["mv"], mask, blocks, mv_partition=True)
+            pb.fill(p["hdr"], p["mv"], mask, blocks, mv_partition=True, short_hdr=True)
             pp = abi.PicParams.from_buffer_copy(p["pp"])
             for r in range(pp.num_ref_idx_l0):
                 pp.ref_list0[r] = k * F + p["pp"].ref_list0[r]
@@ -657,6 +657,7 @@ def main():
     ap.add_argument("--config4", action="store_true", help="also run BASELINE config 4 (20 distinct GOPs, GOP g on rank g mod N); default at N > 1")
     ap.add_argument("--layout", default="packed", choices=["packed", "dense"],
                     help="coefficient transport: h264r_submit_mbs_packed (present blocks only) or h264r_submit_mbs (768 B per macroblock)")
+    ap.add_argument("--hdr", default="short", choices=["short", "long"], help="picture buffers with 8-byte (h264r_mb_hdr8) or 16-byte headers")
     ap.add_argument("--p-block", type=float, default=None, help="density sweep: share of coded 4x4 blocks inside a coded 8x8 (default 0.45)")
     ap.add_argument("--max-amp", type=float, default=None, help="density sweep: residual amplitude (default 10)")
     args = ap.parse_args()

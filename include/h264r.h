@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define H264R_ABI_VERSION 4
+#define H264R_ABI_VERSION 5
 
 /* ---- status codes ---------------------------------------------------------------------- */
 #define H264R_OK            0
@@ -106,6 +106,14 @@ typedef struct h264r_mb_hdr {
         int8_t  ref_idx[8];   /* P: ref_idx_l0 per 8x8 quadrant in [0..3] (index into ref_list0) */
     } u;
 } h264r_mb_hdr;
+
+/* The same record in 8 bytes, for picture buffers (h264r_picture_buf.hdr_bytes = 8): half the header bytes on the wire; the
+ * engine expands it on the device (k_blk_scan) into the 16-byte record its kernels read.
+ *   w0: bits 0-2 mb_class, 3-8 flags, 9-12 intra_modes, 13-18 qp_y, 19-24 qp_cb, 25-30 qp_cr
+ *   w1: bits 0-5 cbp, 6-13 sub_mb_type, 14-29 ref_idx[0..3], 4 bits each
+ * The prediction modes of an intra macroblock (u.pred4x4, 8 bytes) travel as the FIRST 8-byte unit of the macroblock's
+ * coefficient blocks, in front of the units its blk_mask announces. */
+typedef struct h264r_mb_hdr8 { uint32_t w0, w1; } h264r_mb_hdr8;
 
 /* Motion vectors: int16 (x, y) in quarter-sample units, one pair per 4x4 luma block in RASTER
  * order inside the macroblock (block b = 4*(y/4) + x/4), 64 bytes per MB; the final vectors
@@ -226,9 +234,18 @@ typedef struct h264r_picture_buf {
                                    _INT8, two units each.  n_blocks of h264r_submit_picture counts UNITS.  A quarter of the
                                    _INT16 bytes at two levels per block                                                   */
     void*         base;       /* owned by the library       */
+    int32_t       hdr_bytes;  /* 16 (default): hdr[] holds h264r_mb_hdr records.  8: hdr8[] holds h264r_mb_hdr8 records, blk_mask and
+                                 blocks follow them directly (set by h264r_picture_buf_format(); H264R_LEVELS_COMPACT only) and every
+                                 intra macroblock's first unit holds its u.pred4x4 bytes (counted in n_blocks)                  */
+    int32_t       reserved_;
+    h264r_mb_hdr8* hdr8;      /* [n_mbs], hdr_bytes = 8     */
 } h264r_picture_buf;
 /* (include/h264r_writer.h: header-only helper that fills a picture buffer macroblock by macroblock in these formats.) */
 int  h264r_picture_buf_alloc(h264r_ctx* ctx, size_t max_blocks, h264r_picture_buf* out);
+/* Chooses the header format of a picture buffer before it is filled: hdr_bytes = 16 or 8.  Re-points hdr / hdr8 / blk_mask /
+ * blocks inside the buffer (with 8-byte headers the masks and the blocks move up so that the picture stays one contiguous
+ * range, 8 bytes per macroblock shorter). */
+int  h264r_picture_buf_format(h264r_ctx* ctx, h264r_picture_buf* buf, int hdr_bytes);
 void h264r_picture_buf_free(h264r_ctx* ctx, h264r_picture_buf* buf);
 /* n_mvs < 0: buf->mv holds the per-4x4 layout described above (16 vectors per macroblock).
  * n_mvs >= 0: n_mvs vectors in PARTITION order, stored backward from buf->mv_end -- per macroblock, in macroblock order, one vector per

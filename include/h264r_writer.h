@@ -42,6 +42,19 @@ static inline void h264r_writer_begin(h264r_writer* w, h264r_picture_buf* buf, i
     w->n_units = 0; w->n_mvs = 0; w->n_intra = 0;
 }
 
+/* the 8-byte form of a header (h264r_mb_hdr8 in h264r.h) */
+static inline h264r_mb_hdr8 h264r_hdr8_pack(const h264r_mb_hdr* h)
+{
+    h264r_mb_hdr8 s;
+    s.w0 = (uint32_t)(h->mb_class & 7u) | ((uint32_t)(h->flags & 63u) << 3) | ((uint32_t)(h->intra_modes & 15u) << 9) |
+           ((uint32_t)(h->qp_y & 63u) << 13) | ((uint32_t)(h->qp_cb & 63u) << 19) | ((uint32_t)(h->qp_cr & 63u) << 25);
+    s.w1 = (uint32_t)(h->cbp & 63u) | ((uint32_t)h->sub_mb_type << 6);
+    if (h->mb_class > H264R_MB_I16x16)
+        s.w1 |= ((uint32_t)(h->u.ref_idx[0] & 15) << 14) | ((uint32_t)(h->u.ref_idx[1] & 15) << 18) |
+                ((uint32_t)(h->u.ref_idx[2] & 15) << 22) | ((uint32_t)(h->u.ref_idx[3] & 15) << 26);
+    return s;
+}
+
 /* number of vectors the bitstream carries for a macroblock (mvd loops of macroblock::Parse, h264/macroblock.cpp:360-398) and
  * the first 4x4 block (raster) of each of them */
 static inline int h264r_writer_partitions(const h264r_mb_hdr* h, int first_block[16])
@@ -85,10 +98,13 @@ static inline int h264r_writer_mb(h264r_writer* w, const h264r_mb_hdr* hdr, cons
         }
         if (nz) { mask |= 1u << blk; n_present++; if (nz > 6) compact = 0; }
     }
+    if (b->hdr_bytes == 8 && w->level_fmt != H264R_LEVELS_COMPACT) return H264R_E_INVAL;
     if (w->level_fmt == H264R_LEVELS_COMPACT) {
         uint8_t* units = (uint8_t*)b->blocks;
-        const size_t need = (size_t)n_present * (compact ? 1 : 2);
+        const int ext = b->hdr_bytes == 8 && hdr->mb_class <= H264R_MB_I16x16;      /* prediction modes in front of the blocks */
+        const size_t need = (size_t)n_present * (compact ? 1 : 2) + (size_t)ext;
         if (w->n_units + need > b->max_blocks * 4) return H264R_E_CAPACITY;
+        if (ext) { memcpy(units + w->n_units * 8, hdr->u.pred4x4, 8); w->n_units += 1; }
         for (blk = 0; blk < 24; blk++) {
             uint8_t* u = units + w->n_units * 8;
             const int16_t* c = coeff + blk * 16;
@@ -110,7 +126,7 @@ static inline int h264r_writer_mb(h264r_writer* w, const h264r_mb_hdr* hdr, cons
         for (blk = 0; blk < 24; blk++)
             if ((mask >> blk) & 1u) { memcpy(b->blocks + w->n_units * 16, coeff + blk * 16, 32); w->n_units++; }
     }
-    b->hdr[w->next_mb] = *hdr;
+    if (b->hdr_bytes == 8) b->hdr8[w->next_mb] = h264r_hdr8_pack(hdr); else b->hdr[w->next_mb] = *hdr;
     b->blk_mask[w->next_mb] = mask;
     n_part = mv ? h264r_writer_partitions(hdr, part) : 0;
     for (k = 0; k < n_part; k++) {             /* vector i of the picture at mv_end[-2(i+1)], mv_end[-2(i+1)+1] */

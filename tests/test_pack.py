@@ -54,3 +54,98 @@ def test_pack_compact_empty_picture():
     mask = np.zeros(10, dtype=np.uint32)
     cmask, units = pack.pack_compact(mask, np.zeros((0, 16), dtype=np.int16))
     assert units.shape == (0, 8) and not cmask.any()
+
+
+_WRITER_PROG = r'''
+#include <stdio.h>
+#include <stdlib.h>
+#include "h264r_writer.h"
+/* reads n, then hdr[n] (16 B), mv[n][32] int16, coeff[n][384] int16 from stdin-named file; runs the writer with 8-byte headers on a
+   plain host buffer; writes n_units, n_mvs, n_intra, hdr8[n], mask[n], units, mvs */
+int main(int argc, char** argv)
+{
+    FILE* f = fopen(argv[1], "rb"); FILE* o = fopen(argv[2], "wb");
+    int n; if (fread(&n, 4, 1, f) != 1) return 1;
+    h264r_mb_hdr* hdr = malloc(sizeof(h264r_mb_hdr) * n); int16_t* mv = malloc(64 * n); int16_t* coeff = malloc(768 * n);
+    if (fread(hdr, 16, n, f) != (size_t)n || fread(mv, 64, n, f) != (size_t)n || fread(coeff, 768, n, f) != (size_t)n) return 1;
+    h264r_picture_buf b; memset(&b, 0, sizeof b);
+    b.hdr_bytes = 8; b.hdr8 = malloc(8 * n); b.blk_mask = malloc(4 * n); b.blocks = malloc(768 * n + 8 * n); b.max_blocks = 24 * (size_t)n + n;
+    int16_t* mvbuf = malloc(64 * n); b.mv = mvbuf; b.mv_end = mvbuf + 32 * n;
+    h264r_writer w; h264r_writer_begin(&w, &b, n, H264R_LEVELS_COMPACT);
+    for (int a = 0; a < n; a++) { int rc = h264r_writer_mb(&w, &hdr[a], hdr[a].mb_class >= H264R_MB_P16x16 ? mv + 32 * a : NULL, coeff + 384 * a); if (rc) return 10 - rc; }
+    size_t nu; long nm; if (h264r_writer_end(&w, &nu, &nm)) return 2;
+    int32_t head[3] = {(int32_t)nu, (int32_t)nm, b.n_intra};
+    fwrite(head, 4, 3, o); fwrite(b.hdr8, 8, n, o); fwrite(b.blk_mask, 4, n, o); fwrite(b.blocks, 8, nu, o); fwrite(b.mv_end - 2 * nm, 4, nm, o);
+    fclose(o); return 0;
+}
+'''
+
+
+def unpack_hdr8(h8):
+    """plain restatement of h264r_mb_hdr8 (include/h264r.h) -> 16-byte records (u.pred4x4 of intra macroblocks left zero)"""
+    out = np.zeros(h8.shape[0], dtype=abi.MB_HDR_DTYPE)
+    w0, w1 = h8[:, 0].astype(np.uint32), h8[:, 1].astype(np.uint32)
+    out["mb_class"] = w0 & 7
+    out["flags"] = (w0 >> 3) & 63
+    out["intra_modes"] = (w0 >> 9) & 15
+    out["qp_y"] = (w0 >> 13) & 63
+    out["qp_cb"] = (w0 >> 19) & 63
+    out["qp_cr"] = (w0 >> 25) & 63
+    out["cbp"] = w1 & 63
+    out["sub_mb_type"] = (w1 >> 6) & 255
+    u = out["u"].reshape(-1, 8)
+    inter = out["mb_class"] > abi.MB_I16x16
+    for q in range(4):
+        u[inter, q] = ((w1 >> (14 + 4 * q)) & 15)[inter]
+    return out
+
+
+def test_short_headers_c_writer_and_python_twin(tmp_path):
+    """8-byte headers: include/h264r_writer.h and pack.py (pack_hdr8, insert_intra_units) write the same bytes; the headers expand
+    back to the 16-byte records and the intra macroblocks' prediction modes sit in front of their blocks"""
+    import os
+    import subprocess
+    from videodecoder_b200 import workload
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    (tmp_path / "w.c").write_text(_WRITER_PROG)
+    r = subprocess.run(["gcc", "-std=c99", "-O1", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(tmp_path / "w.c"), "-o", str(tmp_path / "w")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rng = np.random.default_rng(77)
+    wm, hm = 9, 7
+    cfg = workload.WorkloadConfig(compat=False, num_ref=3, p_intra_in_p=0.2, p_i8x8=0.3, p_t8x8=0.3, p_sub=(0.25, 0.25, 0.25, 0.25), chroma_qp_offset=-3)
+    for p in workload.make_gop(rng, wm, hm, 3, cfg):
+        n = wm * hm
+        hdr = np.ascontiguousarray(p["hdr"]).view(abi.MB_HDR_DTYPE).reshape(-1)
+        mv = p["mv"] if p["mv"] is not None else np.zeros((n, 32), dtype=np.int16)
+        with open(tmp_path / "in.bin", "wb") as f:
+            f.write(np.int32(n).tobytes()); f.write(hdr.tobytes()); f.write(np.ascontiguousarray(mv, dtype=np.int16).tobytes())
+            f.write(np.ascontiguousarray(p["coeff"], dtype=np.int16).tobytes())
+        r = subprocess.run([str(tmp_path / "w"), str(tmp_path / "in.bin"), str(tmp_path / "out.bin")])
+        assert r.returncode == 0
+        raw = open(tmp_path / "out.bin", "rb").read()
+        nu, nm, ni = np.frombuffer(raw, dtype=np.int32, count=3)
+        off = 12
+        h8 = np.frombuffer(raw, dtype=np.uint32, count=2 * n, offset=off).reshape(n, 2); off += 8 * n
+        mask_c = np.frombuffer(raw, dtype=np.uint32, count=n, offset=off); off += 4 * n
+        units_c = np.frombuffer(raw, dtype=np.uint8, count=8 * nu, offset=off).reshape(-1, 8); off += 8 * nu
+        mvs_c = np.frombuffer(raw, dtype=np.int16, count=2 * nm, offset=off).reshape(-1, 2)
+        mask, blocks = pack.pack_blocks(p["coeff"])
+        cmask, units = pack.pack_compact(mask, blocks)
+        units = pack.insert_intra_units(hdr, cmask, units)
+        assert np.array_equal(pack.pack_hdr8(hdr), h8)
+        assert np.array_equal(cmask, mask_c) and np.array_equal(units, units_c)
+        assert ni == int((hdr["mb_class"] <= abi.MB_I16x16).sum()) and nu == units.shape[0]
+        if p["mv"] is not None:
+            assert np.array_equal(pack.pack_mvs_partition(hdr, p["mv"])[::-1], mvs_c)
+        # expansion: everything but the intra prediction modes comes back from the 8 bytes
+        back = unpack_hdr8(h8)
+        intra = hdr["mb_class"] <= abi.MB_I16x16
+        for k in ("mb_class", "flags", "intra_modes", "qp_y", "qp_cb", "qp_cr", "cbp"):
+            assert np.array_equal(back[k], hdr[k]), k
+        assert np.array_equal(back["sub_mb_type"][~intra], hdr["sub_mb_type"][~intra])
+        assert np.array_equal(back["u"].reshape(-1, 8)[~intra][:, :4], hdr["u"].reshape(-1, 8)[~intra][:, :4])
+        # the first unit of every intra macroblock = its u.pred4x4 bytes
+        per_mb = np.array([bin(int(m) & 0xFFFFFF).count("1") * (1 if int(m) & abi.BLK_COMPACT else 2) for m in cmask]) + intra
+        first = np.concatenate(([0], np.cumsum(per_mb)))[:-1]
+        assert np.array_equal(units_c[first[intra]], hdr["u"].reshape(-1, 8)[intra].view(np.uint8))

@@ -3,7 +3,7 @@ import ctypes
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 REF_COMPAT = 0x1
 DIGESTS = 0x2      # digest of every picture as part of its reconstruction
 

@@ -31,6 +31,7 @@ struct Pending {
     int layout;             // 0 = nothing submitted yet, 1 = dense (h264r_submit_mbs), 2 = packed (h264r_submit_mbs_packed)
     size_t n_blocks;        // packed: coefficient blocks stored so far
     bool mv_partition;      // vectors in partition order (h264r_submit_picture with n_mvs >= 0)
+    bool short_hdr;         // picture buffer with 8-byte headers (h264r_picture_buf.hdr_bytes = 8): k_blk_scan expands them
     int level_bytes;        // H264R_LEVELS_*: int16 levels (32-byte blocks); picture buffers only: int8 levels (16-byte blocks), compact (8-byte units)
     uint64_t seq;           // order of frame_end calls (= order of the uploads on the copy stream)
     bool early;             // flush: the upload had landed when the flush began (index structures made up front, nothing to wait for)
@@ -107,7 +108,9 @@ struct h264r_ctx {
     // arena slot = what the uploads carry, in this order: descriptor | hdr | blk_mask | mv | coefficient blocks;
     // then blk_off and mv_off (written by k_blk_scan, never uploaded)
     // then the residual scratch of the intra macroblocks (device only)
-    size_t slot_bytes = 0, off_desc = 0, off_hdr = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_mvoff = 0, off_coeff = 0, off_res = 0, off_nz = 0, off_dbrec = 0, off_ilist = 0, off_idone = 0, off_mbox = 0;
+    size_t slot_bytes = 0, off_desc = 0, off_hdr = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_mvoff = 0, off_coeff = 0, off_res = 0, off_nz = 0, off_dbrec = 0, off_ilist = 0, off_idone = 0, off_mbox = 0, off_hdr16 = 0;
+    // 8-byte headers: masks and blocks of the upload move up behind the shorter header array
+    size_t off_mask_s = 0, off_coeff_s = 0;
     uint32_t mbox_stamp = 0;                // launch number of k_deblock_rows (stamp of its hand-over records)
     int sparse_stamp = 0;                   // launch stamp of k_intra_list (intra_done words of older launches are smaller)
     // per-flush control block (descriptors + picture lists), pinned host mirror + device copy
@@ -184,12 +187,13 @@ void fill_desc(h264r_ctx* c, const Pending& p, PicDesc& pd)
 {
     memset(&pd, 0, sizeof(pd));
     uint8_t* s = c->slot_ptr(p.slot);
-    pd.hdr = reinterpret_cast<const h264r_mb_hdr*>(s + c->off_hdr);
+    pd.hdr = reinterpret_cast<const h264r_mb_hdr*>(s + (p.short_hdr ? c->off_hdr16 : c->off_hdr));
+    pd.hdr8 = p.short_hdr ? reinterpret_cast<const uint2*>(s + c->off_hdr) : nullptr;
     pd.mv = reinterpret_cast<const int16_t*>(s + (p.mv_partition ? c->off_desc : c->off_mv));
-    pd.coeff = reinterpret_cast<const int16_t*>(s + c->off_coeff);
+    pd.coeff = reinterpret_cast<const int16_t*>(s + (p.short_hdr ? c->off_coeff_s : c->off_coeff));
     pd.level_fmt = p.level_bytes;
     if (p.layout == 2) {
-        pd.blk_mask = reinterpret_cast<const uint32_t*>(s + c->off_mask);
+        pd.blk_mask = reinterpret_cast<const uint32_t*>(s + (p.short_hdr ? c->off_mask_s : c->off_mask));
         pd.blk_off = reinterpret_cast<const uint32_t*>(s + c->off_boff);
     } else { pd.blk_mask = c->d_dense_mask; pd.blk_off = c->d_dense_off; }
     pd.nzmask = reinterpret_cast<uint32_t*>(s + c->off_nz);
@@ -292,7 +296,10 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     c->off_ilist = c->off_dbrec + ((flags & H264R_REF_COMPAT) ? 0 : align_up((size_t)c->n_mbs * DBREC_BYTES, 256));
     c->off_idone = c->off_ilist + align_up((size_t)(c->n_mbs + 1) * 4, 256);
     c->off_mbox = c->off_idone + align_up((size_t)c->n_mbs * 4, 256);
-    c->slot_bytes = c->off_mbox + ((flags & H264R_REF_COMPAT) ? 0 : align_up((size_t)c->n_mbs * MBOX_WORDS * 4, 256));
+    c->off_hdr16 = c->off_mbox + ((flags & H264R_REF_COMPAT) ? 0 : align_up((size_t)c->n_mbs * MBOX_WORDS * 4, 256));      // device only: headers expanded from the 8-byte form
+    c->slot_bytes = c->off_hdr16 + align_up((size_t)c->n_mbs * sizeof(h264r_mb_hdr), 256);
+    c->off_mask_s = c->off_hdr + (size_t)c->n_mbs * sizeof(h264r_mb_hdr8);
+    c->off_coeff_s = align_up(c->off_mask_s + (size_t)c->n_mbs * 4, 16);
     c->ctrl_bytes = align_up((size_t)max_pending * sizeof(PicDesc), 256);      // descriptor table, one entry per arena slot
     auto cleanup = [&](int code) { h264r_destroy(c); return code; };
 #define CUC(call)                                                                                             \
@@ -598,6 +605,22 @@ int h264r_picture_buf_alloc(h264r_ctx* ctx, size_t max_blocks, h264r_picture_buf
     out->n_intra = -1;
     out->level_bytes = 2;
     out->base = b;
+    out->hdr_bytes = 16;
+    out->reserved_ = 0;
+    out->hdr8 = nullptr;
+    return H264R_OK;
+}
+
+int h264r_picture_buf_format(h264r_ctx* ctx, h264r_picture_buf* buf, int hdr_bytes)
+{
+    if (!ctx || !buf || !buf->base || (hdr_bytes != 16 && hdr_bytes != 8)) return fail(ctx, H264R_E_INVAL, "picture_buf_format: bad argument");
+    uint8_t* b = static_cast<uint8_t*>(buf->base);
+    const bool s8 = hdr_bytes == 8;
+    buf->hdr_bytes = hdr_bytes;
+    buf->hdr = reinterpret_cast<h264r_mb_hdr*>(b + ctx->off_hdr);
+    buf->hdr8 = s8 ? reinterpret_cast<h264r_mb_hdr8*>(b + ctx->off_hdr) : nullptr;
+    buf->blk_mask = reinterpret_cast<uint32_t*>(b + (s8 ? ctx->off_mask_s : ctx->off_mask));
+    buf->blocks = reinterpret_cast<int16_t*>(b + (s8 ? ctx->off_coeff_s : ctx->off_coeff));
     return H264R_OK;
 }
 
@@ -617,6 +640,9 @@ int h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* 
     Pending* p = find_pending(ctx, frame_id);
     if (!p || p->ended) return fail(ctx, H264R_E_STATE, "submit_picture: no open picture with this frame id");
     if (p->layout || p->n_submitted) return fail(ctx, H264R_E_STATE, "submit_picture: the picture already has macroblocks");
+    const bool short_hdr = buf->hdr_bytes == 8;
+    if (short_hdr && (buf->level_bytes != H264R_LEVELS_COMPACT || buf->hdr8 != reinterpret_cast<h264r_mb_hdr8*>(static_cast<uint8_t*>(buf->base) + ctx->off_hdr)))
+        return fail(ctx, H264R_E_INVAL, "submit_picture: 8-byte headers need H264R_LEVELS_COMPACT and a buffer formatted by h264r_picture_buf_format");
     if (buf->n_intra >= 0) {
         // the parser counted while parsing: no second pass over the headers
         if (buf->n_intra > ctx->n_mbs || (p->pp.slice_type != H264R_SLICE_P && buf->n_intra != ctx->n_mbs))
@@ -624,13 +650,13 @@ int h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* 
         p->n_intra = buf->n_intra;
         p->n_intra_claimed = buf->n_intra;
     } else {
-        const h264r_mb_hdr* hdr = buf->hdr;
         for (int i = 0; i < ctx->n_mbs; i++) {
-            uint8_t cls = hdr[i].mb_class;
+            const uint8_t cls = short_hdr ? (uint8_t)(buf->hdr8[i].w0 & 7u) : buf->hdr[i].mb_class;
+            const uint8_t mbf = short_hdr ? (uint8_t)((buf->hdr8[i].w0 >> 3) & 63u) : buf->hdr[i].flags;
             if (cls == 3 || cls > H264R_MB_P8x8) return fail(ctx, H264R_E_INVAL, "submit_picture: unknown mb_class");
             if (cls <= H264R_MB_I16x16) p->n_intra++;
             else if (p->pp.slice_type != H264R_SLICE_P) return fail(ctx, H264R_E_INVAL, "submit_picture: inter macroblock in an I picture");
-            if ((ctx->flags & H264R_REF_COMPAT) && (cls == H264R_MB_I8x8 || (hdr[i].flags & H264R_T8x8)))
+            if ((ctx->flags & H264R_REF_COMPAT) && (cls == H264R_MB_I8x8 || (mbf & H264R_T8x8)))
                 return fail(ctx, H264R_E_INVAL, "submit_picture: 8x8 transform is not part of REF_COMPAT (the reference has none)");
         }
     }
@@ -643,6 +669,7 @@ int h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* 
     p->n_blocks = n_blocks;
     p->n_submitted = ctx->n_mbs;
     p->mv_partition = n_mvs >= 0;
+    p->short_hdr = short_hdr;
     p->level_bytes = buf->level_bytes;
     // ONE transfer: the vectors present (backward from the descriptor), descriptor, headers, masks, the blocks present
     uint8_t* hb = static_cast<uint8_t*>(buf->base);
@@ -651,7 +678,7 @@ int h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* 
     const size_t mv_bytes = !is_p ? 0 : (n_mvs >= 0 ? (size_t)n_mvs * 4 : ctx->off_desc);      // per-4x4 layout: the whole area
     const size_t first = ctx->off_desc - mv_bytes;
     const size_t unit_bytes = buf->level_bytes == H264R_LEVELS_INT16 ? 32 : (buf->level_bytes == H264R_LEVELS_INT8 ? 16 : 8);
-    CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot) + first, hb + first, ctx->off_coeff + n_blocks * unit_bytes - first,
+    CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot) + first, hb + first, (short_hdr ? ctx->off_coeff_s : ctx->off_coeff) + n_blocks * unit_bytes - first,
                        cudaMemcpyHostToDevice, ctx->copy_stream));
     CU(cudaEventRecord(ctx->ev_copied[p->slot], ctx->copy_stream));
     p->seq = ++ctx->end_seq;

@@ -58,7 +58,8 @@ HD void mb_xy(const Geometry& g, int a, int& mbx, int& mby)
 
 // Everything a kernel needs to know about one picture of a wave (lives in device memory).
 struct PicDesc {
-    const h264r_mb_hdr* hdr;
+    const h264r_mb_hdr* hdr;   // 16-byte headers: uploaded, or expanded by k_blk_scan from hdr8
+    const uint2* hdr8;         // picture buffers with 8-byte headers (h264r_mb_hdr8), else null
     const int16_t* mv;         // motion vectors (x, y): per 4x4 block (16 per macroblock, forward from here) or per partition
                                // (stored BACKWARD from here: vector i at mv[-2(i+1)], see mv_off)
     const uint32_t* mv_off;    // null: per-4x4 layout; else per macroblock the index of its first vector, partition order

@@ -555,6 +555,7 @@ __global__ void __launch_bounds__(1024) k_blk_scan(const DescTable descs, const 
     uint32_t* off = pd.packed ? const_cast<uint32_t*>(pd.blk_off) : nullptr;
     uint32_t* mvoff = pd.packed ? const_cast<uint32_t*>(pd.mv_off) : nullptr;
     uint32_t* ilist = pd.intra_list;
+    const uint2* hdr8 = pd.hdr8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ unsigned long long wsum[32];
     __shared__ uint32_t isum[32];
@@ -575,8 +576,20 @@ __global__ void __launch_bounds__(1024) k_blk_scan(const DescTable descs, const 
                     const uint32_t mw = __ldg(mask + first + k);       // units: one per block, or two for the plain blocks of a compact picture
                     c[k] = (unsigned long long)(__popc(mw & 0xFFFFFFu) << ((pd.level_fmt == H264R_LEVELS_COMPACT && !(mw & H264R_BLK_COMPACT)) ? 1 : 0));
                 }
-                if (mvoff || ilist) {
-                    const uint2 hw = __ldg(reinterpret_cast<const uint2*>(pd.hdr + first + k));     // mb_class = byte 0, sub_mb_type = byte 7
+                if (mvoff || ilist || hdr8) {
+                    uint2 hw;
+                    if (hdr8) {
+                        // 8-byte header (h264r_mb_hdr8) -> the 16-byte record of the kernels; the prediction modes of an intra
+                        // macroblock follow below, once the scan knows where its units begin
+                        const uint2 s8 = __ldg(hdr8 + first + k);
+                        hw.x = (s8.x & 7u) | (((s8.x >> 3) & 63u) << 8) | (((s8.x >> 13) & 63u) << 16) | (((s8.x >> 19) & 63u) << 24);
+                        hw.y = ((s8.x >> 25) & 63u) | ((s8.y & 63u) << 8) | (((s8.x >> 9) & 15u) << 16) | (((s8.y >> 6) & 255u) << 24);
+                        const uint32_t r = s8.y >> 14;
+                        const uint32_t refs = (r & 15u) | (((r >> 4) & 15u) << 8) | (((r >> 8) & 15u) << 16) | (((r >> 12) & 15u) << 24);
+                        *reinterpret_cast<uint4*>(const_cast<h264r_mb_hdr*>(pd.hdr) + first + k) = uint4{hw.x, hw.y, is_intra((int)(hw.x & 255u)) ? 0u : refs, 0u};
+                        if (is_intra((int)(hw.x & 255u))) c[k] += 1ull;       // the unit with its prediction modes
+                    } else
+                        hw = __ldg(reinterpret_cast<const uint2*>(pd.hdr + first + k));     // mb_class = byte 0, sub_mb_type = byte 7
                     const int cls = (int)(hw.x & 255u);
                     if (mvoff) c[k] += (unsigned long long)mv_count(cls, (int)(hw.y >> 24)) << 32;
                     if (is_intra(cls)) intra_bits |= 1u << k;
@@ -617,7 +630,11 @@ __global__ void __launch_bounds__(1024) k_blk_scan(const DescTable descs, const 
 #pragma unroll
         for (int k = 0; k < 8; k++)
             if (first + k < n_mbs) {
-                if (off) off[first + k] = (uint32_t)run;
+                const bool ext = hdr8 && ((intra_bits >> k) & 1u);
+                if (off) off[first + k] = (uint32_t)run + (ext ? 1u : 0u);
+                if (ext)       // u.pred4x4 of the expanded header <- the macroblock's first unit
+                    *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(const_cast<h264r_mb_hdr*>(pd.hdr) + first + k) + 8) =
+                        __ldg(reinterpret_cast<const uint2*>(pd.coeff) + (uint32_t)run);
                 if (mvoff) mvoff[first + k] = (uint32_t)(run >> 32);
                 run += c[k];
                 if (ilist && ((intra_bits >> k) & 1u)) ilist[1 + irun++] = (uint32_t)(first + k);

@@ -12,7 +12,8 @@ from . import abi, build
 
 class PictureBufStruct(ctypes.Structure):
     _fields_ = [("hdr", ctypes.c_void_p), ("mv", ctypes.c_void_p), ("mv_end", ctypes.c_void_p), ("blk_mask", ctypes.c_void_p), ("blocks", ctypes.c_void_p),
-                ("max_blocks", ctypes.c_size_t), ("n_intra", ctypes.c_int32), ("level_bytes", ctypes.c_int32), ("base", ctypes.c_void_p)]
+                ("max_blocks", ctypes.c_size_t), ("n_intra", ctypes.c_int32), ("level_bytes", ctypes.c_int32), ("base", ctypes.c_void_p),
+                ("hdr_bytes", ctypes.c_int32), ("reserved_", ctypes.c_int32), ("hdr8", ctypes.c_void_p)]
 
 
 _lib = None
@@ -56,6 +57,7 @@ def load_library():
     L.h264r_set_lanes.argtypes = [vp, ci]
     L.h264r_picture_buf_alloc.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(PictureBufStruct)]
     L.h264r_picture_buf_free.argtypes = [vp, ctypes.POINTER(PictureBufStruct)]
+    L.h264r_picture_buf_format.argtypes = [vp, ctypes.POINTER(PictureBufStruct), ctypes.c_int]
     L.h264r_picture_buf_free.restype = None
     L.h264r_submit_picture.argtypes = [vp, ci, ctypes.POINTER(PictureBufStruct), ctypes.c_size_t, ctypes.c_long]
     L.h264r_frame_end.argtypes = [vp, ci]
@@ -88,7 +90,7 @@ def load_library():
 
 EXPORTS = [
     "h264r_abi_version", "h264r_last_error", "h264r_create", "h264r_destroy", "h264r_host_alloc", "h264r_host_free",
-    "h264r_frame_begin", "h264r_submit_mbs", "h264r_submit_mbs_packed", "h264r_wait_uploads", "h264r_set_lanes", "h264r_picture_buf_alloc", "h264r_picture_buf_free", "h264r_submit_picture", "h264r_frame_end", "h264r_frame_abort", "h264r_device_status", "h264r_flush", "h264r_sync", "h264r_read_planes",
+    "h264r_frame_begin", "h264r_submit_mbs", "h264r_submit_mbs_packed", "h264r_wait_uploads", "h264r_set_lanes", "h264r_picture_buf_alloc", "h264r_picture_buf_free", "h264r_picture_buf_format", "h264r_submit_picture", "h264r_frame_end", "h264r_frame_abort", "h264r_device_status", "h264r_flush", "h264r_sync", "h264r_read_planes",
     "h264r_frame_layout", "h264r_read_frame_async", "h264r_wait_readbacks",
     "h264r_frame_digest", "h264r_frame_digests", "h264r_range_excursions", "h264r_excursion_map",
     "h264r_residual_mbs", "h264r_release", "h264r_last_flush_stats", "h264r_set_profiling",
@@ -138,20 +140,42 @@ class PictureBuf:
             dt = np.dtype(dtype)
             buf = (ctypes.c_uint8 * (count * dt.itemsize)).from_address(ptr)
             return np.frombuffer(buf, dtype=dt, count=count)
-        self.hdr = view(self.c.hdr, abi.MB_HDR_DTYPE, n)
+        self._view = view
         self.mv = view(self.c.mv, np.int16, n * 32).reshape(n, 32)
         self.mv_tail = view(self.c.mv_end - n * 64, np.int16, n * 32).reshape(-1, 2)     # ends at mv_end: partition-order stream
-        self.blk_mask = view(self.c.blk_mask, np.uint32, n)
-        self.blocks = view(self.c.blocks, np.int16, int(self.c.max_blocks) * 16).reshape(-1, 16)
+        self._map()
         self.n_blocks = 0
         self.n_mvs = -1
 
-    def fill(self, hdr, mv, blk_mask, blocks, mv_partition=False, level8=None, compact=None):
+    def _map(self):
+        n = self.engine.n_mbs
+        self.hdr = self._view(self.c.hdr, abi.MB_HDR_DTYPE, n)
+        self.hdr8 = self._view(self.c.hdr8, np.uint32, n * 2).reshape(n, 2) if self.c.hdr8 else None
+        self.blk_mask = self._view(self.c.blk_mask, np.uint32, n)
+        self.blocks = self._view(self.c.blocks, np.int16, int(self.c.max_blocks) * 16).reshape(-1, 16)
+
+    def set_header_bytes(self, hdr_bytes):
+        """16: h264r_mb_hdr records; 8: h264r_mb_hdr8 (masks and blocks move up behind them; compact levels only)"""
+        if self.c.hdr_bytes != hdr_bytes:
+            self.engine._check(self.engine.L.h264r_picture_buf_format(self.engine.ctx, ctypes.byref(self.c), hdr_bytes))
+            self._map()
+
+    def fill(self, hdr, mv, blk_mask, blocks, mv_partition=False, level8=None, compact=None, short_hdr=False):
         """mv: per-4x4 vectors (n, 32); mv_partition: store them in partition order (pack.pack_mvs_partition).
         level8 / compact: level storage (None: the narrowest that holds the picture -- H264R_LEVELS_COMPACT when every
-        level fits int8, else int16)"""
+        level fits int8, else int16).  short_hdr: 8-byte headers when the levels go compact (else the 16-byte ones)"""
         from . import pack
-        self.hdr[:] = np.ascontiguousarray(hdr).view(abi.MB_HDR_DTYPE).reshape(-1)
+        blocks = np.asarray(blocks)
+        if level8 is None:
+            level8 = blocks.shape[0] > 0 and int(blocks.min()) >= -128 and int(blocks.max()) <= 127
+        if compact is None:
+            compact = level8
+        short_hdr = bool(short_hdr and level8 and compact)
+        self.set_header_bytes(8 if short_hdr else 16)
+        if short_hdr:
+            self.hdr8[:] = pack.pack_hdr8(hdr)
+        else:
+            self.hdr[:] = np.ascontiguousarray(hdr).view(abi.MB_HDR_DTYPE).reshape(-1)
         self.n_mvs = -1
         if mv is not None:
             if mv_partition:
@@ -163,12 +187,10 @@ class PictureBuf:
                 self.mv[:] = mv
         self.blk_mask[:] = blk_mask
         self.n_blocks = int(blocks.shape[0])
-        if level8 is None:
-            level8 = self.n_blocks > 0 and int(blocks.min()) >= -128 and int(blocks.max()) <= 127
-        if compact is None:
-            compact = level8
         if level8 and compact:      # 8-byte units: significance map + levels where a macroblock's blocks are sparse
             mask, units = pack.pack_compact(blk_mask, blocks)
+            if short_hdr:
+                units = pack.insert_intra_units(hdr, mask, units)
             self.blk_mask[:] = mask
             self.n_blocks = int(units.shape[0])       # what h264r_submit_picture is told: units
             self.blocks.view(np.uint8).reshape(-1, 8)[:self.n_blocks] = units
@@ -179,11 +201,11 @@ class PictureBuf:
         else:
             self.blocks[:self.n_blocks] = blocks
             self.c.level_bytes = abi.LEVELS_INT16
-        self.c.n_intra = int((self.hdr["mb_class"] <= abi.MB_I16x16).sum())       # a parser counts this as it goes
+        self.c.n_intra = int((np.ascontiguousarray(hdr).view(abi.MB_HDR_DTYPE).reshape(-1)["mb_class"] <= abi.MB_I16x16).sum())       # a parser counts this as it goes
 
     def free(self):
         if self.c.base:
-            self.hdr = self.mv = self.mv_tail = self.blk_mask = self.blocks = None
+            self.hdr = self.hdr8 = self.mv = self.mv_tail = self.blk_mask = self.blocks = None
             self.engine.L.h264r_picture_buf_free(self.engine.ctx, ctypes.byref(self.c))
 
 

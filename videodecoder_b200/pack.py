@@ -218,6 +218,33 @@ def pack_compact(blk_mask, blocks):
     return mask, units
 
 
+def pack_hdr8(hdr):
+    """8-byte headers (h264r_mb_hdr8 of include/h264r.h) from 16-byte ones: [n, 2] uint32."""
+    h = np.ascontiguousarray(hdr).view(abi.MB_HDR_DTYPE).reshape(-1)
+    u32 = lambda a: a.astype(np.uint32)
+    w0 = (u32(h["mb_class"]) & 7) | ((u32(h["flags"]) & 63) << 3) | ((u32(h["intra_modes"]) & 15) << 9) | \
+         ((u32(h["qp_y"]) & 63) << 13) | ((u32(h["qp_cb"]) & 63) << 19) | ((u32(h["qp_cr"]) & 63) << 25)
+    w1 = (u32(h["cbp"]) & 63) | (u32(h["sub_mb_type"]) << 6)
+    u = h["u"].reshape(-1, 8)
+    refs = ((u32(u[:, 0]) & 15) << 14) | ((u32(u[:, 1]) & 15) << 18) | ((u32(u[:, 2]) & 15) << 22) | ((u32(u[:, 3]) & 15) << 26)
+    w1 = np.where(h["mb_class"] > abi.MB_I16x16, w1 | refs, w1)
+    return np.stack([w0, w1], axis=1).astype(np.uint32)
+
+
+def insert_intra_units(hdr, mask, units):
+    """8-byte headers: every intra macroblock's u.pred4x4 bytes become the first unit of its blocks.  mask / units as
+    returned by pack_compact; returns the unit stream with the extra units inserted."""
+    h = np.ascontiguousarray(hdr).view(abi.MB_HDR_DTYPE).reshape(-1)
+    mask = np.asarray(mask, dtype=np.uint32)
+    per_mb = np.unpackbits((mask & 0xFFFFFF).view(np.uint8).reshape(-1, 4), axis=1).sum(axis=1).astype(np.int64)
+    per_mb = per_mb * np.where((mask >> 24) & 1, 1, 2)
+    first = np.concatenate(([0], np.cumsum(per_mb)))[:-1]
+    intra = np.flatnonzero(h["mb_class"] <= abi.MB_I16x16)
+    if intra.size == 0:
+        return units
+    return np.insert(units, first[intra], h["u"].reshape(-1, 8)[intra].view(np.uint8), axis=0)
+
+
 _ZZ8 = np.array([0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
                  35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63])
 

@@ -246,7 +246,14 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
     for (int a = 0; a < n; a++) {
         h264r_mb_hdr h = load_hdr(pd, a);
         if (is_intra(h.mb_class)) continue;
-        if (compat) seq_inter_any<true, false>(ex, ww, pd, g, h, a); else seq_inter_any<false, false>(ex, ww, pd, g, h, a);
+        if (compat) seq_inter_any<true, false>(ex, ww, pd, g, h, a);
+        else if (flags & 0x08000000u) {
+            // test switch bit 27: the three spec-mode parts of k_inter (luma without / with the 8x8 transform, chroma), one after the other
+            const MbPre pre = load_pre(pd, a);
+            seq_inter_any<false, false, false, PART_LUMA4>(ex, ww, pd, g, h, a, pre);
+            seq_inter_any<false, false, false, PART_LUMA8>(ex, ww, pd, g, h, a, pre);
+            seq_inter_any<false, false, false, PART_CHROMA>(ex, ww, pd, g, h, a, pre);
+        } else seq_inter_any<false, false>(ex, ww, pd, g, h, a);
     }
     // as on the device: the flat kernels leave the residual of the intra macroblocks in the picture's scratch
     std::vector<int16_t> scratch((size_t)n * 384);

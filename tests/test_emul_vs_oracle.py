@@ -30,7 +30,8 @@ def test_gop(built, compat, seed, w, h):
 
 
 @pytest.mark.parametrize("compat", [True, False])
-@pytest.mark.parametrize("variant", [emul.PACKED, emul.PACKED | emul.COMPACT, emul.PACKED | emul.COMPACT | emul.GENERIC_INTRA, emul.GENERIC_INTRA])
+@pytest.mark.parametrize("variant", [emul.PACKED, emul.PACKED | emul.COMPACT, emul.PACKED | emul.COMPACT | emul.GENERIC_INTRA, emul.GENERIC_INTRA,
+                                     emul.PACKED | emul.COMPACT | emul.PARTS, emul.PARTS])
 def test_gop_variants(built, compat, variant):
     """packed coefficient storage (what h264r_submit_mbs_packed delivers) and the generic intra phases give the
     same pictures as the default paths"""

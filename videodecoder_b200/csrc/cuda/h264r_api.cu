@@ -61,6 +61,7 @@ struct h264r_ctx {
     int digest_every = 1;                   // K5 launches cover this many waves of a flush (H264R_DIGEST_EVERY; measured: 1 is best)
     bool lean_inter = true;                 // k_inter<LEAN> for pictures that qualify (H264R_LEAN=0: the generic instantiation)
     bool pdl = true;                        // programmatic dependent launch of the P-wave kernels (H264R_PDL=0: plain launches)
+    bool inter_parts = true;                // spec-mode lean launches as three kernels (H264R_INTER_PARTS=0: one)
     bool inter_group = true;                // k_inter_grp for REF_COMPAT launches of lean pictures (H264R_INTER_GROUP=0: k_inter<LEAN>)
     int inter_group_gens = 4;               // its grid = SMs x 32 x this (H264R_GROUP_GENS)
     int inter_generations = 8;              // k_inter grid = SMs x inter_ctas_per_sm x this: a few CTA generations balance the tail
@@ -321,6 +322,8 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
         if (e5 && atoi(e5) > 0) c->inter_generations = atoi(e5);
         const char* e7 = getenv("H264R_DIGEST_EVERY");
         if (e7 && atoi(e7) > 0) c->digest_every = atoi(e7);
+        const char* e12 = getenv("H264R_INTER_PARTS");
+        if (e12) c->inter_parts = atoi(e12) != 0;
         const char* e10 = getenv("H264R_INTER_GROUP");
         if (e10) c->inter_group = atoi(e10) != 0;
         const char* e11 = getenv("H264R_GROUP_GENS");
@@ -951,7 +954,14 @@ int h264r_flush(h264r_ctx* ctx)
                     launch_pdl(k_inter_grp<true>, dim3((unsigned)(groups < gcap ? groups : gcap), (unsigned)L.n), dim3(32), st, pdl, d_desc, L, ctx->g);
                 } else if (lean) {
                     if (compat) { if (tma) launch_pdl(k_inter<true, true, true>, grid, blk, st, pdl, d_desc, L, ctx->g); else launch_pdl(k_inter<true, false, true>, grid, blk, st, pdl, d_desc, L, ctx->g); }
-                    else { if (tma) launch_pdl(k_inter<false, true, true>, grid, blk, st, pdl, d_desc, L, ctx->g); else launch_pdl(k_inter<false, false, true>, grid, blk, st, pdl, d_desc, L, ctx->g); }
+                    else if (tma) launch_pdl(k_inter<false, true, true>, grid, blk, st, pdl, d_desc, L, ctx->g);
+                    else if (ctx->inter_parts) {
+                        // spec mode: three kernels that fit the instruction cache instead of one that does not (see PART in h264r_mc.cuh)
+                        launch_pdl(k_inter<false, false, true, PART_LUMA4>, grid, blk, st, pdl, d_desc, L, ctx->g);
+                        launch_pdl(k_inter<false, false, true, PART_LUMA8>, grid, blk, st, pdl, d_desc, L, ctx->g);
+                        launch_pdl(k_inter<false, false, true, PART_CHROMA>, grid, blk, st, pdl, d_desc, L, ctx->g);
+                        ctx->last_launches += 2;
+                    } else launch_pdl(k_inter<false, false, true>, grid, blk, st, pdl, d_desc, L, ctx->g);
                 } else {
                     if (compat) { if (tma) launch_pdl(k_inter<true, true, false>, grid, blk, st, pdl, d_desc, L, ctx->g); else launch_pdl(k_inter<true, false, false>, grid, blk, st, pdl, d_desc, L, ctx->g); }
                     else { if (tma) launch_pdl(k_inter<false, true, false>, grid, blk, st, pdl, d_desc, L, ctx->g); else launch_pdl(k_inter<false, false, false>, grid, blk, st, pdl, d_desc, L, ctx->g); }

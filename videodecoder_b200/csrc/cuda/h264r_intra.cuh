@@ -27,9 +27,9 @@ namespace h264r {
 // nz_flags (optional, 16 bytes): lane b < 16 records whether luma block b has a non-zero level, at its raster index.
 template <bool COMPAT, bool LEAN, bool INTER>
 HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane, uint8_t* nz_flags, bool chroma_only,
-                            const MbPre* pre)
+                            const MbPre* pre, bool luma_only)
 {
-    if (lane >= 24 || (chroma_only && lane < 16)) return;
+    if (lane >= 24 || (chroma_only && lane < 16) || (luma_only && lane >= 16)) return;
     const int fmt = LEAN ? H264R_LEVELS_COMPACT : pd.level_fmt;       // LEAN: see k_inter
     const BlkRef br = pre ? BlkRef{pre->blk_mask, pre->blk_off} : load_blkref(pd, a);
     const int cbp_l = h.cbp & 15, cbp_c = (h.cbp >> 4) & 3;

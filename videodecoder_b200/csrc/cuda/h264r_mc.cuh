@@ -296,7 +296,7 @@ HD void idct4_fast(const int c[16], const Dequant& q, bool dc_bypass, int r[16])
 // K1 for any 4x4-transform macroblock: h264r_intra.cuh
 template <bool COMPAT, bool LEAN = false, bool INTER = false>
 HD void phase_residual_fast(int16_t* res, const PicDesc& pd, const h264r_mb_hdr& h, int a, int lane, uint8_t* nz_flags = nullptr,
-                            bool chroma_only = false, const MbPre* pre = nullptr);
+                            bool chroma_only = false, const MbPre* pre = nullptr, bool luma_only = false);
 
 // ---- K1 with the 8x8 transform (ITU-T H.264 8.5.13, flat scaling lists; the reference has no 8x8 transform) ------------
 // LevelScale8x8 / 16 for position (i, j), qP % 6 = m: six classes of positions, one byte per class and m
@@ -731,7 +731,12 @@ HD uint32_t weight_packed(uint32_t pred, int logwd, int wgt, int off)
 
 // Phase M1: compute and store the macroblock (luma from the staged windows; chroma: COMPAT = residual
 // only, D4; spec = bilinear from the padded reference planes, ITU-T H.264 8.4.2.2.2).
-template <bool COMPAT, bool TMA, bool LEAN>
+// PART: which share of the macroblock this instantiation reconstructs -- 0 everything; 1 / 2 its luma (instantiations for the
+// macroblocks without / with the 8x8 transform differ only in the residual phases of seq_inter_mb_fast); 3 its chroma.  The parts
+// exist for spec mode, whose single instantiation is 60 KB of hot code against a 32 KB instruction cache (ncu: 12 of 22 stall
+// cycles per issue are "no instruction"): three launches of kernels that fit run faster than one that does not.
+constexpr int PART_ALL = 0, PART_LUMA4 = 1, PART_LUMA8 = 2, PART_CHROMA = 3;
+template <bool COMPAT, bool TMA, bool LEAN, int PART = PART_ALL>
 HD void phase_inter_compute(InterWork& w, TmaState& ts, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane, bool coded,
                             uint32_t mv_own)
 {
@@ -739,6 +744,8 @@ HD void phase_inter_compute(InterWork& w, TmaState& ts, const PicDesc& pd, const
     const bool weighted = LEAN ? false : pd.weighted_pred != 0;
     int mbx, mby;
     mb_xy(g, a, mbx, mby);
+    uint32_t exc = 0;
+    if (PART != PART_CHROMA) {
     // warp-wide union of the NEED bits
     int wn;
 #if defined(__CUDA_ARCH__)
@@ -796,15 +803,15 @@ HD void phase_inter_compute(InterWork& w, TmaState& ts, const PicDesc& pd, const
     }
     const int row = by * 4 + half * 2, col = bx * 4;
     uint8_t* yp = pd.y + (size_t)(mby * 16 + row) * g.pitch_y + mbx * 16 + col;
-    uint32_t exc = 0;
     if (coded) {
         exc += add_residual<COMPAT>(pred[0], &w.res[row * 16 + col], pred[0]);
         exc += add_residual<COMPAT>(pred[1], &w.res[(row + 1) * 16 + col], pred[1]);
     }
     *reinterpret_cast<uint32_t*>(yp) = pred[0];
     *reinterpret_cast<uint32_t*>(yp + g.pitch_y) = pred[1];
+    }
     // chroma: lane -> plane (lane >> 4), row (l >> 1), 4 samples
-    {
+    if (PART == PART_ALL || PART == PART_CHROMA) {
         int plane = lane >> 4, l = lane & 15, cy = l >> 1, cx0 = (l & 1) * 4;
         uint8_t* cbase = (plane ? pd.v : pd.u) + (size_t)(mby * 8 + cy) * g.pitch_c + mbx * 8 + cx0;
         uint32_t packed = 0;
@@ -848,23 +855,33 @@ HD void phase_inter_compute(InterWork& w, TmaState& ts, const PicDesc& pd, const
 
 // K1+K3 sequence for one inter macroblock (4x4 transform).  8x8-transform macroblocks take seq_inter_mb
 // of h264r_seq.cuh.
-template <bool COMPAT, bool TMA, bool LEAN, class Exec>
+template <bool COMPAT, bool TMA, bool LEAN, int PART = PART_ALL, class Exec>
 HD void seq_inter_mb_fast(Exec& ex, InterWork& w, TmaState& ts, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, const MbPre& pre)
 {
-    const bool coded = h.cbp != 0;
-    const bool t8 = !COMPAT && coded && (h.flags & H264R_T8x8);        // REF_COMPAT has no 8x8 transform
+    static_assert(PART == PART_ALL || !COMPAT, "the parts are spec-mode instantiations");
+    const bool t8flag = !COMPAT && h.cbp != 0 && (h.flags & H264R_T8x8);        // REF_COMPAT has no 8x8 transform
+    if (PART == PART_LUMA4 && t8flag) return;
+    if (PART == PART_LUMA8 && !t8flag) return;
+    // what "coded" means for the share at hand: any residual / luma residual / chroma residual
+    const bool coded = PART == PART_ALL ? h.cbp != 0 : (PART == PART_CHROMA ? (h.cbp >> 4) != 0 : (h.cbp & 15) != 0);
+    const bool t8 = PART == PART_CHROMA ? false : (PART == PART_LUMA8 ? coded : t8flag);       // (LUMA8 with cbp luma = 0: nothing to transform)
     PerLane<uint32_t> mv_own;
+    if (PART == PART_CHROMA) {
+        if (coded) ex([&](int lane) { phase_residual_fast<COMPAT, LEAN, true>(w.res, pd, h, a, lane, nullptr, true, &pre); });
+        ex([&](int lane) { phase_inter_compute<COMPAT, TMA, LEAN, PART>(w, ts, pd, g, h, a, lane, coded, 0u); });
+        return;
+    }
     ex([&](int lane) {
         if (t8) {
             phase_residual8_rows(w, pd, h, a, lane);
-            phase_residual_fast<COMPAT, LEAN, true>(w.res, pd, h, a, lane, nullptr, true, &pre);
-        } else if (coded) phase_residual_fast<COMPAT, LEAN, true>(w.res, pd, h, a, lane, (!COMPAT && pd.nzmask) ? w.nzf : nullptr, false, &pre);
+            if (PART == PART_ALL) phase_residual_fast<COMPAT, LEAN, true>(w.res, pd, h, a, lane, nullptr, true, &pre);
+        } else if (coded) phase_residual_fast<COMPAT, LEAN, true>(w.res, pd, h, a, lane, (!COMPAT && pd.nzmask) ? w.nzf : nullptr, false, &pre, PART != PART_ALL);
         phase_inter_stage<COMPAT, TMA, LEAN>(w, ts, pd, g, h, a, lane, mv_own(lane), pre);
     });
     if (t8) ex([&](int lane) { phase_residual8_cols(w, lane); });
     ex([&](int lane) {
         if (!COMPAT && pd.nzmask && lane == 0) pd.nzmask[a] = !coded ? 0u : (t8 ? nz_pack8(w.nzf) : nz_pack(w.nzf));
-        phase_inter_compute<COMPAT, TMA, LEAN>(w, ts, pd, g, h, a, lane, coded, mv_own(lane));
+        phase_inter_compute<COMPAT, TMA, LEAN, PART>(w, ts, pd, g, h, a, lane, coded, mv_own(lane));
     });
     if (COMPAT) {        // border macroblocks replicate their samples into the frame's border (see phase_pad_mb_luma)
         int mbx, mby;

@@ -81,10 +81,10 @@ struct WarpWork {
 };
 
 // K1 + K3 for any inter macroblock: fast path for the 4x4 transform, generic phases for the 8x8 transform.
-template <bool COMPAT, bool TMA, bool LEAN, class Exec>
+template <bool COMPAT, bool TMA, bool LEAN, int PART = PART_ALL, class Exec>
 HD void seq_inter_any(Exec& ex, WarpWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, const MbPre& pre)
 {
-    seq_inter_mb_fast<COMPAT, TMA, LEAN>(ex, w.in, w.tma, pd, g, h, a, pre);
+    seq_inter_mb_fast<COMPAT, TMA, LEAN, PART>(ex, w.in, w.tma, pd, g, h, a, pre);
 }
 template <bool COMPAT, bool TMA, class Exec>
 HD void seq_inter_any(Exec& ex, WarpWork& w, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a)

@@ -312,6 +312,7 @@ def measure(a, rank, world, local, dist, torch, extras=True):
     # digests of every frame are part of the job (GOP-sharded decoding compares them across ranks): K5 runs with each wave
     eng = engine.Engine(Wm, Hm, max_frames=G * F, flags=flags | abi.DIGESTS, device=local)
     packed = a.layout == "packed"
+    rings = None
     coded_blocks = 0
     level_stats = [0, 0]
     pinned = []
@@ -319,11 +320,13 @@ def measure(a, rank, world, local, dist, torch, extras=True):
     if packed:
         # one pinned picture buffer per picture of the step, in the engine's upload layout: what a host parser writes into
         packed_src = [[pack.pack_blocks(p["coeff"]) for p in g] for g in gops]
+        # one RING of picture buffers per round of access units (picture i of every GOP): a round travels as one strided DMA
+        rings = [eng.picture_ring(G, max(1, max(packed_src[u][i][1].shape[0] for u in range(U)))) for i in range(F)] if a.ring else None
         for g in range(G):
             frames = []
             for i, p in enumerate(gops[g % U]):
                 mask, blocks = packed_src[g % U][i]
-                pb = eng.picture_buf(max(1, blocks.shape[0]))
+                pb = rings[i][g] if rings else eng.picture_buf(max(1, blocks.shape[0]))
                 pb.fill(p["hdr"], p["mv"], mask, blocks, mv_partition=True, short_hdr=a.hdr == "short")
                 if g < U:
                     coded_blocks += int(blocks.shape[0])
@@ -353,19 +356,30 @@ def measure(a, rank, world, local, dist, torch, extras=True):
                 pp2.ref_list0[k] = g * F + gops[g % U][i]["pp"].ref_list0[k]
             pps.append(pp2)
     h2d = 0
-    # bytes of one picture-buffer transfer: descriptor + headers + vectors + masks (fixed) + the blocks present
-    upload_fixed = (pinned[0][0][0].c.blocks - pinned[0][0][0].c.mv_end) if packed else 0
-    for g in range(G):
-        for i in range(F):
+    # bytes of the transfers: a picture buffer travels from its first vector (they grow backward from the descriptor) to its last
+    # unit; a ring round as one strided DMA over the union of its pictures' ranges
+    def span(hb):
+        base = hb.c.base
+        return (hb.c.mv_end - base) - max(0, hb.n_mvs) * 4, (hb.c.blocks - base) + hb.n_blocks * {2: 32, 1: 16, 3: 8}[hb.c.level_bytes]
+    for i in range(F):
+        spans = []
+        for g in range(G):
             hb, mb, cb, kb = pinned[g if packed else g % U][i]
             if packed:
-                h2d += (hb.c.blocks - hb.c.mv_end) + max(0, hb.n_mvs) * 4 + hb.n_blocks * {2: 32, 1: 16, 3: 8}[hb.c.level_bytes]
+                spans.append(span(hb))
             else:
                 h2d += hb.nbytes + cb.nbytes + (mb.nbytes if mb else 0)
+        if packed and rings:
+            h2d += (max(e for _, e in spans) - min(f for f, _ in spans)) * G
+        elif packed:
+            h2d += sum(e - f for f, e in spans)
     all_ids = list(range(G * F))
 
     def submit_round(i):
         L, ctx = eng.L, eng.ctx
+        if packed and rings:
+            eng.submit_ring(rings[i], [g * F + i for g in range(G)], [pps[g * F + i] for g in range(G)])
+            return
         for g in range(G):
             fid = g * F + i
             hb, mb, cb, kb = pinned[g if packed else g % U][i]
@@ -658,6 +672,7 @@ def main():
     ap.add_argument("--layout", default="packed", choices=["packed", "dense"],
                     help="coefficient transport: h264r_submit_mbs_packed (present blocks only) or h264r_submit_mbs (768 B per macroblock)")
     ap.add_argument("--hdr", default="short", choices=["short", "long"], help="picture buffers with 8-byte (h264r_mb_hdr8) or 16-byte headers")
+    ap.add_argument("--no-ring", dest="ring", action="store_false", help="one pinned buffer and one DMA per picture instead of a ring and one strided DMA per round")
     ap.add_argument("--p-block", type=float, default=None, help="density sweep: share of coded 4x4 blocks inside a coded 8x8 (default 0.45)")
     ap.add_argument("--max-amp", type=float, default=None, help="density sweep: residual amplitude (default 10)")
     args = ap.parse_args()

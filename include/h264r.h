@@ -237,11 +237,15 @@ typedef struct h264r_picture_buf {
     int32_t       hdr_bytes;  /* 16 (default): hdr[] holds h264r_mb_hdr records.  8: hdr8[] holds h264r_mb_hdr8 records, blk_mask and
                                  blocks follow them directly (set by h264r_picture_buf_format(); H264R_LEVELS_COMPACT only) and every
                                  intra macroblock's first unit holds its u.pred4x4 bytes (counted in n_blocks)                  */
-    int32_t       reserved_;
+    int32_t       ring_index; /* 0: a buffer of its own; i + 1: member i of a ring (h264r_picture_ring_alloc)                       */
     h264r_mb_hdr8* hdr8;      /* [n_mbs], hdr_bytes = 8     */
 } h264r_picture_buf;
 /* (include/h264r_writer.h: header-only helper that fills a picture buffer macroblock by macroblock in these formats.) */
 int  h264r_picture_buf_alloc(h264r_ctx* ctx, size_t max_blocks, h264r_picture_buf* out);
+/* n picture buffers in ONE pinned allocation, at a constant stride: what a host that parses several streams round-robin fills
+ * per round.  h264r_submit_pictures() then ships consecutive members with one strided transfer (a round of half-megabyte pictures
+ * moves faster as one DMA than as sixteen).  h264r_picture_buf_free(&out[0]) frees the ring; freeing other members is a no-op. */
+int  h264r_picture_ring_alloc(h264r_ctx* ctx, int n, size_t max_blocks, h264r_picture_buf* out /* [n] */);
 /* Chooses the header format of a picture buffer before it is filled: hdr_bytes = 16 or 8.  Re-points hdr / hdr8 / blk_mask /
  * blocks inside the buffer (with 8-byte headers the masks and the blocks move up so that the picture stays one contiguous
  * range, 8 bytes per macroblock shorter). */
@@ -254,6 +258,12 @@ void h264r_picture_buf_free(h264r_ctx* ctx, h264r_picture_buf* buf);
  * macroblock::Parse, h264/macroblock.cpp:360-398).  The engine derives each macroblock's first vector from
  * mb_class / sub_mb_type on the device. */
 int  h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* buf, size_t n_blocks, long n_mvs);
+
+/* h264r_submit_picture for n pictures begun with h264r_frame_begin.  Pictures whose buffers are consecutive members of a ring and
+ * which were begun back to back (their syntax slots are then neighbours) travel together in one strided transfer; any other
+ * picture travels on its own, so the call is always equivalent to n h264r_submit_picture calls.  On an error at picture k the
+ * pictures before it are submitted and the code of picture k is returned. */
+int  h264r_submit_pictures(h264r_ctx* ctx, int n, const int* frame_ids, const h264r_picture_buf* bufs, const size_t* n_blocks, const long* n_mvs);
 
 /* Gives up a picture that was begun but not completed (a failed submit, a damaged slice): its syntax slot and its frame
  * slot are free again.  The reference has no counterpart (it exit()s). */

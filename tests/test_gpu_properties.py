@@ -417,3 +417,52 @@ def test_create_rejects_unsupported_width(built):
     with pytest.raises(engine.H264RError) as e:
         engine.Engine(513, 2, max_frames=1, flags=0)
     assert e.value.code == abi.E_INVAL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("short_hdr", [False, True])
+def test_ring_submit_equals_single_submits(built, short_hdr):
+    """h264r_picture_ring_alloc + h264r_submit_pictures: a round of pictures (one per GOP) shipped with one strided transfer gives
+    the digests of per-picture submits; members begun in another order than they lie in the ring (slots not consecutive) fall
+    back to single transfers and give the same"""
+    import ctypes
+    w, h, n_gops, n_pics = 9, 6, 5, 4
+    rng = np.random.default_rng(91)
+    cfg = workload.WorkloadConfig(compat=True, p_intra_in_p=0.1, num_ref=1)
+    gops = [workload.make_gop(rng, w, h, n_pics, cfg) for _ in range(n_gops)]
+    for g in gops:
+        sanitize_with_oracle(w, h, g)
+    ref, _, exc = run_engine(w, h, abi.REF_COMPAT, gops, transport="bufmv", flush="round")
+    assert exc == 0
+    for order in ("ring", "reversed"):
+        eng = engine.Engine(w, h, max_frames=n_gops * n_pics, flags=abi.REF_COMPAT)
+        rings = []
+        for i in range(n_pics):
+            packed = [pack.pack_blocks(g[i]["coeff"]) for g in gops]
+            ring = eng.picture_ring(n_gops, max(1, max(b.shape[0] for _, b in packed)))
+            fids, pps = [], []
+            for k, g in enumerate(gops):
+                p = g[i]
+                ring[k].fill(p["hdr"], p["mv"], packed[k][0], packed[k][1], mv_partition=True, short_hdr=short_hdr)
+                pp = abi.PicParams.from_buffer_copy(p["pp"])
+                for r in range(pp.num_ref_idx_l0):
+                    pp.ref_list0[r] = k * n_pics + p["pp"].ref_list0[r]
+                fids.append(k * n_pics + i); pps.append(pp)
+            if order == "ring":
+                eng.submit_ring(ring, fids, pps)
+            else:
+                for k in reversed(range(n_gops)):        # slots are handed out in begin order: the ring's members get descending slots
+                    eng.frame_begin(fids[k], pps[k])
+                ids = (ctypes.c_int * n_gops)(*fids)
+                nb = (ctypes.c_size_t * n_gops)(*[ring[k].n_blocks for k in range(n_gops)])
+                nm = (ctypes.c_long * n_gops)(*[ring[k].n_mvs for k in range(n_gops)])
+                eng._check(eng.L.h264r_submit_pictures(eng.ctx, n_gops, ids, ring.array, nb, nm))
+            rings.append(ring)
+            eng.flush()
+        eng.sync()
+        dig = eng.digests(list(range(n_gops * n_pics)))
+        assert eng.range_excursions() == 0
+        assert np.array_equal(dig, ref), order
+        for r in rings:
+            r.free()
+        eng.close()

@@ -609,8 +609,34 @@ int h264r_picture_buf_alloc(h264r_ctx* ctx, size_t max_blocks, h264r_picture_buf
     out->level_bytes = 2;
     out->base = b;
     out->hdr_bytes = 16;
-    out->reserved_ = 0;
+    out->ring_index = 0;
     out->hdr8 = nullptr;
+    return H264R_OK;
+}
+
+int h264r_picture_ring_alloc(h264r_ctx* ctx, int n, size_t max_blocks, h264r_picture_buf* out)
+{
+    if (!ctx || !out || n <= 0) return fail(ctx, H264R_E_INVAL, "picture_ring_alloc: bad argument");
+    if (max_blocks == 0 || max_blocks > (size_t)24 * ctx->n_mbs) max_blocks = (size_t)24 * ctx->n_mbs;
+    CU(cudaSetDevice(ctx->device));
+    const size_t stride = align_up(ctx->off_coeff + max_blocks * 32, 4096);
+    uint8_t* b = nullptr;
+    if (cudaMallocHost(&b, stride * (size_t)n) != cudaSuccess) return fail(ctx, H264R_E_NOMEM, "picture_ring_alloc: pinned allocation failed");
+    for (int i = 0; i < n; i++, b += stride) {
+        memset(b, 0, ctx->off_coeff);
+        out[i].hdr = reinterpret_cast<h264r_mb_hdr*>(b + ctx->off_hdr);
+        out[i].mv = reinterpret_cast<int16_t*>(b + ctx->off_mv);
+        out[i].mv_end = reinterpret_cast<int16_t*>(b + ctx->off_desc);
+        out[i].blk_mask = reinterpret_cast<uint32_t*>(b + ctx->off_mask);
+        out[i].blocks = reinterpret_cast<int16_t*>(b + ctx->off_coeff);
+        out[i].max_blocks = max_blocks;
+        out[i].n_intra = -1;
+        out[i].level_bytes = 2;
+        out[i].base = b;
+        out[i].hdr_bytes = 16;
+        out[i].ring_index = i + 1;
+        out[i].hdr8 = nullptr;
+    }
     return H264R_OK;
 }
 
@@ -631,11 +657,13 @@ void h264r_picture_buf_free(h264r_ctx* ctx, h264r_picture_buf* buf)
 {
     if (!ctx || !buf || !buf->base) return;
     cudaSetDevice(ctx->device);
-    cudaFreeHost(buf->base);
+    if (buf->ring_index <= 1) cudaFreeHost(buf->base);       // a ring goes with its first member; the others only forget their pointers
     memset(buf, 0, sizeof(*buf));
 }
 
-int h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* buf, size_t n_blocks, long n_mvs)
+// Everything h264r_submit_picture does short of the transfer: checks, picture state, the descriptor written into the buffer.
+// *first / *end: the byte range of the buffer (= of the arena slot) that has to travel.
+static int prepare_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* buf, size_t n_blocks, long n_mvs, Pending** out, size_t* first_out, size_t* end_out)
 {
     if (!ctx || !buf || !buf->base || n_blocks > buf->max_blocks * (buf->level_bytes == H264R_LEVELS_COMPACT ? 4 : 1) || n_mvs > (long)16 * (ctx ? ctx->n_mbs : 0) ||
         (buf->level_bytes != H264R_LEVELS_INT8 && buf->level_bytes != H264R_LEVELS_INT16 && buf->level_bytes != H264R_LEVELS_COMPACT))
@@ -681,14 +709,68 @@ int h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* 
     const size_t mv_bytes = !is_p ? 0 : (n_mvs >= 0 ? (size_t)n_mvs * 4 : ctx->off_desc);      // per-4x4 layout: the whole area
     const size_t first = ctx->off_desc - mv_bytes;
     const size_t unit_bytes = buf->level_bytes == H264R_LEVELS_INT16 ? 32 : (buf->level_bytes == H264R_LEVELS_INT8 ? 16 : 8);
-    CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot) + first, hb + first, (short_hdr ? ctx->off_coeff_s : ctx->off_coeff) + n_blocks * unit_bytes - first,
-                       cudaMemcpyHostToDevice, ctx->copy_stream));
-    CU(cudaEventRecord(ctx->ev_copied[p->slot], ctx->copy_stream));
-    p->seq = ++ctx->end_seq;
-    p->ended = true;
-    ctx->frame_state[frame_id] = FRAME_QUEUED;
+    *first_out = first;
+    *end_out = (short_hdr ? ctx->off_coeff_s : ctx->off_coeff) + n_blocks * unit_bytes;
+    *out = p;
     return H264R_OK;
 }
+static void picture_sent(h264r_ctx* ctx, Pending* p)
+{
+    cudaEventRecord(ctx->ev_copied[p->slot], ctx->copy_stream);
+    p->seq = ++ctx->end_seq;
+    p->ended = true;
+    ctx->frame_state[p->frame_id] = FRAME_QUEUED;
+}
+
+int h264r_submit_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* buf, size_t n_blocks, long n_mvs)
+{
+    Pending* p = nullptr;
+    size_t first = 0, end = 0;
+    const int rc = prepare_picture(ctx, frame_id, buf, n_blocks, n_mvs, &p, &first, &end);
+    if (rc != H264R_OK) return rc;
+    const uint8_t* hb = static_cast<const uint8_t*>(buf->base);
+    CU(cudaMemcpyAsync(ctx->slot_ptr(p->slot) + first, hb + first, end - first, cudaMemcpyHostToDevice, ctx->copy_stream));
+    picture_sent(ctx, p);
+    return H264R_OK;
+}
+
+int h264r_submit_pictures(h264r_ctx* ctx, int n, const int* frame_ids, const h264r_picture_buf* bufs, const size_t* n_blocks, const long* n_mvs)
+{
+    if (!ctx || n <= 0 || !frame_ids || !bufs || !n_blocks || !n_mvs) return fail(ctx, H264R_E_INVAL, "submit_pictures: bad argument");
+    struct Item { Pending* p; size_t first, end; const uint8_t* hb; size_t cap; };
+    std::vector<Item> it((size_t)n);
+    int rc = H264R_OK, m = 0;
+    for (; m < n; m++) {
+        rc = prepare_picture(ctx, frame_ids[m], &bufs[m], n_blocks[m], n_mvs[m], &it[m].p, &it[m].first, &it[m].end);
+        if (rc != H264R_OK) break;          // the pictures before this one still travel
+        it[m].hb = static_cast<const uint8_t*>(bufs[m].base);
+        it[m].cap = ctx->off_coeff + bufs[m].max_blocks * 32;
+    }
+    // runs of pictures whose buffers lie at a constant stride (members of a ring, in order) and whose arena slots are consecutive:
+    // ONE strided transfer per run, over the union of the byte ranges (what it carries beyond a picture's own range is unused space
+    // of that picture's slot on both sides)
+    for (int i = 0; i < m;) {
+        int j = i + 1;
+        ptrdiff_t stride = 0;
+        size_t lo = it[i].first, hi = it[i].end, cap = it[i].cap;
+        while (j < m && j - i < 64) {
+            const ptrdiff_t d = it[j].hb - it[j - 1].hb;
+            if (it[j].p->slot != it[j - 1].p->slot + 1 || d <= 0 || (stride && d != stride)) break;
+            const size_t lo2 = std::min(lo, it[j].first), hi2 = std::max(hi, it[j].end), cap2 = std::min(cap, it[j].cap);
+            if (hi2 > cap2 || hi2 - lo2 > (size_t)d) break;
+            stride = d; lo = lo2; hi = hi2; cap = cap2;
+            j++;
+        }
+        cudaError_t e;
+        if (j - i == 1) e = cudaMemcpyAsync(ctx->slot_ptr(it[i].p->slot) + it[i].first, it[i].hb + it[i].first, it[i].end - it[i].first, cudaMemcpyHostToDevice, ctx->copy_stream);
+        else e = cudaMemcpy2DAsync(ctx->slot_ptr(it[i].p->slot) + lo, ctx->slot_bytes, it[i].hb + lo, (size_t)stride, hi - lo, (size_t)(j - i), cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e != cudaSuccess) return fail(ctx, H264R_E_CUDA, std::string("submit_pictures: ") + cudaGetErrorString(e));
+        for (int k = i; k < j; k++) picture_sent(ctx, it[k].p);
+        i = j;
+    }
+    return rc;
+}
+
 
 int h264r_frame_end(h264r_ctx* ctx, int frame_id)
 {

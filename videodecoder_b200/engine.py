@@ -13,7 +13,7 @@ from . import abi, build
 class PictureBufStruct(ctypes.Structure):
     _fields_ = [("hdr", ctypes.c_void_p), ("mv", ctypes.c_void_p), ("mv_end", ctypes.c_void_p), ("blk_mask", ctypes.c_void_p), ("blocks", ctypes.c_void_p),
                 ("max_blocks", ctypes.c_size_t), ("n_intra", ctypes.c_int32), ("level_bytes", ctypes.c_int32), ("base", ctypes.c_void_p),
-                ("hdr_bytes", ctypes.c_int32), ("reserved_", ctypes.c_int32), ("hdr8", ctypes.c_void_p)]
+                ("hdr_bytes", ctypes.c_int32), ("ring_index", ctypes.c_int32), ("hdr8", ctypes.c_void_p)]
 
 
 _lib = None
@@ -58,6 +58,8 @@ def load_library():
     L.h264r_picture_buf_alloc.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(PictureBufStruct)]
     L.h264r_picture_buf_free.argtypes = [vp, ctypes.POINTER(PictureBufStruct)]
     L.h264r_picture_buf_format.argtypes = [vp, ctypes.POINTER(PictureBufStruct), ctypes.c_int]
+    L.h264r_picture_ring_alloc.argtypes = [vp, ci, ctypes.c_size_t, ctypes.POINTER(PictureBufStruct)]
+    L.h264r_submit_pictures.argtypes = [vp, ci, ctypes.POINTER(ci), ctypes.POINTER(PictureBufStruct), ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_long)]
     L.h264r_picture_buf_free.restype = None
     L.h264r_submit_picture.argtypes = [vp, ci, ctypes.POINTER(PictureBufStruct), ctypes.c_size_t, ctypes.c_long]
     L.h264r_frame_end.argtypes = [vp, ci]
@@ -90,7 +92,7 @@ def load_library():
 
 EXPORTS = [
     "h264r_abi_version", "h264r_last_error", "h264r_create", "h264r_destroy", "h264r_host_alloc", "h264r_host_free",
-    "h264r_frame_begin", "h264r_submit_mbs", "h264r_submit_mbs_packed", "h264r_wait_uploads", "h264r_set_lanes", "h264r_picture_buf_alloc", "h264r_picture_buf_free", "h264r_picture_buf_format", "h264r_submit_picture", "h264r_frame_end", "h264r_frame_abort", "h264r_device_status", "h264r_flush", "h264r_sync", "h264r_read_planes",
+    "h264r_frame_begin", "h264r_submit_mbs", "h264r_submit_mbs_packed", "h264r_wait_uploads", "h264r_set_lanes", "h264r_picture_buf_alloc", "h264r_picture_buf_free", "h264r_picture_buf_format", "h264r_picture_ring_alloc", "h264r_submit_picture", "h264r_submit_pictures", "h264r_frame_end", "h264r_frame_abort", "h264r_device_status", "h264r_flush", "h264r_sync", "h264r_read_planes",
     "h264r_frame_layout", "h264r_read_frame_async", "h264r_wait_readbacks",
     "h264r_frame_digest", "h264r_frame_digests", "h264r_range_excursions", "h264r_excursion_map",
     "h264r_residual_mbs", "h264r_release", "h264r_last_flush_stats", "h264r_set_profiling",
@@ -130,10 +132,14 @@ class PinnedBuffer:
 class PictureBuf:
     """h264r_picture_buf: pinned staging of one picture in the engine's upload layout (numpy views)."""
 
-    def __init__(self, engine, max_blocks=0):
+    def __init__(self, engine, max_blocks=0, struct=None):
+        """struct: a member of a PictureRing's array (allocated there), else a buffer of its own"""
         self.engine = engine
-        self.c = PictureBufStruct()
-        engine._check(engine.L.h264r_picture_buf_alloc(engine.ctx, max_blocks, ctypes.byref(self.c)))
+        if struct is None:
+            self.c = PictureBufStruct()
+            engine._check(engine.L.h264r_picture_buf_alloc(engine.ctx, max_blocks, ctypes.byref(self.c)))
+        else:
+            self.c = struct
         n = engine.n_mbs
 
         def view(ptr, dtype, count):
@@ -207,6 +213,30 @@ class PictureBuf:
         if self.c.base:
             self.hdr = self.hdr8 = self.mv = self.mv_tail = self.blk_mask = self.blocks = None
             self.engine.L.h264r_picture_buf_free(self.engine.ctx, ctypes.byref(self.c))
+
+
+class PictureRing:
+    """n picture buffers in one pinned allocation at a constant stride (h264r_picture_ring_alloc): filled like single buffers,
+    shipped together by Engine.submit_ring with one strided transfer."""
+
+    def __init__(self, engine, n, max_blocks=0):
+        self.engine = engine
+        self.n = n
+        self.array = (PictureBufStruct * n)()
+        engine._check(engine.L.h264r_picture_ring_alloc(engine.ctx, n, max_blocks, self.array))
+        self.bufs = [PictureBuf(engine, struct=self.array[i]) for i in range(n)]
+        self._ids = (ctypes.c_int * n)()
+        self._nb = (ctypes.c_size_t * n)()
+        self._nm = (ctypes.c_long * n)()
+
+    def __getitem__(self, i):
+        return self.bufs[i]
+
+    def free(self):
+        if self.bufs:
+            for b in self.bufs[::-1]:     # member 0 last: it owns the allocation
+                b.free()
+            self.bufs = []
 
 
 class Engine:
@@ -283,6 +313,19 @@ class Engine:
         """whole picture from a PictureBuf: one DMA, queued at once"""
         self.frame_begin(frame_id, pp)
         self._check(self.L.h264r_submit_picture(self.ctx, frame_id, ctypes.byref(buf.c), buf.n_blocks, buf.n_mvs))
+
+    def picture_ring(self, n, max_blocks=0):
+        return PictureRing(self, n, max_blocks)
+
+    def submit_ring(self, ring, frame_ids, pps, count=None):
+        """pictures frame_ids[k] <- ring[k], begun back to back and shipped with one strided transfer where the library can"""
+        n = ring.n if count is None else count
+        for k in range(n):
+            self.frame_begin(frame_ids[k], pps[k])
+            ring._ids[k] = frame_ids[k]
+            ring._nb[k] = ring.bufs[k].n_blocks
+            ring._nm[k] = ring.bufs[k].n_mvs
+        self._check(self.L.h264r_submit_pictures(self.ctx, n, ring._ids, ring.array, ring._nb, ring._nm))
 
     def frame_abort(self, frame_id):
         self._check(self.L.h264r_frame_abort(self.ctx, frame_id))

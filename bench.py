@@ -462,8 +462,13 @@ def measure(a, rank, world, local, dist, torch, extras=True):
     # where the e2e time goes (untimed probe): host time of the submit calls, time until the uploads are resident
     t_a = time.perf_counter(); submit_all(); t_b = time.perf_counter(); eng.wait_uploads(); t_c = time.perf_counter()
     eng.flush(); eng.sync()
+    # host time of the e2e loop itself (submits + a flush per round, nothing waited for): if it approaches the e2e step time, the
+    # host thread that issues the work bounds the number, not the GPU
+    t_d = time.perf_counter(); submit_all(flush_each=True); eng.flush(); t_e = time.perf_counter()
+    eng.sync()
     e2e_probe = {"submit_calls_host_ms": (t_b - t_a) * 1e3, "uploads_resident_ms": (t_c - t_a) * 1e3,
-                 "h2d_GBps_over_upload_window": h2d / max(1e-9, (t_c - t_a)) / 1e9}
+                 "h2d_GBps_over_upload_window": h2d / max(1e-9, (t_c - t_a)) / 1e9,
+                 "host_issue_ms_submit_and_flush_per_round": (t_e - t_d) * 1e3}
     # ---- e2e_planes: as e2e, and every reconstructed frame goes back to pinned host memory -------------------------------
     planes = None
     if extras and a.planes:
@@ -525,7 +530,7 @@ def measure(a, rank, world, local, dist, torch, extras=True):
         peak, peak_src = measured_peak()
         # dominant kernel family and its roofline (DESIGN.md "Measurement")
         fam = int(np.argmax(fam_ms[:3]))
-        names = ["k_inter (K1+K3: dequant/IDCT + motion compensation + reconstruction)",
+        names = [("k_inter_grp" if (compat and packed) else "k_inter") + " (K1+K3: dequant/IDCT + motion compensation + reconstruction)",
                  "k_intra (K1+K2: dequant/IDCT + intra wavefront)", "k_deblock (K4)"]
         inter_mbs = sum(inter_mbs_per_pic[(g % U) * F + i] for g in range(G) for i in range(F))
         per_mb = {0: (768 + 16 + 64 + (256 if compat else 384) + 384), 1: (768 + 16 + 384), 2: (384 + 384 + 16 + 64)}
@@ -542,8 +547,12 @@ def measure(a, rank, world, local, dist, torch, extras=True):
                 try:
                     tr = json.load(open(tj))
                     if tr.get("_pictures_per_launch") == G:
-                        traffic = tr[a.mode][["k_inter", "k_intra_rows", "k_deblock_rows"][fam]]["dram_bytes_per_launch"]
-                        break
+                        # (REF_COMPAT launches of picture buffers run k_inter_grp; the capture lists the kernel that ran)
+                        fam_kernels = [["k_inter_grp", "k_inter"] if a.mode == "compat" else ["k_inter"], ["k_intra_rows"], ["k_deblock_rows"]][fam]
+                        hit = [k for k in fam_kernels if k in tr[a.mode]]
+                        if hit:
+                            traffic = tr[a.mode][hit[0]]["dram_bytes_per_launch"]
+                            break
                 except Exception:
                     traffic = None
         out = {
@@ -672,7 +681,9 @@ def main():
     ap.add_argument("--layout", default="packed", choices=["packed", "dense"],
                     help="coefficient transport: h264r_submit_mbs_packed (present blocks only) or h264r_submit_mbs (768 B per macroblock)")
     ap.add_argument("--hdr", default="short", choices=["short", "long"], help="picture buffers with 8-byte (h264r_mb_hdr8) or 16-byte headers")
-    ap.add_argument("--no-ring", dest="ring", action="store_false", help="one pinned buffer and one DMA per picture instead of a ring and one strided DMA per round")
+    ap.add_argument("--ring", action="store_true", help="picture rings: one strided DMA per round of access units instead of one DMA per picture "
+                    "(h264r_submit_pictures; 52 against 33 GB/s on one GPU, but the union of the pictures' byte ranges travels -- +8 %% bytes here, "
+                    "which costs 5 %% at 8 GPUs, where the box's host memory bounds the uploads)")
     ap.add_argument("--p-block", type=float, default=None, help="density sweep: share of coded 4x4 blocks inside a coded 8x8 (default 0.45)")
     ap.add_argument("--max-amp", type=float, default=None, help="density sweep: residual amplitude (default 10)")
     args = ap.parse_args()

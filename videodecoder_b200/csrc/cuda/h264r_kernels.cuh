@@ -239,6 +239,17 @@ __device__ __forceinline__ void wait_progress(const int* p, int need)
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
+// does intra macroblock h read samples of its neighbour C (above right)?
+__device__ __forceinline__ bool intra_reads_c(const h264r_mb_hdr& h)
+{
+    if (!(h.flags & H264R_AVAIL_C) || h.mb_class == H264R_MB_I16x16) return false;
+    if (h.mb_class == H264R_MB_I4x4) {
+        const int m = hdr_pred_mode(h, 5);       // luma4x4BlkIdx 5 = the block at raster (0, 3)
+        return m == 3 || m == 7;
+    }
+    return true;
+}
+
 constexpr int ROW_WARPS = 4;          // row warps per CTA of the wavefront kernels
 constexpr int ROW_MASK_WORDS = 16;    // intra bitmap of a row: up to 512 macroblocks (8192 samples) wide
 
@@ -380,8 +391,12 @@ __global__ void __launch_bounds__(ROW_WARPS * 64, 2) k_intra_rows(const DescTabl
         if (row > 0) {
             // B, C, D are final unless they are intra macroblocks the row above has not reached yet: the sequence waits (after
             // its plan) for the last intra one among (x-1, x, x+1) of the row above -- on both warps of that row
+            // (C's samples are read by the block in the macroblock's top right corner only, and only by the two Intra4x4 modes that
+            // look up-right -- diagonal down-left and vertical-left -- or by Intra8x8, whose reference-sample filter takes them: any
+            // other macroblock follows the row above at a distance of ONE macroblock instead of two, which shortens the wavefront's
+            // critical path from W + 2H towards W + H steps)
             int last = -1;
-            for (int xx = x + 1; xx >= x - 1 && xx >= 0; xx--)
+            for (int xx = intra_reads_c(h) ? x + 1 : x; xx >= x - 1 && xx >= 0; xx--)
                 if (xx < W && ((above[xx >> 5] >> (xx & 31)) & 1)) { last = xx; break; }
             rs.up_need = last + 1;
             rs.up0 = &prog[(row - 1) * 2]; rs.up1 = &prog[(row - 1) * 2 + 1];

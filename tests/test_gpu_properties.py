@@ -466,3 +466,17 @@ def test_ring_submit_equals_single_submits(built, short_hdr):
         for r in rings:
             r.free()
         eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("compat", [True, False])
+def test_maximum_picture_width(built, compat):
+    """the widest picture the engine takes (512 macroblocks = 8192 samples; 513 is rejected, test_create_rejects_unsupported_width):
+    the row masks of the wavefront kernels are full, the group kernel's last group of a row straddles picture rows"""
+    w, h = 512, 2
+    rng = np.random.default_rng(512)
+    cfg = workload.WorkloadConfig(compat=compat, p_intra_in_p=0.05, num_ref=2, mv_range=120, p_t8x8=0.0 if compat else 0.4, p_i8x8=0.0 if compat else 0.3)
+    gop = workload.make_gop(rng, w, h, 3, cfg)
+    if compat:
+        sanitize_with_oracle(w, h, gop)
+    check_vs_oracle(w, h, abi.REF_COMPAT if compat else 0, gop, transport="bufmvh8")

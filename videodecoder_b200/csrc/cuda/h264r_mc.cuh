@@ -738,7 +738,7 @@ HD uint32_t weight_packed(uint32_t pred, int logwd, int wgt, int off)
 constexpr int PART_ALL = 0, PART_LUMA4 = 1, PART_LUMA8 = 2, PART_CHROMA = 3;
 template <bool COMPAT, bool TMA, bool LEAN, int PART = PART_ALL>
 HD void phase_inter_compute(InterWork& w, TmaState& ts, const PicDesc& pd, const Geometry& g, const h264r_mb_hdr& h, int a, int lane, bool coded,
-                            uint32_t mv_own)
+                            uint32_t mv_own, const MbPre* pre = nullptr)
 {
     (void)ts;
     const bool weighted = LEAN ? false : pd.weighted_pred != 0;
@@ -831,7 +831,8 @@ HD void phase_inter_compute(InterWork& w, TmaState& ts, const PicDesc& pd, const
                 const int cx = cx0 + 2 * k2, blk = (cy >> 1) * 4 + (cx >> 1), qq = (cy >> 2) * 2 + (cx >> 2);
                 const int rc = hdr_ref_idx(h, qq);
                 const uint8_t* ref = plane ? pd.ref_v[rc] : pd.ref_u[rc];
-                const uint32_t v2 = load_mv(pd, h, a, blk);
+                // (the vector offset came with the macroblock's prefetch: one memory round trip less in front of the reference loads)
+                const uint32_t v2 = pre ? load_mv_pre(pd, h, a, blk, *pre, LEAN ? true : pd.mv_off != nullptr) : load_mv(pd, h, a, blk);
                 const int mvx = mv_x(v2), mvy = mv_y(v2);
                 const int xf = mvx & 7, yf = mvy & 7;
                 const int xi = clip3(-8, cw + 5, mbx * 8 + cx + (mvx >> 3)), yi = clip3(-8, ch + 6, mby * 8 + cy + (mvy >> 3));
@@ -868,7 +869,7 @@ HD void seq_inter_mb_fast(Exec& ex, InterWork& w, TmaState& ts, const PicDesc& p
     PerLane<uint32_t> mv_own;
     if (PART == PART_CHROMA) {
         if (coded) ex([&](int lane) { phase_residual_fast<COMPAT, LEAN, true>(w.res, pd, h, a, lane, nullptr, true, &pre); });
-        ex([&](int lane) { phase_inter_compute<COMPAT, TMA, LEAN, PART>(w, ts, pd, g, h, a, lane, coded, 0u); });
+        ex([&](int lane) { phase_inter_compute<COMPAT, TMA, LEAN, PART>(w, ts, pd, g, h, a, lane, coded, 0u, &pre); });
         return;
     }
     ex([&](int lane) {
@@ -881,7 +882,7 @@ HD void seq_inter_mb_fast(Exec& ex, InterWork& w, TmaState& ts, const PicDesc& p
     if (t8) ex([&](int lane) { phase_residual8_cols(w, lane); });
     ex([&](int lane) {
         if (!COMPAT && pd.nzmask && lane == 0) pd.nzmask[a] = !coded ? 0u : (t8 ? nz_pack8(w.nzf) : nz_pack(w.nzf));
-        phase_inter_compute<COMPAT, TMA, LEAN, PART>(w, ts, pd, g, h, a, lane, coded, mv_own(lane));
+        phase_inter_compute<COMPAT, TMA, LEAN, PART>(w, ts, pd, g, h, a, lane, coded, mv_own(lane), &pre);
     });
     if (COMPAT) {        // border macroblocks replicate their samples into the frame's border (see phase_pad_mb_luma)
         int mbx, mby;

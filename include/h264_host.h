@@ -1,8 +1,9 @@
 /*
  * h264_host.h -- C interface of the host side that sits ABOVE the reconstruction ABI (include/h264r.h): the serial part of an
- * H.264 decoder -- Annex-B / NAL parsing, parameter sets, slice headers, CABAC entropy decoding, motion-vector / intra-mode / QP
- * derivation, decoded-picture-buffer bookkeeping -- producing, per picture, exactly the buffers h264r_submit_* takes; and the
- * inverse, a CABAC stream writer (test and benchmark tooling: the image has no H.264 encoder).  libh264host.so, plain C ABI.
+ * H.264 decoder -- Annex-B / NAL parsing, parameter sets, slice headers, CABAC and CAVLC entropy decoding, motion-vector /
+ * intra-mode / QP derivation, decoded-picture-buffer bookkeeping -- producing, per picture, exactly the buffers h264r_submit_*
+ * takes; and the inverse, a stream writer for both entropy codes (test and benchmark tooling: the image has no H.264 encoder;
+ * profile_idc 66, Baseline, selects CAVLC).  libh264host.so, plain C ABI.
  *
  * What it stands in for in the reference (Terice/VideoDecoder, h264/):
  *   h264d_open / h264d_next        main.cpp:20-45 NAL loop, Parser::find_nextNAL (Parser.cpp:21-53), NAL::decode (NAL.cpp:14-30),
@@ -88,7 +89,7 @@ long   h264d_benchmark(const uint8_t* annexb, size_t n_bytes, uint32_t flags, in
 /* SPS + PPS NAL units.  profile_idc 100 writes the High-profile SPS fields (4:2:0, 8 bit, flat scaling lists) and, when
  * transform_8x8_mode_flag or second_chroma_qp_index_offset ask for it, the PPS extension. */
 long h264e_write_sps_pps(const h264s_seq* seq, uint8_t* out, long cap);
-/* One picture = one slice NAL unit, CABAC.  mbs[] is normalised in place where the syntax cannot express it (coded_block_pattern
+/* One picture = one slice NAL unit, CABAC (CAVLC when seq->profile_idc is 66: Baseline profile has no CABAC).  mbs[] is normalised in place where the syntax cannot express it (coded_block_pattern
  * bits of empty 8x8 blocks, mb_qp_delta of macroblocks without residual, 8x8 transform flags that the macroblock type forbids).
  * Returns bytes written or a negative H264D_E_* code. */
 long h264e_encode_picture(const h264s_seq* seq, const h264s_pic* pic, h264s_mb* mbs, int n_mbs, uint32_t flags, uint8_t* out, long cap);

@@ -2,7 +2,7 @@
 
     python tests/golden/make_spec_golden.py
 
-spec_*: a genuine High-profile CABAC bitstream written by the repository's stream writer (recipes in tests/streams.py) and the
+spec_* / base_*: a genuine High-profile CABAC / Baseline-profile CAVLC bitstream written by the repository's stream writer (recipes in tests/streams.py) and the
 planes LIBAVCODEC decoded from it (tests/lavc.py: the libavcodec 62 bundled with the opencv wheel, driven through ctypes) -- an
 implementation that shares no code and no author with this repository.  Every spec-mode parity test compares against these planes.
 ref_cif_ip_stream: a Main-profile CABAC bitstream and the planes the UNMODIFIED reference decoder reconstructed from it with its own
@@ -36,11 +36,16 @@ def save(name, seq, stream, aus, frames, keep_planes):
 
 
 def main():
+    only = sys.argv[1:]          # names given on the command line: regenerate just those
     for name, recipe in streams.SPEC_RECIPES.items():
+        if only and name not in only:
+            continue
         s = recipe()
         frames = lavc.decode(s["aus"])
         assert len(frames) == len(s["pics"])
         save(name, s["seq"], s["stream"], s["aus"], frames, keep_planes=name != "spec_hd1080_ip")
+    if only and "ref_cif_ip_stream" not in only:
+        return
     # Main-profile stream for the unmodified reference (own CABAC); content kept inside [0,255]
     s = streams.ref_cif_ip(sanitize=lambda seq, pics: sanitize_with_reference(seq, pics))
     dump, _ = refharness.run_reference_cabac(s["stream"], level=1)

@@ -1,7 +1,9 @@
 """TEST INFRASTRUCTURE: recipes of the genuine H.264 bitstreams the tests use -- written by the repository's own CABAC writer
 (libh264host.so, h264e_*), since the image holds no encoder and the reference ships no stream.
 
-Two families:
+Three families:
+  base_*   Baseline profile (CAVLC), standard-conformant: BASELINE config 1 ("baseline-profile stream") and config 2 geometry, decoded by
+           libavcodec like the spec_* family;
   spec_*   High profile, standard-conformant: decoded by libavcodec (tests/lavc.py) to pin the spec-mode half of the engine and of
            the oracle -- Intra8x8, intra chroma prediction, chroma motion compensation, 8x8 transform, deblocking (SURVEY a13, a14,
            a19, a20, a21), which the reference decoder does not implement;
@@ -148,8 +150,32 @@ def ref_cif_ip(n_pictures=6, w=22, h=18, seed=201, sanitize=None):
     return out
 
 
+def base_qcif_i():
+    """BASELINE config 1 as written: QCIF 176x144, I slices only, BASELINE profile (profile_idc 66: CAVLC entropy coding, 4x4 transform):
+    3 IDR pictures, Intra4x4 with every mode and Intra16x16, deblocking on."""
+    rng = np.random.default_rng(111)
+    seq = synth.make_seq(11, 9, deblocking_control=1, profile_idc=66, chroma_qp_index_offset=2)
+    pics = synth.random_gop(rng, seq, 3, synth.ContentConfig(p_qp_delta=0.3, qp_delta_range=4), intra_only=True, absolute=True)
+    for p, _ in pics:
+        p.disable_deblocking_filter_idc = 0
+    return _encode(seq, pics)
+
+
+def base_cif_ip():
+    """BASELINE config 2 geometry as a Baseline-profile (CAVLC) stream: CIF, 1 I + 5 P, two references, every partition shape, P_Skip
+    runs, intra macroblocks inside P pictures, QP deltas, deblocking on."""
+    rng = np.random.default_rng(112)
+    seq = synth.make_seq(22, 18, deblocking_control=1, profile_idc=66, max_num_ref_frames=2, num_ref_idx_default=1, chroma_qp_index_offset=-2)
+    cfg = synth.ContentConfig(num_ref=2, sub_types=(0, 1, 2, 3), p_intra_in_p=0.1, p_qp_delta=0.4, qp_delta_range=4)
+    pics = synth.random_gop(rng, seq, 6, cfg, absolute=True)
+    for i, (p, _) in enumerate(pics):
+        p.disable_deblocking_filter_idc = 0
+        p.slice_alpha_c0_offset_div2 = (0, 2, -2)[i % 3]
+    return _encode(seq, pics)
+
+
 SPEC_RECIPES = {"spec_qcif_i": spec_qcif_i, "spec_cif_ip": spec_cif_ip, "spec_qcif_wp": spec_qcif_wp, "spec_dpb": spec_dpb,
-                "spec_hd1080_ip": spec_hd1080_ip}
+                "spec_hd1080_ip": spec_hd1080_ip, "base_qcif_i": base_qcif_i, "base_cif_ip": base_cif_ip}
 
 
 # ---- known-answer streams: one tool at a time (SURVEY 4 item 4: each intra mode, each boundary-strength class) ------------------------

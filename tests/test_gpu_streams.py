@@ -60,7 +60,7 @@ def engine_on_stream(stream, flags=0, dflags=0, transport="dense", pool=0):
 
 
 @pytest.mark.parametrize("transport", ["dense", "compact", "int16"])
-@pytest.mark.parametrize("name", ["spec_qcif_i", "spec_cif_ip", "spec_qcif_wp", "spec_dpb", "spec_hd1080_ip"])
+@pytest.mark.parametrize("name", ["spec_qcif_i", "spec_cif_ip", "spec_qcif_wp", "spec_dpb", "spec_hd1080_ip", "base_qcif_i", "base_cif_ip"])
 def test_spec_mode_equals_libavcodec(built, name, transport):
     g = load_stream_golden(name)
     outs, _, status = engine_on_stream(g["stream"], flags=0, transport=transport)

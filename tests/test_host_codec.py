@@ -9,7 +9,7 @@ import lavc
 import streams
 from videodecoder_b200 import hoststream
 
-SPEC_SMALL = ["spec_qcif_i", "spec_cif_ip", "spec_qcif_wp", "spec_dpb"]
+SPEC_SMALL = ["spec_qcif_i", "spec_cif_ip", "spec_qcif_wp", "spec_dpb", "base_qcif_i", "base_cif_ip"]
 need_lavc = pytest.mark.skipif(not lavc.available(), reason="no libavcodec in this image")
 need_ref_cabac = pytest.mark.skipif(not refharness.have_cabac_harness(), reason="reference harness (own CABAC) not built")
 
@@ -193,15 +193,27 @@ def test_decoder_rejects_damaged_and_unsupported_streams(built):
             hoststream.decode_stream(bytes(b))
         except RuntimeError:
             pass
-    # CAVLC parameter set: outside the scope, reported as such
+    # the same for a CAVLC stream (mb_skip_run, coeff_token, level escapes, run_before all read from damaged bits)
+    s2 = load_stream_golden("base_cif_ip")["stream"]
+    for k in range(40):
+        b = bytearray(s2)
+        for pos in rng.integers(60, len(b), size=8):
+            b[pos] ^= 1 << int(rng.integers(0, 8))
+        try:
+            hoststream.decode_stream(bytes(b))
+        except RuntimeError:
+            pass
+    # a CABAC stream whose parameter set claims CAVLC: garbage in, an error or garbage out, no crash
     seq = synth.make_seq(3, 3)
     pics = synth.random_gop(np.random.default_rng(1), seq, 1, synth.ContentConfig())
     good = hoststream.encode_stream(seq, pics)
     i = good.index(b"\x00\x00\x00\x01\x68")
     bad = bytearray(good)
     bad[i + 5] &= 0xDF          # pps: ue(0) ue(0) then entropy_coding_mode_flag = bit 2 of the first payload byte ('1 1 1' -> '1 1 0')
-    with pytest.raises(RuntimeError, match="CAVLC"):
+    try:
         hoststream.decode_stream(bytes(bad))
+    except RuntimeError:
+        pass
 
 
 def test_host_decoder_throughput_is_reported(built):
@@ -234,3 +246,90 @@ def test_known_answer_streams_against_libavcodec(built, name):
                 elif h["mb_class"] == abi.MB_I16x16:
                     seen16.add(int(h["intra_modes"]) & 3)
         assert seen4 == set(range(9)) and seen8 == set(range(9)) and seen16 == set(range(4))
+
+
+# ---- CAVLC (entropy_coding_mode_flag = 0; profile_idc 66 selects it in the writer) ---------------------------------------------
+def _cavlc_table(name):
+    import os
+    import re
+    src = open(os.path.join(ROOT, "videodecoder_b200", "csrc", "host", "cavlc_tables.h")).read()
+    m = re.search(r"%s(\[[^=]*\])+\s*=\s*(\{.*?\});" % name, src, re.S)
+    rows = re.findall(r"\{([^{}]*)\}", m.group(2))
+    return [[int(x) for x in r.replace("\n", " ").split(",") if x.strip()] for r in rows]
+
+
+def test_cavlc_tables_are_prefix_codes():
+    """every VLC table of cavlc_tables.h (Tables 9-5, 9-7, 9-8, 9-9a, 9-10 of the standard) is prefix-free, and complete up to the one
+    all-zero codeword the standard leaves unused in its longest-code tables; the me(v) maps are permutations of 0..47"""
+    from fractions import Fraction
+
+    def kraft(lens, bits):
+        codes = [format(b, "0%db" % l) for l, b in zip(lens, bits) if l]
+        assert len(set(codes)) == len(codes)
+        for a in codes:
+            assert not any(b != a and b.startswith(a) for b in codes), a
+        return sum(Fraction(1, 2 ** len(c)) for c in codes), max(len(c) for c in codes), len(codes)
+
+    for lens, bits, entries in zip(_cavlc_table("kCoeffTokenLen"), _cavlc_table("kCoeffTokenBits"), (62, 62, 62, 62)):
+        k, longest, n = kraft(lens, bits)
+        assert n == entries and (1 - k).numerator == 1 and (1 - k).denominator >= 32        # one unused (all-zero) codeword
+    assert kraft(_cavlc_table("kChromaDcTokenLen")[0], _cavlc_table("kChromaDcTokenBits")[0])[0] == 1
+    for tc, (lens, bits) in enumerate(zip(_cavlc_table("kTotalZerosLen"), _cavlc_table("kTotalZerosBits")), 1):
+        k, longest, n = kraft(lens, bits)
+        assert n == 17 - tc and (k == 1 if tc > 1 else (1 - k).numerator == 1)
+    for lens, bits in zip(_cavlc_table("kChromaDcTotalZerosLen"), _cavlc_table("kChromaDcTotalZerosBits")):
+        assert kraft(lens, bits)[0] == 1
+    for zl, (lens, bits) in enumerate(zip(_cavlc_table("kRunLen"), _cavlc_table("kRunBits")), 1):
+        lens, bits = lens + [0] * (16 - len(lens)), bits + [0] * (16 - len(bits))
+        k, longest, n = kraft(lens, bits)
+        assert n == (15 if zl == 7 else zl + 1) and (k == 1 if zl < 7 else (1 - k).numerator == 1)
+    assert sorted(_cavlc_table("kCbpIntra")[0]) == list(range(48)) and sorted(_cavlc_table("kCbpInter")[0]) == list(range(48))
+
+
+@pytest.mark.parametrize("profile", [66, 100])
+def test_cavlc_writer_reader_round_trip(built, profile):
+    """CAVLC slices: what the writer emits the decoder reads back, record for record -- Baseline (profile_idc 66), and the 8x8
+    transform travelling as four interleaved 4x4 blocks (checked through the codec templates with a High-profile PPS is not
+    possible from the writer, which ties CAVLC to profile 66: the High case round-trips through CABAC above)"""
+    if profile != 66:
+        pytest.skip("the writer selects CAVLC through profile_idc 66 only")
+    rng = np.random.default_rng(21)
+    seq = synth.make_seq(13, 7, max_num_ref_frames=3, num_ref_idx_default=2, profile_idc=66, deblocking_control=1)
+    cfg = synth.ContentConfig(num_ref=3, sub_types=(0, 1, 2, 3), p_intra_in_p=0.15, p_qp_delta=0.5, qp_delta_range=6)
+    pics = synth.random_gop(rng, seq, 5, cfg)
+    # large values: level_prefix 14 / 15 escapes and beyond, long mvd codes
+    pics[0][1]["luma"][3][2][0] = 2000
+    pics[0][1]["luma"][3][2][1] = -17
+    pics[0][1]["luma"][3][2][5] = 40
+    pics[0][1]["cbp_luma"][3] |= 1
+    pics[1][1]["mvd"][:, 0, :] = rng.integers(-900, 900, size=(pics[1][1].size, 2))
+    stream = hoststream.encode_stream(seq, pics)
+    dec, tail = hoststream.decode_stream(stream, flags=hoststream.KEEP_SYNTAX)
+    assert len(dec) == len(pics)
+    for i, ((pic, mbs), d) in enumerate(zip(pics, dec)):
+        for name in mbs.dtype.names:
+            assert np.array_equal(mbs[name], d["syntax"][name]), "picture %d field %s" % (i, name)
+
+
+@need_lavc
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_baseline_cavlc_streams_against_libavcodec(built, seed):
+    """Baseline-profile (CAVLC) streams of random content -- BASELINE config 1's "baseline-profile stream" made literal: QCIF I-only
+    (seed 1) and I+P with every partition shape, several references, QP deltas, deblocking on: libavcodec's planes == host decoder +
+    spec-mode oracle"""
+    rng = np.random.default_rng(700 + seed)
+    w, h = [(11, 9), (9, 4), (5, 6), (22, 18)][seed - 1]
+    seq = synth.make_seq(w, h, max_num_ref_frames=2, num_ref_idx_default=1, profile_idc=66, deblocking_control=1,
+                         chroma_qp_index_offset=int(rng.integers(-4, 5)), pic_init_qp=int(rng.integers(20, 38)))
+    cfg = synth.ContentConfig(num_ref=2, sub_types=(0, 1, 2, 3), p_intra_in_p=0.25, p_qp_delta=0.5, qp_delta_range=5, mv_range=100)
+    n = 3 if seed == 1 else 5
+    pics = synth.random_gop(rng, seq, n, cfg, absolute=True, intra_only=(seed == 1))
+    for i, (p, _) in enumerate(pics):
+        p.slice_qp_delta = int(rng.integers(-3, 4))
+    stream, aus = hoststream.encode_stream(seq, pics, flags=hoststream.E_ABSOLUTE, per_picture=True)
+    frames = lavc.decode(aus)
+    _, outs = oracle_on_stream(stream)
+    assert len(frames) == len(outs) == len(pics)
+    for i, (f, o) in enumerate(zip(frames, outs)):
+        for k, ref in zip("yuv", f):
+            assert np.array_equal(o[k], ref), "picture %d plane %s" % (i, k)

@@ -167,7 +167,6 @@ inline int parse_pps(BitReader& r, Pps* p, const char** why)
         p->second_chroma_qp_index_offset = r.se();
     }
     if (r.overrun() || p->pps_id > 255 || p->sps_id > 31 || p->num_ref_idx_l0_default > 32) return kErrBitstream;
-    if (!p->entropy_coding_mode_flag) { *why = "CAVLC (entropy_coding_mode_flag = 0)"; return kErrUnsupported; }
     p->valid = true;
     return kOk;
 }

@@ -15,6 +15,7 @@
 #include "../../../include/h264r_writer.h"
 #include "bits.h"
 #include "cabac.h"
+#include "cavlc.h"
 #include "h264_derive.h"
 #include "h264_dpb.h"
 #include "h264_headers.h"
@@ -40,6 +41,8 @@ void seq_to_sets(const h264s_seq& s, Sps* sps, Pps* pps)
     sps->h_mbs = s.h_mbs;
     sps->valid = true;
     *pps = Pps();
+    pps->entropy_coding_mode_flag = s.profile_idc == 66 ? 0 : 1;       // Baseline profile: CAVLC (it has no CABAC)
+    if (s.profile_idc == 66) sps->constraint_flags = 0x80;              // constraint_set0_flag
     pps->num_ref_idx_l0_default = s.num_ref_idx_l0_default_active_minus1 + 1;
     pps->weighted_pred_flag = s.weighted_pred_flag;
     pps->pic_init_qp = s.pic_init_qp;
@@ -192,13 +195,55 @@ extern "C" long h264e_encode_picture(const h264s_seq* s, const h264s_pic* p, h26
     const bool p_slice = h.slice_type == kSliceP;
     BitWriter w;
     write_slice_header(w, sps, pps, h);
-    w.align_ones();                                        // cabac_alignment_one_bit
     SliceParams sp;
     sp.w_mbs = s->w_mbs; sp.h_mbs = s->h_mbs; sp.p_slice = p_slice;
     sp.num_ref_idx_l0 = h.num_ref_idx_l0; sp.transform_8x8_mode = pps.transform_8x8_mode_flag != 0;
     std::vector<MbInfo> info((size_t)n_mbs);
     memset(info.data(), 0, sizeof(MbInfo) * (size_t)n_mbs);
     const int slice_qp = pps.pic_init_qp + h.slice_qp_delta;
+    if (!pps.entropy_coding_mode_flag) {
+        // CAVLC slice data (7.3.4): mb_skip_run in front of every coded macroblock of a P slice (and at the end of the slice)
+        std::vector<NnzInfo> nnz((size_t)n_mbs);
+        VlcWriter io{w};
+        CavlcSliceCodec<VlcWriter> codec(io, sp, info.data(), nnz.data(), 0);
+        PicDerive drv;
+        if (flags & H264E_ABSOLUTE) {
+            DeriveParams dp;
+            dp.w_mbs = s->w_mbs; dp.h_mbs = s->h_mbs;
+            dp.ref_quirks = (flags & H264E_REF_QUIRKS) != 0;
+            dp.constrained_intra_pred = pps.constrained_intra_pred_flag != 0;
+            drv.begin_picture(dp);
+            drv.begin_slice(slice_qp);
+        }
+        uint32_t skip_run = 0;
+        for (int a = 0; a < n_mbs; a++) {
+            h264s_mb& m = mbs[a];
+            int rc = normalise_mb(m, p_slice, sp.transform_8x8_mode, (flags & H264E_ABSOLUTE) != 0);
+            if (rc) return rc;
+            if (flags & H264E_ABSOLUTE) {
+                info[(size_t)a].slice = 1;
+                info[(size_t)a].kind = m.kind;
+                drv.underive_mb(a, m, info.data());
+            }
+            if (m.kind == H264S_PSKIP) {
+                if (!p_slice) return kErrState;
+                codec.skipped(a, m);
+                skip_run++;
+                continue;
+            }
+            if (p_slice) { w.ue(skip_run); skip_run = 0; }
+            rc = codec.mb(a, m);
+            if (rc) return rc;
+        }
+        if (p_slice && skip_run) w.ue(skip_run);
+        w.trailing();
+        std::vector<uint8_t> o;
+        nal_emit(h.nal_ref_idc, h.nal_unit_type, w.bytes, o);
+        if ((long)o.size() > cap) return kErrCapacity;
+        memcpy(out, o.data(), o.size());
+        return (long)o.size();
+    }
+    w.align_ones();                                        // cabac_alignment_one_bit
     CabacEncoder enc;
     enc.ctx.init(slice_qp, !p_slice, h.cabac_init_idc);
     enc.start();
@@ -247,6 +292,7 @@ struct h264d {
     Pps pps[256];
     Dpb dpb;
     std::vector<MbInfo> info;
+    std::vector<NnzInfo> nnz;               // CAVLC: total_coeff of the picture's blocks
     PicDerive drv;
     std::vector<h264r_mb_hdr> hdr;
     std::vector<int16_t> mv, coeff;
@@ -263,7 +309,6 @@ namespace {
 // slice_data() of one slice NAL into the picture's buffers.  Returns the address after the last macroblock or a negative error.
 int decode_slice_data(h264d* d, BitReader& r, const Pps& pps, const SliceHeader& h, int slice_no, int64_t* bytes)
 {
-    r.align();                                             // cabac_alignment_one_bit
     const int n_mbs = d->w_mbs * d->h_mbs;
     if (h.first_mb >= n_mbs) return d->fail(kErrBitstream, "first_mb_in_slice beyond the picture");
     SliceParams sp;
@@ -271,6 +316,54 @@ int decode_slice_data(h264d* d, BitReader& r, const Pps& pps, const SliceHeader&
     sp.num_ref_idx_l0 = h.num_ref_idx_l0; sp.transform_8x8_mode = pps.transform_8x8_mode_flag != 0;
     const int slice_qp = pps.pic_init_qp + h.slice_qp_delta;
     if (slice_qp < 0 || slice_qp > 51) return d->fail(kErrBitstream, "slice QP out of range");
+    if (!pps.entropy_coding_mode_flag) {
+        // CAVLC slice data (7.3.4)
+        *bytes += (int64_t)r.bytes_left();
+        if (d->nnz.size() != (size_t)n_mbs) d->nnz.assign((size_t)n_mbs, NnzInfo());
+        VlcReader io{r};
+        CavlcSliceCodec<VlcReader> codec(io, sp, d->info.data(), d->nnz.data(), slice_no);
+        d->drv.begin_slice(slice_qp);
+        h264s_mb local;
+        const bool keep = (d->flags & H264D_KEEP_SYNTAX) != 0;
+        int addr = h.first_mb;
+        auto finish_mb = [&](h264s_mb& m) -> int {
+            const int lim = h.num_ref_idx_l0 + (h.num_ref_idx_l0 == 0);
+            if (m.ref_idx[0] >= lim || m.ref_idx[1] >= lim || m.ref_idx[2] >= lim || m.ref_idx[3] >= lim)
+                return d->fail(kErrBitstream, "ref_idx_l0 beyond num_ref_idx_l0_active");
+            d->drv.derive_mb(addr, m, d->info.data(), &d->hdr[(size_t)addr], &d->mv[(size_t)addr * H264R_MV_PER_MB],
+                             &d->coeff[(size_t)addr * H264R_COEFF_PER_MB]);
+            if (d->hdr[(size_t)addr].mb_class <= H264R_MB_I16x16) d->n_intra++;
+            addr++;
+            return 0;
+        };
+        bool more = r.more_rbsp_data();
+        while (more) {
+            if (sp.p_slice) {
+                const uint32_t run = r.ue();
+                if (run > (uint32_t)(n_mbs - addr)) return d->fail(kErrBitstream, "mb_skip_run runs past the last macroblock");
+                for (uint32_t k = 0; k < run; k++) {
+                    if (d->info[(size_t)addr].slice != 0) return d->fail(kErrBitstream, "macroblock coded twice");
+                    h264s_mb& m = keep ? d->syntax[(size_t)addr] : local;
+                    codec.skipped(addr, m);
+                    const int rc = finish_mb(m);
+                    if (rc) return rc;
+                }
+                more = r.more_rbsp_data();
+                if (!more) break;
+            }
+            if (addr >= n_mbs) return d->fail(kErrBitstream, "slice runs past the last macroblock");
+            if (d->info[(size_t)addr].slice != 0) return d->fail(kErrBitstream, "macroblock coded twice");
+            h264s_mb& m = keep ? d->syntax[(size_t)addr] : local;
+            const int rc = codec.mb(addr, m);
+            if (rc == -2) return d->fail(kErrUnsupported, "I_PCM macroblock");
+            if (rc || r.overrun()) return d->fail(kErrBitstream, "macroblock layer");
+            const int rc2 = finish_mb(m);
+            if (rc2) return rc2;
+            more = r.more_rbsp_data();
+        }
+        return addr;
+    }
+    r.align();                                             // cabac_alignment_one_bit
     CabacDecoder dec;
     dec.ctx.init(slice_qp, !sp.p_slice, h.cabac_init_idc);
     dec.start(r.byte_ptr(), r.bytes_left());

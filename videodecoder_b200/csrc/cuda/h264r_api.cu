@@ -1059,7 +1059,7 @@ int h264r_flush(h264r_ctx* ctx)
                 auto launch = [&]() {
                     if (!SL.n) return;
                     const int total = SL.cum[SL.n];
-                    int blocks = std::min((total + ROW_WARPS - 1) / ROW_WARPS, sm_count * LIST_CTAS_PER_SM);      // persistent warps
+                    int blocks = std::min((total + ROW_WARPS - 1) / ROW_WARPS, sm_count * list_ctas_per_sm(compat));      // persistent warps
                     int* sync = sync_region(1);       // the ticket
                     ctx->sparse_stamp++;
                     prof_begin(1);

@@ -232,7 +232,11 @@ __device__ __forceinline__ void wait_progress(const int* p, int need)
     if (ld_relaxed_gpu(p) < need) {
         int spins = 0;
         do {
+#ifndef H264R_POLL_NOSLEEP
             __nanosleep(20);
+#else
+            if (spins > H264R_POLL_NOSLEEP) __nanosleep(20);      // tuning: the first polls back to back
+#endif
             if (++spins > (1 << 24)) __trap();       // seconds: a hand-over that never comes must end the launch, not hang the GPU
         } while (ld_relaxed_gpu(p) < need);
     }
@@ -429,11 +433,14 @@ __global__ void __launch_bounds__(ROW_WARPS * 64, 2) k_intra_rows(const DescTabl
 constexpr int SPARSE_PICS = 64;
 struct SparseList { int n; int slot[SPARSE_PICS]; int cum[SPARSE_PICS + 1]; };      // cum[i] = tickets before picture i
 #ifndef H264R_LIST_MIN_CTAS
-#define H264R_LIST_MIN_CTAS 4        // resident CTAs per SM k_intra_list is compiled for (4: 128 registers)
+#define H264R_LIST_MIN_CTAS 4        // resident CTAs per SM k_intra_list is compiled for in spec mode (4: 128 registers)
 #endif
-constexpr int LIST_CTAS_PER_SM = H264R_LIST_MIN_CTAS;
+#ifndef H264R_LIST_MIN_CTAS_COMPAT
+#define H264R_LIST_MIN_CTAS_COMPAT 8 // ... under REF_COMPAT (8: 64 registers, 16 bytes of spills): the benchmark's 3 900 intra macroblocks per
+#endif                               // wave then have a resident warp each instead of two in a row per warp (0.14 ms less per step)
+constexpr int list_ctas_per_sm(bool compat) { return compat ? H264R_LIST_MIN_CTAS_COMPAT : H264R_LIST_MIN_CTAS; }
 template <bool COMPAT>
-__global__ void __launch_bounds__(ROW_WARPS * 32, H264R_LIST_MIN_CTAS) k_intra_list(const DescTable descs, const __grid_constant__ SparseList list,
+__global__ void __launch_bounds__(ROW_WARPS * 32, list_ctas_per_sm(COMPAT)) k_intra_list(const DescTable descs, const __grid_constant__ SparseList list,
                                                               Geometry g, int* ticket, int stamp)
 {
     __shared__ MbWork work[ROW_WARPS];

@@ -19,6 +19,7 @@ _lib = None
 # test switches of the emulator (upper bits of `flags`, never seen by the engine)
 PACKED = 0x40000000          # store coefficients packed (mask + offset + non-zero blocks) as h264r_submit_mbs_packed does
 COMPACT = 0x20000000         # with PACKED: H264R_LEVELS_COMPACT storage (8-byte units, significance map + levels)
+GROUP_RAW = 0x04000000       # with GROUP: windows staged as aligned words and shifted by the consumer (what the tensor-copy variant of k_inter_grp does)
 PARTS = 0x08000000           # spec mode: inter macroblocks through the three parts of k_inter (luma 4x4 / luma 8x8 transform / chroma)
 GROUP = 0x10000000           # with PACKED | COMPACT under REF_COMPAT: inter macroblocks through the group sequence of k_inter_grp
 GENERIC_INTRA = 0x80000000   # run the generic intra phases of h264r_core.cuh instead of h264r_intra.cuh

@@ -241,7 +241,11 @@ unsigned long long h264emul_recon_picture(int w_mbs, int h_mbs, unsigned flags, 
     if ((flags & 0x10000000u) && mv) {
         // test switch bit 28: the group sequence of k_inter_grp (h264r_mcgrp.cuh), GRP_MBS macroblocks per step
         static GroupWork gw;
-        for (int a0 = 0; a0 < n; a0 += GRP_MBS) seq_inter_group<true>(ex, gw, pd, g, a0, n, []() {});
+        // bit 26: the tensor-copy variant's staging (aligned words, shifted by the consumer)
+        for (int a0 = 0; a0 < n; a0 += GRP_MBS) {
+            if (flags & 0x04000000u) seq_inter_group<true, true>(ex, gw, pd, g, a0, n, []() {});
+            else seq_inter_group<true, false>(ex, gw, pd, g, a0, n, []() {});
+        }
     } else
     for (int a = 0; a < n; a++) {
         h264r_mb_hdr h = load_hdr(pd, a);

@@ -51,12 +51,13 @@ def test_gop_variants(built, compat, variant):
         assert a["excursions"] == b["excursions"]
 
 
+@pytest.mark.parametrize("raw", [False, True])
 @pytest.mark.parametrize("seed,w,h,dense", [(31, 7, 5, False), (32, 11, 3, False), (33, 3, 3, True), (34, 1, 1, False), (35, 9, 2, True), (36, 17, 1, False)])
-def test_group_sequence(built, seed, w, h, dense):
+def test_group_sequence(built, seed, w, h, dense, raw):
     """the group sequence of k_inter_grp (h264r_mcgrp.cuh: residual of the coded blocks of eight macroblocks in dense passes, then
     staging + interpolation per macroblock) gives the oracle's pictures; picture sizes that leave partial groups, content dense
     enough that a group's coded blocks exceed the residual slots (the group is then taken in parts), intra macroblocks between
-    the inter ones, weighted prediction off (the lean path)"""
+    the inter ones, weighted prediction off (the lean path); raw: the staging of the tensor-copy variant (aligned words, consumer shifts)"""
     rng = np.random.default_rng(seed)
     cfg = workload.WorkloadConfig(compat=True, num_ref=2, p_intra_in_p=0.15, mv_range=80, p_sub=(0.4, 0, 0.3, 0.3), qp=int(rng.integers(16, 40)))
     if dense:       # nearly every block of every macroblock coded, small amplitudes
@@ -67,7 +68,7 @@ def test_group_sequence(built, seed, w, h, dense):
     if dense:
         assert max(int((p["coeff"].reshape(-1, 24, 16) != 0).any(axis=2).reshape(-1, 24)[:8].sum()) for p in gop[1:]) > 64
     want = run_sequence(oracle.recon_picture, w, h, abi.REF_COMPAT, gop)
-    got = run_sequence(emul.recon_picture, w, h, abi.REF_COMPAT | emul.PACKED | emul.COMPACT | emul.GROUP, gop)
+    got = run_sequence(emul.recon_picture, w, h, abi.REF_COMPAT | emul.PACKED | emul.COMPACT | emul.GROUP | (emul.GROUP_RAW if raw else 0), gop)
     for i, (a, b) in enumerate(zip(want, got)):
         for k in "yuv":
             assert np.array_equal(a[k], b[k]), "picture %d plane %s" % (i, k)

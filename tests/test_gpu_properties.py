@@ -192,6 +192,31 @@ def test_1080p_tma_window_staging(built, hd_gops):
             os.environ["H264R_TMA"] = old
 
 
+def test_group_kernel_tensor_copy_ring(built, hd_gops):
+    """k_inter_grp<.., TMA> (H264R_GROUP_TMA=1): the windows of 16x16 macroblocks by cp.async.bulk.tensor into a two-deep ring, every
+    other window as aligned words, shifted consumer: the same pictures as the default load staging -- 1080p GOPs, and a small
+    picture whose vectors point far outside (boxes at every border of the padded plane) against the oracle"""
+    w, h, gops = hd_gops
+    old = os.environ.get("H264R_GROUP_TMA")
+    try:
+        os.environ["H264R_GROUP_TMA"] = "0"
+        ref, _, _ = run_engine(w, h, abi.REF_COMPAT, gops, transport="bufmv")
+        os.environ["H264R_GROUP_TMA"] = "1"
+        dig, _, exc = run_engine(w, h, abi.REF_COMPAT, gops, transport="bufmvh8", flush="round")
+        assert exc == 0 and np.array_equal(dig, ref)
+        for seed, (pw, ph) in ((78, (9, 5)), (79, (4, 3)), (80, (1, 2))):
+            rng = np.random.default_rng(seed)
+            cfg = workload.WorkloadConfig(compat=True, mv_range=300, num_ref=2, p_intra_in_p=0.1, p_skip=0.5)
+            gop = workload.make_gop(rng, pw, ph, 4, cfg)
+            sanitize_with_oracle(pw, ph, gop)
+            check_vs_oracle(pw, ph, abi.REF_COMPAT, gop, transport="bufmv")
+    finally:
+        if old is None:
+            os.environ.pop("H264R_GROUP_TMA", None)
+        else:
+            os.environ["H264R_GROUP_TMA"] = old
+
+
 def test_frame_slot_reuse_across_gops(built, hd_gops):
     """a frame pool smaller than the job: slots are released and reused GOP after GOP (Decoder::ctrl_Memory's role)"""
     w, h, gops = hd_gops

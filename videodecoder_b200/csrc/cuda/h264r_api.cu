@@ -62,6 +62,7 @@ struct h264r_ctx {
     bool lean_inter = true;                 // k_inter<LEAN> for pictures that qualify (H264R_LEAN=0: the generic instantiation)
     bool pdl = true;                        // programmatic dependent launch of the P-wave kernels (H264R_PDL=0: plain launches)
     bool inter_parts = true;                // spec-mode lean launches as three kernels (H264R_INTER_PARTS=0: one)
+    bool tma_old = false, group_tma = false; // tensor-copy window staging in k_inter (H264R_TMA=1) / in k_inter_grp (H264R_GROUP_TMA=1): opt-in, see DESIGN.md
     bool inter_group = true;                // k_inter_grp for REF_COMPAT launches of lean pictures (H264R_INTER_GROUP=0: k_inter<LEAN>)
     int inter_group_gens = 4;               // its grid = SMs x 32 x this (H264R_GROUP_GENS)
     int inter_generations = 8;              // k_inter grid = SMs x inter_ctas_per_sm x this: a few CTA generations balance the tail
@@ -372,9 +373,11 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     CUC(cudaEventCreate(&c->ev1));
     CUC(cudaMalloc(&c->d_frames, c->frame_bytes * max_frames));
     CUC(cudaMalloc(&c->d_digests, (size_t)max_frames * 16));
-    // TMA staging of the reference windows is implemented and parity-green, but not yet the default: without a
-    // one-macroblock-ahead prefetch its latency is exposed and it measures slower than load staging
-    if (getenv("H264R_TMA") && atoi(getenv("H264R_TMA")) != 0) {
+    // Tensor maps of the padded luma planes: the tensor-copy variants of the inter kernels stage the windows of 16x16 macroblocks with them
+    // (H264R_GROUP_TMA=1: k_inter_grp<.., TMA>; H264R_TMA=1: the per-macroblock kernels k_inter<.., TMA, ..>)
+    c->tma_old = getenv("H264R_TMA") && atoi(getenv("H264R_TMA")) != 0;
+    if (getenv("H264R_GROUP_TMA")) c->group_tma = atoi(getenv("H264R_GROUP_TMA")) != 0;
+    {
         // one tensor map per frame slot and window shape over the PADDED luma plane (u8, pitch x rows); k_inter issues
         // cp.async.bulk.tensor copies of 48 x 22 (16x16 blocks) and 32 x 14 (8x8 quadrants) boxes from them
         // the encoder is a driver entry point: resolved through the runtime so that the library itself does not link
@@ -1027,13 +1030,15 @@ int h264r_flush(h264r_ctx* ctx)
                 int cap = (sm_count * ctx->inter_ctas_per_sm * (4 / KINTER_WARPS) * ctx->inter_generations + L.n - 1) / L.n;      // inter_ctas_per_sm counts four warps
                 dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)L.n);
                 prof_begin(0);
-                const bool tma = ctx->d_tmaps != nullptr;
+                const bool tma = ctx->d_tmaps != nullptr && ctx->tma_old;
                 const dim3 blk(KINTER_WARPS * 32);
                 if (lean && compat && !tma && ctx->inter_group) {
                     // group kernel: one warp per CTA, GRP_MBS macroblocks per step, inter_group_gens CTA generations
                     const int groups = (ctx->n_mbs + GRP_MBS - 1) / GRP_MBS;
                     const int gcap = (sm_count * H264R_GRP_MIN_CTAS * ctx->inter_group_gens + L.n - 1) / L.n;
-                    launch_pdl(k_inter_grp<true>, dim3((unsigned)(groups < gcap ? groups : gcap), (unsigned)L.n), dim3(32), st, pdl, d_desc, L, ctx->g);
+                    const dim3 ggrid((unsigned)(groups < gcap ? groups : gcap), (unsigned)L.n);
+                    if (ctx->group_tma && ctx->d_tmaps) launch_pdl(k_inter_grp<true, true>, ggrid, dim3(32), st, pdl, d_desc, L, ctx->g);
+                    else launch_pdl(k_inter_grp<true, false>, ggrid, dim3(32), st, pdl, d_desc, L, ctx->g);
                 } else if (lean) {
                     if (compat) { if (tma) launch_pdl(k_inter<true, true, true>, grid, blk, st, pdl, d_desc, L, ctx->g); else launch_pdl(k_inter<true, false, true>, grid, blk, st, pdl, d_desc, L, ctx->g); }
                     else if (tma) launch_pdl(k_inter<false, true, true>, grid, blk, st, pdl, d_desc, L, ctx->g);

@@ -21,8 +21,14 @@
 
 namespace h264r {
 
-constexpr int GRP_MBS = 8;          // macroblocks a warp takes at a time
-constexpr int GRP_SLOTS = 64;       // residual blocks the working set holds; a group with more active blocks is taken in parts
+#ifndef H264R_GRP_MBS
+#define H264R_GRP_MBS 8
+#endif
+#ifndef H264R_GRP_SLOTS
+#define H264R_GRP_SLOTS 64
+#endif
+constexpr int GRP_MBS = H264R_GRP_MBS;          // macroblocks a warp takes at a time
+constexpr int GRP_SLOTS = H264R_GRP_SLOTS;      // residual blocks the working set holds; a group with more active blocks is taken in parts
 
 struct alignas(16) GrpMb {          // record of one macroblock of the group, written by its lane in G0
     h264r_mb_hdr h;
@@ -37,12 +43,25 @@ constexpr uint32_t GRP_BORDER = 1u << 18, GRP_INTER = 1u << 19;
 HD int grp_slot0(uint32_t meta) { return (int)(meta & 255u); }
 HD int grp_n_items(uint32_t meta) { return (int)((meta >> 8) & 255u); }
 HD int grp_shape(uint32_t meta) { return (int)((meta >> 16) & 3u); }
+// Windows are staged as the ALIGNED words that contain them: a window that starts `s` bytes into its first word is normalised by
+// the consumer with one funnel shift per word (mc_groups<true>), so a staged word is one load and one store -- and a 16x16
+// macroblock's window can equally well arrive as a tensor copy (TMA), whose boxes must start on a 16-byte column anyway.
+// Tensor-copy boxes of 16x16 macroblocks (48 x 22 bytes, pitch 12 words) alternate between the first 1056 bytes of `win` and
+// `win_b`, so that the box of the NEXT macroblock is in flight while the current one is interpolated.
+constexpr int GRP_TMA_WORDS = TMA0_W * TMA0_H / 4;       // 264
 struct alignas(128) GroupWork {
     uint32_t win[512];              // staged windows, layouts of h264r_mc.cuh (phase_inter_stage)
     uint4 slots[GRP_SLOTS * 2];     // residual blocks: 16 int16 each, raster 4x4
     GrpMb mb[GRP_MBS];
     uint8_t items[GRP_SLOTS];       // item -> macroblock of the group << 5 | block
     uint8_t need[32];               // host emulation of the warp reduction over the lanes' NEED bits
+};
+
+// what the tensor-copy variant keeps next to the working set (kept out of GroupWork: shared memory the default kernel does not
+// use is L1 cache it loses)
+struct alignas(128) GroupTma {
+    uint32_t win_b[GRP_TMA_WORDS + 24];   // second tensor-copy buffer (+ slack: the consumer's fourth word of a row may lie behind the last row)
+    unsigned long long mbar[2];           // completion barriers of the two tensor-copy buffers
 };
 
 // bit q of a 4-bit coded_block_pattern -> nibble q (luma4x4BlkIdx 4q..4q+3 belong to 8x8 block q)
@@ -210,35 +229,85 @@ HD uint32_t grp_load_mv(const PicDesc& pd, const GrpMb& m, int lane)
     return H264R_LDG(mv32 - 1 - (ptrdiff_t)(m.mv_off + (uint32_t)mv_part_index(m.h.mb_class, m.h.sub_mb_type, lane >> 1)));
 }
 
-// M0: windows of macroblock m (load staging of phase_inter_stage, coordinates from the record)
-template <bool COMPAT>
+// Items first, first + STRIDE, ... of a window of NROWS x NWORDS ALIGNED words: word (row, j) is the aligned word at byte
+// (sx & ~3) + 4 j of row sy + row of the padded reference plane (the plane origin is 16-byte aligned, so sx & 3 is the misalignment).
+template <int NROWS, int NWORDS, int STRIDE, int DPITCH>
+HD void stage_window_raw(uint32_t* dst, const uint8_t* ref, int gpitch, int sx, int sy, int first)
+{
+    constexpr int DR = STRIDE / NWORDS, DJ = STRIDE % NWORDS;       // one step = DR rows + DJ words
+    int row = first / NWORDS, j = first - row * NWORDS;
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(ref + (ptrdiff_t)(sy + row) * gpitch + (sx & ~3)) + j;
+    const int wpitch = gpitch >> 2;
+#pragma unroll
+    for (int i = 0; i < (NROWS * NWORDS + STRIDE - 1) / STRIDE; i++) {
+        const int it = first + i * STRIDE;
+        if (it < NROWS * NWORDS) dst[DPITCH == NWORDS ? it : row * DPITCH + j] = H264R_LDG(q);
+        q += DR * wpitch + DJ;
+        if (DPITCH != NWORDS) row += DR;
+        if (DJ) {
+            j += DJ;
+            if (j >= NWORDS) { j -= NWORDS; if (DPITCH != NWORDS) row++; q += wpitch - NWORDS; }
+        }
+    }
+}
+
+// integer position of the lane's prediction block (clamped as phase_inter_stage clamps it) -> x of the window's first byte
+HD int grp_window_x(const Geometry& g, const GrpMb& m, int lane, uint32_t v)
+{
+    const int shape = grp_shape(m.meta), W = g.w_mbs * 16, x0 = (int)(m.xy & 0xffffu) * 16;
+    const int b = lane >> 1, bx = b & 3, by = b >> 2, q = (by >> 1) * 2 + (bx >> 1);
+    if (shape == 0) return clip3(-19, W + 2, x0 + (mv_x(v) >> 2)) - 2;
+    if (shape == 1) return clip3(-11, W + 2, x0 + (q & 1) * 8 + (mv_x(v) >> 2)) - 2;
+    return clip3(-7, W + 2, x0 + bx * 4 + (mv_x(v) >> 2)) - 2;
+}
+
+// M0: windows of macroblock m, load staging.  RAW: the aligned words that contain the window (the consumer shifts: the tensor-copy
+// variant, where every shape shares the shifted consumer); else words already shifted to the window's first byte (stage_window).
+template <bool COMPAT, bool RAW>
 HD void phase_grp_stage(GroupWork& w, const PicDesc& pd, const Geometry& g, const GrpMb& m, int lane, uint32_t v)
 {
     const h264r_mb_hdr& h = m.h;
     const int shape = grp_shape(m.meta);
-    const int W = g.w_mbs * 16, H = g.h_mbs * 16, x0 = (int)(m.xy & 0xffffu) * 16, y0 = (int)(m.xy >> 16) * 16;
+    const int H = g.h_mbs * 16, y0 = (int)(m.xy >> 16) * 16;
+    const int sx = grp_window_x(g, m, lane, v);
 #if !defined(__CUDA_ARCH__)
     w.need[lane] = (uint8_t)mc_need(mv_x(v) & 3, mv_y(v) & 3);
 #endif
     if (shape == 0) {
         const uint8_t* ref = pd.ref_y[hdr_ref_idx(h, 0)];
-        const int xb = clip3(-19, W + 2, x0 + (mv_x(v) >> 2)), yb = clip3(-19, H + 3, y0 + (mv_y(v) >> 2));
-        stage_window<22, 6, 32, WIN0_PITCH>(w.win, ref, g.pitch_y, xb - 2, yb - 3, lane);
+        const int yb = clip3(-19, H + 3, y0 + (mv_y(v) >> 2));
+        if (RAW) stage_window_raw<22, 6, 32, WIN0_PITCH>(w.win, ref, g.pitch_y, sx, yb - 3, lane);
+        else stage_window<22, 6, 32, WIN0_PITCH>(w.win, ref, g.pitch_y, sx, yb - 3, lane);
     } else if (shape == 1) {
         const int b = lane >> 1, bx = b & 3, by = b >> 2, q = (by >> 1) * 2 + (bx >> 1);
         const uint8_t* ref = pd.ref_y[hdr_ref_idx(h, q)];
-        const int xb = clip3(-11, W + 2, x0 + (q & 1) * 8 + (mv_x(v) >> 2)), yb = clip3(-11, H + 3, y0 + (q >> 1) * 8 + (mv_y(v) >> 2));
-        stage_window<14, 4, 8, WIN1_PITCH>(w.win + q * WIN1_STRIDE, ref, g.pitch_y, xb - 2, yb - 3, ((by & 1) * 2 + (bx & 1)) * 2 + (lane & 1));
+        const int yb = clip3(-11, H + 3, y0 + (q >> 1) * 8 + (mv_y(v) >> 2));
+        if (RAW) stage_window_raw<14, 4, 8, WIN1_PITCH>(w.win + q * WIN1_STRIDE, ref, g.pitch_y, sx, yb - 3, ((by & 1) * 2 + (bx & 1)) * 2 + (lane & 1));
+        else stage_window<14, 4, 8, WIN1_PITCH>(w.win + q * WIN1_STRIDE, ref, g.pitch_y, sx, yb - 3, ((by & 1) * 2 + (bx & 1)) * 2 + (lane & 1));
     } else {
         const int b = lane >> 1, bx = b & 3, by = b >> 2, q = (by >> 1) * 2 + (bx >> 1);
         const uint8_t* ref = pd.ref_y[hdr_ref_idx(h, q)];
         int ys = y0 + by * 4;
         // reference's source-row offset for 4x4 sub-partitions 2 and 3 (D8, h264/macroblock.cpp:786-789)
         if (COMPAT && h.mb_class == H264R_MB_P8x8 && ((h.sub_mb_type >> (2 * q)) & 3) == H264R_SUB_4x4 && (by & 1)) ys -= 3;
-        const int xb = clip3(-7, W + 2, x0 + bx * 4 + (mv_x(v) >> 2)), yb = clip3(-7, H + 3, ys + (mv_y(v) >> 2));
-        stage_window<10, 3, 2, 3>(w.win + b * 30, ref, g.pitch_y, xb - 2, yb - 3, lane & 1);
+        const int yb = clip3(-7, H + 3, ys + (mv_y(v) >> 2));
+        if (RAW) stage_window_raw<10, 3, 2, 3>(w.win + b * 30, ref, g.pitch_y, sx, yb - 3, lane & 1);
+        else stage_window<10, 3, 2, 3>(w.win + b * 30, ref, g.pitch_y, sx, yb - 3, lane & 1);
     }
 }
+
+#if defined(__CUDACC__)
+// M0 by tensor copy (16x16 macroblocks): lane 0 posts the 48 x 22 box of macroblock m -- the 16-byte columns that contain its
+// window -- into `dst` and arms `bar`; mv0 = the macroblock's vector.  Tensor coordinates are relative to the padded plane.
+__device__ __forceinline__ void grp_tma_post(uint32_t* dst, unsigned long long* bar, const PicDesc& pd, const Geometry& g, const GrpMb& m, uint32_t mv0)
+{
+    const int W = g.w_mbs * 16, H = g.h_mbs * 16, x0 = (int)(m.xy & 0xffffu) * 16, y0 = (int)(m.xy >> 16) * 16;
+    const int xb = clip3(-19, W + 2, x0 + (mv_x(mv0) >> 2)), yb = clip3(-19, H + 3, y0 + (mv_y(mv0) >> 2));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the buffer was last read through the generic proxy
+    mbar_expect_tx(bar, (uint32_t)(TMA0_W * TMA0_H));
+    tma_load_2d(dst, static_cast<const char*>(pd.tmaps) + ((size_t)tma_ref_slot(pd, hdr_ref_idx(m.h, 0)) * 2) * 128, (PAD_X + xb - 2) & ~15, PAD_Y + yb - 3, bar);
+}
+#endif
 
 // packed prediction + two residual pairs -> packed samples; returns the number of samples that left [0,255]
 template <bool COMPAT>
@@ -255,8 +324,10 @@ HD uint32_t add_residual_words(uint32_t pred, uint32_t rx, uint32_t ry, uint32_t
 }
 
 // M1: interpolation, residual from the slots, stores (REF_COMPAT: chroma = residual, D4)
-template <bool COMPAT>
-HD void phase_grp_compute(GroupWork& w, const PicDesc& pd, const Geometry& g, const GrpMb& m, int a, int lane, uint32_t v)
+// tbuf: null = the windows were load-staged into w.win; else the tensor-copy buffer that holds the macroblock's 48 x 22 box
+// SH: the windows hold aligned words (phase_grp_stage<.., RAW> / tensor copies) and the consumer shifts
+template <bool COMPAT, bool SH>
+HD void phase_grp_compute(GroupWork& w, const PicDesc& pd, const Geometry& g, const GrpMb& m, int a, int lane, uint32_t v, const uint32_t* tbuf = nullptr)
 {
     static_assert(COMPAT, "the group path covers REF_COMPAT");
     int wn;
@@ -275,14 +346,18 @@ HD void phase_grp_compute(GroupWork& w, const PicDesc& pd, const Geometry& g, co
     const int shape = grp_shape(m.meta);
     const uint32_t* wp;
     int pitch;
-    if (shape == 0) { wp = w.win + (by * 4 + half * 2) * WIN0_PITCH + bx; pitch = WIN0_PITCH; }
+    // the window starts sx & 3 bytes into its first staged word (load staging) / sx & 15 bytes into its box (tensor copy)
+    const int sx = SH ? grp_window_x(g, m, lane, v) : 0;
+    const int sh = (sx & 3) * 8;
+    if (SH && tbuf) { wp = tbuf + (by * 4 + half * 2) * TMA0_PITCH + (((PAD_X + sx) & 15) >> 2) + bx; pitch = TMA0_PITCH; }
+    else if (shape == 0) { wp = w.win + (by * 4 + half * 2) * WIN0_PITCH + bx; pitch = WIN0_PITCH; }
     else if (shape == 1) { wp = w.win + q * WIN1_STRIDE + ((by & 1) * 4 + half * 2) * WIN1_PITCH + (bx & 1); pitch = WIN1_PITCH; }
     else { wp = w.win + b * 30 + half * 2 * 3; pitch = 3; }
     const McSel sel = mc_select(mv_x(v) & 3, mv_y(v) & 3);
     uint32_t pred[2];
-    if (wn == 0) mc_patch<COMPAT, 0, false>(wp, pitch, 0, sel, pred, wn);
-    else if (!(wn & NEED_J)) mc_patch<COMPAT, 1, false>(wp, pitch, 0, sel, pred, wn);
-    else mc_patch<COMPAT, 2, false>(wp, pitch, 0, sel, pred, wn);
+    if (wn == 0) mc_patch<COMPAT, 0, SH>(wp, pitch, sh, sel, pred, wn);
+    else if (!(wn & NEED_J)) mc_patch<COMPAT, 1, SH>(wp, pitch, sh, sel, pred, wn);
+    else mc_patch<COMPAT, 2, SH>(wp, pitch, sh, sel, pred, wn);
     const int row = by * 4 + half * 2, col = bx * 4;
     uint8_t* yp = pd.y + (m.yoff + row * g.pitch_y + col);
     uint32_t exc = 0;
@@ -316,8 +391,14 @@ HD void phase_grp_compute(GroupWork& w, const PicDesc& pd, const Geometry& g, co
 
 // K1+K3 for the inter macroblocks among a0 .. a0 + GRP_MBS - 1.  `before_samples` runs once, after the residual of the
 // first part and before the first reference sample is read (the kernel awaits its predecessor there).
-template <bool COMPAT, class Exec, class Before>
-HD void seq_inter_group(Exec& ex, GroupWork& w, const PicDesc& pd, const Geometry& g, int a0, int n_mbs, Before before_samples)
+// TMA: the windows of 16x16 macroblocks arrive as tensor copies, two deep -- while macroblock i is interpolated the box of the
+// next macroblock of the part (if it is a 16x16 one) is already on its way into the other buffer -- and every other window as
+// aligned words; the consumer shifts.  (On the host, where there are no tensor copies, TMA selects the aligned-word staging for
+// every shape: the emulator covers the shifted consumer that way.)  par: phase parities of the two barriers, carried across
+// groups by the kernel; tw: the second buffer and the barriers.
+template <bool COMPAT, bool TMA, class Exec, class Before>
+HD void seq_inter_group(Exec& ex, GroupWork& w, const PicDesc& pd, const Geometry& g, int a0, int n_mbs, Before before_samples, uint32_t* par = nullptr,
+                        GroupTma* tw = nullptr)
 {
     ex([&](int lane) { phase_grp_load(w, pd, g, a0, n_mbs, lane); });
     int first = 0;
@@ -327,16 +408,47 @@ HD void seq_inter_group(Exec& ex, GroupWork& w, const PicDesc& pd, const Geometr
         const int take_end = te(0), n_items = ni(0);      // macroblocks [first, take_end) of the group are in this part, with n_items active blocks
         for (int base = 0; base < n_items; base += 32) ex([&](int lane) { phase_grp_residual<COMPAT>(w, pd, base + lane, n_items); });
         if (first == 0) before_samples();
+        // tensor staging state: `have` = the box of the macroblock at hand was posted during the previous one, into buffer hb
+        bool have = false;
+        int hb = 1;
         for (int i = first; i < take_end; i++) {
             const GrpMb& m = w.mb[i];
             if (!(m.meta & GRP_INTER)) continue;       // warp-uniform: intra (the intra kernels reconstruct it afterwards) or beyond the picture
             const int a = a0 + i;
             PerLane<uint32_t> mv_own;
+            const uint32_t* tbuf = nullptr;
+#if defined(__CUDA_ARCH__)
+            if (TMA) {
+                const bool t0 = grp_shape(m.meta) == 0;                  // this macroblock's window is a tensor copy
+                const int cb = t0 ? (have ? hb : 1) : -1;                // ... in this buffer
+                int j = i + 1;                                           // the next inter macroblock of the part
+                while (j < take_end && !(w.mb[j].meta & GRP_INTER)) j++;
+                const bool tj = j < take_end && grp_shape(w.mb[j].meta) == 0;
+                // its box goes to the buffer this macroblock leaves alone: the other tensor buffer, or win_b when this one is
+                // load-staged (into w.win, whose head is tensor buffer 0)
+                const int nb = t0 ? cb ^ 1 : 1;
+                ex([&](int lane) {
+                    mv_own(lane) = grp_load_mv(pd, m, lane);
+                    if (!t0) phase_grp_stage<COMPAT, TMA>(w, pd, g, m, lane, mv_own(lane));
+                    if (lane == 0) {
+                        if (t0 && !have) grp_tma_post(tw->win_b, &tw->mbar[1], pd, g, m, mv_own(lane));
+                        if (tj) grp_tma_post(nb ? tw->win_b : w.win, &tw->mbar[nb], pd, g, w.mb[j], grp_load_mv(pd, w.mb[j], 0));
+                    }
+                });
+                if (t0) {
+                    mbar_wait(&tw->mbar[cb], par[cb]);
+                    par[cb] ^= 1u;
+                    tbuf = cb ? tw->win_b : w.win;
+                }
+                have = tj;
+                hb = nb;
+            } else
+#endif
             ex([&](int lane) {
                 mv_own(lane) = grp_load_mv(pd, m, lane);
-                phase_grp_stage<COMPAT>(w, pd, g, m, lane, mv_own(lane));
+                phase_grp_stage<COMPAT, TMA>(w, pd, g, m, lane, mv_own(lane));
             });
-            ex([&](int lane) { phase_grp_compute<COMPAT>(w, pd, g, m, a, lane, mv_own(lane)); });
+            ex([&](int lane) { phase_grp_compute<COMPAT, TMA>(w, pd, g, m, a, lane, mv_own(lane), tbuf); });
             if (COMPAT && (m.meta & GRP_BORDER))
                 ex([&](int lane) { pad_mb_luma_cold(pd.y, g.pitch_y, g.w_mbs, g.h_mbs, (int)(m.xy & 0xffffu), (int)(m.xy >> 16), lane); });
         }

@@ -29,9 +29,12 @@ def engine_on_stream(stream, flags=0, dflags=0, transport="dense", pool=0):
             eng.submit_picture(p["frame_id"], p["pp"], p["hdr"], p["mv"], p["coeff"])
         else:
             b = eng.picture_buf(0)
-            fmt = abi.LEVELS_COMPACT if transport == "compact" else abi.LEVELS_INT16
+            fmt = abi.LEVELS_COMPACT if transport in ("compact", "compact8") else abi.LEVELS_INT16
+            if transport == "compact8":          # 8-byte headers: the host decoder writes through h264r_writer.h, which follows buf.hdr_bytes
+                b.set_header_bytes(8)
             rc, nb, nm = d.fill_picture_buf(b.c, fmt)
             if rc == abi.E_INVAL and fmt == abi.LEVELS_COMPACT:      # a level outside int8: the writer says so, the caller falls back
+                b.set_header_bytes(16)
                 rc, nb, nm = d.fill_picture_buf(b.c, abi.LEVELS_INT16)
             assert rc == 0, rc
             b.n_blocks, b.n_mvs = nb, nm
@@ -59,7 +62,7 @@ def engine_on_stream(stream, flags=0, dflags=0, transport="dense", pool=0):
     return [outs[i] for i in range(n)], exc, status
 
 
-@pytest.mark.parametrize("transport", ["dense", "compact", "int16"])
+@pytest.mark.parametrize("transport", ["dense", "compact", "compact8", "int16"])
 @pytest.mark.parametrize("name", ["spec_qcif_i", "spec_cif_ip", "spec_qcif_wp", "spec_dpb", "spec_hd1080_ip", "base_qcif_i", "base_cif_ip"])
 def test_spec_mode_equals_libavcodec(built, name, transport):
     g = load_stream_golden(name)
@@ -68,7 +71,7 @@ def test_spec_mode_equals_libavcodec(built, name, transport):
     check_against_stream_golden(g, outs, "engine (spec mode) vs libavcodec")
 
 
-@pytest.mark.parametrize("transport", ["dense", "compact"])
+@pytest.mark.parametrize("transport", ["dense", "compact", "compact8"])
 def test_ref_compat_equals_the_unmodified_reference(built, transport):
     g = load_stream_golden("ref_cif_ip_stream")
     outs, exc, status = engine_on_stream(g["stream"], flags=abi.REF_COMPAT, dflags=hoststream.REF_QUIRKS, transport=transport)

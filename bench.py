@@ -118,7 +118,7 @@ def config_of(args):
                 args.res, w, h, args.gop_len, args.gop_len - 1, args.gops,
                 "REF_COMPAT (what the reference decoder computes: 4x4 transform, luma prediction, no deblock)" if compat
                 else "spec mode (chroma prediction + MC, 8x8 transform, Intra8x8, deblocking)", WORKLOAD_SEED),
-            "mode": args.mode, "layout": args.layout, "headers": "8-byte (h264r_mb_hdr8)" if (args.hdr == "short" and args.layout == "packed") else "16-byte", "gops_per_gpu": args.gops, "gop_len": args.gop_len, "unique_gops": min(args.unique_gops, args.gops),
+            "mode": args.mode, "layout": args.layout, "headers": ({"stream": "stream form (8-byte headers + one stream per picture, H264R_HDR_STREAM)", "short": "8-byte (h264r_mb_hdr8)", "long": "16-byte"}[args.hdr] if args.layout == "packed" else "16-byte"), "gops_per_gpu": args.gops, "gop_len": args.gop_len, "unique_gops": min(args.unique_gops, args.gops),
             "sharding": "one GOP set per rank, no data-path collective",
             "l2_policy": "the syntax of a step exceeds the 126 MB L2 and is re-uploaded between timed steps"}
 
@@ -321,13 +321,15 @@ def measure(a, rank, world, local, dist, torch, extras=True):
         # one pinned picture buffer per picture of the step, in the engine's upload layout: what a host parser writes into
         packed_src = [[pack.pack_blocks(p["coeff"]) for p in g] for g in gops]
         # one RING of picture buffers per round of access units (picture i of every GOP): a round travels as one strided DMA
-        rings = [eng.picture_ring(G, max(1, max(packed_src[u][i][1].shape[0] for u in range(U)))) for i in range(F)] if a.ring else None
+        rings = [eng.picture_ring(G, max(1, max(packed_src[u][i][1].shape[0] for u in range(U))) + 2 * n_mbs) for i in range(F)] if a.ring else None
         for g in range(G):
             frames = []
             for i, p in enumerate(gops[g % U]):
                 mask, blocks = packed_src[g % U][i]
-                pb = rings[i][g] if rings else eng.picture_buf(max(1, blocks.shape[0]))
-                pb.fill(p["hdr"], p["mv"], mask, blocks, mv_partition=True, short_hdr=a.hdr == "short")
+                # (+ 2 blocks' worth of bytes per macroblock: in the stream form the vectors and masks share the block area)
+                pb = rings[i][g] if rings else eng.picture_buf(max(1, blocks.shape[0]) + (2 * n_mbs if a.hdr == "stream" else 0))
+                if not (a.hdr == "stream" and pb.fill_stream(p["hdr"], p["mv"], p["coeff"])):
+                    pb.fill(p["hdr"], p["mv"], mask, blocks, mv_partition=True, short_hdr=a.hdr != "long")
                 if g < U:
                     coded_blocks += int(blocks.shape[0])
                     level_stats[0] += int((blocks != 0).sum())
@@ -360,6 +362,8 @@ def measure(a, rank, world, local, dist, torch, extras=True):
     # unit; a ring round as one strided DMA over the union of its pictures' ranges
     def span(hb):
         base = hb.c.base
+        if hb.c.hdr_bytes == abi.HDR_STREAM:          # descriptor, 8-byte headers, word counts, the stream
+            return hb.c.mv_end - base, (hb.c.stream - base) + hb.n_blocks * 4
         return (hb.c.mv_end - base) - max(0, hb.n_mvs) * 4, (hb.c.blocks - base) + hb.n_blocks * {2: 32, 1: 16, 3: 8}[hb.c.level_bytes]
     for i in range(F):
         spans = []
@@ -614,8 +618,9 @@ def config4(rank, world, local, dist, torch):
         row = []
         for i, p in enumerate(gop):
             mask, blocks = pack.pack_blocks(p["coeff"])
-            pb = eng.picture_buf(max(1, blocks.shape[0]))
-            pb.fill(p["hdr"], p["mv"], mask, blocks, mv_partition=True, short_hdr=True)
+            pb = eng.picture_buf(max(1, blocks.shape[0]) + 2 * W_MBS * H_MBS)
+            if not pb.fill_stream(p["hdr"], p["mv"], p["coeff"]):
+                pb.fill(p["hdr"], p["mv"], mask, blocks, mv_partition=True, short_hdr=True)
             pp = abi.PicParams.from_buffer_copy(p["pp"])
             for r in range(pp.num_ref_idx_l0):
                 pp.ref_list0[r] = k * F + p["pp"].ref_list0[r]
@@ -680,7 +685,8 @@ def main():
     ap.add_argument("--config4", action="store_true", help="also run BASELINE config 4 (20 distinct GOPs, GOP g on rank g mod N); default at N > 1")
     ap.add_argument("--layout", default="packed", choices=["packed", "dense"],
                     help="coefficient transport: h264r_submit_mbs_packed (present blocks only) or h264r_submit_mbs (768 B per macroblock)")
-    ap.add_argument("--hdr", default="short", choices=["short", "long"], help="picture buffers with 8-byte (h264r_mb_hdr8) or 16-byte headers")
+    ap.add_argument("--hdr", default="stream", choices=["stream", "short", "long"],
+                    help="picture buffers in stream form (8-byte headers + one stream per picture: H264R_HDR_STREAM), with 8-byte (h264r_mb_hdr8) or with 16-byte headers")
     ap.add_argument("--ring", action="store_true", help="picture rings: one strided DMA per round of access units instead of one DMA per picture "
                     "(h264r_submit_pictures; 52 against 33 GB/s on one GPU, but the union of the pictures' byte ranges travels -- +8 %% bytes here, "
                     "which costs 5 %% at 8 GPUs, where the box's host memory bounds the uploads)")

@@ -76,6 +76,11 @@ const char* h264d_error(const h264d* d);
  * H264R_LEVELS_COMPACT or H264R_LEVELS_INT16.  Returns H264R_OK or an H264R_E_* code (H264R_E_INVAL: a level outside int8 under
  * COMPACT -- call again with INT16). */
 int    h264d_fill_picture_buf(h264d* d, h264r_picture_buf* buf, int level_fmt, size_t* n_blocks, long* n_mvs);
+/* The same packing for a caller that has a picture's syntax in the engine's dense per-macroblock arrays (hdr [n_mbs], mv
+ * [n_mbs * 32] or NULL, coeff [n_mbs * 384], include/h264r.h): runs include/h264r_writer.h over them, in whatever form the buffer
+ * was formatted for (h264r_picture_buf_format).  Returns H264R_OK or the writer's code. */
+int    h264w_pack_arrays(h264r_picture_buf* buf, int n_mbs, const h264r_mb_hdr* hdr, const int16_t* mv, const int16_t* coeff,
+                         int level_fmt, size_t* n_blocks, long* n_mvs);
 /* Parse-only throughput: decodes the whole stream `repeat` times without keeping anything; returns pictures parsed, *seconds = CPU
  * wall time of the parsing alone. */
 long   h264d_benchmark(const uint8_t* annexb, size_t n_bytes, uint32_t flags, int repeat, double* seconds);

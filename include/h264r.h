@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define H264R_ABI_VERSION 5
+#define H264R_ABI_VERSION 6
 
 /* ---- status codes ---------------------------------------------------------------------- */
 #define H264R_OK            0
@@ -114,6 +114,21 @@ typedef struct h264r_mb_hdr {
  * The prediction modes of an intra macroblock (u.pred4x4, 8 bytes) travel as the FIRST 8-byte unit of the macroblock's
  * coefficient blocks, in front of the units its blk_mask announces. */
 typedef struct h264r_mb_hdr8 { uint32_t w0, w1; } h264r_mb_hdr8;
+/* STREAM form of a picture buffer (hdr_bytes = H264R_HDR_STREAM; compact levels only): the fewest bytes on the wire.  8-byte
+ * headers, one byte per macroblock with the number of 32-bit words the macroblock has in `stream`, and the stream itself, per
+ * macroblock and in this order:
+ *   - its blk_mask word (bits 0-23 present blocks, H264R_BLK_COMPACT)            only if cbp != 0 or the macroblock is Intra16x16
+ *                                                                                 (else the mask is 0)
+ *   - u.pred4x4, two words                                                        intra macroblocks
+ *   - its vectors in partition order, one word each (x | y << 16)                 inter macroblocks; none for a P_L0_16x16 /
+ *     P_Skip macroblock whose vector fits 13 bits per component and rides in the header: w0 bit 31 (H264R_HDR8_MV_INLINE) set,
+ *     x = w1 bits 6-13 | w0 bits 9-12 << 8 | w1 bit 30 << 12, y = w1 bits 18-29 | w1 bit 31 << 12, both two's complement
+ *   - its present blocks in ascending block index: H264R_BLK_COMPACT macroblocks one word per block with at most two levels
+ *     (significance map | level << 16 | level << 24) and two words (the 8-byte unit of H264R_LEVELS_COMPACT) per block with three
+ *     to six; other macroblocks four words per block (16 int8 levels, raster).
+ * The engine expands the stream on the device (k_blk_scan) into the forms its kernels read. */
+#define H264R_HDR_STREAM       9
+#define H264R_HDR8_MV_INLINE   (1u << 31)
 
 /* Motion vectors: int16 (x, y) in quarter-sample units, one pair per 4x4 luma block in RASTER
  * order inside the macroblock (block b = 4*(y/4) + x/4), 64 bytes per MB; the final vectors
@@ -238,7 +253,10 @@ typedef struct h264r_picture_buf {
                                  blocks follow them directly (set by h264r_picture_buf_format(); H264R_LEVELS_COMPACT only) and every
                                  intra macroblock's first unit holds its u.pred4x4 bytes (counted in n_blocks)                  */
     int32_t       ring_index; /* 0: a buffer of its own; i + 1: member i of a ring (h264r_picture_ring_alloc)                       */
-    h264r_mb_hdr8* hdr8;      /* [n_mbs], hdr_bytes = 8     */
+    h264r_mb_hdr8* hdr8;      /* [n_mbs], hdr_bytes = 8 or H264R_HDR_STREAM */
+    uint8_t*      mb_words;   /* [n_mbs], H264R_HDR_STREAM: 32-bit words of each macroblock in stream[]                          */
+    uint32_t*     stream;     /* H264R_HDR_STREAM: see above; n_blocks of h264r_submit_picture counts its WORDS                  */
+    size_t        max_stream_words;
 } h264r_picture_buf;
 /* (include/h264r_writer.h: header-only helper that fills a picture buffer macroblock by macroblock in these formats.) */
 int  h264r_picture_buf_alloc(h264r_ctx* ctx, size_t max_blocks, h264r_picture_buf* out);
@@ -246,7 +264,7 @@ int  h264r_picture_buf_alloc(h264r_ctx* ctx, size_t max_blocks, h264r_picture_bu
  * per round.  h264r_submit_pictures() then ships consecutive members with one strided transfer (a round of half-megabyte pictures
  * moves faster as one DMA than as sixteen).  h264r_picture_buf_free(&out[0]) frees the ring; freeing other members is a no-op. */
 int  h264r_picture_ring_alloc(h264r_ctx* ctx, int n, size_t max_blocks, h264r_picture_buf* out /* [n] */);
-/* Chooses the header format of a picture buffer before it is filled: hdr_bytes = 16 or 8.  Re-points hdr / hdr8 / blk_mask /
+/* Chooses the header format of a picture buffer before it is filled: hdr_bytes = 16, 8 or H264R_HDR_STREAM.  Re-points hdr / hdr8 / blk_mask /
  * blocks inside the buffer (with 8-byte headers the masks and the blocks move up so that the picture stays one contiguous
  * range, 8 bytes per macroblock shorter). */
 int  h264r_picture_buf_format(h264r_ctx* ctx, h264r_picture_buf* buf, int hdr_bytes);

@@ -55,6 +55,9 @@ static inline h264r_mb_hdr8 h264r_hdr8_pack(const h264r_mb_hdr* h)
     return s;
 }
 
+/* signed 13-bit range of the inline vector of the stream form */
+static inline int h264r_mv_fits_inline(int x, int y) { return x >= -4096 && x <= 4095 && y >= -4096 && y <= 4095; }
+
 /* number of vectors the bitstream carries for a macroblock (mvd loops of macroblock::Parse, h264/macroblock.cpp:360-398) and
  * the first 4x4 block (raster) of each of them */
 static inline int h264r_writer_partitions(const h264r_mb_hdr* h, int first_block[16])
@@ -98,7 +101,56 @@ static inline int h264r_writer_mb(h264r_writer* w, const h264r_mb_hdr* hdr, cons
         }
         if (nz) { mask |= 1u << blk; n_present++; if (nz > 6) compact = 0; }
     }
-    if (b->hdr_bytes == 8 && w->level_fmt != H264R_LEVELS_COMPACT) return H264R_E_INVAL;
+    if ((b->hdr_bytes == 8 || b->hdr_bytes == H264R_HDR_STREAM) && w->level_fmt != H264R_LEVELS_COMPACT) return H264R_E_INVAL;
+    if (b->hdr_bytes == H264R_HDR_STREAM) {
+        /* stream form: everything of the macroblock behind its 8-byte header and its word count, see h264r.h */
+        uint32_t* s = b->stream + w->n_units;              /* n_units counts stream WORDS here */
+        uint32_t words[2 + 1 + 16 + 24 * 4];
+        int nw = 0, inline_mv = 0;
+        const int intra = hdr->mb_class <= H264R_MB_I16x16;
+        h264r_mb_hdr8 h8 = h264r_hdr8_pack(hdr);
+        if (compact && n_present) mask |= H264R_BLK_COMPACT;
+        if (hdr->cbp || hdr->mb_class == H264R_MB_I16x16) words[nw++] = mask;      /* (Intra16x16 DC levels come without a pattern bit) */
+        else if (mask & 0xFFFFFFu) return H264R_E_INVAL;   /* levels without coded_block_pattern */
+        if (intra) { memcpy(&words[nw], hdr->u.pred4x4, 8); nw += 2; }
+        n_part = (mv && !intra) ? h264r_writer_partitions(hdr, part) : 0;
+        if (hdr->mb_class == H264R_MB_P16x16 && n_part == 1 && h264r_mv_fits_inline(mv[0], mv[1])) {
+            const uint32_t x = (uint32_t)mv[0] & 0x1FFFu, y = (uint32_t)mv[1] & 0x1FFFu;
+            h8.w0 |= H264R_HDR8_MV_INLINE | (((x >> 8) & 15u) << 9);
+            h8.w1 = (h8.w1 & 0x3C03Fu) | ((x & 255u) << 6) | (((x >> 12) & 1u) << 30) | ((y & 0xFFFu) << 18) | (((y >> 12) & 1u) << 31);
+            inline_mv = 1;
+        } else
+            for (k = 0; k < n_part; k++) words[nw++] = (uint32_t)(uint16_t)mv[part[k] * 2] | ((uint32_t)(uint16_t)mv[part[k] * 2 + 1] << 16);
+        for (blk = 0; blk < 24; blk++) {
+            const int16_t* c = coeff + blk * 16;
+            if (!((mask >> blk) & 1u)) continue;
+            if (compact) {
+                uint8_t u[8];
+                int n = 0;
+                memset(u, 0, 8);
+                for (k = 0; k < 16; k++)
+                    if (c[k]) { u[k >> 3] |= (uint8_t)(1u << (k & 7)); u[2 + n++] = (uint8_t)(int8_t)c[k]; }
+                memcpy(&words[nw], u, 8);
+                nw += n <= 2 ? 1 : 2;
+            } else {
+                uint8_t u[16];
+                for (k = 0; k < 16; k++) u[k] = (uint8_t)(int8_t)c[k];
+                memcpy(&words[nw], u, 16);
+                nw += 4;
+            }
+        }
+        if (nw > 255) return H264R_E_INVAL;
+        if (w->n_units + (size_t)nw > b->max_stream_words) return H264R_E_CAPACITY;
+        memcpy(s, words, (size_t)nw * 4);
+        w->n_units += (size_t)nw;
+        b->hdr8[w->next_mb] = h8;
+        b->mb_words[w->next_mb] = (uint8_t)nw;
+        w->n_mvs += n_part;
+        (void)inline_mv;
+        if (intra) w->n_intra++;
+        w->next_mb++;
+        return H264R_OK;
+    }
     if (w->level_fmt == H264R_LEVELS_COMPACT) {
         uint8_t* units = (uint8_t*)b->blocks;
         const int ext = b->hdr_bytes == 8 && hdr->mb_class <= H264R_MB_I16x16;      /* prediction modes in front of the blocks */

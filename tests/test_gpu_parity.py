@@ -13,10 +13,12 @@ def engine_sequence(w_mbs, h_mbs, flags, pics, batch=True, packed=False):
     eng = engine.Engine(w_mbs, h_mbs, max_frames=len(pics), flags=flags)
     bufs = []
     for i, p in enumerate(pics):
-        if packed in ("buf", "bufmv", "bufmvh8"):
+        if packed in ("buf", "bufmv", "bufmvh8", "bufstream"):
             mask, blocks = pack.pack_blocks(p["coeff"])
-            b = eng.picture_buf(max(1, blocks.shape[0]))
-            b.fill(p["hdr"], p["mv"], mask, blocks, mv_partition=packed != "buf", short_hdr=packed == "bufmvh8")     # bufmvh8: 8-byte headers
+            b = eng.picture_buf(0 if packed == "bufstream" else max(1, blocks.shape[0]))
+            # bufmvh8: 8-byte headers; bufstream: the stream form (a picture with a level beyond int8 falls back to the 16-byte form)
+            if not (packed == "bufstream" and b.fill_stream(p["hdr"], p["mv"], p["coeff"])):
+                b.fill(p["hdr"], p["mv"], mask, blocks, mv_partition=packed != "buf", short_hdr=packed == "bufmvh8")
             bufs.append(b)
             eng.submit_picture_buf(i, p["pp"], b)
         elif packed:
@@ -37,7 +39,7 @@ def engine_sequence(w_mbs, h_mbs, flags, pics, batch=True, packed=False):
 
 
 @pytest.mark.parametrize("name", ["qcif_i", "cif_ip", "qcif_wp", "hd1080_ip"])
-@pytest.mark.parametrize("batch,packed", [(True, False), (False, False), (True, True), (False, True), (True, "buf"), (False, "buf"), (True, "bufmv"), (False, "bufmv"), (True, "bufmvh8"), (False, "bufmvh8")])
+@pytest.mark.parametrize("batch,packed", [(True, False), (False, False), (True, True), (False, True), (True, "buf"), (False, "buf"), (True, "bufmv"), (False, "bufmv"), (True, "bufmvh8"), (False, "bufmvh8"), (True, "bufstream"), (False, "bufstream")])
 def test_golden_reference_parity(built, name, batch, packed):
     """bit-exact Y/U/V against what the reference decoder reconstructed (MD5 + planes); dense and packed submits,
     one flush for the whole sequence and one flush per picture."""
@@ -52,7 +54,7 @@ def test_golden_reference_parity(built, name, batch, packed):
         assert bytes(dig[i]) == oracle.digest(o["y"], o["u"], o["v"])
 
 
-@pytest.mark.parametrize("packed", [False, True, "buf", "bufmv", "bufmvh8"])
+@pytest.mark.parametrize("packed", [False, True, "buf", "bufmv", "bufmvh8", "bufstream"])
 @pytest.mark.parametrize("name", ["qcif_i", "cif_ip", "qcif_wp"])
 def test_spec_mode_vs_oracle(built, name, packed):
     """same syntax in spec mode (Clip1, chroma prediction/MC, deblocking): engine == oracle."""

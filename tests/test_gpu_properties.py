@@ -42,12 +42,13 @@ def run_engine(w, h, flags, gops, transport="buf", flush="all", max_frames=None)
             if transport == "packed":
                 eng.submit_picture_packed(fid, pp, np.ascontiguousarray(p["hdr"]), p["mv"], mask, blocks)
             else:
-                b = eng.picture_buf(max(1, blocks.shape[0]))
+                b = eng.picture_buf(0 if transport == "bufstream" else max(1, blocks.shape[0]))
                 # bufmv: the narrowest storage (compact units); bufmv8: int8 blocks; bufmv16: int16 blocks
-                # bufmvh8: compact units + 8-byte headers
-                b.fill(p["hdr"], p["mv"], mask, blocks, mv_partition=transport in ("bufmv", "bufmv8", "bufmv16", "bufmvh8"),
-                       level8=False if transport == "bufmv16" else None, compact=False if transport == "bufmv8" else None,
-                       short_hdr=transport == "bufmvh8")
+                # bufmvh8: compact units + 8-byte headers; bufstream: the stream form
+                if not (transport == "bufstream" and b.fill_stream(p["hdr"], p["mv"], p["coeff"])):
+                    b.fill(p["hdr"], p["mv"], mask, blocks, mv_partition=transport in ("bufmv", "bufmv8", "bufmv16", "bufmvh8", "bufstream"),
+                           level8=False if transport == "bufmv16" else None, compact=False if transport == "bufmv8" else None,
+                           short_hdr=transport == "bufmvh8")
                 bufs.append(b)
                 eng.submit_picture_buf(fid, pp, b)
         if flush == "each":
@@ -94,7 +95,7 @@ def test_ragged_geometries(built, compat, w, h):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("transport", ["bufmv", "bufmv8", "bufmvh8", "packed"])
+@pytest.mark.parametrize("transport", ["bufmv", "bufmv8", "bufmvh8", "bufstream", "packed"])
 def test_compact_transport_dense_and_extreme_levels(built, transport):
     """H264R_LEVELS_COMPACT with macroblocks of every kind: all blocks sparse (one unit per block), blocks with 7..16 levels
     (plain int8 blocks, two units), levels at -128 / 127; Intra16x16 and chroma DC levels read through the compact form.
@@ -141,7 +142,7 @@ def test_1080p_transport_and_flush_invariance(built, hd_gops):
     w, h, gops = hd_gops
     ref, lasts, exc = run_engine(w, h, abi.REF_COMPAT, gops, transport="dense", flush="all")
     assert exc == 0
-    for transport, flush in (("packed", "all"), ("buf", "each"), ("bufmv", "round"), ("bufmv", "all"), ("bufmvh8", "round"), ("bufmvh8", "all"), ("bufmv8", "all"), ("bufmv16", "all")):
+    for transport, flush in (("packed", "all"), ("buf", "each"), ("bufmv", "round"), ("bufmv", "all"), ("bufmvh8", "round"), ("bufmvh8", "all"), ("bufstream", "round"), ("bufstream", "all"), ("bufmv8", "all"), ("bufmv16", "all")):
         dig, _, exc = run_engine(w, h, abi.REF_COMPAT, gops, transport=transport, flush=flush)
         assert exc == 0
         assert np.array_equal(dig, ref), (transport, flush)
@@ -505,3 +506,4 @@ def test_maximum_picture_width(built, compat):
     if compat:
         sanitize_with_oracle(w, h, gop)
     check_vs_oracle(w, h, abi.REF_COMPAT if compat else 0, gop, transport="bufmvh8")
+    check_vs_oracle(w, h, abi.REF_COMPAT if compat else 0, gop, transport="bufstream")

@@ -149,3 +149,107 @@ def test_short_headers_c_writer_and_python_twin(tmp_path):
         per_mb = np.array([bin(int(m) & 0xFFFFFF).count("1") * (1 if int(m) & abi.BLK_COMPACT else 2) for m in cmask]) + intra
         first = np.concatenate(([0], np.cumsum(per_mb)))[:-1]
         assert np.array_equal(units_c[first[intra]], hdr["u"].reshape(-1, 8)[intra].view(np.uint8))
+
+
+def unpack_stream(hdr8, mb_words, stream):
+    """plain restatement of the stream form (H264R_HDR_STREAM, include/h264r.h) -- what k_blk_scan's expansion produces on the device:
+    16-byte headers, dense block masks, 8-byte units, the vectors in partition order"""
+    n = hdr8.shape[0]
+    hdr = unpack_hdr8(hdr8)
+    mask = np.zeros(n, dtype=np.uint32)
+    units, mvs = [], []
+    wo = 0
+    for a in range(n):
+        w0, w1 = int(hdr8[a, 0]), int(hdr8[a, 1])
+        cls = w0 & 7
+        intra = cls <= abi.MB_I16x16
+        inline = (not intra) and bool(w0 >> 31)
+        p = wo
+        if (w1 & 63) or cls == abi.MB_I16x16:
+            mask[a] = stream[p]; p += 1
+        if intra:
+            hdr["u"].reshape(-1, 8)[a] = stream[p:p + 2].view(np.uint8); p += 2
+        elif inline:
+            x = ((w1 >> 6) & 255) | (((w0 >> 9) & 15) << 8) | (((w1 >> 30) & 1) << 12)
+            y = ((w1 >> 18) & 0xFFF) | ((w1 >> 31) << 12)
+            sx = lambda v: v - 8192 if v & 4096 else v
+            mvs.append((sx(x), sx(y)))
+            hdr["intra_modes"][a] = 0; hdr["sub_mb_type"][a] = 0
+            hdr["u"].reshape(-1, 8)[a, 1:4] = hdr["u"].reshape(-1, 8)[a, 0]       # the reference index of a 16x16 macroblock, in all four quadrant fields
+        else:
+            sub = (w1 >> 6) & 255
+            cnt = {abi.MB_P16x16: 1, abi.MB_P16x8: 2, abi.MB_P8x16: 2}.get(cls, sum((1, 2, 2, 4)[(sub >> (2 * q)) & 3] for q in range(4)))
+            for i in range(cnt):
+                v = int(stream[p + i])
+                mvs.append((np.int16(np.uint16(v & 0xffff)), np.int16(np.uint16(v >> 16))))
+            p += cnt
+        m = int(mask[a])
+        for b in range(24):
+            if not (m >> b) & 1:
+                continue
+            if m & abi.BLK_COMPACT:
+                first = int(stream[p])
+                if bin(first & 0xffff).count("1") <= 2:
+                    units.append(np.array([first, 0], dtype=np.uint32).view(np.uint8)); p += 1
+                else:
+                    units.append(stream[p:p + 2].view(np.uint8)); p += 2
+            else:
+                units.append(stream[p:p + 2].view(np.uint8)); units.append(stream[p + 2:p + 4].view(np.uint8)); p += 4
+        assert p - wo == int(mb_words[a]), "macroblock %d: %d words walked, %d announced" % (a, p - wo, mb_words[a])
+        wo = p
+    return hdr, mask, (np.array(units, dtype=np.uint8).reshape(-1, 8)), np.array(mvs, dtype=np.int16).reshape(-1, 2), wo
+
+
+def test_stream_form_c_writer_against_restatement(built):
+    """the stream form written by include/h264r_writer.h (through libh264host's h264w_pack_arrays) expands -- by the plain restatement
+    above of what k_blk_scan does -- to exactly what the other picture-buffer forms carry: headers, masks, compact units, vectors in
+    partition order; P_L0_16x16 vectors ride in the header when they fit 13 bits and in the stream when they do not"""
+    import ctypes
+    from videodecoder_b200 import engine, hoststream, workload
+    rng = np.random.default_rng(99)
+    wm, hm = 10, 6
+    n = wm * hm
+    cfg = workload.WorkloadConfig(compat=False, num_ref=3, p_intra_in_p=0.15, p_i8x8=0.3, p_t8x8=0.3, p_sub=(0.25, 0.25, 0.25, 0.25), mv_range=200)
+    total_saved = 0
+    for pi, p in enumerate(workload.make_gop(rng, wm, hm, 4, cfg)):
+        hdr = np.ascontiguousarray(p["hdr"]).view(abi.MB_HDR_DTYPE).reshape(-1).copy()
+        coeff = np.ascontiguousarray(p["coeff"], dtype=np.int16).copy()
+        mv = np.ascontiguousarray(p["mv"], dtype=np.int16).copy() if p["mv"] is not None else None
+        if mv is not None:      # a few vectors beyond the inline range
+            big = np.flatnonzero(hdr["mb_class"] == abi.MB_P16x16)[:3]
+            mv[big] = np.tile(np.array([5000, -4500], dtype=np.int16), 16)
+        c3 = coeff.reshape(n, 24, 16)
+        if pi == 2:             # a macroblock with a dense block: plain int8 storage, four words per block
+            a = int(np.flatnonzero(hdr["cbp"] & 1)[0])
+            c3[a, 0, :9] = np.arange(1, 10)
+        hdr8 = np.zeros((n, 2), dtype=np.uint32); words = np.zeros(n, dtype=np.uint8); stream = np.zeros(n * 120, dtype=np.uint32)
+        buf = engine.PictureBufStruct()
+        buf.hdr8 = hdr8.ctypes.data; buf.mb_words = words.ctypes.data; buf.stream = stream.ctypes.data
+        buf.max_stream_words = stream.size; buf.hdr_bytes = abi.HDR_STREAM
+        nb, nm = ctypes.c_size_t(0), ctypes.c_long(0)
+        rc = hoststream.lib().h264w_pack_arrays(ctypes.byref(buf), n, hdr.ctypes.data_as(ctypes.c_void_p), mv.ctypes.data_as(ctypes.c_void_p) if mv is not None else None,
+                                                coeff.ctypes.data_as(ctypes.c_void_p), abi.LEVELS_COMPACT, ctypes.byref(nb), ctypes.byref(nm))
+        assert rc == 0
+        got_hdr, got_mask, got_units, got_mvs, used = unpack_stream(hdr8, words, stream)
+        assert used == nb.value == int(words.sum())
+        mask, blocks = pack.pack_blocks(coeff)
+        cmask, units = pack.pack_compact(mask, blocks)
+        assert np.array_equal(got_mask, cmask) and np.array_equal(got_units, units)
+        intra = hdr["mb_class"] <= abi.MB_I16x16
+        for k in ("mb_class", "flags", "qp_y", "qp_cb", "qp_cr", "cbp"):
+            assert np.array_equal(got_hdr[k], hdr[k]), k
+        assert np.array_equal(got_hdr["intra_modes"][intra], hdr["intra_modes"][intra])
+        assert np.array_equal(got_hdr["u"].reshape(-1, 8)[intra], hdr["u"].reshape(-1, 8)[intra])
+        p8 = hdr["mb_class"] == abi.MB_P8x8
+        assert np.array_equal(got_hdr["sub_mb_type"][p8], hdr["sub_mb_type"][p8])
+        inter = ~intra
+        assert np.array_equal(got_hdr["u"].reshape(-1, 8)[inter][:, 0], hdr["u"].reshape(-1, 8)[inter][:, 0])
+        assert np.array_equal(got_hdr["u"].reshape(-1, 8)[inter][:, :4], hdr["u"].reshape(-1, 8)[inter][:, :4])
+        if mv is not None:
+            want = pack.pack_mvs_partition(hdr, mv)
+            assert np.array_equal(got_mvs, want) and nm.value == want.shape[0]
+            inl = (hdr8[:, 0] >> 31).astype(bool)
+            assert inl.sum() == (hdr["mb_class"] == abi.MB_P16x16).sum() - 3
+        short_bytes = 8 * n + 4 * n + units.shape[0] * 8 + (0 if mv is None else 4 * pack.pack_mvs_partition(hdr, mv).shape[0]) + 8 * int(intra.sum())
+        total_saved += short_bytes - (9 * n + 4 * used)
+    assert total_saved > 0

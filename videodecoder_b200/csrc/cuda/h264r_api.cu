@@ -32,6 +32,7 @@ struct Pending {
     size_t n_blocks;        // packed: coefficient blocks stored so far
     bool mv_partition;      // vectors in partition order (h264r_submit_picture with n_mvs >= 0)
     bool short_hdr;         // picture buffer with 8-byte headers (h264r_picture_buf.hdr_bytes = 8): k_blk_scan expands them
+    bool stream;            // ... in stream form (H264R_HDR_STREAM): k_blk_scan expands headers, masks, vectors and blocks
     int level_bytes;        // H264R_LEVELS_*: int16 levels (32-byte blocks); picture buffers only: int8 levels (16-byte blocks), compact (8-byte units)
     uint64_t seq;           // order of frame_end calls (= order of the uploads on the copy stream)
     bool early;             // flush: the upload had landed when the flush began (index structures made up front, nothing to wait for)
@@ -113,6 +114,8 @@ struct h264r_ctx {
     size_t slot_bytes = 0, off_desc = 0, off_hdr = 0, off_mv = 0, off_mask = 0, off_boff = 0, off_mvoff = 0, off_coeff = 0, off_res = 0, off_nz = 0, off_dbrec = 0, off_ilist = 0, off_idone = 0, off_mbox = 0, off_hdr16 = 0;
     // 8-byte headers: masks and blocks of the upload move up behind the shorter header array
     size_t off_mask_s = 0, off_coeff_s = 0;
+    // stream form: word counts and stream behind the 8-byte headers (upload); expanded masks / units in device-only areas
+    size_t off_words = 0, off_stream = 0, off_xmask = 0, off_xunits = 0;
     uint32_t mbox_stamp = 0;                // launch number of k_deblock_rows (stamp of its hand-over records)
     int sparse_stamp = 0;                   // launch stamp of k_intra_list (intra_done words of older launches are smaller)
     // per-flush control block (descriptors + picture lists), pinned host mirror + device copy
@@ -191,11 +194,13 @@ void fill_desc(h264r_ctx* c, const Pending& p, PicDesc& pd)
     uint8_t* s = c->slot_ptr(p.slot);
     pd.hdr = reinterpret_cast<const h264r_mb_hdr*>(s + (p.short_hdr ? c->off_hdr16 : c->off_hdr));
     pd.hdr8 = p.short_hdr ? reinterpret_cast<const uint2*>(s + c->off_hdr) : nullptr;
+    pd.mb_words = p.stream ? s + c->off_words : nullptr;
+    pd.stream = p.stream ? reinterpret_cast<const uint32_t*>(s + c->off_stream) : nullptr;
     pd.mv = reinterpret_cast<const int16_t*>(s + (p.mv_partition ? c->off_desc : c->off_mv));
-    pd.coeff = reinterpret_cast<const int16_t*>(s + (p.short_hdr ? c->off_coeff_s : c->off_coeff));
+    pd.coeff = reinterpret_cast<const int16_t*>(s + (p.stream ? c->off_xunits : (p.short_hdr ? c->off_coeff_s : c->off_coeff)));
     pd.level_fmt = p.level_bytes;
     if (p.layout == 2) {
-        pd.blk_mask = reinterpret_cast<const uint32_t*>(s + (p.short_hdr ? c->off_mask_s : c->off_mask));
+        pd.blk_mask = reinterpret_cast<const uint32_t*>(s + (p.stream ? c->off_xmask : (p.short_hdr ? c->off_mask_s : c->off_mask)));
         pd.blk_off = reinterpret_cast<const uint32_t*>(s + c->off_boff);
     } else { pd.blk_mask = c->d_dense_mask; pd.blk_off = c->d_dense_off; }
     pd.nzmask = reinterpret_cast<uint32_t*>(s + c->off_nz);
@@ -299,7 +304,11 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     c->off_idone = c->off_ilist + align_up((size_t)(c->n_mbs + 1) * 4, 256);
     c->off_mbox = c->off_idone + align_up((size_t)c->n_mbs * 4, 256);
     c->off_hdr16 = c->off_mbox + ((flags & H264R_REF_COMPAT) ? 0 : align_up((size_t)c->n_mbs * MBOX_WORDS * 4, 256));      // device only: headers expanded from the 8-byte form
-    c->slot_bytes = c->off_hdr16 + align_up((size_t)c->n_mbs * sizeof(h264r_mb_hdr), 256);
+    c->off_xmask = c->off_hdr16 + align_up((size_t)c->n_mbs * sizeof(h264r_mb_hdr), 256);
+    c->off_xunits = c->off_xmask + align_up((size_t)c->n_mbs * 4, 256);
+    c->slot_bytes = c->off_xunits + align_up((size_t)c->n_mbs * 48 * 8, 256);          // 24 blocks x two 8-byte units
+    c->off_words = c->off_hdr + (size_t)c->n_mbs * sizeof(h264r_mb_hdr8);
+    c->off_stream = align_up(c->off_words + (size_t)c->n_mbs, 16);
     c->off_mask_s = c->off_hdr + (size_t)c->n_mbs * sizeof(h264r_mb_hdr8);
     c->off_coeff_s = align_up(c->off_mask_s + (size_t)c->n_mbs * 4, 16);
     c->ctrl_bytes = align_up((size_t)max_pending * sizeof(PicDesc), 256);      // descriptor table, one entry per arena slot
@@ -614,6 +623,7 @@ int h264r_picture_buf_alloc(h264r_ctx* ctx, size_t max_blocks, h264r_picture_buf
     out->hdr_bytes = 16;
     out->ring_index = 0;
     out->hdr8 = nullptr;
+    out->mb_words = nullptr; out->stream = nullptr; out->max_stream_words = 0;
     return H264R_OK;
 }
 
@@ -639,20 +649,25 @@ int h264r_picture_ring_alloc(h264r_ctx* ctx, int n, size_t max_blocks, h264r_pic
         out[i].hdr_bytes = 16;
         out[i].ring_index = i + 1;
         out[i].hdr8 = nullptr;
+        out[i].mb_words = nullptr; out[i].stream = nullptr; out[i].max_stream_words = 0;
     }
     return H264R_OK;
 }
 
 int h264r_picture_buf_format(h264r_ctx* ctx, h264r_picture_buf* buf, int hdr_bytes)
 {
-    if (!ctx || !buf || !buf->base || (hdr_bytes != 16 && hdr_bytes != 8)) return fail(ctx, H264R_E_INVAL, "picture_buf_format: bad argument");
+    if (!ctx || !buf || !buf->base || (hdr_bytes != 16 && hdr_bytes != 8 && hdr_bytes != H264R_HDR_STREAM))
+        return fail(ctx, H264R_E_INVAL, "picture_buf_format: bad argument");
     uint8_t* b = static_cast<uint8_t*>(buf->base);
-    const bool s8 = hdr_bytes == 8;
+    const bool s8 = hdr_bytes == 8, st = hdr_bytes == H264R_HDR_STREAM;
     buf->hdr_bytes = hdr_bytes;
     buf->hdr = reinterpret_cast<h264r_mb_hdr*>(b + ctx->off_hdr);
-    buf->hdr8 = s8 ? reinterpret_cast<h264r_mb_hdr8*>(b + ctx->off_hdr) : nullptr;
+    buf->hdr8 = (s8 || st) ? reinterpret_cast<h264r_mb_hdr8*>(b + ctx->off_hdr) : nullptr;
     buf->blk_mask = reinterpret_cast<uint32_t*>(b + (s8 ? ctx->off_mask_s : ctx->off_mask));
     buf->blocks = reinterpret_cast<int16_t*>(b + (s8 ? ctx->off_coeff_s : ctx->off_coeff));
+    buf->mb_words = st ? b + ctx->off_words : nullptr;
+    buf->stream = st ? reinterpret_cast<uint32_t*>(b + ctx->off_stream) : nullptr;
+    buf->max_stream_words = st ? (ctx->off_coeff + buf->max_blocks * 32 - ctx->off_stream) / 4 : 0;
     return H264R_OK;
 }
 
@@ -668,13 +683,17 @@ void h264r_picture_buf_free(h264r_ctx* ctx, h264r_picture_buf* buf)
 // *first / *end: the byte range of the buffer (= of the arena slot) that has to travel.
 static int prepare_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf* buf, size_t n_blocks, long n_mvs, Pending** out, size_t* first_out, size_t* end_out)
 {
-    if (!ctx || !buf || !buf->base || n_blocks > buf->max_blocks * (buf->level_bytes == H264R_LEVELS_COMPACT ? 4 : 1) || n_mvs > (long)16 * (ctx ? ctx->n_mbs : 0) ||
+    const bool stream = buf && buf->hdr_bytes == H264R_HDR_STREAM;
+    if (!ctx || !buf || !buf->base || (!stream && n_blocks > buf->max_blocks * (buf->level_bytes == H264R_LEVELS_COMPACT ? 4 : 1)) ||
+        (stream && (n_blocks > buf->max_stream_words || n_mvs < 0)) || n_mvs > (long)16 * (ctx ? ctx->n_mbs : 0) ||
         (buf->level_bytes != H264R_LEVELS_INT8 && buf->level_bytes != H264R_LEVELS_INT16 && buf->level_bytes != H264R_LEVELS_COMPACT))
         return fail(ctx, H264R_E_INVAL, "submit_picture: bad argument");
     Pending* p = find_pending(ctx, frame_id);
     if (!p || p->ended) return fail(ctx, H264R_E_STATE, "submit_picture: no open picture with this frame id");
     if (p->layout || p->n_submitted) return fail(ctx, H264R_E_STATE, "submit_picture: the picture already has macroblocks");
-    const bool short_hdr = buf->hdr_bytes == 8;
+    const bool short_hdr = buf->hdr_bytes == 8 || stream;
+    if (stream && buf->stream != reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(buf->base) + ctx->off_stream))
+        return fail(ctx, H264R_E_INVAL, "submit_picture: the stream form needs a buffer formatted by h264r_picture_buf_format");
     if (short_hdr && (buf->level_bytes != H264R_LEVELS_COMPACT || buf->hdr8 != reinterpret_cast<h264r_mb_hdr8*>(static_cast<uint8_t*>(buf->base) + ctx->off_hdr)))
         return fail(ctx, H264R_E_INVAL, "submit_picture: 8-byte headers need H264R_LEVELS_COMPACT and a buffer formatted by h264r_picture_buf_format");
     if (buf->n_intra >= 0) {
@@ -704,16 +723,17 @@ static int prepare_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf
     p->n_submitted = ctx->n_mbs;
     p->mv_partition = n_mvs >= 0;
     p->short_hdr = short_hdr;
+    p->stream = stream;
     p->level_bytes = buf->level_bytes;
     // ONE transfer: the vectors present (backward from the descriptor), descriptor, headers, masks, the blocks present
     uint8_t* hb = static_cast<uint8_t*>(buf->base);
     fill_desc(ctx, *p, *reinterpret_cast<PicDesc*>(hb + ctx->off_desc));
     const bool is_p = p->pp.slice_type == H264R_SLICE_P;
-    const size_t mv_bytes = !is_p ? 0 : (n_mvs >= 0 ? (size_t)n_mvs * 4 : ctx->off_desc);      // per-4x4 layout: the whole area
+    const size_t mv_bytes = (!is_p || stream) ? 0 : (n_mvs >= 0 ? (size_t)n_mvs * 4 : ctx->off_desc);      // per-4x4 layout: the whole area; stream form: inside the stream
     const size_t first = ctx->off_desc - mv_bytes;
     const size_t unit_bytes = buf->level_bytes == H264R_LEVELS_INT16 ? 32 : (buf->level_bytes == H264R_LEVELS_INT8 ? 16 : 8);
     *first_out = first;
-    *end_out = (short_hdr ? ctx->off_coeff_s : ctx->off_coeff) + n_blocks * unit_bytes;
+    *end_out = stream ? ctx->off_stream + n_blocks * 4 : (buf->hdr_bytes == 8 ? ctx->off_coeff_s : ctx->off_coeff) + n_blocks * unit_bytes;
     *out = p;
     return H264R_OK;
 }

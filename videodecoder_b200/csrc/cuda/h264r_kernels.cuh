@@ -582,9 +582,152 @@ __global__ void __launch_bounds__(128) k_deblock_prep(const DescTable descs, con
 // The three scans share the passes (block count in the low, vector count in the high half of a 64-bit word; intra
 // count in a second word).
 // ------------------------------------------------------------------------------------------------
+// exclusive prefix of v over the CTA's 1024 threads (sm: 33 words; total = the sum over the CTA); all threads call it
+__device__ __forceinline__ unsigned long long cta_excl_prefix(unsigned long long v, unsigned long long* sm, unsigned long long& total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) sm[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned long long x = sm[lane];
+        unsigned long long ix = x;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, ix, o);
+            if (lane >= o) ix += t;
+        }
+        sm[lane] = ix - x;
+        if (lane == 31) sm[32] = ix;
+    }
+    __syncthreads();
+    const unsigned long long r = sm[warp] + incl - v;
+    total = sm[32];
+    __syncthreads();
+    return r;
+}
+
+// k_blk_scan for a picture in STREAM form (H264R_HDR_STREAM, include/h264r.h): the wire carries 8-byte headers, a word count per
+// macroblock and one stream with each macroblock's mask, prediction modes, vectors and blocks; this expands it into what the
+// kernels read -- 16-byte headers, dense masks, the vector stream in partition order, 8-byte units -- next to the usual index
+// structures.  Two prefix sums per tile: the stream offsets (from the word counts), then unit / vector / intra counts (the
+// masks are IN the stream, so they can only be read once the offsets are known).
+__device__ void blk_scan_stream(const PicDesc& pd, int n_mbs)
+{
+    __shared__ unsigned long long sm[33];
+    h264r_mb_hdr* hdr16 = const_cast<h264r_mb_hdr*>(pd.hdr);
+    uint32_t* xmask = const_cast<uint32_t*>(pd.blk_mask);
+    uint2* xunits = reinterpret_cast<uint2*>(const_cast<int16_t*>(pd.coeff));
+    uint32_t* xmv = reinterpret_cast<uint32_t*>(const_cast<int16_t*>(pd.mv));       // entry i at xmv[-1 - i]
+    uint32_t* off = const_cast<uint32_t*>(pd.blk_off);
+    uint32_t* mvoff = const_cast<uint32_t*>(pd.mv_off);
+    uint32_t* ilist = pd.intra_list;
+    unsigned long long wbase = 0, base = 0, ibase = 0;
+    for (int t0 = 0; t0 < n_mbs; t0 += 8192) {
+        const int first = t0 + (int)threadIdx.x * 8;
+        // the eight word counts of this thread's macroblocks (the array is 16-byte aligned, `first` a multiple of 8)
+        uint2 wc = uint2{0u, 0u};
+        if (first + 8 <= n_mbs) wc = __ldg(reinterpret_cast<const uint2*>(pd.mb_words + first));
+        else for (int k = 0; k < 8; k++) if (first + k < n_mbs) { const uint32_t b = __ldg(pd.mb_words + first + k); if (k < 4) wc.x |= b << (8 * k); else wc.y |= b << (8 * (k - 4)); }
+        const uint32_t s4 = (wc.x & 0x00ff00ffu) + ((wc.x >> 8) & 0x00ff00ffu) + (wc.y & 0x00ff00ffu) + ((wc.y >> 8) & 0x00ff00ffu);
+        unsigned long long tot;
+        const uint32_t woff0 = (uint32_t)(wbase + cta_excl_prefix((s4 & 0xffffu) + (s4 >> 16), sm, tot));
+        wbase += tot;
+        // counts: units in the low, vectors in the high half; intra separately
+        uint32_t c[8];
+        unsigned long long sum = 0;
+        uint32_t n_intra = 0;
+        {
+            uint32_t wo = woff0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                c[k] = 0;
+                if (first + k < n_mbs) {
+                    const uint2 s8 = __ldg(pd.hdr8 + first + k);
+                    const int cls = (int)(s8.x & 7u);
+                    const uint32_t mw = ((s8.y & 63u) || cls == H264R_MB_I16x16) ? __ldg(pd.stream + wo) : 0u;
+                    const uint32_t units = (uint32_t)__popc(mw & 0xFFFFFFu) << ((mw & H264R_BLK_COMPACT) ? 0 : 1);
+                    const uint32_t mvs = (uint32_t)mv_count(cls, (int)((s8.y >> 6) & 255u));
+                    c[k] = units | (mvs << 8) | (is_intra(cls) ? 1u << 16 : 0u);
+                    sum += (unsigned long long)units | ((unsigned long long)mvs << 32);
+                    n_intra += is_intra(cls) ? 1u : 0u;
+                    if (cls == 3 || cls > H264R_MB_P8x8) atomicOr(pd.exc_counter + 1, H264R_STATUS_BAD_CLASS);
+                    else if (!is_intra(cls) && pd.slice_type != H264R_SLICE_P) atomicOr(pd.exc_counter + 1, H264R_STATUS_INTER_IN_I);
+                }
+                wo += (k < 4 ? wc.x >> (8 * k) : wc.y >> (8 * (k - 4))) & 255u;
+            }
+        }
+        unsigned long long run = base + cta_excl_prefix(sum, sm, tot);
+        base += tot;
+        uint32_t irun = (uint32_t)(ibase + cta_excl_prefix(n_intra, sm, tot));
+        ibase += tot;
+        // expansion
+        uint32_t wo = woff0;
+#pragma unroll 1
+        for (int k = 0; k < 8; k++) {
+            const int a = first + k;
+            if (a >= n_mbs) break;
+            const uint32_t nw = (k < 4 ? wc.x >> (8 * k) : wc.y >> (8 * (k - 4))) & 255u;
+            const uint2 s8 = __ldg(pd.hdr8 + a);
+            const bool intra = (c[k] >> 16) & 1u, inl = !intra && (s8.x & H264R_HDR8_MV_INLINE);
+            const uint32_t* p = pd.stream + wo;
+            uint32_t mw = 0;
+            if ((s8.y & 63u) || (s8.x & 7u) == H264R_MB_I16x16) mw = __ldg(p++);
+            // 16-byte header (fields of h264r_mb_hdr8; an inline vector borrows intra_modes, sub_mb_type and ref_idx 1..3)
+            uint4 h;
+            h.x = (s8.x & 7u) | (((s8.x >> 3) & 63u) << 8) | (((s8.x >> 13) & 63u) << 16) | (((s8.x >> 19) & 63u) << 24);
+            h.y = ((s8.x >> 25) & 63u) | ((s8.y & 63u) << 8) | (inl ? 0u : ((s8.x >> 9) & 15u) << 16) | (inl ? 0u : ((s8.y >> 6) & 255u) << 24);
+            const uint32_t r = s8.y >> 14;
+            // (a 16x16 macroblock's reference index stands in all four quadrant fields, as the packers write it)
+            h.z = inl ? (r & 15u) * 0x01010101u : ((r & 15u) | (((r >> 4) & 15u) << 8) | (((r >> 8) & 15u) << 16) | (((r >> 12) & 15u) << 24));
+            h.w = 0u;
+            const uint32_t uo = (uint32_t)run, mo = (uint32_t)(run >> 32), nmv = (c[k] >> 8) & 255u;
+            if (intra) {
+                h.z = __ldg(p); h.w = __ldg(p + 1);
+                p += 2;
+                ilist[1 + irun++] = (uint32_t)a;
+            } else if (inl) {
+                const uint32_t x = ((s8.y >> 6) & 255u) | (((s8.x >> 9) & 15u) << 8) | (((s8.y >> 30) & 1u) << 12);
+                const uint32_t y = ((s8.y >> 18) & 0xFFFu) | ((s8.y >> 31) << 12);
+                const int xs = (int)(x << 19) >> 19, ys = (int)(y << 19) >> 19;       // sign-extend 13 bits
+                xmv[-1 - (ptrdiff_t)mo] = ((uint32_t)xs & 0xffffu) | ((uint32_t)ys << 16);
+            } else {
+                for (uint32_t i = 0; i < nmv; i++) xmv[-1 - (ptrdiff_t)(mo + i)] = __ldg(p + i);
+                p += nmv;
+            }
+            *reinterpret_cast<uint4*>(hdr16 + a) = h;
+            xmask[a] = mw;
+            off[a] = uo;
+            mvoff[a] = mo;
+            uint2* u = xunits + uo;
+            for (uint32_t m = mw & 0xFFFFFFu; m; m &= m - 1) {
+                if (mw & H264R_BLK_COMPACT) {
+                    const uint32_t w0 = __ldg(p);
+                    if (__popc(w0 & 0xffffu) <= 2) { *u++ = uint2{w0, 0u}; p += 1; }
+                    else { *u++ = uint2{w0, __ldg(p + 1)}; p += 2; }
+                } else {
+                    u[0] = uint2{__ldg(p), __ldg(p + 1)};
+                    u[1] = uint2{__ldg(p + 2), __ldg(p + 3)};
+                    u += 2; p += 4;
+                }
+            }
+            run += (unsigned long long)(c[k] & 255u) | ((unsigned long long)nmv << 32);
+            wo += nw;
+        }
+    }
+    if (threadIdx.x == 0) {
+        ilist[0] = (uint32_t)ibase;
+        if (pd.n_intra_host >= 0 && ibase > (unsigned long long)pd.n_intra_host) atomicOr(pd.exc_counter + 1, H264R_STATUS_N_INTRA);
+    }
+}
+
 __global__ void __launch_bounds__(1024) k_blk_scan(const DescTable descs, const __grid_constant__ PicList list, int n_mbs)
 {
     const PicDesc& pd = descs[list.slot[blockIdx.x]];
+    if (pd.stream) { blk_scan_stream(pd, n_mbs); return; }
     const uint32_t* mask = pd.blk_mask;
     uint32_t* off = pd.packed ? const_cast<uint32_t*>(pd.blk_off) : nullptr;
     uint32_t* mvoff = pd.packed ? const_cast<uint32_t*>(pd.mv_off) : nullptr;

@@ -570,6 +570,20 @@ extern "C" int h264d_next(h264d* d, h264d_picture* out)
     }
 }
 
+extern "C" int h264w_pack_arrays(h264r_picture_buf* buf, int n_mbs, const h264r_mb_hdr* hdr, const int16_t* mv, const int16_t* coeff,
+                                 int level_fmt, size_t* n_blocks, long* n_mvs)
+{
+    if (!buf || !hdr || !coeff || !n_blocks || !n_mvs || n_mbs <= 0) return H264R_E_INVAL;
+    h264r_writer w;
+    h264r_writer_begin(&w, buf, n_mbs, level_fmt);
+    for (int a = 0; a < n_mbs; a++) {
+        const int16_t* v = (mv && hdr[a].mb_class >= H264R_MB_P16x16) ? mv + (size_t)a * H264R_MV_PER_MB : nullptr;
+        const int rc = h264r_writer_mb(&w, &hdr[a], v, coeff + (size_t)a * H264R_COEFF_PER_MB);
+        if (rc != H264R_OK) return rc;
+    }
+    return h264r_writer_end(&w, n_blocks, n_mvs);
+}
+
 extern "C" int h264d_fill_picture_buf(h264d* d, h264r_picture_buf* buf, int level_fmt, size_t* n_blocks, long* n_mvs)
 {
     if (!d || !buf || !d->have_picture) return H264R_E_STATE;

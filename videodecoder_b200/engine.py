@@ -13,7 +13,8 @@ from . import abi, build
 class PictureBufStruct(ctypes.Structure):
     _fields_ = [("hdr", ctypes.c_void_p), ("mv", ctypes.c_void_p), ("mv_end", ctypes.c_void_p), ("blk_mask", ctypes.c_void_p), ("blocks", ctypes.c_void_p),
                 ("max_blocks", ctypes.c_size_t), ("n_intra", ctypes.c_int32), ("level_bytes", ctypes.c_int32), ("base", ctypes.c_void_p),
-                ("hdr_bytes", ctypes.c_int32), ("ring_index", ctypes.c_int32), ("hdr8", ctypes.c_void_p)]
+                ("hdr_bytes", ctypes.c_int32), ("ring_index", ctypes.c_int32), ("hdr8", ctypes.c_void_p),
+                ("mb_words", ctypes.c_void_p), ("stream", ctypes.c_void_p), ("max_stream_words", ctypes.c_size_t)]
 
 
 _lib = None
@@ -157,14 +158,36 @@ class PictureBuf:
         n = self.engine.n_mbs
         self.hdr = self._view(self.c.hdr, abi.MB_HDR_DTYPE, n)
         self.hdr8 = self._view(self.c.hdr8, np.uint32, n * 2).reshape(n, 2) if self.c.hdr8 else None
+        self.mb_words = self._view(self.c.mb_words, np.uint8, n) if self.c.mb_words else None
+        self.stream = self._view(self.c.stream, np.uint32, int(self.c.max_stream_words)) if self.c.stream else None
         self.blk_mask = self._view(self.c.blk_mask, np.uint32, n)
         self.blocks = self._view(self.c.blocks, np.int16, int(self.c.max_blocks) * 16).reshape(-1, 16)
 
     def set_header_bytes(self, hdr_bytes):
-        """16: h264r_mb_hdr records; 8: h264r_mb_hdr8 (masks and blocks move up behind them; compact levels only)"""
+        """16: h264r_mb_hdr records; 8: h264r_mb_hdr8 (masks and blocks move up behind them; compact levels only); abi.HDR_STREAM: the
+        stream form (8-byte headers + word counts + one stream per picture)"""
         if self.c.hdr_bytes != hdr_bytes:
             self.engine._check(self.engine.L.h264r_picture_buf_format(self.engine.ctx, ctypes.byref(self.c), hdr_bytes))
             self._map()
+
+    def fill_stream(self, hdr, mv, coeff):
+        """stream form (abi.HDR_STREAM) from the dense per-macroblock arrays, packed by the C writer (include/h264r_writer.h through
+        libh264host.so: h264w_pack_arrays).  Returns False when a level leaves int8 (the picture then needs another form)."""
+        from . import hoststream
+        self.set_header_bytes(abi.HDR_STREAM)
+        hdr = np.ascontiguousarray(hdr).view(abi.MB_HDR_DTYPE).reshape(-1)
+        coeff = np.ascontiguousarray(coeff, dtype=np.int16)
+        mvp = np.ascontiguousarray(mv, dtype=np.int16) if mv is not None else None
+        nb, nm = ctypes.c_size_t(0), ctypes.c_long(0)
+        L = hoststream.lib()
+        rc = L.h264w_pack_arrays(ctypes.byref(self.c), hdr.size, hdr.ctypes.data_as(ctypes.c_void_p), mvp.ctypes.data_as(ctypes.c_void_p) if mvp is not None else None,
+                                 coeff.ctypes.data_as(ctypes.c_void_p), abi.LEVELS_COMPACT, ctypes.byref(nb), ctypes.byref(nm))
+        if rc == abi.E_INVAL:
+            return False
+        if rc:
+            raise H264RError(rc, "h264w_pack_arrays (-6: the buffer's stream area is too small for the picture)")
+        self.n_blocks, self.n_mvs = int(nb.value), int(nm.value)
+        return True
 
     def fill(self, hdr, mv, blk_mask, blocks, mv_partition=False, level8=None, compact=None, short_hdr=False):
         """mv: per-4x4 vectors (n, 32); mv_partition: store them in partition order (pack.pack_mvs_partition).
@@ -211,7 +234,7 @@ class PictureBuf:
 
     def free(self):
         if self.c.base:
-            self.hdr = self.hdr8 = self.mv = self.mv_tail = self.blk_mask = self.blocks = None
+            self.hdr = self.hdr8 = self.mv = self.mv_tail = self.blk_mask = self.blocks = self.mb_words = self.stream = None
             self.engine.L.h264r_picture_buf_free(self.engine.ctx, ctypes.byref(self.c))
 
 

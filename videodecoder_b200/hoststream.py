@@ -49,6 +49,8 @@ def lib():
         _lib.h264d_error.argtypes = [ctypes.c_void_p]
         _lib.h264d_fill_picture_buf.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t),
                                                 ctypes.POINTER(ctypes.c_long)]
+        _lib.h264w_pack_arrays.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                           ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_long)]
         _lib.h264d_benchmark.restype = ctypes.c_long
         _lib.h264d_benchmark.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     return _lib

@@ -64,6 +64,7 @@ struct h264r_ctx {
     bool pdl = true;                        // programmatic dependent launch of the P-wave kernels (H264R_PDL=0: plain launches)
     bool inter_parts = true;                // spec-mode lean launches as three kernels (H264R_INTER_PARTS=0: one)
     bool tma_old = false, group_tma = false; // tensor-copy window staging in k_inter (H264R_TMA=1) / in k_inter_grp (H264R_GROUP_TMA=1): opt-in, see DESIGN.md
+    bool any_stream = false;                // a stream-form picture has been submitted: scans are followed by k_stream_expand
     bool inter_group = true;                // k_inter_grp for REF_COMPAT launches of lean pictures (H264R_INTER_GROUP=0: k_inter<LEAN>)
     int inter_group_gens = 4;               // its grid = SMs x 32 x this (H264R_GROUP_GENS)
     int inter_generations = 8;              // k_inter grid = SMs x inter_ctas_per_sm x this: a few CTA generations balance the tail
@@ -115,7 +116,7 @@ struct h264r_ctx {
     // 8-byte headers: masks and blocks of the upload move up behind the shorter header array
     size_t off_mask_s = 0, off_coeff_s = 0;
     // stream form: word counts and stream behind the 8-byte headers (upload); expanded masks / units in device-only areas
-    size_t off_words = 0, off_stream = 0, off_xmask = 0, off_xunits = 0;
+    size_t off_words = 0, off_stream = 0, off_xmask = 0, off_xunits = 0, off_xwoff = 0;
     uint32_t mbox_stamp = 0;                // launch number of k_deblock_rows (stamp of its hand-over records)
     int sparse_stamp = 0;                   // launch stamp of k_intra_list (intra_done words of older launches are smaller)
     // per-flush control block (descriptors + picture lists), pinned host mirror + device copy
@@ -196,6 +197,7 @@ void fill_desc(h264r_ctx* c, const Pending& p, PicDesc& pd)
     pd.hdr8 = p.short_hdr ? reinterpret_cast<const uint2*>(s + c->off_hdr) : nullptr;
     pd.mb_words = p.stream ? s + c->off_words : nullptr;
     pd.stream = p.stream ? reinterpret_cast<const uint32_t*>(s + c->off_stream) : nullptr;
+    pd.stream_off = reinterpret_cast<uint32_t*>(s + c->off_xwoff);
     pd.mv = reinterpret_cast<const int16_t*>(s + (p.mv_partition ? c->off_desc : c->off_mv));
     pd.coeff = reinterpret_cast<const int16_t*>(s + (p.stream ? c->off_xunits : (p.short_hdr ? c->off_coeff_s : c->off_coeff)));
     pd.level_fmt = p.level_bytes;
@@ -306,7 +308,8 @@ int h264r_create(h264r_ctx** out, int device, int w_mbs, int h_mbs, int max_fram
     c->off_hdr16 = c->off_mbox + ((flags & H264R_REF_COMPAT) ? 0 : align_up((size_t)c->n_mbs * MBOX_WORDS * 4, 256));      // device only: headers expanded from the 8-byte form
     c->off_xmask = c->off_hdr16 + align_up((size_t)c->n_mbs * sizeof(h264r_mb_hdr), 256);
     c->off_xunits = c->off_xmask + align_up((size_t)c->n_mbs * 4, 256);
-    c->slot_bytes = c->off_xunits + align_up((size_t)c->n_mbs * 48 * 8, 256);          // 24 blocks x two 8-byte units
+    c->off_xwoff = c->off_xunits + align_up((size_t)c->n_mbs * 48 * 8, 256);           // 24 blocks x two 8-byte units
+    c->slot_bytes = c->off_xwoff + align_up((size_t)c->n_mbs * 4, 256);
     c->off_words = c->off_hdr + (size_t)c->n_mbs * sizeof(h264r_mb_hdr8);
     c->off_stream = align_up(c->off_words + (size_t)c->n_mbs, 16);
     c->off_mask_s = c->off_hdr + (size_t)c->n_mbs * sizeof(h264r_mb_hdr8);
@@ -724,6 +727,7 @@ static int prepare_picture(h264r_ctx* ctx, int frame_id, const h264r_picture_buf
     p->mv_partition = n_mvs >= 0;
     p->short_hdr = short_hdr;
     p->stream = stream;
+    if (stream) ctx->any_stream = true;
     p->level_bytes = buf->level_bytes;
     // ONE transfer: the vectors present (backward from the descriptor), descriptor, headers, masks, the blocks present
     uint8_t* hb = static_cast<uint8_t*>(buf->base);
@@ -941,8 +945,8 @@ int h264r_flush(h264r_ctx* ctx)
         }
         if (list.n) { list_frames.n = list.n; f(list); }
     };
-    std::vector<uint8_t> lane_used(NL, 0);
-    bool dig_used = false;
+    std::vector<uint8_t> lane_used(NL, 0), lane_late_waited(NL, 0);
+    bool dig_used = false, late_scans = false;       // late_scans: the structures of the waves behind wave 0 come with ev_scan[5]
     auto sparse = [&](const Pending& p) { return ctx->sparse_intra && p.pp.slice_type == H264R_SLICE_P && p.n_intra > 0 && p.n_intra * 8 < ctx->n_mbs; };
     // Pictures whose upload has landed already (all of them in a resident batch): their index structures in one go, ahead
     // of every wave, and no per-wave wait later -- stream operations between the kernels of two waves would serialise
@@ -955,6 +959,10 @@ int h264r_flush(h264r_ctx* ctx)
             if (!EL.n) return;
             k_blk_scan<<<EL.n, 1024, 0, ctx->prep_stream>>>(d_desc, EL, ctx->n_mbs);
             ctx->last_launches++;
+            if (ctx->any_stream) {
+                k_stream_expand<<<dim3((unsigned)((ctx->n_mbs + 255) / 256), (unsigned)EL.n), 256, 0, ctx->prep_stream>>>(d_desc, EL, ctx->n_mbs);
+                ctx->last_launches++;
+            }
             any = true;
             EL.n = 0;
         };
@@ -969,18 +977,24 @@ int h264r_flush(h264r_ctx* ctx)
             if (cudaEventQuery(ctx->ev_copied[by_seq[mid]->slot]) == cudaSuccess) lo = mid + 1; else hi = mid;
         }
         for (int i = 0; i < n; i++) by_seq[i]->early = i < lo;
-        for (int i = 0; i < n; i++) {
-            Pending* p = run[i];
-            if (p->early && (p->layout == 2 || sparse(*p))) {
-                EL.slot[EL.n++] = p->slot;
-                if (EL.n == PIC_LIST_MAX) launch();
+        // the pictures of wave 0 first: the lanes start as soon as THEIR structures are made, and the scans of the later waves
+        // (an expansion of the whole picture in the stream form) run beside wave 0
+        for (int pass = 0; pass < 2; pass++) {
+            any = false;
+            for (int i = 0; i < n; i++) {
+                Pending* p = run[i];
+                if (p->early && (p->wave == 0) == (pass == 0) && (p->layout == 2 || sparse(*p))) {
+                    EL.slot[EL.n++] = p->slot;
+                    if (EL.n == PIC_LIST_MAX) launch();
+                }
             }
-        }
-        launch();
-        (void)cudaGetLastError();       // cudaErrorNotReady of the queries is not an error
-        if (any) {
-            CU(cudaEventRecord(ctx->ev_scan[0], ctx->prep_stream));
-            for (int l = 0; l < NL; l++) CU(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->ev_scan[0], 0));
+            launch();
+            (void)cudaGetLastError();       // cudaErrorNotReady of the queries is not an error
+            if (any) {
+                CU(cudaEventRecord(ctx->ev_scan[pass ? 5 : 0], ctx->prep_stream));
+                if (pass == 0) for (int l = 0; l < NL; l++) CU(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->ev_scan[0], 0));
+                else late_scans = true;
+            }
         }
     }
     const int dig_every = ctx->digest_every;
@@ -1001,6 +1015,10 @@ int h264r_flush(h264r_ctx* ctx)
                 }
             if (!any_pic) continue;
             lane_used[lane] = 1;
+            if (wv > 0 && late_scans && !lane_late_waited[lane]) {
+                CU(cudaStreamWaitEvent(st, ctx->ev_scan[5], 0));
+                lane_late_waited[lane] = 1;
+            }
             // block / vector offsets of the pictures that arrived packed: on the prep stream, behind the uploads and
             // ahead of the lanes (in a resident batch the scans of all waves are done while wave 0 computes)
             bool scanned = false;
@@ -1009,6 +1027,10 @@ int h264r_flush(h264r_ctx* ctx)
                 scanned = true;
                 k_blk_scan<<<L.n, 1024, 0, ctx->prep_stream>>>(d_desc, L, ctx->n_mbs);
                 ctx->last_launches++;
+                if (ctx->any_stream) {
+                    k_stream_expand<<<dim3((unsigned)((ctx->n_mbs + 255) / 256), (unsigned)L.n), 256, 0, ctx->prep_stream>>>(d_desc, L, ctx->n_mbs);
+                    ctx->last_launches++;
+                }
             });
             if (scanned) {
                 CU(cudaEventRecord(ctx->ev_scan[1 + (lane & 3)], ctx->prep_stream));

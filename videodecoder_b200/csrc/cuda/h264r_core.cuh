@@ -62,6 +62,7 @@ struct PicDesc {
     const uint2* hdr8;         // picture buffers with 8-byte headers (h264r_mb_hdr8), else null
     const uint8_t* mb_words;   // stream form (H264R_HDR_STREAM): words of each macroblock in `stream`, else null; k_blk_scan expands the
     const uint32_t* stream;    // stream into hdr / blk_mask / coeff / mv (which then all point at device-only areas)
+    uint32_t* stream_off;      // device only, stream form: first word of every macroblock in `stream` (k_blk_scan -> k_stream_expand)
     const int16_t* mv;         // motion vectors (x, y): per 4x4 block (16 per macroblock, forward from here) or per partition
                                // (stored BACKWARD from here: vector i at mv[-2(i+1)], see mv_off)
     const uint32_t* mv_off;    // null: per-4x4 layout; else per macroblock the index of its first vector, partition order

@@ -618,10 +618,6 @@ __device__ __forceinline__ unsigned long long cta_excl_prefix(unsigned long long
 __device__ void blk_scan_stream(const PicDesc& pd, int n_mbs)
 {
     __shared__ unsigned long long sm[33];
-    h264r_mb_hdr* hdr16 = const_cast<h264r_mb_hdr*>(pd.hdr);
-    uint32_t* xmask = const_cast<uint32_t*>(pd.blk_mask);
-    uint2* xunits = reinterpret_cast<uint2*>(const_cast<int16_t*>(pd.coeff));
-    uint32_t* xmv = reinterpret_cast<uint32_t*>(const_cast<int16_t*>(pd.mv));       // entry i at xmv[-1 - i]
     uint32_t* off = const_cast<uint32_t*>(pd.blk_off);
     uint32_t* mvoff = const_cast<uint32_t*>(pd.mv_off);
     uint32_t* ilist = pd.intra_list;
@@ -664,58 +660,19 @@ __device__ void blk_scan_stream(const PicDesc& pd, int n_mbs)
         base += tot;
         uint32_t irun = (uint32_t)(ibase + cta_excl_prefix(n_intra, sm, tot));
         ibase += tot;
-        // expansion
+        // where every macroblock's words, units and vectors begin; the expansion itself is k_stream_expand's (one thread per macroblock)
         uint32_t wo = woff0;
-#pragma unroll 1
+#pragma unroll
         for (int k = 0; k < 8; k++) {
             const int a = first + k;
-            if (a >= n_mbs) break;
-            const uint32_t nw = (k < 4 ? wc.x >> (8 * k) : wc.y >> (8 * (k - 4))) & 255u;
-            const uint2 s8 = __ldg(pd.hdr8 + a);
-            const bool intra = (c[k] >> 16) & 1u, inl = !intra && (s8.x & H264R_HDR8_MV_INLINE);
-            const uint32_t* p = pd.stream + wo;
-            uint32_t mw = 0;
-            if ((s8.y & 63u) || (s8.x & 7u) == H264R_MB_I16x16) mw = __ldg(p++);
-            // 16-byte header (fields of h264r_mb_hdr8; an inline vector borrows intra_modes, sub_mb_type and ref_idx 1..3)
-            uint4 h;
-            h.x = (s8.x & 7u) | (((s8.x >> 3) & 63u) << 8) | (((s8.x >> 13) & 63u) << 16) | (((s8.x >> 19) & 63u) << 24);
-            h.y = ((s8.x >> 25) & 63u) | ((s8.y & 63u) << 8) | (inl ? 0u : ((s8.x >> 9) & 15u) << 16) | (inl ? 0u : ((s8.y >> 6) & 255u) << 24);
-            const uint32_t r = s8.y >> 14;
-            // (a 16x16 macroblock's reference index stands in all four quadrant fields, as the packers write it)
-            h.z = inl ? (r & 15u) * 0x01010101u : ((r & 15u) | (((r >> 4) & 15u) << 8) | (((r >> 8) & 15u) << 16) | (((r >> 12) & 15u) << 24));
-            h.w = 0u;
-            const uint32_t uo = (uint32_t)run, mo = (uint32_t)(run >> 32), nmv = (c[k] >> 8) & 255u;
-            if (intra) {
-                h.z = __ldg(p); h.w = __ldg(p + 1);
-                p += 2;
-                ilist[1 + irun++] = (uint32_t)a;
-            } else if (inl) {
-                const uint32_t x = ((s8.y >> 6) & 255u) | (((s8.x >> 9) & 15u) << 8) | (((s8.y >> 30) & 1u) << 12);
-                const uint32_t y = ((s8.y >> 18) & 0xFFFu) | ((s8.y >> 31) << 12);
-                const int xs = (int)(x << 19) >> 19, ys = (int)(y << 19) >> 19;       // sign-extend 13 bits
-                xmv[-1 - (ptrdiff_t)mo] = ((uint32_t)xs & 0xffffu) | ((uint32_t)ys << 16);
-            } else {
-                for (uint32_t i = 0; i < nmv; i++) xmv[-1 - (ptrdiff_t)(mo + i)] = __ldg(p + i);
-                p += nmv;
+            if (a < n_mbs) {
+                pd.stream_off[a] = wo;
+                off[a] = (uint32_t)run;
+                mvoff[a] = (uint32_t)(run >> 32);
+                if ((c[k] >> 16) & 1u) ilist[1 + irun++] = (uint32_t)a;
+                run += (unsigned long long)(c[k] & 255u) | ((unsigned long long)((c[k] >> 8) & 255u) << 32);
             }
-            *reinterpret_cast<uint4*>(hdr16 + a) = h;
-            xmask[a] = mw;
-            off[a] = uo;
-            mvoff[a] = mo;
-            uint2* u = xunits + uo;
-            for (uint32_t m = mw & 0xFFFFFFu; m; m &= m - 1) {
-                if (mw & H264R_BLK_COMPACT) {
-                    const uint32_t w0 = __ldg(p);
-                    if (__popc(w0 & 0xffffu) <= 2) { *u++ = uint2{w0, 0u}; p += 1; }
-                    else { *u++ = uint2{w0, __ldg(p + 1)}; p += 2; }
-                } else {
-                    u[0] = uint2{__ldg(p), __ldg(p + 1)};
-                    u[1] = uint2{__ldg(p + 2), __ldg(p + 3)};
-                    u += 2; p += 4;
-                }
-            }
-            run += (unsigned long long)(c[k] & 255u) | ((unsigned long long)nmv << 32);
-            wo += nw;
+            wo += (k < 4 ? wc.x >> (8 * k) : wc.y >> (8 * (k - 4))) & 255u;
         }
     }
     if (threadIdx.x == 0) {
@@ -823,6 +780,62 @@ __global__ void __launch_bounds__(1024) k_blk_scan(const DescTable descs, const 
     if (ilist && threadIdx.x == 0) {
         ilist[0] = ibase;
         if (pd.n_intra_host >= 0 && ibase > (uint32_t)pd.n_intra_host) atomicOr(pd.exc_counter + 1, H264R_STATUS_N_INTRA);      // macroblocks left unreconstructed
+    }
+}
+
+// The expansion of stream-form pictures (see blk_scan_stream): one thread per macroblock, behind k_blk_scan on the prep stream.
+// A thread reads its macroblock's 8-byte header and its words of the stream and writes the 16-byte header, the dense mask, the
+// vectors into the partition-order stream and the blocks as 8-byte units, at the offsets the scan left.
+__global__ void __launch_bounds__(256) k_stream_expand(const DescTable descs, const __grid_constant__ PicList list, int n_mbs)
+{
+    const PicDesc& pd = descs[list.slot[blockIdx.y]];
+    if (!pd.stream) return;
+    const int a = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (a >= n_mbs) return;
+    h264r_mb_hdr* hdr16 = const_cast<h264r_mb_hdr*>(pd.hdr);
+    uint32_t* xmask = const_cast<uint32_t*>(pd.blk_mask);
+    uint32_t* xmv = reinterpret_cast<uint32_t*>(const_cast<int16_t*>(pd.mv));       // entry i at xmv[-1 - i]
+    const uint2 s8 = __ldg(pd.hdr8 + a);
+    const int cls = (int)(s8.x & 7u);
+    const bool intra = is_intra(cls), inl = !intra && (s8.x & H264R_HDR8_MV_INLINE);
+    const uint32_t* p = pd.stream + pd.stream_off[a];
+    const uint32_t uo = __ldg(pd.blk_off + a), mo = __ldg(pd.mv_off + a);
+    uint32_t mw = 0;
+    if ((s8.y & 63u) || cls == H264R_MB_I16x16) mw = __ldg(p++);
+    // 16-byte header (fields of h264r_mb_hdr8; an inline vector borrows intra_modes, sub_mb_type and ref_idx 1..3)
+    uint4 h;
+    h.x = (s8.x & 7u) | (((s8.x >> 3) & 63u) << 8) | (((s8.x >> 13) & 63u) << 16) | (((s8.x >> 19) & 63u) << 24);
+    h.y = ((s8.x >> 25) & 63u) | ((s8.y & 63u) << 8) | (inl ? 0u : ((s8.x >> 9) & 15u) << 16) | (inl ? 0u : ((s8.y >> 6) & 255u) << 24);
+    const uint32_t r = s8.y >> 14;
+    // (a 16x16 macroblock's reference index stands in all four quadrant fields, as the packers write it)
+    h.z = inl ? (r & 15u) * 0x01010101u : ((r & 15u) | (((r >> 4) & 15u) << 8) | (((r >> 8) & 15u) << 16) | (((r >> 12) & 15u) << 24));
+    h.w = 0u;
+    if (intra) {
+        h.z = __ldg(p); h.w = __ldg(p + 1);
+        p += 2;
+    } else if (inl) {
+        const uint32_t x = ((s8.y >> 6) & 255u) | (((s8.x >> 9) & 15u) << 8) | (((s8.y >> 30) & 1u) << 12);
+        const uint32_t y = ((s8.y >> 18) & 0xFFFu) | ((s8.y >> 31) << 12);
+        const int xs = (int)(x << 19) >> 19, ys = (int)(y << 19) >> 19;       // sign-extend 13 bits
+        xmv[-1 - (ptrdiff_t)mo] = ((uint32_t)xs & 0xffffu) | ((uint32_t)ys << 16);
+    } else {
+        const uint32_t nmv = (uint32_t)mv_count(cls, (int)((s8.y >> 6) & 255u));
+        for (uint32_t i = 0; i < nmv; i++) xmv[-1 - (ptrdiff_t)(mo + i)] = __ldg(p + i);
+        p += nmv;
+    }
+    *reinterpret_cast<uint4*>(hdr16 + a) = h;
+    xmask[a] = mw;
+    uint2* u = reinterpret_cast<uint2*>(const_cast<int16_t*>(pd.coeff)) + uo;
+    for (uint32_t m = mw & 0xFFFFFFu; m; m &= m - 1) {
+        if (mw & H264R_BLK_COMPACT) {
+            const uint32_t w0 = __ldg(p);
+            if (__popc(w0 & 0xffffu) <= 2) { *u++ = uint2{w0, 0u}; p += 1; }
+            else { *u++ = uint2{w0, __ldg(p + 1)}; p += 2; }
+        } else {
+            u[0] = uint2{__ldg(p), __ldg(p + 1)};
+            u[1] = uint2{__ldg(p + 2), __ldg(p + 3)};
+            u += 2; p += 4;
+        }
     }
 }
 

@@ -150,6 +150,26 @@ struct MvStore {
 
 extern "C" {
 
+// Stream form (H264R_HDR_STREAM): what k_blk_scan + k_stream_expand leave in a slot, macroblocks in order -- the scans as running
+// sums of stream_mb_counts, the expansion by stream_expand_mb (the functions the kernels call).  mv_end: end of a buffer of at
+// least max_mvs words (vector i at mv_end[-1 - i]).  Returns the words walked; totals through n_units / n_mvs / n_intra.
+long h264emul_stream_expand(int n_mbs, const uint32_t* hdr8, const uint8_t* mb_words, const uint32_t* stream, h264r_mb_hdr* hdr16,
+                            uint32_t* mask, uint32_t* mv_end, uint32_t* units, uint32_t* blk_off, uint32_t* mv_off, uint32_t* intra_list,
+                            long* n_units, long* n_mvs, long* n_intra)
+{
+    uint32_t wo = 0, uo = 0, mo = 0, ni = 0;
+    for (int a = 0; a < n_mbs; a++) {
+        const uint2 s8 = uint2{hdr8[2 * a], hdr8[2 * a + 1]};
+        const uint32_t c = stream_mb_counts(s8, stream_mb_has_mask(s8) ? stream[wo] : 0u);
+        blk_off[a] = uo; mv_off[a] = mo;
+        if (c >> 16) intra_list[ni++] = (uint32_t)a;
+        stream_expand_mb(s8, stream + wo, uo, mo, reinterpret_cast<uint4*>(hdr16 + a), mask + a, mv_end, reinterpret_cast<uint2*>(units));
+        wo += mb_words[a]; uo += c & 255u; mo += (c >> 8) & 255u;
+    }
+    *n_units = uo; *n_mvs = mo; *n_intra = ni;
+    return (long)wo;
+}
+
 // residual of every MB: out[n_mbs][384] int16
 void h264emul_residual(int w_mbs, int h_mbs, unsigned flags, const h264r_mb_hdr* hdr, const int16_t* coeff, int16_t* out)
 {

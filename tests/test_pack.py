@@ -2,6 +2,7 @@
 import numpy as np
 
 from videodecoder_b200 import abi, pack
+import emul
 
 
 def unpack_compact(mask, units):
@@ -235,6 +236,15 @@ def test_stream_form_c_writer_against_restatement(built):
         mask, blocks = pack.pack_blocks(coeff)
         cmask, units = pack.pack_compact(mask, blocks)
         assert np.array_equal(got_mask, cmask) and np.array_equal(got_units, units)
+        # the device's own expansion functions (h264r_core.cuh: stream_mb_counts / stream_expand_mb, run by the host emulator in
+        # macroblock order) give the same headers, masks, units, vectors -- and the scans and the intra list the kernels use
+        dev = emul.stream_expand(hdr8, words, stream, units.shape[0], 16 * n)
+        assert dev["words"] == used
+        assert np.array_equal(dev["hdr"].view(np.uint8), got_hdr.view(np.uint8))
+        assert np.array_equal(dev["mask"], cmask) and np.array_equal(dev["units"], units) and np.array_equal(dev["mvs"], got_mvs)
+        per_mb = np.array([bin(int(m) & 0xFFFFFF).count("1") * (1 if int(m) & abi.BLK_COMPACT else 2) for m in cmask])
+        assert np.array_equal(dev["blk_off"], np.concatenate([[0], np.cumsum(per_mb)[:-1]]))
+        assert np.array_equal(dev["intra_list"], np.flatnonzero(hdr["mb_class"] <= abi.MB_I16x16))
         intra = hdr["mb_class"] <= abi.MB_I16x16
         for k in ("mb_class", "flags", "qp_y", "qp_cb", "qp_cr", "cbp"):
             assert np.array_equal(got_hdr[k], hdr[k]), k

@@ -12,7 +12,7 @@ timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --cloc
 # full sections: the first launches of every family of that step (wave 0 = I pictures, wave 1.. = P pictures)
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'k_(inter|intra|residual|digest|zero)' -c 12 \
     -o gpurun_out/prof_step_${tag} -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_step_${tag}.log 2>&1
-timeout 600 ncu --set full --clock-control none --profile-from-start off -k regex:k_blk_scan -c 2 \
+timeout 600 ncu --set full --clock-control none --profile-from-start off -k regex:'k_(blk_scan|stream_expand)' -c 4 \
     -o gpurun_out/prof_scan_${tag} -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_scan_${tag}.log 2>&1
 timeout 900 ncu --set full --clock-control none --profile-from-start off -k regex:'k_(deblock|pad|inter|intra)' -s 6 -c 8 \
     -o gpurun_out/prof_spec_${tag} -f python bench.py --mode spec --steps 1 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_spec_${tag}.log 2>&1

@@ -13,6 +13,7 @@
 // ITU-T H.264 listed in include/h264r.h.
 #pragma once
 #include <stdint.h>
+#include <stddef.h>
 #include "../../../include/h264r.h"
 
 #ifdef __CUDACC__
@@ -240,6 +241,64 @@ HD int mv_count(int mb_class, int sub_mb_type)
     if (mb_class != H264R_MB_P8x8) return 2;
     return mv_sub_count(sub_mb_type & 3) + mv_sub_count((sub_mb_type >> 2) & 3) + mv_sub_count((sub_mb_type >> 4) & 3) + mv_sub_count((sub_mb_type >> 6) & 3);
 }
+// Stream form of a picture buffer (include/h264r.h, H264R_HDR_STREAM).  A macroblock is its 8-byte header s8 (h264r_mb_hdr8 as two
+// words) + mb_words[a] words of the stream: [mask word] [2 words of prediction modes] [vectors] [blocks].  These three functions
+// are all the device knows about the form: k_blk_scan sums stream_mb_counts, k_stream_expand runs stream_expand_mb per macroblock
+// (and the host emulator runs both in macroblock order, tests/emul).
+HD bool stream_mb_has_mask(uint2 s8) { return (s8.y & 63u) != 0u || (int)(s8.x & 7u) == H264R_MB_I16x16; }
+// units (8 bytes each) | vectors << 8 | intra << 16 of a macroblock; mw = its mask word (0 if it has none)
+HD uint32_t stream_mb_counts(uint2 s8, uint32_t mw)
+{
+    const int cls = (int)(s8.x & 7u);
+    const uint32_t units = (uint32_t)popc32(mw & 0xFFFFFFu) << ((mw & H264R_BLK_COMPACT) ? 0 : 1);
+    return units | ((uint32_t)mv_count(cls, (int)((s8.y >> 6) & 255u)) << 8) | (cls <= H264R_MB_I16x16 ? 1u << 16 : 0u);
+}
+// Expands macroblock a: p = its words, uo / mo = its first unit / vector (the scans).  Writes the 16-byte header, the dense mask
+// word, the vectors (entry i at xmv_end[-1 - i]) and the blocks as 8-byte units.
+HD void stream_expand_mb(uint2 s8, const uint32_t* p, uint32_t uo, uint32_t mo, uint4* hdr16, uint32_t* mask, uint32_t* xmv_end, uint2* units)
+{
+    const int cls = (int)(s8.x & 7u);
+    const bool intra = cls <= H264R_MB_I16x16, inl = !intra && (s8.x & H264R_HDR8_MV_INLINE);
+    uint32_t mw = 0;
+    if (stream_mb_has_mask(s8)) mw = H264R_LDG(p++);
+    // fields of h264r_mb_hdr8 at their places in h264r_mb_hdr (an inline vector borrows intra_modes, sub_mb_type and ref_idx 1..3)
+    uint4 h;
+    h.x = (s8.x & 7u) | (((s8.x >> 3) & 63u) << 8) | (((s8.x >> 13) & 63u) << 16) | (((s8.x >> 19) & 63u) << 24);
+    h.y = ((s8.x >> 25) & 63u) | ((s8.y & 63u) << 8) | (inl ? 0u : ((s8.x >> 9) & 15u) << 16) | (inl ? 0u : ((s8.y >> 6) & 255u) << 24);
+    const uint32_t r = s8.y >> 14;
+    // (a 16x16 macroblock's reference index stands in all four quadrant fields, as the packers write it)
+    h.z = inl ? (r & 15u) * 0x01010101u : ((r & 15u) | (((r >> 4) & 15u) << 8) | (((r >> 8) & 15u) << 16) | (((r >> 12) & 15u) << 24));
+    h.w = 0u;
+    if (intra) {
+        h.z = H264R_LDG(p); h.w = H264R_LDG(p + 1);
+        p += 2;
+    } else if (inl) {
+        const uint32_t x = ((s8.y >> 6) & 255u) | (((s8.x >> 9) & 15u) << 8) | (((s8.y >> 30) & 1u) << 12);
+        const uint32_t y = ((s8.y >> 18) & 0xFFFu) | ((s8.y >> 31) << 12);
+        const int xs = (int)(x << 19) >> 19, ys = (int)(y << 19) >> 19;       // sign-extend 13 bits
+        xmv_end[-1 - (ptrdiff_t)mo] = ((uint32_t)xs & 0xffffu) | ((uint32_t)ys << 16);
+    } else {
+        const uint32_t nmv = (uint32_t)mv_count(cls, (int)((s8.y >> 6) & 255u));
+        for (uint32_t i = 0; i < nmv; i++) xmv_end[-1 - (ptrdiff_t)(mo + i)] = H264R_LDG(p + i);
+        p += nmv;
+    }
+    *hdr16 = h;
+    *mask = mw;
+    uint2* u = units + uo;
+    for (uint32_t m = mw & 0xFFFFFFu; m; m &= m - 1) {
+        if (mw & H264R_BLK_COMPACT) {
+            // a block of at most two levels is one word (map + two int8 levels), any other compact block a whole unit
+            const uint32_t w0 = H264R_LDG(p);
+            if (popc32(w0 & 0xffffu) <= 2) { *u++ = uint2{w0, 0u}; p += 1; }
+            else { *u++ = uint2{w0, H264R_LDG(p + 1)}; p += 2; }
+        } else {
+            u[0] = uint2{H264R_LDG(p), H264R_LDG(p + 1)};
+            u[1] = uint2{H264R_LDG(p + 2), H264R_LDG(p + 3)};
+            u += 2; p += 4;
+        }
+    }
+}
+
 // index (within the macroblock's vectors) of the partition that covers 4x4 block blk (raster)
 HD int mv_part_index(int mb_class, int sub_mb_type, int blk)
 {

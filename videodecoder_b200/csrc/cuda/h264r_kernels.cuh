@@ -644,12 +644,9 @@ __device__ void blk_scan_stream(const PicDesc& pd, int n_mbs)
                 if (first + k < n_mbs) {
                     const uint2 s8 = __ldg(pd.hdr8 + first + k);
                     const int cls = (int)(s8.x & 7u);
-                    const uint32_t mw = ((s8.y & 63u) || cls == H264R_MB_I16x16) ? __ldg(pd.stream + wo) : 0u;
-                    const uint32_t units = (uint32_t)__popc(mw & 0xFFFFFFu) << ((mw & H264R_BLK_COMPACT) ? 0 : 1);
-                    const uint32_t mvs = (uint32_t)mv_count(cls, (int)((s8.y >> 6) & 255u));
-                    c[k] = units | (mvs << 8) | (is_intra(cls) ? 1u << 16 : 0u);
-                    sum += (unsigned long long)units | ((unsigned long long)mvs << 32);
-                    n_intra += is_intra(cls) ? 1u : 0u;
+                    c[k] = stream_mb_counts(s8, stream_mb_has_mask(s8) ? __ldg(pd.stream + wo) : 0u);
+                    sum += (unsigned long long)(c[k] & 255u) | ((unsigned long long)((c[k] >> 8) & 255u) << 32);
+                    n_intra += c[k] >> 16;
                     if (cls == 3 || cls > H264R_MB_P8x8) atomicOr(pd.exc_counter + 1, H264R_STATUS_BAD_CLASS);
                     else if (!is_intra(cls) && pd.slice_type != H264R_SLICE_P) atomicOr(pd.exc_counter + 1, H264R_STATUS_INTER_IN_I);
                 }
@@ -792,51 +789,9 @@ __global__ void __launch_bounds__(256) k_stream_expand(const DescTable descs, co
     if (!pd.stream) return;
     const int a = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (a >= n_mbs) return;
-    h264r_mb_hdr* hdr16 = const_cast<h264r_mb_hdr*>(pd.hdr);
-    uint32_t* xmask = const_cast<uint32_t*>(pd.blk_mask);
-    uint32_t* xmv = reinterpret_cast<uint32_t*>(const_cast<int16_t*>(pd.mv));       // entry i at xmv[-1 - i]
-    const uint2 s8 = __ldg(pd.hdr8 + a);
-    const int cls = (int)(s8.x & 7u);
-    const bool intra = is_intra(cls), inl = !intra && (s8.x & H264R_HDR8_MV_INLINE);
-    const uint32_t* p = pd.stream + pd.stream_off[a];
-    const uint32_t uo = __ldg(pd.blk_off + a), mo = __ldg(pd.mv_off + a);
-    uint32_t mw = 0;
-    if ((s8.y & 63u) || cls == H264R_MB_I16x16) mw = __ldg(p++);
-    // 16-byte header (fields of h264r_mb_hdr8; an inline vector borrows intra_modes, sub_mb_type and ref_idx 1..3)
-    uint4 h;
-    h.x = (s8.x & 7u) | (((s8.x >> 3) & 63u) << 8) | (((s8.x >> 13) & 63u) << 16) | (((s8.x >> 19) & 63u) << 24);
-    h.y = ((s8.x >> 25) & 63u) | ((s8.y & 63u) << 8) | (inl ? 0u : ((s8.x >> 9) & 15u) << 16) | (inl ? 0u : ((s8.y >> 6) & 255u) << 24);
-    const uint32_t r = s8.y >> 14;
-    // (a 16x16 macroblock's reference index stands in all four quadrant fields, as the packers write it)
-    h.z = inl ? (r & 15u) * 0x01010101u : ((r & 15u) | (((r >> 4) & 15u) << 8) | (((r >> 8) & 15u) << 16) | (((r >> 12) & 15u) << 24));
-    h.w = 0u;
-    if (intra) {
-        h.z = __ldg(p); h.w = __ldg(p + 1);
-        p += 2;
-    } else if (inl) {
-        const uint32_t x = ((s8.y >> 6) & 255u) | (((s8.x >> 9) & 15u) << 8) | (((s8.y >> 30) & 1u) << 12);
-        const uint32_t y = ((s8.y >> 18) & 0xFFFu) | ((s8.y >> 31) << 12);
-        const int xs = (int)(x << 19) >> 19, ys = (int)(y << 19) >> 19;       // sign-extend 13 bits
-        xmv[-1 - (ptrdiff_t)mo] = ((uint32_t)xs & 0xffffu) | ((uint32_t)ys << 16);
-    } else {
-        const uint32_t nmv = (uint32_t)mv_count(cls, (int)((s8.y >> 6) & 255u));
-        for (uint32_t i = 0; i < nmv; i++) xmv[-1 - (ptrdiff_t)(mo + i)] = __ldg(p + i);
-        p += nmv;
-    }
-    *reinterpret_cast<uint4*>(hdr16 + a) = h;
-    xmask[a] = mw;
-    uint2* u = reinterpret_cast<uint2*>(const_cast<int16_t*>(pd.coeff)) + uo;
-    for (uint32_t m = mw & 0xFFFFFFu; m; m &= m - 1) {
-        if (mw & H264R_BLK_COMPACT) {
-            const uint32_t w0 = __ldg(p);
-            if (__popc(w0 & 0xffffu) <= 2) { *u++ = uint2{w0, 0u}; p += 1; }
-            else { *u++ = uint2{w0, __ldg(p + 1)}; p += 2; }
-        } else {
-            u[0] = uint2{__ldg(p), __ldg(p + 1)};
-            u[1] = uint2{__ldg(p + 2), __ldg(p + 3)};
-            u += 2; p += 4;
-        }
-    }
+    stream_expand_mb(__ldg(pd.hdr8 + a), pd.stream + pd.stream_off[a], __ldg(pd.blk_off + a), __ldg(pd.mv_off + a),
+                     reinterpret_cast<uint4*>(const_cast<h264r_mb_hdr*>(pd.hdr) + a), const_cast<uint32_t*>(pd.blk_mask) + a,
+                     reinterpret_cast<uint32_t*>(const_cast<int16_t*>(pd.mv)), reinterpret_cast<uint2*>(const_cast<int16_t*>(pd.coeff)));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -347,6 +347,9 @@ int h264r_range_excursions(h264r_ctx* ctx, uint64_t* count);
 #define H264R_STATUS_BAD_CLASS   0x1u   /* a header with an unknown mb_class                                          */
 #define H264R_STATUS_INTER_IN_I  0x2u   /* an inter macroblock in an I picture                                        */
 #define H264R_STATUS_N_INTRA     0x4u   /* more intra macroblocks than n_intra said: some were not reconstructed       */
+#define H264R_STATUS_STREAM      0x8u   /* stream form: mb_words[] does not add up to the submitted word count, or a
+                                           macroblock's words are not what its header and mask announce (the picture is
+                                           reconstructed from what was read; every access stays inside the picture's slot)   */
 int h264r_device_status(h264r_ctx* ctx, uint32_t* flags);
 
 /* Per-macroblock map of the same event for one frame: out[mb_addr] = 1 where a luma sample of that

@@ -434,6 +434,20 @@ def test_device_status_reports_bad_picture_buffers(built):
     bufs.append(send(3, gop[1], patch=bad_class))
     eng.sync()
     assert eng.device_status() & abi.STATUS_BAD_CLASS
+    # stream form: word counts that do not add up, or do not match what a macroblock's header and mask announce
+    for damage in (None, "count", "total"):
+        p = gop[1]
+        b = eng.picture_buf(0)
+        assert b.fill_stream(p["hdr"], p["mv"], p["coeff"])
+        if damage == "count":
+            a = int(np.flatnonzero(b.mb_words)[0])
+            b.mb_words[a] -= 1; b.mb_words[a + 1] += 1          # the total still agrees
+        elif damage == "total":
+            b.n_blocks += 1
+        eng.submit_picture_buf(2, p["pp"], b)
+        eng.sync()
+        assert eng.device_status() == (abi.STATUS_STREAM if damage else 0), damage
+        bufs.append(b)
     for b in bufs:
         b.free()
     eng.close()

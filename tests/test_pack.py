@@ -245,6 +245,9 @@ def test_stream_form_c_writer_against_restatement(built):
         per_mb = np.array([bin(int(m) & 0xFFFFFF).count("1") * (1 if int(m) & abi.BLK_COMPACT else 2) for m in cmask])
         assert np.array_equal(dev["blk_off"], np.concatenate([[0], np.cumsum(per_mb)[:-1]]))
         assert np.array_equal(dev["intra_list"], np.flatnonzero(hdr["mb_class"] <= abi.MB_I16x16))
+        # a word count that does not match what the macroblock holds is noticed at that macroblock (H264R_STATUS_STREAM on the device)
+        bad = words.copy(); bad[7] += 1
+        assert emul.stream_expand(hdr8, bad, stream, units.shape[0] + 48, 16 * n)["words"] == -1 - 7
         intra = hdr["mb_class"] <= abi.MB_I16x16
         for k in ("mb_class", "flags", "qp_y", "qp_cb", "qp_cr", "cbp"):
             assert np.array_equal(got_hdr[k], hdr[k]), k

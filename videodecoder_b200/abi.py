@@ -18,7 +18,7 @@ LEVELS_INT16, LEVELS_INT8, LEVELS_COMPACT = 2, 1, 3      # h264r_picture_buf.lev
 BLK_COMPACT = 1 << 24
 
 E_INVAL, E_CUDA, E_NOMEM, E_STATE, E_NODEVICE, E_CAPACITY = -1, -2, -3, -4, -5, -6
-STATUS_BAD_CLASS, STATUS_INTER_IN_I, STATUS_N_INTRA = 1, 2, 4      # h264r_device_status
+STATUS_BAD_CLASS, STATUS_INTER_IN_I, STATUS_N_INTRA, STATUS_STREAM = 1, 2, 4, 8      # h264r_device_status
 
 MB_HDR_DTYPE = np.dtype([
     ("mb_class", "u1"), ("flags", "u1"), ("qp_y", "u1"), ("qp_cb", "u1"), ("qp_cr", "u1"), ("cbp", "u1"),

@@ -198,6 +198,7 @@ void fill_desc(h264r_ctx* c, const Pending& p, PicDesc& pd)
     pd.mb_words = p.stream ? s + c->off_words : nullptr;
     pd.stream = p.stream ? reinterpret_cast<const uint32_t*>(s + c->off_stream) : nullptr;
     pd.stream_off = reinterpret_cast<uint32_t*>(s + c->off_xwoff);
+    pd.stream_words = p.stream ? (uint32_t)p.n_blocks : 0u;
     pd.mv = reinterpret_cast<const int16_t*>(s + (p.mv_partition ? c->off_desc : c->off_mv));
     pd.coeff = reinterpret_cast<const int16_t*>(s + (p.stream ? c->off_xunits : (p.short_hdr ? c->off_coeff_s : c->off_coeff)));
     pd.level_fmt = p.level_bytes;

@@ -63,6 +63,7 @@ struct PicDesc {
     const uint2* hdr8;         // picture buffers with 8-byte headers (h264r_mb_hdr8), else null
     const uint8_t* mb_words;   // stream form (H264R_HDR_STREAM): words of each macroblock in `stream`, else null; k_blk_scan expands the
     const uint32_t* stream;    // stream into hdr / blk_mask / coeff / mv (which then all point at device-only areas)
+    uint32_t stream_words;     // stream form: words of `stream` the caller submitted
     uint32_t* stream_off;      // device only, stream form: first word of every macroblock in `stream` (k_blk_scan -> k_stream_expand)
     const int16_t* mv;         // motion vectors (x, y): per 4x4 block (16 per macroblock, forward from here) or per partition
                                // (stored BACKWARD from here: vector i at mv[-2(i+1)], see mv_off)
@@ -254,9 +255,10 @@ HD uint32_t stream_mb_counts(uint2 s8, uint32_t mw)
     return units | ((uint32_t)mv_count(cls, (int)((s8.y >> 6) & 255u)) << 8) | (cls <= H264R_MB_I16x16 ? 1u << 16 : 0u);
 }
 // Expands macroblock a: p = its words, uo / mo = its first unit / vector (the scans).  Writes the 16-byte header, the dense mask
-// word, the vectors (entry i at xmv_end[-1 - i]) and the blocks as 8-byte units.
-HD void stream_expand_mb(uint2 s8, const uint32_t* p, uint32_t uo, uint32_t mo, uint4* hdr16, uint32_t* mask, uint32_t* xmv_end, uint2* units)
+// word, the vectors (entry i at xmv_end[-1 - i]) and the blocks as 8-byte units; returns the words it walked.
+HD uint32_t stream_expand_mb(uint2 s8, const uint32_t* p, uint32_t uo, uint32_t mo, uint4* hdr16, uint32_t* mask, uint32_t* xmv_end, uint2* units)
 {
+    const uint32_t* const p0 = p;
     const int cls = (int)(s8.x & 7u);
     const bool intra = cls <= H264R_MB_I16x16, inl = !intra && (s8.x & H264R_HDR8_MV_INLINE);
     uint32_t mw = 0;
@@ -297,6 +299,7 @@ HD void stream_expand_mb(uint2 s8, const uint32_t* p, uint32_t uo, uint32_t mo, 
             u += 2; p += 4;
         }
     }
+    return (uint32_t)(p - p0);          // words walked: mb_words[a] in a well-formed buffer
 }
 
 // index (within the macroblock's vectors) of the partition that covers 4x4 block blk (raster)

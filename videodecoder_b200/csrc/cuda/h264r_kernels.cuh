@@ -675,6 +675,7 @@ __device__ void blk_scan_stream(const PicDesc& pd, int n_mbs)
     if (threadIdx.x == 0) {
         ilist[0] = (uint32_t)ibase;
         if (pd.n_intra_host >= 0 && ibase > (unsigned long long)pd.n_intra_host) atomicOr(pd.exc_counter + 1, H264R_STATUS_N_INTRA);
+        if (wbase != (unsigned long long)pd.stream_words) atomicOr(pd.exc_counter + 1, H264R_STATUS_STREAM);
     }
 }
 
@@ -789,9 +790,10 @@ __global__ void __launch_bounds__(256) k_stream_expand(const DescTable descs, co
     if (!pd.stream) return;
     const int a = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (a >= n_mbs) return;
-    stream_expand_mb(__ldg(pd.hdr8 + a), pd.stream + pd.stream_off[a], __ldg(pd.blk_off + a), __ldg(pd.mv_off + a),
+    const uint32_t walked = stream_expand_mb(__ldg(pd.hdr8 + a), pd.stream + pd.stream_off[a], __ldg(pd.blk_off + a), __ldg(pd.mv_off + a),
                      reinterpret_cast<uint4*>(const_cast<h264r_mb_hdr*>(pd.hdr) + a), const_cast<uint32_t*>(pd.blk_mask) + a,
                      reinterpret_cast<uint32_t*>(const_cast<int16_t*>(pd.mv)), reinterpret_cast<uint2*>(const_cast<int16_t*>(pd.coeff)));
+    if (walked != (uint32_t)__ldg(pd.mb_words + a)) atomicOr(pd.exc_counter + 1, H264R_STATUS_STREAM);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -81,8 +81,11 @@ int    h264d_fill_picture_buf(h264d* d, h264r_picture_buf* buf, int level_fmt, s
  * was formatted for (h264r_picture_buf_format).  Returns H264R_OK or the writer's code. */
 int    h264w_pack_arrays(h264r_picture_buf* buf, int n_mbs, const h264r_mb_hdr* hdr, const int16_t* mv, const int16_t* coeff,
                          int level_fmt, size_t* n_blocks, long* n_mvs);
-/* Parse-only throughput: decodes the whole stream `repeat` times without keeping anything; returns pictures parsed, *seconds = CPU
- * wall time of the parsing alone. */
+/* Host-side throughput: decodes the whole stream `repeat` times without keeping anything; returns pictures parsed, *seconds = CPU
+ * wall time of the parsing alone -- or, with H264D_BENCH_PACK in flags, of parsing + packing every picture into the stream form
+ * of a picture buffer (plain memory; h264d_fill_picture_buf), i.e. everything a host thread does per picture before
+ * h264r_submit_picture. */
+#define H264D_BENCH_PACK 0x100u
 long   h264d_benchmark(const uint8_t* annexb, size_t n_bytes, uint32_t flags, int repeat, double* seconds);
 
 /* ---- stream writer (tooling) ----------------------------------------------------------------------------------------------------- */

@@ -58,6 +58,34 @@ static inline h264r_mb_hdr8 h264r_hdr8_pack(const h264r_mb_hdr* h)
 /* signed 13-bit range of the inline vector of the stream form */
 static inline int h264r_mv_fits_inline(int x, int y) { return x >= -4096 && x <= 4095 && y >= -4096 && y <= 4095; }
 
+static inline int h264r_writer_popcount(unsigned v)
+{
+#if defined(__GNUC__)
+    return __builtin_popcount(v);
+#else
+    int n = 0;
+    for (; v; v &= v - 1) n++;
+    return n;
+#endif
+}
+/* one 8-byte unit of H264R_LEVELS_COMPACT: bytes 0-1 the significance map, bytes 2-7 the (at most six) levels of the set
+ * positions in ascending order; returns their number */
+static inline int h264r_writer_compact_unit(const int16_t* c, unsigned map, uint8_t u[8])
+{
+    int n = 0;
+    memset(u, 0, 8);
+    u[0] = (uint8_t)map; u[1] = (uint8_t)(map >> 8);
+    for (; map; map &= map - 1) {
+#if defined(__GNUC__)
+        const unsigned k = (unsigned)__builtin_ctz(map);
+#else
+        unsigned k = 0, t = map & (0u - map);
+        while (t >>= 1) k++;
+#endif
+        u[2 + n++] = (uint8_t)(int8_t)c[k];
+    }
+    return n;
+}
 /* number of vectors the bitstream carries for a macroblock (mvd loops of macroblock::Parse, h264/macroblock.cpp:360-398) and
  * the first 4x4 block (raster) of each of them */
 static inline int h264r_writer_partitions(const h264r_mb_hdr* h, int first_block[16])
@@ -89,17 +117,24 @@ static inline int h264r_writer_mb(h264r_writer* w, const h264r_mb_hdr* hdr, cons
     h264r_picture_buf* b = w->buf;
     uint32_t mask = 0;
     int blk, k, n_present = 0, compact = 1, part[16], n_part;
+    uint16_t map[24];
     if (w->next_mb >= w->n_mbs) return H264R_E_STATE;
     for (blk = 0; blk < 24; blk++) {
-        int nz = 0;
+        /* most blocks are empty: four 64-bit words say so; of the others, the significance map (bit k = position k holds a level) */
+        uint64_t q[4];
+        unsigned m16 = 0, wide = 0;
+        memcpy(q, coeff + blk * 16, 32);
+        map[blk] = 0;
+        if (!(q[0] | q[1] | q[2] | q[3])) continue;
         for (k = 0; k < 16; k++) {
             const int v = coeff[blk * 16 + k];
-            if (v) {
-                nz++;
-                if (w->level_fmt == H264R_LEVELS_COMPACT && (v < -128 || v > 127)) return H264R_E_INVAL;
-            }
+            m16 |= (unsigned)(v != 0) << k;
+            wide |= (unsigned)(v + 128) > 255u;
         }
-        if (nz) { mask |= 1u << blk; n_present++; if (nz > 6) compact = 0; }
+        if (wide && w->level_fmt == H264R_LEVELS_COMPACT) return H264R_E_INVAL;
+        map[blk] = (uint16_t)m16;
+        mask |= 1u << blk; n_present++;
+        if (h264r_writer_popcount(m16) > 6) compact = 0;
     }
     if ((b->hdr_bytes == 8 || b->hdr_bytes == H264R_HDR_STREAM) && w->level_fmt != H264R_LEVELS_COMPACT) return H264R_E_INVAL;
     if (b->hdr_bytes == H264R_HDR_STREAM) {
@@ -126,10 +161,7 @@ static inline int h264r_writer_mb(h264r_writer* w, const h264r_mb_hdr* hdr, cons
             if (!((mask >> blk) & 1u)) continue;
             if (compact) {
                 uint8_t u[8];
-                int n = 0;
-                memset(u, 0, 8);
-                for (k = 0; k < 16; k++)
-                    if (c[k]) { u[k >> 3] |= (uint8_t)(1u << (k & 7)); u[2 + n++] = (uint8_t)(int8_t)c[k]; }
+                const int n = h264r_writer_compact_unit(c, map[blk], u);
                 memcpy(&words[nw], u, 8);
                 nw += n <= 2 ? 1 : 2;
             } else {
@@ -162,10 +194,7 @@ static inline int h264r_writer_mb(h264r_writer* w, const h264r_mb_hdr* hdr, cons
             const int16_t* c = coeff + blk * 16;
             if (!((mask >> blk) & 1u)) continue;
             if (compact) {                     /* significance map, then the levels in position order */
-                int n = 0;
-                memset(u, 0, 8);
-                for (k = 0; k < 16; k++)
-                    if (c[k]) { u[k >> 3] |= (uint8_t)(1u << (k & 7)); u[2 + n++] = (uint8_t)(int8_t)c[k]; }
+                h264r_writer_compact_unit(c, map[blk], u);
                 w->n_units += 1;
             } else {                           /* int8 levels, raster: two units */
                 for (k = 0; k < 16; k++) u[k] = (uint8_t)(int8_t)c[k];

@@ -459,6 +459,13 @@ private:
     }
 
     // ---- coefficient levels: scan order -> the engine's block layout ("Coefficients" in include/h264r.h) -----------------------------
+    // (most blocks of a coded quadrant are empty: four 64-bit words say so before the sixteen levels are looked at)
+    static bool block_is_zero(const int16_t* lv)
+    {
+        uint64_t q[4];
+        memcpy(q, lv, 32);
+        return !(q[0] | q[1] | q[2] | q[3]);
+    }
     static void scan_levels(const h264s_mb& m, int16_t* coeff)
     {
         memset(coeff, 0, sizeof(int16_t) * H264R_COEFF_PER_MB);
@@ -467,9 +474,11 @@ private:
             for (int k = 0; k < 16; k++)
                 if (m.luma_dc[k]) coeff[kBlkRaster[kZigzag4x4[k]] * 16] = m.luma_dc[k];
             if (m.cbp_luma)
-                for (int b = 0; b < 16; b++)
+                for (int b = 0; b < 16; b++) {
+                    if (block_is_zero(m.luma[b])) continue;
                     for (int k = 0; k < 15; k++)
                         if (m.luma[b][k]) coeff[b * 16 + kZigzag4x4[k + 1]] = m.luma[b][k];
+                }
         } else if (m.t8x8) {
             for (int q = 0; q < 4; q++) {
                 if (!((m.cbp_luma >> q) & 1)) continue;
@@ -479,7 +488,7 @@ private:
             }
         } else {
             for (int b = 0; b < 16; b++) {
-                if (!((m.cbp_luma >> (b >> 2)) & 1)) continue;
+                if (!((m.cbp_luma >> (b >> 2)) & 1) || block_is_zero(m.luma[b])) continue;
                 for (int k = 0; k < 16; k++)
                     if (m.luma[b][k]) coeff[b * 16 + kZigzag4x4[k]] = m.luma[b][k];
             }
@@ -489,7 +498,7 @@ private:
                 for (int b = 0; b < 4; b++) {
                     int16_t* o = coeff + (16 + c * 4 + b) * 16;
                     o[0] = m.chroma_dc[c][b];
-                    if (m.cbp_chroma == 2)
+                    if (m.cbp_chroma == 2 && !block_is_zero(m.chroma_ac[c][b]))
                         for (int k = 0; k < 15; k++)
                             if (m.chroma_ac[c][b][k]) o[kZigzag4x4[k + 1]] = m.chroma_ac[c][b][k];
                 }

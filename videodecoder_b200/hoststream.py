@@ -12,6 +12,7 @@ import numpy as np
 from . import abi, synth
 
 REF_QUIRKS, KEEP_SYNTAX = 0x1, 0x2          # h264d_open flags
+BENCH_PACK = 0x100                          # h264d_benchmark: + packing of every picture into a stream-form picture buffer
 E_ABSOLUTE, E_REF_QUIRKS = 0x1, 0x2         # h264e_encode_picture flags
 
 

@@ -16,10 +16,24 @@
 
 #include "cabac_tables.h"
 
+// The decoder's decision() is called from some sixty places of the syntax walker; left to its heuristics the compiler keeps it a
+// function with a call per bin.  (Measured on top of this and NOT kept: the engine's registers as a local copy inside the
+// residual-block and vector-difference loops -- no change; a branch-free decision with the MPS / LPS outcome as a mask -- 4 %
+// slower, twice: the chain range -> LPS range -> comparison -> renormalisation is what a bin costs, not its branches.)
+#if defined(__GNUC__)
+#define H264HOST_INLINE inline __attribute__((always_inline))
+#define H264HOST_NOINLINE __attribute__((noinline))
+#else
+#define H264HOST_INLINE inline
+#define H264HOST_NOINLINE
+#endif
+
 namespace h264host {
 
 struct CabacContexts {
-    uint8_t s[kNumCtx];          // pStateIdx << 1 | valMPS
+    // pStateIdx << 1 | valMPS.  Sixteen bits wide on purpose: a store through a character type may alias anything, the engine's
+    // range / offset / bit count included
+    uint16_t s[kNumCtx];
     // 9.3.1.1: preCtxState = Clip3(1, 126, ((m * Clip3(0, 51, SliceQPY)) >> 4) + n)
     void init(int slice_qp, bool i_slice, int cabac_init_idc)
     {
@@ -28,17 +42,26 @@ struct CabacContexts {
         for (int i = 0; i < kNumCtx; i++) {
             int pre = ((t[i][0] * qp) >> 4) + t[i][1];
             pre = pre < 1 ? 1 : (pre > 126 ? 126 : pre);
-            s[i] = pre <= 63 ? (uint8_t)((63 - pre) << 1) : (uint8_t)(((pre - 64) << 1) | 1);
+            s[i] = pre <= 63 ? (uint16_t)((63 - pre) << 1) : (uint16_t)(((pre - 64) << 1) | 1);
         }
     }
 };
 
-inline uint8_t cabac_next_state(uint8_t s, bool was_mps)
+inline uint16_t cabac_next_state(uint16_t s, bool was_mps)
 {
     const int st = s >> 1, mps = s & 1;
-    if (was_mps) return (uint8_t)(((st < 62 ? st + 1 : st) << 1) | mps);
-    return (uint8_t)((kTransLps[st] << 1) | (st == 0 ? 1 - mps : mps));
+    if (was_mps) return (uint16_t)(((st < 62 ? st + 1 : st) << 1) | mps);
+    return (uint16_t)((kTransLps[st] << 1) | (st == 0 ? 1 - mps : mps));
 }
+// ... as a table for the decoder: t[0] after an MPS, t[1] after an LPS
+struct CabacNextTable {
+    uint16_t t[2][128];
+    CabacNextTable()
+    {
+        for (int s = 0; s < 128; s++) { t[0][s] = cabac_next_state((uint16_t)s, true); t[1][s] = cabac_next_state((uint16_t)s, false); }
+    }
+};
+static const CabacNextTable kCabacNext;
 
 class CabacDecoder {
 public:
@@ -55,27 +78,27 @@ public:
         bits_ -= 9;
         overrun_ = false;
     }
-    int decision(int c, int /*bin*/ = 0)
+    H264HOST_INLINE int decision(int c, int /*bin*/ = 0)
     {
-        uint8_t& s = ctx.s[c];
+        uint16_t& s = ctx.s[c];
         const uint32_t lps = kRangeLps[s >> 1][(range_ >> 6) & 3];
         range_ -= lps;
         const uint64_t scaled = (uint64_t)range_ << bits_;
         int bin;
         if (value_ < scaled) {
             bin = s & 1;
-            s = cabac_next_state(s, true);
+            s = kCabacNext.t[0][s];
             if (range_ >= 256) return bin;
         } else {
             value_ -= scaled;
             range_ = lps;
             bin = (s & 1) ^ 1;
-            s = cabac_next_state(s, false);
+            s = kCabacNext.t[1][s];
         }
         renorm();
         return bin;
     }
-    int bypass(int /*bin*/ = 0)
+    H264HOST_INLINE int bypass(int /*bin*/ = 0)
     {
         if (bits_ < 1) refill();
         bits_ -= 1;
@@ -95,7 +118,7 @@ public:
     // after terminate() returned 1 for I_PCM: not supported here (no pcm alignment restart)
 
 private:
-    void renorm()
+    H264HOST_INLINE void renorm()
     {
         if (range_ >= 256) return;
         const int n = __builtin_clz(range_) - 23;      // range_ < 256: shift that brings bit 8 up
@@ -103,7 +126,7 @@ private:
         bits_ -= n;
         if (bits_ < 0) refill();
     }
-    void refill()
+    H264HOST_NOINLINE void refill()
     {
         // append 32 bits below the window
         uint32_t w = 0;
@@ -136,7 +159,7 @@ public:
     }
     int decision(int c, int bin)
     {
-        uint8_t& s = ctx.s[c];
+        uint16_t& s = ctx.s[c];
         const uint32_t lps = kRangeLps[s >> 1][(range_ >> 6) & 3];
         range_ -= lps;
         if (bin != (s & 1)) {

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define H264R_ABI_VERSION 6
+#define H264R_ABI_VERSION 7
 
 /* ---- status codes ---------------------------------------------------------------------- */
 #define H264R_OK            0
@@ -123,9 +123,10 @@ typedef struct h264r_mb_hdr8 { uint32_t w0, w1; } h264r_mb_hdr8;
  *   - its vectors in partition order, one word each (x | y << 16)                 inter macroblocks; none for a P_L0_16x16 /
  *     P_Skip macroblock whose vector fits 13 bits per component and rides in the header: w0 bit 31 (H264R_HDR8_MV_INLINE) set,
  *     x = w1 bits 6-13 | w0 bits 9-12 << 8 | w1 bit 30 << 12, y = w1 bits 18-29 | w1 bit 31 << 12, both two's complement
- *   - its present blocks in ascending block index: H264R_BLK_COMPACT macroblocks one word per block with at most two levels
- *     (significance map | level << 16 | level << 24) and two words (the 8-byte unit of H264R_LEVELS_COMPACT) per block with three
- *     to six; other macroblocks four words per block (16 int8 levels, raster).
+ *   - its present blocks in ascending block index: H264R_BLK_COMPACT macroblocks as a BYTE run -- per block the 16-bit
+ *     significance map (low byte first) and one byte per level in position order, i.e. the 8-byte unit of
+ *     H264R_LEVELS_COMPACT without its padding -- zero-padded to the next 32-bit word at the end of the macroblock; other
+ *     macroblocks four words per block (16 int8 levels, raster).
  * The engine expands the stream on the device (k_blk_scan) into the forms its kernels read. */
 #define H264R_HDR_STREAM       9
 #define H264R_HDR8_MV_INLINE   (1u << 31)

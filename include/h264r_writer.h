@@ -156,21 +156,29 @@ static inline int h264r_writer_mb(h264r_writer* w, const h264r_mb_hdr* hdr, cons
             inline_mv = 1;
         } else
             for (k = 0; k < n_part; k++) words[nw++] = (uint32_t)(uint16_t)mv[part[k] * 2] | ((uint32_t)(uint16_t)mv[part[k] * 2 + 1] << 16);
-        for (blk = 0; blk < 24; blk++) {
-            const int16_t* c = coeff + blk * 16;
-            if (!((mask >> blk) & 1u)) continue;
-            if (compact) {
+        if (compact && n_present) {
+            /* a byte run: per block the 16-bit significance map and one byte per level, zero-padded to the next word */
+            uint8_t* q = (uint8_t*)&words[nw];
+            int nb = 0;
+            for (blk = 0; blk < 24; blk++) {
                 uint8_t u[8];
-                const int n = h264r_writer_compact_unit(c, map[blk], u);
-                memcpy(&words[nw], u, 8);
-                nw += n <= 2 ? 1 : 2;
-            } else {
+                int n;
+                if (!((mask >> blk) & 1u)) continue;
+                n = h264r_writer_compact_unit(coeff + blk * 16, map[blk], u);
+                memcpy(q + nb, u, (size_t)(2 + n));
+                nb += 2 + n;
+            }
+            while (nb & 3) q[nb++] = 0;
+            nw += nb >> 2;
+        } else
+            for (blk = 0; blk < 24; blk++) {
+                const int16_t* c = coeff + blk * 16;
                 uint8_t u[16];
+                if (!((mask >> blk) & 1u)) continue;
                 for (k = 0; k < 16; k++) u[k] = (uint8_t)(int8_t)c[k];
                 memcpy(&words[nw], u, 16);
                 nw += 4;
             }
-        }
         if (nw > 255) return H264R_E_INVAL;
         if (w->n_units + (size_t)nw > b->max_stream_words) return H264R_E_CAPACITY;
         memcpy(s, words, (size_t)nw * 4);

@@ -185,17 +185,24 @@ def unpack_stream(hdr8, mb_words, stream):
                 mvs.append((np.int16(np.uint16(v & 0xffff)), np.int16(np.uint16(v >> 16))))
             p += cnt
         m = int(mask[a])
-        for b in range(24):
-            if not (m >> b) & 1:
-                continue
-            if m & abi.BLK_COMPACT:
-                first = int(stream[p])
-                if bin(first & 0xffff).count("1") <= 2:
-                    units.append(np.array([first, 0], dtype=np.uint32).view(np.uint8)); p += 1
-                else:
-                    units.append(stream[p:p + 2].view(np.uint8)); p += 2
-            else:
-                units.append(stream[p:p + 2].view(np.uint8)); units.append(stream[p + 2:p + 4].view(np.uint8)); p += 4
+        if m & abi.BLK_COMPACT:
+            # a byte run: per block a 16-bit significance map and one byte per level, zero-padded to the next word
+            run = stream[p:].view(np.uint8)
+            q = 0
+            for b in range(24):
+                if not (m >> b) & 1:
+                    continue
+                n = bin(int(run[q]) | (int(run[q + 1]) << 8)).count("1")
+                assert 1 <= n <= 6
+                unit = np.zeros(8, dtype=np.uint8)
+                unit[:2 + n] = run[q:q + 2 + n]
+                units.append(unit); q += 2 + n
+            assert not run[q:(q + 3) // 4 * 4].any(), "padding of macroblock %d is not zero" % a
+            p += (q + 3) // 4
+        else:
+            for b in range(24):
+                if (m >> b) & 1:
+                    units.append(stream[p:p + 2].view(np.uint8)); units.append(stream[p + 2:p + 4].view(np.uint8)); p += 4
         assert p - wo == int(mb_words[a]), "macroblock %d: %d words walked, %d announced" % (a, p - wo, mb_words[a])
         wo = p
     return hdr, mask, (np.array(units, dtype=np.uint8).reshape(-1, 8)), np.array(mvs, dtype=np.int16).reshape(-1, 2), wo

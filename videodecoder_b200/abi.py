@@ -3,7 +3,7 @@ import ctypes
 
 import numpy as np
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 HDR_STREAM = 9            # h264r_picture_buf.hdr_bytes: the stream form (include/h264r.h)
 REF_COMPAT = 0x1
 DIGESTS = 0x2      # digest of every picture as part of its reconstruction

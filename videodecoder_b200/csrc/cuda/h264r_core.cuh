@@ -287,18 +287,28 @@ HD uint32_t stream_expand_mb(uint2 s8, const uint32_t* p, uint32_t uo, uint32_t 
     *hdr16 = h;
     *mask = mw;
     uint2* u = units + uo;
-    for (uint32_t m = mw & 0xFFFFFFu; m; m &= m - 1) {
-        if (mw & H264R_BLK_COMPACT) {
-            // a block of at most two levels is one word (map + two int8 levels), any other compact block a whole unit
-            const uint32_t w0 = H264R_LDG(p);
-            if (popc32(w0 & 0xffffu) <= 2) { *u++ = uint2{w0, 0u}; p += 1; }
-            else { *u++ = uint2{w0, H264R_LDG(p + 1)}; p += 2; }
-        } else {
+    if (mw & H264R_BLK_COMPACT) {
+        // a byte run: per block the 16-bit significance map and one byte per level (at most six); the unit the kernels read is the
+        // same bytes padded to eight
+        const uint8_t* q = reinterpret_cast<const uint8_t*>(p);
+        for (uint32_t m = mw & 0xFFFFFFu; m; m &= m - 1) {
+            const uint32_t map = (uint32_t)H264R_LDG(q) | ((uint32_t)H264R_LDG(q + 1) << 8);
+            const int n = popc32(map) < 6 ? popc32(map) : 6;
+            uint32_t lo = map, hi = 0u;
+            for (int i = 0; i < n; i++) {
+                const uint32_t b = H264R_LDG(q + 2 + i);
+                if (i < 2) lo |= b << (16 + 8 * i); else hi |= b << (8 * (i - 2));
+            }
+            *u++ = uint2{lo, hi};
+            q += 2 + n;
+        }
+        p += (uint32_t)(q - reinterpret_cast<const uint8_t*>(p) + 3) >> 2;
+    } else
+        for (uint32_t m = mw & 0xFFFFFFu; m; m &= m - 1) {
             u[0] = uint2{H264R_LDG(p), H264R_LDG(p + 1)};
             u[1] = uint2{H264R_LDG(p + 2), H264R_LDG(p + 3)};
             u += 2; p += 4;
         }
-    }
     return (uint32_t)(p - p0);          // words walked: mb_words[a] in a well-formed buffer
 }
 

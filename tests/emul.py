@@ -41,7 +41,7 @@ def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
 
 
-def stream_expand(hdr8, mb_words, stream, max_units, max_mvs):
+def stream_expand(hdr8, mb_words, stream, max_units, max_mvs, strict=True, canary=None):
     """the stream form of a picture through the functions k_blk_scan / k_stream_expand call (h264r_core.cuh): 16-byte headers,
     dense masks, 8-byte units, partition-order vectors, the two offset scans, the intra list, words walked"""
     n = hdr8.shape[0]
@@ -50,15 +50,22 @@ def stream_expand(hdr8, mb_words, stream, max_units, max_mvs):
     stream = np.ascontiguousarray(stream, dtype=np.uint32)
     hdr16 = np.zeros(n, dtype=abi.MB_HDR_DTYPE)
     mask = np.zeros(n, dtype=np.uint32)
-    mvbuf = np.zeros(max_mvs + 1, dtype=np.uint32)
-    units = np.zeros((max_units + 2, 2), dtype=np.uint32)
+    pad = 0 if canary is None else 64
+    mvbuf = np.zeros(max_mvs + 1 + pad, dtype=np.uint32)
+    units = np.zeros((max_units + 2 + pad, 2), dtype=np.uint32)
+    if canary is not None:          # guard words around what the expansion may write: they must come back untouched
+        mvbuf[:pad] = canary
+        units[max_units + 2:] = canary
     blk_off = np.zeros(n, dtype=np.uint32); mv_off = np.zeros(n, dtype=np.uint32); ilist = np.zeros(n, dtype=np.uint32)
     nu, nm, ni = ctypes.c_long(0), ctypes.c_long(0), ctypes.c_long(0)
     f = lib().h264emul_stream_expand
     f.restype = ctypes.c_long
     used = f(n, _ptr(hdr8), _ptr(mb_words), _ptr(stream), _ptr(hdr16), _ptr(mask),
              ctypes.c_void_p(mvbuf.ctypes.data + 4 * mvbuf.size), _ptr(units), _ptr(blk_off), _ptr(mv_off), _ptr(ilist),
-             ctypes.byref(nu), ctypes.byref(nm), ctypes.byref(ni))
+             ctypes.byref(nu), ctypes.byref(nm), ctypes.byref(ni), 1 if strict else 0)
+    if canary is not None:
+        assert (mvbuf[:pad] == canary).all() and (units[max_units + 2:] == canary).all(), "the expansion wrote outside its areas"
+        assert nu.value <= max_units and nm.value <= max_mvs
     mvs = mvbuf[::-1][:nm.value].copy().view(np.int16).reshape(-1, 2)
     return dict(hdr=hdr16, mask=mask, units=units[:nu.value].copy().view(np.uint8).reshape(-1, 8), mvs=mvs, blk_off=blk_off, mv_off=mv_off,
                 intra_list=ilist[:ni.value].copy(), words=int(used))

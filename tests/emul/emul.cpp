@@ -152,23 +152,28 @@ extern "C" {
 
 // Stream form (H264R_HDR_STREAM): what k_blk_scan + k_stream_expand leave in a slot, macroblocks in order -- the scans as running
 // sums of stream_mb_counts, the expansion by stream_expand_mb (the functions the kernels call).  mv_end: end of a buffer of at
-// least max_mvs words (vector i at mv_end[-1 - i]).  Returns the words walked (-1 - a if macroblock a is not as long as mb_words[a] says); totals through n_units / n_mvs / n_intra.
+// least max_mvs words (vector i at mv_end[-1 - i]).  Returns the words walked (strict: -1 - a if macroblock a is not as long as mb_words[a] says; else minus the number of such
+// macroblocks); totals through n_units / n_mvs / n_intra.
 long h264emul_stream_expand(int n_mbs, const uint32_t* hdr8, const uint8_t* mb_words, const uint32_t* stream, h264r_mb_hdr* hdr16,
                             uint32_t* mask, uint32_t* mv_end, uint32_t* units, uint32_t* blk_off, uint32_t* mv_off, uint32_t* intra_list,
-                            long* n_units, long* n_mvs, long* n_intra)
+                            long* n_units, long* n_mvs, long* n_intra, int strict)
 {
     uint32_t wo = 0, uo = 0, mo = 0, ni = 0;
+    long bad = 0;
     for (int a = 0; a < n_mbs; a++) {
         const uint2 s8 = uint2{hdr8[2 * a], hdr8[2 * a + 1]};
         const uint32_t c = stream_mb_counts(s8, stream_mb_has_mask(s8) ? stream[wo] : 0u);
         blk_off[a] = uo; mv_off[a] = mo;
         if (c >> 16) intra_list[ni++] = (uint32_t)a;
         const uint32_t walked = stream_expand_mb(s8, stream + wo, uo, mo, reinterpret_cast<uint4*>(hdr16 + a), mask + a, mv_end, reinterpret_cast<uint2*>(units));
-        if (walked != mb_words[a]) return -1 - a;          // what k_stream_expand reports as H264R_STATUS_STREAM
+        if (walked != mb_words[a]) {                       // what k_stream_expand reports as H264R_STATUS_STREAM
+            if (strict) return -1 - a;
+            bad++;                                         // (the device goes on: whatever it reads, it stays inside the slot)
+        }
         wo += mb_words[a]; uo += c & 255u; mo += (c >> 8) & 255u;
     }
     *n_units = uo; *n_mvs = mo; *n_intra = ni;
-    return (long)wo;
+    return bad ? -bad : (long)wo;
 }
 
 // residual of every MB: out[n_mbs][384] int16

@@ -273,3 +273,19 @@ def test_stream_form_c_writer_against_restatement(built):
         short_bytes = 8 * n + 4 * n + units.shape[0] * 8 + (0 if mv is None else 4 * pack.pack_mvs_partition(hdr, mv).shape[0]) + 8 * int(intra.sum())
         total_saved += short_bytes - (9 * n + 4 * used)
     assert total_saved > 0
+
+
+def test_stream_expansion_of_garbage_stays_inside_its_areas(built):
+    """whatever a damaged stream-form buffer holds, the expansion the kernels run (stream_mb_counts / stream_expand_mb) writes at most
+    48 units and 16 vectors per macroblock -- the sizes of the slot's areas -- and reads at most 116 words past a macroblock's first
+    word (the device keeps the stream in front of areas of the same slot that are longer than that)"""
+    rng = np.random.default_rng(5)
+    n = 200
+    for trial in range(20):
+        hdr8 = rng.integers(0, 2 ** 32, size=(n, 2), dtype=np.uint64).astype(np.uint32)
+        if trial % 2:
+            hdr8[:, 0] &= ~np.uint32(4)              # intra / inter mix of legal classes now and then
+        words = rng.integers(0, 256, size=n, dtype=np.uint8)
+        stream = rng.integers(0, 2 ** 32, size=n * 255 + 128, dtype=np.uint64).astype(np.uint32)
+        dev = emul.stream_expand(hdr8, words, stream, 48 * n, 16 * n, strict=False, canary=0xC0FFEE)
+        assert dev["words"] < 0          # and it is reported

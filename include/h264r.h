@@ -123,13 +123,17 @@ typedef struct h264r_mb_hdr8 { uint32_t w0, w1; } h264r_mb_hdr8;
  *   - its vectors in partition order, one word each (x | y << 16)                 inter macroblocks; none for a P_L0_16x16 /
  *     P_Skip macroblock whose vector fits 13 bits per component and rides in the header: w0 bit 31 (H264R_HDR8_MV_INLINE) set,
  *     x = w1 bits 6-13 | w0 bits 9-12 << 8 | w1 bit 30 << 12, y = w1 bits 18-29 | w1 bit 31 << 12, both two's complement
+ *     With w1 bit 30 (H264R_HDR8_MV_SHORT; a macroblock without an inline vector) the vectors are int8 pairs (x, y), two bytes
+ *     each, possible when every component of the macroblock's vectors lies in [-128, 127]; they then open the byte run below.
  *   - its present blocks in ascending block index: H264R_BLK_COMPACT macroblocks as a BYTE run -- per block the 16-bit
  *     significance map (low byte first) and one byte per level in position order, i.e. the 8-byte unit of
- *     H264R_LEVELS_COMPACT without its padding -- zero-padded to the next 32-bit word at the end of the macroblock; other
- *     macroblocks four words per block (16 int8 levels, raster).
+ *     H264R_LEVELS_COMPACT without its padding; other macroblocks four words per block (16 int8 levels, raster), word-aligned.
+ *     The bytes of a macroblock (short vectors, byte run) are zero-padded to the next 32-bit word where its int8 blocks begin
+ *     and at its end.
  * The engine expands the stream on the device (k_blk_scan) into the forms its kernels read. */
 #define H264R_HDR_STREAM       9
-#define H264R_HDR8_MV_INLINE   (1u << 31)
+#define H264R_HDR8_MV_INLINE   (1u << 31)    /* in w0 */
+#define H264R_HDR8_MV_SHORT    (1u << 30)    /* in w1 */
 
 /* Motion vectors: int16 (x, y) in quarter-sample units, one pair per 4x4 luma block in RASTER
  * order inside the macroblock (block b = 4*(y/4) + x/4), 64 bytes per MB; the final vectors

@@ -140,7 +140,7 @@ static inline int h264r_writer_mb(h264r_writer* w, const h264r_mb_hdr* hdr, cons
     if (b->hdr_bytes == H264R_HDR_STREAM) {
         /* stream form: everything of the macroblock behind its 8-byte header and its word count, see h264r.h */
         uint32_t* s = b->stream + w->n_units;              /* n_units counts stream WORDS here */
-        uint32_t words[2 + 1 + 16 + 24 * 4];
+        uint32_t words[2 + 1 + 16 + 24 * 4 + 1];
         int nw = 0, inline_mv = 0;
         const int intra = hdr->mb_class <= H264R_MB_I16x16;
         h264r_mb_hdr8 h8 = h264r_hdr8_pack(hdr);
@@ -154,31 +154,46 @@ static inline int h264r_writer_mb(h264r_writer* w, const h264r_mb_hdr* hdr, cons
             h8.w0 |= H264R_HDR8_MV_INLINE | (((x >> 8) & 15u) << 9);
             h8.w1 = (h8.w1 & 0x3C03Fu) | ((x & 255u) << 6) | (((x >> 12) & 1u) << 30) | ((y & 0xFFFu) << 18) | (((y >> 12) & 1u) << 31);
             inline_mv = 1;
-        } else
-            for (k = 0; k < n_part; k++) words[nw++] = (uint32_t)(uint16_t)mv[part[k] * 2] | ((uint32_t)(uint16_t)mv[part[k] * 2 + 1] << 16);
-        if (compact && n_present) {
-            /* a byte run: per block the 16-bit significance map and one byte per level, zero-padded to the next word */
+        }
+        {
+            /* behind the words: a byte run -- the vectors as int8 pairs when all of them fit (H264R_HDR8_MV_SHORT; else as words),
+             * then per block of a compact macroblock the 16-bit significance map and one byte per level -- zero-padded to the next
+             * word (also in front of the int8 blocks of any other macroblock) */
             uint8_t* q = (uint8_t*)&words[nw];
             int nb = 0;
-            for (blk = 0; blk < 24; blk++) {
-                uint8_t u[8];
-                int n;
-                if (!((mask >> blk) & 1u)) continue;
-                n = h264r_writer_compact_unit(coeff + blk * 16, map[blk], u);
-                memcpy(q + nb, u, (size_t)(2 + n));
-                nb += 2 + n;
+            if (!inline_mv && n_part) {
+                int fits = 1;
+                for (k = 0; k < n_part; k++) fits &= mv[part[k] * 2] >= -128 && mv[part[k] * 2] <= 127 && mv[part[k] * 2 + 1] >= -128 && mv[part[k] * 2 + 1] <= 127;
+                if (fits) {
+                    h8.w1 |= H264R_HDR8_MV_SHORT;
+                    for (k = 0; k < n_part; k++) { q[nb++] = (uint8_t)(int8_t)mv[part[k] * 2]; q[nb++] = (uint8_t)(int8_t)mv[part[k] * 2 + 1]; }
+                } else
+                    for (k = 0; k < n_part; k++) {
+                        const uint32_t v = (uint32_t)(uint16_t)mv[part[k] * 2] | ((uint32_t)(uint16_t)mv[part[k] * 2 + 1] << 16);
+                        memcpy(q + nb, &v, 4);
+                        nb += 4;
+                    }
+            }
+            if (compact && n_present) {
+                for (blk = 0; blk < 24; blk++) {
+                    uint8_t u[8];
+                    int n;
+                    if (!((mask >> blk) & 1u)) continue;
+                    n = h264r_writer_compact_unit(coeff + blk * 16, map[blk], u);
+                    memcpy(q + nb, u, (size_t)(2 + n));
+                    nb += 2 + n;
+                }
+            } else {
+                while (nb & 3) q[nb++] = 0;
+                for (blk = 0; blk < 24; blk++) {
+                    const int16_t* c = coeff + blk * 16;
+                    if (!((mask >> blk) & 1u)) continue;
+                    for (k = 0; k < 16; k++) q[nb++] = (uint8_t)(int8_t)c[k];
+                }
             }
             while (nb & 3) q[nb++] = 0;
             nw += nb >> 2;
-        } else
-            for (blk = 0; blk < 24; blk++) {
-                const int16_t* c = coeff + blk * 16;
-                uint8_t u[16];
-                if (!((mask >> blk) & 1u)) continue;
-                for (k = 0; k < 16; k++) u[k] = (uint8_t)(int8_t)c[k];
-                memcpy(&words[nw], u, 16);
-                nw += 4;
-            }
+        }
         if (nw > 255) return H264R_E_INVAL;
         if (w->n_units + (size_t)nw > b->max_stream_words) return H264R_E_CAPACITY;
         memcpy(s, words, (size_t)nw * 4);

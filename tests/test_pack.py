@@ -170,6 +170,12 @@ def unpack_stream(hdr8, mb_words, stream):
             mask[a] = stream[p]; p += 1
         if intra:
             hdr["u"].reshape(-1, 8)[a] = stream[p:p + 2].view(np.uint8); p += 2
+        # behind the words the macroblock is a byte run: short vectors, compact blocks; zero-padded to a word in front of int8 blocks
+        # and at the end
+        run = stream[p:].view(np.uint8)
+        q = 0
+        if intra:
+            pass
         elif inline:
             x = ((w1 >> 6) & 255) | (((w0 >> 9) & 15) << 8) | (((w1 >> 30) & 1) << 12)
             y = ((w1 >> 18) & 0xFFF) | ((w1 >> 31) << 12)
@@ -179,16 +185,15 @@ def unpack_stream(hdr8, mb_words, stream):
             hdr["u"].reshape(-1, 8)[a, 1:4] = hdr["u"].reshape(-1, 8)[a, 0]       # the reference index of a 16x16 macroblock, in all four quadrant fields
         else:
             sub = (w1 >> 6) & 255
-            cnt = {abi.MB_P16x16: 1, abi.MB_P16x8: 2, abi.MB_P8x16: 2}.get(cls, sum((1, 2, 2, 4)[(sub >> (2 * q)) & 3] for q in range(4)))
-            for i in range(cnt):
-                v = int(stream[p + i])
-                mvs.append((np.int16(np.uint16(v & 0xffff)), np.int16(np.uint16(v >> 16))))
-            p += cnt
+            cnt = {abi.MB_P16x16: 1, abi.MB_P16x8: 2, abi.MB_P8x16: 2}.get(cls, sum((1, 2, 2, 4)[(sub >> (2 * k)) & 3] for k in range(4)))
+            if (w1 >> 30) & 1:                                  # H264R_HDR8_MV_SHORT: int8 pairs
+                for i in range(cnt):
+                    mvs.append((int(run[q:q + 1].view(np.int8)[0]), int(run[q + 1:q + 2].view(np.int8)[0]))); q += 2
+            else:
+                for i in range(cnt):
+                    mvs.append(tuple(int(v) for v in run[q:q + 4].view(np.int16))); q += 4
         m = int(mask[a])
         if m & abi.BLK_COMPACT:
-            # a byte run: per block a 16-bit significance map and one byte per level, zero-padded to the next word
-            run = stream[p:].view(np.uint8)
-            q = 0
             for b in range(24):
                 if not (m >> b) & 1:
                     continue
@@ -197,12 +202,14 @@ def unpack_stream(hdr8, mb_words, stream):
                 unit = np.zeros(8, dtype=np.uint8)
                 unit[:2 + n] = run[q:q + 2 + n]
                 units.append(unit); q += 2 + n
-            assert not run[q:(q + 3) // 4 * 4].any(), "padding of macroblock %d is not zero" % a
-            p += (q + 3) // 4
-        else:
+        elif m & 0xFFFFFF:
+            assert not run[q:(q + 3) // 4 * 4].any(), "padding in front of the int8 blocks of macroblock %d is not zero" % a
+            q = (q + 3) // 4 * 4
             for b in range(24):
                 if (m >> b) & 1:
-                    units.append(stream[p:p + 2].view(np.uint8)); units.append(stream[p + 2:p + 4].view(np.uint8)); p += 4
+                    units.append(run[q:q + 8].copy()); units.append(run[q + 8:q + 16].copy()); q += 16
+        assert not run[q:(q + 3) // 4 * 4].any(), "padding of macroblock %d is not zero" % a
+        p += (q + 3) // 4
         assert p - wo == int(mb_words[a]), "macroblock %d: %d words walked, %d announced" % (a, p - wo, mb_words[a])
         wo = p
     return hdr, mask, (np.array(units, dtype=np.uint8).reshape(-1, 8)), np.array(mvs, dtype=np.int16).reshape(-1, 2), wo
@@ -226,6 +233,8 @@ def test_stream_form_c_writer_against_restatement(built):
         if mv is not None:      # a few vectors beyond the inline range
             big = np.flatnonzero(hdr["mb_class"] == abi.MB_P16x16)[:3]
             mv[big] = np.tile(np.array([5000, -4500], dtype=np.int16), 16)
+            small = np.flatnonzero(hdr["mb_class"] > abi.MB_P16x16)[::2]       # ... and every other partitioned macroblock within int8
+            mv[small] = np.clip(mv[small], -128, 127)
         c3 = coeff.reshape(n, 24, 16)
         if pi == 2:             # a macroblock with a dense block: plain int8 storage, four words per block
             a = int(np.flatnonzero(hdr["cbp"] & 1)[0])
@@ -270,6 +279,9 @@ def test_stream_form_c_writer_against_restatement(built):
             assert np.array_equal(got_mvs, want) and nm.value == want.shape[0]
             inl = (hdr8[:, 0] >> 31).astype(bool)
             assert inl.sum() == (hdr["mb_class"] == abi.MB_P16x16).sum() - 3
+            short = ((hdr8[:, 1] >> 30) & 1).astype(bool) & ~inl
+            multi = (hdr["mb_class"] > abi.MB_P16x16) & ~inl
+            assert short.any() and (multi & ~short).any(), "both vector widths must occur: %d short, %d long of %d" % (short.sum(), (multi & ~short).sum(), multi.sum())
         short_bytes = 8 * n + 4 * n + units.shape[0] * 8 + (0 if mv is None else 4 * pack.pack_mvs_partition(hdr, mv).shape[0]) + 8 * int(intra.sum())
         total_saved += short_bytes - (9 * n + 4 * used)
     assert total_saved > 0

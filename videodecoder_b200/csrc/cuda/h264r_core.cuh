@@ -271,26 +271,38 @@ HD uint32_t stream_expand_mb(uint2 s8, const uint32_t* p, uint32_t uo, uint32_t 
     // (a 16x16 macroblock's reference index stands in all four quadrant fields, as the packers write it)
     h.z = inl ? (r & 15u) * 0x01010101u : ((r & 15u) | (((r >> 4) & 15u) << 8) | (((r >> 8) & 15u) << 16) | (((r >> 12) & 15u) << 24));
     h.w = 0u;
+    // behind the words (mask, prediction modes) the macroblock is a byte run, padded to a word where int8 blocks begin and at its end
+    const uint8_t* q;
     if (intra) {
         h.z = H264R_LDG(p); h.w = H264R_LDG(p + 1);
-        p += 2;
+        q = reinterpret_cast<const uint8_t*>(p + 2);
     } else if (inl) {
         const uint32_t x = ((s8.y >> 6) & 255u) | (((s8.x >> 9) & 15u) << 8) | (((s8.y >> 30) & 1u) << 12);
         const uint32_t y = ((s8.y >> 18) & 0xFFFu) | ((s8.y >> 31) << 12);
         const int xs = (int)(x << 19) >> 19, ys = (int)(y << 19) >> 19;       // sign-extend 13 bits
         xmv_end[-1 - (ptrdiff_t)mo] = ((uint32_t)xs & 0xffffu) | ((uint32_t)ys << 16);
+        q = reinterpret_cast<const uint8_t*>(p);
     } else {
         const uint32_t nmv = (uint32_t)mv_count(cls, (int)((s8.y >> 6) & 255u));
-        for (uint32_t i = 0; i < nmv; i++) xmv_end[-1 - (ptrdiff_t)(mo + i)] = H264R_LDG(p + i);
-        p += nmv;
+        if (s8.y & H264R_HDR8_MV_SHORT) {
+            // int8 pairs
+            q = reinterpret_cast<const uint8_t*>(p);
+            for (uint32_t i = 0; i < nmv; i++) {
+                const int xs = (int8_t)H264R_LDG(q + 2 * i), ys = (int8_t)H264R_LDG(q + 2 * i + 1);
+                xmv_end[-1 - (ptrdiff_t)(mo + i)] = ((uint32_t)xs & 0xffffu) | ((uint32_t)ys << 16);
+            }
+            q += 2 * nmv;
+        } else {
+            for (uint32_t i = 0; i < nmv; i++) xmv_end[-1 - (ptrdiff_t)(mo + i)] = H264R_LDG(p + i);
+            q = reinterpret_cast<const uint8_t*>(p + nmv);
+        }
     }
     *hdr16 = h;
     *mask = mw;
     uint2* u = units + uo;
     if (mw & H264R_BLK_COMPACT) {
-        // a byte run: per block the 16-bit significance map and one byte per level (at most six); the unit the kernels read is the
-        // same bytes padded to eight
-        const uint8_t* q = reinterpret_cast<const uint8_t*>(p);
+        // per block the 16-bit significance map and one byte per level (at most six); the unit the kernels read is the same bytes
+        // padded to eight
         for (uint32_t m = mw & 0xFFFFFFu; m; m &= m - 1) {
             const uint32_t map = (uint32_t)H264R_LDG(q) | ((uint32_t)H264R_LDG(q + 1) << 8);
             const int n = popc32(map) < 6 ? popc32(map) : 6;
@@ -302,13 +314,16 @@ HD uint32_t stream_expand_mb(uint2 s8, const uint32_t* p, uint32_t uo, uint32_t 
             *u++ = uint2{lo, hi};
             q += 2 + n;
         }
-        p += (uint32_t)(q - reinterpret_cast<const uint8_t*>(p) + 3) >> 2;
-    } else
+    } else if (mw & 0xFFFFFFu) {
+        const uint32_t* pw = p0 + ((uint32_t)(q - reinterpret_cast<const uint8_t*>(p0)) + 3u) / 4u;
         for (uint32_t m = mw & 0xFFFFFFu; m; m &= m - 1) {
-            u[0] = uint2{H264R_LDG(p), H264R_LDG(p + 1)};
-            u[1] = uint2{H264R_LDG(p + 2), H264R_LDG(p + 3)};
-            u += 2; p += 4;
+            u[0] = uint2{H264R_LDG(pw), H264R_LDG(pw + 1)};
+            u[1] = uint2{H264R_LDG(pw + 2), H264R_LDG(pw + 3)};
+            u += 2; pw += 4;
         }
+        q = reinterpret_cast<const uint8_t*>(pw);
+    }
+    p = p0 + ((uint32_t)(q - reinterpret_cast<const uint8_t*>(p0)) + 3u) / 4u;
     return (uint32_t)(p - p0);          // words walked: mb_words[a] in a well-formed buffer
 }
 

@@ -220,6 +220,9 @@ def test_host_decoder_throughput_is_reported(built):
     g = load_stream_golden("spec_cif_ip")
     n, sec = hoststream.benchmark(g["stream"], repeat=2)
     assert n == 2 * g["n_pics"] and sec > 0
+    # ... and with every picture packed into the stream form of a picture buffer (what bench.py's host block reports beside it)
+    n2, sec2 = hoststream.benchmark(g["stream"], flags=hoststream.BENCH_PACK, repeat=2)
+    assert n2 == n and sec2 > 0
 
 
 @need_lavc

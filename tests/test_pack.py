@@ -301,3 +301,39 @@ def test_stream_expansion_of_garbage_stays_inside_its_areas(built):
         stream = rng.integers(0, 2 ** 32, size=n * 255 + 128, dtype=np.uint64).astype(np.uint32)
         dev = emul.stream_expand(hdr8, words, stream, 48 * n, 16 * n, strict=False, canary=0xC0FFEE)
         assert dev["words"] < 0          # and it is reported
+
+
+def wire_md5(n, p):
+    """MD5 over what travels for picture p in the stream form: 8-byte headers | word counts | stream words (+ the two counts the
+    submit call takes)"""
+    import ctypes, hashlib
+    from videodecoder_b200 import engine, hoststream
+    hdr = np.ascontiguousarray(p["hdr"]).view(abi.MB_HDR_DTYPE).reshape(-1).copy()
+    coeff = np.ascontiguousarray(p["coeff"], dtype=np.int16).copy()
+    mv = np.ascontiguousarray(p["mv"], dtype=np.int16).copy() if p["mv"] is not None else None
+    hdr8 = np.zeros((n, 2), dtype=np.uint32); words = np.zeros(n, dtype=np.uint8); stream = np.zeros(n * 120, dtype=np.uint32)
+    buf = engine.PictureBufStruct()
+    buf.hdr8 = hdr8.ctypes.data; buf.mb_words = words.ctypes.data; buf.stream = stream.ctypes.data
+    buf.max_stream_words = stream.size; buf.hdr_bytes = abi.HDR_STREAM
+    nb, nm = ctypes.c_size_t(0), ctypes.c_long(0)
+    rc = hoststream.lib().h264w_pack_arrays(ctypes.byref(buf), n, hdr.ctypes.data_as(ctypes.c_void_p), mv.ctypes.data_as(ctypes.c_void_p) if mv is not None else None,
+                                            coeff.ctypes.data_as(ctypes.c_void_p), abi.LEVELS_COMPACT, ctypes.byref(nb), ctypes.byref(nm))
+    if rc:
+        return "rc %d" % rc           # a picture with a level beyond int8: not in this form
+    h = hashlib.md5()
+    h.update(hdr8.tobytes()); h.update(words.tobytes()); h.update(stream[:nb.value].tobytes())
+    h.update(np.array([nb.value, nm.value], dtype=np.int64).tobytes())
+    return h.hexdigest()
+
+
+def test_wire_format_known_answer(built):
+    """the bytes of the stream form are a contract between a host that fills picture buffers and the device that expands them:
+    committed MD5s of the committed fixtures' pictures (tests/golden/make_wire_golden.py), tied to the ABI version"""
+    import json, os
+    from common import load_golden
+    kat = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stream_form_md5.json")))
+    assert kat["abi_version"] == abi.ABI_VERSION, "ABI version changed: regenerate tests/golden/stream_form_md5.json"
+    for name, want in kat["pictures"].items():
+        g = load_golden(name)
+        got = [wire_md5(g["w_mbs"] * g["h_mbs"], p) for p in g["pics"]]
+        assert got == want, name

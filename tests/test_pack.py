@@ -337,3 +337,36 @@ def test_wire_format_known_answer(built):
         g = load_golden(name)
         got = [wire_md5(g["w_mbs"] * g["h_mbs"], p) for p in g["pics"]]
         assert got == want, name
+
+
+def test_stream_form_of_empty_macroblocks(built):
+    """edge cases of the stream form: an all-skip P picture is its headers and nothing else (every vector inline, zero stream words),
+    an Intra16x16 picture without levels still carries a mask word and its prediction modes per macroblock -- through the C writer
+    and the expansion functions the kernels call"""
+    import ctypes
+    from videodecoder_b200 import engine, hoststream
+    n = 12
+    for intra in (False, True):
+        hdr = np.zeros(n, dtype=abi.MB_HDR_DTYPE)
+        hdr["mb_class"] = abi.MB_I16x16 if intra else abi.MB_P16x16
+        hdr["qp_y"] = 30; hdr["qp_cb"] = 29; hdr["qp_cr"] = 29
+        hdr["intra_modes"] = 2 if intra else 0
+        coeff = np.zeros((n, 384), dtype=np.int16)
+        mv = None if intra else np.tile(np.array([3, -7], dtype=np.int16), (n, 16))
+        hdr8 = np.zeros((n, 2), dtype=np.uint32); words = np.zeros(n, dtype=np.uint8); stream = np.zeros(n * 120, dtype=np.uint32)
+        buf = engine.PictureBufStruct()
+        buf.hdr8 = hdr8.ctypes.data; buf.mb_words = words.ctypes.data; buf.stream = stream.ctypes.data
+        buf.max_stream_words = stream.size; buf.hdr_bytes = abi.HDR_STREAM
+        nb, nm = ctypes.c_size_t(0), ctypes.c_long(0)
+        rc = hoststream.lib().h264w_pack_arrays(ctypes.byref(buf), n, hdr.ctypes.data_as(ctypes.c_void_p), mv.ctypes.data_as(ctypes.c_void_p) if mv is not None else None,
+                                                coeff.ctypes.data_as(ctypes.c_void_p), abi.LEVELS_COMPACT, ctypes.byref(nb), ctypes.byref(nm))
+        assert rc == 0
+        assert nb.value == (3 * n if intra else 0) and nm.value == (0 if intra else n)
+        dev = emul.stream_expand(hdr8, words, stream, 4, 16 * n, canary=0xABCD)
+        assert dev["words"] == nb.value and dev["units"].shape[0] == 0 and not dev["mask"].any()
+        assert np.array_equal(dev["hdr"]["mb_class"], hdr["mb_class"]) and np.array_equal(dev["hdr"]["qp_y"], hdr["qp_y"])
+        if intra:
+            assert np.array_equal(dev["intra_list"], np.arange(n)) and np.array_equal(dev["hdr"]["intra_modes"], hdr["intra_modes"])
+        else:
+            assert dev["intra_list"].size == 0 and np.array_equal(dev["mvs"], np.tile(np.array([3, -7], dtype=np.int16), (n, 1)))
+            assert ((hdr8[:, 0] >> 31) == 1).all()
